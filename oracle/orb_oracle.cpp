@@ -1,0 +1,948 @@
+// orb_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// An OpenCV-free C++ restatement of the reference's ORB extraction / Hamming matching hot path
+// (OpenMAVIS, an ORB-SLAM3 fork; all file:line cites are relative to /root/reference).  It exists to
+// CHECK the CUDA product in tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs.  Nothing under openmavis_b200/ may include, link or call it.
+//
+// Parity status: the reference ships no golden vectors for this path, and its own
+// sources cannot be compiled here (no OpenCV/Eigen/Sophus headers).  The oracle is therefore pinned
+// primitive by primitive against the reference's third-party dependency itself — OpenCV, through the
+// cv2 4.13.0 wheel in this image (tests/test_oracle_vs_cv2.py: resize, copyMakeBorder, FAST, GaussianBlur,
+// fastAtan2, BFMatcher.knnMatch) — and against committed fixtures generated from cv2
+// (tests/golden/, tools/gen_golden.py).  The glue between primitives (cell grid, quadtree
+// distribution, orientation, rBRIEF, lapping-area partition, matcher bookkeeping) follows the
+// reference line by line and is additionally checked by an independent Python/cv2 restatement.
+//
+// Build: oracle/Makefile  (g++ -O3 -march=native -ffp-contract=off, mirrors CMakeLists.txt:13-16
+// except that contraction is off; the FMA behaviour of GET_VALUE is an explicit switch, see below).
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <list>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "../include/orbx_pattern.h"
+
+namespace {
+
+const int kPatchSize = 31;       // ORBextractor.cc:15
+const int kHalfPatch = 15;       // ORBextractor.cc:16
+const int kEdge = 19;            // ORBextractor.cc:17 (EDGE_THRESHOLD)
+const signed char kPattern[1024] = {ORBX_PATTERN_VALUES};
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }   // cvRound(float): cvtss2si, half-to-even
+inline int cv_round_d(double v) { return (int)lrint(v); }   // cvRound(double)
+
+struct KeyPt {   // mirrors cv::KeyPoint field for field
+    float x, y, size, angle, response;
+    int octave, class_id;
+};
+
+// ----------------------------------------------------------------------------------------------
+// Per-level tables.  ORBextractor.cc:351-414.
+// ----------------------------------------------------------------------------------------------
+struct Params {
+    int nfeatures, nlevels, iniTh, minTh;
+    double scaleFactor;   // double member holding the float argument (ORBextractor.h:70)
+    std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
+    std::vector<int> nfeat;
+    int umax[kHalfPatch + 1];
+};
+
+void make_params(Params &p, int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
+    p.nfeatures = nfeatures; p.nlevels = nlevels; p.iniTh = iniTh; p.minTh = minTh;
+    p.scaleFactor = scaleFactor;
+    p.sf.assign(nlevels, 1.0f); p.sigma2.assign(nlevels, 1.0f);
+    for (int i = 1; i < nlevels; i++) {
+        p.sf[i] = (float)(p.sf[i - 1] * p.scaleFactor);          // :366
+        p.sigma2[i] = p.sf[i] * p.sf[i];                         // :367
+    }
+    p.inv_sf.resize(nlevels); p.inv_sigma2.resize(nlevels);
+    for (int i = 0; i < nlevels; i++) {
+        p.inv_sf[i] = 1.0f / p.sf[i];
+        p.inv_sigma2[i] = 1.0f / p.sigma2[i];
+    }
+    p.nfeat.assign(nlevels, 0);
+    float factor = (float)(1.0f / p.scaleFactor);                // :380
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        p.nfeat[l] = cv_round_f(nDesired);
+        sum += p.nfeat[l];
+        nDesired *= factor;
+    }
+    p.nfeat[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // umax: :399-413
+    int v, v0;
+    int vmax = (int)floorf(kHalfPatch * sqrtf(2.f) / 2 + 1);
+    int vmin = (int)ceilf(kHalfPatch * sqrtf(2.f) / 2);
+    const double hp2 = kHalfPatch * kHalfPatch;
+    for (v = 0; v <= kHalfPatch; v++) p.umax[v] = 0;
+    for (v = 0; v <= vmax; ++v) p.umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+        while (p.umax[v0] == p.umax[v0 + 1]) ++v0;
+        p.umax[v] = v0;
+        ++v0;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// cv::resize(INTER_LINEAR) for CV_8UC1 — fixed-point restatement (OpenCV imgproc/resize.cpp,
+// HResizeLinear / VResizeLinear with INTER_RESIZE_COEF_BITS = 11).  Called at ORBextractor.cc:1083.
+// ----------------------------------------------------------------------------------------------
+void linear_taps(int src, int dst, std::vector<int> &ofs, std::vector<short> &c0, std::vector<short> &c1) {
+    ofs.resize(dst); c0.resize(dst); c1.resize(dst);
+    double inv_scale = (double)dst / src;
+    double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dst; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        if (s < 0) { f = 0; s = 0; }
+        if (s >= src - 1) { f = 0; s = src - 1; }
+        ofs[d] = s;
+        c0[d] = (short)cv_round_f((1.f - f) * 2048.f);
+        c1[d] = (short)cv_round_f(f * 2048.f);
+    }
+}
+
+void resize_linear(const uint8_t *src, int sw, int sh, int sstride, uint8_t *dst, int dw, int dh, int dstride) {
+    std::vector<int> xo, yo; std::vector<short> a0, a1, b0, b1;
+    linear_taps(sw, dw, xo, a0, a1);
+    linear_taps(sh, dh, yo, b0, b1);
+    std::vector<int> r0(dw), r1(dw);
+    for (int y = 0; y < dh; y++) {
+        int sy0 = yo[y], sy1 = std::min(sy0 + 1, sh - 1);
+        const uint8_t *S0 = src + (size_t)sy0 * sstride, *S1 = src + (size_t)sy1 * sstride;
+        for (int x = 0; x < dw; x++) {
+            int sx0 = xo[x], sx1 = std::min(sx0 + 1, sw - 1);
+            r0[x] = S0[sx0] * a0[x] + S0[sx1] * a1[x];
+            r1[x] = S1[sx0] * a0[x] + S1[sx1] * a1[x];
+        }
+        uint8_t *D = dst + (size_t)y * dstride;
+        for (int x = 0; x < dw; x++)
+            D[x] = (uint8_t)((((b0[y] * (r0[x] >> 4)) >> 16) + ((b1[y] * (r1[x] >> 4)) >> 16) + 2) >> 2);
+    }
+}
+
+// cv::copyMakeBorder(BORDER_REFLECT_101) around a w x h interior that already sits at (b,b) of buf.
+inline int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) { if (i < 0) i = -i; else i = 2 * (n - 1) - i; }
+    return i;
+}
+void fill_border_reflect101(uint8_t *buf, int w, int h, int stride, int b) {
+    uint8_t *in = buf + (size_t)b * stride + b;
+    for (int y = 0; y < h; y++) {
+        uint8_t *row = in + (size_t)y * stride;
+        for (int k = 1; k <= b; k++) { row[-k] = row[reflect101(-k, w)]; row[w - 1 + k] = row[reflect101(w - 1 + k, w)]; }
+    }
+    for (int k = 1; k <= b; k++) {
+        memcpy(buf + (size_t)(b - k) * stride, buf + (size_t)(b + reflect101(-k, h)) * stride, w + 2 * b);
+        memcpy(buf + (size_t)(b + h - 1 + k) * stride, buf + (size_t)(b + reflect101(h - 1 + k, h)) * stride, w + 2 * b);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// cv::FAST(img, kps, threshold, nonmaxSuppression=true)  (TYPE_9_16) — restatement of OpenCV
+// features2d/fast.cpp FAST_t<16> + fast_score.cpp cornerScore<16>.  Called at ORBextractor.cc:745,765.
+// ----------------------------------------------------------------------------------------------
+const int kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+const int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+int corner_score16(const uint8_t *p, const int *off, int threshold) {
+    const int K = 8, N = K * 3 + 1;
+    int v = p[0];
+    short d[N];
+    for (int k = 0; k < N; k++) d[k] = (short)(v - p[off[k]]);
+    int a0 = threshold;
+    for (int k = 0; k < 16; k += 2) {
+        int a = std::min((int)d[k + 1], (int)d[k + 2]);
+        a = std::min(a, (int)d[k + 3]);
+        if (a <= a0) continue;
+        a = std::min(a, (int)d[k + 4]); a = std::min(a, (int)d[k + 5]);
+        a = std::min(a, (int)d[k + 6]); a = std::min(a, (int)d[k + 7]);
+        a = std::min(a, (int)d[k + 8]);
+        a0 = std::max(a0, std::min(a, (int)d[k]));
+        a0 = std::max(a0, std::min(a, (int)d[k + 9]));
+    }
+    int b0 = -a0;
+    for (int k = 0; k < 16; k += 2) {
+        int b = std::max((int)d[k + 1], (int)d[k + 2]);
+        b = std::max(b, (int)d[k + 3]); b = std::max(b, (int)d[k + 4]);
+        b = std::max(b, (int)d[k + 5]);
+        if (b >= b0) continue;
+        b = std::max(b, (int)d[k + 6]); b = std::max(b, (int)d[k + 7]);
+        b = std::max(b, (int)d[k + 8]);
+        b0 = std::min(b0, std::max(b, (int)d[k]));
+        b0 = std::min(b0, std::max(b, (int)d[k + 9]));
+    }
+    return -b0 - 1;
+}
+
+struct FastPt { int x, y, score; };
+
+void fast9_16(const uint8_t *img, int w, int h, int stride, int threshold, std::vector<FastPt> &out) {
+    out.clear();
+    if (w < 7 || h < 7) return;
+    threshold = std::min(std::max(threshold, 0), 255);
+    int off[25];
+    for (int k = 0; k < 25; k++) off[k] = kRingDy[k % 16] * stride + kRingDx[k % 16];
+    std::vector<uint8_t> sbuf((size_t)3 * w, 0);
+    std::vector<int> cbuf((size_t)3 * (w + 1), 0);
+    uint8_t *buf[3] = {sbuf.data(), sbuf.data() + w, sbuf.data() + 2 * w};
+    int *cp[3] = {cbuf.data(), cbuf.data() + (w + 1), cbuf.data() + 2 * (w + 1)};
+    for (int i = 3; i < h - 2; i++) {
+        const uint8_t *ptr = img + (size_t)i * stride + 3;
+        uint8_t *curr = buf[(i - 3) % 3];
+        int *cornerpos = cp[(i - 3) % 3] + 1;
+        memset(curr, 0, w);
+        int ncorners = 0;
+        if (i < h - 3) {
+            for (int j = 3; j < w - 3; j++, ptr++) {
+                int v = ptr[0];
+                int lo = v - threshold, hi = v + threshold;
+                // >= 9 contiguous ring pixels all darker than v-t, or all brighter than v+t
+                bool corner = false;
+                int count = 0;
+                for (int k = 0; k < 25; k++) {
+                    if (ptr[off[k]] < lo) { if (++count > 8) { corner = true; break; } } else count = 0;
+                }
+                if (!corner) {
+                    count = 0;
+                    for (int k = 0; k < 25; k++) {
+                        if (ptr[off[k]] > hi) { if (++count > 8) { corner = true; break; } } else count = 0;
+                    }
+                }
+                if (corner) {
+                    cornerpos[ncorners++] = j;
+                    curr[j] = (uint8_t)corner_score16(ptr, off, threshold);
+                }
+            }
+        }
+        cornerpos[-1] = ncorners;
+        if (i == 3) continue;
+        const uint8_t *prev = buf[(i - 4 + 3) % 3];
+        const uint8_t *pprev = buf[(i - 5 + 3) % 3];
+        cornerpos = cp[(i - 4 + 3) % 3] + 1;
+        ncorners = cornerpos[-1];
+        for (int k = 0; k < ncorners; k++) {
+            int j = cornerpos[k];
+            int score = prev[j];
+            if (score > prev[j + 1] && score > prev[j - 1] && score > pprev[j - 1] && score > pprev[j] &&
+                score > pprev[j + 1] && score > curr[j - 1] && score > curr[j] && score > curr[j + 1])
+                out.push_back({j, i - 1, score});
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) for CV_8U — OpenCV's fixed-point (Q8.8) path:
+// kernel {18,34,48,56,48,34,18}/256, horizontal u8->u16, vertical u16->u32, (v + 2^15) >> 16.
+// Called at ORBextractor.cc:1036 on a borderless clone.
+// ----------------------------------------------------------------------------------------------
+const int kBlurK[7] = {18, 34, 48, 56, 48, 34, 18};
+void blur7(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride) {
+    std::vector<uint16_t> tmp((size_t)w * h);
+    for (int y = 0; y < h; y++) {
+        const uint8_t *S = src + (size_t)y * sstride;
+        for (int x = 0; x < w; x++) {
+            int acc = 0;
+            for (int k = 0; k < 7; k++) acc += kBlurK[k] * S[reflect101(x + k - 3, w)];
+            tmp[(size_t)y * w + x] = (uint16_t)acc;
+        }
+    }
+    for (int y = 0; y < h; y++) {
+        const uint16_t *R[7];
+        for (int k = 0; k < 7; k++) R[k] = tmp.data() + (size_t)reflect101(y + k - 3, h) * w;
+        uint8_t *D = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++) {
+            uint32_t acc = 0;
+            for (int k = 0; k < 7; k++) acc += (uint32_t)kBlurK[k] * R[k][x];
+            D[x] = (uint8_t)((acc + 32768u) >> 16);
+        }
+    }
+}
+
+// cv::fastAtan2(y, x) in degrees — OpenCV core/mathfuncs_core (scalar atan_f32), each op fp32-rounded.
+float fast_atan2(float y, float x) {
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s;
+    const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float eps = (float)2.2204460492503131e-16;
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + eps); c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + eps); c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// IC_Angle.  ORBextractor.cc:19-43.
+float ic_angle(const uint8_t *img, int stride, int x, int y, const int *umax) {
+    int m01 = 0, m10 = 0;
+    const uint8_t *c = img + (size_t)y * stride + x;
+    for (int u = -kHalfPatch; u <= kHalfPatch; ++u) m10 += u * c[u];
+    for (int v = 1; v <= kHalfPatch; ++v) {
+        int vsum = 0, d = umax[v];
+        for (int u = -d; u <= d; ++u) {
+            int vp = c[u + v * stride], vm = c[u - v * stride];
+            vsum += (vp - vm);
+            m10 += u * (vp + vm);
+        }
+        m01 += v * vsum;
+    }
+    return fast_atan2((float)m01, (float)m10);
+}
+
+// computeOrbDescriptor.  ORBextractor.cc:46-90.  fma_mode 0: every op rounded separately;
+// fma_mode 1: GET_VALUE contracted the way g++ -O3 -march=<fma cpu> does it
+// (fma(px, b, py*a), fma(px, a, -(py*b))) — SURVEY.md §8c "oracle definition".
+void orb_descriptor(const uint8_t *img, int stride, int x, int y, float angle_deg, int fma_mode, uint8_t *desc) {
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    float angle = angle_deg * factorPI;
+    float a = (float)cosf(angle), b = (float)sinf(angle);
+    const uint8_t *c = img + (size_t)y * stride + x;
+    for (int i = 0; i < 32; i++) {
+        int val = 0;
+        for (int k = 0; k < 8; k++) {
+            int t[2];
+            for (int e = 0; e < 2; e++) {
+                float px = kPattern[(i * 16 + 2 * k + e) * 2], py = kPattern[(i * 16 + 2 * k + e) * 2 + 1];
+                float fy, fx;
+                if (fma_mode) { fy = fmaf(px, b, py * a); fx = fmaf(px, a, -(py * b)); }
+                else { fy = px * b + py * a; fx = px * a - py * b; }
+                t[e] = c[cv_round_f(fy) * stride + cv_round_f(fx)];
+            }
+            val |= (t[0] < t[1]) << k;
+        }
+        desc[i] = (uint8_t)val;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// DistributeOctTree.  ORBextractor.cc:425-702 — std::list / std::sort faithful restatement.
+// Keys are indices into the candidate array (the reference copies KeyPoints; order is what matters).
+// ----------------------------------------------------------------------------------------------
+struct Node {
+    std::vector<int> keys;
+    int ulx, uly, urx, ury, blx, bly, brx, bry;
+    std::list<Node>::iterator lit;
+    bool noMore = false;
+};
+
+void divide_node(const Node &n, const std::vector<FastPt> &pts, Node &n1, Node &n2, Node &n3, Node &n4) {
+    const int halfX = (int)ceilf((float)(n.urx - n.ulx) / 2);
+    const int halfY = (int)ceilf((float)(n.bry - n.uly) / 2);
+    n1.ulx = n.ulx; n1.uly = n.uly; n1.urx = n.ulx + halfX; n1.ury = n.uly;
+    n1.blx = n.ulx; n1.bly = n.uly + halfY; n1.brx = n.ulx + halfX; n1.bry = n.uly + halfY;
+    n2.ulx = n1.urx; n2.uly = n1.ury; n2.urx = n.urx; n2.ury = n.ury;
+    n2.blx = n1.brx; n2.bly = n1.bry; n2.brx = n.urx; n2.bry = n.uly + halfY;
+    n3.ulx = n1.blx; n3.uly = n1.bly; n3.urx = n1.brx; n3.ury = n1.bry;
+    n3.blx = n.blx; n3.bly = n.bly; n3.brx = n1.brx; n3.bry = n.bly;
+    n4.ulx = n3.urx; n4.uly = n3.ury; n4.urx = n2.brx; n4.ury = n2.bry;
+    n4.blx = n3.brx; n4.bly = n3.bry; n4.brx = n.brx; n4.bry = n.bry;
+    for (int k : n.keys) {
+        float px = (float)pts[k].x, py = (float)pts[k].y;
+        if (px < n1.urx) { if (py < n1.bry) n1.keys.push_back(k); else n3.keys.push_back(k); }
+        else if (py < n1.bry) n2.keys.push_back(k);
+        else n4.keys.push_back(k);
+    }
+    if (n1.keys.size() == 1) n1.noMore = true;
+    if (n2.keys.size() == 1) n2.noMore = true;
+    if (n3.keys.size() == 1) n3.noMore = true;
+    if (n4.keys.size() == 1) n4.noMore = true;
+}
+
+bool compare_nodes(std::pair<int, Node *> &e1, std::pair<int, Node *> &e2) {   // :482-494
+    if (e1.first < e2.first) return true;
+    if (e1.first > e2.first) return false;
+    return e1.second->ulx < e2.second->ulx;
+}
+
+// returns the selected candidate indices, in std::list order
+void distribute_octtree(const std::vector<FastPt> &pts, int minX, int maxX, int minY, int maxY, int N,
+                        std::vector<int> &result) {
+    result.clear();
+    const int nIni = (int)roundf((float)(maxX - minX) / (maxY - minY));
+    const float hX = (float)(maxX - minX) / nIni;
+    std::list<Node> nodes;
+    std::vector<Node *> ini(nIni);
+    for (int i = 0; i < nIni; i++) {
+        Node ni;
+        ni.ulx = (int)(hX * (float)i); ni.uly = 0;
+        ni.urx = (int)(hX * (float)(i + 1)); ni.ury = 0;
+        ni.blx = ni.ulx; ni.bly = maxY - minY;
+        ni.brx = ni.urx; ni.bry = maxY - minY;
+        nodes.push_back(ni);
+        ini[i] = &nodes.back();
+    }
+    for (size_t i = 0; i < pts.size(); i++) ini[(size_t)((float)pts[i].x / hX)]->keys.push_back((int)i);
+    auto lit = nodes.begin();
+    while (lit != nodes.end()) {
+        if (lit->keys.size() == 1) { lit->noMore = true; lit++; }
+        else if (lit->keys.empty()) lit = nodes.erase(lit);
+        else lit++;
+    }
+    bool finish = false;
+    std::vector<std::pair<int, Node *>> sizeAndNode;
+    auto push_children = [&](Node *ch[4], int *nToExpand) {
+        for (int c = 0; c < 4; c++) {
+            if (ch[c]->keys.size() > 0) {
+                nodes.push_front(*ch[c]);
+                if (ch[c]->keys.size() > 1) {
+                    if (nToExpand) (*nToExpand)++;
+                    sizeAndNode.push_back(std::make_pair((int)ch[c]->keys.size(), &nodes.front()));
+                    nodes.front().lit = nodes.begin();
+                }
+            }
+        }
+    };
+    while (!finish) {
+        int prevSize = (int)nodes.size();
+        lit = nodes.begin();
+        int nToExpand = 0;
+        sizeAndNode.clear();
+        while (lit != nodes.end()) {
+            if (lit->noMore) { lit++; continue; }
+            Node n1, n2, n3, n4; Node *ch[4] = {&n1, &n2, &n3, &n4};
+            divide_node(*lit, pts, n1, n2, n3, n4);
+            push_children(ch, &nToExpand);
+            lit = nodes.erase(lit);
+        }
+        if ((int)nodes.size() >= N || (int)nodes.size() == prevSize) {
+            finish = true;
+        } else if (((int)nodes.size() + nToExpand * 3) > N) {
+            while (!finish) {
+                prevSize = (int)nodes.size();
+                std::vector<std::pair<int, Node *>> prev = sizeAndNode;
+                sizeAndNode.clear();
+                std::sort(prev.begin(), prev.end(), compare_nodes);
+                for (int j = (int)prev.size() - 1; j >= 0; j--) {
+                    Node n1, n2, n3, n4; Node *ch[4] = {&n1, &n2, &n3, &n4};
+                    divide_node(*prev[j].second, pts, n1, n2, n3, n4);
+                    push_children(ch, nullptr);
+                    nodes.erase(prev[j].second->lit);
+                    if ((int)nodes.size() >= N) break;
+                }
+                if ((int)nodes.size() >= N || (int)nodes.size() == prevSize) finish = true;
+            }
+        }
+    }
+    for (auto &n : nodes) {   // :683-699 — first strictly-greatest response
+        int best = n.keys[0];
+        float maxResp = (float)pts[best].score;
+        for (size_t k = 1; k < n.keys.size(); k++)
+            if ((float)pts[n.keys[k]].score > maxResp) { best = n.keys[k]; maxResp = (float)pts[best].score; }
+        result.push_back(best);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// The extractor object: ComputePyramid (:1073-1104), ComputeKeyPointsOctTree (:704-823),
+// operator() (:987-1071).  Keeps every stage's output so tests can compare stage by stage.
+// ----------------------------------------------------------------------------------------------
+struct Level {
+    int w = 0, h = 0, stride = 0;        // interior size, bordered-buffer stride
+    std::vector<uint8_t> buf;            // (h+38) x stride, interior at (19,19)
+    std::vector<uint8_t> blur;           // w x h borderless (only when the level has keypoints)
+    std::vector<FastPt> cand;            // vToDistributeKeys (border-relative coords)
+    std::vector<KeyPt> kps;              // after DistributeOctTree + orientation (level coords)
+    bool blurred = false;
+};
+
+struct Extractor {
+    Params p;
+    std::vector<Level> lv;
+    std::vector<KeyPt> out_kps;
+    std::vector<uint8_t> out_desc;
+    int n_mono = 0;
+    double t_stage[6] = {0, 0, 0, 0, 0, 0};   // pyramid, fast, octree, angle, blur, desc+epilogue (s)
+};
+
+double now_s() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+void compute_pyramid(Extractor &E, const uint8_t *img, int w, int h, int stride) {
+    E.lv.assign(E.p.nlevels, Level());
+    for (int l = 0; l < E.p.nlevels; l++) {
+        Level &L = E.lv[l];
+        float scale = E.p.inv_sf[l];
+        L.w = cv_round_f((float)w * scale); L.h = cv_round_f((float)h * scale);
+        L.stride = L.w + 2 * kEdge;
+        L.buf.assign((size_t)L.stride * (L.h + 2 * kEdge), 0);
+        uint8_t *in = L.buf.data() + (size_t)kEdge * L.stride + kEdge;
+        if (l == 0) for (int y = 0; y < h; y++) memcpy(in + (size_t)y * L.stride, img + (size_t)y * stride, w);
+        else {
+            Level &P = E.lv[l - 1];
+            resize_linear(P.buf.data() + (size_t)kEdge * P.stride + kEdge, P.w, P.h, P.stride, in, L.w, L.h, L.stride);
+        }
+        fill_border_reflect101(L.buf.data(), L.w, L.h, L.stride, kEdge);
+    }
+}
+
+void detect_level(Extractor &E, int l) {
+    Level &L = E.lv[l];
+    const uint8_t *in = L.buf.data() + (size_t)kEdge * L.stride + kEdge;
+    const int minBX = kEdge - 3, minBY = minBX;
+    const int maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
+    const float W = 35;
+    const float width = (float)(maxBX - minBX), height = (float)(maxBY - minBY);
+    const int nCols = (int)(width / W), nRows = (int)(height / W);
+    L.cand.clear();
+    if (nCols <= 0 || nRows <= 0) return;   // reference would divide by zero; defined as "no cells"
+    const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
+    std::vector<FastPt> cell;
+    for (int i = 0; i < nRows; i++) {
+        const float iniY = (float)(minBY + i * hCell);
+        float maxY = iniY + hCell + 6;
+        if (iniY >= maxBY - 3) continue;
+        if (maxY > maxBY) maxY = (float)maxBY;
+        for (int j = 0; j < nCols; j++) {
+            const float iniX = (float)(minBX + j * wCell);
+            float maxX = iniX + wCell + 6;
+            if (iniX >= maxBX - 6) continue;
+            if (maxX > maxBX) maxX = (float)maxBX;
+            int x0 = (int)iniX, y0 = (int)iniY, cw = (int)maxX - x0, chh = (int)maxY - y0;
+            const uint8_t *roi = in + (size_t)y0 * L.stride + x0;
+            fast9_16(roi, cw, chh, L.stride, E.p.iniTh, cell);
+            if (cell.empty()) fast9_16(roi, cw, chh, L.stride, E.p.minTh, cell);
+            for (auto &k : cell) L.cand.push_back({k.x + j * wCell, k.y + i * hCell, k.score});
+        }
+    }
+}
+
+void select_level(Extractor &E, int l) {
+    Level &L = E.lv[l];
+    const int minBX = kEdge - 3, minBY = minBX;
+    const int maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
+    std::vector<int> sel;
+    L.kps.clear();
+    if (L.cand.empty()) return;   // reference: DistributeOctTree on an empty set returns nothing
+    distribute_octtree(L.cand, minBX, maxBX, minBY, maxBY, E.p.nfeat[l], sel);
+    const int scaledPatch = (int)(kPatchSize * E.p.sf[l]);
+    for (int k : sel) {
+        KeyPt kp;
+        kp.x = (float)L.cand[k].x + minBX; kp.y = (float)L.cand[k].y + minBY;
+        kp.size = (float)scaledPatch; kp.angle = -1; kp.response = (float)L.cand[k].score;
+        kp.octave = l; kp.class_id = -1;
+        L.kps.push_back(kp);
+    }
+}
+
+int extract(Extractor &E, const uint8_t *img, int w, int h, int stride, int lap0, int lap1, int fma_mode) {
+    E.out_kps.clear(); E.out_desc.clear(); E.n_mono = 0;
+    if (!img || w <= 0 || h <= 0) return -1;   // :994-995
+    double t0 = now_s();
+    compute_pyramid(E, img, w, h, stride);
+    double t1 = now_s();
+    for (int l = 0; l < E.p.nlevels; l++) detect_level(E, l);
+    double t2 = now_s();
+    for (int l = 0; l < E.p.nlevels; l++) select_level(E, l);
+    double t3 = now_s();
+    for (int l = 0; l < E.p.nlevels; l++) {
+        Level &L = E.lv[l];
+        const uint8_t *in = L.buf.data() + (size_t)kEdge * L.stride + kEdge;
+        for (auto &kp : L.kps) kp.angle = ic_angle(in, L.stride, cv_round_f(kp.x), cv_round_f(kp.y), E.p.umax);
+    }
+    double t4 = now_s();
+    int n = 0;
+    for (auto &L : E.lv) n += (int)L.kps.size();
+    E.out_kps.assign(n, KeyPt());
+    E.out_desc.assign((size_t)n * 32, 0);
+    int mono = 0, stereo = n - 1;
+    double tb = 0;
+    for (int l = 0; l < E.p.nlevels; l++) {
+        Level &L = E.lv[l];
+        if (L.kps.empty()) continue;
+        double tb0 = now_s();
+        L.blur.assign((size_t)L.w * L.h, 0);
+        blur7(L.buf.data() + (size_t)kEdge * L.stride + kEdge, L.w, L.h, L.stride, L.blur.data(), L.w);
+        L.blurred = true;
+        tb += now_s() - tb0;
+        float scale = E.p.sf[l];
+        for (auto &kp0 : L.kps) {
+            uint8_t d[32];
+            orb_descriptor(L.blur.data(), L.w, cv_round_f(kp0.x), cv_round_f(kp0.y), kp0.angle, fma_mode, d);
+            KeyPt kp = kp0;
+            if (l != 0) { kp.x *= scale; kp.y *= scale; }
+            int slot;
+            if (kp.x >= lap0 && kp.x <= lap1) slot = stereo--; else slot = mono++;
+            E.out_kps[slot] = kp;
+            memcpy(&E.out_desc[(size_t)slot * 32], d, 32);
+        }
+    }
+    double t5 = now_s();
+    E.n_mono = mono;
+    E.t_stage[0] += t1 - t0; E.t_stage[1] += t2 - t1; E.t_stage[2] += t3 - t2;
+    E.t_stage[3] += t4 - t3; E.t_stage[4] += tb; E.t_stage[5] += (t5 - t4) - tb;
+    return mono;
+}
+
+// ORBmatcher::DescriptorDistance.  ORBmatcher.cc:2577-2591 (bit-twiddling popcount over 8 x u32).
+int descriptor_distance(const uint8_t *a, const uint8_t *b) {
+    int32_t pa[8], pb[8];
+    memcpy(pa, a, 32); memcpy(pb, b, 32);
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        unsigned int v = pa[i] ^ pb[i];
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+// Frame grid.  Frame.h:24-25, Frame.cc:541-582 (AssignFeaturesToGrid), 969-978 (PosInGrid),
+// 890-967 (GetFeaturesInArea).  One grid per camera, camera-local indices.
+const int kGridCols = 64, kGridRows = 48;
+struct Grid {
+    float minX, minY, invW, invH;
+    std::vector<int> cell[kGridCols][kGridRows];
+};
+void grid_build(Grid &g, const KeyPt *kps, int n, float minX, float maxX, float minY, float maxY) {
+    g.minX = minX; g.minY = minY;
+    g.invW = (float)kGridCols / (maxX - minX);
+    g.invH = (float)kGridRows / (maxY - minY);
+    for (int i = 0; i < kGridCols; i++) for (int j = 0; j < kGridRows; j++) g.cell[i][j].clear();
+    for (int i = 0; i < n; i++) {
+        int px = (int)roundf((kps[i].x - minX) * g.invW);
+        int py = (int)roundf((kps[i].y - minY) * g.invH);
+        if (px < 0 || px >= kGridCols || py < 0 || py >= kGridRows) continue;
+        g.cell[px][py].push_back(i);
+    }
+}
+void features_in_area(const Grid &g, const KeyPt *kps, float x, float y, float r, int minLevel, int maxLevel,
+                      std::vector<int> &out) {
+    out.clear();
+    const int c0 = std::max(0, (int)floorf((x - g.minX - r) * g.invW));
+    if (c0 >= kGridCols) return;
+    const int c1 = std::min(kGridCols - 1, (int)ceilf((x - g.minX + r) * g.invW));
+    if (c1 < 0) return;
+    const int r0 = std::max(0, (int)floorf((y - g.minY - r) * g.invH));
+    if (r0 >= kGridRows) return;
+    const int r1 = std::min(kGridRows - 1, (int)ceilf((y - g.minY + r) * g.invH));
+    if (r1 < 0) return;
+    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = c0; ix <= c1; ix++)
+        for (int iy = r0; iy <= r1; iy++)
+            for (int idx : g.cell[ix][iy]) {
+                const KeyPt &kp = kps[idx];
+                if (checkLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                if (fabsf(kp.x - x) < r && fabsf(kp.y - y) < r) out.push_back(idx);
+            }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C interface (ctypes).  Everything is prefixed orc_ ("oracle").
+// ================================================================================================
+extern "C" {
+
+struct orc_kp { float x, y, size, angle, response; int octave, class_id; };
+
+void *orc_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
+    Extractor *E = new Extractor();
+    make_params(E->p, nfeatures, scaleFactor, nlevels, iniTh, minTh);
+    return E;
+}
+void orc_destroy(void *h) { delete (Extractor *)h; }
+
+void orc_tables(void *h, float *sf, float *inv_sf, float *sigma2, float *inv_sigma2, int *nfeat, int *umax) {
+    Extractor *E = (Extractor *)h;
+    for (int i = 0; i < E->p.nlevels; i++) {
+        sf[i] = E->p.sf[i]; inv_sf[i] = E->p.inv_sf[i]; sigma2[i] = E->p.sigma2[i];
+        inv_sigma2[i] = E->p.inv_sigma2[i]; nfeat[i] = E->p.nfeat[i];
+    }
+    for (int v = 0; v <= kHalfPatch; v++) umax[v] = E->p.umax[v];
+}
+
+int orc_extract(void *h, const uint8_t *img, int w, int hh, int stride, int lap0, int lap1, int fma_mode) {
+    return extract(*(Extractor *)h, img, w, hh, stride, lap0, lap1, fma_mode);
+}
+int orc_num_keypoints(void *h) { return (int)((Extractor *)h)->out_kps.size(); }
+void orc_result(void *h, orc_kp *kps, uint8_t *desc) {
+    Extractor *E = (Extractor *)h;
+    memcpy(kps, E->out_kps.data(), E->out_kps.size() * sizeof(KeyPt));
+    memcpy(desc, E->out_desc.data(), E->out_desc.size());
+}
+void orc_level_size(void *h, int l, int *w, int *hh, int *stride) {
+    Level &L = ((Extractor *)h)->lv[l]; *w = L.w; *hh = L.h; *stride = L.stride;
+}
+void orc_level_bordered(void *h, int l, uint8_t *dst) {   // (h+38) x (w+38), tightly packed
+    Level &L = ((Extractor *)h)->lv[l]; memcpy(dst, L.buf.data(), L.buf.size());
+}
+int orc_level_blur(void *h, int l, uint8_t *dst) {        // h x w tightly packed; 0 if level not blurred
+    Level &L = ((Extractor *)h)->lv[l]; if (!L.blurred) return 0; memcpy(dst, L.blur.data(), L.blur.size()); return 1;
+}
+int orc_level_num_candidates(void *h, int l) { return (int)((Extractor *)h)->lv[l].cand.size(); }
+void orc_level_candidates(void *h, int l, int *xs, int *ys, int *scores) {
+    Level &L = ((Extractor *)h)->lv[l];
+    for (size_t i = 0; i < L.cand.size(); i++) { xs[i] = L.cand[i].x; ys[i] = L.cand[i].y; scores[i] = L.cand[i].score; }
+}
+int orc_level_num_keypoints(void *h, int l) { return (int)((Extractor *)h)->lv[l].kps.size(); }
+void orc_level_keypoints(void *h, int l, orc_kp *kps) {
+    Level &L = ((Extractor *)h)->lv[l]; memcpy(kps, L.kps.data(), L.kps.size() * sizeof(KeyPt));
+}
+void orc_stage_seconds(void *h, double *t6, int reset) {
+    Extractor *E = (Extractor *)h;
+    for (int i = 0; i < 6; i++) { t6[i] = E->t_stage[i]; if (reset) E->t_stage[i] = 0; }
+}
+
+// --- primitives, individually testable against cv2 -------------------------------------------------
+void orc_resize_linear(const uint8_t *src, int sw, int sh, int sstride, uint8_t *dst, int dw, int dh, int dstride) {
+    resize_linear(src, sw, sh, sstride, dst, dw, dh, dstride);
+}
+void orc_border_reflect101(uint8_t *buf, int w, int h, int stride, int b) { fill_border_reflect101(buf, w, h, stride, b); }
+int orc_fast(const uint8_t *img, int w, int h, int stride, int threshold, int *xs, int *ys, int *scores, int cap) {
+    std::vector<FastPt> out; fast9_16(img, w, h, stride, threshold, out);
+    int n = (int)out.size();
+    for (int i = 0; i < n && i < cap; i++) { xs[i] = out[i].x; ys[i] = out[i].y; scores[i] = out[i].score; }
+    return n;
+}
+void orc_blur7(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride) { blur7(src, w, h, sstride, dst, dstride); }
+float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+void orc_fast_atan2_n(const float *y, const float *x, float *out, int n) { for (int i = 0; i < n; i++) out[i] = fast_atan2(y[i], x[i]); }
+float orc_ic_angle(const uint8_t *img, int stride, int x, int y) {
+    Params p; make_params(p, 1000, 1.2f, 8, 20, 7);
+    return ic_angle(img, stride, x, y, p.umax);
+}
+void orc_descriptor(const uint8_t *img, int stride, int x, int y, float angle, int fma_mode, uint8_t *desc) {
+    orb_descriptor(img, stride, x, y, angle, fma_mode, desc);
+}
+// candidate selection alone: pts (x,y,score) border-relative -> selected indices in output order
+int orc_distribute(const int *xs, const int *ys, const int *scores, int n, int minX, int maxX, int minY, int maxY,
+                   int N, int *sel, int cap) {
+    std::vector<FastPt> pts(n);
+    for (int i = 0; i < n; i++) pts[i] = {xs[i], ys[i], scores[i]};
+    std::vector<int> r;
+    if (n > 0) distribute_octtree(pts, minX, maxX, minY, maxY, N, r);
+    for (size_t i = 0; i < r.size() && (int)i < cap; i++) sel[i] = r[i];
+    return (int)r.size();
+}
+// std::sort with compareNodes on (size, UL.x) pairs: returns the permutation (for the introsort emulation test)
+void orc_sort_nodes(const int *sizes, const int *ulx, int n, int *perm) {
+    std::vector<Node> nodes(n);
+    std::vector<std::pair<int, Node *>> v(n);
+    for (int i = 0; i < n; i++) { nodes[i].ulx = ulx[i]; v[i] = std::make_pair(sizes[i], &nodes[i]); }
+    std::sort(v.begin(), v.end(), compare_nodes);
+    for (int i = 0; i < n; i++) perm[i] = (int)(v[i].second - nodes.data());
+}
+
+// glibc cosf/sinf as the reference calls them (ORBextractor.cc:48) — for the device restatement test
+void orc_libm_sincosf_n(const float *x, float *s, float *c, int n) { for (int i = 0; i < n; i++) { s[i] = sinf(x[i]); c[i] = cosf(x[i]); } }
+
+// --- batch extraction on host threads (CPU baseline: one std::thread per image, Frame.cc:1841-1862) ---
+// imgs: n images, each w x h tightly packed.  Returns total keypoints; per-image counts in n_kp/n_mono.
+int orc_extract_batch(int nimg, const uint8_t *imgs, int w, int h, int nfeatures, float sf, int nlevels, int iniTh,
+                      int minTh, int lap0, int lap1, int fma_mode, int nthreads, int *n_kp, int *n_mono) {
+    std::atomic<int> next(0), total(0);
+    auto work = [&]() {
+        Extractor E; make_params(E.p, nfeatures, sf, nlevels, iniTh, minTh);
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= nimg) break;
+            int m = extract(E, imgs + (size_t)i * w * h, w, h, w, lap0, lap1, fma_mode);
+            if (n_kp) n_kp[i] = (int)E.out_kps.size();
+            if (n_mono) n_mono[i] = m;
+            total += (int)E.out_kps.size();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < std::max(1, nthreads); t++) th.emplace_back(work);
+    for (auto &t : th) t.join();
+    return total.load();
+}
+
+// --- matching -----------------------------------------------------------------------------------------
+int orc_hamming(const uint8_t *a, const uint8_t *b) { return descriptor_distance(a, b); }
+
+// cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2) (Frame.cc:1427,1483): per query the two nearest train rows,
+// ordered (distance asc, trainIdx asc).  idx/dist are [nq][2]; missing entries are -1.
+void orc_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt, int *idx, int *dist, int nthreads) {
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            int i0 = next.fetch_add(64);
+            if (i0 >= nq) break;
+            for (int i = i0; i < std::min(nq, i0 + 64); i++) {
+                int b0 = 1 << 30, b1 = 1 << 30, i0x = -1, i1x = -1;
+                for (int j = 0; j < nt; j++) {
+                    int d = descriptor_distance(q + (size_t)i * 32, t + (size_t)j * 32);
+                    if (d < b0) { b1 = b0; i1x = i0x; b0 = d; i0x = j; }
+                    else if (d < b1) { b1 = d; i1x = j; }
+                }
+                idx[2 * i] = i0x; dist[2 * i] = i0x < 0 ? -1 : b0;
+                idx[2 * i + 1] = i1x; dist[2 * i + 1] = i1x < 0 ? -1 : b1;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int k = 0; k < std::max(1, nthreads); k++) th.emplace_back(work);
+    for (auto &x : th) x.join();
+}
+
+// Lowe ratio test as the callers write it (Frame.cc:1434 ratio 0.7, :1491 ratio 0.8): float distances,
+// the product evaluated in double.  keep[i] = 1 iff two neighbours exist and d0 < d1 * ratio.
+void orc_ratio_test(const int *dist, int nq, double ratio, uint8_t *keep) {
+    for (int i = 0; i < nq; i++)
+        keep[i] = (dist[2 * i] >= 0 && dist[2 * i + 1] >= 0 && (float)dist[2 * i] < (float)dist[2 * i + 1] * ratio) ? 1 : 0;
+}
+
+// Frame grid (per camera)
+void *orc_grid_create(const orc_kp *kps, int n, float minX, float maxX, float minY, float maxY) {
+    Grid *g = new Grid(); grid_build(*g, (const KeyPt *)kps, n, minX, maxX, minY, maxY); return g;
+}
+void orc_grid_destroy(void *g) { delete (Grid *)g; }
+int orc_grid_query(void *g, const orc_kp *kps, float x, float y, float r, int minLevel, int maxLevel, int *out, int cap) {
+    std::vector<int> v; features_in_area(*(Grid *)g, (const KeyPt *)kps, x, y, r, minLevel, maxLevel, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+// ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints), ORBmatcher.cc:23-340,
+// over plain arrays.  Frame side: ncam cameras (1 = the Nleft==-1 monocular/rectified layout, 2 or 4 = the
+// multi-camera layout with Nleft..Nsideright), camera c owns global rows [cam_off[c], cam_off[c+1]).
+//   kps / desc            : all keypoints (camera-local order inside each block) and their descriptor rows
+//   grids[c]              : orc_grid_create() of camera c's keypoints
+//   sf                    : F.mvScaleFactors
+//   occupied[idx]         : 1 iff F.mvpMapPoints[idx] is set with Observations()>0 on entry (global idx)
+//   l2r / r2l             : mvLeftToRightMatch (size Nleft) / mvRightToLeftMatch (size Nright), or NULL
+//   u_right               : F.mvuRight (only read when ncam==1), or NULL
+// Map-point side (nmp points; per-camera arrays are [nmp][4]):
+//   in_view, proj_x, proj_y, level, view_cos ; proj_xr[nmp] (rectified right u) ; depth[nmp]; bad[nmp];
+//   has_obs[nmp] (Observations()>0 — what makes a claim visible to later points); mp_desc [nmp][32]
+// Output: assigned[idx] = map-point index written to F.mvpMapPoints[idx] (last writer), -1 if untouched.
+// Returns nmatches.
+int orc_search_by_projection(int ncam, const int *cam_off, const orc_kp *kps, const uint8_t *desc, void **grids,
+                             const float *sf, const uint8_t *occupied, const int *l2r, const int *r2l,
+                             const float *u_right, int nmp, const uint8_t *in_view, const float *proj_x,
+                             const float *proj_y, const int *level, const float *view_cos, const float *proj_xr,
+                             const float *depth, const uint8_t *bad, const uint8_t *has_obs, const uint8_t *mp_desc,
+                             float th, int bFarPoints, float thFarPoints, float nnratio, int *assigned) {
+    const int N = cam_off[ncam];
+    std::vector<uint8_t> occ(occupied, occupied + N);
+    for (int i = 0; i < N; i++) assigned[i] = -1;
+    const int TH_HIGH = 100;
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> cand;
+    for (int m = 0; m < nmp; m++) {
+        const uint8_t *iv = in_view + 4 * m;
+        if (!iv[0] && !iv[1] && !iv[2] && !iv[3]) continue;
+        if (bFarPoints && depth[m] > thFarPoints) continue;
+        if (bad[m]) continue;
+        bool skip_rest = false;
+        for (int c = 0; c < 4 && !skip_rest; c++) {
+            if (!iv[c]) continue;
+            if (c >= 1 && ncam < 2) continue;           // F.Nleft == -1
+            if (c >= 2 && ncam < 4) continue;           // F.Nsideleft == -1
+            const int lvl = level[4 * m + c];
+            if (c >= 1 && lvl == -1) continue;
+            float r = view_cos[4 * m + c] > 0.998 ? 2.5f : 4.0f;   // RadiusByViewingCos :342-347
+            if (c == 0 && bFactor) r *= th;                        // only camera 0 applies th (:51-52)
+            const KeyPt *ck = (const KeyPt *)kps + cam_off[c];
+            features_in_area(*(Grid *)grids[c], ck, proj_x[4 * m + c], proj_y[4 * m + c], r * sf[lvl], lvl - 1, lvl, cand);
+            if (cand.empty()) continue;
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            for (int idx : cand) {
+                const int g = idx + cam_off[c];
+                if (occ[g]) continue;
+                if (c == 0 && ncam == 1 && u_right && u_right[idx] > 0) {
+                    const float er = fabsf(proj_xr[m] - u_right[idx]);
+                    if (er > r * sf[lvl]) continue;
+                }
+                const int dist = descriptor_distance(mp_desc + (size_t)m * 32, desc + (size_t)g * 32);
+                if (dist < bestDist) {
+                    bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
+                    bestLevel = ck[idx].octave; bestIdx = idx;
+                } else if (dist < bestDist2) { bestLevel2 = ck[idx].octave; bestDist2 = dist; }
+            }
+            if (bestDist <= TH_HIGH) {
+                if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) { skip_rest = true; continue; }  // `continue` of the MapPoint loop
+                const int g = bestIdx + cam_off[c];
+                if (c == 0) {
+                    assigned[g] = m; occ[g] = has_obs[m];
+                    if (ncam >= 2 && l2r && l2r[bestIdx] != -1) {
+                        const int gr = l2r[bestIdx] + cam_off[1];
+                        assigned[gr] = m; occ[gr] = has_obs[m];
+                        nmatches++;
+                    }
+                    nmatches++;
+                } else if (c == 1) {
+                    if (r2l && r2l[bestIdx] != -1) {
+                        const int gl = r2l[bestIdx];
+                        assigned[gl] = m; occ[gl] = has_obs[m];
+                        nmatches++;
+                    }
+                    assigned[g] = m; occ[g] = has_obs[m];
+                    nmatches++;
+                } else {
+                    assigned[g] = m; occ[g] = has_obs[m];
+                    nmatches++;
+                }
+            }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForTriangulation Hamming core, ORBmatcher.cc:1218-1427, with the vocabulary FeatureVectors
+// given as CSR (sorted node ids + index lists) and the geometry test as an optional pair mask.
+//   nodes1[nn1], ptr1[nn1+1], idx1[...] : KF1 feature vector ; same for KF2
+//   skip1[idx] / skip2[idx] : keypoint already has a MapPoint (or fails bOnlyStereo) -> skipped
+//   pair_ok : NULL (bCoarse=true) or a callback standing for the epipole-distance + epipolarConstrain tests
+// Output: match12[n1] = idx2 or -1.  Returns nmatches.  (vbMatched2 is never set by the reference, :1204/1261.)
+typedef int (*orc_pair_pred)(int idx1, int idx2, void *user);
+int orc_search_for_triangulation(int nn1, const int *nodes1, const int *ptr1, const int *idx1v, int nn2,
+                                 const int *nodes2, const int *ptr2, const int *idx2v, const uint8_t *desc1, int n1,
+                                 const uint8_t *desc2, const uint8_t *skip1, const uint8_t *skip2,
+                                 orc_pair_pred pair_ok, void *user, int *match12) {
+    const int TH_LOW = 50;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int i1 = ptr1[a]; i1 < ptr1[a + 1]; i1++) {
+                const int id1 = idx1v[i1];
+                if (skip1[id1]) continue;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = ptr2[b]; i2 < ptr2[b + 1]; i2++) {
+                    const int id2 = idx2v[i2];
+                    if (skip2[id2]) continue;
+                    const int dist = descriptor_distance(desc1 + (size_t)id1 * 32, desc2 + (size_t)id2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    if (pair_ok && !pair_ok(id1, id2, user)) continue;
+                    bestIdx2 = id2; bestDist = dist;
+                }
+                if (bestIdx2 >= 0) { match12[id1] = bestIdx2; nmatches++; }
+            }
+            a++; b++;
+        } else if (nodes1[a] < nodes2[b]) {
+            while (a < nn1 && nodes1[a] < nodes2[b]) a++;   // lower_bound
+        } else {
+            while (b < nn2 && nodes2[b] < nodes1[a]) b++;
+        }
+    }
+    return nmatches;
+}
+
+}  // extern "C"
