@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the ORB-extraction / Hamming-matching hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config 3 of BASELINE.json, the one the metric is quoted on): Hilti-2022 rig frames, 5 x 720x540 cameras,
+1500 features/camera, FAST 20/7, 8 levels, scale 1.2, lapping {0,720} on the two front cameras; a "step" extracts a
+batch of --frames rig frames per GPU (default 64 = 320 images; the pyramids of one batch are ~460 MB, larger than the
+126 MB L2).  Weak scaling: every rank owns its own batch of rig frames, no data-path collective.
+
+One JSON line is printed by rank 0:
+  value     rig-frames/s, inputs resident in HBM, device pipeline only (CUDA events, max over ranks)
+  e2e       rig-frames/s through the host-buffer C-ABI call orbx_extract_batch (pinned host images in, keypoints +
+            descriptors out, copies inside the timed region)
+  roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  cpu_baseline  the CPU oracle (oracle/liborb_oracle.so, a port of the reference's CPU path) on the host cores
+  matching  secondary metric: brute-force Hamming 2-NN pairs/s vs the measured popc issue rate
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NCAM, NFEAT, INI, MIN = 720, 540, 5, 1500, 20, 7
+LAPS = [(0, 720), (0, 720), (0, 0), (0, 0), (0, 0)]
+# algorithmic bytes per level-0 pixel: pyramid 7.1, FAST 3.1, blur 6.2  => 16.4 per image pixel
+ALG_BYTES_PER_PX = {'pyramid': 7.12, 'fast': 3.095, 'blur': 6.19, 'total': 16.4}
+
+
+def make_batch(frames, rank):
+    """frames x 5 synthetic camera images.  10 distinct textured images are generated (numpy, deterministic); the rest of
+    the batch are shifted/flipped variants so that every image has different content at the same statistics."""
+    from openmavis_b200.synth import synth_image
+    base = [synth_image(W, H, 3000 + 10 * rank + i) for i in range(10)]
+    rng = np.random.default_rng(rank)
+    out = np.empty((frames * NCAM, H, W), np.uint8)
+    for i in range(frames * NCAM):
+        im = base[i % 10]
+        if i >= 10:
+            im = np.roll(im, (int(rng.integers(1, H)), int(rng.integers(1, W))), axis=(0, 1))
+            if rng.random() < 0.5:
+                im = im[:, ::-1]
+        out[i] = im
+    return out
+
+
+class ClockSampler:
+    FIELDS = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active') and t0 - 0.05 <= ts <= t1 + 0.15:
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+def cpu_oracle_run(frames, threads, rank=0):
+    """Times the CPU oracle (port of the reference's ORBextractor) on `frames` rig frames with `threads` host threads."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import oracle_lib as O
+    imgs = make_batch(frames, rank)[: frames * NCAM]
+    L = O.lib()
+    n = imgs.shape[0]
+    nkp = np.zeros(n, np.int32); nm = np.zeros(n, np.int32)
+    # lapping differs per camera; the oracle batch call takes one pair -> run the two groups separately (same total work)
+    t0 = time.perf_counter()
+    front = np.ascontiguousarray(imgs.reshape(frames, NCAM, H, W)[:, :2].reshape(-1, H, W))
+    side = np.ascontiguousarray(imgs.reshape(frames, NCAM, H, W)[:, 2:].reshape(-1, H, W))
+    tot = L.orc_extract_batch(front.shape[0], O.p(front), W, H, NFEAT, O.C.c_float(1.2), 8, INI, MIN, 0, 720, 0, threads, O.p(nkp), O.p(nm))
+    tot += L.orc_extract_batch(side.shape[0], O.p(side), W, H, NFEAT, O.C.c_float(1.2), 8, INI, MIN, 0, 0, 0, threads, O.p(nkp), O.p(nm))
+    dt = time.perf_counter() - t0
+    return frames / dt, dt, tot
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Its sources need OpenCV/Eigen/Sophus headers
+    that are not in this image, so the timed code is the oracle port, with all host threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    frames = max(1, min(args.ref_frames, 64))
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_oracle_run(1, threads)
+    vals, tot_t = [], 0.0
+    for _ in range(args.steps):
+        v, dt, _ = cpu_oracle_run(frames, threads)
+        vals.append(v); tot_t += dt
+    value = frames * args.steps / tot_t
+    line = {
+        'impl': 'reference', 'metric': 'rig-frames/sec ORB extract (5x720x540, 1500 kp/cam)', 'value': value, 'unit': 'rig-frames/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'frames_per_step': frames, 'features_per_camera': NFEAT,
+                   'fast_thresholds': [INI, MIN], 'levels': 8, 'scale_factor': 1.2},
+        'cpu_baseline': {'value': value, 'unit': 'rig-frames/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d rig frames x %d steps, %d host threads (one image per thread)' % (frames, args.steps, threads)},
+        'e2e': {'value': value, 'unit': 'rig-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--frames', type=int, default=64, help='rig frames per step per GPU')
+    ap.add_argument('--ref-frames', type=int, default=8, help='rig frames per step of the CPU reference arm')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline sample')
+    ap.add_argument('--no-matching', action='store_true')
+    ap.add_argument('--knn-n', type=int, default=100000)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import openmavis_b200 as ob
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    frames = args.frames
+    n_img = frames * NCAM
+    host_imgs = make_batch(frames, rank)
+    pinned = torch.from_numpy(host_imgs).pin_memory()
+    d_imgs = pinned.to(dev, non_blocking=False)
+    params = ob.make_params(n_img, NFEAT, INI, MIN, LAPS * frames)
+    rig = ob.RigExtractor(W, H, n_img, NFEAT, 1.2, 8, device=local)
+    stream = torch.cuda.current_stream()
+    rig.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # L2 flush buffer (inputs are > L2 anyway)
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for _ in range(args.warmup):
+        rig.extract_device(d_imgs.data_ptr(), n_img, params)
+    barrier()
+    rig.set_profiling(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        rig.extract_device(d_imgs.data_ptr(), n_img, params)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    stage = rig.stage_ms()
+    rig.set_profiling(False)
+    launches_per_step = rig.last_launches()
+    value = world * frames * args.steps / (ms_total * 1e-3)
+    res = rig.fetch(n_img)
+    kp_per_image = float(np.mean([len(r[1]) for r in res]))
+
+    # ---------------- end to end through the host-buffer C-ABI call (`e2e`) ----------------
+    import ctypes as C
+    ptrs = (C.c_void_p * n_img)(*[pinned.data_ptr() + i * W * H for i in range(n_img)])
+    strides = np.full(n_img, W, np.int32)
+    cap = rig.cap
+    out_kps = torch.empty((n_img, cap, 28), dtype=torch.uint8).pin_memory()
+    out_desc = torch.empty((n_img, cap, 32), dtype=torch.uint8).pin_memory()
+    out_n = torch.empty((2, n_img), dtype=torch.int32).pin_memory()
+    kps_np, desc_np = out_kps.numpy().view(ob.KP_DTYPE).reshape(n_img, cap), out_desc.numpy()
+    nkp_np, nmono_np = out_n.numpy()[0], out_n.numpy()[1]
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(2):
+        rig.extract_host_raw(ptrs, strides, params, kps_np, desc_np, nkp_np, nmono_np, n_img)
+    barrier()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        rig.extract_host_raw(ptrs, strides, params, kps_np, desc_np, nkp_np, nmono_np, n_img)
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * frames * e2e_steps / (ms_e2e * 1e-3)
+    h2d = n_img * W * H + n_img * (20 + 32)
+    d2h = n_img * cap * (28 + 32) + 2 * 4 * n_img
+    # the e2e results must equal the device-resident ones
+    for i in (0, n_img - 1):
+        assert nkp_np[i] == len(res[i][1]) and np.array_equal(desc_np[i, :nkp_np[i]], res[i][2])
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks, peak_kind = measured_peaks()
+    kernels = {k: stage[k] for k in ('pyramid', 'blur', 'fast', 'octree', 'slots', 'orient_desc')}
+    dom = max(kernels, key=kernels.get)
+    px = n_img * W * H
+    alg = {'pyramid': ALG_BYTES_PER_PX['pyramid'] * px, 'blur': ALG_BYTES_PER_PX['blur'] * px, 'fast': ALG_BYTES_PER_PX['fast'] * px,
+           'octree': None, 'slots': None, 'orient_desc': None}
+    hbm_dom = dom if alg[dom] else max(('pyramid', 'blur', 'fast'), key=lambda k: kernels[k])
+    achieved = alg[hbm_dom] / (kernels[hbm_dom] * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': hbm_dom, 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_kind,
+                'stage_ms': stage, 'dominant_stage': dom,
+                'pipeline_frac': ALG_BYTES_PER_PX['total'] * px / (stage['total'] * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                'per_kernel_frac': {k: (alg[k] / (kernels[k] * 1e-3) / 1e9 / peaks['hbm_gbs']) for k in ('pyramid', 'blur', 'fast')}}
+
+    # ---------------- secondary metric: brute-force Hamming 2-NN ----------------
+    matching = None
+    if not args.no_matching:
+        from openmavis_b200.synth import synth_descriptors, synth_query_from_train
+        n = args.knn_n
+        m = ob.ORBmatcher(0.8, device=local)
+        m.set_stream(stream.cuda_stream)
+        train = synth_descriptors(n, 5)
+        query = synth_query_from_train(train, 6)
+        per = (n + world - 1) // world
+        lo, hi = rank * per, min(n, (rank + 1) * per)
+        d_q = torch.from_numpy(query[lo:hi]).to(dev)
+        d_local_train = torch.from_numpy(train[lo:hi]).to(dev)
+        d_idx = torch.empty((hi - lo, 2), dtype=torch.int32, device=dev)
+        d_dist = torch.empty((hi - lo, 2), dtype=torch.int32, device=dev)
+
+        def knn_step():
+            if world > 1:    # the one real exchange step: NCCL all-gather of the train rows over NVLink
+                parts = [torch.empty((min(n, (r + 1) * per) - r * per, 32), dtype=torch.uint8, device=dev) for r in range(world)]
+                dist.all_gather(parts, d_local_train)
+                d_t = torch.cat(parts)
+            else:
+                d_t = d_local_train
+            m.knnMatch2_device(d_q.data_ptr(), hi - lo, d_t.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+            return d_t
+        for _ in range(2):
+            knn_step()
+        barrier()
+        ksteps = 5
+        e0.record(stream)
+        for _ in range(ksteps):
+            knn_step()
+        e1.record(stream)
+        barrier()
+        ms_knn = max_over_ranks(e0.elapsed_time(e1)) / ksteps
+        pairs = float(n) * float(n)
+        popc = ob.popc_peak(local)
+        matching = {'metric': 'Hamming matches/sec (brute-force 2-NN %dx%d)' % (n, n), 'value': pairs / (ms_knn * 1e-3), 'unit': 'pairs/s',
+                    'ms': ms_knn, 'popc_gops_achieved': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world, 'popc_gops_peak_measured': popc,
+                    'frac_of_popc_peak': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world / popc, 'n_gpus': world,
+                    'collective': 'nccl all_gather of train rows' if world > 1 else None}
+        idx_h = d_idx.cpu().numpy(); dist_h = d_dist.cpu().numpy()
+        chk = np.unpackbits(query[lo:hi][:256] ^ train[idx_h[:256, 0]], axis=1).sum(axis=1)
+        assert np.array_equal(chk, dist_h[:256, 0])
+
+    # ---------------- CPU baseline (rank 0, N == 1 only; bounded sample) ----------------
+    cpu = None
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        v1, dt1, _ = cpu_oracle_run(1, threads)
+        nfr = int(max(1, min(32, args.cpu_seconds / max(dt1, 1e-3))))
+        v, dt, _ = cpu_oracle_run(nfr, threads)
+        cpu = {'value': v, 'unit': 'rig-frames/s', 'cores': threads, 'kind': 'port',
+               'sample': '%d rig frames (%d images) of the same workload, %.1f s, %d host threads' % (nfr, nfr * NCAM, dt, threads)}
+
+    if rank == 0:
+        line = {
+            'metric': 'rig-frames/sec ORB extract (5x720x540, 1500 kp/cam)', 'value': value, 'unit': 'rig-frames/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+            'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'frames_per_step_per_gpu': frames, 'images_per_step_per_gpu': n_img,
+                       'features_per_camera': NFEAT, 'fast_thresholds': [INI, MIN], 'levels': 8, 'scale_factor': 1.2,
+                       'keypoints_per_image': kp_per_image,
+                       'l2': 'inputs+pyramids per step (%.0f MB) exceed the 126 MB L2' % ((px * 1.0 + px * 3.7 * 2) / 1e6)},
+            'e2e': {'value': e2e_value, 'unit': 'rig-frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps},
+            'gpu_launches': launches_per_step * args.steps,
+            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'matching': matching,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

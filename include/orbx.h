@@ -1,0 +1,217 @@
+/* orbx.h — C ABI of liborbx.so: B200-native (sm_100a) ORB extraction and Hamming matching.
+ *
+ * This is the drop-in boundary for the hot path of OpenMAVIS (an ORB-SLAM3 fork).  The reference has
+ * no FFI layer: the path is two C++ classes, ORB_SLAM3::ORBextractor (include/ORBextractor.h:28-84,
+ * src/ORBextractor.cc) and ORB_SLAM3::ORBmatcher (include/ORBmatcher.h:17-123, src/ORBmatcher.cc), plus
+ * the cv::BFMatcher call in Frame (src/Frame.cc:24,1427,1483).  The header-compatible shims in
+ * openmavis_b200/csrc/host/ are written on top of exactly these entry points.
+ *
+ * Conventions: plain C types only; opaque handles; caller-owned output buffers with an explicit capacity;
+ * every function returns ORBX_OK (0) or a negative orbx_status and never throws; orbx_last_error() gives
+ * the message of the calling thread's last failure.  A handle may be used by one thread at a time;
+ * different handles are independent (one CUDA stream set per handle).  There is NO CPU fallback: without
+ * a CUDA device every compute entry point fails with ORBX_ERR_NO_DEVICE.
+ *
+ * All file:line cites are relative to the reference tree.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum orbx_status {
+    ORBX_OK = 0,
+    ORBX_ERR_INVALID = -1,     /* bad argument */
+    ORBX_ERR_NO_DEVICE = -2,   /* no CUDA device / device index out of range */
+    ORBX_ERR_CUDA = -3,        /* CUDA runtime error (message in orbx_last_error) */
+    ORBX_ERR_CAPACITY = -4,    /* caller buffer too small / batch larger than the handle was created for */
+    ORBX_ERR_EMPTY = -5        /* empty image: the reference returns -1 (src/ORBextractor.cc:994-995) */
+} orbx_status;
+
+/* Field-for-field cv::KeyPoint (pt.x, pt.y, size, angle, response, octave, class_id): 28 bytes. */
+typedef struct orbx_kp {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbx_kp;
+
+/* Per-image extractor settings: the constructor arguments of ORBextractor that may differ between the
+ * cameras of a rig (src/Tracking.cc:572-587: side cameras get 2*nFeatures) and the vLappingArea argument
+ * of operator() (src/ORBextractor.cc:987-992). */
+typedef struct orbx_image_params {
+    int32_t nfeatures;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+    int32_t lap0, lap1;        /* vLappingArea[0], vLappingArea[1] */
+} orbx_image_params;
+
+const char *orbx_last_error(void);
+int orbx_device_count(void);
+/* Library / build identification, e.g. "orbx 0.1 sm_100a". */
+const char *orbx_version(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Extraction — replaces ORBextractor::ORBextractor (src/ORBextractor.cc:351-414) and
+ * ORBextractor::operator() (src/ORBextractor.cc:987-1071) with everything under it: ComputePyramid
+ * (:1073-1104), ComputeKeyPointsOctTree (:704-823), DistributeOctTree (:496-702), IC_Angle (:19-43),
+ * GaussianBlur + computeOrbDescriptor (:1035-1036, :46-90) and the lapping-area partition (:1024-1068).
+ *
+ * A handle is created for one image geometry (width x height), pyramid shape (nlevels, scale_factor) and
+ * a maximum batch size; one call processes up to max_images images (all cameras of a rig frame, or many
+ * rig frames) in one launch set.  fma_mode: 0 = every float op of the descriptor rotation rounded
+ * separately; 1 = contracted the way g++ -O3 -march=native contracts src/ORBextractor.cc:56-57.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct orbx_extractor orbx_extractor;
+
+int orbx_extractor_create(orbx_extractor **out, int device, int width, int height, int max_images,
+                          int max_nfeatures, float scale_factor, int nlevels, int fma_mode);
+void orbx_extractor_destroy(orbx_extractor *ex);
+
+/* Launch all work of this handle on an existing CUDA stream (cudaStream_t passed as void*); NULL restores
+ * the handle's own stream. */
+int orbx_extractor_set_stream(orbx_extractor *ex, void *cuda_stream);
+
+/* Rows of the per-image output buffers the caller must provide (>= nfeatures plus the quadtree overshoot). */
+int orbx_extractor_capacity(const orbx_extractor *ex);
+
+/* Per-level tables = the getters of ORBextractor.h:40-50 (GetScaleFactors, GetInverseScaleFactors,
+ * GetScaleSigmaSquares, GetInverseScaleSigmaSquares) and the level sizes of ComputePyramid. Any pointer may be NULL. */
+int orbx_extractor_tables(const orbx_extractor *ex, float *scale, float *inv_scale, float *sigma2,
+                          float *inv_sigma2, int *level_w, int *level_h);
+/* mnFeaturesPerLevel for a given nfeatures (src/ORBextractor.cc:378-391). */
+int orbx_features_per_level(int nfeatures, float scale_factor, int nlevels, int *out);
+
+/* Host-buffer call (what ORBextractor::operator() binds to).  images[i] points to a CV_8UC1 image of the
+ * handle's geometry with row stride strides[i] bytes in HOST memory.  Outputs, all HOST memory:
+ *   kps  [n_images][cap]      keypoints, mono block first then the reversed lapping block
+ *   desc [n_images][cap][32]  descriptor rows in the same order
+ *   n_kp [n_images]           number of keypoints     n_mono [n_images]  return value of operator()
+ * The call uploads, computes, downloads and returns when the outputs are valid. */
+int orbx_extract_batch(orbx_extractor *ex, int n_images, const uint8_t *const *images, const int *strides,
+                       const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp,
+                       int *n_mono);
+
+/* Single image, reference-shaped: returns n_mono (>= 0) like operator(), or -1 for an empty image,
+ * or another negative orbx_status. */
+int orbx_extract(orbx_extractor *ex, const uint8_t *image, int stride, const orbx_image_params *params,
+                 orbx_kp *kps, uint8_t *desc, int cap, int *n_kp);
+
+/* Device-resident call: d_images is DEVICE memory holding n_images tightly packed width x height images.
+ * Enqueues the whole pipeline on the handle's stream and returns without synchronising; results stay in
+ * the handle's device buffers until fetched. */
+int orbx_extract_batch_device(orbx_extractor *ex, int n_images, const uint8_t *d_images,
+                              const orbx_image_params *params);
+/* Copies the results of the last (device or host) call to host buffers; synchronises the stream. */
+int orbx_extract_fetch(orbx_extractor *ex, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono);
+/* Device pointers of the last results (for device-side consumers such as the matchers):
+ * kps [max_images][cap], desc [max_images][cap][32], counts: n_kp[max_images], n_mono[max_images]. */
+int orbx_extract_device_results(orbx_extractor *ex, const orbx_kp **d_kps, const uint8_t **d_desc,
+                                const int **d_n_kp, const int **d_n_mono);
+
+/* mvImagePyramid[level] of image `image` from the last call (public member read by
+ * src/Frame.cc:1063,1147,1163).  with_border=0: the w x h level; 1: the (w+38) x (h+38) buffer with the
+ * 19-px BORDER_REFLECT_101 frame.  Downloaded lazily, on request. */
+int orbx_extractor_pyramid_level(orbx_extractor *ex, int image, int level, int with_border, uint8_t *dst,
+                                 int dst_stride);
+
+/* Stage intermediates of the last call, for stage-by-stage parity tests:
+ * blurred level (w x h), FAST candidates in vToDistributeKeys order (border-relative coordinates,
+ * src/ORBextractor.cc:784-791), per-level keypoints after DistributeOctTree + IC_Angle (level coordinates). */
+int orbx_debug_blur_level(orbx_extractor *ex, int image, int level, uint8_t *dst, int dst_stride);
+int orbx_debug_candidates(orbx_extractor *ex, int image, int level, int *xs, int *ys, int *scores, int cap,
+                          int *n);
+int orbx_debug_level_keypoints(orbx_extractor *ex, int image, int level, orbx_kp *kps, int cap, int *n);
+
+/* Per-stage device time of the last call, measured with CUDA events on the handle's stream when
+ * profiling is enabled (adds event records between stages; off by default).
+ * ms[0..ORBX_NUM_STAGES): pyramid, blur, fast, octree, slots, orient+descriptor, total. */
+#define ORBX_NUM_STAGES 7
+int orbx_extractor_set_profiling(orbx_extractor *ex, int enabled);
+int orbx_extractor_stage_ms(orbx_extractor *ex, float *ms);
+/* Number of kernel launches enqueued by the last call. */
+int orbx_extractor_last_launches(const orbx_extractor *ex);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Matching.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2577-2591) / FORB::distance
+ * (Thirdparty/DBoW2/DBoW2/FORB.cpp:81-101) for n independent pairs a[i], b[i] (32-byte rows, HOST). */
+int orbx_descriptor_distance(int device, const uint8_t *a, const uint8_t *b, int n, int *dist);
+
+typedef struct orbx_matcher orbx_matcher;
+int orbx_matcher_create(orbx_matcher **out, int device);
+void orbx_matcher_destroy(orbx_matcher *m);
+int orbx_matcher_set_stream(orbx_matcher *m, void *cuda_stream);
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2) (src/Frame.cc:1427, 1483): for each of the
+ * nq query rows the two nearest of the nt train rows, ordered (distance asc, trainIdx asc).
+ * idx/dist are [nq][2]; an entry that does not exist (nt < 2) is -1.  HOST pointers. */
+int orbx_knn2(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt, int *idx, int *dist);
+/* Same with DEVICE pointers, asynchronous on the matcher's stream (no host synchronisation). */
+int orbx_knn2_device(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt, int *d_idx,
+                     int *d_dist);
+/* Lowe ratio test exactly as the callers evaluate it (src/Frame.cc:1434 ratio 0.7; :1491 ratio 0.8):
+ * keep[i] = two neighbours exist && (float)d0 < (float)d1 * ratio (product in double). HOST, pure host code. */
+int orbx_ratio_test(const int *dist, int nq, double ratio, uint8_t *keep);
+
+/* Candidate-list matching: the Hamming core shared by the guided matchers (SearchByProjection overloads,
+ * Fuse, SearchBySim3, SearchForInitialization; src/ORBmatcher.cc:72-114 and its clones).  Query q is
+ * compared with train rows cand[row_ptr[q] .. row_ptr[q+1]) in that order.  Per query:
+ *   best_idx / best_dist    first minimum in candidate order (strict <), -1 / 256 if the list is empty
+ *   second_dist             ORB-SLAM second-best rule: `else if (dist < bestDist2)` (src/ORBmatcher.cc:103)
+ *   best_pos / second_pos   positions inside the candidate list (for level bookkeeping), -1 if none
+ * HOST pointers. */
+int orbx_match_csr(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt, const int *row_ptr,
+                   const int *cand, int *best_idx, int *best_dist, int *second_dist, int *best_pos,
+                   int *second_pos);
+/* All candidate distances, CSR-aligned: dist[k] = hamming(query[q], train[cand[k]]) for k in row q. */
+int orbx_match_csr_dists(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt,
+                         const int *row_ptr, const int *cand, int *dist);
+
+/* ORBmatcher::SearchForTriangulation Hamming core (src/ORBmatcher.cc:1218-1427, bCoarse semantics): the two
+ * vocabulary FeatureVectors as CSR (ascending node ids, index lists); skip1/skip2 mark keypoints that
+ * already have a MapPoint (or fail bOnlyStereo).  match12[n1] = idx2 or -1: minimum distance <= TH_LOW(50),
+ * LAST minimum on ties (src/ORBmatcher.cc:1274).  Returns the number of matches in *nmatches. HOST pointers. */
+int orbx_search_for_triangulation(orbx_matcher *m, int nn1, const int *nodes1, const int *ptr1, const int *idx1,
+                                  int nn2, const int *nodes2, const int *ptr2, const int *idx2,
+                                  const uint8_t *desc1, int n1, const uint8_t *desc2, int n2, const uint8_t *skip1,
+                                  const uint8_t *skip2, int *match12, int *nmatches);
+
+/* Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea (src/Frame.cc:541-582, 890-967, 969-978) for one
+ * camera: builds the 64x48 grid of `kps` on the device and answers nq window queries, producing CSR
+ * candidate lists in the reference's order (cell column-major, insertion order inside a cell).
+ * row_ptr[nq+1]; cand has capacity cand_cap; *n_cand receives the total (may exceed cand_cap -> ORBX_ERR_CAPACITY). */
+int orbx_grid_candidates(orbx_matcher *m, const orbx_kp *kps, int n, float min_x, float max_x, float min_y,
+                         float max_y, const float *qx, const float *qy, const float *qr, const int *min_level,
+                         const int *max_level, int nq, int *row_ptr, int *cand, int cand_cap, int *n_cand);
+
+/* ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+ * (src/ORBmatcher.cc:23-340) over plain arrays; argument meaning as in oracle/orb_oracle.cpp
+ * (orc_search_by_projection).  Candidate generation, Hamming distances, best/second selection and the ordered
+ * claim resolution (a keypoint claimed by an earlier map point is skipped by later ones, :77-79) all run on
+ * the device; assigned[N] receives the map-point index written to F.mvpMapPoints (or -1). HOST pointers. */
+int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
+                              const float *grid_bounds /* [ncam][4] minX,maxX,minY,maxY */, const float *scale_factors,
+                              int nlevels, const uint8_t *occupied, const int *l2r, const int *r2l, int nmp,
+                              const uint8_t *in_view, const float *proj_x, const float *proj_y, const int *level,
+                              const float *view_cos, const float *depth, const uint8_t *bad, const uint8_t *has_obs,
+                              const uint8_t *mp_desc, float th, int far_points, float th_far_points, float nnratio,
+                              int *assigned, int *nmatches);
+
+/* Launch count / device time of the matcher's last call (CUDA events on its stream). */
+int orbx_matcher_last_ms(orbx_matcher *m, float *ms);
+int orbx_matcher_last_launches(const orbx_matcher *m);
+
+/* Peak-rate microbenchmark used as the matching roofline denominator: issues `iters` dependent-free
+ * popc.b32 per thread on a full grid and returns giga-popc/s. */
+int orbx_popc_peak(int device, double *gpopc_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

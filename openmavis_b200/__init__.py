@@ -1,0 +1,397 @@
+"""openmavis_b200 — B200-native ORB extraction + Hamming matching (the OpenMAVIS / ORB-SLAM3 front-end hot path).
+
+Python host-side mirror of the reference's operator interface on top of the C ABI of liborbx.so
+(include/orbx.h).  The classes keep the reference's names and argument meaning:
+
+  ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)      include/ORBextractor.h:28-84
+      __call__(image, mask, vLappingArea) -> (n_mono, keypoints, descriptors)   src/ORBextractor.cc:987-1071
+  ORBmatcher(nnratio, checkOri)                                             include/ORBmatcher.h:17-123
+      DescriptorDistance, SearchByProjection, SearchForTriangulation, ...
+
+There is no CPU fallback: importing works anywhere (so the CPU test-suite can check the ABI surface), but every
+compute call raises OrbxError unless liborbx.so is built and a CUDA device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liborbx.so')
+
+KP_DTYPE = np.dtype([('x', 'f4'), ('y', 'f4'), ('size', 'f4'), ('angle', 'f4'), ('response', 'f4'),
+                     ('octave', 'i4'), ('class_id', 'i4')])
+PARAMS_DTYPE = np.dtype([('nfeatures', 'i4'), ('ini_th_fast', 'i4'), ('min_th_fast', 'i4'), ('lap0', 'i4'), ('lap1', 'i4')])
+NUM_STAGES = 7
+STAGE_NAMES = ('pyramid', 'blur', 'fast', 'octree', 'slots', 'orient_desc', 'total')
+
+TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30     # src/ORBmatcher.cc:15-17
+
+
+class OrbxError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads liborbx.so (built in-tree by openmavis_b200/csrc/Makefile).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OrbxError('liborbx.so not built: run `make -C openmavis_b200/csrc` (or __graft_entry__.build())')
+        L = C.CDLL(LIB_PATH)
+        L.orbx_last_error.restype = C.c_char_p
+        L.orbx_version.restype = C.c_char_p
+        L.orbx_extractor_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                            C.c_int, C.c_int]
+        L.orbx_extractor_destroy.argtypes = [C.c_void_p]
+        L.orbx_matcher_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.orbx_matcher_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(status):
+    if status < 0:
+        raise OrbxError('orbx status %d: %s' % (status, lib().orbx_last_error().decode()))
+    return status
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return lib().orbx_device_count()
+
+
+def features_per_level(nfeatures, scale_factor=1.2, nlevels=8):
+    out = np.zeros(nlevels, np.int32)
+    _check(lib().orbx_features_per_level(int(nfeatures), C.c_float(scale_factor), int(nlevels), _p(out)))
+    return out
+
+
+def make_params(n, nfeatures, ini_th, min_th, lapping=(0, 0)):
+    p = np.zeros(n, PARAMS_DTYPE)
+    p['nfeatures'] = nfeatures; p['ini_th_fast'] = ini_th; p['min_th_fast'] = min_th
+    lap = np.asarray(lapping, np.int32).reshape(-1, 2)
+    p['lap0'] = lap[:, 0]; p['lap1'] = lap[:, 1]
+    return p
+
+
+class RigExtractor:
+    """Batched extractor for one image geometry: all cameras of a rig frame, or many rig frames, per call."""
+
+    def __init__(self, width, height, max_images, max_nfeatures, scale_factor=1.2, nlevels=8, device=0, fma_mode=0):
+        self.L = lib()
+        self.width, self.height, self.max_images, self.nlevels = int(width), int(height), int(max_images), int(nlevels)
+        self.max_nfeatures = int(max_nfeatures)
+        self.scale_factor = float(scale_factor)
+        h = C.c_void_p()
+        _check(self.L.orbx_extractor_create(C.byref(h), int(device), self.width, self.height, self.max_images,
+                                            self.max_nfeatures, C.c_float(scale_factor), self.nlevels, int(fma_mode)))
+        self.h = h
+        self.cap = _check(self.L.orbx_extractor_capacity(self.h))
+        n = self.nlevels
+        self.scale, self.inv_scale, self.sigma2, self.inv_sigma2 = (np.zeros(n, np.float32) for _ in range(4))
+        self.level_w, self.level_h = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        _check(self.L.orbx_extractor_tables(self.h, _p(self.scale), _p(self.inv_scale), _p(self.sigma2), _p(self.inv_sigma2),
+                                            _p(self.level_w), _p(self.level_h)))
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.L.orbx_extractor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        _check(self.L.orbx_extractor_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def set_profiling(self, on):
+        _check(self.L.orbx_extractor_set_profiling(self.h, int(bool(on))))
+
+    def stage_ms(self):
+        ms = np.zeros(NUM_STAGES, np.float32)
+        _check(self.L.orbx_extractor_stage_ms(self.h, _p(ms)))
+        return dict(zip(STAGE_NAMES, ms.tolist()))
+
+    def last_launches(self):
+        return self.L.orbx_extractor_last_launches(self.h)
+
+    def alloc_outputs(self, n):
+        return (np.zeros((n, self.cap), KP_DTYPE), np.zeros((n, self.cap, 32), np.uint8), np.zeros(n, np.int32),
+                np.zeros(n, np.int32))
+
+    def extract(self, images, params, out=None):
+        """images: list/array of HxW uint8 host images.  Returns [(n_mono, keypoints, descriptors)] per image."""
+        n = len(images)
+        imgs = [np.ascontiguousarray(im) if im.strides[1] != 1 else im for im in images]
+        for im in imgs:
+            if im.dtype != np.uint8 or im.ndim != 2 or im.shape != (self.height, self.width):
+                raise OrbxError('image must be CV_8UC1 of %dx%d' % (self.width, self.height))
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        strides = np.array([im.strides[0] for im in imgs], np.int32)
+        params = np.ascontiguousarray(params, PARAMS_DTYPE)
+        kps, desc, nkp, nmono = out if out is not None else self.alloc_outputs(n)
+        _check(self.L.orbx_extract_batch(self.h, n, ptrs, _p(strides), _p(params), _p(kps), _p(desc), self.cap, _p(nkp), _p(nmono)))
+        return [(int(nmono[i]), kps[i, :nkp[i]], desc[i, :nkp[i]]) for i in range(n)]
+
+    def extract_host_raw(self, ptrs, strides, params, kps, desc, nkp, nmono, n):
+        """Zero-overhead variant for benchmarks: ctypes pointer array + preallocated outputs."""
+        _check(self.L.orbx_extract_batch(self.h, n, ptrs, _p(strides), _p(params), _p(kps), _p(desc), self.cap, _p(nkp), _p(nmono)))
+
+    def extract_device(self, d_images_ptr, n, params):
+        """Device-resident input (n tightly packed images at device address d_images_ptr); asynchronous."""
+        params = np.ascontiguousarray(params, PARAMS_DTYPE)
+        _check(self.L.orbx_extract_batch_device(self.h, int(n), C.c_void_p(d_images_ptr), _p(params)))
+
+    def fetch(self, n, out=None):
+        kps, desc, nkp, nmono = out if out is not None else self.alloc_outputs(n)
+        _check(self.L.orbx_extract_fetch(self.h, _p(kps), _p(desc), self.cap, _p(nkp), _p(nmono)))
+        return [(int(nmono[i]), kps[i, :nkp[i]], desc[i, :nkp[i]]) for i in range(n)]
+
+    def device_results(self):
+        a, b, c, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(self.L.orbx_extract_device_results(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def pyramid_level(self, image, level, with_border=False):
+        w, h = int(self.level_w[level]), int(self.level_h[level])
+        if with_border:
+            w, h = w + 38, h + 38
+        out = np.zeros((h, w), np.uint8)
+        _check(self.L.orbx_extractor_pyramid_level(self.h, int(image), int(level), int(with_border), _p(out), out.strides[0]))
+        return out
+
+    def debug_blur_level(self, image, level):
+        out = np.zeros((int(self.level_h[level]), int(self.level_w[level])), np.uint8)
+        _check(self.L.orbx_debug_blur_level(self.h, int(image), int(level), _p(out), out.strides[0]))
+        return out
+
+    def debug_candidates(self, image, level):
+        n = C.c_int(0)
+        _check(self.L.orbx_debug_candidates(self.h, int(image), int(level), None, None, None, 0, C.byref(n)))
+        xs, ys, sc = (np.zeros(max(n.value, 1), np.int32) for _ in range(3))
+        _check(self.L.orbx_debug_candidates(self.h, int(image), int(level), _p(xs), _p(ys), _p(sc), n.value, C.byref(n)))
+        return xs[:n.value], ys[:n.value], sc[:n.value]
+
+    def debug_level_keypoints(self, image, level):
+        n = C.c_int(0)
+        kps = np.zeros(self.cap, KP_DTYPE)
+        _check(self.L.orbx_debug_level_keypoints(self.h, int(image), int(level), _p(kps), self.cap, C.byref(n)))
+        return kps[:n.value]
+
+
+class ORBextractor:
+    """Drop-in mirror of ORB_SLAM3::ORBextractor (include/ORBextractor.h:28-84) for one camera."""
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0, fma_mode=0):
+        self.nfeatures, self.scaleFactor, self.nlevels = int(nfeatures), float(np.float32(scaleFactor)), int(nlevels)
+        self.iniThFAST, self.minThFAST = int(iniThFAST), int(minThFAST)
+        self.device, self.fma_mode = device, fma_mode
+        self._rig = None
+        lib()   # fail early if the native library is missing
+
+    def _handle(self, w, h):
+        if self._rig is None or (self._rig.width, self._rig.height) != (w, h):
+            if self._rig is not None:
+                self._rig.close()
+            self._rig = RigExtractor(w, h, 1, self.nfeatures, self.scaleFactor, self.nlevels, self.device, self.fma_mode)
+        return self._rig
+
+    def __call__(self, image, mask=None, vLappingArea=(0, 0)):
+        """Returns (monoIndex, keypoints, descriptors); (-1, empty, empty) for an empty image
+        (src/ORBextractor.cc:994-995).  `mask` is ignored, as in the reference."""
+        if image is None or image.size == 0:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise OrbxError('image.type() must be CV_8UC1 (src/ORBextractor.cc:998)')
+        rig = self._handle(image.shape[1], image.shape[0])
+        params = make_params(1, self.nfeatures, self.iniThFAST, self.minThFAST, vLappingArea)
+        return rig.extract([image], params)[0]
+
+    @property
+    def mvImagePyramid(self):
+        if self._rig is None:
+            return []
+        return [self._rig.pyramid_level(0, l) for l in range(self.nlevels)]
+
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return self.scaleFactor
+
+    def _tables(self):
+        n = self.nlevels
+        out = [np.zeros(n, np.float32) for _ in range(4)]
+        if self._rig is not None:
+            return self._rig.scale, self._rig.inv_scale, self._rig.sigma2, self._rig.inv_sigma2
+        sf = np.ones(n, np.float32)
+        for i in range(1, n):
+            sf[i] = np.float32(np.float64(sf[i - 1]) * np.float64(np.float32(self.scaleFactor)))
+        out[0][:] = sf; out[1][:] = np.float32(1.0) / sf; out[2][:] = sf * sf; out[3][:] = np.float32(1.0) / (sf * sf)
+        return out
+
+    def GetScaleFactors(self):
+        return self._tables()[0].copy()
+
+    def GetInverseScaleFactors(self):
+        return self._tables()[1].copy()
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()[2].copy()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()[3].copy()
+
+
+class ORBmatcher:
+    """Hamming cores of ORB_SLAM3::ORBmatcher (include/ORBmatcher.h) and of the cv::BFMatcher call in Frame."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = TH_LOW, TH_HIGH, HISTO_LENGTH
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.L = lib()
+        self.mfNNratio = float(np.float32(nnratio))
+        self.mbCheckOrientation = bool(checkOri)
+        self.device = device
+        h = C.c_void_p()
+        _check(self.L.orbx_matcher_create(C.byref(h), int(device)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.L.orbx_matcher_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        _check(self.L.orbx_matcher_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def last_ms(self):
+        ms = C.c_float(0)
+        _check(self.L.orbx_matcher_last_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def last_launches(self):
+        return self.L.orbx_matcher_last_launches(self.h)
+
+    @staticmethod
+    def DescriptorDistance(a, b, device=0):
+        """src/ORBmatcher.cc:2577-2591.  a, b: (32,) or (n,32) uint8.  Returns int or int array."""
+        a2 = np.ascontiguousarray(np.atleast_2d(a), np.uint8); b2 = np.ascontiguousarray(np.atleast_2d(b), np.uint8)
+        assert a2.shape == b2.shape and a2.shape[1] == 32
+        d = np.zeros(a2.shape[0], np.int32)
+        _check(lib().orbx_descriptor_distance(int(device), _p(a2), _p(b2), a2.shape[0], _p(d)))
+        return int(d[0]) if np.ndim(a) == 1 else d
+
+    def knnMatch2(self, query, train):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) (src/Frame.cc:1427,1483) -> idx[nq,2], dist[nq,2]."""
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        idx = np.full((q.shape[0], 2), -1, np.int32); dist = np.full((q.shape[0], 2), -1, np.int32)
+        _check(self.L.orbx_knn2(self.h, _p(q), q.shape[0], _p(t), t.shape[0], _p(idx), _p(dist)))
+        return idx, dist
+
+    def knnMatch2_device(self, d_query, nq, d_train, nt, d_idx, d_dist):
+        _check(self.L.orbx_knn2_device(self.h, C.c_void_p(d_query), int(nq), C.c_void_p(d_train), int(nt), C.c_void_p(d_idx),
+                                       C.c_void_p(d_dist)))
+
+    @staticmethod
+    def ratio_test(dist, ratio):
+        dist = np.ascontiguousarray(dist, np.int32)
+        keep = np.zeros(dist.shape[0], np.uint8)
+        _check(lib().orbx_ratio_test(_p(dist), dist.shape[0], C.c_double(ratio), _p(keep)))
+        return keep.astype(bool)
+
+    def match_csr(self, query, train, row_ptr, cand):
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        row_ptr = np.ascontiguousarray(row_ptr, np.int32); cand = np.ascontiguousarray(cand, np.int32)
+        nq = q.shape[0]
+        o = [np.zeros(nq, np.int32) for _ in range(5)]
+        _check(self.L.orbx_match_csr(self.h, _p(q), nq, _p(t), t.shape[0], _p(row_ptr), _p(cand), *[_p(x) for x in o]))
+        return dict(best_idx=o[0], best_dist=o[1], second_dist=o[2], best_pos=o[3], second_pos=o[4])
+
+    def match_csr_dists(self, query, train, row_ptr, cand):
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        row_ptr = np.ascontiguousarray(row_ptr, np.int32); cand = np.ascontiguousarray(cand, np.int32)
+        d = np.zeros(max(int(row_ptr[-1]), 1), np.int32)
+        _check(self.L.orbx_match_csr_dists(self.h, _p(q), q.shape[0], _p(t), t.shape[0], _p(row_ptr), _p(cand), _p(d)))
+        return d[:int(row_ptr[-1])]
+
+    def SearchForTriangulation(self, fv1, fv2, desc1, desc2, skip1=None, skip2=None):
+        """Hamming core of src/ORBmatcher.cc:1131-1456 (bCoarse semantics).  fv = (nodes, ptr, idx) CSR of a
+        DBoW2 FeatureVector.  Returns (nmatches, vMatchedPairs[(idx1, idx2)...] ascending idx1)."""
+        n1n, p1, i1 = (np.ascontiguousarray(x, np.int32) for x in fv1)
+        n2n, p2, i2 = (np.ascontiguousarray(x, np.int32) for x in fv2)
+        d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        s1 = np.zeros(d1.shape[0], np.uint8) if skip1 is None else np.ascontiguousarray(skip1, np.uint8)
+        s2 = np.zeros(d2.shape[0], np.uint8) if skip2 is None else np.ascontiguousarray(skip2, np.uint8)
+        m12 = np.full(d1.shape[0], -1, np.int32)
+        nm = C.c_int(0)
+        _check(self.L.orbx_search_for_triangulation(self.h, n1n.size, _p(n1n), _p(p1), _p(i1), n2n.size, _p(n2n), _p(p2), _p(i2),
+                                                    _p(d1), d1.shape[0], _p(d2), d2.shape[0], _p(s1), _p(s2), _p(m12),
+                                                    C.byref(nm)))
+        pairs = [(int(i), int(m12[i])) for i in np.nonzero(m12 >= 0)[0]]
+        return nm.value, pairs, m12
+
+    def grid_candidates(self, kps, bounds, qx, qy, qr, min_level, max_level, cand_cap=None):
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        qx, qy, qr = (np.ascontiguousarray(a, np.float32) for a in (qx, qy, qr))
+        mn, mx = np.ascontiguousarray(min_level, np.int32), np.ascontiguousarray(max_level, np.int32)
+        nq = qx.size
+        cap = int(cand_cap) if cand_cap else max(64 * nq, 1024)
+        row_ptr = np.zeros(nq + 1, np.int32); cand = np.zeros(cap, np.int32); n = C.c_int(0)
+        _check(self.L.orbx_grid_candidates(self.h, _p(kps), kps.size, C.c_float(bounds[0]), C.c_float(bounds[1]),
+                                           C.c_float(bounds[2]), C.c_float(bounds[3]), _p(qx), _p(qy), _p(qr), _p(mn), _p(mx), nq,
+                                           _p(row_ptr), _p(cand), cap, C.byref(n)))
+        return row_ptr, cand[:n.value]
+
+    def SearchByProjection(self, frame, points, th=3.0, bFarPoints=False, thFarPoints=50.0):
+        """src/ORBmatcher.cc:23-340 over plain arrays.
+        frame : dict(cam_off[ncam+1], kps, desc, bounds[ncam,4], scale_factors, occupied?, l2r?, r2l?)
+        points: dict(in_view[n,4], proj_x[n,4], proj_y[n,4], level[n,4], view_cos[n,4], desc[n,32], depth?, bad?, has_obs?)
+        Returns (nmatches, assigned[N])  — assigned[idx] = index of the map point written to F.mvpMapPoints[idx]."""
+        cam_off = np.ascontiguousarray(frame['cam_off'], np.int32)
+        ncam = cam_off.size - 1
+        N = int(cam_off[-1])
+        kps = np.ascontiguousarray(frame['kps'], KP_DTYPE); desc = np.ascontiguousarray(frame['desc'], np.uint8)
+        bounds = np.ascontiguousarray(frame['bounds'], np.float32).reshape(ncam, 4)
+        sf = np.ascontiguousarray(frame['scale_factors'], np.float32)
+        occ = None if frame.get('occupied') is None else np.ascontiguousarray(frame['occupied'], np.uint8)
+        l2r = None if frame.get('l2r') is None else np.ascontiguousarray(frame['l2r'], np.int32)
+        r2l = None if frame.get('r2l') is None else np.ascontiguousarray(frame['r2l'], np.int32)
+        nmp = int(np.asarray(points['in_view']).shape[0])
+        iv = np.ascontiguousarray(points['in_view'], np.uint8).reshape(nmp, 4)
+        px = np.ascontiguousarray(points['proj_x'], np.float32).reshape(nmp, 4)
+        py = np.ascontiguousarray(points['proj_y'], np.float32).reshape(nmp, 4)
+        lv = np.ascontiguousarray(points['level'], np.int32).reshape(nmp, 4)
+        vc = np.ascontiguousarray(points['view_cos'], np.float32).reshape(nmp, 4)
+        md = np.ascontiguousarray(points['desc'], np.uint8).reshape(nmp, 32)
+        depth = None if points.get('depth') is None else np.ascontiguousarray(points['depth'], np.float32)
+        bad = None if points.get('bad') is None else np.ascontiguousarray(points['bad'], np.uint8)
+        ho = None if points.get('has_obs') is None else np.ascontiguousarray(points['has_obs'], np.uint8)
+        assigned = np.full(max(N, 1), -1, np.int32); nm = C.c_int(0)
+        _check(self.L.orbx_search_by_projection(self.h, ncam, _p(cam_off), _p(kps), _p(desc), _p(bounds), _p(sf), sf.size, _p(occ),
+                                                _p(l2r), _p(r2l), nmp, _p(iv), _p(px), _p(py), _p(lv), _p(vc), _p(depth), _p(bad),
+                                                _p(ho), _p(md), C.c_float(th), int(bool(bFarPoints)), C.c_float(thFarPoints),
+                                                C.c_float(self.mfNNratio), _p(assigned), C.byref(nm)))
+        return nm.value, assigned[:N]
+
+
+def popc_peak(device=0):
+    v = C.c_double(0)
+    _check(lib().orbx_popc_peak(int(device), C.byref(v)))
+    return v.value

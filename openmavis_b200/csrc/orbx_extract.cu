@@ -1,0 +1,521 @@
+// orbx_extract.cu — host side of the extraction C ABI (include/orbx.h): geometry tables, device arenas,
+// launch sequence.  Replaces ORBextractor::ORBextractor / operator() (src/ORBextractor.cc:351-414, 987-1071).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/orbx_pattern.h"
+#include "orbx_extract_kernels.cuh"
+
+namespace orbx {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(orbx_status st, const std::string &msg) { g_err = msg; return (int)st; }
+const char *last_error() { return g_err.c_str(); }
+
+// src/ORBextractor.cc:362-376
+void level_scale_tables(float scale_factor, int nlevels, float *sf, float *inv_sf, float *sigma2, float *inv_sigma2) {
+    const double scale = scale_factor;   // `double scaleFactor` member (include/ORBextractor.h:70)
+    std::vector<float> s(nlevels), g(nlevels);
+    s[0] = 1.0f; g[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) { s[i] = (float)(s[i - 1] * scale); g[i] = s[i] * s[i]; }
+    for (int i = 0; i < nlevels; i++) {
+        if (sf) sf[i] = s[i];
+        if (sigma2) sigma2[i] = g[i];
+        if (inv_sf) inv_sf[i] = 1.0f / s[i];
+        if (inv_sigma2) inv_sigma2[i] = 1.0f / g[i];
+    }
+}
+
+// src/ORBextractor.cc:378-391
+void features_per_level(int nfeatures, float scale_factor, int nlevels, int *out) {
+    const double scale = scale_factor;
+    float factor = (float)(1.0f / scale);
+    float desired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        out[l] = (int)lrintf(desired);
+        sum += out[l];
+        desired *= factor;
+    }
+    out[nlevels - 1] = std::max(nfeatures - sum, 0);
+}
+
+}  // namespace orbx
+
+using namespace orbx;
+
+struct orbx_extractor {
+    int device = 0;
+    int width = 0, height = 0, max_images = 0, max_nfeatures = 0, nlevels = 0;
+    float scale_factor = 1.2f;
+    Geom G;
+    BlurTiles blur_tiles;
+    int blur_total_tiles = 0;
+    int fast_tile_pitch = 0;
+    size_t fast_smem = 0, oct_smem = 0;
+    int oct_list_cap = 0;
+    long long pyr_bytes_per_batch = 0;
+    std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    static constexpr int kRing = 16;                 // profiled calls kept for orbx_extractor_stage_ms
+    cudaEvent_t ev[kRing][ORBX_NUM_STAGES] = {};
+    int prof_calls = 0;                              // profiled calls since profiling was switched on
+    cudaEvent_t ev_staging = nullptr;
+    bool profiling = false, have_times = false;
+    int last_launches = 0, last_n = 0;
+
+    // device
+    uint8_t *d_in = nullptr, *d_pyr = nullptr, *d_blur = nullptr, *d_out_desc = nullptr;
+    ResizeTap *d_taps = nullptr;
+    signed char *d_pattern = nullptr;
+    uint32_t *d_cells = nullptr, *d_lin = nullptr, *d_lvl_kp = nullptr;
+    unsigned short *d_node = nullptr;
+    int *d_cell_cnt = nullptr, *d_cell_off = nullptr, *d_lin_n = nullptr, *d_lvl_n = nullptr, *d_slot = nullptr;
+    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr;
+    float *d_lvl_angle = nullptr;
+    orbx_kp *d_out_kp = nullptr;
+    orbx_image_params *d_params = nullptr;
+    // pinned staging
+    uint8_t *h_in = nullptr;
+    orbx_image_params *h_params = nullptr;
+    int *h_nfeat = nullptr;
+};
+
+static int build_geometry(orbx_extractor *ex, int fma_mode) {
+    Geom &G = ex->G;
+    memset(&G, 0, sizeof(G));
+    const int nl = ex->nlevels;
+    G.nlevels = nl; G.width = ex->width; G.height = ex->height; G.fma_mode = fma_mode;
+    ex->sf.resize(nl); ex->inv_sf.resize(nl); ex->sigma2.resize(nl); ex->inv_sigma2.resize(nl);
+    level_scale_tables(ex->scale_factor, nl, ex->sf.data(), ex->inv_sf.data(), ex->sigma2.data(), ex->inv_sigma2.data());
+    std::vector<int> nfeat(nl);
+    features_per_level(ex->max_nfeatures, ex->scale_factor, nl, nfeat.data());
+    long long plane_off = 0, cand_off = 0;
+    int cell_base = 0, kp_off = 0, tap_off = 0, max_cell_w = 0, max_cell_h = 0, max_list = 0;
+    for (int l = 0; l < nl; l++) {
+        LevelGeom &L = G.lv[l];
+        L.w = (int)lrintf((float)ex->width * ex->inv_sf[l]);      // src/ORBextractor.cc:1075-1076
+        L.h = (int)lrintf((float)ex->height * ex->inv_sf[l]);
+        if (L.w < 2 * kFastBorder + 36 || L.h < 2 * kFastBorder + 36)
+            return fail(ORBX_ERR_INVALID, "image too small for this pyramid depth (level " + std::to_string(l) + ")");
+        L.pitch = (kXO + L.w + kEdge + 127) & ~127;
+        L.rows = L.h + 2 * kEdge;
+        L.plane_bytes = (long long)L.pitch * L.rows;
+        L.plane_off = plane_off;
+        plane_off += L.plane_bytes * ex->max_images;
+        L.tap_x = tap_off; tap_off += L.w;
+        L.tap_y = tap_off; tap_off += L.h;
+        // src/ORBextractor.cc:709-724
+        L.max_bx = L.w - kEdge + 3; L.max_by = L.h - kEdge + 3;
+        const float width = (float)(L.max_bx - kFastBorder), height = (float)(L.max_by - kFastBorder);
+        L.n_cols = (int)(width / 35.f); L.n_rows = (int)(height / 35.f);
+        L.w_cell = (int)ceilf(width / L.n_cols); L.h_cell = (int)ceilf(height / L.n_rows);
+        L.cell_base = cell_base; cell_base += L.n_cols * L.n_rows;
+        L.cell_cap = ((L.w_cell + 1) / 2) * ((L.h_cell + 1) / 2);
+        L.cand_off = cand_off;
+        L.cand_cap = L.n_cols * L.n_rows * L.cell_cap;
+        cand_off += L.cand_cap;
+        max_cell_w = std::max(max_cell_w, L.w_cell + 6); max_cell_h = std::max(max_cell_h, L.h_cell + 6);
+        // src/ORBextractor.cc:505-507
+        L.n_ini = (int)roundf((float)(L.max_bx - kFastBorder) / (L.max_by - kFastBorder));
+        if (L.n_ini < 1) return fail(ORBX_ERR_INVALID, "image aspect ratio below 1:2 is not supported (nIni == 0)");
+        L.h_x = (float)(L.max_bx - kFastBorder) / L.n_ini;
+        const int lcap = oct_list_cap(nfeat[l], L.n_ini) + 8;
+        max_list = std::max(max_list, lcap);
+        L.kp_off = kp_off; L.kp_cap = lcap; kp_off += lcap;
+        L.scale = ex->sf[l];
+        L.patch = (float)(int)(31 * ex->sf[l]);                   // src/ORBextractor.cc:806
+        if (L.w + 2 * kFastBorder >= 4096 || L.h + 2 * kFastBorder >= 4096)
+            return fail(ORBX_ERR_INVALID, "images larger than 4000 px are not supported");
+    }
+    G.total_cells = cell_base; G.cand_per_image = cand_off; G.kp_per_image = kp_off; G.out_cap = kp_off;
+    ex->pyr_bytes_per_batch = plane_off;
+    ex->fast_tile_pitch = (max_cell_w + 3) & ~3;
+    ex->fast_smem = (size_t)2 * ex->fast_tile_pitch * max_cell_h;
+    ex->oct_list_cap = max_list;
+    ex->oct_smem = oct_work_bytes(max_list);
+    if (ex->oct_smem > 200 * 1024) return fail(ORBX_ERR_INVALID, "nfeatures too large for the quadtree workspace");
+    int tiles = 0;
+    for (int l = 0; l < nl; l++) {
+        ex->blur_tiles.base[l] = tiles;
+        tiles += ((G.lv[l].w + kBlurTW - 1) / kBlurTW) * ((G.lv[l].h + kBlurTH - 1) / kBlurTH);
+    }
+    for (int l = nl; l <= kMaxLevels; l++) ex->blur_tiles.base[l] = tiles;
+    ex->blur_total_tiles = tiles;
+    return ORBX_OK;
+}
+
+template <class T>
+static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+extern "C" {
+
+const char *orbx_last_error(void) { return orbx::last_error(); }
+const char *orbx_version(void) { return "orbx 0.1 (sm_100a)"; }
+
+int orbx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int orbx_features_per_level(int nfeatures, float scale_factor, int nlevels, int *out) {
+    if (!out || nlevels < 1 || nlevels > kMaxLevels || nfeatures < 0) return fail(ORBX_ERR_INVALID, "bad arguments");
+    features_per_level(nfeatures, scale_factor, nlevels, out);
+    return ORBX_OK;
+}
+
+void orbx_extractor_destroy(orbx_extractor *ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    cudaFree(ex->d_in); cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_out_desc); cudaFree(ex->d_taps);
+    cudaFree(ex->d_pattern); cudaFree(ex->d_cells); cudaFree(ex->d_lin); cudaFree(ex->d_lvl_kp); cudaFree(ex->d_node);
+    cudaFree(ex->d_cell_cnt); cudaFree(ex->d_cell_off); cudaFree(ex->d_lin_n); cudaFree(ex->d_lvl_n); cudaFree(ex->d_slot);
+    cudaFree(ex->d_n_kp); cudaFree(ex->d_n_mono); cudaFree(ex->d_nfeat); cudaFree(ex->d_lvl_angle); cudaFree(ex->d_out_kp);
+    cudaFree(ex->d_params);
+    if (ex->h_in) cudaFreeHost(ex->h_in);
+    if (ex->h_params) cudaFreeHost(ex->h_params);
+    if (ex->h_nfeat) cudaFreeHost(ex->h_nfeat);
+    for (auto &r : ex->ev) for (auto &e : r) if (e) cudaEventDestroy(e);
+    if (ex->ev_staging) cudaEventDestroy(ex->ev_staging);
+    if (ex->own_stream) cudaStreamDestroy(ex->own_stream);
+    delete ex;
+}
+
+int orbx_extractor_create(orbx_extractor **out, int device, int width, int height, int max_images, int max_nfeatures,
+                          float scale_factor, int nlevels, int fma_mode) {
+    if (!out) return fail(ORBX_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || max_images <= 0 || max_nfeatures <= 0 || nlevels < 1 || nlevels > kMaxLevels ||
+        !(scale_factor > 1.0f))
+        return fail(ORBX_ERR_INVALID, "bad extractor arguments");
+    int ndev = orbx_device_count();
+    if (ndev <= 0) return fail(ORBX_ERR_NO_DEVICE, "no CUDA device (liborbx has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(ORBX_ERR_NO_DEVICE, "device index out of range");
+    orbx_extractor *ex = new orbx_extractor();
+    ex->device = device; ex->width = width; ex->height = height; ex->max_images = max_images;
+    ex->max_nfeatures = max_nfeatures; ex->nlevels = nlevels; ex->scale_factor = scale_factor;
+    int st = build_geometry(ex, fma_mode ? 1 : 0);
+    if (st != ORBX_OK) { delete ex; return st; }
+    const Geom &G = ex->G;
+    const size_t B = (size_t)max_images;
+#define EX_CUDA(call)                                                                                 \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            std::string m = std::string(#call) + ": " + cudaGetErrorString(_e);                       \
+            orbx_extractor_destroy(ex);                                                               \
+            return fail(ORBX_ERR_CUDA, m);                                                            \
+        }                                                                                             \
+    } while (0)
+    EX_CUDA(cudaSetDevice(device));
+    EX_CUDA(cudaStreamCreateWithFlags(&ex->own_stream, cudaStreamNonBlocking));
+    ex->stream = ex->own_stream;
+    for (auto &r : ex->ev) for (auto &e : r) EX_CUDA(cudaEventCreate(&e));
+    EX_CUDA(cudaEventCreateWithFlags(&ex->ev_staging, cudaEventDisableTiming));
+    EX_CUDA(dalloc(&ex->d_in, B * width * height));
+    EX_CUDA(dalloc(&ex->d_pyr, (size_t)ex->pyr_bytes_per_batch));
+    EX_CUDA(dalloc(&ex->d_blur, (size_t)ex->pyr_bytes_per_batch));
+    EX_CUDA(dalloc(&ex->d_cells, B * G.cand_per_image));
+    EX_CUDA(dalloc(&ex->d_lin, B * G.cand_per_image));
+    EX_CUDA(dalloc(&ex->d_node, B * G.cand_per_image));
+    EX_CUDA(dalloc(&ex->d_cell_cnt, B * G.total_cells));
+    EX_CUDA(dalloc(&ex->d_cell_off, B * G.total_cells));
+    EX_CUDA(dalloc(&ex->d_lin_n, B * nlevels));
+    EX_CUDA(dalloc(&ex->d_lvl_n, B * nlevels));
+    EX_CUDA(dalloc(&ex->d_nfeat, B * nlevels));
+    EX_CUDA(dalloc(&ex->d_lvl_kp, B * G.kp_per_image));
+    EX_CUDA(dalloc(&ex->d_lvl_angle, B * G.kp_per_image));
+    EX_CUDA(dalloc(&ex->d_slot, B * G.kp_per_image));
+    EX_CUDA(dalloc(&ex->d_out_kp, B * G.out_cap));
+    EX_CUDA(dalloc(&ex->d_out_desc, B * G.out_cap * 32));
+    EX_CUDA(dalloc(&ex->d_n_kp, B));
+    EX_CUDA(dalloc(&ex->d_n_mono, B));
+    EX_CUDA(dalloc(&ex->d_params, B));
+    EX_CUDA(cudaMallocHost((void **)&ex->h_in, B * width * height));
+    EX_CUDA(cudaMallocHost((void **)&ex->h_params, B * sizeof(orbx_image_params)));
+    EX_CUDA(cudaMallocHost((void **)&ex->h_nfeat, B * nlevels * sizeof(int)));
+    EX_CUDA(cudaMemsetAsync(ex->d_pyr, 0, (size_t)ex->pyr_bytes_per_batch, ex->stream));
+    EX_CUDA(cudaMemsetAsync(ex->d_blur, 0, (size_t)ex->pyr_bytes_per_batch, ex->stream));
+    EX_CUDA(cudaMemsetAsync(ex->d_n_kp, 0, B * sizeof(int), ex->stream));
+    EX_CUDA(cudaMemsetAsync(ex->d_n_mono, 0, B * sizeof(int), ex->stream));
+    EX_CUDA(cudaMemsetAsync(ex->d_lvl_n, 0, B * nlevels * sizeof(int), ex->stream));
+    EX_CUDA(cudaMemsetAsync(ex->d_lin_n, 0, B * nlevels * sizeof(int), ex->stream));
+    // resize taps
+    {
+        int ntap = 0;
+        for (int l = 0; l < nlevels; l++) ntap += G.lv[l].w + G.lv[l].h;
+        std::vector<ResizeTap> taps(ntap);
+        for (int l = 1; l < nlevels; l++) {
+            orbx_resize_taps(G.lv[l - 1].w, G.lv[l].w, taps.data() + G.lv[l].tap_x);
+            orbx_resize_taps(G.lv[l - 1].h, G.lv[l].h, taps.data() + G.lv[l].tap_y);
+        }
+        EX_CUDA(dalloc(&ex->d_taps, (size_t)ntap));
+        EX_CUDA(cudaMemcpy(ex->d_taps, taps.data(), ntap * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+        static const signed char pat[1024] = {ORBX_PATTERN_VALUES};
+        EX_CUDA(dalloc(&ex->d_pattern, (size_t)1024));
+        EX_CUDA(cudaMemcpy(ex->d_pattern, pat, 1024, cudaMemcpyHostToDevice));
+    }
+    if (ex->fast_smem > 48 * 1024)
+        EX_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fast_smem));
+    if (ex->oct_smem > 48 * 1024)
+        EX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->oct_smem));
+    EX_CUDA(cudaStreamSynchronize(ex->stream));
+#undef EX_CUDA
+    *out = ex;
+    return ORBX_OK;
+}
+
+int orbx_extractor_set_stream(orbx_extractor *ex, void *cuda_stream) {
+    if (!ex) return fail(ORBX_ERR_INVALID, "NULL handle");
+    ex->stream = cuda_stream ? (cudaStream_t)cuda_stream : ex->own_stream;
+    return ORBX_OK;
+}
+
+int orbx_extractor_capacity(const orbx_extractor *ex) { return ex ? ex->G.out_cap : (int)ORBX_ERR_INVALID; }
+
+int orbx_extractor_tables(const orbx_extractor *ex, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2,
+                          int *level_w, int *level_h) {
+    if (!ex) return fail(ORBX_ERR_INVALID, "NULL handle");
+    for (int l = 0; l < ex->nlevels; l++) {
+        if (scale) scale[l] = ex->sf[l];
+        if (inv_scale) inv_scale[l] = ex->inv_sf[l];
+        if (sigma2) sigma2[l] = ex->sigma2[l];
+        if (inv_sigma2) inv_sigma2[l] = ex->inv_sigma2[l];
+        if (level_w) level_w[l] = ex->G.lv[l].w;
+        if (level_h) level_h[l] = ex->G.lv[l].h;
+    }
+    return ORBX_OK;
+}
+
+int orbx_extractor_set_profiling(orbx_extractor *ex, int enabled) {
+    if (!ex) return fail(ORBX_ERR_INVALID, "NULL handle");
+    ex->profiling = enabled != 0; ex->have_times = false; ex->prof_calls = 0;
+    return ORBX_OK;
+}
+
+int orbx_extractor_last_launches(const orbx_extractor *ex) { return ex ? ex->last_launches : 0; }
+
+// Enqueue the whole pipeline for n images whose pixels are at d_images (device, tightly packed).
+static int enqueue(orbx_extractor *ex, int n, const uint8_t *d_images, const orbx_image_params *params) {
+    if (n <= 0 || n > ex->max_images) return fail(ORBX_ERR_CAPACITY, "n_images exceeds the handle's max_images");
+    const Geom &G = ex->G;
+    const int nl = ex->nlevels;
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    // pinned staging of the per-image parameters may still be in flight from the previous call
+    ORBX_CUDA(cudaEventSynchronize(ex->ev_staging));
+    for (int i = 0; i < n; i++) {
+        const orbx_image_params &p = params[i];
+        if (p.nfeatures <= 0 || p.nfeatures > ex->max_nfeatures)
+            return fail(ORBX_ERR_INVALID, "params[i].nfeatures outside (0, max_nfeatures]");
+        ex->h_params[i] = p;
+        features_per_level(p.nfeatures, ex->scale_factor, nl, ex->h_nfeat + (size_t)i * nl);
+        for (int l = 0; l < nl; l++)
+            if (oct_list_cap(ex->h_nfeat[(size_t)i * nl + l], G.lv[l].n_ini) > G.lv[l].kp_cap)
+                return fail(ORBX_ERR_CAPACITY, "per-level feature target exceeds the handle's capacity");
+    }
+    cudaStream_t s = ex->stream;
+    ORBX_CUDA(cudaMemcpyAsync(ex->d_params, ex->h_params, n * sizeof(orbx_image_params), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaMemcpyAsync(ex->d_nfeat, ex->h_nfeat, (size_t)n * nl * sizeof(int), cudaMemcpyHostToDevice, s));
+    ORBX_CUDA(cudaEventRecord(ex->ev_staging, s));
+    int launches = 0;
+    const bool prof = ex->profiling;
+    cudaEvent_t *ev = ex->ev[ex->prof_calls % orbx_extractor::kRing];
+    if (prof) ORBX_CUDA(cudaEventRecord(ev[0], s));
+    {   // pyramid
+        const LevelGeom &L0 = G.lv[0];
+        const int chunks = (kXO + L0.w + kEdge + 15) >> 4;
+        dim3 grid((chunks * L0.rows + 255) / 256, n);
+        k_level0<<<grid, 256, 0, s>>>(d_images, (long long)ex->width * ex->height, ex->width, ex->d_pyr, L0);
+        launches++;
+        for (int l = 1; l < nl; l++) {
+            const LevelGeom &D = G.lv[l];
+            const int ch = (kXO + D.w + kEdge + 3) >> 2;
+            dim3 g((ch * D.rows + 255) / 256, n);
+            k_resize<<<g, 256, 0, s>>>(ex->d_pyr, G.lv[l - 1], D, ex->d_taps);
+            launches++;
+        }
+    }
+    if (prof) ORBX_CUDA(cudaEventRecord(ev[1], s));
+    k_blur<<<dim3(ex->blur_total_tiles, n), 256, 0, s>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles);
+    launches++;
+    if (prof) ORBX_CUDA(cudaEventRecord(ev[2], s));
+    k_fast<<<dim3(G.total_cells, n), 256, ex->fast_smem, s>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt,
+                                                              ex->fast_tile_pitch);
+    launches++;
+    if (prof) ORBX_CUDA(cudaEventRecord(ev[3], s));
+    k_octree<<<dim3(nl, n), 512, ex->oct_smem, s>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
+                                                    ex->d_lin_n, ex->d_node, ex->d_slot, ex->d_lvl_kp, ex->d_lvl_n,
+                                                    ex->oct_list_cap);
+    launches++;
+    if (prof) ORBX_CUDA(cudaEventRecord(ev[4], s));
+    k_slots<<<n, 256, 0, s>>>(G, ex->d_params, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot, ex->d_n_kp, ex->d_n_mono);
+    launches++;
+    if (prof) ORBX_CUDA(cudaEventRecord(ev[5], s));
+    k_orient_desc<<<dim3((G.kp_per_image * 32 + 255) / 256, n), 256, 0, s>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern,
+                                                                             ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,
+                                                                             ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc);
+    launches++;
+    if (prof) { ORBX_CUDA(cudaEventRecord(ev[6], s)); ex->have_times = true; ex->prof_calls++; }
+    ORBX_CUDA(cudaGetLastError());
+    ex->last_launches = launches;
+    ex->last_n = n;
+    return ORBX_OK;
+}
+
+int orbx_extract_batch_device(orbx_extractor *ex, int n_images, const uint8_t *d_images, const orbx_image_params *params) {
+    if (!ex || !d_images || !params) return fail(ORBX_ERR_INVALID, "NULL argument");
+    return enqueue(ex, n_images, d_images, params);
+}
+
+int orbx_extract_fetch(orbx_extractor *ex, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono) {
+    if (!ex) return fail(ORBX_ERR_INVALID, "NULL handle");
+    const int n = ex->last_n;
+    if (n <= 0) return fail(ORBX_ERR_INVALID, "no results to fetch");
+    if (cap < ex->G.out_cap && (kps || desc)) return fail(ORBX_ERR_CAPACITY, "cap smaller than orbx_extractor_capacity()");
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    cudaStream_t s = ex->stream;
+    const int oc = ex->G.out_cap;
+    if (kps)
+        ORBX_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orbx_kp), ex->d_out_kp, (size_t)oc * sizeof(orbx_kp),
+                                    (size_t)oc * sizeof(orbx_kp), n, cudaMemcpyDeviceToHost, s));
+    if (desc)
+        ORBX_CUDA(cudaMemcpy2DAsync(desc, (size_t)cap * 32, ex->d_out_desc, (size_t)oc * 32, (size_t)oc * 32, n,
+                                    cudaMemcpyDeviceToHost, s));
+    if (n_kp) ORBX_CUDA(cudaMemcpyAsync(n_kp, ex->d_n_kp, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (n_mono) ORBX_CUDA(cudaMemcpyAsync(n_mono, ex->d_n_mono, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+int orbx_extract_device_results(orbx_extractor *ex, const orbx_kp **d_kps, const uint8_t **d_desc, const int **d_n_kp,
+                                const int **d_n_mono) {
+    if (!ex) return fail(ORBX_ERR_INVALID, "NULL handle");
+    if (d_kps) *d_kps = ex->d_out_kp;
+    if (d_desc) *d_desc = ex->d_out_desc;
+    if (d_n_kp) *d_n_kp = ex->d_n_kp;
+    if (d_n_mono) *d_n_mono = ex->d_n_mono;
+    return ORBX_OK;
+}
+
+int orbx_extract_batch(orbx_extractor *ex, int n_images, const uint8_t *const *images, const int *strides,
+                       const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono) {
+    if (!ex || !images || !params) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (n_images <= 0 || n_images > ex->max_images) return fail(ORBX_ERR_CAPACITY, "n_images exceeds the handle's max_images");
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    const size_t img_bytes = (size_t)ex->width * ex->height;
+    cudaStream_t s = ex->stream;
+    for (int i = 0; i < n_images; i++) {
+        if (!images[i]) return fail(ORBX_ERR_EMPTY, "empty image");
+        const int st = strides ? strides[i] : ex->width;
+        if (st < ex->width) return fail(ORBX_ERR_INVALID, "stride smaller than width");
+        ORBX_CUDA(cudaMemcpy2DAsync(ex->d_in + i * img_bytes, ex->width, images[i], st, ex->width, ex->height,
+                                    cudaMemcpyHostToDevice, s));
+    }
+    int st = enqueue(ex, n_images, ex->d_in, params);
+    if (st != ORBX_OK) return st;
+    return orbx_extract_fetch(ex, kps, desc, cap, n_kp, n_mono);
+}
+
+int orbx_extract(orbx_extractor *ex, const uint8_t *image, int stride, const orbx_image_params *params, orbx_kp *kps,
+                 uint8_t *desc, int cap, int *n_kp) {
+    if (!image) return -1;   // src/ORBextractor.cc:994-995
+    int mono = 0, nk = 0;
+    const uint8_t *imgs[1] = {image};
+    int st = orbx_extract_batch(ex, 1, imgs, &stride, params, kps, desc, cap, &nk, &mono);
+    if (st != ORBX_OK) return st;
+    if (n_kp) *n_kp = nk;
+    return mono;
+}
+
+int orbx_extractor_pyramid_level(orbx_extractor *ex, int image, int level, int with_border, uint8_t *dst, int dst_stride) {
+    if (!ex || !dst) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (image < 0 || image >= ex->max_images || level < 0 || level >= ex->nlevels) return fail(ORBX_ERR_INVALID, "bad index");
+    const LevelGeom &L = ex->G.lv[level];
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    const uint8_t *p = ex->d_pyr + L.plane_off + (long long)image * L.plane_bytes;
+    const int w = with_border ? L.w + 2 * kEdge : L.w, h = with_border ? L.h + 2 * kEdge : L.h;
+    if (dst_stride < w) return fail(ORBX_ERR_INVALID, "dst_stride too small");
+    const uint8_t *src = with_border ? p + (kXO - kEdge) : p + (long long)kYO * L.pitch + kXO;
+    ORBX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, src, L.pitch, w, h, cudaMemcpyDeviceToHost, ex->stream));
+    ORBX_CUDA(cudaStreamSynchronize(ex->stream));
+    return ORBX_OK;
+}
+
+int orbx_debug_blur_level(orbx_extractor *ex, int image, int level, uint8_t *dst, int dst_stride) {
+    if (!ex || !dst) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (image < 0 || image >= ex->max_images || level < 0 || level >= ex->nlevels) return fail(ORBX_ERR_INVALID, "bad index");
+    const LevelGeom &L = ex->G.lv[level];
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    const uint8_t *p = ex->d_blur + L.plane_off + (long long)image * L.plane_bytes + (long long)kYO * L.pitch + kXO;
+    ORBX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, p, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, ex->stream));
+    ORBX_CUDA(cudaStreamSynchronize(ex->stream));
+    return ORBX_OK;
+}
+
+int orbx_debug_candidates(orbx_extractor *ex, int image, int level, int *xs, int *ys, int *scores, int cap, int *n) {
+    if (!ex || !n) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (image < 0 || image >= ex->max_images || level < 0 || level >= ex->nlevels) return fail(ORBX_ERR_INVALID, "bad index");
+    const LevelGeom &L = ex->G.lv[level];
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    int cnt = 0;
+    ORBX_CUDA(cudaStreamSynchronize(ex->stream));
+    ORBX_CUDA(cudaMemcpy(&cnt, ex->d_lin_n + image * ex->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    const int m = std::min(cnt, cap);
+    if (m > 0 && xs && ys && scores) {
+        std::vector<uint32_t> v(m);
+        ORBX_CUDA(cudaMemcpy(v.data(), ex->d_lin + (long long)image * ex->G.cand_per_image + L.cand_off, m * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) { xs[i] = cand_x(v[i]); ys[i] = cand_y(v[i]); scores[i] = cand_score(v[i]); }
+    }
+    return ORBX_OK;
+}
+
+int orbx_debug_level_keypoints(orbx_extractor *ex, int image, int level, orbx_kp *kps, int cap, int *n) {
+    if (!ex || !n) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (image < 0 || image >= ex->max_images || level < 0 || level >= ex->nlevels) return fail(ORBX_ERR_INVALID, "bad index");
+    const LevelGeom &L = ex->G.lv[level];
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    ORBX_CUDA(cudaStreamSynchronize(ex->stream));
+    int cnt = 0;
+    ORBX_CUDA(cudaMemcpy(&cnt, ex->d_lvl_n + image * ex->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    const int m = std::min(cnt, cap);
+    if (m > 0 && kps) {
+        std::vector<uint32_t> v(m);
+        std::vector<float> a(m);
+        const long long off = (long long)image * ex->G.kp_per_image + L.kp_off;
+        ORBX_CUDA(cudaMemcpy(v.data(), ex->d_lvl_kp + off, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        ORBX_CUDA(cudaMemcpy(a.data(), ex->d_lvl_angle + off, m * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) {
+            kps[i].x = (float)cand_x(v[i]); kps[i].y = (float)cand_y(v[i]); kps[i].size = L.patch; kps[i].angle = a[i];
+            kps[i].response = (float)cand_score(v[i]); kps[i].octave = level; kps[i].class_id = -1;
+        }
+    }
+    return ORBX_OK;
+}
+
+int orbx_extractor_stage_ms(orbx_extractor *ex, float *ms) {
+    if (!ex || !ms) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (!ex->have_times) return fail(ORBX_ERR_INVALID, "profiling was not enabled for the last call");
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    // average over the profiled calls still in the ring (at most kRing most recent ones)
+    const int have = std::min(ex->prof_calls, (int)orbx_extractor::kRing);
+    for (int i = 0; i < ORBX_NUM_STAGES; i++) ms[i] = 0.f;
+    for (int c = 0; c < have; c++) {
+        cudaEvent_t *ev = ex->ev[(ex->prof_calls - 1 - c) % orbx_extractor::kRing];
+        ORBX_CUDA(cudaEventSynchronize(ev[6]));
+        for (int i = 0; i < 6; i++) { float t = 0; ORBX_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1])); ms[i] += t / have; }
+        float t = 0; ORBX_CUDA(cudaEventElapsedTime(&t, ev[0], ev[6])); ms[6] += t / have;
+    }
+    return ORBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,499 @@
+// orbx_match.cu — host side of the matching C ABI (include/orbx.h).
+// Replaces the Hamming cores of ORBmatcher (src/ORBmatcher.cc) and cv::BFMatcher::knnMatch (src/Frame.cc:1427,1483).
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "orbx_match_kernels.cuh"
+#include "orbx_sbp_kernels.cuh"
+
+using namespace orbx;
+
+namespace {
+// growable device buffer
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max<size_t>(bytes + bytes / 4, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() { return (T *)p; }
+};
+}  // namespace
+
+struct orbx_matcher {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    bool timed = false;
+    DBuf b[24];
+};
+
+#define M_CUDA ORBX_CUDA
+
+static int upload(orbx_matcher *m, DBuf &buf, const void *src, size_t bytes) {
+    M_CUDA(buf.ensure(bytes));
+    if (bytes) M_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, m->stream));
+    return ORBX_OK;
+}
+
+static int knn2_launch(orbx_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int *d_idx, int *d_dist) {
+    if (nt >= (1 << kKeyShift)) return fail(ORBX_ERR_INVALID, "knn2: more than 8388607 train rows are not supported");
+    const int per_block = kKnnThreads * kKnnQPT;
+    const int qblocks = (nq + per_block - 1) / per_block;
+    // split the train set so that small problems still fill the machine (2 waves of 148 SMs x resident CTAs)
+    int slices = std::max(1, std::min((2 * m->sm_count * 4 + qblocks - 1) / qblocks, (nt + kKnnTile - 1) / kKnnTile));
+    int slice_rows = ((nt + slices - 1) / slices + kKnnTile - 1) / kKnnTile * kKnnTile;
+    slices = (nt + slice_rows - 1) / slice_rows;
+    M_CUDA(m->b[0].ensure((size_t)slices * nq * sizeof(uint2)));
+    k_knn2<<<dim3(qblocks, slices), kKnnThreads, 0, m->stream>>>((const uint4 *)d_q, nq, (const uint4 *)d_t, nt, slice_rows,
+                                                                 m->b[0].as<uint2>());
+    k_knn2_merge<<<(nq + 255) / 256, 256, 0, m->stream>>>(m->b[0].as<uint2>(), nq, slices, d_idx, d_dist);
+    m->last_launches += 2;
+    M_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" {
+
+int orbx_matcher_create(orbx_matcher **out, int device) {
+    if (!out) return fail(ORBX_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    const int ndev = orbx_device_count();
+    if (ndev <= 0) return fail(ORBX_ERR_NO_DEVICE, "no CUDA device (liborbx has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(ORBX_ERR_NO_DEVICE, "device index out of range");
+    M_CUDA(cudaSetDevice(device));
+    orbx_matcher *m = new orbx_matcher();
+    m->device = device;
+    cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess) {
+        delete m;
+        return fail(ORBX_ERR_CUDA, "stream/event creation failed");
+    }
+    m->stream = m->own_stream;
+    *out = m;
+    return ORBX_OK;
+}
+
+void orbx_matcher_destroy(orbx_matcher *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (auto &b : m->b) b.release();
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    delete m;
+}
+
+int orbx_matcher_set_stream(orbx_matcher *m, void *cuda_stream) {
+    if (!m) return fail(ORBX_ERR_INVALID, "NULL handle");
+    m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+    return ORBX_OK;
+}
+
+int orbx_matcher_last_launches(const orbx_matcher *m) { return m ? m->last_launches : 0; }
+
+int orbx_matcher_last_ms(orbx_matcher *m, float *ms) {
+    if (!m || !ms) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (!m->timed) return fail(ORBX_ERR_INVALID, "no timed call yet");
+    M_CUDA(cudaEventSynchronize(m->ev1));
+    M_CUDA(cudaEventElapsedTime(ms, m->ev0, m->ev1));
+    return ORBX_OK;
+}
+
+int orbx_descriptor_distance(int device, const uint8_t *a, const uint8_t *b, int n, int *dist) {
+    if (!a || !b || !dist || n < 0) return fail(ORBX_ERR_INVALID, "bad arguments");
+    if (orbx_device_count() <= device || device < 0) return fail(ORBX_ERR_NO_DEVICE, "no such CUDA device");
+    if (n == 0) return ORBX_OK;
+    M_CUDA(cudaSetDevice(device));
+    uint8_t *da = nullptr, *db = nullptr; int *dd = nullptr;
+    M_CUDA(cudaMalloc((void **)&da, (size_t)n * 32));
+    M_CUDA(cudaMalloc((void **)&db, (size_t)n * 32));
+    M_CUDA(cudaMalloc((void **)&dd, (size_t)n * sizeof(int)));
+    M_CUDA(cudaMemcpy(da, a, (size_t)n * 32, cudaMemcpyHostToDevice));
+    M_CUDA(cudaMemcpy(db, b, (size_t)n * 32, cudaMemcpyHostToDevice));
+    k_pair_distance<<<(n + 255) / 256, 256>>>((const uint4 *)da, (const uint4 *)db, n, dd);
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaMemcpy(dist, dd, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    return ORBX_OK;
+}
+
+int orbx_knn2_device(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt, int *d_idx, int *d_dist) {
+    if (!m || nq < 0 || nt < 0 || !d_idx || !d_dist) return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    if (nq == 0) return ORBX_OK;
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    if (nt == 0) {
+        M_CUDA(cudaMemsetAsync(d_idx, 0xFF, (size_t)nq * 2 * sizeof(int), m->stream));
+        M_CUDA(cudaMemsetAsync(d_dist, 0xFF, (size_t)nq * 2 * sizeof(int), m->stream));
+    } else {
+        int st = knn2_launch(m, d_query, nq, d_train, nt, d_idx, d_dist);
+        if (st != ORBX_OK) return st;
+    }
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    return ORBX_OK;
+}
+
+int orbx_knn2(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt, int *idx, int *dist) {
+    if (!m || nq < 0 || nt < 0 || !idx || !dist || (nq && !query) || (nt && !train)) return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    if (nq == 0) return ORBX_OK;
+    int st;
+    if ((st = upload(m, m->b[1], query, (size_t)nq * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], train, (size_t)nt * 32)) != ORBX_OK) return st;
+    M_CUDA(m->b[3].ensure((size_t)nq * 2 * sizeof(int)));
+    M_CUDA(m->b[4].ensure((size_t)nq * 2 * sizeof(int)));
+    st = orbx_knn2_device(m, m->b[1].as<uint8_t>(), nq, m->b[2].as<uint8_t>(), nt, m->b[3].as<int>(), m->b[4].as<int>());
+    if (st != ORBX_OK) return st;
+    M_CUDA(cudaMemcpyAsync(idx, m->b[3].p, (size_t)nq * 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(dist, m->b[4].p, (size_t)nq * 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_ratio_test(const int *dist, int nq, double ratio, uint8_t *keep) {
+    if (!dist || !keep || nq < 0) return fail(ORBX_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < nq; i++)   // (*it)[0].distance < (*it)[1].distance * 0.7 : float * double
+        keep[i] = (dist[2 * i] >= 0 && dist[2 * i + 1] >= 0 && (double)(float)dist[2 * i] < (double)(float)dist[2 * i + 1] * ratio) ? 1 : 0;
+    return ORBX_OK;
+}
+
+static int match_csr_impl(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt, const int *row_ptr,
+                          const int *cand, int *best_idx, int *best_dist, int *second_dist, int *best_pos, int *second_pos,
+                          int *all_dist) {
+    if (!m || nq < 0 || nt < 0 || !row_ptr || (nq && !query)) return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    if (nq == 0) return ORBX_OK;
+    const int total = row_ptr[nq];
+    if (total < 0 || (total && (!cand || !train))) return fail(ORBX_ERR_INVALID, "bad candidate lists");
+    for (int k = 0; k < total; k++)
+        if (cand[k] < 0 || cand[k] >= nt) return fail(ORBX_ERR_INVALID, "candidate index out of range");
+    int st;
+    if ((st = upload(m, m->b[1], query, (size_t)nq * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], train, (size_t)nt * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[5], row_ptr, (size_t)(nq + 1) * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[6], cand, (size_t)total * sizeof(int))) != ORBX_OK) return st;
+    M_CUDA(m->b[7].ensure((size_t)nq * 5 * sizeof(int)));
+    M_CUDA(m->b[8].ensure((size_t)std::max(total, 1) * sizeof(int)));
+    int *o = m->b[7].as<int>();
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    k_match_csr<<<(nq + 127) / 128, 128, 0, m->stream>>>((const uint4 *)m->b[1].p, nq, (const uint4 *)m->b[2].p, m->b[5].as<int>(),
+                                                         m->b[6].as<int>(), best_idx ? o : nullptr, o + nq, o + 2 * nq, o + 3 * nq,
+                                                         o + 4 * nq, all_dist ? m->b[8].as<int>() : nullptr);
+    m->last_launches = 1;
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    const size_t nb = (size_t)nq * sizeof(int);
+    if (best_idx) {
+        M_CUDA(cudaMemcpyAsync(best_idx, o, nb, cudaMemcpyDeviceToHost, m->stream));
+        M_CUDA(cudaMemcpyAsync(best_dist, o + nq, nb, cudaMemcpyDeviceToHost, m->stream));
+        M_CUDA(cudaMemcpyAsync(second_dist, o + 2 * nq, nb, cudaMemcpyDeviceToHost, m->stream));
+        M_CUDA(cudaMemcpyAsync(best_pos, o + 3 * nq, nb, cudaMemcpyDeviceToHost, m->stream));
+        M_CUDA(cudaMemcpyAsync(second_pos, o + 4 * nq, nb, cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (all_dist && total) M_CUDA(cudaMemcpyAsync(all_dist, m->b[8].p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_match_csr(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt, const int *row_ptr, const int *cand,
+                   int *best_idx, int *best_dist, int *second_dist, int *best_pos, int *second_pos) {
+    if (!best_idx || !best_dist || !second_dist || !best_pos || !second_pos) return fail(ORBX_ERR_INVALID, "NULL output");
+    return match_csr_impl(m, query, nq, train, nt, row_ptr, cand, best_idx, best_dist, second_dist, best_pos, second_pos, nullptr);
+}
+
+int orbx_match_csr_dists(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *train, int nt, const int *row_ptr,
+                         const int *cand, int *dist) {
+    if (!dist) return fail(ORBX_ERR_INVALID, "NULL output");
+    return match_csr_impl(m, query, nq, train, nt, row_ptr, cand, nullptr, nullptr, nullptr, nullptr, nullptr, dist);
+}
+
+int orbx_search_for_triangulation(orbx_matcher *m, int nn1, const int *nodes1, const int *ptr1, const int *idx1, int nn2,
+                                  const int *nodes2, const int *ptr2, const int *idx2, const uint8_t *desc1, int n1,
+                                  const uint8_t *desc2, int n2, const uint8_t *skip1, const uint8_t *skip2, int *match12,
+                                  int *nmatches) {
+    if (!m || !match12 || n1 < 0 || n2 < 0 || nn1 < 0 || nn2 < 0) return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    if (nmatches) *nmatches = 0;
+    // merge-walk of the two FeatureVectors (src/ORBmatcher.cc:1218-1222, 1420-1427) — host, O(nn1 + nn2)
+    std::vector<int> row_q, row_begin, row_len;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int k = ptr1[a]; k < ptr1[a + 1]; k++) {
+                const int i1 = idx1[k];
+                if (i1 < 0 || i1 >= n1) return fail(ORBX_ERR_INVALID, "idx1 out of range");
+                if (skip1 && skip1[i1]) continue;
+                row_q.push_back(i1); row_begin.push_back(ptr2[b]); row_len.push_back(ptr2[b + 1] - ptr2[b]);
+            }
+            a++; b++;
+        } else if (nodes1[a] < nodes2[b]) {
+            a = (int)(std::lower_bound(nodes1 + a, nodes1 + nn1, nodes2[b]) - nodes1);
+        } else {
+            b = (int)(std::lower_bound(nodes2 + b, nodes2 + nn2, nodes1[a]) - nodes2);
+        }
+    }
+    const int nrows = (int)row_q.size();
+    if (nrows == 0) return ORBX_OK;
+    const int tot2 = ptr2[nn2];
+    for (int k = 0; k < tot2; k++)
+        if (idx2[k] < 0 || idx2[k] >= n2) return fail(ORBX_ERR_INVALID, "idx2 out of range");
+    std::vector<uint8_t> zero;
+    if (!skip2) { zero.assign(n2, 0); skip2 = zero.data(); }
+    int st;
+    if ((st = upload(m, m->b[1], desc1, (size_t)n1 * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], desc2, (size_t)n2 * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[9], row_q.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[10], row_begin.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[11], row_len.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[12], idx2, (size_t)tot2 * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[13], skip2, (size_t)n2)) != ORBX_OK) return st;
+    M_CUDA(m->b[14].ensure((size_t)n1 * sizeof(int)));
+    M_CUDA(cudaMemsetAsync(m->b[14].p, 0xFF, (size_t)n1 * sizeof(int), m->stream));
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    k_match_groups<<<(nrows + 127) / 128, 128, 0, m->stream>>>((const uint4 *)m->b[1].p, (const uint4 *)m->b[2].p, nrows,
+                                                               m->b[9].as<int>(), m->b[10].as<int>(), m->b[11].as<int>(),
+                                                               m->b[12].as<int>(), m->b[13].as<uint8_t>(), 50 /* TH_LOW */,
+                                                               m->b[14].as<int>());
+    m->last_launches = 1;
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    M_CUDA(cudaMemcpyAsync(match12, m->b[14].p, (size_t)n1 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    int nm = 0;
+    for (int i = 0; i < n1; i++) nm += match12[i] >= 0;
+    if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
+// builds the device grid of one camera into buffers b[base .. base+3]; returns device pointers
+static int grid_build(orbx_matcher *m, int base, const orbx_kp *d_kps, int n, float min_x, float min_y, float inv_w, float inv_h,
+                      int **cell_start, int **cell_items) {
+    const int nc = kGridCols * kGridRows;
+    M_CUDA(m->b[base].ensure((size_t)nc * sizeof(int)));            // counts
+    M_CUDA(m->b[base + 1].ensure((size_t)(nc + 1) * sizeof(int)));  // starts
+    M_CUDA(m->b[base + 2].ensure((size_t)nc * sizeof(int)));        // cursors
+    M_CUDA(m->b[base + 3].ensure((size_t)std::max(n, 1) * sizeof(int)));
+    M_CUDA(cudaMemsetAsync(m->b[base].p, 0, (size_t)nc * sizeof(int), m->stream));
+    if (n > 0) k_grid_count<<<(n + 255) / 256, 256, 0, m->stream>>>(d_kps, n, min_x, min_y, inv_w, inv_h, m->b[base].as<int>());
+    k_grid_scan<<<1, 1024, 0, m->stream>>>(m->b[base].as<int>(), m->b[base + 1].as<int>(), m->b[base + 2].as<int>());
+    if (n > 0) {
+        k_grid_fill<<<(n + 255) / 256, 256, 0, m->stream>>>(d_kps, n, min_x, min_y, inv_w, inv_h, m->b[base + 1].as<int>(),
+                                                            m->b[base + 2].as<int>(), m->b[base + 3].as<int>());
+        k_grid_sort_cells<<<(nc + 255) / 256, 256, 0, m->stream>>>(m->b[base + 1].as<int>(), m->b[base + 3].as<int>());
+    }
+    m->last_launches += n > 0 ? 4 : 1;
+    M_CUDA(cudaGetLastError());
+    *cell_start = m->b[base + 1].as<int>();
+    *cell_items = m->b[base + 3].as<int>();
+    return ORBX_OK;
+}
+
+int orbx_grid_candidates(orbx_matcher *m, const orbx_kp *kps, int n, float min_x, float max_x, float min_y, float max_y,
+                         const float *qx, const float *qy, const float *qr, const int *min_level, const int *max_level, int nq,
+                         int *row_ptr, int *cand, int cand_cap, int *n_cand) {
+    if (!m || n < 0 || nq < 0 || !row_ptr || !n_cand || !(max_x > min_x) || !(max_y > min_y)) return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    const float inv_w = (float)kGridCols / (max_x - min_x), inv_h = (float)kGridRows / (max_y - min_y);   // Frame.cc:1914-1917
+    int st;
+    if ((st = upload(m, m->b[1], kps, (size_t)n * sizeof(orbx_kp))) != ORBX_OK) return st;
+    int *cell_start, *cell_items;
+    if ((st = grid_build(m, 15, m->b[1].as<orbx_kp>(), n, min_x, min_y, inv_w, inv_h, &cell_start, &cell_items)) != ORBX_OK) return st;
+    row_ptr[0] = 0; *n_cand = 0;
+    if (nq == 0) { M_CUDA(cudaStreamSynchronize(m->stream)); return ORBX_OK; }
+    const size_t fb = (size_t)nq * sizeof(float), ib = (size_t)nq * sizeof(int);
+    M_CUDA(m->b[5].ensure(3 * fb + 2 * ib));
+    float *dqx = m->b[5].as<float>(), *dqy = dqx + nq, *dqr = dqy + nq;
+    int *dmin = (int *)(dqr + nq), *dmax = dmin + nq;
+    M_CUDA(cudaMemcpyAsync(dqx, qx, fb, cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(cudaMemcpyAsync(dqy, qy, fb, cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(cudaMemcpyAsync(dqr, qr, fb, cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(cudaMemcpyAsync(dmin, min_level, ib, cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(cudaMemcpyAsync(dmax, max_level, ib, cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(m->b[6].ensure(ib));
+    M_CUDA(m->b[7].ensure(ib + sizeof(int)));
+    M_CUDA(m->b[8].ensure((size_t)std::max(cand_cap, 1) * sizeof(int)));
+    const orbx_kp *dk = m->b[1].as<orbx_kp>();
+    k_grid_query_count<<<(nq + 127) / 128, 128, 0, m->stream>>>(dk, cell_start, cell_items, min_x, min_y, inv_w, inv_h, dqx, dqy, dqr,
+                                                                dmin, dmax, nq, m->b[6].as<int>());
+    k_excl_scan<<<1, 1024, 0, m->stream>>>(m->b[6].as<int>(), nq, m->b[7].as<int>());
+    k_grid_query_fill<<<(nq + 127) / 128, 128, 0, m->stream>>>(dk, cell_start, cell_items, min_x, min_y, inv_w, inv_h, dqx, dqy, dqr,
+                                                               dmin, dmax, nq, m->b[7].as<int>(), m->b[8].as<int>(), cand_cap);
+    m->last_launches += 3;
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaMemcpyAsync(row_ptr, m->b[7].p, ib + sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    *n_cand = row_ptr[nq];
+    if (*n_cand > cand_cap) return fail(ORBX_ERR_CAPACITY, "candidate buffer too small");
+    if (*n_cand > 0 && cand) {
+        M_CUDA(cudaMemcpyAsync(cand, m->b[8].p, (size_t)*n_cand * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        M_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
+                              const float *grid_bounds, const float *scale_factors, int nlevels, const uint8_t *occupied,
+                              const int *l2r, const int *r2l, int nmp, const uint8_t *in_view, const float *proj_x,
+                              const float *proj_y, const int *level, const float *view_cos, const float *depth, const uint8_t *bad,
+                              const uint8_t *has_obs, const uint8_t *mp_desc, float th, int far_points, float th_far_points,
+                              float nnratio, int *assigned, int *nmatches) {
+    if (!m || !cam_off || !kps || !desc || !grid_bounds || !scale_factors || !assigned || !nmatches || nmp < 0 ||
+        !(ncam == 1 || ncam == 2 || ncam == 4) || nlevels < 1 || nlevels > 32)
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    const int N = cam_off[ncam];
+    for (int i = 0; i < N; i++) assigned[i] = -1;
+    *nmatches = 0;
+    if (nmp == 0 || N == 0) return ORBX_OK;
+    if (N >= 65535) return fail(ORBX_ERR_INVALID, "more than 65534 keypoints per frame are not supported");
+    int st;
+    // ---- frame side
+    if ((st = upload(m, m->b[1], kps, (size_t)N * sizeof(orbx_kp))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], desc, (size_t)N * 32)) != ORBX_OK) return st;
+    SbpFrame F;
+    memset(&F, 0, sizeof(F));
+    F.ncam = ncam; F.n_total = N;
+    F.kps = m->b[1].as<orbx_kp>(); F.desc = (const uint4 *)m->b[2].p;
+    for (int c = 0; c <= ncam; c++) F.cam_off[c] = cam_off[c];
+    for (int c = 0; c < ncam; c++) {
+        const float *gb = grid_bounds + 4 * c;
+        if (!(gb[1] > gb[0]) || !(gb[3] > gb[2])) return fail(ORBX_ERR_INVALID, "bad grid bounds");
+        F.min_x[c] = gb[0]; F.min_y[c] = gb[2];
+        F.inv_w[c] = (float)kGridCols / (gb[1] - gb[0]); F.inv_h[c] = (float)kGridRows / (gb[3] - gb[2]);
+    }
+    // grids: 4 cameras x {count,start,cursor,items} packed into b[15..18] with per-camera offsets
+    const int nc = kGridCols * kGridRows;
+    M_CUDA(m->b[15].ensure((size_t)4 * nc * sizeof(int)));
+    M_CUDA(m->b[16].ensure((size_t)4 * (nc + 1) * sizeof(int)));
+    M_CUDA(m->b[17].ensure((size_t)4 * nc * sizeof(int)));
+    M_CUDA(m->b[18].ensure((size_t)N * sizeof(int)));
+    M_CUDA(cudaMemsetAsync(m->b[15].p, 0, (size_t)4 * nc * sizeof(int), m->stream));
+    for (int c = 0; c < ncam; c++) {
+        const int n = cam_off[c + 1] - cam_off[c];
+        const orbx_kp *dk = F.kps + cam_off[c];
+        int *cnt = m->b[15].as<int>() + c * nc, *start = m->b[16].as<int>() + c * (nc + 1), *cur = m->b[17].as<int>() + c * nc;
+        int *items = m->b[18].as<int>() + cam_off[c];
+        if (n > 0) k_grid_count<<<(n + 255) / 256, 256, 0, m->stream>>>(dk, n, F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], cnt);
+        k_grid_scan<<<1, 1024, 0, m->stream>>>(cnt, start, cur);
+        if (n > 0) {
+            k_grid_fill<<<(n + 255) / 256, 256, 0, m->stream>>>(dk, n, F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], start, cur, items);
+            k_grid_sort_cells<<<(nc + 255) / 256, 256, 0, m->stream>>>(start, items);
+        }
+        m->last_launches += n > 0 ? 4 : 1;
+        F.cell_start[c] = start; F.cell_items[c] = items;
+    }
+    if ((st = upload(m, m->b[19], scale_factors, (size_t)nlevels * sizeof(float))) != ORBX_OK) return st;
+    F.scale_factors = m->b[19].as<float>();
+    // occupied / l2r / r2l
+    std::vector<uint8_t> occ(N, 0);
+    if (occupied) memcpy(occ.data(), occupied, N);
+    if ((st = upload(m, m->b[20], occ.data(), (size_t)N)) != ORBX_OK) return st;
+    F.occupied0 = m->b[20].as<uint8_t>();
+    const int nleft = cam_off[1] - cam_off[0], nright = ncam >= 2 ? cam_off[2] - cam_off[1] : 0;
+    std::vector<int> lr(std::max(nleft, 1), -1), rl(std::max(nright, 1), -1);
+    if (l2r && ncam >= 2) memcpy(lr.data(), l2r, (size_t)nleft * sizeof(int));
+    if (r2l && ncam >= 2) memcpy(rl.data(), r2l, (size_t)nright * sizeof(int));
+    M_CUDA(m->b[21].ensure((lr.size() + rl.size()) * sizeof(int)));
+    M_CUDA(cudaMemcpyAsync(m->b[21].p, lr.data(), lr.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(cudaMemcpyAsync(m->b[21].as<int>() + lr.size(), rl.data(), rl.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    F.l2r = m->b[21].as<int>(); F.r2l = m->b[21].as<int>() + lr.size();
+    // ---- map-point side: one query per (map point, camera) in reference order
+    const size_t q = (size_t)nmp * 4;
+    const size_t bytes = q * (1 + 4 + 4 + 4 + 4) + (size_t)nmp * (4 + 1 + 1 + 32);
+    uint8_t *base = nullptr;
+    SbpPoints P;
+    P.nmp = nmp;
+    size_t off = 0;
+    auto put = [&](const void *src, size_t nb) -> void * {
+        void *d = base + off;
+        cudaMemcpyAsync(d, src, nb, cudaMemcpyHostToDevice, m->stream);
+        off += (nb + 15) & ~(size_t)15;
+        return d;
+    };
+    M_CUDA(m->b[22].ensure(bytes + 16 * 16));
+    base = m->b[22].as<uint8_t>();
+    P.proj_x = (const float *)put(proj_x, q * 4);
+    P.proj_y = (const float *)put(proj_y, q * 4);
+    P.level = (const int *)put(level, q * 4);
+    P.view_cos = (const float *)put(view_cos, q * 4);
+    P.desc = (const uint4 *)put(mp_desc, (size_t)nmp * 32);
+    P.in_view = (const uint8_t *)put(in_view, q);
+    std::vector<uint8_t> active(nmp), hobs(nmp);
+    for (int i = 0; i < nmp; i++) {   // the per-point early `continue`s (src/ORBmatcher.cc:34-43)
+        const uint8_t *iv = in_view + 4 * i;
+        bool a = iv[0] || iv[1] || iv[2] || iv[3];
+        if (far_points && depth && depth[i] > th_far_points) a = false;
+        if (bad && bad[i]) a = false;
+        active[i] = a; hobs[i] = has_obs ? has_obs[i] : 1;
+    }
+    P.active = (const uint8_t *)put(active.data(), nmp);
+    P.has_obs = (const uint8_t *)put(hobs.data(), nmp);
+    M_CUDA(cudaGetLastError());
+    P.th = th; P.nnratio = nnratio;
+    // ---- device work buffers
+    M_CUDA(m->b[23].ensure(sbp_work_bytes(nmp, N)));
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    st = sbp_run(F, P, m->b[23].as<uint8_t>(), m->b[0], m->stream, &m->last_launches);
+    if (st != ORBX_OK) return st;
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    SbpResult R;
+    sbp_result_ptrs(m->b[23].as<uint8_t>(), nmp, N, &R);
+    M_CUDA(cudaMemcpyAsync(assigned, R.assigned, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(nmatches, R.nmatches, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_popc_peak(int device, double *gpopc_per_s) {
+    if (!gpopc_per_s) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (orbx_device_count() <= device || device < 0) return fail(ORBX_ERR_NO_DEVICE, "no such CUDA device");
+    M_CUDA(cudaSetDevice(device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    uint32_t *d = nullptr;
+    M_CUDA(cudaMalloc((void **)&d, 64));
+    cudaEvent_t e0, e1;
+    M_CUDA(cudaEventCreate(&e0)); M_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = sms * 8;
+    k_popc_peak<<<blocks, 256>>>(d, 64, 1);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        M_CUDA(cudaEventRecord(e0));
+        k_popc_peak<<<blocks, 256>>>(d, iters, 1 + rep);
+        M_CUDA(cudaEventRecord(e1));
+        M_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        M_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    M_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *gpopc_per_s = (double)blocks * 256 * iters * 8 / (best * 1e-3) * 1e-9;
+    return ORBX_OK;
+}
+
+}  // extern "C"

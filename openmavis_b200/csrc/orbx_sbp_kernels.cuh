@@ -1,0 +1,215 @@
+// orbx_sbp_kernels.cuh — ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, ...) on the device
+// (src/ORBmatcher.cc:23-340).
+//
+// The reference walks the map points sequentially; a keypoint claimed by an earlier point (F.mvpMapPoints[idx]
+// with Observations()>0, :77-79) is invisible to later points, and a failed ratio test on camera c skips the
+// remaining cameras of that point (the `continue` at :119-120 continues the MapPoint loop).  Here:
+//   phase A (parallel over (point, camera) queries): window query on the 64x48 grid (src/Frame.cc:890-967) ->
+//            CSR candidate lists in reference order, Hamming distance + octave per candidate;
+//   phase B (one block, ordered resolve): a point is FINAL in a round iff it is the smallest unresolved point
+//            on every keypoint it may read or write (its candidates and their stereo mirrors, :125-131 /
+//            :195-201).  Final points of a round touch disjoint keypoints, so they are applied in parallel and
+//            the result equals the sequential walk.  The smallest unresolved point is always final, so the
+//            loop terminates.
+#pragma once
+
+#include "orbx_match_kernels.cuh"
+
+namespace orbx {
+
+struct SbpFrame {
+    int ncam, n_total;
+    int cam_off[5];
+    const orbx_kp *kps;          // all cameras, camera-local order
+    const uint4 *desc;
+    float min_x[4], min_y[4], inv_w[4], inv_h[4];
+    const int *cell_start[4];
+    const int *cell_items[4];    // camera-local indices
+    const float *scale_factors;
+    const uint8_t *occupied0;    // initial occupancy (global index)
+    const int *l2r, *r2l;
+};
+
+struct SbpPoints {
+    int nmp;
+    const float *proj_x, *proj_y, *view_cos;   // [nmp][4]
+    const int *level;                          // [nmp][4]
+    const uint8_t *in_view;                    // [nmp][4]
+    const uint8_t *active, *has_obs;           // [nmp]
+    const uint4 *desc;                         // [nmp][2]
+    float th, nnratio;
+};
+
+struct SbpWork {
+    int *counts;      // [nq]
+    int *q_ptr;       // [nq+1]
+    int *tmin;        // [N]
+    int *occ;         // [N]
+    int *assigned;    // [N]
+    int *resolved;    // [nmp]
+    int *nmatches;    // [4]: nmatches, unresolved count, scratch
+};
+struct SbpResult { const int *assigned; const int *nmatches; };
+
+inline size_t sbp_work_bytes(int nmp, int N) {
+    return ((size_t)nmp * 4 * 2 + 1 + (size_t)N * 3 + nmp + 8) * sizeof(int) + 256;
+}
+inline void sbp_carve(uint8_t *base, int nmp, int N, SbpWork *w) {
+    int *p = (int *)base;
+    const size_t nq = (size_t)nmp * 4;
+    w->counts = p; p += nq;
+    w->q_ptr = p; p += nq + 1;
+    w->tmin = p; p += N;
+    w->occ = p; p += N;
+    w->assigned = p; p += N;
+    w->resolved = p; p += nmp;
+    w->nmatches = p;
+}
+inline void sbp_result_ptrs(uint8_t *base, int nmp, int N, SbpResult *r) {
+    SbpWork w; sbp_carve(base, nmp, N, &w);
+    r->assigned = w.assigned; r->nmatches = w.nmatches;
+}
+
+__device__ __forceinline__ bool sbp_query(const SbpFrame &F, const SbpPoints &P, int q, int &c, float &x, float &y, float &rr,
+                                          int &lvl) {
+    const int mp = q >> 2;
+    c = q & 3;
+    if (!P.active[mp] || !P.in_view[q]) return false;
+    if (c >= 1 && F.ncam < 2) return false;     // F.Nleft == -1
+    if (c >= 2 && F.ncam < 4) return false;     // F.Nsideleft == -1
+    lvl = P.level[q];
+    if (lvl < 0) return false;                  // :142 nPredictedLevel != -1 (camera 0 assumes a valid level)
+    float r = ((double)P.view_cos[q] > 0.998) ? 2.5f : 4.0f;    // RadiusByViewingCos :342-347
+    if (c == 0 && P.th != 1.0f) r = __fmul_rn(r, P.th);         // only camera 0 applies th (:51-52)
+    rr = __fmul_rn(r, F.scale_factors[lvl]);
+    x = P.proj_x[q]; y = P.proj_y[q];
+    return true;
+}
+
+__global__ void k_sbp_count(SbpFrame F, SbpPoints P, int *__restrict__ counts) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.nmp * 4) return;
+    int c, lvl, n = 0; float x, y, rr;
+    if (sbp_query(F, P, q, c, x, y, rr, lvl))
+        grid_query(F.kps + F.cam_off[c], F.cell_start[c], F.cell_items[c], F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], x, y, rr,
+                   lvl - 1, lvl, [&](int) { n++; });
+    counts[q] = n;
+}
+
+// candidate record: local index | dist << 16 | octave << 25
+__global__ void k_sbp_fill(SbpFrame F, SbpPoints P, const int *__restrict__ q_ptr, uint32_t *__restrict__ cand) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.nmp * 4) return;
+    int c, lvl; float x, y, rr;
+    if (!sbp_query(F, P, q, c, x, y, rr, lvl)) return;
+    const int mp = q >> 2;
+    const uint4 qa = P.desc[2 * mp], qb = P.desc[2 * mp + 1];
+    int o = q_ptr[q];
+    const orbx_kp *ck = F.kps + F.cam_off[c];
+    const uint4 *cd = F.desc + 2 * (long long)F.cam_off[c];
+    grid_query(ck, F.cell_start[c], F.cell_items[c], F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], x, y, rr, lvl - 1, lvl,
+               [&](int idx) {
+                   const int d = hamming256(qa, qb, cd[2 * idx], cd[2 * idx + 1]);
+                   cand[o++] = (uint32_t)idx | ((uint32_t)d << 16) | ((uint32_t)(ck[idx].octave & 0x7F) << 25);
+               });
+}
+
+template <class Fn>
+__device__ __forceinline__ void sbp_for_touch(const SbpFrame &F, const int *q_ptr, const uint32_t *cand, int mp, Fn fn) {
+    for (int c = 0; c < 4; c++) {
+        const int q = mp * 4 + c;
+        for (int k = q_ptr[q]; k < q_ptr[q + 1]; k++) {
+            const int idx = (int)(cand[k] & 0xFFFF);
+            fn(idx + F.cam_off[c]);
+            if (F.ncam >= 2) {
+                if (c == 0 && F.l2r[idx] != -1) fn(F.l2r[idx] + F.cam_off[1]);
+                if (c == 1 && F.r2l[idx] != -1) fn(F.r2l[idx]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, SbpWork W, const uint32_t *__restrict__ cand) {
+    __shared__ int s_left;
+    const int N = F.n_total, nmp = P.nmp;
+    for (int g = threadIdx.x; g < N; g += blockDim.x) { W.occ[g] = F.occupied0[g]; W.assigned[g] = -1; }
+    for (int u = threadIdx.x; u < nmp; u += blockDim.x) W.resolved[u] = (W.q_ptr[4 * u + 4] == W.q_ptr[4 * u]) ? 1 : 0;
+    if (threadIdx.x == 0) W.nmatches[0] = 0;
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) s_left = 0;
+        for (int g = threadIdx.x; g < N; g += blockDim.x) W.tmin[g] = 0x7FFFFFFF;
+        __syncthreads();
+        for (int u = threadIdx.x; u < nmp; u += blockDim.x) {
+            if (W.resolved[u]) continue;
+            sbp_for_touch(F, W.q_ptr, cand, u, [&](int g) { atomicMin(&W.tmin[g], u); });
+        }
+        __syncthreads();
+        for (int u = threadIdx.x; u < nmp; u += blockDim.x) {
+            if (W.resolved[u]) continue;
+            bool fin = true;
+            sbp_for_touch(F, W.q_ptr, cand, u, [&](int g) { if (W.tmin[g] != u) fin = false; });
+            if (!fin) { atomicAdd(&s_left, 1); continue; }
+            // ---- sequential body of the reference for map point u
+            int nm = 0;
+            for (int c = 0; c < 4; c++) {
+                const int q = u * 4 + c;
+                const int b = W.q_ptr[q], e = W.q_ptr[q + 1];
+                if (b == e) continue;
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+                for (int k = b; k < e; k++) {
+                    const uint32_t r = cand[k];
+                    const int idx = (int)(r & 0xFFFF), dist = (int)((r >> 16) & 0x1FF), oct = (int)(r >> 25);
+                    if (W.occ[idx + F.cam_off[c]]) continue;
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+                    else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+                }
+                if (bestDist <= 100) {   // TH_HIGH
+                    if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(P.nnratio, (float)bestDist2)) break;
+                    const int g = bestIdx + F.cam_off[c];
+                    const int ho = P.has_obs[u];
+                    if (c == 0) {
+                        W.assigned[g] = u; W.occ[g] = ho;
+                        if (F.ncam >= 2 && F.l2r[bestIdx] != -1) {
+                            const int gr = F.l2r[bestIdx] + F.cam_off[1];
+                            W.assigned[gr] = u; W.occ[gr] = ho; nm++;
+                        }
+                        nm++;
+                    } else if (c == 1) {
+                        if (F.r2l[bestIdx] != -1) { const int gl = F.r2l[bestIdx]; W.assigned[gl] = u; W.occ[gl] = ho; nm++; }
+                        W.assigned[g] = u; W.occ[g] = ho; nm++;
+                    } else {
+                        W.assigned[g] = u; W.occ[g] = ho; nm++;
+                    }
+                }
+            }
+            if (nm) atomicAdd(&W.nmatches[0], nm);
+            W.resolved[u] = 1;
+        }
+        __syncthreads();
+        if (s_left == 0) break;
+        __syncthreads();
+    }
+}
+
+// host driver (orbx_match.cu)
+template <class DBufT>
+inline int sbp_run(SbpFrame F, SbpPoints P, uint8_t *work, DBufT &candbuf, cudaStream_t s, int *launches) {
+    SbpWork W;
+    sbp_carve(work, P.nmp, F.n_total, &W);
+    const int nq = P.nmp * 4;
+    k_sbp_count<<<(nq + 127) / 128, 128, 0, s>>>(F, P, W.counts);
+    k_excl_scan<<<1, 1024, 0, s>>>(W.counts, nq, W.q_ptr);
+    int total = 0;
+    ORBX_CUDA(cudaMemcpyAsync(&total, W.q_ptr + nq, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaStreamSynchronize(s));
+    ORBX_CUDA(candbuf.ensure((size_t)(total + 1) * sizeof(uint32_t)));
+    uint32_t *cand = (uint32_t *)candbuf.p;
+    k_sbp_fill<<<(nq + 127) / 128, 128, 0, s>>>(F, P, W.q_ptr, cand);
+    k_sbp_resolve<<<1, 1024, 0, s>>>(F, P, W, cand);
+    *launches += 4;
+    ORBX_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+}  // namespace orbx

@@ -195,6 +195,8 @@ void fast9_16(const uint8_t *img, int w, int h, int stride, int threshold, std::
     threshold = std::min(std::max(threshold, 0), 255);
     int off[25];
     for (int k = 0; k < 25; k++) off[k] = kRingDy[k % 16] * stride + kRingDx[k % 16];
+    uint8_t ttab[512];
+    for (int i = -255; i <= 255; i++) ttab[i + 255] = (uint8_t)(i < -threshold ? 1 : i > threshold ? 2 : 0);
     std::vector<uint8_t> sbuf((size_t)3 * w, 0);
     std::vector<int> cbuf((size_t)3 * (w + 1), 0);
     uint8_t *buf[3] = {sbuf.data(), sbuf.data() + w, sbuf.data() + 2 * w};
@@ -208,15 +210,29 @@ void fast9_16(const uint8_t *img, int w, int h, int stride, int threshold, std::
         if (i < h - 3) {
             for (int j = 3; j < w - 3; j++, ptr++) {
                 int v = ptr[0];
+                // high-speed test of fast.cpp (a necessary condition for an arc of 9): tab = 1 darker, 2 brighter
+                const uint8_t *tab = &ttab[0] - v + 255;
+                int d = tab[ptr[off[0]]] | tab[ptr[off[8]]];
+                if (d == 0) continue;
+                d &= tab[ptr[off[2]]] | tab[ptr[off[10]]];
+                d &= tab[ptr[off[4]]] | tab[ptr[off[12]]];
+                d &= tab[ptr[off[6]]] | tab[ptr[off[14]]];
+                if (d == 0) continue;
+                d &= tab[ptr[off[1]]] | tab[ptr[off[9]]];
+                d &= tab[ptr[off[3]]] | tab[ptr[off[11]]];
+                d &= tab[ptr[off[5]]] | tab[ptr[off[13]]];
+                d &= tab[ptr[off[7]]] | tab[ptr[off[15]]];
                 int lo = v - threshold, hi = v + threshold;
                 // >= 9 contiguous ring pixels all darker than v-t, or all brighter than v+t
                 bool corner = false;
-                int count = 0;
-                for (int k = 0; k < 25; k++) {
-                    if (ptr[off[k]] < lo) { if (++count > 8) { corner = true; break; } } else count = 0;
+                if (d & 1) {
+                    int count = 0;
+                    for (int k = 0; k < 25; k++) {
+                        if (ptr[off[k]] < lo) { if (++count > 8) { corner = true; break; } } else count = 0;
+                    }
                 }
-                if (!corner) {
-                    count = 0;
+                if (!corner && (d & 2)) {
+                    int count = 0;
                     for (int k = 0; k < 25; k++) {
                         if (ptr[off[k]] > hi) { if (++count > 8) { corner = true; break; } } else count = 0;
                     }
@@ -251,21 +267,23 @@ void fast9_16(const uint8_t *img, int w, int h, int stride, int threshold, std::
 const int kBlurK[7] = {18, 34, 48, 56, 48, 34, 18};
 void blur7(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride) {
     std::vector<uint16_t> tmp((size_t)w * h);
+    std::vector<uint8_t> row(w + 6);
     for (int y = 0; y < h; y++) {
         const uint8_t *S = src + (size_t)y * sstride;
-        for (int x = 0; x < w; x++) {
-            int acc = 0;
-            for (int k = 0; k < 7; k++) acc += kBlurK[k] * S[reflect101(x + k - 3, w)];
-            tmp[(size_t)y * w + x] = (uint16_t)acc;
-        }
+        for (int k = 0; k < 3; k++) { row[k] = S[reflect101(k - 3, w)]; row[w + 3 + k] = S[reflect101(w + k, w)]; }
+        memcpy(row.data() + 3, S, w);
+        uint16_t *T = tmp.data() + (size_t)y * w;
+        const uint8_t *R = row.data();
+        for (int x = 0; x < w; x++)
+            T[x] = (uint16_t)(18 * (R[x] + R[x + 6]) + 34 * (R[x + 1] + R[x + 5]) + 48 * (R[x + 2] + R[x + 4]) + 56 * R[x + 3]);
     }
     for (int y = 0; y < h; y++) {
         const uint16_t *R[7];
         for (int k = 0; k < 7; k++) R[k] = tmp.data() + (size_t)reflect101(y + k - 3, h) * w;
         uint8_t *D = dst + (size_t)y * dstride;
         for (int x = 0; x < w; x++) {
-            uint32_t acc = 0;
-            for (int k = 0; k < 7; k++) acc += (uint32_t)kBlurK[k] * R[k][x];
+            uint32_t acc = 18u * ((uint32_t)R[0][x] + R[6][x]) + 34u * ((uint32_t)R[1][x] + R[5][x]) +
+                           48u * ((uint32_t)R[2][x] + R[4][x]) + 56u * (uint32_t)R[3][x];
             D[x] = (uint8_t)((acc + 32768u) >> 16);
         }
     }

@@ -1,0 +1,65 @@
+"""CPU checks of the C-ABI surface: liborbx.so loads, exports every symbol include/orbx.h declares, and refuses to
+compute without a CUDA device (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def ob():
+    import openmavis_b200 as ob
+    if not os.path.exists(ob.LIB_PATH):
+        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'openmavis_b200', 'csrc')])
+    return ob
+
+
+def test_exports_every_declared_symbol(ob):
+    L = ob.lib()
+    hdr = open(os.path.join(ROOT, 'include', 'orbx.h')).read()
+    names = sorted(set(re.findall(r'\b(orbx_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_features_per_level_host_logic(ob):
+    # mnFeaturesPerLevel, src/ORBextractor.cc:378-391
+    assert ob.features_per_level(1000).tolist() == [217, 181, 151, 126, 105, 87, 73, 60]
+    assert ob.features_per_level(1200).tolist() == [261, 217, 181, 151, 126, 105, 87, 72]
+    assert ob.features_per_level(1500).tolist() == [326, 271, 226, 189, 157, 131, 109, 91]
+    assert ob.features_per_level(500).tolist() == [109, 90, 75, 63, 52, 44, 36, 31]
+
+
+def test_ratio_test_host_logic(ob):
+    import oracle_lib as O
+    rng = np.random.default_rng(0)
+    d = rng.integers(0, 120, size=(500, 2)).astype(np.int32)
+    d[:, 1] = np.maximum(d[:, 1], d[:, 0]); d[::17, 1] = -1
+    for r in (0.7, 0.8):
+        assert np.array_equal(ob.ORBmatcher.ratio_test(d, r), O.ratio_test(d, r))
+
+
+def test_no_cpu_fallback(ob):
+    if ob.device_count() > 0:
+        pytest.skip('CUDA device present')
+    with pytest.raises(ob.OrbxError):
+        ob.RigExtractor(752, 480, 1, 1000)
+    with pytest.raises(ob.OrbxError):
+        ob.ORBmatcher()
+    with pytest.raises(ob.OrbxError):
+        ob.ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.zeros(32, np.uint8))
+
+
+def test_product_does_not_reference_oracle():
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, 'openmavis_b200')):
+        for f in fs:
+            if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
+                if re.search(r'oracle/|orb_oracle|oracle_lib|orc_', open(os.path.join(dp, f), errors='ignore').read().replace('orc_search_by_projection', '')):
+                    bad.append(f)
+    assert not bad, bad

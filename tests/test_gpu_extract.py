@@ -1,0 +1,204 @@
+"""GPU parity tests (run on the B200 box): the CUDA extraction path through the C ABI vs the CPU oracle,
+stage by stage and end to end, bit-exact.  Reference path: src/ORBextractor.cc:987-1071."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import openmavis_b200 as ob
+from openmavis_b200.synth import synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device: -m gpu tests must run on the GPU box')
+
+
+def compare_image(rig, b, img, nf, ini, mn, lap, result, fma_mode=0, stages=True):
+    E = O.OracleExtractor(nf, 1.2, 8, ini, mn)
+    mono, kps, desc = E(img, lap, fma_mode)
+    if stages:
+        for l in range(8):
+            ref = E.level(l)
+            got = rig.pyramid_level(b, l, with_border=True)
+            assert np.array_equal(ref, got), 'pyramid level %d differs (%d px)' % (l, int((ref != got).sum()))
+            assert np.array_equal(ref[19:-19, 19:-19], rig.pyramid_level(b, l))
+            xs, ys, sc = E.level_candidates(l)
+            gx, gy, gs = rig.debug_candidates(b, l)
+            assert len(xs) == len(gx), 'level %d: %d vs %d candidates' % (l, len(xs), len(gx))
+            assert np.array_equal(xs, gx) and np.array_equal(ys, gy) and np.array_equal(sc, gs), 'candidates level %d' % l
+            rb = E.level_blur(l)
+            if rb is not None:
+                assert np.array_equal(rb, rig.debug_blur_level(b, l)), 'blur level %d' % l
+            rk = E.level_keypoints(l)
+            gk = rig.debug_level_keypoints(b, l)
+            assert len(rk) == len(gk), 'level %d: %d vs %d keypoints' % (l, len(rk), len(gk))
+            for f in ('x', 'y', 'response', 'octave', 'size'):
+                assert np.array_equal(rk[f], gk[f]), 'level %d keypoint field %s' % (l, f)
+            assert np.array_equal(rk['angle'].view(np.uint32), gk['angle'].view(np.uint32)), 'angle bits level %d' % l
+    gmono, gk, gd = result
+    assert gmono == mono
+    assert len(gk) == len(kps)
+    for f in KPF:
+        assert np.array_equal(kps[f].view(np.uint32), gk[f].view(np.uint32)), 'final keypoint field %s' % f
+    assert np.array_equal(desc, gd), '%d descriptor rows differ' % int((desc != gd).any(axis=1).sum())
+    return len(kps)
+
+
+KPF = ('x', 'y', 'size', 'angle', 'response', 'octave', 'class_id')
+
+
+# config 1 (BASELINE.json): one 752x480 EuRoC-mono frame, nF=1000, 8 levels, 1.2, FAST 20/7; mono lapping {0,1000} (D7) and {0,0}
+@pytest.mark.parametrize('lap', [(0, 1000), (0, 0), (300, 500)])
+def test_config1_euroc_mono(lap):
+    _need_gpu()
+    img = synth_image(752, 480, 1000)
+    rig = ob.RigExtractor(752, 480, 1, 1000)
+    res = rig.extract([img], ob.make_params(1, 1000, 20, 7, lap))
+    n = compare_image(rig, 0, img, 1000, 20, 7, lap, res[0])
+    assert n >= 900
+
+
+def test_operator_mirror_single_image():
+    _need_gpu()
+    img = synth_image(752, 480, 1001)
+    ex = ob.ORBextractor(1000, 1.2, 8, 20, 7)
+    mono, kps, desc = ex(img, None, (0, 1000))
+    rm, rk, rd = O.OracleExtractor(1000, 1.2, 8, 20, 7)(img, (0, 1000))
+    assert mono == rm and np.array_equal(desc, rd)
+    for f in KPF:
+        assert np.array_equal(kps[f], rk[f])
+    assert ex(None)[0] == -1 and ex(np.zeros((0, 0), np.uint8))[0] == -1
+    pyr = ex.mvImagePyramid
+    assert len(pyr) == 8 and pyr[0].shape == (480, 752) and np.array_equal(pyr[0], img)
+    assert ex.GetLevels() == 8 and np.allclose(ex.GetScaleFactors()[1], 1.2)
+    t = O.OracleExtractor(1000, 1.2, 8, 20, 7).tables()
+    assert np.array_equal(ex.GetScaleFactors(), t['sf']) and np.array_equal(ex.GetInverseScaleSigmaSquares(), t['inv_sigma2'])
+
+
+# config 2: EuRoC stereo pair 2x752x480, nF=1200
+def test_config2_stereo_pair():
+    _need_gpu()
+    imgs = [synth_image(752, 480, 2000 + c) for c in range(2)]
+    rig = ob.RigExtractor(752, 480, 2, 1200)
+    res = rig.extract(imgs, ob.make_params(2, 1200, 20, 7, (0, 0)))
+    for b in range(2):
+        compare_image(rig, b, imgs[b], 1200, 20, 7, (0, 0), res[b])
+
+
+# config 3: Hilti rig 5x720x540, nF=1500/camera; and the yaml-faithful 4-camera wiring 500/500/1000/1000, ini 15
+def test_config3_rig_5cam():
+    _need_gpu()
+    imgs = [synth_image(720, 540, 3000 + c) for c in range(5)]
+    laps = [(0, 720), (0, 720), (0, 0), (0, 0), (0, 0)]
+    rig = ob.RigExtractor(720, 540, 5, 1500)
+    res = rig.extract(imgs, ob.make_params(5, 1500, 20, 7, laps))
+    for b in range(5):
+        compare_image(rig, b, imgs[b], 1500, 20, 7, laps[b], res[b], stages=(b < 2))
+
+
+def test_config3_rig_4cam_yaml_params():
+    _need_gpu()
+    imgs = [synth_image(720, 540, 3010 + c) for c in range(4)]
+    nfs = [500, 500, 1000, 1000]
+    laps = [(0, 720), (0, 720), (0, 0), (0, 0)]
+    rig = ob.RigExtractor(720, 540, 4, 1000)
+    p = ob.make_params(4, 500, 15, 7, laps); p['nfeatures'] = nfs
+    res = rig.extract(imgs, p)
+    for b in range(4):
+        compare_image(rig, b, imgs[b], nfs[b], 15, 7, laps[b], res[b], stages=(b in (0, 3)))
+
+
+# config 4: TUM-VI 2x512x512, nF=1500, lapping {0,511}
+def test_config4_tumvi():
+    _need_gpu()
+    imgs = [synth_image(512, 512, 4000 + c) for c in range(2)]
+    rig = ob.RigExtractor(512, 512, 2, 1500)
+    res = rig.extract(imgs, ob.make_params(2, 1500, 20, 7, (0, 511)))
+    for b in range(2):
+        compare_image(rig, b, imgs[b], 1500, 20, 7, (0, 511), res[b])
+
+
+# config 5 geometry: 1280x1024, nF=2000 (small batch here; the 64-frame batch is exercised by bench.py)
+def test_config5_geometry_small_batch():
+    _need_gpu()
+    imgs = [synth_image(1280, 1024, 5000 + c) for c in range(3)]
+    rig = ob.RigExtractor(1280, 1024, 3, 2000)
+    res = rig.extract(imgs, ob.make_params(3, 2000, 20, 7, (0, 0)))
+    for b in range(3):
+        compare_image(rig, b, imgs[b], 2000, 20, 7, (0, 0), res[b], stages=(b == 0))
+
+
+def test_fma_mode_switch():
+    _need_gpu()
+    img = synth_image(752, 480, 1003)
+    rig = ob.RigExtractor(752, 480, 1, 1000, fma_mode=1)
+    res = rig.extract([img], ob.make_params(1, 1000, 20, 7, (0, 0)))
+    compare_image(rig, 0, img, 1000, 20, 7, (0, 0), res[0], fma_mode=1, stages=False)
+
+
+@pytest.mark.parametrize('kind', ['zeros', 'const255', 'checker', 'noise', 'halfflat'])
+def test_adversarial_images(kind):
+    _need_gpu()
+    w, h = 640, 480
+    rng = np.random.default_rng(9)
+    if kind == 'zeros':
+        img = np.zeros((h, w), np.uint8)
+    elif kind == 'const255':
+        img = np.full((h, w), 255, np.uint8)
+    elif kind == 'checker':
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = ((((yy // 8) + (xx // 8)) % 2) * 200 + 20).astype(np.uint8)
+    elif kind == 'noise':
+        img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    else:
+        img = synth_image(w, h, 17); img[:, : w // 2] = 90
+    rig = ob.RigExtractor(w, h, 1, 1000)
+    res = rig.extract([img], ob.make_params(1, 1000, 20, 7, (100, 400)))
+    n = compare_image(rig, 0, img, 1000, 20, 7, (100, 400), res[0])
+    if kind in ('zeros', 'const255'):
+        assert n == 0 and res[0][2].shape == (0, 32) and res[0][0] == 0
+
+
+def test_non_contiguous_input_and_handle_reuse():
+    _need_gpu()
+    big = synth_image(800, 500, 21)
+    view = big[10:490, 24:776]           # 752x480 view with stride 800
+    rig = ob.RigExtractor(752, 480, 2, 1000)
+    res = rig.extract([view], ob.make_params(1, 1000, 20, 7, (0, 0)))
+    compare_image(rig, 0, np.ascontiguousarray(view), 1000, 20, 7, (0, 0), res[0], stages=False)
+    # second call on the same handle with other content and a smaller nfeatures: no state leaks between calls
+    img2 = synth_image(752, 480, 22)
+    res2 = rig.extract([img2, view], ob.make_params(2, 600, 12, 5, (0, 0)))
+    compare_image(rig, 0, img2, 600, 12, 5, (0, 0), res2[0])
+    compare_image(rig, 1, np.ascontiguousarray(view), 600, 12, 5, (0, 0), res2[1], stages=False)
+
+
+def test_device_resident_path_matches_host_path():
+    _need_gpu()
+    import torch
+    imgs = np.stack([synth_image(720, 540, 3100 + c) for c in range(4)])
+    rig = ob.RigExtractor(720, 540, 4, 1500)
+    p = ob.make_params(4, 1500, 20, 7, (0, 720))
+    host = rig.extract(list(imgs), p)
+    host = [(m, k.copy(), d.copy()) for m, k, d in host]
+    t = torch.from_numpy(imgs).cuda()
+    rig.set_stream(torch.cuda.current_stream().cuda_stream)
+    rig.extract_device(t.data_ptr(), 4, p)
+    dev = rig.fetch(4)
+    for (m0, k0, d0), (m1, k1, d1) in zip(host, dev):
+        assert m0 == m1 and np.array_equal(k0, k1) and np.array_equal(d0, d1)
+
+
+def test_errors():
+    _need_gpu()
+    with pytest.raises(ob.OrbxError):
+        ob.RigExtractor(100, 80, 1, 1000)             # too small for 8 levels
+    rig = ob.RigExtractor(752, 480, 1, 1000)
+    with pytest.raises(ob.OrbxError):
+        rig.extract([synth_image(752, 480, 1)] * 2, ob.make_params(2, 1000, 20, 7))    # batch > max_images
+    with pytest.raises(ob.OrbxError):
+        rig.extract([synth_image(752, 480, 1)], ob.make_params(1, 5000, 20, 7))        # nfeatures > max_nfeatures
+    with pytest.raises(ob.OrbxError):
+        rig.extract([synth_image(640, 480, 1)], ob.make_params(1, 1000, 20, 7))        # wrong geometry

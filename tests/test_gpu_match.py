@@ -1,0 +1,248 @@
+"""GPU parity tests of the Hamming-matching kernels vs the CPU oracle (bit-exact indices and distances).
+Reference: src/ORBmatcher.cc (DescriptorDistance :2577, SearchByProjection :23-340, SearchForTriangulation :1131-1456),
+cv::BFMatcher::knnMatch at src/Frame.cc:1427,1483, Frame grid src/Frame.cc:541-582, 890-967."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import openmavis_b200 as ob
+from openmavis_b200.synth import synth_descriptors, synth_image, synth_query_from_train
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def M():
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device: -m gpu tests must run on the GPU box')
+    return ob.ORBmatcher(0.8)
+
+
+def test_descriptor_distance(M):
+    a = synth_descriptors(1000, 1); b = synth_descriptors(1000, 2)
+    b[:10] = a[:10]; b[10:20] = ~a[10:20]
+    d = ob.ORBmatcher.DescriptorDistance(a, b)
+    ref = np.array([O.hamming(a[i], b[i]) for i in range(1000)])
+    assert np.array_equal(d, ref) and d[0] == 0 and d[10] == 256
+    assert ob.ORBmatcher.DescriptorDistance(a[5], b[500]) == ref_single(a[5], b[500])
+
+
+def ref_single(a, b):
+    return O.hamming(a, b)
+
+
+@pytest.mark.parametrize('nq,nt', [(1, 1), (1, 2), (7, 3), (300, 1), (1500, 1500), (1537, 2049), (40, 9000), (5000, 257)])
+def test_knn2_matches_oracle(M, nq, nt):
+    t = synth_descriptors(nt, 100 + nt)
+    t[: nt // 3, 6:] = 0                       # distance ties between different train rows
+    q = synth_query_from_train(np.resize(t, (max(nq, nt), 32))[:max(nq, nt)], 7)[:nq]
+    idx, dist = M.knnMatch2(q, t)
+    ridx, rdist = O.knn2(q, t)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+    assert np.array_equal(ob.ORBmatcher.ratio_test(dist, 0.8), O.ratio_test(rdist, 0.8))
+
+
+def test_knn2_empty_inputs(M):
+    t = synth_descriptors(10, 1)
+    idx, dist = M.knnMatch2(np.zeros((0, 32), np.uint8), t)
+    assert idx.shape == (0, 2)
+    idx, dist = M.knnMatch2(t, np.zeros((0, 32), np.uint8))
+    assert (idx == -1).all() and (dist == -1).all()
+
+
+def test_knn2_100k_property(M):
+    """Config 5 size (100k x 100k): too big for the scalar oracle -> size-independent properties: every planted
+    neighbour is recovered with its exact distance, results are (dist asc, idx asc), and a random sample of rows
+    equals the oracle's full scan."""
+    n = 100000
+    train = synth_descriptors(n, 5)
+    rng = np.random.default_rng(6)
+    src = rng.integers(0, n, size=n)
+    flips = np.packbits(rng.random((n, 256)) < 0.04, axis=1, bitorder='little')
+    q = train[src] ^ flips
+    idx, dist = M.knnMatch2(q, train)
+    planted = np.unpackbits(flips, axis=1).sum(axis=1)
+    d_to_src = np.unpackbits(q ^ train[src], axis=1).sum(axis=1)
+    assert np.array_equal(planted, d_to_src)
+    assert (dist[:, 0] <= planted).all()
+    same = idx[:, 0] == src
+    assert same.mean() > 0.999 and np.array_equal(dist[same, 0], planted[same])
+    assert (dist[:, 0] <= dist[:, 1]).all()
+    tie = dist[:, 0] == dist[:, 1]
+    assert (idx[tie, 0] < idx[tie, 1]).all()
+    got_d0 = np.unpackbits(q ^ train[idx[:, 0]], axis=1).sum(axis=1)
+    got_d1 = np.unpackbits(q ^ train[idx[:, 1]], axis=1).sum(axis=1)
+    assert np.array_equal(got_d0, dist[:, 0]) and np.array_equal(got_d1, dist[:, 1])
+    rows = rng.integers(0, n, size=48)
+    ridx, rdist = O.knn2(q[rows], train)
+    assert np.array_equal(idx[rows], ridx) and np.array_equal(dist[rows], rdist)
+
+
+def _oracle_csr(q, t, row_ptr, cand):
+    nq = q.shape[0]
+    out = dict(best_idx=np.full(nq, -1, np.int32), best_dist=np.full(nq, 256, np.int32), second_dist=np.full(nq, 256, np.int32),
+               best_pos=np.full(nq, -1, np.int32), second_pos=np.full(nq, -1, np.int32))
+    dists = np.zeros(len(cand), np.int32)
+    for i in range(nq):
+        bd, bd2, bi, bp, bp2 = 256, 256, -1, -1, -1
+        for k in range(row_ptr[i], row_ptr[i + 1]):
+            d = O.hamming(q[i], t[cand[k]]); dists[k] = d
+            if d < bd:
+                bd2, bp2, bd, bi, bp = bd, bp, d, cand[k], k - row_ptr[i]
+            elif d < bd2:
+                bd2, bp2 = d, k - row_ptr[i]
+        out['best_idx'][i], out['best_dist'][i], out['second_dist'][i], out['best_pos'][i], out['second_pos'][i] = bi, bd, bd2, bp, bp2
+    return out, dists
+
+
+def test_match_csr(M):
+    rng = np.random.default_rng(3)
+    t = synth_descriptors(800, 31); t[:200, 3:] = 0
+    q = synth_query_from_train(t, 32)[:500]
+    lens = rng.integers(0, 40, size=500); lens[::9] = 0
+    row_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cand = rng.integers(0, 800, size=int(row_ptr[-1])).astype(np.int32)
+    got = M.match_csr(q, t, row_ptr, cand)
+    ref, rd = _oracle_csr(q, t, row_ptr, cand)
+    for k in ref:
+        assert np.array_equal(ref[k], got[k]), k
+    assert np.array_equal(M.match_csr_dists(q, t, row_ptr, cand), rd)
+
+
+def _feature_vector(desc, nbits=6):
+    """Stand-in for DBoW2 level-4 nodes (vocabulary file absent): node = first nbits of the descriptor."""
+    node = desc[:, 0].astype(np.int32) & ((1 << nbits) - 1)
+    order = np.argsort(node, kind='stable')
+    nodes, counts = np.unique(node, return_counts=True)
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return nodes.astype(np.int32), ptr, order.astype(np.int32)
+
+
+def test_search_for_triangulation(M):
+    rng = np.random.default_rng(4)
+    d2 = synth_descriptors(1200, 41)
+    d1 = synth_query_from_train(d2, 42, p_flip=0.05)[:1200]
+    d1[:, 0] = (d1[:, 0] & 0xC0) | (d2[rng.integers(0, 1200, 1200), 0] & 0x3F)
+    d2[100:160] = d2[100]                              # exact duplicates -> last-minimum tie rule
+    fv1, fv2 = _feature_vector(d1), _feature_vector(d2)
+    fv1 = (fv1[0][::2].copy(), np.concatenate([[0], np.cumsum(np.diff(fv1[1])[::2])]).astype(np.int32),
+           np.concatenate([fv1[2][fv1[1][i]:fv1[1][i + 1]] for i in range(0, len(fv1[0]), 2)]).astype(np.int32))  # nodes only in KF2
+    skip1 = (rng.random(1200) < 0.3).astype(np.uint8); skip2 = (rng.random(1200) < 0.3).astype(np.uint8)
+    nm, pairs, m12 = M.SearchForTriangulation(fv1, fv2, d1, d2, skip1, skip2)
+    ref = np.zeros(1200, np.int32)
+    L = O.lib()
+    rn = L.orc_search_for_triangulation(len(fv1[0]), O.p(fv1[0]), O.p(fv1[1]), O.p(fv1[2]), len(fv2[0]), O.p(fv2[0]), O.p(fv2[1]),
+                                        O.p(fv2[2]), O.p(d1), 1200, O.p(d2), O.p(skip1), O.p(skip2), None, None, O.p(ref))
+    assert rn == nm and np.array_equal(ref, m12) and nm > 50
+    assert pairs == [(int(i), int(ref[i])) for i in np.nonzero(ref >= 0)[0]]
+
+
+def _extract_frame(w, h, nf, seeds, lap):
+    rig = ob.RigExtractor(w, h, len(seeds), nf)
+    imgs = [synth_image(w, h, s) for s in seeds]
+    return rig, rig.extract(imgs, ob.make_params(len(seeds), nf, 20, 7, lap))
+
+
+def test_grid_candidates_match_frame_grid(M):
+    rig, res = _extract_frame(512, 512, 1500, [4100], (0, 511))
+    kps = res[0][1].copy()
+    bounds = (0.0, 512.0, 0.0, 512.0)
+    rng = np.random.default_rng(5)
+    nq = 3000
+    qx = rng.uniform(-20, 530, nq).astype(np.float32); qy = rng.uniform(-20, 530, nq).astype(np.float32)
+    lv = rng.integers(0, 8, nq).astype(np.int32)
+    qr = (rng.choice([2.5, 4.0, 7.5, 15.0], nq) * rig.scale[lv]).astype(np.float32)
+    mn = lv - 1; mx = lv.copy(); mx[::11] = -1; mn[::11] = -1     # also the "no level check" form
+    row_ptr, cand = M.grid_candidates(kps, bounds, qx, qy, qr, mn, mx)
+    g = O.lib().orc_grid_create(O.p(kps), kps.size, C.c_float(0), C.c_float(512), C.c_float(0), C.c_float(512))
+    buf = np.zeros(4096, np.int32)
+    for i in range(nq):
+        n = O.lib().orc_grid_query(C.c_void_p(g), O.p(kps), C.c_float(qx[i]), C.c_float(qy[i]), C.c_float(qr[i]), int(mn[i]), int(mx[i]),
+                                   O.p(buf), 4096)
+        assert n == row_ptr[i + 1] - row_ptr[i], i
+        assert np.array_equal(buf[:n], cand[row_ptr[i]:row_ptr[i + 1]]), i
+    O.lib().orc_grid_destroy(C.c_void_p(g))
+    assert row_ptr[-1] > 10000
+
+
+def _sbp_case(ncam, seed, nmp=5000, th=3.0, nnratio=0.8):
+    """Config 4 style: map-point descriptors come from the frame's own keypoints (70 %, with a few
+    flipped bits) or are random (30 %); predicted position = keypoint position + U(-3,3)."""
+    rng = np.random.default_rng(seed)
+    w = h = 512
+    rig, res = _extract_frame(w, h, 1500, [4200 + seed * 10 + c for c in range(ncam)], (0, 511))
+    kps = np.concatenate([r[1] for r in res]); desc = np.concatenate([r[2] for r in res])
+    cam_off = np.concatenate([[0], np.cumsum([len(r[1]) for r in res])]).astype(np.int32)
+    N = int(cam_off[-1])
+    in_view = np.zeros((nmp, 4), np.uint8); px = np.zeros((nmp, 4), np.float32); py = np.zeros((nmp, 4), np.float32)
+    lvl = np.full((nmp, 4), -1, np.int32); vc = np.zeros((nmp, 4), np.float32); md = synth_descriptors(nmp, seed + 1)
+    for i in range(nmp):
+        cams = [c for c in range(ncam) if rng.random() < (0.9 if c == 0 else 0.5)]
+        src_cam = cams[0] if cams else 0
+        k = int(rng.integers(cam_off[src_cam], cam_off[src_cam + 1]))
+        if rng.random() < 0.7:
+            flips = np.packbits(rng.random(256) < 0.06, bitorder='little')
+            md[i] = desc[k] ^ flips
+        for c in cams:
+            kk = k if c == src_cam else int(rng.integers(cam_off[c], cam_off[c + 1]))
+            in_view[i, c] = 1
+            px[i, c] = kps['x'][kk] + rng.uniform(-3, 3); py[i, c] = kps['y'][kk] + rng.uniform(-3, 3)
+            lvl[i, c] = min(7, max(0, int(kps['octave'][kk]) + int(rng.integers(0, 2))))
+            vc[i, c] = rng.choice([0.9990, 0.99])
+    occupied = (rng.random(N) < 0.05).astype(np.uint8)
+    has_obs = (rng.random(nmp) < 0.9).astype(np.uint8)
+    bad = (rng.random(nmp) < 0.02).astype(np.uint8)
+    depth = rng.uniform(1, 80, nmp).astype(np.float32)
+    l2r = r2l = None
+    if ncam >= 2:
+        nl, nr = int(cam_off[1]), int(cam_off[2] - cam_off[1])
+        l2r = np.full(nl, -1, np.int32); r2l = np.full(nr, -1, np.int32)
+        for a, b in zip(rng.permutation(nl)[:300], rng.permutation(nr)[:300]):
+            l2r[a] = b; r2l[b] = a
+    frame = dict(cam_off=cam_off, kps=kps, desc=desc, bounds=np.tile(np.array([0, w, 0, h], np.float32), (ncam, 1)),
+                 scale_factors=rig.scale, occupied=occupied, l2r=l2r, r2l=r2l)
+    points = dict(in_view=in_view, proj_x=px, proj_y=py, level=lvl, view_cos=vc, desc=md, depth=depth, bad=bad, has_obs=has_obs)
+    return frame, points, th, nnratio
+
+
+def _oracle_sbp(frame, points, th, nnratio, far, thfar):
+    L = O.lib()
+    cam_off = frame['cam_off']; ncam = len(cam_off) - 1; N = int(cam_off[-1])
+    kps = np.ascontiguousarray(frame['kps']); desc = np.ascontiguousarray(frame['desc'])
+    grids = (C.c_void_p * 4)()
+    for c in range(ncam):
+        b = frame['bounds'][c]
+        sub = np.ascontiguousarray(kps[cam_off[c]:cam_off[c + 1]])
+        grids[c] = L.orc_grid_create(O.p(sub), sub.size, C.c_float(b[0]), C.c_float(b[1]), C.c_float(b[2]), C.c_float(b[3]))
+    assigned = np.zeros(N, np.int32)
+    L.orc_search_by_projection.restype = C.c_int
+    n = L.orc_search_by_projection(ncam, O.p(cam_off), O.p(kps), O.p(desc), grids, O.p(frame['scale_factors']), O.p(frame['occupied']),
+                                   None if frame['l2r'] is None else O.p(frame['l2r']), None if frame['r2l'] is None else O.p(frame['r2l']),
+                                   None, points['in_view'].shape[0], O.p(points['in_view']), O.p(points['proj_x']), O.p(points['proj_y']),
+                                   O.p(points['level']), O.p(points['view_cos']), None, O.p(points['depth']), O.p(points['bad']),
+                                   O.p(points['has_obs']), O.p(points['desc']), C.c_float(th), int(far), C.c_float(thfar),
+                                   C.c_float(nnratio), O.p(assigned))
+    for c in range(ncam):
+        L.orc_grid_destroy(C.c_void_p(grids[c]))
+    return n, assigned
+
+
+@pytest.mark.parametrize('ncam,th,far', [(1, 1.0, False), (1, 3.0, True), (2, 3.0, False), (2, 6.0, True), (4, 3.0, False)])
+def test_search_by_projection(ncam, th, far):
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    frame, points, _, nnratio = _sbp_case(ncam, seed=ncam * 3 + int(th))
+    M = ob.ORBmatcher(nnratio)
+    nm, assigned = M.SearchByProjection(frame, points, th, far, 40.0)
+    rn, rassigned = _oracle_sbp(frame, points, th, np.float32(nnratio), far, 40.0)
+    assert rn == nm, (rn, nm)
+    assert np.array_equal(assigned, rassigned), int((assigned != rassigned).sum())
+    assert nm > 500
+
+
+def test_popc_peak_reports_a_rate():
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    assert ob.popc_peak() > 100.0
