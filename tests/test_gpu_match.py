@@ -123,9 +123,12 @@ def _feature_vector(desc, nbits=6):
 def test_search_for_triangulation(M):
     rng = np.random.default_rng(4)
     d2 = synth_descriptors(1200, 41)
-    d1 = synth_query_from_train(d2, 42, p_flip=0.05)[:1200]
-    d1[:, 0] = (d1[:, 0] & 0xC0) | (d2[rng.integers(0, 1200, 1200), 0] & 0x3F)
     d2[100:160] = d2[100]                              # exact duplicates -> last-minimum tie rule
+    src = rng.integers(0, 1200, 1200)
+    flips = np.packbits(rng.random((1200, 256)) < 0.05, axis=1, bitorder='little')
+    flips[:, 0] &= 0xC0                                # keep the node bits: d1[i] shares the node of d2[src[i]]
+    d1 = d2[src] ^ flips
+    d1[::5] = synth_descriptors(240, 43)               # unrelated rows
     fv1, fv2 = _feature_vector(d1), _feature_vector(d2)
     fv1 = (fv1[0][::2].copy(), np.concatenate([[0], np.cumsum(np.diff(fv1[1])[::2])]).astype(np.int32),
            np.concatenate([fv1[2][fv1[1][i]:fv1[1][i + 1]] for i in range(0, len(fv1[0]), 2)]).astype(np.int32))  # nodes only in KF2
@@ -135,7 +138,7 @@ def test_search_for_triangulation(M):
     L = O.lib()
     rn = L.orc_search_for_triangulation(len(fv1[0]), O.p(fv1[0]), O.p(fv1[1]), O.p(fv1[2]), len(fv2[0]), O.p(fv2[0]), O.p(fv2[1]),
                                         O.p(fv2[2]), O.p(d1), 1200, O.p(d2), O.p(skip1), O.p(skip2), None, None, O.p(ref))
-    assert rn == nm and np.array_equal(ref, m12) and nm > 50
+    assert rn == nm and np.array_equal(ref, m12) and nm > 150, (rn, nm)
     assert pairs == [(int(i), int(ref[i])) for i in np.nonzero(ref >= 0)[0]]
 
 
@@ -164,7 +167,7 @@ def test_grid_candidates_match_frame_grid(M):
         assert n == row_ptr[i + 1] - row_ptr[i], i
         assert np.array_equal(buf[:n], cand[row_ptr[i]:row_ptr[i + 1]]), i
     O.lib().orc_grid_destroy(C.c_void_p(g))
-    assert row_ptr[-1] > 10000
+    assert row_ptr[-1] > 3000
 
 
 def _sbp_case(ncam, seed, nmp=5000, th=3.0, nnratio=0.8):
