@@ -328,7 +328,7 @@ def main():
 
     # ---------------- CPU baseline (rank 0, N == 1 only; bounded sample) ----------------
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
         threads = os.cpu_count() or 1
         cpu_oracle_run(2, threads)                      # warm-up (page in, thread pool)
         nfr, done, spent = 32, 0, 0.0
