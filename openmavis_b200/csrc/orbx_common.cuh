@@ -28,6 +28,8 @@ struct LevelGeom {
     // FAST cell grid (src/ORBextractor.cc:709-741)
     int n_cols, n_rows, w_cell, h_cell, max_bx, max_by;
     int cell_base;             // first cell of this level in the per-image cell numbering
+    int fast_tile_base;        // first FAST tile (CTA) of this level in the per-image tile numbering
+    int fast_tiles_x;          // tiles per cell row = ceil(n_cols / Geom::fast_g)
     int cell_cap;              // candidate slots per cell: ceil(w_cell/2)*ceil(h_cell/2) (3x3 strict NMS bound)
     long long cand_off;        // offset (u32 slots) of this level's cell slots / linear list inside an image's arena
     int cand_cap;              // n_cells * cell_cap
@@ -48,6 +50,9 @@ struct Geom {
     int kp_per_image;          // sum of kp_cap
     int out_cap;               // rows of the final per-image outputs
     int fma_mode;
+    int fast_g;                // cells per FAST tile
+    int fast_ip, fast_ymax;    // shared-memory row pitch (bytes, multiple of 32) and max tested rows of a FAST tile
+    int fast_total_tiles;      // FAST tiles per image over all levels
     LevelGeom lv[kMaxLevels];
 };
 

@@ -56,7 +56,6 @@ struct orbx_extractor {
     Geom G;
     BlurTiles blur_tiles;
     int blur_total_tiles = 0;
-    int fast_tile_pitch = 0;
     size_t fast_smem = 0, oct_smem = 0;
     int oct_list_cap = 0;
     long long pyr_bytes_per_batch = 0;
@@ -136,8 +135,21 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     }
     G.total_cells = cell_base; G.cand_per_image = cand_off; G.kp_per_image = kp_off; G.out_cap = kp_off;
     ex->pyr_bytes_per_batch = plane_off;
-    ex->fast_tile_pitch = (max_cell_w + 3) & ~3;
-    ex->fast_smem = (size_t)2 * ex->fast_tile_pitch * max_cell_h;
+    // FAST tiles: fast_g adjacent cells of a cell row per CTA
+    G.fast_g = kFastMaxG;
+    int ftiles = 0;
+    for (int l = 0; l < nl; l++) {
+        LevelGeom &L = G.lv[l];
+        L.fast_tiles_x = (L.n_cols + G.fast_g - 1) / G.fast_g;
+        L.fast_tile_base = ftiles;
+        ftiles += L.fast_tiles_x * L.n_rows;
+    }
+    G.fast_total_tiles = ftiles;
+    G.fast_ymax = max_cell_h - 6;
+    G.fast_ip = (std::min(G.fast_g, 64) * (max_cell_w - 6) + 21 + 15 + 31) & ~31;
+    ex->fast_smem = fast_smem_bytes(G.fast_ip, G.fast_ymax);
+    if (ex->fast_smem > 200 * 1024 || (size_t)(G.fast_ymax + 6) * G.fast_ip > 65535)
+        return fail(ORBX_ERR_INVALID, "FAST tile does not fit in shared memory");
     ex->oct_list_cap = max_list;
     ex->oct_smem = oct_work_bytes(max_list);
     if (ex->oct_smem > 200 * 1024) return fail(ORBX_ERR_INVALID, "nfeatures too large for the quadtree workspace");
@@ -346,8 +358,7 @@ static int enqueue(orbx_extractor *ex, int n, const uint8_t *d_images, const orb
     k_blur<<<dim3(ex->blur_total_tiles, n), 256, 0, s>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles);
     launches++;
     if (prof) ORBX_CUDA(cudaEventRecord(ev[2], s));
-    k_fast<<<dim3(G.total_cells, n), 256, ex->fast_smem, s>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt,
-                                                              ex->fast_tile_pitch);
+    k_fast<<<dim3(G.fast_total_tiles, n), kFastThreads, ex->fast_smem, s>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, 0);
     launches++;
     if (prof) ORBX_CUDA(cudaEventRecord(ev[3], s));
     k_octree<<<dim3(nl, n), 512, ex->oct_smem, s>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,

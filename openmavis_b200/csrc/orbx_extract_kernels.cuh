@@ -164,131 +164,254 @@ __global__ void __launch_bounds__(256) k_blur(const uint8_t *__restrict__ pyr, u
 
 // ------------------------------------------------------------------------------------------------------
 // K2  per-cell FAST-9-16 with non-max suppression and the iniThFAST -> minThFAST retry
-// (src/ORBextractor.cc:726-794; cv::FAST semantics in SURVEY.md §8a-a3).  One block per (cell, image).
-// The cell ROI and its score map live in shared memory; candidates are emitted in row-major order with a
-// ballot/popc prefix so the output order equals OpenCV's.
+// (src/ORBextractor.cc:726-794; cv::FAST semantics in SURVEY.md §8a-a3).
+//
+// Formulation.  With ring values r[0..15] around a centre v,
+//     A = min over the 16 arcs of 9 of (max of the arc),   B = max over the arcs of (min of the arc),
+//     S = max(v - A, B - v) - 1
+// is exactly cornerScore<16>() of every pixel that is a corner, and a pixel is a corner at threshold t iff
+// S >= t (an arc of 9 with v - r > t exists iff v - A > t; the bright case is symmetric; the two cases
+// exclude each other because two arcs of 9 overlap on a 16-ring).  S does not depend on t, and cv::FAST's
+// 3x3 non-max suppression keeps p iff S(p) is strictly greater than the scores of its 8 neighbours inside
+// the tested area of the SAME cell ROI (outside it the score buffer is 0), so
+//     keypoints of a cell at threshold t  =  { p : S(p) >= t, S(p) > S(q) for the neighbours q of the cell }.
+// The tested areas of the cells tile the level without gaps or overlap, which makes the work regular:
+// one CTA = one tile of up to G adjacent cells of a cell row, staged once in shared memory.
+//   1. quick reject, 4 pixels per thread with byte-SIMD (VABSDIFF4): a corner needs |v - r| > t on at least one
+//      of the ring pixels {0, 8} and one of {4, 12};
+//   2. survivors are compacted into a per-warp queue and scored two at a time with packed u16x2 3-input
+//      min/max (VIMNMX3.U16x2): no divergence, no per-threshold corner test;
+//   3. sparse sweep of the score map: strict 3x3 maximum inside the cell -> keep bitmap;
+//   4. cells without a keypoint repeat 1-3 with minThFAST (block-uniform, rare);
+//   5. one warp per cell emits the kept pixels in row-major order (the order of cv::FAST) from the bitmap.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool cell_rect(const LevelGeom &L, int i, int j, int &x0, int &y0, int &cw, int &ch) {
-    const int ini_y = kFastBorder + i * L.h_cell;
-    if (ini_y >= L.max_by - 3) return false;
-    const int max_y = min(ini_y + L.h_cell + 6, L.max_by);
-    const int ini_x = kFastBorder + j * L.w_cell;
-    if (ini_x >= L.max_bx - 6) return false;
-    const int max_x = min(ini_x + L.w_cell + 6, L.max_bx);
-    x0 = ini_x; y0 = ini_y; cw = max_x - ini_x; ch = max_y - ini_y;
-    return true;
+constexpr int kFastThreads = 256;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastQueue = 192;               // per-warp survivor queue (u16 entries): < 64 left + up to 128 new
+constexpr int kFastMaxG = 8;
+
+// shared memory of one CTA:
+//   img [(ymax + 6)][ip]  level pixels, row 0 = tile row -3, column 0 = plane column pc0 (16-byte aligned)
+//   sc  [(ymax + 2)][ip]  scores, same column indexing, rows 0 and Y+1 stay zero
+//   bm  [ymax][ip / 32]   keep bitmap (rounded up to 16 bytes)
+//   q   [kFastWarps][kFastQueue] u16, has [kFastMaxG] int
+__host__ __device__ inline size_t fast_zero_bytes(int ip, int ymax) { return ((size_t)(ymax + 2) * ip + (size_t)ymax * (ip >> 5) * 4 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t fast_smem_bytes(int ip, int ymax) {
+    return (size_t)(ymax + 6) * ip + fast_zero_bytes(ip, ymax) + (size_t)kFastWarps * kFastQueue * 2 + kFastMaxG * sizeof(int);
 }
 
-// score of a pixel that is known to be a corner: max over the 16 arcs of 9 of min(d) (dark) or min(-d)
-// (bright), minus 1 == cornerScore<16>() for every threshold the pixel passes.
-__device__ __forceinline__ int arc9_max_min(const int *d) {
-    int m3[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) m3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
-    int best = -1000;
-#pragma unroll
-    for (int k = 0; k < 16; k++) best = max(best, min(min(m3[k], m3[(k + 3) & 15]), m3[(k + 6) & 15]));
-    return best;
+__device__ __forceinline__ uint32_t bytes_gt(uint32_t ad, uint32_t t1x4) {
+    // per byte: 0x80 where ad > t (t1x4 = (t + 1) * 0x01010101, t <= 126)
+    return (ad | ((ad | 0x80808080u) - t1x4)) & 0x80808080u;
 }
 
-__global__ void __launch_bounds__(256) k_fast(const uint8_t *__restrict__ pyr, Geom G,
-                                              const orbx_image_params *__restrict__ params, uint32_t *__restrict__ cells,
-                                              int *__restrict__ cell_cnt, int tile_pitch) {
-    extern __shared__ uint8_t smem[];
-    __shared__ int s_warp[8];
-    __shared__ int s_base;
-    const int b = blockIdx.y;
+// scores entries e0 / e1 (byte offsets of two centre pixels inside img) with packed u16x2 arithmetic
+__device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *sc, int ip, int e0, int e1, int t) {
+    const uint8_t *p0 = img + e0, *p1 = img + e1;
+    const int o[16] = {3 * ip, 3 * ip + 1, 2 * ip + 2, ip + 3, 3, -ip + 3, -2 * ip + 2, -3 * ip + 1,
+                       -3 * ip, -3 * ip - 1, -2 * ip - 2, -ip - 3, -3, ip - 3, 2 * ip - 2, 3 * ip - 1};
+    uint32_t r[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) r[k] = (uint32_t)p0[o[k]] | ((uint32_t)p1[o[k]] << 16);
+    uint32_t mx3[16], mn3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mx3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        mn3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+    uint32_t A = 0xFFFFFFFFu, B = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t a0 = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+        const uint32_t a1 = __vimax3_u16x2(mx3[k + 1], mx3[(k + 4) & 15], mx3[(k + 7) & 15]);
+        A = __vimin3_u16x2(A, a0, a1);
+        const uint32_t b0 = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+        const uint32_t b1 = __vimin3_u16x2(mn3[k + 1], mn3[(k + 4) & 15], mn3[(k + 7) & 15]);
+        B = __vimax3_u16x2(B, b0, b1);
+    }
+    const int v0 = p0[0], v1 = p1[0];
+    const int s0 = max(v0 - (int)(A & 0xFFFFu), (int)(B & 0xFFFFu) - v0) - 1;
+    const int s1 = max(v1 - (int)(A >> 16), (int)(B >> 16) - v1) - 1;
+    if (s0 >= t) sc[e0] = (uint8_t)s0;      // score map shares the column indexing of img; row offset applied by the caller
+    if (s1 >= t) sc[e1] = (uint8_t)s1;
+}
+
+__global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict__ pyr, Geom G,
+                                                       const orbx_image_params *__restrict__ params,
+                                                       uint32_t *__restrict__ cells, int *__restrict__ cell_cnt, int img0) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int b = blockIdx.y + img0;
     int lvl = 0;
-    while (lvl + 1 < G.nlevels && (int)blockIdx.x >= G.lv[lvl + 1].cell_base) lvl++;
+    while (lvl + 1 < G.nlevels && (int)blockIdx.x >= G.lv[lvl + 1].fast_tile_base) lvl++;
     const LevelGeom &L = G.lv[lvl];
-    const int cell = blockIdx.x - L.cell_base;
-    const int ci = cell / L.n_cols, cj = cell - ci * L.n_cols;
-    int *cnt_out = cell_cnt + (long long)b * G.total_cells + blockIdx.x;
-    int x0, y0, cw, ch;
-    if (!cell_rect(L, ci, cj, x0, y0, cw, ch) || cw < 7 || ch < 7) {
-        if (threadIdx.x == 0) *cnt_out = 0;
+    const int tile = blockIdx.x - L.fast_tile_base;
+    const int ci = tile / L.fast_tiles_x, jt = tile - ci * L.fast_tiles_x;
+    const int j0 = jt * G.fast_g, j1 = min(j0 + G.fast_g, L.n_cols);
+    const int ncell = j1 - j0;
+    const int wc = L.w_cell;
+    // tested area of the tile in level coordinates (see the header comment of this kernel)
+    const int tx0 = kEdge + j0 * wc, tx1 = min(kEdge + j1 * wc, L.w - kEdge);
+    const int ty0 = kEdge + ci * L.h_cell, ty1 = min(ty0 + L.h_cell, L.h - kEdge);
+    int *cnt_out = cell_cnt + (long long)b * G.total_cells + L.cell_base + ci * L.n_cols + j0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tx1 <= tx0 || ty1 <= ty0) {
+        if (tid < ncell) cnt_out[tid] = 0;
         return;
     }
-    uint8_t *tile = smem;                                  // [ch][tile_pitch]
-    uint8_t *score = smem + (size_t)tile_pitch * (L.h_cell + 6);   // same shape
-    const uint8_t *src = plane_ptr(pyr, L, b) + (long long)(kYO + y0) * L.pitch + kXO + x0;
-    for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
-        const int r = i / cw, c = i - r * cw;
-        tile[r * tile_pitch + c] = __ldg(src + (long long)r * L.pitch + c);
+    const int X = tx1 - tx0, Y = ty1 - ty0;
+    const int ip = G.fast_ip, bw = ip >> 5;
+    uint8_t *img = smem;
+    uint8_t *sc = img + (size_t)ip * (G.fast_ymax + 6);
+    uint32_t *bm = reinterpret_cast<uint32_t *>(sc + (size_t)ip * (G.fast_ymax + 2));
+    unsigned short *q0 = reinterpret_cast<unsigned short *>(sc + fast_zero_bytes(ip, G.fast_ymax));
+    unsigned short *q = q0 + wid * kFastQueue;
+    int *has = reinterpret_cast<int *>(q0 + kFastWarps * kFastQueue);
+    // ---- stage the tile: plane rows kYO + ty0 - 3 .. kYO + ty1 + 3, 16-byte columns from pc0
+    const int pc0 = (kXO + tx0 - 3) & ~15;
+    const int c0 = kXO + tx0 - pc0;                 // smem column of level column tx0 (>= 3)
+    const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
+    {
+        const uint8_t *src = plane_ptr(pyr, L, b) + (long long)(kYO + ty0 - 3) * L.pitch + pc0;
+        const int total = (Y + 6) * nvec;
+        for (int i = tid; i < total; i += kFastThreads) {
+            const int r = i / nvec, c = i - r * nvec;
+            *reinterpret_cast<uint4 *>(img + r * ip + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * L.pitch + 16 * c));
+        }
+        uint4 *z = reinterpret_cast<uint4 *>(sc);             // score map and bitmap are contiguous
+        const int nz = (int)(fast_zero_bytes(ip, G.fast_ymax) >> 4);
+        for (int i = tid; i < nz; i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
+        if (tid < kFastMaxG) has[tid] = 0;
     }
-    const int dw = cw - 6, dh = ch - 6;
-    uint32_t *out = cells + (long long)b * G.cand_per_image + L.cand_off + (long long)cell * L.cell_cap;
-    const int off_x = cj * L.w_cell, off_y = ci * L.h_cell;
+    __syncthreads();
     const orbx_image_params prm = params[b];
-    int total = 0;
+    const int t_ini = min(max(prm.ini_th_fast, 0), 255), t_min = min(max(prm.min_th_fast, 0), 255);
+    const int w0 = c0 >> 2, w1 = (c0 + X - 1) >> 2;    // words of a row that hold tested pixels
+    const int nw = w1 - w0 + 1;
+    unsigned retry = 0;                                 // cells (bit k = cell j0 + k) processed in this pass; 0 = all
+    uint8_t *sc1 = sc + ip;                             // score row of tile row 0
     for (int pass = 0; pass < 2; pass++) {
-        const int t = min(max(pass == 0 ? prm.ini_th_fast : prm.min_th_fast, 0), 255);
-        for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) score[(i / cw) * tile_pitch + (i % cw)] = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < dw * dh; i += blockDim.x) {
-            const int r = i / dw + 3, c = i - (i / dw) * dw + 3;
-            const uint8_t *p = tile + r * tile_pitch + c;
-            const int v = p[0];
-            // high-speed reject (necessary condition for an arc of 9): each diametral pair needs a pass
-            const int lo = v - t, hi = v + t;
-            const int a0 = p[3 * tile_pitch], a8 = p[-3 * tile_pitch];
-            if (!((a0 < lo) || (a8 < lo) || (a0 > hi) || (a8 > hi))) continue;
-            const int a4 = p[3], a12 = p[-3];
-            if (!((a4 < lo) || (a12 < lo) || (a4 > hi) || (a12 > hi))) continue;
-            int d[16];
-            d[0] = v - a0; d[4] = v - a4; d[8] = v - a8; d[12] = v - a12;
-            d[1] = v - p[3 * tile_pitch + 1]; d[2] = v - p[2 * tile_pitch + 2]; d[3] = v - p[tile_pitch + 3];
-            d[5] = v - p[-tile_pitch + 3]; d[6] = v - p[-2 * tile_pitch + 2]; d[7] = v - p[-3 * tile_pitch + 1];
-            d[9] = v - p[-3 * tile_pitch - 1]; d[10] = v - p[-2 * tile_pitch - 2]; d[11] = v - p[-tile_pitch - 3];
-            d[13] = v - p[tile_pitch - 3]; d[14] = v - p[2 * tile_pitch - 2]; d[15] = v - p[3 * tile_pitch - 1];
-            uint32_t md = 0, mb = 0;
+        const int t = pass == 0 ? t_ini : t_min;
+        const uint32_t t1x4 = (uint32_t)(min(t, 126) + 1) * 0x01010101u;
+        // ---- 1 + 2: quick reject and pair scoring, warp-local
+        int qn = 0;
+        const int items = Y * nw;
+        for (int it0 = wid * 32; it0 < items; it0 += kFastWarps * 32) {
+            const int it = it0 + lane;
+            uint32_t m = 0;
+            int row = 0, wi = 0;
+            if (it < items) {
+                row = it / nw; wi = w0 + (it - row * nw);
+                const uint32_t *c = reinterpret_cast<const uint32_t *>(img + (row + 3) * ip) + wi;
+                const uint32_t v = c[0], pv = c[-1], nx = c[1];
+                const uint32_t up = *(reinterpret_cast<const uint32_t *>(img + row * ip) + wi);
+                const uint32_t dn = *(reinterpret_cast<const uint32_t *>(img + (row + 6) * ip) + wi);
+                const uint32_t lf = __byte_perm(pv, v, 0x4321), rt = __byte_perm(v, nx, 0x6543);
+                const uint32_t gv = bytes_gt(__vabsdiffu4(v, up), t1x4) | bytes_gt(__vabsdiffu4(v, dn), t1x4);
+                const uint32_t gh = bytes_gt(__vabsdiffu4(v, lf), t1x4) | bytes_gt(__vabsdiffu4(v, rt), t1x4);
+                m = gv & gh;
+                // bytes outside the tested columns, or (second pass) outside the cells that are retried
+                const int x_first = 4 * wi - c0;           // level column - tx0 of byte 0
 #pragma unroll
-            for (int k = 0; k < 16; k++) { md |= (d[k] > t ? 1u : 0u) << k; mb |= (d[k] < -t ? 1u : 0u) << k; }
-            md |= md << 16; mb |= mb << 16;
-            uint32_t xd = md & (md >> 1); xd &= xd >> 2; xd &= xd >> 4; xd &= md >> 8;
-            uint32_t xb = mb & (mb >> 1); xb &= xb >> 2; xb &= xb >> 4; xb &= mb >> 8;
-            int sc = 0;
-            if (xd & 0xFFFF) {
-                sc = arc9_max_min(d) - 1;
-            } else if (xb & 0xFFFF) {
-#pragma unroll
-                for (int k = 0; k < 16; k++) d[k] = -d[k];
-                sc = arc9_max_min(d) - 1;
+                for (int k = 0; k < 4; k++) {
+                    const int xt = x_first + k;
+                    bool ok = xt >= 0 && xt < X;
+                    if (ok && retry) ok = (retry >> (xt / wc)) & 1u;
+                    if (!ok) m &= ~(0x80u << (8 * k));
+                }
             }
-            if (sc > 0) score[r * tile_pitch + c] = (uint8_t)sc;
+            // append the survivors of this warp iteration to the queue (order inside the queue is irrelevant)
+            int base = qn;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool s = (m >> (8 * k + 7)) & 1u;
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, s);
+                if (s) q[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((row + 3) * ip + 4 * wi + k);
+                base += __popc(bal);
+            }
+            qn = base;
+            __syncwarp();
+            while (qn >= 64) {
+                qn -= 64;
+                fast_score_pair(img, sc1 - 3 * ip, ip, q[qn + lane], q[qn + 32 + lane], t);
+                __syncwarp();
+            }
+        }
+        if (qn > 0) {
+            const int e0 = q[lane < qn ? lane : 0], e1 = q[lane + 32 < qn ? lane + 32 : 0];
+            fast_score_pair(img, sc1 - 3 * ip, ip, e0, e1, t);
         }
         __syncthreads();
-        // 3x3 strict non-max suppression + ordered compaction
-        total = 0;
-        for (int s = 0; s < dw * dh; s += blockDim.x) {
-            const int i = s + threadIdx.x;
-            bool keep = false;
-            int r = 0, c = 0, sc = 0;
-            if (i < dw * dh) {
-                r = i / dw + 3; c = i - (i / dw) * dw + 3;
-                const uint8_t *q = score + r * tile_pitch + c;
-                sc = q[0];
-                keep = sc > 0 && sc > q[-1] && sc > q[1] && sc > q[-tile_pitch - 1] && sc > q[-tile_pitch] &&
-                       sc > q[-tile_pitch + 1] && sc > q[tile_pitch - 1] && sc > q[tile_pitch] && sc > q[tile_pitch + 1];
-            }
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-            if (lane == 0) s_warp[wid] = __popc(bal);
-            __syncthreads();
-            int before = 0, all = 0;
+        // ---- 3: strict 3x3 maximum inside the cell (sparse sweep over the score words)
+        for (int it = tid; it < items; it += kFastThreads) {
+            const int row = it / nw, wi = w0 + (it - row * nw);
+            const uint32_t wv = *(reinterpret_cast<const uint32_t *>(sc1 + row * ip) + wi);
+            if (wv == 0) continue;
 #pragma unroll
-            for (int k = 0; k < 8; k++) { const int n = s_warp[k]; all += n; if (k < wid) before += n; }
-            if (keep) {
-                const int pos = total + before + __popc(bal & ((1u << lane) - 1));
-                if (pos < L.cell_cap) out[pos] = cand_pack(c + off_x, r + off_y, sc);
+            for (int k = 0; k < 4; k++) {
+                const int s = (wv >> (8 * k)) & 0xFF;
+                if (s == 0) continue;
+                const int col = 4 * wi + k, xt = col - c0;
+                const int cj = xt / wc, xl = xt - cj * wc;
+                if (retry && !((retry >> cj) & 1u)) continue;
+                const uint8_t *n = sc1 + row * ip + col;
+                bool keep = s > n[-ip] && s > n[ip];
+                if (xl > 0) keep = keep && s > n[-1] && s > n[-ip - 1] && s > n[ip - 1];
+                if (xl < wc - 1) keep = keep && s > n[1] && s > n[-ip + 1] && s > n[ip + 1];
+                if (keep) {
+                    atomicOr(&bm[row * bw + (col >> 5)], 1u << (col & 31));
+                    has[cj] = 1;
+                }
             }
-            total += all;
-            __syncthreads();
         }
-        if (total > 0) break;
+        __syncthreads();
+        // ---- 4: cells that found nothing are repeated with minThFAST (src/ORBextractor.cc:760-782)
+        if (pass == 0) {
+            retry = 0;
+            for (int k = 0; k < ncell; k++) if (!has[k]) retry |= 1u << k;
+            if (retry == 0 || t_min >= t_ini) break;
+        }
     }
-    if (threadIdx.x == 0) *cnt_out = min(total, L.cell_cap);
-    (void)s_base;
+    // ---- 5: one warp per cell, rows in parallel, row-major emission from the bitmap
+    for (int k = wid; k < ncell; k += kFastWarps) {
+        const int cx0 = c0 + k * wc, cx1 = min(cx0 + wc, c0 + X);    // smem columns of the cell
+        uint32_t *out = cells + (long long)b * G.cand_per_image + L.cand_off + (long long)(ci * L.n_cols + j0 + k) * L.cell_cap;
+        int total = 0;
+        if (cx1 > cx0) {
+            const int wa = cx0 >> 5, wb = (cx1 - 1) >> 5;
+            for (int r0 = 0; r0 < Y; r0 += 32) {
+                const int row = r0 + lane;
+                int n = 0;
+                if (row < Y)
+                    for (int w = wa; w <= wb; w++) {
+                        uint32_t bits = bm[row * bw + w];
+                        if (w == wa) bits &= 0xFFFFFFFFu << (cx0 & 31);
+                        if (w == wb && (cx1 & 31)) bits &= (1u << (cx1 & 31)) - 1;
+                        n += __popc(bits);
+                    }
+                int inc = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
+                int pos = total + inc - n;
+                total += __shfl_sync(0xFFFFFFFFu, inc, 31);
+                if (n)
+                    for (int w = wa; w <= wb; w++) {
+                        uint32_t bits = bm[row * bw + w];
+                        if (w == wa) bits &= 0xFFFFFFFFu << (cx0 & 31);
+                        if (w == wb && (cx1 & 31)) bits &= (1u << (cx1 & 31)) - 1;
+                        while (bits) {
+                            const int bit = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const int col = 32 * w + bit;
+                            // border-relative coordinates (src/ORBextractor.cc:784-791): level coordinate - 16
+                            if (pos < L.cell_cap)
+                                out[pos] = cand_pack(tx0 + (col - c0) - kFastBorder, ty0 + row - kFastBorder, sc1[row * ip + col]);
+                            pos++;
+                        }
+                    }
+            }
+        }
+        if (lane == 0) cnt_out[k] = min(total, L.cell_cap);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
