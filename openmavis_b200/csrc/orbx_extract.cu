@@ -56,7 +56,8 @@ struct orbx_extractor {
     Geom G;
     BlurTiles blur_tiles;
     int blur_total_tiles = 0;
-    size_t fast_smem = 0, oct_smem = 0;
+    size_t fast_smem = 0, oct_smem = 0, rsz_smem = 0;
+    int rsz_rows = 0, rsz_pitch = 0;
     int oct_list_cap = 0;
     long long pyr_bytes_per_batch = 0;
     std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
@@ -136,7 +137,8 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     G.total_cells = cell_base; G.cand_per_image = cand_off; G.kp_per_image = kp_off; G.out_cap = kp_off;
     ex->pyr_bytes_per_batch = plane_off;
     // FAST tiles: fast_g adjacent cells of a cell row per CTA
-    G.fast_g = kFastMaxG;
+    // entries of the survivor queue pack (row, column) into 16 bits: the staged tile must be at most 512 columns wide
+    G.fast_g = std::max(1, std::min(kFastMaxG, (512 - 68) / std::max(1, max_cell_w - 6)));
     int ftiles = 0;
     for (int l = 0; l < nl; l++) {
         LevelGeom &L = G.lv[l];
@@ -148,7 +150,7 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     G.fast_ymax = max_cell_h - 6;
     G.fast_ip = (std::min(G.fast_g, 64) * (max_cell_w - 6) + 21 + 15 + 31) & ~31;
     ex->fast_smem = fast_smem_bytes(G.fast_ip, G.fast_ymax);
-    if (ex->fast_smem > 200 * 1024 || (size_t)(G.fast_ymax + 6) * G.fast_ip > 65535)
+    if (ex->fast_smem > 200 * 1024 || G.fast_ip > (1 << kFastColBits) || G.fast_ymax + 6 >= 128)
         return fail(ORBX_ERR_INVALID, "FAST tile does not fit in shared memory");
     ex->oct_list_cap = max_list;
     ex->oct_smem = oct_work_bytes(max_list);
@@ -268,6 +270,18 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
             orbx_resize_taps(G.lv[l - 1].w, G.lv[l].w, taps.data() + G.lv[l].tap_x);
             orbx_resize_taps(G.lv[l - 1].h, G.lv[l].h, taps.data() + G.lv[l].tap_y);
         }
+        // staged source extent of the largest resize tile (rows, 16-byte aligned columns)
+        for (int l = 1; l < nlevels; l++) {
+            const ResizeTap *tx = taps.data() + G.lv[l].tap_x, *ty = taps.data() + G.lv[l].tap_y;
+            for (int y0 = 0; y0 < G.lv[l].h; y0 += kRszTH)
+                ex->rsz_rows = std::max(ex->rsz_rows, ty[std::min(y0 + kRszTH, G.lv[l].h) - 1].s1 - ty[y0].s0 + 1);
+            for (int x0 = 0; x0 < G.lv[l].w; x0 += kRszTW)
+                ex->rsz_pitch = std::max(ex->rsz_pitch, ((tx[std::min(x0 + kRszTW, G.lv[l].w) - 1].s1 - (tx[x0].s0 & ~15) + 16) >> 4) << 4);
+        }
+        ex->rsz_smem = resize_smem_bytes(ex->rsz_rows, ex->rsz_pitch);
+        if (ex->rsz_smem > 200 * 1024) { orbx_extractor_destroy(ex); return fail(ORBX_ERR_INVALID, "scale factor too large for the resize tile"); }
+        if (ex->rsz_smem > 48 * 1024)
+            EX_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->rsz_smem));
         EX_CUDA(dalloc(&ex->d_taps, (size_t)ntap));
         EX_CUDA(cudaMemcpy(ex->d_taps, taps.data(), ntap * sizeof(ResizeTap), cudaMemcpyHostToDevice));
         static const signed char pat[1024] = {ORBX_PATTERN_VALUES};
@@ -343,19 +357,18 @@ static int enqueue(orbx_extractor *ex, int n, const uint8_t *d_images, const orb
     {   // pyramid
         const LevelGeom &L0 = G.lv[0];
         const int chunks = (kXO + L0.w + kEdge + 15) >> 4;
-        dim3 grid((chunks * L0.rows + 255) / 256, n);
-        k_level0<<<grid, 256, 0, s>>>(d_images, (long long)ex->width * ex->height, ex->width, ex->d_pyr, L0);
+        dim3 grid((chunks * ((L0.rows + kL0Rows - 1) / kL0Rows) + 255) / 256, n);
+        k_level0<<<grid, 256, 0, s>>>(d_images, (long long)ex->width * ex->height, ex->width, ex->d_pyr, L0, 0);
         launches++;
         for (int l = 1; l < nl; l++) {
             const LevelGeom &D = G.lv[l];
-            const int ch = (kXO + D.w + kEdge + 3) >> 2;
-            dim3 g((ch * D.rows + 255) / 256, n);
-            k_resize<<<g, 256, 0, s>>>(ex->d_pyr, G.lv[l - 1], D, ex->d_taps);
+            dim3 g(((D.w + kRszTW - 1) / kRszTW) * ((D.h + kRszTH - 1) / kRszTH), n);
+            k_resize<<<g, kRszThreads, ex->rsz_smem, s>>>(ex->d_pyr, G.lv[l - 1], D, ex->d_taps, ex->rsz_rows, ex->rsz_pitch, 0);
             launches++;
         }
     }
     if (prof) ORBX_CUDA(cudaEventRecord(ev[1], s));
-    k_blur<<<dim3(ex->blur_total_tiles, n), 256, 0, s>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles);
+    k_blur<<<dim3(ex->blur_total_tiles, n), kBlurWarps * 32, kBlurSmem, s>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles, 0);
     launches++;
     if (prof) ORBX_CUDA(cudaEventRecord(ev[2], s));
     k_fast<<<dim3(G.fast_total_tiles, n), kFastThreads, ex->fast_smem, s>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, 0);

@@ -7,6 +7,8 @@
 // (level-major), so one launch per stage covers all cameras x frames.
 #pragma once
 
+#include <limits.h>
+
 #include "math_core.cuh"
 #include "octree_core.cuh"
 #include "orbx_common.cuh"
@@ -24,89 +26,166 @@ __device__ __forceinline__ uint8_t *plane_ptr(uint8_t *arena, const LevelGeom &L
 
 // ------------------------------------------------------------------------------------------------------
 // K1a  level 0: copyMakeBorder(image, temp, 19.., BORDER_REFLECT_101)  (src/ORBextractor.cc:1094-1101)
-// one thread = 16 output bytes of one plane row (one 128-bit store)
+// one thread = 16 output bytes (one 128-bit store) of kL0Rows consecutive plane rows: the loads of all rows are
+// issued before the first store.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ img, long long img_bytes, int img_stride,
-                                                uint8_t *__restrict__ pyr, LevelGeom L) {
-    const int chunks = (kXO + L.w + kEdge + 15) >> 4;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= chunks * L.rows) return;
-    const int row = idx / chunks, c0 = (idx - row * chunks) << 4;
-    const int b = blockIdx.y;
-    const uint8_t *src = img + (long long)b * img_bytes;
-    const int iy = orbx_reflect101(row - kYO, L.h);
-    const uint8_t *srow = src + (long long)iy * img_stride;
-    uint4 v;
-    const int x0 = c0 - kXO;
-    if (x0 >= 0 && x0 + 16 <= L.w && ((reinterpret_cast<uintptr_t>(srow + x0) & 15) == 0)) {
-        v = __ldg(reinterpret_cast<const uint4 *>(srow + x0));
-    } else {
-        uint32_t wds[4];
+constexpr int kL0Rows = 4;
+
+__device__ __forceinline__ uint4 level0_chunk(const uint8_t *__restrict__ srow, int x0, int w) {
+    if (x0 >= 0 && x0 + 16 <= w && ((reinterpret_cast<uintptr_t>(srow + x0) & 15) == 0))
+        return __ldg(reinterpret_cast<const uint4 *>(srow + x0));
+    uint32_t wds[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t wv = 0;
+    for (int k = 0; k < 4; k++) {
+        uint32_t wv = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int x = x0 + 4 * k + j;
-                x = max(-kEdge, min(L.w - 1 + kEdge, x));
-                wv |= (uint32_t)__ldg(srow + orbx_reflect101(x, L.w)) << (8 * j);
-            }
-            wds[k] = wv;
+        for (int j = 0; j < 4; j++) {
+            int x = x0 + 4 * k + j;
+            x = max(-kEdge, min(w - 1 + kEdge, x));
+            wv |= (uint32_t)__ldg(srow + orbx_reflect101(x, w)) << (8 * j);
         }
-        v = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        wds[k] = wv;
     }
-    *reinterpret_cast<uint4 *>(plane_ptr(pyr, L, b) + (long long)row * L.pitch + c0) = v;
+    return make_uint4(wds[0], wds[1], wds[2], wds[3]);
+}
+
+__global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ img, long long img_bytes, int img_stride,
+                                                uint8_t *__restrict__ pyr, LevelGeom L, int img0) {
+    const int chunks = (kXO + L.w + kEdge + 15) >> 4;
+    const int row_groups = (L.rows + kL0Rows - 1) / kL0Rows;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= chunks * row_groups) return;
+    const int rg = idx / chunks, c0 = (idx - rg * chunks) << 4;
+    const int b = blockIdx.y + img0;
+    const uint8_t *src = img + (long long)blockIdx.y * img_bytes;
+    uint4 v[kL0Rows];
+#pragma unroll
+    for (int k = 0; k < kL0Rows; k++) {
+        const int row = min(rg * kL0Rows + k, L.rows - 1);
+        v[k] = level0_chunk(src + (long long)orbx_reflect101(row - kYO, L.h) * img_stride, c0 - kXO, L.w);
+    }
+    uint8_t *dst = plane_ptr(pyr, L, b) + c0;
+#pragma unroll
+    for (int k = 0; k < kL0Rows; k++) {
+        const int row = rg * kL0Rows + k;
+        if (row < L.rows) *reinterpret_cast<uint4 *>(dst + (long long)row * L.pitch) = v[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // K1b  level l>0: resize(level l-1 -> level l, INTER_LINEAR) + copyMakeBorder(REFLECT_101|ISOLATED)
-// (src/ORBextractor.cc:1083-1092).  The border is produced by evaluating the resize at the reflected
-// interior coordinate, so a level is finished by a single pass and only the previous interior is read.
-// Fixed-point arithmetic of OpenCV's 8-bit linear resize, exact.
-// one thread = 4 output pixels (one 32-bit store)
+// (src/ORBextractor.cc:1083-1092).  Fixed-point arithmetic of OpenCV's 8-bit linear resize, exact
+// (SURVEY.md §8a-a2):  r[sy][d] = S[sy][sx]*a0 + S[sy][sx+1]*a1 ;  dst = (((b0*(r[sy]>>4))>>16) + ((b1*(r[sy+1]>>4))>>16) + 2) >> 2.
+// CTA tile = 64 x 32 interior outputs.  The source rows the tile needs (about 1.2 x 32 + 2) are staged in shared
+// memory with 16-byte loads; phase H resizes every staged row horizontally ONCE into a u16 buffer (r >> 4 < 2^15);
+// phase V combines two buffered rows per output, 4 pixels per thread, one 32-bit store.  The 19-px REFLECT_101 frame is
+// written by the CTA that produced the mirrored interior pixel (extra row / byte stores on edge tiles only).
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_resize(uint8_t *__restrict__ pyr, LevelGeom S, LevelGeom D,
-                                                const ResizeTap *__restrict__ taps) {
-    const int chunks = (kXO + D.w + kEdge + 3) >> 2;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= chunks * D.rows) return;
-    const int row = idx / chunks, c0 = (idx - row * chunks) << 2;
-    const int b = blockIdx.y;
-    const uint8_t *src = plane_ptr((const uint8_t *)pyr, S, b) + (long long)kYO * S.pitch + kXO;
-    const int iy = orbx_reflect101(row - kYO, D.h);
-    const ResizeTap ty = taps[D.tap_y + iy];
-    const uint8_t *s0 = src + (long long)ty.s0 * S.pitch;
-    const uint8_t *s1 = src + (long long)ty.s1 * S.pitch;
-    uint32_t out = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        int x = c0 + j - kXO;
-        x = max(-kEdge, min(D.w - 1 + kEdge, x));
-        const ResizeTap tx = taps[D.tap_x + orbx_reflect101(x, D.w)];
-        const int r0 = (int)s0[tx.s0] * tx.a0 + (int)s0[tx.s1] * tx.a1;
-        const int r1 = (int)s1[tx.s0] * tx.a0 + (int)s1[tx.s1] * tx.a1;
-        const int v = (((ty.a0 * (r0 >> 4)) >> 16) + ((ty.a1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        out |= (uint32_t)(v & 0xFF) << (8 * j);
+constexpr int kRszTW = 64, kRszTH = 32;
+constexpr int kRszThreads = 256;
+// dynamic shared memory: staged source [src_rows][src_pitch] u8, horizontal sums [src_rows][kRszTW] u16, y taps [kRszTH];
+// src_rows / src_pitch are the maxima over all tiles of all levels, computed by the host from the tap tables
+__host__ __device__ inline size_t resize_smem_bytes(int src_rows, int src_pitch) {
+    return (size_t)src_rows * src_pitch + (size_t)src_rows * kRszTW * 2 + kRszTH * sizeof(ResizeTap);
+}
+
+__global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ pyr, LevelGeom S, LevelGeom D,
+                                                        const ResizeTap *__restrict__ taps, int src_rows, int src_pitch, int img0) {
+    extern __shared__ __align__(16) uint8_t rsz_smem[];
+    uint8_t *s_src = rsz_smem;
+    unsigned short *s_h = reinterpret_cast<unsigned short *>(rsz_smem + (size_t)src_rows * src_pitch);
+    ResizeTap *s_ty = reinterpret_cast<ResizeTap *>(s_h + (size_t)src_rows * kRszTW);
+    const int tiles_x = (D.w + kRszTW - 1) / kRszTW;
+    const int ty_ = blockIdx.x / tiles_x, tx_ = blockIdx.x - ty_ * tiles_x;
+    const int ox0 = tx_ * kRszTW, oy0 = ty_ * kRszTH;
+    const int ow = min(kRszTW, D.w - ox0), oh = min(kRszTH, D.h - oy0);
+    const int b = blockIdx.y + img0;
+    const int tid = threadIdx.x;
+    const ResizeTap *tapx = taps + D.tap_x + ox0, *tapy = taps + D.tap_y + oy0;
+    if (tid < oh) s_ty[tid] = tapy[tid];
+    const int sy_lo = tapy[0].s0, sy_hi = tapy[oh - 1].s1;
+    const int sx_lo = tapx[0].s0, sx_hi = tapx[ow - 1].s1;
+    const int sx_al = sx_lo & ~15;                              // staged columns start 16-byte aligned
+    const int nrow = sy_hi - sy_lo + 1, nvec = (sx_hi - sx_al + 16) >> 4;
+    {
+        const uint8_t *src = plane_ptr((const uint8_t *)pyr, S, b) + (long long)(kYO + sy_lo) * S.pitch + kXO + sx_al;
+        for (int i = tid; i < nrow * nvec; i += kRszThreads) {
+            const int r = i / nvec, c = i - r * nvec;
+            *reinterpret_cast<uint4 *>(s_src + r * src_pitch + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * S.pitch + 16 * c));
+        }
     }
-    *reinterpret_cast<uint32_t *>(plane_ptr(pyr, D, b) + (long long)row * D.pitch + c0) = out;
+    __syncthreads();
+    {   // phase H: thread = one output column, rows strided by 4
+        const int c = tid & (kRszTW - 1), rg = tid >> 6;
+        if (c < ow) {
+            const ResizeTap t = tapx[c];
+            const int o0 = t.s0 - sx_al, o1 = t.s1 - sx_al;
+            for (int r = rg; r < nrow; r += kRszThreads / kRszTW) {
+                const uint8_t *sr = s_src + r * src_pitch;
+                s_h[r * kRszTW + c] = (unsigned short)(((int)sr[o0] * t.a0 + (int)sr[o1] * t.a1) >> 4);
+            }
+        }
+    }
+    __syncthreads();
+    // phase V: thread = 4 adjacent output columns of one row
+    uint8_t *dplane = plane_ptr(pyr, D, b);
+    const int cg = tid & 15, c4 = 4 * cg;
+    if (c4 >= ow) return;
+    for (int r = tid >> 4; r < oh; r += kRszThreads / 16) {
+        const ResizeTap t = s_ty[r];
+        const uint2 h0 = *reinterpret_cast<const uint2 *>(s_h + (t.s0 - sy_lo) * kRszTW + c4);
+        const uint2 h1 = *reinterpret_cast<const uint2 *>(s_h + (t.s1 - sy_lo) * kRszTW + c4);
+        const int b0 = t.a0, b1 = t.a1;
+        const int p0 = (((b0 * (int)(h0.x & 0xFFFF)) >> 16) + ((b1 * (int)(h1.x & 0xFFFF)) >> 16) + 2) >> 2;
+        const int p1 = (((b0 * (int)(h0.x >> 16)) >> 16) + ((b1 * (int)(h1.x >> 16)) >> 16) + 2) >> 2;
+        const int p2 = (((b0 * (int)(h0.y & 0xFFFF)) >> 16) + ((b1 * (int)(h1.y & 0xFFFF)) >> 16) + 2) >> 2;
+        const int p3 = (((b0 * (int)(h0.y >> 16)) >> 16) + ((b1 * (int)(h1.y >> 16)) >> 16) + 2) >> 2;
+        const uint32_t out = (uint32_t)(p0 & 0xFF) | ((uint32_t)(p1 & 0xFF) << 8) | ((uint32_t)(p2 & 0xFF) << 16) | ((uint32_t)(p3 & 0xFF) << 24);
+        const int y = oy0 + r, x = ox0 + c4;
+        const int nvalid = min(4, D.w - x);
+        // rows that receive this output row: itself and its REFLECT_101 images in the top / bottom frame
+        int rows[3] = {y, (y >= 1 && y <= kEdge) ? -y : INT_MIN, (y <= D.h - 2 && y >= D.h - 1 - kEdge) ? 2 * (D.h - 1) - y : INT_MIN};
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            if (rows[q] == INT_MIN) continue;
+            uint8_t *drow = dplane + (long long)(kYO + rows[q]) * D.pitch + kXO;
+            if (nvalid == 4) *reinterpret_cast<uint32_t *>(drow + x) = out;
+            else for (int k = 0; k < nvalid; k++) drow[x + k] = (uint8_t)(out >> (8 * k));
+            // left / right frame columns mirrored from interior columns 1..19 and w-20..w-2
+            if (x <= kEdge || x + 3 >= D.w - 1 - kEdge) {
+                for (int k = 0; k < nvalid; k++) {
+                    const int xx = x + k;
+                    const uint8_t pv = (uint8_t)(out >> (8 * k));
+                    if (xx >= 1 && xx <= kEdge) drow[-xx] = pv;
+                    if (xx <= D.w - 2 && xx >= D.w - 1 - kEdge) drow[2 * (D.w - 1) - xx] = pv;
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // K5  GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of every level (src/ORBextractor.cc:1035-1036).
 // Q8.8 kernel {18,34,48,56,48,34,18}: horizontal u8->u16, vertical u16->u32, (v + 2^15) >> 16 — exact.
 // The clone's REFLECT_101 edge is already materialised by the plane's 19-px frame, so the tile load needs
-// no index arithmetic.  Tile = 128 x 32 outputs; source tile staged in shared memory with 32-bit loads.
+// no index arithmetic.
+// CTA tile = 128 x 128 outputs staged once in shared memory (16-byte loads); each warp owns a 128 x 32 strip and
+// MARCHES down it: a lane holds 4 adjacent columns, computes the horizontal sums of one source row with
+// 8 IDP.4A on funnel-shifted words and keeps the last 7 rows of sums in registers, so the vertical pass is
+// 3 adds + 4 multiply-adds per pixel with no intermediate buffer.  One 32-bit store per lane and row.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 128, kBlurTH = 32;
-constexpr int kBlurSW = kBlurTW + 8;          // source columns x0-4 .. x0+131
-constexpr int kBlurSH = kBlurTH + 6;
+constexpr int kBlurTW = 128, kBlurTH = 128;
+constexpr int kBlurStrip = 32;                      // rows marched by one warp
+constexpr int kBlurWarps = kBlurTH / kBlurStrip;
+constexpr int kBlurSP = kBlurTW + 32;               // staged columns x0-16 .. x0+144
+constexpr int kBlurSR = kBlurTH + 6;
+constexpr size_t kBlurSmem = (size_t)kBlurSP * kBlurSR;
 
 struct BlurTiles { int base[kMaxLevels + 1]; };
 
-__global__ void __launch_bounds__(256) k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, Geom G,
-                                              BlurTiles T) {
-    __shared__ uint32_t s_src[kBlurSH][kBlurSW / 4];
-    __shared__ uint16_t s_h[kBlurSH][kBlurTW + 8];
+__global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, Geom G,
+                                                          BlurTiles T, int img0) {
+    extern __shared__ __align__(16) uint8_t s_src[];   // [kBlurSR][kBlurSP]
     int lvl = 0;
     while (lvl + 1 < G.nlevels && (int)blockIdx.x >= T.base[lvl + 1]) lvl++;
     const LevelGeom &L = G.lv[lvl];
@@ -114,51 +193,50 @@ __global__ void __launch_bounds__(256) k_blur(const uint8_t *__restrict__ pyr, u
     const int t = blockIdx.x - T.base[lvl];
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + img0;
     const uint8_t *src = plane_ptr(pyr, L, b);
-    // source tile: plane rows (kYO + y0 - 3 ...), plane columns (kXO + x0 - 4 ...), 4-byte aligned
-    for (int i = threadIdx.x; i < kBlurSH * (kBlurSW / 4); i += blockDim.x) {
-        const int r = i / (kBlurSW / 4), c = i - r * (kBlurSW / 4);
-        const int pr = min(kYO + y0 - 3 + r, L.rows - 1);
-        const int pc = kXO + x0 - 4 + 4 * c;
-        uint32_t v = 0;
-        if (pc + 4 <= L.pitch) v = __ldg(reinterpret_cast<const uint32_t *>(src + (long long)pr * L.pitch + pc));
-        s_src[r][c] = v;
+    // stage plane rows kYO + y0 - 3 .., plane columns kXO + x0 - 16 .. (16-byte aligned)
+    const int rows_needed = min(kBlurSR, L.h + 3 - (y0 - 3));
+    for (int i = threadIdx.x; i < rows_needed * (kBlurSP / 16); i += kBlurWarps * 32) {
+        const int r = i / (kBlurSP / 16), c = i - r * (kBlurSP / 16);
+        const int pc = kXO + x0 - 16 + 16 * c;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (pc + 16 <= L.pitch) v = __ldg(reinterpret_cast<const uint4 *>(src + (long long)(kYO + y0 - 3 + r) * L.pitch + pc));
+        *reinterpret_cast<uint4 *>(s_src + r * kBlurSP + 16 * c) = v;
     }
     __syncthreads();
-    // horizontal: 4 adjacent outputs per item from 3 words (bytes x-4..x+7, taps x-3..x+6)
-    for (int i = threadIdx.x; i < kBlurSH * (kBlurTW / 4); i += blockDim.x) {
-        const int r = i / (kBlurTW / 4), c = i - r * (kBlurTW / 4);
-        const uint32_t w0 = s_src[r][c], w1 = s_src[r][c + 1], w2 = s_src[r][c + 2];
-        int p[12];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ys = y0 + wid * kBlurStrip;              // first output row of this warp's strip
+    const int xb = x0 + 4 * lane;
+    if (ys >= L.h || xb >= L.w) return;
+    const uint8_t *sp = s_src + (wid * kBlurStrip) * kBlurSP + 12 + 4 * lane;
+    uint8_t *dst = plane_ptr(blur, L, b) + (long long)(kYO + ys) * L.pitch + kXO + xb;
+    const int nrows = min(kBlurStrip, L.h - ys);       // output rows of the strip
+    uint32_t hw[7][4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { p[k] = (w0 >> (8 * k)) & 0xFF; p[4 + k] = (w1 >> (8 * k)) & 0xFF; p[8 + k] = (w2 >> (8 * k)) & 0xFF; }
+    for (int r = 0; r < kBlurStrip + 6; r++) {
+        if (r < nrows + 6) {
+            const uint32_t wl = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP);
+            const uint32_t wc = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 4);
+            const uint32_t wr = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 8);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int acc = 18 * (p[k + 1] + p[k + 7]) + 34 * (p[k + 2] + p[k + 6]) + 48 * (p[k + 3] + p[k + 5]) + 56 * p[k + 4];
-            s_h[r][4 * c + k] = (uint16_t)acc;
+            for (int j = 0; j < 6; j++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) hw[j][k] = hw[j + 1][k];
+            // pixel k needs bytes k+1 .. k+7 of the 12-byte window (wl, wc, wr)
+            hw[6][0] = __dp4a(__funnelshift_r(wl, wc, 8), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 8), 0x00122230u, 0u));
+            hw[6][1] = __dp4a(__funnelshift_r(wl, wc, 16), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 16), 0x00122230u, 0u));
+            hw[6][2] = __dp4a(__funnelshift_r(wl, wc, 24), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 24), 0x00122230u, 0u));
+            hw[6][3] = __dp4a(wc, 0x38302212u, __dp4a(wr, 0x00122230u, 0u));
+            if (r >= 6) {
+                uint32_t v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    v[k] = 18u * (hw[0][k] + hw[6][k]) + 34u * (hw[1][k] + hw[5][k]) + 48u * (hw[2][k] + hw[4][k]) + 56u * hw[3][k] + 32768u;
+                const uint32_t lo = __byte_perm(v[0], v[1], 0x0062), hi = __byte_perm(v[2], v[3], 0x0062);
+                *reinterpret_cast<uint32_t *>(dst + (long long)(r - 6) * L.pitch) = __byte_perm(lo, hi, 0x5410);
+            }
         }
-    }
-    __syncthreads();
-    uint8_t *dst = plane_ptr(blur, L, b);
-    for (int i = threadIdx.x; i < kBlurTH * (kBlurTW / 4); i += blockDim.x) {
-        const int r = i / (kBlurTW / 4), c = i - r * (kBlurTW / 4);
-        const int y = y0 + r, x = x0 + 4 * c;
-        if (y >= L.h || x >= L.w) continue;
-        uint32_t acc[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 7; k++) {
-            const int kw = (k == 0 || k == 6) ? 18 : (k == 1 || k == 5) ? 34 : (k == 2 || k == 4) ? 48 : 56;
-            const uint2 hv = *reinterpret_cast<const uint2 *>(&s_h[r + k][4 * c]);
-            acc[0] += kw * (hv.x & 0xFFFF); acc[1] += kw * (hv.x >> 16);
-            acc[2] += kw * (hv.y & 0xFFFF); acc[3] += kw * (hv.y >> 16);
-        }
-        uint32_t out = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) out |= ((acc[k] + 32768u) >> 16) << (8 * k);
-        uint8_t *d = dst + (long long)(kYO + y) * L.pitch + kXO + x;
-        if (x + 4 <= L.w) *reinterpret_cast<uint32_t *>(d) = out;
-        else for (int k = 0; k < L.w - x; k++) d[k] = (uint8_t)(out >> (8 * k));
     }
 }
 
@@ -189,15 +267,17 @@ constexpr int kFastThreads = 256;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastQueue = 192;               // per-warp survivor queue (u16 entries): < 64 left + up to 128 new
 constexpr int kFastMaxG = 8;
+constexpr int kFastCorners = 3072;            // dense corner list of a tile; a tile with more corners falls back to a sweep
+constexpr int kFastColBits = 9;               // queue / list entry = (img row << 9) | img column  (ip <= 512, rows < 128)
 
 // shared memory of one CTA:
 //   img [(ymax + 6)][ip]  level pixels, row 0 = tile row -3, column 0 = plane column pc0 (16-byte aligned)
 //   sc  [(ymax + 2)][ip]  scores, same column indexing, rows 0 and Y+1 stay zero
 //   bm  [ymax][ip / 32]   keep bitmap (rounded up to 16 bytes)
-//   q   [kFastWarps][kFastQueue] u16, has [kFastMaxG] int
+//   q   [kFastWarps][kFastQueue] u16, cl [kFastCorners] u16, has [kFastMaxG] int, ncl int
 __host__ __device__ inline size_t fast_zero_bytes(int ip, int ymax) { return ((size_t)(ymax + 2) * ip + (size_t)ymax * (ip >> 5) * 4 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t fast_smem_bytes(int ip, int ymax) {
-    return (size_t)(ymax + 6) * ip + fast_zero_bytes(ip, ymax) + (size_t)kFastWarps * kFastQueue * 2 + kFastMaxG * sizeof(int);
+    return (size_t)(ymax + 6) * ip + fast_zero_bytes(ip, ymax) + (size_t)(kFastWarps * kFastQueue + kFastCorners) * 2 + (kFastMaxG + 4) * sizeof(int);
 }
 
 __device__ __forceinline__ uint32_t bytes_gt(uint32_t ad, uint32_t t1x4) {
@@ -205,9 +285,16 @@ __device__ __forceinline__ uint32_t bytes_gt(uint32_t ad, uint32_t t1x4) {
     return (ad | ((ad | 0x80808080u) - t1x4)) & 0x80808080u;
 }
 
-// scores entries e0 / e1 (byte offsets of two centre pixels inside img) with packed u16x2 arithmetic
-__device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *sc, int ip, int e0, int e1, int t) {
-    const uint8_t *p0 = img + e0, *p1 = img + e1;
+// exact x / d for 0 <= x < 4096, 8 <= d: (x + 0.5) / d is at least 0.5 / d away from an integer, far above fp32 error
+__device__ __forceinline__ int small_div(int x, float inv_d) { return (int)(((float)x + 0.5f) * inv_d); }
+
+// Scores the centre pixels e0 / e1 (queue entries) with packed u16x2 arithmetic, stores S where S >= t and appends those
+// pixels to the tile's corner list.
+__device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *sc1, int ip, int e0, int e1, bool ok0, bool ok1, int t,
+                                                unsigned short *cl, int *ncl, int lane) {
+    const int a0 = (e0 >> kFastColBits) * ip + (e0 & ((1 << kFastColBits) - 1));
+    const int a1 = (e1 >> kFastColBits) * ip + (e1 & ((1 << kFastColBits) - 1));
+    const uint8_t *p0 = img + a0, *p1 = img + a1;
     const int o[16] = {3 * ip, 3 * ip + 1, 2 * ip + 2, ip + 3, 3, -ip + 3, -2 * ip + 2, -3 * ip + 1,
                        -3 * ip, -3 * ip - 1, -2 * ip - 2, -ip - 3, -3, ip - 3, 2 * ip - 2, 3 * ip - 1};
     uint32_t r[16];
@@ -222,18 +309,47 @@ __device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *sc,
     uint32_t A = 0xFFFFFFFFu, B = 0u;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        const uint32_t a0 = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
-        const uint32_t a1 = __vimax3_u16x2(mx3[k + 1], mx3[(k + 4) & 15], mx3[(k + 7) & 15]);
-        A = __vimin3_u16x2(A, a0, a1);
-        const uint32_t b0 = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
-        const uint32_t b1 = __vimin3_u16x2(mn3[k + 1], mn3[(k + 4) & 15], mn3[(k + 7) & 15]);
-        B = __vimax3_u16x2(B, b0, b1);
+        const uint32_t x0 = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+        const uint32_t x1 = __vimax3_u16x2(mx3[k + 1], mx3[(k + 4) & 15], mx3[(k + 7) & 15]);
+        A = __vimin3_u16x2(A, x0, x1);
+        const uint32_t y0 = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+        const uint32_t y1 = __vimin3_u16x2(mn3[k + 1], mn3[(k + 4) & 15], mn3[(k + 7) & 15]);
+        B = __vimax3_u16x2(B, y0, y1);
     }
     const int v0 = p0[0], v1 = p1[0];
     const int s0 = max(v0 - (int)(A & 0xFFFFu), (int)(B & 0xFFFFu) - v0) - 1;
     const int s1 = max(v1 - (int)(A >> 16), (int)(B >> 16) - v1) - 1;
-    if (s0 >= t) sc[e0] = (uint8_t)s0;      // score map shares the column indexing of img; row offset applied by the caller
-    if (s1 >= t) sc[e1] = (uint8_t)s1;
+    const bool c0 = ok0 && s0 >= t, c1 = ok1 && s1 >= t;
+    // score map: same column indexing as img, tile row = img row - 3
+    if (c0) sc1[a0 - 3 * ip] = (uint8_t)s0;
+    if (c1) sc1[a1 - 3 * ip] = (uint8_t)s1;
+    const unsigned b0 = __ballot_sync(0xFFFFFFFFu, c0), b1 = __ballot_sync(0xFFFFFFFFu, c1);
+    const int n0 = __popc(b0), n = n0 + __popc(b1);
+    if (n) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ncl, n);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        const unsigned lm = (1u << lane) - 1;
+        if (c0) { const int p = base + __popc(b0 & lm); if (p < kFastCorners) cl[p] = (unsigned short)e0; }
+        if (c1) { const int p = base + n0 + __popc(b1 & lm); if (p < kFastCorners) cl[p] = (unsigned short)e1; }
+    }
+}
+
+// strict 3x3 maximum of the score at (tile row, img column) inside its cell -> keep bitmap
+__device__ __forceinline__ void fast_nms_one(const uint8_t *sc1, uint32_t *bm, int *has, int ip, int bw, int row, int col, int c0,
+                                             int wc, float inv_wc, unsigned retry) {
+    const uint8_t *n = sc1 + row * ip + col;
+    const int s = n[0];
+    const int xt = col - c0;
+    const int cj = small_div(xt, inv_wc), xl = xt - cj * wc;
+    if (retry && !((retry >> cj) & 1u)) return;
+    bool keep = s > n[-ip] && s > n[ip];
+    if (xl > 0) keep = keep && s > n[-1] && s > n[-ip - 1] && s > n[ip - 1];
+    if (xl < wc - 1) keep = keep && s > n[1] && s > n[-ip + 1] && s > n[ip + 1];
+    if (keep) {
+        atomicOr(&bm[row * bw + (col >> 5)], 1u << (col & 31));
+        has[cj] = 1;
+    }
 }
 
 __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict__ pyr, Geom G,
@@ -249,6 +365,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict
     const int j0 = jt * G.fast_g, j1 = min(j0 + G.fast_g, L.n_cols);
     const int ncell = j1 - j0;
     const int wc = L.w_cell;
+    const float inv_wc = 1.0f / (float)wc;
     // tested area of the tile in level coordinates (see the header comment of this kernel)
     const int tx0 = kEdge + j0 * wc, tx1 = min(kEdge + j1 * wc, L.w - kEdge);
     const int ty0 = kEdge + ci * L.h_cell, ty1 = min(ty0 + L.h_cell, L.h - kEdge);
@@ -265,42 +382,45 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict
     uint32_t *bm = reinterpret_cast<uint32_t *>(sc + (size_t)ip * (G.fast_ymax + 2));
     unsigned short *q0 = reinterpret_cast<unsigned short *>(sc + fast_zero_bytes(ip, G.fast_ymax));
     unsigned short *q = q0 + wid * kFastQueue;
-    int *has = reinterpret_cast<int *>(q0 + kFastWarps * kFastQueue);
+    unsigned short *cl = q0 + kFastWarps * kFastQueue;
+    int *has = reinterpret_cast<int *>(cl + kFastCorners);
+    int *ncl = has + kFastMaxG;
     // ---- stage the tile: plane rows kYO + ty0 - 3 .. kYO + ty1 + 3, 16-byte columns from pc0
     const int pc0 = (kXO + tx0 - 3) & ~15;
     const int c0 = kXO + tx0 - pc0;                 // smem column of level column tx0 (>= 3)
     const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
     {
         const uint8_t *src = plane_ptr(pyr, L, b) + (long long)(kYO + ty0 - 3) * L.pitch + pc0;
-        const int total = (Y + 6) * nvec;
-        for (int i = tid; i < total; i += kFastThreads) {
-            const int r = i / nvec, c = i - r * nvec;
-            *reinterpret_cast<uint4 *>(img + r * ip + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * L.pitch + 16 * c));
-        }
+        for (int r = wid; r < Y + 6; r += kFastWarps)
+            for (int c = lane; c < nvec; c += 32)
+                *reinterpret_cast<uint4 *>(img + r * ip + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * L.pitch + 16 * c));
         uint4 *z = reinterpret_cast<uint4 *>(sc);             // score map and bitmap are contiguous
         const int nz = (int)(fast_zero_bytes(ip, G.fast_ymax) >> 4);
         for (int i = tid; i < nz; i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
         if (tid < kFastMaxG) has[tid] = 0;
+        if (tid == 0) *ncl = 0;
     }
     __syncthreads();
     const orbx_image_params prm = params[b];
     const int t_ini = min(max(prm.ini_th_fast, 0), 255), t_min = min(max(prm.min_th_fast, 0), 255);
     const int w0 = c0 >> 2, w1 = (c0 + X - 1) >> 2;    // words of a row that hold tested pixels
     const int nw = w1 - w0 + 1;
+    const float inv_nw = 1.0f / (float)nw;
+    const uint32_t m_first = 0x80808080u << (8 * (c0 & 3)), m_last = 0x80808080u >> (8 * (3 - ((c0 + X - 1) & 3)));
     unsigned retry = 0;                                 // cells (bit k = cell j0 + k) processed in this pass; 0 = all
     uint8_t *sc1 = sc + ip;                             // score row of tile row 0
+    const int items = Y * nw;
     for (int pass = 0; pass < 2; pass++) {
         const int t = pass == 0 ? t_ini : t_min;
         const uint32_t t1x4 = (uint32_t)(min(t, 126) + 1) * 0x01010101u;
         // ---- 1 + 2: quick reject and pair scoring, warp-local
         int qn = 0;
-        const int items = Y * nw;
         for (int it0 = wid * 32; it0 < items; it0 += kFastWarps * 32) {
             const int it = it0 + lane;
             uint32_t m = 0;
             int row = 0, wi = 0;
             if (it < items) {
-                row = it / nw; wi = w0 + (it - row * nw);
+                row = small_div(it, inv_nw); wi = w0 + (it - row * nw);
                 const uint32_t *c = reinterpret_cast<const uint32_t *>(img + (row + 3) * ip) + wi;
                 const uint32_t v = c[0], pv = c[-1], nx = c[1];
                 const uint32_t up = *(reinterpret_cast<const uint32_t *>(img + row * ip) + wi);
@@ -309,58 +429,53 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict
                 const uint32_t gv = bytes_gt(__vabsdiffu4(v, up), t1x4) | bytes_gt(__vabsdiffu4(v, dn), t1x4);
                 const uint32_t gh = bytes_gt(__vabsdiffu4(v, lf), t1x4) | bytes_gt(__vabsdiffu4(v, rt), t1x4);
                 m = gv & gh;
-                // bytes outside the tested columns, or (second pass) outside the cells that are retried
-                const int x_first = 4 * wi - c0;           // level column - tx0 of byte 0
+                if (wi == w0) m &= m_first;                // bytes left / right of the tested columns
+                if (wi == w1) m &= m_last;
+                if (retry) {                               // second pass: only the cells that are retried
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int xt = x_first + k;
-                    bool ok = xt >= 0 && xt < X;
-                    if (ok && retry) ok = (retry >> (xt / wc)) & 1u;
-                    if (!ok) m &= ~(0x80u << (8 * k));
+                    for (int k = 0; k < 4; k++) {
+                        const int xt = min(max(4 * wi + k - c0, 0), X - 1);
+                        if (!((retry >> small_div(xt, inv_wc)) & 1u)) m &= ~(0x80u << (8 * k));
+                    }
                 }
             }
             // append the survivors of this warp iteration to the queue (order inside the queue is irrelevant)
-            int base = qn;
+            const int ebase = ((row + 3) << kFastColBits) | (4 * wi);
+            const unsigned lm = (1u << lane) - 1;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const bool s = (m >> (8 * k + 7)) & 1u;
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, s);
-                if (s) q[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((row + 3) * ip + 4 * wi + k);
-                base += __popc(bal);
+                if (s) q[qn + __popc(bal & lm)] = (unsigned short)(ebase + k);
+                qn += __popc(bal);
             }
-            qn = base;
             __syncwarp();
             while (qn >= 64) {
                 qn -= 64;
-                fast_score_pair(img, sc1 - 3 * ip, ip, q[qn + lane], q[qn + 32 + lane], t);
+                fast_score_pair(img, sc1, ip, q[qn + lane], q[qn + 32 + lane], true, true, t, cl, ncl, lane);
                 __syncwarp();
             }
         }
         if (qn > 0) {
-            const int e0 = q[lane < qn ? lane : 0], e1 = q[lane + 32 < qn ? lane + 32 : 0];
-            fast_score_pair(img, sc1 - 3 * ip, ip, e0, e1, t);
+            const bool ok0 = lane < qn, ok1 = lane + 32 < qn;
+            fast_score_pair(img, sc1, ip, q[ok0 ? lane : 0], q[ok1 ? lane + 32 : 0], ok0, ok1, t, cl, ncl, lane);
         }
         __syncthreads();
-        // ---- 3: strict 3x3 maximum inside the cell (sparse sweep over the score words)
-        for (int it = tid; it < items; it += kFastThreads) {
-            const int row = it / nw, wi = w0 + (it - row * nw);
-            const uint32_t wv = *(reinterpret_cast<const uint32_t *>(sc1 + row * ip) + wi);
-            if (wv == 0) continue;
+        // ---- 3: strict 3x3 maximum inside the cell, over the dense corner list (or a sweep of the score map if it overflowed)
+        const int nc = *ncl;
+        if (nc <= kFastCorners) {
+            for (int i = tid; i < nc; i += kFastThreads) {
+                const int e = cl[i];
+                fast_nms_one(sc1, bm, has, ip, bw, (e >> kFastColBits) - 3, e & ((1 << kFastColBits) - 1), c0, wc, inv_wc, retry);
+            }
+        } else {
+            for (int it = tid; it < items; it += kFastThreads) {
+                const int row = small_div(it, inv_nw), wi = w0 + (it - row * nw);
+                const uint32_t wv = *(reinterpret_cast<const uint32_t *>(sc1 + row * ip) + wi);
+                if (wv == 0) continue;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int s = (wv >> (8 * k)) & 0xFF;
-                if (s == 0) continue;
-                const int col = 4 * wi + k, xt = col - c0;
-                const int cj = xt / wc, xl = xt - cj * wc;
-                if (retry && !((retry >> cj) & 1u)) continue;
-                const uint8_t *n = sc1 + row * ip + col;
-                bool keep = s > n[-ip] && s > n[ip];
-                if (xl > 0) keep = keep && s > n[-1] && s > n[-ip - 1] && s > n[ip - 1];
-                if (xl < wc - 1) keep = keep && s > n[1] && s > n[-ip + 1] && s > n[ip + 1];
-                if (keep) {
-                    atomicOr(&bm[row * bw + (col >> 5)], 1u << (col & 31));
-                    has[cj] = 1;
-                }
+                for (int k = 0; k < 4; k++)
+                    if ((wv >> (8 * k)) & 0xFF) fast_nms_one(sc1, bm, has, ip, bw, row, 4 * wi + k, c0, wc, inv_wc, retry);
             }
         }
         __syncthreads();
@@ -369,6 +484,9 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict
             retry = 0;
             for (int k = 0; k < ncell; k++) if (!has[k]) retry |= 1u << k;
             if (retry == 0 || t_min >= t_ini) break;
+            __syncthreads();
+            if (tid == 0) *ncl = 0;
+            __syncthreads();
         }
     }
     // ---- 5: one warp per cell, rows in parallel, row-major emission from the bitmap
@@ -376,7 +494,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict
         const int cx0 = c0 + k * wc, cx1 = min(cx0 + wc, c0 + X);    // smem columns of the cell
         uint32_t *out = cells + (long long)b * G.cand_per_image + L.cand_off + (long long)(ci * L.n_cols + j0 + k) * L.cell_cap;
         int total = 0;
-        if (cx1 > cx0) {
+        if (cx1 > cx0 && has[k]) {
             const int wa = cx0 >> 5, wb = (cx1 - 1) >> 5;
             for (int r0 = 0; r0 < Y; r0 += 32) {
                 const int row = r0 + lane;
@@ -561,9 +679,10 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int au = u < 0 ? -u : u;
-#pragma unroll 1
-        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-            if (au <= c_umax[v < 0 ? -v : v]) {
+        constexpr int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // src/ORBextractor.cc:399-413
+#pragma unroll
+        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {   // fully unrolled: 31 independent loads in flight
+            if (au <= umax[v < 0 ? -v : v]) {
                 const int val = __ldg(c + (long long)v * L.pitch + u);
                 m10 += u * val; m01 += v * val;
             }
