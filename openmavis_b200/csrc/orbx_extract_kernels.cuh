@@ -214,28 +214,32 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
     const int nrows = min(kBlurStrip, L.h - ys);       // output rows of the strip
     uint32_t hw[7][4];
 #pragma unroll
+    for (int j = 0; j < 7; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) hw[j][k] = 0;
+    // Fully unrolled with no control flow around the register window (rows below the strip compute on stale shared memory
+    // and are simply not stored), so the 7-row window is pure register renaming.
+#pragma unroll
     for (int r = 0; r < kBlurStrip + 6; r++) {
-        if (r < nrows + 6) {
-            const uint32_t wl = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP);
-            const uint32_t wc = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 4);
-            const uint32_t wr = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 8);
+        const uint32_t wl = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP);
+        const uint32_t wc = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 4);
+        const uint32_t wr = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 8);
 #pragma unroll
-            for (int j = 0; j < 6; j++)
+        for (int j = 0; j < 6; j++)
 #pragma unroll
-                for (int k = 0; k < 4; k++) hw[j][k] = hw[j + 1][k];
-            // pixel k needs bytes k+1 .. k+7 of the 12-byte window (wl, wc, wr)
-            hw[6][0] = __dp4a(__funnelshift_r(wl, wc, 8), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 8), 0x00122230u, 0u));
-            hw[6][1] = __dp4a(__funnelshift_r(wl, wc, 16), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 16), 0x00122230u, 0u));
-            hw[6][2] = __dp4a(__funnelshift_r(wl, wc, 24), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 24), 0x00122230u, 0u));
-            hw[6][3] = __dp4a(wc, 0x38302212u, __dp4a(wr, 0x00122230u, 0u));
-            if (r >= 6) {
-                uint32_t v[4];
+            for (int k = 0; k < 4; k++) hw[j][k] = hw[j + 1][k];
+        // pixel k needs bytes k+1 .. k+7 of the 12-byte window (wl, wc, wr)
+        hw[6][0] = __dp4a(__funnelshift_r(wl, wc, 8), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 8), 0x00122230u, 0u));
+        hw[6][1] = __dp4a(__funnelshift_r(wl, wc, 16), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 16), 0x00122230u, 0u));
+        hw[6][2] = __dp4a(__funnelshift_r(wl, wc, 24), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 24), 0x00122230u, 0u));
+        hw[6][3] = __dp4a(wc, 0x38302212u, __dp4a(wr, 0x00122230u, 0u));
+        if (r >= 6) {
+            uint32_t v[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    v[k] = 18u * (hw[0][k] + hw[6][k]) + 34u * (hw[1][k] + hw[5][k]) + 48u * (hw[2][k] + hw[4][k]) + 56u * hw[3][k] + 32768u;
-                const uint32_t lo = __byte_perm(v[0], v[1], 0x0062), hi = __byte_perm(v[2], v[3], 0x0062);
-                *reinterpret_cast<uint32_t *>(dst + (long long)(r - 6) * L.pitch) = __byte_perm(lo, hi, 0x5410);
-            }
+            for (int k = 0; k < 4; k++)
+                v[k] = 18u * (hw[0][k] + hw[6][k]) + 34u * (hw[1][k] + hw[5][k]) + 48u * (hw[2][k] + hw[4][k]) + 56u * hw[3][k] + 32768u;
+            const uint32_t lo = __byte_perm(v[0], v[1], 0x0062), hi = __byte_perm(v[2], v[3], 0x0062);
+            if (r - 6 < nrows) *reinterpret_cast<uint32_t *>(dst + (long long)(r - 6) * L.pitch) = __byte_perm(lo, hi, 0x5410);
         }
     }
 }
