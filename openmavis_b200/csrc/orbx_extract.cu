@@ -362,7 +362,7 @@ static int enqueue(orbx_extractor *ex, int n, const uint8_t *d_images, const orb
         launches++;
         for (int l = 1; l < nl; l++) {
             const LevelGeom &D = G.lv[l];
-            dim3 g(((D.w + kRszTW - 1) / kRszTW) * ((D.h + kRszTH - 1) / kRszTH), n);
+            dim3 g((D.w + kRszTW - 1) / kRszTW, (D.h + kRszTH - 1) / kRszTH, n);
             k_resize<<<g, kRszThreads, ex->rsz_smem, s>>>(ex->d_pyr, G.lv[l - 1], D, ex->d_taps, ex->rsz_rows, ex->rsz_pitch, 0);
             launches++;
         }

@@ -41,8 +41,9 @@ __device__ __forceinline__ uint4 level0_chunk(const uint8_t *__restrict__ srow, 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int x = x0 + 4 * k + j;
-            x = max(-kEdge, min(w - 1 + kEdge, x));
-            wv |= (uint32_t)__ldg(srow + orbx_reflect101(x, w)) << (8 * j);
+            x = max(-kEdge, min(w - 1 + kEdge, x));           // plane padding outside the frame repeats the frame's edge
+            x = x < 0 ? -x : (x >= w ? 2 * (w - 1) - x : x);   // BORDER_REFLECT_101, one reflection (w > 19)
+            wv |= (uint32_t)__ldg(srow + x) << (8 * j);
         }
         wds[k] = wv;
     }
@@ -62,7 +63,9 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ img,
 #pragma unroll
     for (int k = 0; k < kL0Rows; k++) {
         const int row = min(rg * kL0Rows + k, L.rows - 1);
-        v[k] = level0_chunk(src + (long long)orbx_reflect101(row - kYO, L.h) * img_stride, c0 - kXO, L.w);
+        int y = row - kYO;
+        y = y < 0 ? -y : (y >= L.h ? 2 * (L.h - 1) - y : y);
+        v[k] = level0_chunk(src + (long long)y * img_stride, c0 - kXO, L.w);
     }
     uint8_t *dst = plane_ptr(pyr, L, b) + c0;
 #pragma unroll
@@ -81,86 +84,94 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ img,
 // phase V combines two buffered rows per output, 4 pixels per thread, one 32-bit store.  The 19-px REFLECT_101 frame is
 // written by the CTA that produced the mirrored interior pixel (extra row / byte stores on edge tiles only).
 // ------------------------------------------------------------------------------------------------------
-constexpr int kRszTW = 64, kRszTH = 32;
+constexpr int kRszTW = 64, kRszTH = 64;
 constexpr int kRszThreads = 256;
-// dynamic shared memory: staged source [src_rows][src_pitch] u8, horizontal sums [src_rows][kRszTW] u16, y taps [kRszTH];
+// dynamic shared memory: staged source [src_rows][src_pitch] u8, horizontal sums [src_rows][kRszTW] u32, y taps [kRszTH];
 // src_rows / src_pitch are the maxima over all tiles of all levels, computed by the host from the tap tables
 __host__ __device__ inline size_t resize_smem_bytes(int src_rows, int src_pitch) {
-    return (size_t)src_rows * src_pitch + (size_t)src_rows * kRszTW * 2 + kRszTH * sizeof(ResizeTap);
+    return (size_t)src_rows * src_pitch + (size_t)src_rows * kRszTW * 4 + kRszTH * sizeof(int4);
 }
 
+__device__ __forceinline__ void resize_store4(uint8_t *drow, int x, uint32_t out, int nvalid, bool x_edge, int w) {
+    if (nvalid == 4) *reinterpret_cast<uint32_t *>(drow + x) = out;
+    else for (int k = 0; k < nvalid; k++) drow[x + k] = (uint8_t)(out >> (8 * k));
+    if (x_edge) {   // left / right frame columns mirrored from interior columns 1..19 and w-20..w-2
+        for (int k = 0; k < nvalid; k++) {
+            const int xx = x + k;
+            const uint8_t pv = (uint8_t)(out >> (8 * k));
+            if (xx >= 1 && xx <= kEdge) drow[-xx] = pv;
+            if (xx <= w - 2 && xx >= w - 1 - kEdge) drow[2 * (w - 1) - xx] = pv;
+        }
+    }
+}
+
+// grid = (tiles_x, tiles_y, images)
 __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ pyr, LevelGeom S, LevelGeom D,
                                                         const ResizeTap *__restrict__ taps, int src_rows, int src_pitch, int img0) {
     extern __shared__ __align__(16) uint8_t rsz_smem[];
     uint8_t *s_src = rsz_smem;
-    unsigned short *s_h = reinterpret_cast<unsigned short *>(rsz_smem + (size_t)src_rows * src_pitch);
-    ResizeTap *s_ty = reinterpret_cast<ResizeTap *>(s_h + (size_t)src_rows * kRszTW);
-    const int tiles_x = (D.w + kRszTW - 1) / kRszTW;
-    const int ty_ = blockIdx.x / tiles_x, tx_ = blockIdx.x - ty_ * tiles_x;
-    const int ox0 = tx_ * kRszTW, oy0 = ty_ * kRszTH;
+    uint32_t *s_h = reinterpret_cast<uint32_t *>(rsz_smem + (size_t)src_rows * src_pitch);
+    int4 *s_ty = reinterpret_cast<int4 *>(s_h + (size_t)src_rows * kRszTW);   // {row0 offset, row1 offset, b0 << 16, b1 << 16}
+    const int ox0 = blockIdx.x * kRszTW, oy0 = blockIdx.y * kRszTH;
     const int ow = min(kRszTW, D.w - ox0), oh = min(kRszTH, D.h - oy0);
-    const int b = blockIdx.y + img0;
+    const int b = blockIdx.z + img0;
     const int tid = threadIdx.x;
     const ResizeTap *tapx = taps + D.tap_x + ox0, *tapy = taps + D.tap_y + oy0;
-    if (tid < oh) s_ty[tid] = tapy[tid];
     const int sy_lo = tapy[0].s0, sy_hi = tapy[oh - 1].s1;
     const int sx_lo = tapx[0].s0, sx_hi = tapx[ow - 1].s1;
     const int sx_al = sx_lo & ~15;                              // staged columns start 16-byte aligned
     const int nrow = sy_hi - sy_lo + 1, nvec = (sx_hi - sx_al + 16) >> 4;
+    if (tid < oh) {
+        const ResizeTap t = tapy[tid];
+        s_ty[tid] = make_int4((t.s0 - sy_lo) * kRszTW, (t.s1 - sy_lo) * kRszTW, (int)t.a0 << 16, (int)t.a1 << 16);
+    }
     {
         const uint8_t *src = plane_ptr((const uint8_t *)pyr, S, b) + (long long)(kYO + sy_lo) * S.pitch + kXO + sx_al;
-        for (int i = tid; i < nrow * nvec; i += kRszThreads) {
-            const int r = i / nvec, c = i - r * nvec;
-            *reinterpret_cast<uint4 *>(s_src + r * src_pitch + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * S.pitch + 16 * c));
-        }
+        for (int c = tid & 7; c < nvec; c += 8)                 // 8 vectors (128 B) per row pass
+            for (int r = tid >> 3; r < nrow; r += kRszThreads / 8)
+                *reinterpret_cast<uint4 *>(s_src + r * src_pitch + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * S.pitch + 16 * c));
     }
     __syncthreads();
-    {   // phase H: thread = one output column, rows strided by 4
+    {   // phase H: thread = one output column, rows strided by 4:  r[sy][d] >> 4
         const int c = tid & (kRszTW - 1), rg = tid >> 6;
         if (c < ow) {
             const ResizeTap t = tapx[c];
-            const int o0 = t.s0 - sx_al, o1 = t.s1 - sx_al;
+            const uint8_t *sr = s_src + rg * src_pitch + (t.s0 - sx_al);
+            const int d1 = t.s1 - t.s0, a0 = t.a0, a1 = t.a1;
+            uint32_t *hp = s_h + rg * kRszTW + c;
+            const int step = (kRszThreads / kRszTW) * src_pitch;
+#pragma unroll 4
             for (int r = rg; r < nrow; r += kRszThreads / kRszTW) {
-                const uint8_t *sr = s_src + r * src_pitch;
-                s_h[r * kRszTW + c] = (unsigned short)(((int)sr[o0] * t.a0 + (int)sr[o1] * t.a1) >> 4);
+                *hp = (uint32_t)(((int)sr[0] * a0 + (int)sr[d1] * a1) >> 4);
+                sr += step; hp += (kRszThreads / kRszTW) * kRszTW;
             }
         }
     }
     __syncthreads();
-    // phase V: thread = 4 adjacent output columns of one row
-    uint8_t *dplane = plane_ptr(pyr, D, b);
-    const int cg = tid & 15, c4 = 4 * cg;
+    // phase V: thread = 4 adjacent output columns, rows strided by 16:
+    //   dst = (((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2, with (b * h) >> 16 == umulhi(b << 16, h)
+    const int c4 = 4 * (tid & 15);
     if (c4 >= ow) return;
+    const int x = ox0 + c4;
+    const int nvalid = min(4, D.w - x);
+    const bool x_edge = (x <= kEdge) || (x + 3 >= D.w - 1 - kEdge);
+    uint8_t *dplane = plane_ptr(pyr, D, b) + kXO;
     for (int r = tid >> 4; r < oh; r += kRszThreads / 16) {
-        const ResizeTap t = s_ty[r];
-        const uint2 h0 = *reinterpret_cast<const uint2 *>(s_h + (t.s0 - sy_lo) * kRszTW + c4);
-        const uint2 h1 = *reinterpret_cast<const uint2 *>(s_h + (t.s1 - sy_lo) * kRszTW + c4);
-        const int b0 = t.a0, b1 = t.a1;
-        const int p0 = (((b0 * (int)(h0.x & 0xFFFF)) >> 16) + ((b1 * (int)(h1.x & 0xFFFF)) >> 16) + 2) >> 2;
-        const int p1 = (((b0 * (int)(h0.x >> 16)) >> 16) + ((b1 * (int)(h1.x >> 16)) >> 16) + 2) >> 2;
-        const int p2 = (((b0 * (int)(h0.y & 0xFFFF)) >> 16) + ((b1 * (int)(h1.y & 0xFFFF)) >> 16) + 2) >> 2;
-        const int p3 = (((b0 * (int)(h0.y >> 16)) >> 16) + ((b1 * (int)(h1.y >> 16)) >> 16) + 2) >> 2;
-        const uint32_t out = (uint32_t)(p0 & 0xFF) | ((uint32_t)(p1 & 0xFF) << 8) | ((uint32_t)(p2 & 0xFF) << 16) | ((uint32_t)(p3 & 0xFF) << 24);
-        const int y = oy0 + r, x = ox0 + c4;
-        const int nvalid = min(4, D.w - x);
-        // rows that receive this output row: itself and its REFLECT_101 images in the top / bottom frame
-        int rows[3] = {y, (y >= 1 && y <= kEdge) ? -y : INT_MIN, (y <= D.h - 2 && y >= D.h - 1 - kEdge) ? 2 * (D.h - 1) - y : INT_MIN};
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            if (rows[q] == INT_MIN) continue;
-            uint8_t *drow = dplane + (long long)(kYO + rows[q]) * D.pitch + kXO;
-            if (nvalid == 4) *reinterpret_cast<uint32_t *>(drow + x) = out;
-            else for (int k = 0; k < nvalid; k++) drow[x + k] = (uint8_t)(out >> (8 * k));
-            // left / right frame columns mirrored from interior columns 1..19 and w-20..w-2
-            if (x <= kEdge || x + 3 >= D.w - 1 - kEdge) {
-                for (int k = 0; k < nvalid; k++) {
-                    const int xx = x + k;
-                    const uint8_t pv = (uint8_t)(out >> (8 * k));
-                    if (xx >= 1 && xx <= kEdge) drow[-xx] = pv;
-                    if (xx <= D.w - 2 && xx >= D.w - 1 - kEdge) drow[2 * (D.w - 1) - xx] = pv;
-                }
-            }
-        }
+        const int4 t = s_ty[r];
+        const uint4 h0 = *reinterpret_cast<const uint4 *>(s_h + t.x + c4);
+        const uint4 h1 = *reinterpret_cast<const uint4 *>(s_h + t.y + c4);
+        const uint32_t p0 = (__umulhi((uint32_t)t.z, h0.x) + __umulhi((uint32_t)t.w, h1.x) + 2u) >> 2;
+        const uint32_t p1 = (__umulhi((uint32_t)t.z, h0.y) + __umulhi((uint32_t)t.w, h1.y) + 2u) >> 2;
+        const uint32_t p2 = (__umulhi((uint32_t)t.z, h0.z) + __umulhi((uint32_t)t.w, h1.z) + 2u) >> 2;
+        const uint32_t p3 = (__umulhi((uint32_t)t.z, h0.w) + __umulhi((uint32_t)t.w, h1.w) + 2u) >> 2;
+        const uint32_t out = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+        const int y = oy0 + r;
+        resize_store4(dplane + (long long)(kYO + y) * D.pitch, x, out, nvalid, x_edge, D.w);
+        // REFLECT_101 image of this row in the top / bottom frame (levels are at least 68 rows high: at most one)
+        int ym = INT_MIN;
+        if (y >= 1 && y <= kEdge) ym = -y;
+        else if (y <= D.h - 2 && y >= D.h - 1 - kEdge) ym = 2 * (D.h - 1) - y;
+        if (ym != INT_MIN) resize_store4(dplane + (long long)(kYO + ym) * D.pitch, x, out, nvalid, x_edge, D.w);
     }
 }
 
@@ -677,41 +688,46 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
     if (i >= lvl_n[b * G.nlevels + lvl]) return;
     const uint32_t kp = lvl_kp[(long long)b * G.kp_per_image + warp];
     const int x = cand_x(kp), y = cand_y(kp);
-    // ---- orientation
-    const uint8_t *c = plane_ptr(pyr, L, b) + (long long)(kYO + y) * L.pitch + kXO + x;
+    // ---- orientation: lane = column u of the patch; the lane's column sum gives m10, the row-weighted sum m01
     const int u = lane - kHalfPatch;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int au = u < 0 ? -u : u;
         constexpr int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // src/ORBextractor.cc:399-413
+        const uint8_t *p = plane_ptr(pyr, L, b) + (long long)(kYO + y - kHalfPatch) * L.pitch + kXO + x + u;
+        int colsum = 0;
 #pragma unroll
         for (int v = -kHalfPatch; v <= kHalfPatch; v++) {   // fully unrolled: 31 independent loads in flight
             if (au <= umax[v < 0 ? -v : v]) {
-                const int val = __ldg(c + (long long)v * L.pitch + u);
-                m10 += u * val; m01 += v * val;
+                const int val = __ldg(p);
+                colsum += val; m01 += v * val;
             }
+            p += L.pitch;
         }
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
     const float angle = orbx_fast_atan2((float)m01, (float)m10);
-    // ---- descriptor
+    // ---- descriptor: lane = output byte; its 16 pattern points are 32 signed bytes = two 128-bit loads
     const float rad = __fmul_rn(angle, 0.0174532924f);   // (float)(CV_PI/180.f)
     float sn, cs;
     orbx_sincosf(rad, &sn, &cs);
     const uint8_t *cb = plane_ptr(blur, L, b) + (long long)(kYO + y) * L.pitch + kXO + x;
-    const signed char *pp = pattern + lane * 32;
+    const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(pattern) + 2 * lane), pb = __ldg(reinterpret_cast<const uint4 *>(pattern) + 2 * lane + 1);
+    const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};   // word k = (x0, y0, x1, y1) of test k
+    const int pitch = L.pitch;
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int tv[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const float px = (float)pp[(2 * k + e) * 2], py = (float)pp[(2 * k + e) * 2 + 1];
+            const float px = (float)(signed char)(pw[k] >> (16 * e)), py = (float)(signed char)(pw[k] >> (16 * e + 8));
             float fy, fx;
             if (G.fma_mode) { fy = __fmaf_rn(px, sn, __fmul_rn(py, cs)); fx = __fmaf_rn(px, cs, -__fmul_rn(py, sn)); }
             else { fy = __fadd_rn(__fmul_rn(px, sn), __fmul_rn(py, cs)); fx = __fsub_rn(__fmul_rn(px, cs), __fmul_rn(py, sn)); }
-            tv[e] = __ldg(cb + (long long)__float2int_rn(fy) * L.pitch + __float2int_rn(fx));
+            tv[e] = __ldg(cb + (__float2int_rn(fy) * pitch + __float2int_rn(fx)));
         }
         val |= (tv[0] < tv[1] ? 1 : 0) << k;
     }

@@ -36,6 +36,14 @@ def main():
     # the report repeats functions per launch; keep the first launch of the kernel
     first = lines[0][0] if lines else None
     lines = [l for l in lines if l[0] == first]
+    agg, order = {}, []
+    for l in lines:            # the same kernel may have been captured several times: aggregate per (file, line)
+        k = (l[1], l[2])
+        if k not in agg:
+            agg[k] = [l[0], l[1], l[2], 0.0, 0.0, 0.0, l[6]]
+            order.append(k)
+        agg[k][3] += l[3]; agg[k][4] += l[4]; agg[k][5] += l[5]
+    lines = [tuple(agg[k]) for k in order]
     tot = sum(l[3] for l in lines) or 1
     tots = sum(l[4] for l in lines) or 1
     print('kernel:', first)
