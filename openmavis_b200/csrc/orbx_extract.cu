@@ -1,6 +1,7 @@
 // orbx_extract.cu — host side of the extraction C ABI (include/orbx.h): geometry tables, device arenas,
 // launch sequence.  Replaces ORBextractor::ORBextractor / operator() (src/ORBextractor.cc:351-414, 987-1071).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -58,11 +59,19 @@ struct orbx_extractor {
     int blur_total_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0, rsz_smem = 0;
     int rsz_rows = 0, rsz_pitch = 0;
-    int oct_list_cap = 0;
+    int oct_list_cap = 0, oct_threads = 256;
     long long pyr_bytes_per_batch = 0;
     std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // chunk pipelines: a batch is cut into chunks of chunk_images; chunk k runs on lane k % kLanes (main + aux stream: the
+    // blur of a chunk overlaps its FAST / quadtree), so the latency-bound stages of one chunk hide behind the
+    // bandwidth-bound stages of the next; host-buffer calls add a copy-in and a copy-out stream.
+    static constexpr int kLanes = 2;
+    cudaStream_t lane_main[kLanes] = {}, lane_aux[kLanes] = {}, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_pyr[kLanes] = {}, ev_blur[kLanes] = {}, ev_lane[kLanes] = {}, ev_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_out;
+    int chunk_images = 0;                            // 0 = choose from the batch size
     static constexpr int kRing = 16;                 // profiled calls kept for orbx_extractor_stage_ms
     cudaEvent_t ev[kRing][ORBX_NUM_STAGES] = {};
     int prof_calls = 0;                              // profiled calls since profiling was switched on
@@ -198,6 +207,19 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     if (ex->h_nfeat) cudaFreeHost(ex->h_nfeat);
     for (auto &r : ex->ev) for (auto &e : r) if (e) cudaEventDestroy(e);
     if (ex->ev_staging) cudaEventDestroy(ex->ev_staging);
+    for (int i = 0; i < orbx_extractor::kLanes; i++) {
+        if (ex->lane_main[i]) cudaStreamDestroy(ex->lane_main[i]);
+        if (ex->lane_aux[i]) cudaStreamDestroy(ex->lane_aux[i]);
+        if (ex->ev_pyr[i]) cudaEventDestroy(ex->ev_pyr[i]);
+        if (ex->ev_blur[i]) cudaEventDestroy(ex->ev_blur[i]);
+        if (ex->ev_lane[i]) cudaEventDestroy(ex->ev_lane[i]);
+    }
+    if (ex->s_h2d) cudaStreamDestroy(ex->s_h2d);
+    if (ex->s_d2h) cudaStreamDestroy(ex->s_d2h);
+    if (ex->ev_fork) cudaEventDestroy(ex->ev_fork);
+    if (ex->ev_d2h) cudaEventDestroy(ex->ev_d2h);
+    for (auto &v : ex->ev_in) cudaEventDestroy(v);
+    for (auto &v : ex->ev_out) cudaEventDestroy(v);
     if (ex->own_stream) cudaStreamDestroy(ex->own_stream);
     delete ex;
 }
@@ -215,6 +237,7 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
     orbx_extractor *ex = new orbx_extractor();
     ex->device = device; ex->width = width; ex->height = height; ex->max_images = max_images;
     ex->max_nfeatures = max_nfeatures; ex->nlevels = nlevels; ex->scale_factor = scale_factor;
+    if (const char *t = getenv("ORBX_OCT_THREADS")) ex->oct_threads = std::max(32, std::min(512, atoi(t) & ~31));   // tuning knob
     int st = build_geometry(ex, fma_mode ? 1 : 0);
     if (st != ORBX_OK) { delete ex; return st; }
     const Geom &G = ex->G;
@@ -233,6 +256,18 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
     ex->stream = ex->own_stream;
     for (auto &r : ex->ev) for (auto &e : r) EX_CUDA(cudaEventCreate(&e));
     EX_CUDA(cudaEventCreateWithFlags(&ex->ev_staging, cudaEventDisableTiming));
+    for (int i = 0; i < orbx_extractor::kLanes; i++) {
+        EX_CUDA(cudaStreamCreateWithFlags(&ex->lane_main[i], cudaStreamNonBlocking));
+        EX_CUDA(cudaStreamCreateWithFlags(&ex->lane_aux[i], cudaStreamNonBlocking));
+        EX_CUDA(cudaEventCreateWithFlags(&ex->ev_pyr[i], cudaEventDisableTiming));
+        EX_CUDA(cudaEventCreateWithFlags(&ex->ev_blur[i], cudaEventDisableTiming));
+        EX_CUDA(cudaEventCreateWithFlags(&ex->ev_lane[i], cudaEventDisableTiming));
+    }
+    EX_CUDA(cudaStreamCreateWithFlags(&ex->s_h2d, cudaStreamNonBlocking));
+    EX_CUDA(cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking));
+    EX_CUDA(cudaEventCreateWithFlags(&ex->ev_fork, cudaEventDisableTiming));
+    EX_CUDA(cudaEventCreateWithFlags(&ex->ev_d2h, cudaEventDisableTiming));
+    if (const char *t = getenv("ORBX_CHUNK")) ex->chunk_images = std::max(0, atoi(t));   // tuning knob
     EX_CUDA(dalloc(&ex->d_in, B * width * height));
     EX_CUDA(dalloc(&ex->d_pyr, (size_t)ex->pyr_bytes_per_batch));
     EX_CUDA(dalloc(&ex->d_blur, (size_t)ex->pyr_bytes_per_batch));
@@ -328,8 +363,66 @@ int orbx_extractor_set_profiling(orbx_extractor *ex, int enabled) {
 
 int orbx_extractor_last_launches(const orbx_extractor *ex) { return ex ? ex->last_launches : 0; }
 
-// Enqueue the whole pipeline for n images whose pixels are at d_images (device, tightly packed).
-static int enqueue(orbx_extractor *ex, int n, const uint8_t *d_images, const orbx_image_params *params) {
+// Launches of one chunk: images [i0, i0 + cnt) of the batch, pixels at d_img (device, tightly packed, image i0 first).
+// sA carries pyramid -> FAST -> quadtree -> slots -> orientation + descriptor; the blur runs on sB between the pyramid and
+// the descriptor.  With sA == sB (profiling) the stages are serial and `ev` receives one event per stage boundary.
+static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_img, cudaStream_t sA, cudaStream_t sB, int lane,
+                         cudaEvent_t *ev) {
+    const Geom &G = ex->G;
+    const int nl = ex->nlevels;
+    int launches = 0;
+    {   // pyramid
+        const LevelGeom &L0 = G.lv[0];
+        const int chunks = (kXO + L0.w + kEdge + 15) >> 4;
+        dim3 grid((chunks * ((L0.rows + kL0Rows - 1) / kL0Rows) + 255) / 256, cnt);
+        k_level0<<<grid, 256, 0, sA>>>(d_img, (long long)ex->width * ex->height, ex->width, ex->d_pyr, L0, i0);
+        launches++;
+        for (int l = 1; l < nl; l++) {
+            const LevelGeom &D = G.lv[l];
+            dim3 g((D.w + kRszTW - 1) / kRszTW, (D.h + kRszTH - 1) / kRszTH, cnt);
+            k_resize<<<g, kRszThreads, ex->rsz_smem, sA>>>(ex->d_pyr, G.lv[l - 1], D, ex->d_taps, ex->rsz_rows, ex->rsz_pitch, i0);
+            launches++;
+        }
+    }
+    if (ev) ORBX_CUDA(cudaEventRecord(ev[1], sA));
+    if (sB != sA) {
+        ORBX_CUDA(cudaEventRecord(ex->ev_pyr[lane], sA));
+        ORBX_CUDA(cudaStreamWaitEvent(sB, ex->ev_pyr[lane], 0));
+    }
+    k_blur<<<dim3(ex->blur_total_tiles, cnt), kBlurWarps * 32, kBlurSmem, sB>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles, i0);
+    launches++;
+    if (sB != sA) ORBX_CUDA(cudaEventRecord(ex->ev_blur[lane], sB));
+    if (ev) ORBX_CUDA(cudaEventRecord(ev[2], sA));
+    k_fast<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, i0);
+    launches++;
+    if (ev) ORBX_CUDA(cudaEventRecord(ev[3], sA));
+    k_octree<<<dim3(nl, cnt), ex->oct_threads, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
+                                                                   ex->d_lin_n, ex->d_node, ex->d_slot, ex->d_lvl_kp, ex->d_lvl_n,
+                                                                   ex->oct_list_cap, i0);
+    launches++;
+    if (ev) ORBX_CUDA(cudaEventRecord(ev[4], sA));
+    k_slots<<<cnt, 256, 0, sA>>>(G, ex->d_params, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot, ex->d_n_kp, ex->d_n_mono, i0);
+    launches++;
+    if (ev) ORBX_CUDA(cudaEventRecord(ev[5], sA));
+    if (sB != sA) ORBX_CUDA(cudaStreamWaitEvent(sA, ex->ev_blur[lane], 0));
+    k_orient_desc<<<dim3((G.kp_per_image * 32 + 255) / 256, cnt), 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp,
+                                                                                ex->d_lvl_n, ex->d_slot, ex->d_lvl_angle, ex->d_out_kp,
+                                                                                ex->d_out_desc, i0);
+    launches++;
+    if (ev) ORBX_CUDA(cudaEventRecord(ev[6], sA));
+    ex->last_launches += launches;
+    return ORBX_OK;
+}
+
+static int images_per_chunk(const orbx_extractor *ex, int n, bool host_io) {
+    if (ex->chunk_images > 0) return std::min(n, ex->chunk_images);
+    if (n <= 16) return n;
+    const int parts = host_io ? 4 : 2;     // measured on B200 (320 images of 720x540): 80-image chunks for host I/O, 160 otherwise
+    return std::max(16, (n + parts - 1) / parts);
+}
+
+// Validates and stages the per-image parameters (pinned staging -> device, on the handle's stream).
+static int stage_params(orbx_extractor *ex, int n, const orbx_image_params *params) {
     if (n <= 0 || n > ex->max_images) return fail(ORBX_ERR_CAPACITY, "n_images exceeds the handle's max_images");
     const Geom &G = ex->G;
     const int nl = ex->nlevels;
@@ -350,52 +443,116 @@ static int enqueue(orbx_extractor *ex, int n, const uint8_t *d_images, const orb
     ORBX_CUDA(cudaMemcpyAsync(ex->d_params, ex->h_params, n * sizeof(orbx_image_params), cudaMemcpyHostToDevice, s));
     ORBX_CUDA(cudaMemcpyAsync(ex->d_nfeat, ex->h_nfeat, (size_t)n * nl * sizeof(int), cudaMemcpyHostToDevice, s));
     ORBX_CUDA(cudaEventRecord(ex->ev_staging, s));
-    int launches = 0;
-    const bool prof = ex->profiling;
-    cudaEvent_t *ev = ex->ev[ex->prof_calls % orbx_extractor::kRing];
-    if (prof) ORBX_CUDA(cudaEventRecord(ev[0], s));
-    {   // pyramid
-        const LevelGeom &L0 = G.lv[0];
-        const int chunks = (kXO + L0.w + kEdge + 15) >> 4;
-        dim3 grid((chunks * ((L0.rows + kL0Rows - 1) / kL0Rows) + 255) / 256, n);
-        k_level0<<<grid, 256, 0, s>>>(d_images, (long long)ex->width * ex->height, ex->width, ex->d_pyr, L0, 0);
-        launches++;
-        for (int l = 1; l < nl; l++) {
-            const LevelGeom &D = G.lv[l];
-            dim3 g((D.w + kRszTW - 1) / kRszTW, (D.h + kRszTH - 1) / kRszTH, n);
-            k_resize<<<g, kRszThreads, ex->rsz_smem, s>>>(ex->d_pyr, G.lv[l - 1], D, ex->d_taps, ex->rsz_rows, ex->rsz_pitch, 0);
-            launches++;
+    ex->last_launches = 0;
+    ex->last_n = n;
+    return ORBX_OK;
+}
+
+// Host images of one chunk -> d_in on stream s: one copy per run of images that are contiguous in host memory.
+static int upload_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *const *images, const int *strides, cudaStream_t s) {
+    const size_t img_bytes = (size_t)ex->width * ex->height;
+    int i = i0;
+    while (i < i0 + cnt) {
+        const int st = strides ? strides[i] : ex->width;
+        if (st == ex->width) {
+            int j = i + 1;
+            while (j < i0 + cnt && (strides ? strides[j] : ex->width) == ex->width && images[j] == images[j - 1] + img_bytes) j++;
+            ORBX_CUDA(cudaMemcpyAsync(ex->d_in + i * img_bytes, images[i], (size_t)(j - i) * img_bytes, cudaMemcpyHostToDevice, s));
+            i = j;
+        } else {
+            ORBX_CUDA(cudaMemcpy2DAsync(ex->d_in + i * img_bytes, ex->width, images[i], st, ex->width, ex->height, cudaMemcpyHostToDevice, s));
+            i++;
         }
     }
-    if (prof) ORBX_CUDA(cudaEventRecord(ev[1], s));
-    k_blur<<<dim3(ex->blur_total_tiles, n), kBlurWarps * 32, kBlurSmem, s>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles, 0);
-    launches++;
-    if (prof) ORBX_CUDA(cudaEventRecord(ev[2], s));
-    k_fast<<<dim3(G.fast_total_tiles, n), kFastThreads, ex->fast_smem, s>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, 0);
-    launches++;
-    if (prof) ORBX_CUDA(cudaEventRecord(ev[3], s));
-    k_octree<<<dim3(nl, n), 512, ex->oct_smem, s>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
-                                                    ex->d_lin_n, ex->d_node, ex->d_slot, ex->d_lvl_kp, ex->d_lvl_n,
-                                                    ex->oct_list_cap);
-    launches++;
-    if (prof) ORBX_CUDA(cudaEventRecord(ev[4], s));
-    k_slots<<<n, 256, 0, s>>>(G, ex->d_params, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot, ex->d_n_kp, ex->d_n_mono);
-    launches++;
-    if (prof) ORBX_CUDA(cudaEventRecord(ev[5], s));
-    k_orient_desc<<<dim3((G.kp_per_image * 32 + 255) / 256, n), 256, 0, s>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern,
-                                                                             ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,
-                                                                             ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc);
-    launches++;
-    if (prof) { ORBX_CUDA(cudaEventRecord(ev[6], s)); ex->have_times = true; ex->prof_calls++; }
+    return ORBX_OK;
+}
+
+// Results of images [i0, i0 + cnt) -> host buffers on stream s.
+static int download_chunk(orbx_extractor *ex, int i0, int cnt, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono, cudaStream_t s) {
+    const size_t oc = (size_t)ex->G.out_cap;
+    if (kps) {
+        if ((size_t)cap == oc)
+            ORBX_CUDA(cudaMemcpyAsync(kps + i0 * oc, ex->d_out_kp + i0 * oc, cnt * oc * sizeof(orbx_kp), cudaMemcpyDeviceToHost, s));
+        else
+            ORBX_CUDA(cudaMemcpy2DAsync(kps + (size_t)i0 * cap, (size_t)cap * sizeof(orbx_kp), ex->d_out_kp + i0 * oc, oc * sizeof(orbx_kp),
+                                        oc * sizeof(orbx_kp), cnt, cudaMemcpyDeviceToHost, s));
+    }
+    if (desc) {
+        if ((size_t)cap == oc)
+            ORBX_CUDA(cudaMemcpyAsync(desc + i0 * oc * 32, ex->d_out_desc + i0 * oc * 32, cnt * oc * 32, cudaMemcpyDeviceToHost, s));
+        else
+            ORBX_CUDA(cudaMemcpy2DAsync(desc + (size_t)i0 * cap * 32, (size_t)cap * 32, ex->d_out_desc + i0 * oc * 32, oc * 32, oc * 32, cnt,
+                                        cudaMemcpyDeviceToHost, s));
+    }
+    if (n_kp) ORBX_CUDA(cudaMemcpyAsync(n_kp + i0, ex->d_n_kp + i0, cnt * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (n_mono) ORBX_CUDA(cudaMemcpyAsync(n_mono + i0, ex->d_n_mono + i0, cnt * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return ORBX_OK;
+}
+
+// The whole batch.  d_images: device pixels (tightly packed) or, when `images` is given, host images that are uploaded
+// chunk by chunk into d_in; with host outputs (kps/desc/...) the results of a chunk are downloaded as soon as it is done.
+static int run_batch(orbx_extractor *ex, int n, const uint8_t *d_images, const uint8_t *const *images, const int *strides,
+                     const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono) {
+    int st = stage_params(ex, n, params);
+    if (st != ORBX_OK) return st;
+    cudaStream_t s = ex->stream;
+    const bool host_io = images != nullptr;
+    const size_t img_bytes = (size_t)ex->width * ex->height;
+    if (ex->profiling) {   // serial, one chunk, stage events on the handle's stream
+        cudaEvent_t *ev = ex->ev[ex->prof_calls % orbx_extractor::kRing];
+        if (host_io && (st = upload_chunk(ex, 0, n, images, strides, s)) != ORBX_OK) return st;
+        ORBX_CUDA(cudaEventRecord(ev[0], s));
+        if ((st = enqueue_chunk(ex, 0, n, host_io ? ex->d_in : d_images, s, s, 0, ev)) != ORBX_OK) return st;
+        ex->have_times = true; ex->prof_calls++;
+        if (host_io && (st = download_chunk(ex, 0, n, kps, desc, cap, n_kp, n_mono, s)) != ORBX_OK) return st;
+        ORBX_CUDA(cudaGetLastError());
+        return ORBX_OK;
+    }
+    const int per = images_per_chunk(ex, n, host_io);
+    const int nchunks = (n + per - 1) / per;
+    while ((int)ex->ev_in.size() < nchunks) {
+        cudaEvent_t a, b;
+        ORBX_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        ORBX_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ex->ev_in.push_back(a); ex->ev_out.push_back(b);
+    }
+    ORBX_CUDA(cudaEventRecord(ex->ev_fork, s));
+    if (host_io) {
+        ORBX_CUDA(cudaStreamWaitEvent(ex->s_h2d, ex->ev_fork, 0));
+        ORBX_CUDA(cudaStreamWaitEvent(ex->s_d2h, ex->ev_fork, 0));
+    }
+    const int lanes = std::min(nchunks, (int)orbx_extractor::kLanes);
+    for (int l = 0; l < lanes; l++) ORBX_CUDA(cudaStreamWaitEvent(ex->lane_main[l], ex->ev_fork, 0));
+    for (int k = 0; k < nchunks; k++) {
+        const int i0 = k * per, cnt = std::min(per, n - i0), lane = k % orbx_extractor::kLanes;
+        cudaStream_t sA = ex->lane_main[lane], sB = ex->lane_aux[lane];
+        if (host_io) {
+            if ((st = upload_chunk(ex, i0, cnt, images, strides, ex->s_h2d)) != ORBX_OK) return st;
+            ORBX_CUDA(cudaEventRecord(ex->ev_in[k], ex->s_h2d));
+            ORBX_CUDA(cudaStreamWaitEvent(sA, ex->ev_in[k], 0));
+        }
+        if ((st = enqueue_chunk(ex, i0, cnt, (host_io ? ex->d_in : d_images) + i0 * img_bytes, sA, sB, lane, nullptr)) != ORBX_OK) return st;
+        if (host_io) {
+            ORBX_CUDA(cudaEventRecord(ex->ev_out[k], sA));
+            ORBX_CUDA(cudaStreamWaitEvent(ex->s_d2h, ex->ev_out[k], 0));
+            if ((st = download_chunk(ex, i0, cnt, kps, desc, cap, n_kp, n_mono, ex->s_d2h)) != ORBX_OK) return st;
+        }
+    }
+    for (int l = 0; l < lanes; l++) {   // join: everything is ordered before later work on the handle's stream
+        ORBX_CUDA(cudaEventRecord(ex->ev_lane[l], ex->lane_main[l]));
+        ORBX_CUDA(cudaStreamWaitEvent(s, ex->ev_lane[l], 0));
+    }
+    if (host_io) {
+        ORBX_CUDA(cudaEventRecord(ex->ev_d2h, ex->s_d2h));
+        ORBX_CUDA(cudaStreamWaitEvent(s, ex->ev_d2h, 0));
+    }
     ORBX_CUDA(cudaGetLastError());
-    ex->last_launches = launches;
-    ex->last_n = n;
     return ORBX_OK;
 }
 
 int orbx_extract_batch_device(orbx_extractor *ex, int n_images, const uint8_t *d_images, const orbx_image_params *params) {
     if (!ex || !d_images || !params) return fail(ORBX_ERR_INVALID, "NULL argument");
-    return enqueue(ex, n_images, d_images, params);
+    return run_batch(ex, n_images, d_images, nullptr, nullptr, params, nullptr, nullptr, 0, nullptr, nullptr);
 }
 
 int orbx_extract_fetch(orbx_extractor *ex, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono) {
@@ -404,17 +561,9 @@ int orbx_extract_fetch(orbx_extractor *ex, orbx_kp *kps, uint8_t *desc, int cap,
     if (n <= 0) return fail(ORBX_ERR_INVALID, "no results to fetch");
     if (cap < ex->G.out_cap && (kps || desc)) return fail(ORBX_ERR_CAPACITY, "cap smaller than orbx_extractor_capacity()");
     ORBX_CUDA(cudaSetDevice(ex->device));
-    cudaStream_t s = ex->stream;
-    const int oc = ex->G.out_cap;
-    if (kps)
-        ORBX_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orbx_kp), ex->d_out_kp, (size_t)oc * sizeof(orbx_kp),
-                                    (size_t)oc * sizeof(orbx_kp), n, cudaMemcpyDeviceToHost, s));
-    if (desc)
-        ORBX_CUDA(cudaMemcpy2DAsync(desc, (size_t)cap * 32, ex->d_out_desc, (size_t)oc * 32, (size_t)oc * 32, n,
-                                    cudaMemcpyDeviceToHost, s));
-    if (n_kp) ORBX_CUDA(cudaMemcpyAsync(n_kp, ex->d_n_kp, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (n_mono) ORBX_CUDA(cudaMemcpyAsync(n_mono, ex->d_n_mono, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    ORBX_CUDA(cudaStreamSynchronize(s));
+    int st = download_chunk(ex, 0, n, kps, desc, cap, n_kp, n_mono, ex->stream);
+    if (st != ORBX_OK) return st;
+    ORBX_CUDA(cudaStreamSynchronize(ex->stream));
     return ORBX_OK;
 }
 
@@ -432,19 +581,16 @@ int orbx_extract_batch(orbx_extractor *ex, int n_images, const uint8_t *const *i
                        const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono) {
     if (!ex || !images || !params) return fail(ORBX_ERR_INVALID, "NULL argument");
     if (n_images <= 0 || n_images > ex->max_images) return fail(ORBX_ERR_CAPACITY, "n_images exceeds the handle's max_images");
-    ORBX_CUDA(cudaSetDevice(ex->device));
-    const size_t img_bytes = (size_t)ex->width * ex->height;
-    cudaStream_t s = ex->stream;
+    if (cap < ex->G.out_cap && (kps || desc)) return fail(ORBX_ERR_CAPACITY, "cap smaller than orbx_extractor_capacity()");
     for (int i = 0; i < n_images; i++) {
         if (!images[i]) return fail(ORBX_ERR_EMPTY, "empty image");
-        const int st = strides ? strides[i] : ex->width;
-        if (st < ex->width) return fail(ORBX_ERR_INVALID, "stride smaller than width");
-        ORBX_CUDA(cudaMemcpy2DAsync(ex->d_in + i * img_bytes, ex->width, images[i], st, ex->width, ex->height,
-                                    cudaMemcpyHostToDevice, s));
+        if (strides && strides[i] < ex->width) return fail(ORBX_ERR_INVALID, "stride smaller than width");
     }
-    int st = enqueue(ex, n_images, ex->d_in, params);
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    int st = run_batch(ex, n_images, nullptr, images, strides, params, kps, desc, cap, n_kp, n_mono);
     if (st != ORBX_OK) return st;
-    return orbx_extract_fetch(ex, kps, desc, cap, n_kp, n_mono);
+    ORBX_CUDA(cudaStreamSynchronize(ex->stream));
+    return ORBX_OK;
 }
 
 int orbx_extract(orbx_extractor *ex, const uint8_t *image, int stride, const orbx_image_params *params, orbx_kp *kps,

@@ -580,10 +580,10 @@ __global__ void __launch_bounds__(512) k_octree(Geom G, const int *__restrict__ 
                                                 const int *__restrict__ cell_cnt, int *__restrict__ cell_off,
                                                 uint32_t *__restrict__ lin, int *__restrict__ lin_n,
                                                 unsigned short *__restrict__ node, int *__restrict__ sel_tmp,
-                                                uint32_t *__restrict__ lvl_kp, int *__restrict__ lvl_n, int list_cap) {
+                                                uint32_t *__restrict__ lvl_kp, int *__restrict__ lvl_n, int list_cap, int img0) {
     extern __shared__ __align__(16) unsigned char oct_smem[];
     __shared__ int s_total;
-    const int lvl = blockIdx.x, b = blockIdx.y;
+    const int lvl = blockIdx.x, b = blockIdx.y + img0;
     const LevelGeom &L = G.lv[lvl];
     DevCtx cx; cx.tid = threadIdx.x; cx.nt = blockDim.x; cx.total = &s_total;
     const int ncell = L.n_cols * L.n_rows;
@@ -626,9 +626,9 @@ __global__ void __launch_bounds__(512) k_octree(Geom G, const int *__restrict__ 
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_slots(Geom G, const orbx_image_params *__restrict__ params,
                                                const uint32_t *__restrict__ lvl_kp, const int *__restrict__ lvl_n,
-                                               int *__restrict__ slot, int *__restrict__ n_kp, int *__restrict__ n_mono) {
+                                               int *__restrict__ slot, int *__restrict__ n_kp, int *__restrict__ n_mono, int img0) {
     __shared__ int s_warp[8];
-    const int b = blockIdx.x;
+    const int b = blockIdx.x + img0;
     const orbx_image_params prm = params[b];
     int n = 0;
     for (int l = 0; l < G.nlevels; l++) n += lvl_n[b * G.nlevels + l];
@@ -676,10 +676,10 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
                                                      const signed char *__restrict__ pattern, const uint32_t *__restrict__ lvl_kp,
                                                      const int *__restrict__ lvl_n, const int *__restrict__ slot,
                                                      float *__restrict__ lvl_angle, orbx_kp *__restrict__ out_kp,
-                                                     uint8_t *__restrict__ out_desc) {
+                                                     uint8_t *__restrict__ out_desc, int img0) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + img0;
     if (warp >= G.kp_per_image) return;
     int lvl = 0;
     while (lvl + 1 < G.nlevels && warp >= G.lv[lvl + 1].kp_off) lvl++;
