@@ -1,0 +1,59 @@
+// ORBextractor.h — header-compatible replacement of the reference's include/ORBextractor.h:28-84, implemented on the C ABI
+// of liborbx.so (include/orbx.h).  Same class name, namespace, public signatures and public data member, so
+// src/Frame.cc (ExtractORB :599-640, the constructors :211-214, :1320-1337, :1841-1862), src/Tracking.cc:572-587 compile
+// unchanged against it.
+#ifndef ORBEXTRACTOR_H
+#define ORBEXTRACTOR_H
+
+#include <vector>
+
+#include "orbx_cv_compat.h"
+
+struct orbx_extractor;
+
+namespace ORB_SLAM3 {
+
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    // include/ORBextractor.h:33-35, src/ORBextractor.cc:351-414
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+    ~ORBextractor();
+
+    // Compute the ORB features and descriptors on an image; mask is ignored (src/ORBextractor.cc:987-1071).
+    // Returns the number of keypoints outside the lapping area, -1 for an empty image.
+    int operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint> &_keypoints, cv::OutputArray _descriptors,
+                   std::vector<int> &vLappingArea);
+
+    int inline GetLevels() { return nlevels; }
+    float inline GetScaleFactor() { return scaleFactor; }
+    std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+    // Host mirrors of the pyramid levels of the last call (read by src/Frame.cc:1063,1147,1163).  They are downloaded after
+    // every call unless switched off (the 4-camera fisheye path never reads them).
+    std::vector<cv::Mat> mvImagePyramid;
+    void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
+    // extension: CUDA device of this extractor (default 0) — call before the first operator()
+    void SetDevice(int device) { mDevice = device; }
+
+protected:
+    int nfeatures;
+    double scaleFactor;
+    int nlevels;
+    int iniThFAST;
+    int minThFAST;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+
+private:
+    orbx_extractor *mHandle = nullptr;
+    int mWidth = 0, mHeight = 0, mDevice = 0;
+    bool mbDownloadPyramid = true;
+    std::vector<unsigned char> mKpBuf, mDescBuf;
+};
+
+}  // namespace ORB_SLAM3
+#endif

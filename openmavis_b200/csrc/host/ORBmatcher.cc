@@ -1,0 +1,73 @@
+// ORBmatcher.cc — array-level ORB_SLAM3::ORBmatcher on top of liborbx.so (Hamming cores of src/ORBmatcher.cc).
+#include "ORBmatcher.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../../include/orbx.h"
+
+namespace ORB_SLAM3 {
+
+const int ORBmatcher::TH_HIGH = 100;
+const int ORBmatcher::TH_LOW = 50;
+const int ORBmatcher::HISTO_LENGTH = 30;
+
+static void die(const char *what) {   // no CPU fallback: fail loudly
+    fprintf(stderr, "ORBmatcher::%s: %s\n", what, orbx_last_error());
+    abort();
+}
+
+ORBmatcher::ORBmatcher(float nnratio, bool checkOri, int device) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {
+    if (orbx_matcher_create(&mHandle, device) != ORBX_OK) die("ORBmatcher");
+}
+ORBmatcher::~ORBmatcher() { orbx_matcher_destroy(mHandle); }
+
+int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b) {
+    int d = 0;
+    if (orbx_descriptor_distance(0, a.ptr<unsigned char>(), b.ptr<unsigned char>(), 1, &d) != ORBX_OK) die("DescriptorDistance");
+    return d;
+}
+
+void ORBmatcher::KnnMatch2(const cv::Mat &query, const cv::Mat &train, std::vector<int> &idx, std::vector<int> &dist) {
+    idx.assign((size_t)query.rows * 2, -1); dist.assign((size_t)query.rows * 2, -1);
+    if (!query.isContinuous() || !train.isContinuous()) { fprintf(stderr, "KnnMatch2: descriptor matrices must be continuous\n"); abort(); }
+    if (orbx_knn2(mHandle, query.ptr<unsigned char>(), query.rows, train.ptr<unsigned char>(), train.rows, idx.data(), dist.data()) != ORBX_OK)
+        die("KnnMatch2");
+}
+
+std::vector<unsigned char> ORBmatcher::RatioTest(const std::vector<int> &dist, double ratio) {
+    std::vector<unsigned char> keep(dist.size() / 2);
+    orbx_ratio_test(dist.data(), (int)keep.size(), ratio, keep.data());
+    return keep;
+}
+
+int ORBmatcher::SearchForTriangulation(const std::vector<int> &nodes1, const std::vector<int> &ptr1, const std::vector<int> &idx1,
+                                       const std::vector<int> &nodes2, const std::vector<int> &ptr2, const std::vector<int> &idx2,
+                                       const cv::Mat &desc1, const cv::Mat &desc2, const std::vector<unsigned char> &skip1,
+                                       const std::vector<unsigned char> &skip2, std::vector<std::pair<size_t, size_t>> &vMatchedPairs) {
+    std::vector<int> m12((size_t)desc1.rows, -1);
+    int nm = 0;
+    if (orbx_search_for_triangulation(mHandle, (int)nodes1.size(), nodes1.data(), ptr1.data(), idx1.data(), (int)nodes2.size(),
+                                      nodes2.data(), ptr2.data(), idx2.data(), desc1.ptr<unsigned char>(), desc1.rows,
+                                      desc2.ptr<unsigned char>(), desc2.rows, skip1.empty() ? nullptr : skip1.data(),
+                                      skip2.empty() ? nullptr : skip2.data(), m12.data(), &nm) != ORBX_OK)
+        die("SearchForTriangulation");
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(nm);
+    for (size_t i = 0; i < m12.size(); i++)           // src/ORBmatcher.cc:1448-1453: ascending idx1
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
+    return nm;
+}
+
+int ORBmatcher::MatchCandidates(const cv::Mat &query, const cv::Mat &train, const std::vector<int> &row_ptr, const std::vector<int> &cand,
+                                std::vector<int> &bestIdx, std::vector<int> &bestDist, std::vector<int> &secondDist,
+                                std::vector<int> &bestPos, std::vector<int> &secondPos) {
+    const size_t nq = (size_t)query.rows;
+    bestIdx.assign(nq, -1); bestDist.assign(nq, 256); secondDist.assign(nq, 256); bestPos.assign(nq, -1); secondPos.assign(nq, -1);
+    if (orbx_match_csr(mHandle, query.ptr<unsigned char>(), query.rows, train.ptr<unsigned char>(), train.rows, row_ptr.data(), cand.data(),
+                       bestIdx.data(), bestDist.data(), secondDist.data(), bestPos.data(), secondPos.data()) != ORBX_OK)
+        die("MatchCandidates");
+    return (int)nq;
+}
+
+}  // namespace ORB_SLAM3

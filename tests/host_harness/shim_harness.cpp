@@ -1,0 +1,60 @@
+// C entry points around the C++ shim classes (openmavis_b200/csrc/host/) so the Python test-suite can drive
+// ORB_SLAM3::ORBextractor / ORBmatcher exactly the way src/Frame.cc does.  Test infrastructure.
+#include <string.h>
+
+#include <vector>
+
+#include "../../openmavis_b200/csrc/host/ORBextractor.h"
+#include "../../openmavis_b200/csrc/host/ORBmatcher.h"
+
+extern "C" {
+
+void *shim_extractor_new(int nf, float sf, int nl, int ini, int mn) { return new ORB_SLAM3::ORBextractor(nf, sf, nl, ini, mn); }
+void shim_extractor_delete(void *e) { delete (ORB_SLAM3::ORBextractor *)e; }
+
+void shim_extractor_tables(void *e, float *sf, float *inv_sf, float *s2, float *inv_s2) {
+    ORB_SLAM3::ORBextractor *x = (ORB_SLAM3::ORBextractor *)e;
+    const int n = x->GetLevels();
+    std::vector<float> a = x->GetScaleFactors(), b = x->GetInverseScaleFactors(), c = x->GetScaleSigmaSquares(), d = x->GetInverseScaleSigmaSquares();
+    memcpy(sf, a.data(), n * 4); memcpy(inv_sf, b.data(), n * 4); memcpy(s2, c.data(), n * 4); memcpy(inv_s2, d.data(), n * 4);
+}
+
+// the call of Frame::ExtractORB (src/Frame.cc:599-640): returns monoIndex; *n = keypoints.size()
+int shim_extract(void *e, unsigned char *img, int w, int h, int stride, int lap0, int lap1, float *kps28, unsigned char *desc, int cap, int *n) {
+    ORB_SLAM3::ORBextractor *x = (ORB_SLAM3::ORBextractor *)e;
+    cv::Mat image = img ? cv::Mat(h, w, CV_8UC1, img, (size_t)stride) : cv::Mat();
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat descriptors;
+    std::vector<int> lap = {lap0, lap1};
+    const int mono = (*x)(image, cv::Mat(), keys, descriptors, lap);
+    *n = (int)keys.size();
+    const int m = *n < cap ? *n : cap;
+    if (m > 0) memcpy(kps28, keys.data(), (size_t)m * sizeof(cv::KeyPoint));
+    for (int i = 0; i < m; i++) memcpy(desc + (size_t)i * 32, descriptors.ptr<unsigned char>(i), 32);
+    return mono;
+}
+
+// copies mvImagePyramid[level] (interior) into dst (tightly packed); returns 0 if the level is empty
+int shim_pyramid_level(void *e, int level, unsigned char *dst, int *w, int *h) {
+    ORB_SLAM3::ORBextractor *x = (ORB_SLAM3::ORBextractor *)e;
+    const cv::Mat &m = x->mvImagePyramid[level];
+    if (m.empty()) return 0;
+    *w = m.cols; *h = m.rows;
+    if (dst) for (int r = 0; r < m.rows; r++) memcpy(dst + (size_t)r * m.cols, m.ptr<unsigned char>(r), m.cols);
+    return 1;
+}
+
+int shim_descriptor_distance(unsigned char *a, unsigned char *b) {
+    return ORB_SLAM3::ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, a, 32), cv::Mat(1, 32, CV_8U, b, 32));
+}
+
+int shim_knn_ratio(unsigned char *q, int nq, unsigned char *t, int nt, double ratio, int *idx, int *dist, unsigned char *keep) {
+    ORB_SLAM3::ORBmatcher m(0.8f, false);
+    std::vector<int> vi, vd;
+    m.KnnMatch2(cv::Mat(nq, 32, CV_8U, q, 32), cv::Mat(nt, 32, CV_8U, t, 32), vi, vd);
+    std::vector<unsigned char> k = ORB_SLAM3::ORBmatcher::RatioTest(vd, ratio);
+    memcpy(idx, vi.data(), vi.size() * 4); memcpy(dist, vd.data(), vd.size() * 4); memcpy(keep, k.data(), k.size());
+    return ORB_SLAM3::ORBmatcher::TH_LOW * 1000 + ORB_SLAM3::ORBmatcher::TH_HIGH;
+}
+
+}  // extern "C"

@@ -59,7 +59,7 @@ def test_product_does_not_reference_oracle():
     bad = []
     for dp, _, fs in os.walk(os.path.join(ROOT, 'openmavis_b200')):
         for f in fs:
-            if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
+            if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp', '.cc')):
                 if re.search(r'oracle/|orb_oracle|oracle_lib|orc_', open(os.path.join(dp, f), errors='ignore').read().replace('orc_search_by_projection', '')):
                     bad.append(f)
     assert not bad, bad

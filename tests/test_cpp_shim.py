@@ -1,0 +1,80 @@
+"""The C++ drop-in classes (openmavis_b200/csrc/host: ORB_SLAM3::ORBextractor / ORBmatcher on the C ABI), driven the way
+src/Frame.cc drives the reference classes, through tests/host_harness/libshim_harness.so."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from openmavis_b200.synth import synth_image, synth_descriptors
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def shim():
+    subprocess.check_call(['make', '-C', os.path.join(ROOT, 'openmavis_b200', 'csrc')], stdout=subprocess.DEVNULL)
+    d = os.path.join(ROOT, 'tests', 'host_harness')
+    subprocess.check_call(['make', '-C', d], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(d, 'libshim_harness.so'))
+    L.shim_extractor_new.restype = C.c_void_p
+    L.shim_extractor_new.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.shim_extractor_delete.argtypes = [C.c_void_p]
+    L.shim_extractor_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    L.shim_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.shim_pyramid_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def test_shim_getters_match_reference_tables(shim):
+    # constructor arithmetic (src/ORBextractor.cc:362-376) — no CUDA needed
+    e = shim.shim_extractor_new(1000, 1.2, 8, 20, 7)
+    a = [np.zeros(8, np.float32) for _ in range(4)]
+    shim.shim_extractor_tables(e, *[O.p(x) for x in a])
+    t = O.OracleExtractor(1000, 1.2, 8, 20, 7).tables()
+    for got, key in zip(a, ('sf', 'inv_sf', 'sigma2', 'inv_sigma2')):
+        assert np.array_equal(got.view(np.uint32), t[key].view(np.uint32))
+    shim.shim_extractor_delete(e)
+
+
+def test_shim_empty_image_returns_minus_one(shim):
+    e = shim.shim_extractor_new(1000, 1.2, 8, 20, 7)
+    n = C.c_int(7)
+    assert shim.shim_extract(e, None, 0, 0, 0, 0, 0, None, None, 0, C.byref(n)) == -1    # src/ORBextractor.cc:994-995
+    shim.shim_extractor_delete(e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('lap', [(0, 0), (0, 1000), (200, 500)])
+def test_shim_operator_matches_oracle(shim, lap):
+    img = synth_image(752, 480, 77)
+    padded = np.zeros((480, 800), np.uint8); padded[:, :752] = img       # non-continuous cv::Mat (row stride 800)
+    e = shim.shim_extractor_new(1000, 1.2, 8, 20, 7)
+    cap = 1200
+    kps = np.zeros(cap, O.KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int(0)
+    mono = shim.shim_extract(e, O.p(padded), 752, 480, 800, lap[0], lap[1], O.p(kps), O.p(desc), cap, C.byref(n))
+    rm, rk, rd = O.OracleExtractor(1000, 1.2, 8, 20, 7)(img, lap)
+    assert mono == rm and n.value == len(rk)
+    assert np.array_equal(kps[:n.value], rk) and np.array_equal(desc[:n.value], rd)
+    E = O.OracleExtractor(1000, 1.2, 8, 20, 7); E(img, lap)
+    for l in (0, 3, 7):                                                   # mvImagePyramid host mirrors
+        w, h = C.c_int(), C.c_int()
+        assert shim.shim_pyramid_level(e, l, None, C.byref(w), C.byref(h)) == 1
+        buf = np.zeros((h.value, w.value), np.uint8)
+        shim.shim_pyramid_level(e, l, O.p(buf), C.byref(w), C.byref(h))
+        assert np.array_equal(buf, E.level(l)[19:-19, 19:-19])
+    shim.shim_extractor_delete(e)
+
+
+@pytest.mark.gpu
+def test_shim_matcher_matches_oracle(shim):
+    t = synth_descriptors(500, 1); q = synth_descriptors(300, 2); q[:100] = t[:100]; q[:100, 0] ^= 3
+    assert shim.shim_descriptor_distance(O.p(q[5]), O.p(t[9])) == O.hamming(q[5], t[9])
+    idx = np.zeros((300, 2), np.int32); dist = np.zeros((300, 2), np.int32); keep = np.zeros(300, np.uint8)
+    consts = shim.shim_knn_ratio(O.p(q), 300, O.p(t), 500, C.c_double(0.8), O.p(idx), O.p(dist), O.p(keep))
+    assert consts == 50 * 1000 + 100
+    ridx, rdist = O.knn2(q, t)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+    assert np.array_equal(keep.astype(bool), O.ratio_test(rdist, 0.8))
