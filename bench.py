@@ -226,6 +226,7 @@ def main():
     barrier()
     t_wall1 = time.perf_counter()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches_per_step = rig.last_launches()          # launches of one timed step (all chunks)
     # per-stage durations: a second, untimed-for-`value` pass with CUDA events between the stages (same stream)
     rig.set_profiling(True)
     for _ in range(min(args.steps, 16)):
@@ -234,7 +235,6 @@ def main():
     clocks = sampler.stop(t_wall0, time.perf_counter()) if sampler else None
     stage = rig.stage_ms()
     rig.set_profiling(False)
-    launches_per_step = rig.last_launches()
     value = world * frames * args.steps / (ms_total * 1e-3)
     res = rig.fetch(n_img)
     kp_per_image = float(np.mean([len(r[1]) for r in res]))

@@ -86,7 +86,7 @@ struct orbx_extractor {
     uint32_t *d_cells = nullptr, *d_lin = nullptr, *d_lvl_kp = nullptr;
     unsigned short *d_node = nullptr;
     int *d_cell_cnt = nullptr, *d_cell_off = nullptr, *d_lin_n = nullptr, *d_lvl_n = nullptr, *d_slot = nullptr;
-    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr;
+    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr, *d_fast_tiles = nullptr;
     float *d_lvl_angle = nullptr;
     orbx_kp *d_out_kp = nullptr;
     orbx_image_params *d_params = nullptr;
@@ -201,7 +201,7 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     cudaFree(ex->d_pattern); cudaFree(ex->d_cells); cudaFree(ex->d_lin); cudaFree(ex->d_lvl_kp); cudaFree(ex->d_node);
     cudaFree(ex->d_cell_cnt); cudaFree(ex->d_cell_off); cudaFree(ex->d_lin_n); cudaFree(ex->d_lvl_n); cudaFree(ex->d_slot);
     cudaFree(ex->d_n_kp); cudaFree(ex->d_n_mono); cudaFree(ex->d_nfeat); cudaFree(ex->d_lvl_angle); cudaFree(ex->d_out_kp);
-    cudaFree(ex->d_params);
+    cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles);
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_params) cudaFreeHost(ex->h_params);
     if (ex->h_nfeat) cudaFreeHost(ex->h_nfeat);
@@ -319,6 +319,12 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
             EX_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->rsz_smem));
         EX_CUDA(dalloc(&ex->d_taps, (size_t)ntap));
         EX_CUDA(cudaMemcpy(ex->d_taps, taps.data(), ntap * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+        std::vector<int> tinfo;   // FAST tile -> level | cell row << 4 | tile column << 16
+        for (int l = 0; l < nlevels; l++)
+            for (int i = 0; i < G.lv[l].n_rows; i++)
+                for (int j = 0; j < G.lv[l].fast_tiles_x; j++) tinfo.push_back(l | (i << 4) | (j << 16));
+        EX_CUDA(dalloc(&ex->d_fast_tiles, tinfo.size()));
+        EX_CUDA(cudaMemcpy(ex->d_fast_tiles, tinfo.data(), tinfo.size() * sizeof(int), cudaMemcpyHostToDevice));
         static const signed char pat[1024] = {ORBX_PATTERN_VALUES};
         EX_CUDA(dalloc(&ex->d_pattern, (size_t)1024));
         EX_CUDA(cudaMemcpy(ex->d_pattern, pat, 1024, cudaMemcpyHostToDevice));
@@ -393,7 +399,7 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
     launches++;
     if (sB != sA) ORBX_CUDA(cudaEventRecord(ex->ev_blur[lane], sB));
     if (ev) ORBX_CUDA(cudaEventRecord(ev[2], sA));
-    k_fast<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, i0);
+    k_fast<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, ex->d_fast_tiles, i0);
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[3], sA));
     k_octree<<<dim3(nl, cnt), ex->oct_threads, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,

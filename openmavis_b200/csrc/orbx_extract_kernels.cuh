@@ -12,6 +12,7 @@
 #include "math_core.cuh"
 #include "octree_core.cuh"
 #include "orbx_common.cuh"
+#include "tma.cuh"
 
 namespace orbx {
 
@@ -125,13 +126,16 @@ __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ py
         const ResizeTap t = tapy[tid];
         s_ty[tid] = make_int4((t.s0 - sy_lo) * kRszTW, (t.s1 - sy_lo) * kRszTW, (int)t.a0 << 16, (int)t.a1 << 16);
     }
-    {
-        const uint8_t *src = plane_ptr((const uint8_t *)pyr, S, b) + (long long)(kYO + sy_lo) * S.pitch + kXO + sx_al;
-        for (int c = tid & 7; c < nvec; c += 8)                 // 8 vectors (128 B) per row pass
-            for (int r = tid >> 3; r < nrow; r += kRszThreads / 8)
-                *reinterpret_cast<uint4 *>(s_src + r * src_pitch + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * S.pitch + 16 * c));
-    }
+    __shared__ __align__(8) uint64_t s_bar;
+    if (tid == 0) mbar_init(&s_bar, 1);
     __syncthreads();
+    if (tid < 32) {   // one TMA bulk copy per staged source row
+        const uint8_t *src = plane_ptr((const uint8_t *)pyr, S, b) + (long long)(kYO + sy_lo) * S.pitch + kXO + sx_al;
+        if (tid == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(nrow * nvec * 16));
+        __syncwarp();
+        for (int r = tid; r < nrow; r += 32) bulk_g2s(s_src + r * src_pitch, src + (long long)r * S.pitch, (uint32_t)(nvec * 16), &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
     {   // phase H: thread = one output column, rows strided by 4:  r[sy][d] >> 4
         const int c = tid & (kRszTW - 1), rg = tid >> 6;
         if (c < ow) {
@@ -208,14 +212,18 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
     const uint8_t *src = plane_ptr(pyr, L, b);
     // stage plane rows kYO + y0 - 3 .., plane columns kXO + x0 - 16 .. (16-byte aligned)
     const int rows_needed = min(kBlurSR, L.h + 3 - (y0 - 3));
-    for (int i = threadIdx.x; i < rows_needed * (kBlurSP / 16); i += kBlurWarps * 32) {
-        const int r = i / (kBlurSP / 16), c = i - r * (kBlurSP / 16);
-        const int pc = kXO + x0 - 16 + 16 * c;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (pc + 16 <= L.pitch) v = __ldg(reinterpret_cast<const uint4 *>(src + (long long)(kYO + y0 - 3 + r) * L.pitch + pc));
-        *reinterpret_cast<uint4 *>(s_src + r * kBlurSP + 16 * c) = v;
-    }
+    __shared__ __align__(8) uint64_t s_bar;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
+    if (threadIdx.x < 32) {   // one TMA bulk copy per source row (clipped to the plane pitch at the right edge)
+        const int pc = kXO + x0 - 16;
+        const uint32_t row_bytes = (uint32_t)min(kBlurSP, L.pitch - pc);
+        const uint8_t *g = src + (long long)(kYO + y0 - 3) * L.pitch + pc;
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, row_bytes * rows_needed);
+        __syncwarp();
+        for (int r = threadIdx.x; r < rows_needed; r += 32) bulk_g2s(s_src + r * kBlurSP, g + (long long)r * L.pitch, row_bytes, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ys = y0 + wid * kBlurStrip;              // first output row of this warp's strip
     const int xb = x0 + 4 * lane;
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
 // ------------------------------------------------------------------------------------------------------
 constexpr int kFastThreads = 256;
 constexpr int kFastWarps = kFastThreads / 32;
-constexpr int kFastQueue = 192;               // per-warp survivor queue (u16 entries): < 64 left + up to 128 new
+constexpr int kFastQueue = 320;               // per-warp survivor queue (u16 entries): < 64 left + up to 256 new
 constexpr int kFastMaxG = 8;
 constexpr int kFastCorners = 3072;            // dense corner list of a tile; a tile with more corners falls back to a sweep
 constexpr int kFastColBits = 9;               // queue / list entry = (img row << 9) | img column  (ip <= 512, rows < 128)
@@ -367,16 +375,15 @@ __device__ __forceinline__ void fast_nms_one(const uint8_t *sc1, uint32_t *bm, i
     }
 }
 
-__global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict__ pyr, Geom G,
+__global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restrict__ pyr, Geom G,
                                                        const orbx_image_params *__restrict__ params,
-                                                       uint32_t *__restrict__ cells, int *__restrict__ cell_cnt, int img0) {
+                                                       uint32_t *__restrict__ cells, int *__restrict__ cell_cnt,
+                                                       const int *__restrict__ tile_info, int img0) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int b = blockIdx.y + img0;
-    int lvl = 0;
-    while (lvl + 1 < G.nlevels && (int)blockIdx.x >= G.lv[lvl + 1].fast_tile_base) lvl++;
-    const LevelGeom &L = G.lv[lvl];
-    const int tile = blockIdx.x - L.fast_tile_base;
-    const int ci = tile / L.fast_tiles_x, jt = tile - ci * L.fast_tiles_x;
+    const int info = __ldg(tile_info + blockIdx.x);          // level | cell row << 4 | tile column << 16
+    const LevelGeom &L = G.lv[info & 15];
+    const int ci = (info >> 4) & 0xFFF, jt = info >> 16;
     const int j0 = jt * G.fast_g, j1 = min(j0 + G.fast_g, L.n_cols);
     const int ncell = j1 - j0;
     const int wc = L.w_cell;
@@ -404,11 +411,16 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict
     const int pc0 = (kXO + tx0 - 3) & ~15;
     const int c0 = kXO + tx0 - pc0;                 // smem column of level column tx0 (>= 3)
     const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
-    {
+    __shared__ __align__(8) uint64_t s_bar;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (wid == 0) {   // one TMA bulk copy per tile row; the rest of the CTA clears the score map meanwhile
         const uint8_t *src = plane_ptr(pyr, L, b) + (long long)(kYO + ty0 - 3) * L.pitch + pc0;
-        for (int r = wid; r < Y + 6; r += kFastWarps)
-            for (int c = lane; c < nvec; c += 32)
-                *reinterpret_cast<uint4 *>(img + r * ip + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * L.pitch + 16 * c));
+        if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)((Y + 6) * nvec * 16));
+        __syncwarp();
+        for (int r = lane; r < Y + 6; r += 32) bulk_g2s(img + r * ip, src + (long long)r * L.pitch, (uint32_t)(nvec * 16), &s_bar);
+    }
+    {
         uint4 *z = reinterpret_cast<uint4 *>(sc);             // score map and bitmap are contiguous
         const int nz = (int)(fast_zero_bytes(ip, G.fast_ymax) >> 4);
         for (int i = tid; i < nz; i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
@@ -416,53 +428,66 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict
         if (tid == 0) *ncl = 0;
     }
     __syncthreads();
+    mbar_wait(&s_bar, 0);
     const orbx_image_params prm = params[b];
     const int t_ini = min(max(prm.ini_th_fast, 0), 255), t_min = min(max(prm.min_th_fast, 0), 255);
     const int w0 = c0 >> 2, w1 = (c0 + X - 1) >> 2;    // words of a row that hold tested pixels
     const int nw = w1 - w0 + 1;
     const float inv_nw = 1.0f / (float)nw;
-    const uint32_t m_first = 0x80808080u << (8 * (c0 & 3)), m_last = 0x80808080u >> (8 * (3 - ((c0 + X - 1) & 3)));
+    // the quick test walks aligned word pairs (8 pixels per lane)
+    const int p0w = w0 & ~1, nw2 = ((w1 | 1) - p0w + 1) >> 1, items2 = Y * nw2;
+    const float inv_nw2 = 1.0f / (float)nw2;
     unsigned retry = 0;                                 // cells (bit k = cell j0 + k) processed in this pass; 0 = all
     uint8_t *sc1 = sc + ip;                             // score row of tile row 0
     const int items = Y * nw;
     for (int pass = 0; pass < 2; pass++) {
         const int t = pass == 0 ? t_ini : t_min;
         const uint32_t t1x4 = (uint32_t)(min(t, 126) + 1) * 0x01010101u;
-        // ---- 1 + 2: quick reject and pair scoring, warp-local
+        // ---- 1 + 2: quick reject and pair scoring, warp-local.  One lane = 8 consecutive pixels (an aligned word pair).
         int qn = 0;
-        for (int it0 = wid * 32; it0 < items; it0 += kFastWarps * 32) {
+        for (int it0 = wid * 32; it0 < items2; it0 += kFastWarps * 32) {
             const int it = it0 + lane;
-            uint32_t m = 0;
+            uint32_t m8 = 0;                               // bit k = pixel k of the pair survives
             int row = 0, wi = 0;
-            if (it < items) {
-                row = small_div(it, inv_nw); wi = w0 + (it - row * nw);
-                const uint32_t *c = reinterpret_cast<const uint32_t *>(img + (row + 3) * ip) + wi;
-                const uint32_t v = c[0], pv = c[-1], nx = c[1];
-                const uint32_t up = *(reinterpret_cast<const uint32_t *>(img + row * ip) + wi);
-                const uint32_t dn = *(reinterpret_cast<const uint32_t *>(img + (row + 6) * ip) + wi);
-                const uint32_t lf = __byte_perm(pv, v, 0x4321), rt = __byte_perm(v, nx, 0x6543);
-                const uint32_t gv = bytes_gt(__vabsdiffu4(v, up), t1x4) | bytes_gt(__vabsdiffu4(v, dn), t1x4);
-                const uint32_t gh = bytes_gt(__vabsdiffu4(v, lf), t1x4) | bytes_gt(__vabsdiffu4(v, rt), t1x4);
-                m = gv & gh;
-                if (wi == w0) m &= m_first;                // bytes left / right of the tested columns
-                if (wi == w1) m &= m_last;
+            if (it < items2) {
+                row = small_div(it, inv_nw2); wi = p0w + 2 * (it - row * nw2);
+                const uint8_t *cr = img + (row + 3) * ip + 4 * wi;
+                const uint2 v = *reinterpret_cast<const uint2 *>(cr);
+                const uint32_t pv = *reinterpret_cast<const uint32_t *>(cr - 4), nx = *reinterpret_cast<const uint32_t *>(cr + 8);
+                const uint2 up = *reinterpret_cast<const uint2 *>(cr - 3 * ip), dn = *reinterpret_cast<const uint2 *>(cr + 3 * ip);
+                const uint32_t lf0 = __byte_perm(pv, v.x, 0x4321), rt0 = __byte_perm(v.x, v.y, 0x6543);
+                const uint32_t lf1 = __byte_perm(v.x, v.y, 0x4321), rt1 = __byte_perm(v.y, nx, 0x6543);
+                uint32_t m0 = (bytes_gt(__vabsdiffu4(v.x, up.x), t1x4) | bytes_gt(__vabsdiffu4(v.x, dn.x), t1x4)) &
+                              (bytes_gt(__vabsdiffu4(v.x, lf0), t1x4) | bytes_gt(__vabsdiffu4(v.x, rt0), t1x4));
+                uint32_t m1 = (bytes_gt(__vabsdiffu4(v.y, up.y), t1x4) | bytes_gt(__vabsdiffu4(v.y, dn.y), t1x4)) &
+                              (bytes_gt(__vabsdiffu4(v.y, lf1), t1x4) | bytes_gt(__vabsdiffu4(v.y, rt1), t1x4));
+                // gather the 0x80 flags of the 8 bytes into 8 bits
+                m8 = ((m0 >> 7) * 0x00204081u >> 21 & 0xFu) | (((m1 >> 7) * 0x00204081u >> 21 & 0xFu) << 4);
+                // pixels left / right of the tested columns
+                const int first = c0 - 4 * wi, last = c0 + X - 1 - 4 * wi;     // valid bit range [first, last]
+                if (first > 0) m8 &= 0xFFu << first;
+                if (last < 7) m8 &= 0xFFu >> (7 - last);
                 if (retry) {                               // second pass: only the cells that are retried
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
+                    for (int k = 0; k < 8; k++) {
                         const int xt = min(max(4 * wi + k - c0, 0), X - 1);
-                        if (!((retry >> small_div(xt, inv_wc)) & 1u)) m &= ~(0x80u << (8 * k));
+                        if (!((retry >> small_div(xt, inv_wc)) & 1u)) m8 &= ~(1u << k);
                     }
                 }
             }
-            // append the survivors of this warp iteration to the queue (order inside the queue is irrelevant)
-            const int ebase = ((row + 3) << kFastColBits) | (4 * wi);
+            // append the survivors to the warp queue (order inside the queue is irrelevant): exclusive prefix of the per-lane
+            // counts from ballots of the count bits
+            const int cnt = __popc(m8);
             const unsigned lm = (1u << lane) - 1;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const bool s = (m >> (8 * k + 7)) & 1u;
-                const unsigned bal = __ballot_sync(0xFFFFFFFFu, s);
-                if (s) q[qn + __popc(bal & lm)] = (unsigned short)(ebase + k);
-                qn += __popc(bal);
+            const unsigned b0 = __ballot_sync(0xFFFFFFFFu, cnt & 1), b1 = __ballot_sync(0xFFFFFFFFu, cnt & 2);
+            const unsigned b2 = __ballot_sync(0xFFFFFFFFu, cnt & 4), b3 = __ballot_sync(0xFFFFFFFFu, cnt & 8);
+            int pos = qn + __popc(b0 & lm) + 2 * __popc(b1 & lm) + 4 * __popc(b2 & lm) + 8 * __popc(b3 & lm);
+            qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+            const int ebase = ((row + 3) << kFastColBits) | (4 * wi);
+            while (m8) {
+                const int k = __ffs(m8) - 1;
+                m8 &= m8 - 1;
+                q[pos++] = (unsigned short)(ebase + k);
             }
             __syncwarp();
             while (qn >= 64) {
@@ -504,43 +529,48 @@ __global__ void __launch_bounds__(kFastThreads) k_fast(const uint8_t *__restrict
             __syncthreads();
         }
     }
-    // ---- 5: one warp per cell, rows in parallel, row-major emission from the bitmap
+    // ---- 5: one warp per cell, one lane per row: row-major emission (the order of cv::FAST) from the keep bitmap
     for (int k = wid; k < ncell; k += kFastWarps) {
         const int cx0 = c0 + k * wc, cx1 = min(cx0 + wc, c0 + X);    // smem columns of the cell
-        uint32_t *out = cells + (long long)b * G.cand_per_image + L.cand_off + (long long)(ci * L.n_cols + j0 + k) * L.cell_cap;
         int total = 0;
         if (cx1 > cx0 && has[k]) {
-            const int wa = cx0 >> 5, wb = (cx1 - 1) >> 5;
+            uint32_t *out = cells + (long long)b * G.cand_per_image + L.cand_off + (long long)(ci * L.n_cols + j0 + k) * L.cell_cap;
+            const int wa = cx0 >> 5, nwords = ((cx1 - 1) >> 5) - wa + 1;          // a cell spans at most 4 bitmap words
+            const uint32_t m_lo = 0xFFFFFFFFu << (cx0 & 31), m_hi = (cx1 & 31) ? (1u << (cx1 & 31)) - 1 : 0xFFFFFFFFu;
             for (int r0 = 0; r0 < Y; r0 += 32) {
                 const int row = r0 + lane;
+                uint32_t bits[4] = {0, 0, 0, 0};
                 int n = 0;
-                if (row < Y)
-                    for (int w = wa; w <= wb; w++) {
-                        uint32_t bits = bm[row * bw + w];
-                        if (w == wa) bits &= 0xFFFFFFFFu << (cx0 & 31);
-                        if (w == wb && (cx1 & 31)) bits &= (1u << (cx1 & 31)) - 1;
-                        n += __popc(bits);
-                    }
+                if (row < Y) {
+#pragma unroll
+                    for (int w = 0; w < 4; w++)
+                        if (w < nwords) {
+                            uint32_t v = bm[row * bw + wa + w];
+                            if (w == 0) v &= m_lo;
+                            if (w == nwords - 1) v &= m_hi;
+                            bits[w] = v; n += __popc(v);
+                        }
+                }
                 int inc = n;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
                 int pos = total + inc - n;
                 total += __shfl_sync(0xFFFFFFFFu, inc, 31);
-                if (n)
-                    for (int w = wa; w <= wb; w++) {
-                        uint32_t bits = bm[row * bw + w];
-                        if (w == wa) bits &= 0xFFFFFFFFu << (cx0 & 31);
-                        if (w == wb && (cx1 & 31)) bits &= (1u << (cx1 & 31)) - 1;
-                        while (bits) {
-                            const int bit = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            const int col = 32 * w + bit;
+                if (n) {
+                    const uint8_t *srow = sc1 + row * ip;
+                    const uint32_t ybits = (uint32_t)(ty0 + row - kFastBorder) << 12;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        uint32_t v = bits[w];
+                        while (v) {
+                            const int col = 32 * (wa + w) + __ffs(v) - 1;
+                            v &= v - 1;
                             // border-relative coordinates (src/ORBextractor.cc:784-791): level coordinate - 16
-                            if (pos < L.cell_cap)
-                                out[pos] = cand_pack(tx0 + (col - c0) - kFastBorder, ty0 + row - kFastBorder, sc1[row * ip + col]);
+                            if (pos < L.cell_cap) out[pos] = (uint32_t)(tx0 + (col - c0) - kFastBorder) | ybits | ((uint32_t)srow[col] << 24);
                             pos++;
                         }
                     }
+                }
             }
         }
         if (lane == 0) cnt_out[k] = min(total, L.cell_cap);
