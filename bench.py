@@ -290,8 +290,9 @@ def main():
         m.set_stream(stream.cuda_stream)
         train = synth_descriptors(n, 5)
         query = synth_query_from_train(train, 6)
-        per = (n + world - 1) // world
-        lo, hi = rank * per, min(n, (rank + 1) * per)
+        from openmavis_b200 import shard
+        lo, cnt = shard.row_shard(n, rank, world)        # query-sharded; train rows start distributed the same way
+        hi = lo + cnt
         d_q = torch.from_numpy(query[lo:hi]).to(dev)
         d_local_train = torch.from_numpy(train[lo:hi]).to(dev)
         d_idx = torch.empty((hi - lo, 2), dtype=torch.int32, device=dev)
@@ -299,9 +300,7 @@ def main():
 
         def knn_step():
             if world > 1:    # the one real exchange step: NCCL all-gather of the train rows over NVLink
-                parts = [torch.empty((min(n, (r + 1) * per) - r * per, 32), dtype=torch.uint8, device=dev) for r in range(world)]
-                dist.all_gather(parts, d_local_train)
-                d_t = torch.cat(parts)
+                d_t = shard.gather_train_rows(d_local_train, n, dist)
             else:
                 d_t = d_local_train
             m.knnMatch2_device(d_q.data_ptr(), hi - lo, d_t.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())

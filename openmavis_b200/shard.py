@@ -1,0 +1,57 @@
+"""Multi-GPU host logic: one process per GPU, rig frames sharded, no data-path collective for extraction; the cross-GPU
+brute-force 2-NN is query-sharded with ONE all-gather of the train descriptor rows.
+
+Works with any torch.distributed backend: NCCL over NVLink on the GPU box, gloo in the CPU test-suite (where the 2-NN
+compute callback is the oracle — the product callback is ORBmatcher.knnMatch2_device)."""
+import numpy as np
+
+
+def frame_shard(n_frames, rank, world):
+    """Contiguous block of rig frames owned by `rank` (all cameras of a rig frame stay on one GPU, so the
+    left/right 2-NN that follows extraction is local).  Returns (first, count); blocks differ by at most one frame."""
+    base, rem = divmod(int(n_frames), int(world))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def row_shard(n_rows, rank, world):
+    return frame_shard(n_rows, rank, world)
+
+
+def gather_train_rows(local_train, n_total, dist, device=None):
+    """all_gather of the train descriptor rows ([n_local, 32] uint8 torch tensor per rank, possibly ragged) -> [n_total, 32]."""
+    import torch
+    world = dist.get_world_size()
+    counts = [row_shard(n_total, r, world)[1] for r in range(world)]
+    assert local_train.shape[0] == counts[dist.get_rank()]
+    m = max(counts)
+    padded = local_train
+    if local_train.shape[0] < m:                       # all_gather needs equal shapes: pad the short shards
+        padded = torch.zeros((m, 32), dtype=torch.uint8, device=local_train.device)
+        padded[:local_train.shape[0]] = local_train
+    parts = [torch.empty((m, 32), dtype=torch.uint8, device=local_train.device) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous())
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
+def knn2_sharded(query_local, train_local, n_total, dist, knn2_fn):
+    """Brute-force 2-NN of this rank's query rows against ALL train rows.  knn2_fn(query, train) -> (idx[nq,2], dist[nq,2]) with
+    GLOBAL train indices, ordered (distance asc, trainIdx asc) like cv::BFMatcher.knnMatch (src/Frame.cc:1427)."""
+    train = gather_train_rows(train_local, n_total, dist)
+    return knn2_fn(query_local, train)
+
+
+def gather_results(idx_local, dist_local, n_total, dist):
+    """Optional gather of the sharded results to every rank (numpy in, numpy out)."""
+    import torch
+    world = dist.get_world_size()
+    counts = [row_shard(n_total, r, world)[1] for r in range(world)]
+    m = max(counts)
+    buf = torch.full((m, 4), -1, dtype=torch.int32)
+    n = idx_local.shape[0]
+    buf[:n, :2] = torch.from_numpy(np.ascontiguousarray(idx_local, np.int32))
+    buf[:n, 2:] = torch.from_numpy(np.ascontiguousarray(dist_local, np.int32))
+    parts = [torch.empty((m, 4), dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    out = torch.cat([p[:c] for p, c in zip(parts, counts)]).numpy()
+    return out[:, :2].copy(), out[:, 2:].copy()
