@@ -74,11 +74,48 @@ OCT_HD void oct_heapsort(uint64_t *a, int first, int last) {   // std::__partial
         oct_adjust_heap(a, first, 0, l - first, v);
     }
 }
+// The sequential scans below read 4 elements ahead of the comparison that decides whether they are needed: the loads do
+// not depend on each other, so one shared-memory latency covers 4 steps.  The array must be readable 3 entries beyond
+// both ends (kOctSortPad); the values read there are never used.
+constexpr int kOctSortPad = 4;
+
 OCT_HD void oct_unguarded_linear_insert(uint64_t *a, int last) {
-    uint64_t val = a[last];
+    const uint64_t val = a[last];
     int next = last - 1;
-    while (oct_lt(val, a[next])) { a[last] = a[next]; last = next; --next; }
+    for (;;) {
+        const uint64_t x0 = a[next], x1 = a[next - 1], x2 = a[next - 2], x3 = a[next - 3];
+        if (!oct_lt(val, x0)) break;
+        a[last] = x0; last = next; --next;
+        if (!oct_lt(val, x1)) break;
+        a[last] = x1; last = next; --next;
+        if (!oct_lt(val, x2)) break;
+        a[last] = x2; last = next; --next;
+        if (!oct_lt(val, x3)) break;
+        a[last] = x3; last = next; --next;
+    }
     a[last] = val;
+}
+// first f' >= f with !(a[f'] < piv)   (the caller guarantees a sentinel inside the range)
+OCT_HD int oct_scan_up(const uint64_t *a, int f, uint64_t piv) {
+    for (;;) {
+        const uint64_t x0 = a[f], x1 = a[f + 1], x2 = a[f + 2], x3 = a[f + 3];
+        if (!oct_lt(x0, piv)) return f;
+        if (!oct_lt(x1, piv)) return f + 1;
+        if (!oct_lt(x2, piv)) return f + 2;
+        if (!oct_lt(x3, piv)) return f + 3;
+        f += 4;
+    }
+}
+// first l' <= l with !(piv < a[l'])
+OCT_HD int oct_scan_down(const uint64_t *a, int l, uint64_t piv) {
+    for (;;) {
+        const uint64_t x0 = a[l], x1 = a[l - 1], x2 = a[l - 2], x3 = a[l - 3];
+        if (!oct_lt(piv, x0)) return l;
+        if (!oct_lt(piv, x1)) return l - 1;
+        if (!oct_lt(piv, x2)) return l - 2;
+        if (!oct_lt(piv, x3)) return l - 3;
+        l -= 4;
+    }
 }
 OCT_HD void oct_insertion_sort(uint64_t *a, int first, int last) {
     if (first == last) return;
@@ -119,9 +156,9 @@ OCT_HD void oct_std_sort(uint64_t *a, int n) {
             }
             int f = first + 1, l = last;   // __unguarded_partition(first+1, last, pivot=first)
             for (;;) {
-                while (oct_lt(a[f], a[first])) ++f;
-                --l;
-                while (oct_lt(a[first], a[l])) --l;
+                const uint64_t piv = a[first];      // the pivot slot is never swapped inside the loop (f > first)
+                f = oct_scan_up(a, f, piv);
+                l = oct_scan_down(a, l - 1, piv);
                 if (!(f < l)) break;
                 oct_swap(a, f, l);
                 ++f;
@@ -173,7 +210,7 @@ OCT_HD size_t oct_work_bytes(int cap) {
     b += (size_t)cap * 4 * sizeof(int) * 2;           // child_cnt, child_pos
     b += 3 * ((size_t)cap + 1) * sizeof(int);          // scans
     b += 4 * (size_t)cap * sizeof(int);                // remap, clist, cidx, order
-    b += (size_t)cap * sizeof(uint64_t);               // srt
+    b += ((size_t)cap + 2 * kOctSortPad) * sizeof(uint64_t);   // srt (+ read-ahead pads)
     b += (size_t)cap * sizeof(unsigned);               // best
     b += 16 * sizeof(int);
     return b + 64;
@@ -183,7 +220,7 @@ OCT_HD void oct_carve(OctWork &w, void *mem, int cap) {
     unsigned char *p = (unsigned char *)mem;
     p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
     w.cap = cap;
-    w.srt = (uint64_t *)p; p += (size_t)cap * sizeof(uint64_t);
+    w.srt = (uint64_t *)p + kOctSortPad; p += ((size_t)cap + 2 * kOctSortPad) * sizeof(uint64_t);
     for (int k = 0; k < 2; k++) { w.t[k].box = (OctBox *)p; p += (size_t)cap * sizeof(OctBox); }
     for (int k = 0; k < 2; k++) { w.t[k].cnt = (int *)p; p += (size_t)cap * sizeof(int); }
     w.child_cnt = (int *)p; p += (size_t)cap * 4 * sizeof(int);

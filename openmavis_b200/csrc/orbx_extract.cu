@@ -164,6 +164,9 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     ex->oct_list_cap = max_list;
     ex->oct_smem = oct_work_bytes(max_list);
     if (ex->oct_smem > 200 * 1024) return fail(ORBX_ERR_INVALID, "nfeatures too large for the quadtree workspace");
+    // the rest of a 56 KB budget (4 CTAs per SM) holds the per-candidate node labels; larger levels use the global array
+    G.oct_scap = ex->oct_smem < 54 * 1024 ? (int)((56 * 1024 - ex->oct_smem) / 2) & ~63 : 0;
+    ex->oct_smem += (size_t)G.oct_scap * 2;
     int tiles = 0;
     for (int l = 0; l < nl; l++) {
         ex->blur_tiles.base[l] = tiles;

@@ -622,7 +622,9 @@ __global__ void __launch_bounds__(512) k_octree(Geom G, const int *__restrict__ 
     __syncthreads();
     const uint32_t *cs = cells + (long long)b * G.cand_per_image + L.cand_off;
     uint32_t *ln = lin + (long long)b * G.cand_per_image + L.cand_off;
-    unsigned short *nd = node + (long long)b * G.cand_per_image + L.cand_off;
+    // node labels are rewritten by every pass: keep them in shared memory when the level's candidates fit
+    unsigned short *nd = n <= G.oct_scap ? reinterpret_cast<unsigned short *>(oct_smem + oct_work_bytes(list_cap))
+                                         : node + (long long)b * G.cand_per_image + L.cand_off;
     const int lane = cx.tid & 31, wid = cx.tid >> 5, nw = cx.nt >> 5;
     for (int c = wid; c < ncell; c += nw) {
         const int k = cc[c], o = co[c];
