@@ -26,8 +26,9 @@
 namespace orbx {
 
 // ---- exact libstdc++ std::sort (introsort, threshold 16) on packed entries --------------------------------
-// entry = key << 16 | payload; key = node size << 13 | UL.x  (compareNodes, :482-494: size, then UL.x)
-OCT_HD bool oct_lt(uint64_t a, uint64_t b) { return (a >> 16) < (b >> 16); }
+// entry = key << 32 | payload; key = node size << 13 | UL.x  (compareNodes, :482-494: size, then UL.x).  The key is the
+// high word, so a comparison is one 32-bit compare of the upper registers.
+OCT_HD bool oct_lt(uint64_t a, uint64_t b) { return (uint32_t)(a >> 32) < (uint32_t)(b >> 32); }
 OCT_HD void oct_swap(uint64_t *a, int i, int j) { uint64_t t = a[i]; a[i] = a[j]; a[j] = t; }
 
 OCT_HD void oct_push_heap(uint64_t *a, int first, int hole, int top, uint64_t value) {
@@ -370,13 +371,19 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
             for (int c = cx.tid; c < m; c += cx.nt) {
                 const int p = w.clist[c];
                 w.cidx[p] = c;
-                w.srt[c] = ((uint64_t)(((uint32_t)T.cnt[p] << 13) | (uint32_t)T.box[p].x0) << 16) | (uint64_t)c;
+                w.srt[c] = ((uint64_t)(((uint32_t)T.cnt[p] << 13) | (uint32_t)T.box[p].x0) << 32) | (uint64_t)c;
             }
             cx.sync();
-            for (int i = cx.tid; i < n; i += cx.nt) {
-                const int p = node[i];
-                const int c = w.cidx[p];
-                if (c >= 0) cx.atomic_add(&w.child_cnt[4 * c + oct_quadrant(T.box[p], cand[i])], 1);
+            // thread 0 runs the sequential std::sort emulation; the other warps build the child histogram meanwhile
+            {
+                const bool split = cx.nt > 32;
+                const int wt = split ? cx.nt - 32 : cx.nt, wi = split ? cx.tid - 32 : cx.tid;
+                if (wi >= 0)
+                    for (int i = wi; i < n; i += wt) {
+                        const int p = node[i];
+                        const int c = w.cidx[p];
+                        if (c >= 0) cx.atomic_add(&w.child_cnt[4 * c + oct_quadrant(T.box[p], cand[i])], 1);
+                    }
             }
             if (cx.tid == 0) oct_std_sort(w.srt, m);
             cx.sync();

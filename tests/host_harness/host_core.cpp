@@ -22,7 +22,7 @@ extern "C" {
 void hc_std_sort(const int *sizes, const int *ulx, int n, int *perm) {
     std::vector<uint64_t> buf(n + 2 * orbx::kOctSortPad, 0);   // the sort reads (never uses) a few entries beyond both ends
     uint64_t *a = buf.data() + orbx::kOctSortPad;
-    for (int i = 0; i < n; i++) a[i] = ((uint64_t)(((uint32_t)sizes[i] << 13) | (uint32_t)ulx[i]) << 16) | (uint64_t)i;
+    for (int i = 0; i < n; i++) a[i] = ((uint64_t)(((uint32_t)sizes[i] << 13) | (uint32_t)ulx[i]) << 32) | (uint64_t)i;
     orbx::oct_std_sort(a, n);
     for (int i = 0; i < n; i++) perm[i] = (int)(a[i] & 0xFFFF);
 }
