@@ -408,15 +408,15 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
     const int pc0 = (kXO + tx0 - 3) & ~15;
     const int c0 = kXO + tx0 - pc0;                 // smem column of level column tx0 (>= 3)
     const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
-    __shared__ __align__(8) uint64_t s_bar;
-    if (tid == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (wid == 0) {   // one TMA bulk copy per tile row; the rest of the CTA clears the score map meanwhile
-        const uint8_t *src = plane_ptr(pyr, L, b) + (long long)(kYO + ty0 - 3) * L.pitch + pc0;
-        if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)((Y + 6) * nvec * 16));
-        __syncwarp();
-        for (int r = lane; r < Y + 6; r += 32) bulk_g2s(img + r * ip, src + (long long)r * L.pitch, (uint32_t)(nvec * 16), &s_bar);
+    // 16-byte cp.async (LDGSTS) copies, in flight while the CTA clears the score map.  (Measured: one TMA bulk copy per
+    // tile row is slower here — ~190 small requests per tile time saturate the SM's TMA unit.)
+    if (lane < nvec) {
+        const uint8_t *src = plane_ptr(pyr, L, b) + (long long)(kYO + ty0 - 3) * L.pitch + pc0 + 16 * lane;
+        const uint32_t dst = smem_u32(img) + 16 * lane;
+        for (int r = wid; r < Y + 6; r += kFastWarps)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * ip), "l"(src + (long long)r * L.pitch) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     {
         uint4 *z = reinterpret_cast<uint4 *>(sc);             // score map and bitmap are contiguous
         const int nz = (int)(fast_zero_bytes(ip, G.fast_ymax) >> 4);
@@ -424,8 +424,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
         if (tid < kFastMaxG) has[tid] = 0;
         if (tid == 0) *ncl = 0;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    mbar_wait(&s_bar, 0);
     const orbx_image_params prm = params[b];
     const int t_ini = min(max(prm.ini_th_fast, 0), 255), t_min = min(max(prm.min_th_fast, 0), 255);
     const int w0 = c0 >> 2, w1 = (c0 + X - 1) >> 2;    // words of a row that hold tested pixels
