@@ -93,17 +93,11 @@ __host__ __device__ inline size_t resize_smem_bytes(int src_rows, int src_pitch)
     return (size_t)src_rows * src_pitch + (size_t)src_rows * kRszTW * 4 + kRszTH * sizeof(int4);
 }
 
-__device__ __forceinline__ void resize_store4(uint8_t *drow, int x, uint32_t out, int nvalid, bool x_edge, int w) {
-    if (nvalid == 4) *reinterpret_cast<uint32_t *>(drow + x) = out;
-    else for (int k = 0; k < nvalid; k++) drow[x + k] = (uint8_t)(out >> (8 * k));
-    if (x_edge) {   // left / right frame columns mirrored from interior columns 1..19 and w-20..w-2
-        for (int k = 0; k < nvalid; k++) {
-            const int xx = x + k;
-            const uint8_t pv = (uint8_t)(out >> (8 * k));
-            if (xx >= 1 && xx <= kEdge) drow[-xx] = pv;
-            if (xx <= w - 2 && xx >= w - 1 - kEdge) drow[2 * (w - 1) - xx] = pv;
-        }
-    }
+// REFLECT_101 image of interior row y in the top / bottom frame, or INT_MIN (levels are at least 68 rows high: at most one)
+__device__ __forceinline__ int resize_row_mirror(int y, int h) {
+    if (y >= 1 && y <= kEdge) return -y;
+    if (y <= h - 2 && y >= h - 1 - kEdge) return 2 * (h - 1) - y;
+    return INT_MIN;
 }
 
 // grid = (tiles_x, tiles_y, images)
@@ -151,28 +145,55 @@ __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ py
     __syncthreads();
     // phase V: thread = 4 adjacent output columns, rows strided by 16:
     //   dst = (((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2, with (b * h) >> 16 == umulhi(b << 16, h)
-    const int c4 = 4 * (tid & 15);
-    if (c4 >= ow) return;
-    const int x = ox0 + c4;
-    const int nvalid = min(4, D.w - x);
-    const bool x_edge = (x <= kEdge) || (x + 3 >= D.w - 1 - kEdge);
+    // The staged source is dead now: its space keeps the output tile for the frame pass below.
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(s_src);     // [kRszTH][kRszTW / 4] words
+    const bool y_band = oy0 <= kEdge || oy0 + oh - 1 >= D.h - 1 - kEdge;       // tile touches rows mirrored into the frame
+    const bool x_band = ox0 <= kEdge || ox0 + ow - 1 >= D.w - 1 - kEdge;
     uint8_t *dplane = plane_ptr(pyr, D, b) + kXO;
-    for (int r = tid >> 4; r < oh; r += kRszThreads / 16) {
-        const int4 t = s_ty[r];
-        const uint4 h0 = *reinterpret_cast<const uint4 *>(s_h + t.x + c4);
-        const uint4 h1 = *reinterpret_cast<const uint4 *>(s_h + t.y + c4);
-        const uint32_t p0 = (__umulhi((uint32_t)t.z, h0.x) + __umulhi((uint32_t)t.w, h1.x) + 2u) >> 2;
-        const uint32_t p1 = (__umulhi((uint32_t)t.z, h0.y) + __umulhi((uint32_t)t.w, h1.y) + 2u) >> 2;
-        const uint32_t p2 = (__umulhi((uint32_t)t.z, h0.z) + __umulhi((uint32_t)t.w, h1.z) + 2u) >> 2;
-        const uint32_t p3 = (__umulhi((uint32_t)t.z, h0.w) + __umulhi((uint32_t)t.w, h1.w) + 2u) >> 2;
-        const uint32_t out = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    const int c4 = 4 * (tid & 15);
+    if (c4 < ow) {
+        const int x = ox0 + c4;
+        const int nvalid = min(4, D.w - x);
+        uint8_t *drow = dplane + (long long)(kYO + oy0 + (tid >> 4)) * D.pitch + x;
+        const long long rstep = (long long)(kRszThreads / 16) * D.pitch;
+        for (int r = tid >> 4; r < oh; r += kRszThreads / 16, drow += rstep) {
+            const int4 t = s_ty[r];
+            const uint4 h0 = *reinterpret_cast<const uint4 *>(s_h + t.x + c4);
+            const uint4 h1 = *reinterpret_cast<const uint4 *>(s_h + t.y + c4);
+            const uint32_t p0 = (__umulhi((uint32_t)t.z, h0.x) + __umulhi((uint32_t)t.w, h1.x) + 2u) >> 2;
+            const uint32_t p1 = (__umulhi((uint32_t)t.z, h0.y) + __umulhi((uint32_t)t.w, h1.y) + 2u) >> 2;
+            const uint32_t p2 = (__umulhi((uint32_t)t.z, h0.z) + __umulhi((uint32_t)t.w, h1.z) + 2u) >> 2;
+            const uint32_t p3 = (__umulhi((uint32_t)t.z, h0.w) + __umulhi((uint32_t)t.w, h1.w) + 2u) >> 2;
+            const uint32_t out = __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
+            if (nvalid == 4) *reinterpret_cast<uint32_t *>(drow) = out;
+            else for (int k = 0; k < nvalid; k++) drow[k] = (uint8_t)(out >> (8 * k));
+            if (x_band) s_out[r * (kRszTW / 4) + (c4 >> 2)] = out;
+            if (y_band) {   // this row's image in the top / bottom frame
+                const int y = oy0 + r, ym = resize_row_mirror(y, D.h);
+                if (ym != INT_MIN) {
+                    uint8_t *mrow = dplane + (long long)(kYO + ym) * D.pitch + x;
+                    if (nvalid == 4) *reinterpret_cast<uint32_t *>(mrow) = out;
+                    else for (int k = 0; k < nvalid; k++) mrow[k] = (uint8_t)(out >> (8 * k));
+                }
+            }
+        }
+    }
+    if (!x_band) return;
+    // frame pass (tiles at the left / right edge only): interior columns 1..19 -> -1..-19, w-2..w-20 -> w..w+18, for every row
+    // of the tile and its own image in the top / bottom frame
+    __syncthreads();
+    const uint8_t *ob = reinterpret_cast<const uint8_t *>(s_out);
+    for (int i = tid; i < oh * 2 * kEdge; i += kRszThreads) {
+        const int r = i / (2 * kEdge), j = i - r * (2 * kEdge);
+        const int side = j >= kEdge, k = j - side * kEdge + 1;          // k = 1..19
+        const int xx = side ? D.w - 1 - k : k;                          // mirrored interior column
+        if (xx < ox0 || xx >= ox0 + ow) continue;
+        const uint8_t pv = ob[r * kRszTW + (xx - ox0)];
+        const int dx = side ? D.w - 1 + k : -k;
         const int y = oy0 + r;
-        resize_store4(dplane + (long long)(kYO + y) * D.pitch, x, out, nvalid, x_edge, D.w);
-        // REFLECT_101 image of this row in the top / bottom frame (levels are at least 68 rows high: at most one)
-        int ym = INT_MIN;
-        if (y >= 1 && y <= kEdge) ym = -y;
-        else if (y <= D.h - 2 && y >= D.h - 1 - kEdge) ym = 2 * (D.h - 1) - y;
-        if (ym != INT_MIN) resize_store4(dplane + (long long)(kYO + ym) * D.pitch, x, out, nvalid, x_edge, D.w);
+        dplane[(long long)(kYO + y) * D.pitch + dx] = pv;
+        const int ym = resize_row_mirror(y, D.h);
+        if (ym != INT_MIN) dplane[(long long)(kYO + ym) * D.pitch + dx] = pv;
     }
 }
 
