@@ -202,3 +202,30 @@ def test_errors():
         rig.extract([synth_image(752, 480, 1)], ob.make_params(1, 5000, 20, 7))        # nfeatures > max_nfeatures
     with pytest.raises(ob.OrbxError):
         rig.extract([synth_image(640, 480, 1)], ob.make_params(1, 1000, 20, 7))        # wrong geometry
+
+
+def test_chunked_pipeline_equals_oracle_and_single_chunk():
+    """A batch larger than one chunk runs as overlapping chunks on several streams (host copies in / out included): every image
+    must still equal the oracle, whatever chunk it fell into, for host buffers, device buffers and profiling (serial) mode."""
+    _need_gpu()
+    import torch
+    n = 37                                                   # not a multiple of the chunk size: 16 + 16 + 5 host-side
+    base = [synth_image(512, 384, 5200 + c) for c in range(5)]
+    imgs = np.stack([np.roll(base[i % 5], (3 * i, 7 * i), axis=(0, 1)) for i in range(n)])
+    laps = [(0, 0), (0, 512), (100, 300)]
+    p = ob.make_params(n, 600, 20, 7, [laps[i % 3] for i in range(n)])
+    p['nfeatures'][::4] = 450                                # per-image feature targets
+    rig = ob.RigExtractor(512, 384, n, 600)
+    host = [(m, k.copy(), d.copy()) for m, k, d in rig.extract(list(imgs), p)]
+    for i in (0, 15, 16, 31, 32, 36):                        # chunk borders
+        E = O.OracleExtractor(int(p['nfeatures'][i]), 1.2, 8, 20, 7)
+        m, k, d = E(imgs[i], (int(p['lap0'][i]), int(p['lap1'][i])))
+        assert host[i][0] == m and np.array_equal(host[i][1], k) and np.array_equal(host[i][2], d), i
+    t = torch.from_numpy(imgs).cuda()
+    for prof in (False, True):
+        rig.set_profiling(prof)
+        rig.extract_device(t.data_ptr(), n, p)
+        dev = rig.fetch(n)
+        for (m0, k0, d0), (m1, k1, d1) in zip(host, dev):
+            assert m0 == m1 and np.array_equal(k0, k1) and np.array_equal(d0, d1)
+    assert sum(rig.stage_ms().values()) > 0
