@@ -414,9 +414,15 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[5], sA));
     if (sB != sA) ORBX_CUDA(cudaStreamWaitEvent(sA, ex->ev_blur[lane], 0));
-    k_orient_desc<<<dim3((G.kp_per_image * 32 + 255) / 256, cnt), 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp,
-                                                                                ex->d_lvl_n, ex->d_slot, ex->d_lvl_angle, ex->d_out_kp,
-                                                                                ex->d_out_desc, i0);
+    {
+        const dim3 grid((G.kp_per_image * 32 + 255) / 256, cnt);
+        if (G.fma_mode)
+            k_orient_desc<true><<<grid, 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,
+                                                      ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, i0);
+        else
+            k_orient_desc<false><<<grid, 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,
+                                                       ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, i0);
+    }
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[6], sA));
     ex->last_launches += launches;

@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
         if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, row_bytes * rows_needed);
         __syncwarp();
         for (int r = threadIdx.x; r < rows_needed; r += 32) bulk_g2s(s_src + r * kBlurSP, g + (long long)r * L.pitch, row_bytes, &s_bar);
+        mbar_wait(&s_bar, 0);   // only the issuing warp polls the mbarrier; the others park on the hardware barrier below
     }
-    mbar_wait(&s_bar, 0);
+    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ys = y0 + wid * kBlurStrip;              // first output row of this warp's strip
     const int xb = x0 + 4 * lane;
@@ -429,6 +430,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
     const int pc0 = (kXO + tx0 - 3) & ~15;
     const int c0 = kXO + tx0 - pc0;                 // smem column of level column tx0 (>= 3)
     const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
+    __shared__ int s_qn[kFastWarps];                      // fill level of each warp's survivor queue
+    int *qcnt = &s_qn[wid];
     // 16-byte cp.async (LDGSTS) copies, in flight while the CTA clears the score map.  (Measured: one TMA bulk copy per
     // tile row is slower here — ~190 small requests per tile time saturate the SM's TMA unit.)
     if (lane < nvec) {
@@ -444,6 +447,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
         for (int i = tid; i < nz; i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
         if (tid < kFastMaxG) has[tid] = 0;
         if (tid == 0) *ncl = 0;
+        if (lane == 0) s_qn[wid] = 0;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -462,7 +466,6 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
         const int t = pass == 0 ? t_ini : t_min;
         const uint32_t t1x4 = (uint32_t)(min(t, 126) + 1) * 0x01010101u;
         // ---- 1 + 2: quick reject and pair scoring, warp-local.  One lane = 8 consecutive pixels (an aligned word pair).
-        int qn = 0;
         for (int it0 = wid * 32; it0 < items2; it0 += kFastWarps * 32) {
             const int it = it0 + lane;
             uint32_t m8 = 0;                               // bit k = pixel k of the pair survives
@@ -493,14 +496,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
                     }
                 }
             }
-            // append the survivors to the warp queue (order inside the queue is irrelevant): exclusive prefix of the per-lane
-            // counts from ballots of the count bits
+            // append the survivors to the warp queue (order inside the queue is irrelevant).  Each lane reserves its slots with one
+            // shared-memory atomic on the warp's counter: the kernel is issue-bound, so one ATOMS (serialised in the LSU, not in the
+            // issue stage) is cheaper than a ballot/popc prefix over the lane counts.
             const int cnt = __popc(m8);
-            const unsigned lm = (1u << lane) - 1;
-            const unsigned b0 = __ballot_sync(0xFFFFFFFFu, cnt & 1), b1 = __ballot_sync(0xFFFFFFFFu, cnt & 2);
-            const unsigned b2 = __ballot_sync(0xFFFFFFFFu, cnt & 4), b3 = __ballot_sync(0xFFFFFFFFu, cnt & 8);
-            int pos = qn + __popc(b0 & lm) + 2 * __popc(b1 & lm) + 4 * __popc(b2 & lm) + 8 * __popc(b3 & lm);
-            qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+            int pos = 0;
+            if (cnt) pos = atomicAdd(qcnt, cnt);
             const int ebase = ((row + 3) << kFastColBits) | (4 * wi);
             while (m8) {
                 const int k = __ffs(m8) - 1;
@@ -508,15 +509,25 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
                 q[pos++] = (unsigned short)(ebase + k);
             }
             __syncwarp();
-            while (qn >= 64) {
-                qn -= 64;
-                fast_score_pair(img, sc1, ip, q[qn + lane], q[qn + 32 + lane], true, true, t, cl, ncl, lane);
+            int qn = *reinterpret_cast<volatile int *>(qcnt);
+            if (qn >= 64) {
+                do {
+                    qn -= 64;
+                    fast_score_pair(img, sc1, ip, q[qn + lane], q[qn + 32 + lane], true, true, t, cl, ncl, lane);
+                } while (qn >= 64);
+                __syncwarp();
+                if (lane == 0) *qcnt = qn;
                 __syncwarp();
             }
         }
-        if (qn > 0) {
-            const bool ok0 = lane < qn, ok1 = lane + 32 < qn;
-            fast_score_pair(img, sc1, ip, q[ok0 ? lane : 0], q[ok1 ? lane + 32 : 0], ok0, ok1, t, cl, ncl, lane);
+        {
+            const int qn = *reinterpret_cast<volatile int *>(qcnt);
+            if (qn > 0) {
+                const bool ok0 = lane < qn, ok1 = lane + 32 < qn;
+                fast_score_pair(img, sc1, ip, q[ok0 ? lane : 0], q[ok1 ? lane + 32 : 0], ok0, ok1, t, cl, ncl, lane);
+            }
+            __syncwarp();
+            if (lane == 0) *qcnt = 0;
         }
         __syncthreads();
         // ---- 3: strict 3x3 maximum inside the cell, over the dense corner list (or a sweep of the score map if it overflowed)
@@ -722,6 +733,7 @@ __global__ void __launch_bounds__(256) k_slots(Geom G, const orbx_image_params *
 // Orientation: lane = column u of the 31-wide patch, loop over the 31 rows; int32 moments reduced with
 // shuffles (order-independent, exact).  Descriptor: lane = output byte, 16 rotated samples per lane.
 // ------------------------------------------------------------------------------------------------------
+template <bool kFma>
 __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, Geom G,
                                                      const signed char *__restrict__ pattern, const uint32_t *__restrict__ lvl_kp,
                                                      const int *__restrict__ lvl_n, const int *__restrict__ slot,
@@ -775,7 +787,7 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
         for (int e = 0; e < 2; e++) {
             const float px = (float)(signed char)(pw[k] >> (16 * e)), py = (float)(signed char)(pw[k] >> (16 * e + 8));
             float fy, fx;
-            if (G.fma_mode) { fy = __fmaf_rn(px, sn, __fmul_rn(py, cs)); fx = __fmaf_rn(px, cs, -__fmul_rn(py, sn)); }
+            if (kFma) { fy = __fmaf_rn(px, sn, __fmul_rn(py, cs)); fx = __fmaf_rn(px, cs, -__fmul_rn(py, sn)); }
             else { fy = __fadd_rn(__fmul_rn(px, sn), __fmul_rn(py, cs)); fx = __fsub_rn(__fmul_rn(px, cs), __fmul_rn(py, sn)); }
             tv[e] = __ldg(cb + (__float2int_rn(fy) * pitch + __float2int_rn(fx)));
         }
