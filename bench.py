@@ -275,8 +275,14 @@ def main():
            'octree': None, 'slots': None, 'orient_desc': None}
     hbm_dom = dom if alg[dom] else max(('pyramid', 'blur', 'fast'), key=lambda k: kernels[k])
     achieved = alg[hbm_dom] / (kernels[hbm_dom] * 1e-3) / 1e9
+    traffic = None          # dram bytes of the same stage from the committed ncu --set full capture (profiles/ncu_traffic.json)
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        traffic = tj['bytes'][hbm_dom] * n_img / tj['images']
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'kernel': hbm_dom, 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_kind,
+                'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'algorithmic_bytes': alg[hbm_dom], 'peak_source': peak_kind,
                 'stage_ms': stage, 'dominant_stage': dom,
                 'pipeline_frac': ALG_BYTES_PER_PX['total'] * px / (stage['total'] * 1e-3) / 1e9 / peaks['hbm_gbs'],
                 'per_kernel_frac': {k: (alg[k] / (kernels[k] * 1e-3) / 1e9 / peaks['hbm_gbs']) for k in ('pyramid', 'blur', 'fast')}}
