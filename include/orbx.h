@@ -118,6 +118,17 @@ int orbx_extract_device_results(orbx_extractor *ex, const orbx_kp **d_kps, const
 int orbx_extractor_pyramid_level(orbx_extractor *ex, int image, int level, int with_border, uint8_t *dst,
                                  int dst_stride);
 
+/* Frame::ComputeStereoMatches (src/Frame.cc:1057-1219) for a rectified pair whose two images were extracted by the LAST call
+ * of this handle (plane indices img_left / img_right): row-band Hamming matching (TH_HIGH, octave +-1, disparity range from
+ * mb / mbf), 11x11 SAD refinement on the device-resident pyramid levels, parabola sub-pixel fit, depth, median-based outlier
+ * removal.  u_right[i] / depth[i] (i < n_kp[img_left], HOST, capacity cap >= orbx_extractor_capacity()) = mvuRight / mvDepth,
+ * -1 where there is no match; *n_matches = number of keypoints that keep a depth.  mb = baseline, mbf = baseline * fx. */
+int orbx_compute_stereo_matches(orbx_extractor *ex, int img_left, int img_right, float mb, float mbf, float *u_right,
+                                float *depth, int cap, int *n_matches);
+/* Same with the two images held by two handles of identical geometry (mpORBextractorLeft / mpORBextractorRight). */
+int orbx_compute_stereo_matches2(orbx_extractor *ex_left, int img_left, orbx_extractor *ex_right, int img_right, float mb, float mbf,
+                                 float *u_right, float *depth, int cap, int *n_matches);
+
 /* Stage intermediates of the last call, for stage-by-stage parity tests:
  * blurred level (w x h), FAST candidates in vToDistributeKeys order (border-relative coordinates,
  * src/ORBextractor.cc:784-791), per-level keypoints after DistributeOctTree + IC_Angle (level coordinates). */
@@ -202,6 +213,12 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
                               const float *view_cos, const float *depth, const uint8_t *bad, const uint8_t *has_obs,
                               const uint8_t *mp_desc, float th, int far_points, float th_far_points, float nnratio,
                               int *assigned, int *nmatches);
+
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483), batched over map points: group g = descriptor rows
+ * [ptr[g], ptr[g+1]) of desc (the observations of one map point, in the order the reference collects them).
+ * best[g] = index inside the group of the descriptor with the least median Hamming distance to the rest (first minimum,
+ * median = sorted row [0.5 * (N - 1)]), -1 for an empty group.  HOST pointers. */
+int orbx_distinctive_descriptors(orbx_matcher *m, const uint8_t *desc, const int *ptr, int ngroups, int *best);
 
 /* Launch count / device time of the matcher's last call (CUDA events on its stream). */
 int orbx_matcher_last_ms(orbx_matcher *m, float *ms);

@@ -162,6 +162,14 @@ class RigExtractor:
         _check(self.L.orbx_extract_device_results(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return a.value, b.value, c.value, d.value
 
+    def compute_stereo_matches(self, img_left, img_right, mb, mbf, right=None):
+        """Frame::ComputeStereoMatches (src/Frame.cc:1057-1219) on two images of the last call(s) -> (n, mvuRight, mvDepth).
+        right: the RigExtractor that holds the right image (default: this one)."""
+        u = np.zeros(self.cap, np.float32); d = np.zeros(self.cap, np.float32); n = C.c_int(0)
+        _check(self.L.orbx_compute_stereo_matches2(self.h, int(img_left), (right or self).h, int(img_right), C.c_float(mb),
+                                                   C.c_float(mbf), _p(u), _p(d), self.cap, C.byref(n)))
+        return n.value, u, d
+
     def pyramid_level(self, image, level, with_border=False):
         w, h = int(self.level_w[level]), int(self.level_h[level])
         if with_border:
@@ -346,6 +354,14 @@ class ORBmatcher:
                                                     C.byref(nm)))
         pairs = [(int(i), int(m12[i])) for i in np.nonzero(m12 >= 0)[0]]
         return nm.value, pairs, m12
+
+    def ComputeDistinctiveDescriptors(self, desc, ptr):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483) for many map points: desc[total,32], ptr[ngroups+1]
+        -> best index inside each group (-1 for an empty group)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); ptr = np.ascontiguousarray(ptr, np.int32)
+        best = np.full(ptr.size - 1, -1, np.int32)
+        _check(self.L.orbx_distinctive_descriptors(self.h, _p(desc), _p(ptr), ptr.size - 1, _p(best)))
+        return best
 
     def grid_candidates(self, kps, bounds, qx, qy, qr, min_level, max_level, cand_cap=None):
         kps = np.ascontiguousarray(kps, KP_DTYPE)

@@ -57,6 +57,14 @@ struct Geom {
     LevelGeom lv[kMaxLevels];
 };
 
+#ifdef __CUDACC__
+__device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
+    // ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2577-2591) == popcount(a ^ b) over 8 words
+    return (__popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z)) +
+           (__popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y)) + (__popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w));
+}
+#endif
+
 // Thread-local error string behind orbx_last_error().
 void set_error(const std::string &msg);
 int fail(orbx_status st, const std::string &msg);

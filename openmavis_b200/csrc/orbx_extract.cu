@@ -10,6 +10,7 @@
 
 #include "../../include/orbx_pattern.h"
 #include "orbx_extract_kernels.cuh"
+#include "orbx_stereo_kernels.cuh"
 
 namespace orbx {
 
@@ -90,6 +91,8 @@ struct orbx_extractor {
     float *d_lvl_angle = nullptr;
     orbx_kp *d_out_kp = nullptr;
     orbx_image_params *d_params = nullptr;
+    float *d_st_uright = nullptr, *d_st_depth = nullptr;   // ComputeStereoMatches outputs (allocated on first use)
+    int *d_st_sad = nullptr, *d_st_kept = nullptr;
     // pinned staging
     uint8_t *h_in = nullptr;
     orbx_image_params *h_params = nullptr;
@@ -205,6 +208,7 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     cudaFree(ex->d_cell_cnt); cudaFree(ex->d_cell_off); cudaFree(ex->d_lin_n); cudaFree(ex->d_lvl_n); cudaFree(ex->d_slot);
     cudaFree(ex->d_n_kp); cudaFree(ex->d_n_mono); cudaFree(ex->d_nfeat); cudaFree(ex->d_lvl_angle); cudaFree(ex->d_out_kp);
     cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles);
+    cudaFree(ex->d_st_uright); cudaFree(ex->d_st_depth); cudaFree(ex->d_st_sad); cudaFree(ex->d_st_kept);
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_params) cudaFreeHost(ex->h_params);
     if (ex->h_nfeat) cudaFreeHost(ex->h_nfeat);
@@ -685,6 +689,54 @@ int orbx_debug_level_keypoints(orbx_extractor *ex, int image, int level, orbx_kp
         }
     }
     return ORBX_OK;
+}
+
+int orbx_compute_stereo_matches2(orbx_extractor *exl, int img_left, orbx_extractor *exr, int img_right, float mb, float mbf,
+                                 float *u_right, float *depth, int cap, int *n_matches) {
+    if (!exl || !exr || !u_right || !depth) return fail(ORBX_ERR_INVALID, "NULL argument");
+    if (img_left < 0 || img_right < 0 || img_left >= exl->last_n || img_right >= exr->last_n)
+        return fail(ORBX_ERR_INVALID, "image index outside the last batch");
+    if (exl->device != exr->device || exl->width != exr->width || exl->height != exr->height || exl->nlevels != exr->nlevels ||
+        exl->scale_factor != exr->scale_factor)
+        return fail(ORBX_ERR_INVALID, "left and right extractor differ in device, image size or pyramid shape");
+    if (cap < exl->G.out_cap) return fail(ORBX_ERR_CAPACITY, "cap smaller than orbx_extractor_capacity()");
+    if (!(mb > 0.0f) || exl->G.out_cap >= 65535 || exr->G.out_cap >= 65535) return fail(ORBX_ERR_INVALID, "bad baseline / too many keypoints");
+    ORBX_CUDA(cudaSetDevice(exl->device));
+    if (exr != exl) ORBX_CUDA(cudaStreamSynchronize(exr->stream));   // the right extraction must be complete
+    const size_t oc = (size_t)exl->G.out_cap, ocr = (size_t)exr->G.out_cap;
+    if (!exl->d_st_uright) {
+        ORBX_CUDA(dalloc(&exl->d_st_uright, oc)); ORBX_CUDA(dalloc(&exl->d_st_depth, oc));
+        ORBX_CUDA(dalloc(&exl->d_st_sad, oc)); ORBX_CUDA(dalloc(&exl->d_st_kept, (size_t)1));
+    }
+    StereoArgs A;
+    A.kpL = exl->d_out_kp + img_left * oc; A.kpR = exr->d_out_kp + img_right * ocr;
+    A.descL = reinterpret_cast<const uint4 *>(exl->d_out_desc + img_left * oc * 32);
+    A.descR = reinterpret_cast<const uint4 *>(exr->d_out_desc + img_right * ocr * 32);
+    A.nL = exl->d_n_kp + img_left; A.nR = exr->d_n_kp + img_right;
+    A.pyrL = exl->d_pyr; A.pyrR = exr->d_pyr;
+    A.imgL = img_left; A.imgR = img_right;
+    for (int l = 0; l < kMaxLevels; l++) A.inv_sf[l] = l < exl->nlevels ? exl->inv_sf[l] : 0.f;
+    A.maxD = mbf / mb; A.mbf = mbf;                                  // src/Frame.cc:1086-1088
+    A.uRight = exl->d_st_uright; A.depth = exl->d_st_depth; A.sad = exl->d_st_sad;
+    cudaStream_t s = exl->stream;
+    // the plane geometry of both arenas is the same only if both handles were created for the same max_images
+    Geom G = exl->G;
+    if (exr != exl && exr->max_images != exl->max_images) return fail(ORBX_ERR_INVALID, "left and right extractor differ in max_images");
+    k_stereo_match<<<(unsigned)((oc * 32 + 255) / 256), 256, 0, s>>>(G, A);
+    k_stereo_filter<<<1, 1024, 0, s>>>(A, exl->d_st_kept);
+    ORBX_CUDA(cudaGetLastError());
+    ORBX_CUDA(cudaMemcpyAsync(u_right, exl->d_st_uright, oc * sizeof(float), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaMemcpyAsync(depth, exl->d_st_depth, oc * sizeof(float), cudaMemcpyDeviceToHost, s));
+    int kept = 0;
+    ORBX_CUDA(cudaMemcpyAsync(&kept, exl->d_st_kept, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ORBX_CUDA(cudaStreamSynchronize(s));
+    if (n_matches) *n_matches = kept;
+    return ORBX_OK;
+}
+
+int orbx_compute_stereo_matches(orbx_extractor *ex, int img_left, int img_right, float mb, float mbf, float *u_right, float *depth,
+                                int cap, int *n_matches) {
+    return orbx_compute_stereo_matches2(ex, img_left, ex, img_right, mb, mbf, u_right, depth, cap, n_matches);
 }
 
 int orbx_extractor_stage_ms(orbx_extractor *ex, float *ms) {

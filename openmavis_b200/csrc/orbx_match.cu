@@ -468,6 +468,31 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     return ORBX_OK;
 }
 
+int orbx_distinctive_descriptors(orbx_matcher *m, const uint8_t *desc, const int *ptr, int ngroups, int *best) {
+    if (!m || !ptr || !best || ngroups < 0) return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    if (ngroups == 0) return ORBX_OK;
+    const int total = ptr[ngroups];
+    if (total < 0 || (total && !desc)) return fail(ORBX_ERR_INVALID, "bad group table");
+    for (int g = 0; g < ngroups; g++)
+        if (ptr[g + 1] < ptr[g]) return fail(ORBX_ERR_INVALID, "group offsets must be non-decreasing");
+    int st;
+    if ((st = upload(m, m->b[1], desc, (size_t)total * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[5], ptr, (size_t)(ngroups + 1) * sizeof(int))) != ORBX_OK) return st;
+    M_CUDA(m->b[7].ensure((size_t)ngroups * sizeof(int)));
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    k_distinctive<<<(ngroups + kDistWarps - 1) / kDistWarps, kDistWarps * 32, 0, m->stream>>>((const uint4 *)m->b[1].p, m->b[5].as<int>(), ngroups,
+                                                                                            m->b[7].as<int>());
+    m->last_launches = 1;
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    M_CUDA(cudaMemcpyAsync(best, m->b[7].p, (size_t)ngroups * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
 int orbx_popc_peak(int device, double *gpopc_per_s) {
     if (!gpopc_per_s) return fail(ORBX_ERR_INVALID, "NULL argument");
     if (orbx_device_count() <= device || device < 0) return fail(ORBX_ERR_NO_DEVICE, "no such CUDA device");

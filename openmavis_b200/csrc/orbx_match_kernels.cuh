@@ -7,12 +7,6 @@
 
 namespace orbx {
 
-__device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
-    // ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2577-2591) == popcount(a ^ b) over 8 words
-    return (__popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z)) +
-           (__popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y)) + (__popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w));
-}
-
 __global__ void k_pair_distance(const uint4 *__restrict__ a, const uint4 *__restrict__ b, int n, int *__restrict__ dist) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -284,6 +278,49 @@ __global__ void __launch_bounds__(1024) k_excl_scan(const int *__restrict__ in, 
         __syncthreads();
     }
     if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483), batched: one warp per map point.  Row i of the
+// distance matrix is never materialised: the warp histograms d(i, j) over the 257 possible distances in shared
+// memory and walks the cumulative counts to the median rank floor(0.5 * (N - 1)).  SURVEY.md §8(f) N4.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kDistWarps = 4;
+constexpr int kDistBins = 288;                  // >= 257, multiple of 32
+
+__global__ void __launch_bounds__(kDistWarps * 32) k_distinctive(const uint4 *__restrict__ desc, const int *__restrict__ ptr, int ngroups,
+                                                                 int *__restrict__ best) {
+    __shared__ int s_hist[kDistWarps][kDistBins];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * kDistWarps + wid;
+    if (g >= ngroups) return;
+    const int b0 = ptr[g], N = ptr[g + 1] - b0;
+    if (N <= 0) { if (lane == 0) best[g] = -1; return; }
+    int *hist = s_hist[wid];
+    const int k = (int)(0.5 * (double)(N - 1));                 // vDists[0.5 * (N - 1)]
+    int best_median = 0x7FFFFFFF, best_idx = 0;
+    for (int i = 0; i < N; i++) {
+        for (int t = lane; t < kDistBins; t += 32) hist[t] = 0;
+        __syncwarp();
+        const uint4 qa = desc[2 * (long long)(b0 + i)], qb = desc[2 * (long long)(b0 + i) + 1];
+        for (int j = lane; j < N; j += 32) atomicAdd(&hist[hamming256(qa, qb, desc[2 * (long long)(b0 + j)], desc[2 * (long long)(b0 + j) + 1])], 1);
+        __syncwarp();
+        // lane owns bins [9 * lane, 9 * lane + 9); the median is the first bin whose inclusive cumulative count exceeds k
+        int c[kDistBins / 32], sum = 0;
+#pragma unroll
+        for (int t = 0; t < kDistBins / 32; t++) { c[t] = hist[(kDistBins / 32) * lane + t]; sum += c[t]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
+        int run = inc - sum, med = 0x7FFFFFFF;
+#pragma unroll
+        for (int t = 0; t < kDistBins / 32; t++) { run += c[t]; if (run > k && med == 0x7FFFFFFF) med = (kDistBins / 32) * lane + t; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) med = min(med, __shfl_xor_sync(0xFFFFFFFFu, med, o));
+        if (med < best_median) { best_median = med; best_idx = i; }     // first minimum (:471-474)
+        __syncwarp();
+    }
+    if (lane == 0) best[g] = best_idx;
 }
 
 // popc.b32 issue-rate microbenchmark (roofline denominator of the matching kernels)

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -961,6 +962,130 @@ int orc_search_for_triangulation(int nn1, const int *nodes1, const int *ptr1, co
         }
     }
     return nmatches;
+}
+
+
+// ---- Frame::ComputeStereoMatches (src/Frame.cc:1057-1219) -------------------------------------------------------
+// hL / hR: oracle extractors that hold the last extraction of the (rectified) left / right image: mvKeys = out_kps of hL,
+// mvKeysRight = out_kps of hR, mDescriptors(Right) = out_desc, mvImagePyramid = lv[].  mb = baseline, mbf = baseline * fx.
+// Outputs mvuRight[N], mvDepth[N] (-1 = no match).  Returns the number of keypoints with depth.
+int orc_compute_stereo_matches(void *hL, void *hR, float mb, float mbf, float *mvuRight, float *mvDepth) {
+    Extractor &EL = *(Extractor *)hL, &ER = *(Extractor *)hR;
+    const int N = (int)EL.out_kps.size();
+    for (int i = 0; i < N; i++) { mvuRight[i] = -1.0f; mvDepth[i] = -1.0f; }             // :1058-1059
+    const int thOrbDist = (100 + 50) / 2;                                                 // :1061
+    const int nRows = EL.lv[0].h;                                                         // :1063
+    std::vector<std::vector<size_t>> vRowIndices(nRows);
+    const int Nr = (int)ER.out_kps.size();
+    for (int iR = 0; iR < Nr; iR++) {                                                     // :1073-1083
+        const KeyPt &kp = ER.out_kps[iR];
+        const float kpY = kp.y;
+        const float r = 2.0f * ER.p.sf[kp.octave];
+        const int maxr = (int)ceil(kpY + r);
+        const int minr = (int)floor(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++)
+            if (yi >= 0 && yi < nRows) vRowIndices[yi].push_back(iR);                     // (the reference indexes unchecked)
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;                                   // :1086-1088
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < N; iL++) {                                                      // :1094-1201
+        const KeyPt &kpL = EL.out_kps[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y, uL = kpL.x;
+        const std::vector<size_t> &vCandidates = vRowIndices[(int)vL];
+        if (vCandidates.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = 100;                                                               // TH_HIGH
+        size_t bestIdxR = 0;
+        const uint8_t *dL = EL.out_desc.data() + (size_t)iL * 32;
+        for (size_t iC = 0; iC < vCandidates.size(); iC++) {
+            const size_t iR = vCandidates[iC];
+            const KeyPt &kpR = ER.out_kps[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = descriptor_distance(dL, ER.out_desc.data() + iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {                                                       // :1138
+            const float uR0 = ER.out_kps[bestIdxR].x;
+            const float scaleFactor = EL.p.inv_sf[kpL.octave];
+            const float scaleduL = roundf(kpL.x * scaleFactor);
+            const float scaledvL = roundf(kpL.y * scaleFactor);
+            const float scaleduR0 = roundf(uR0 * scaleFactor);
+            const int w = 5;
+            const Level &PL = EL.lv[kpL.octave], &PR = ER.lv[kpL.octave];
+            const uint8_t *IL = PL.buf.data() + (size_t)(kEdge + (int)(scaledvL - w)) * PL.stride + kEdge + (int)(scaleduL - w);
+            int bestDistS = INT32_MAX, bestincR = 0;
+            const int L = 5;
+            float vDists[2 * 5 + 1];
+            const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= PR.w) continue;
+            for (int incR = -L; incR <= +L; incR++) {
+                const uint8_t *IR = PR.buf.data() + (size_t)(kEdge + (int)(scaledvL - w)) * PR.stride + kEdge + (int)(scaleduR0 + incR - w);
+                int sad = 0;                                                              // cv::norm(IL, IR, NORM_L1) on 8-bit mats
+                for (int y = 0; y < 2 * w + 1; y++)
+                    for (int x = 0; x < 2 * w + 1; x++) sad += abs((int)IL[(size_t)y * PL.stride + x] - (int)IR[(size_t)y * PR.stride + x]);
+                const float dist = (float)(double)sad;
+                if (dist < bestDistS) { bestDistS = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = EL.p.sf[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                mvDepth[iL] = mbf / disparity;
+                mvuRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestDistS, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return 0;                                                       // (the reference reads vDistIdx[0] unchecked)
+    std::sort(vDistIdx.begin(), vDistIdx.end());                                          // :1203-1205
+    const float median = vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    int kept = (int)vDistIdx.size();
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {                                 // :1207-1214
+        if (vDistIdx[i].first < thDist) break;
+        mvuRight[vDistIdx[i].second] = -1; mvDepth[vDistIdx[i].second] = -1; kept--;
+    }
+    return kept;
+}
+
+
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483), batched over map points ---------------------
+// Group g holds the observed descriptors rows [ptr[g], ptr[g+1]) of `desc` (in the order the reference pushes them into
+// vDescriptors).  best[g] = index inside the group of the descriptor with the least median distance to the others
+// (first minimum; median = sorted row [0.5 * (N - 1)]), or -1 for an empty group.
+void orc_distinctive_descriptors(const uint8_t *desc, const int *ptr, int ngroups, int *best) {
+    for (int g = 0; g < ngroups; g++) {
+        const int N = ptr[g + 1] - ptr[g];
+        best[g] = -1;
+        if (N <= 0) continue;
+        const uint8_t *d = desc + (size_t)ptr[g] * 32;
+        std::vector<float> Distances((size_t)N * N);                                    // :452-461
+        for (int i = 0; i < N; i++) {
+            Distances[(size_t)i * N + i] = 0;
+            for (int j = i + 1; j < N; j++) {
+                const int distij = descriptor_distance(d + (size_t)i * 32, d + (size_t)j * 32);
+                Distances[(size_t)i * N + j] = (float)distij; Distances[(size_t)j * N + i] = (float)distij;
+            }
+        }
+        int BestMedian = INT_MAX, BestIdx = 0;                                           // :464-475
+        for (int i = 0; i < N; i++) {
+            std::vector<int> vDists(Distances.begin() + (size_t)i * N, Distances.begin() + (size_t)(i + 1) * N);
+            std::sort(vDists.begin(), vDists.end());
+            const int median = vDists[(size_t)(0.5 * (N - 1))];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best[g] = BestIdx;
+    }
 }
 
 }  // extern "C"

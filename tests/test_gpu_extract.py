@@ -229,3 +229,33 @@ def test_chunked_pipeline_equals_oracle_and_single_chunk():
         for (m0, k0, d0), (m1, k1, d1) in zip(host, dev):
             assert m0 == m1 and np.array_equal(k0, k1) and np.array_equal(d0, d1)
     assert sum(rig.stage_ms().values()) > 0
+
+
+# Frame::ComputeStereoMatches on the device-resident pyramids / keypoints / descriptors of a stereo pair
+@pytest.mark.parametrize('bf', [(0.11, 47.9), (0.5, 12.0)])
+def test_compute_stereo_matches(bf):
+    _need_gpu()
+    mb, mbf = bf
+    left = synth_image(752, 480, 2001)
+    # rectified right image: the left one shifted by a disparity that varies smoothly along x (3..35 px) plus mild noise
+    xs = np.arange(752)
+    disp = (19 + 16 * np.sin(xs / 90.0)).astype(np.int64)
+    right = left[:, np.clip(xs + disp, 0, 751)]
+    right = np.clip(right.astype(np.int32) + np.random.default_rng(3).integers(-2, 3, right.shape), 0, 255).astype(np.uint8)
+    rig = ob.RigExtractor(752, 480, 2, 1200)
+    res = rig.extract([left, right], ob.make_params(2, 1200, 20, 7, (0, 0)))
+    n, u, d = rig.compute_stereo_matches(0, 1, mb, mbf)
+    EL = O.OracleExtractor(1200, 1.2, 8, 20, 7); ER = O.OracleExtractor(1200, 1.2, 8, 20, 7)
+    EL(left, (0, 0)); ER(right, (0, 0))
+    N = len(res[0][1])
+    ru = np.zeros(N, np.float32); rd = np.zeros(N, np.float32)
+    O.lib().orc_compute_stereo_matches.argtypes = [O.C.c_void_p, O.C.c_void_p, O.C.c_float, O.C.c_float, O.C.c_void_p, O.C.c_void_p]
+    rn = O.lib().orc_compute_stereo_matches(EL.h, ER.h, mb, mbf, O.p(ru), O.p(rd))
+    assert rn == n and n > 100, (rn, n)
+    assert np.array_equal(ru.view(np.uint32), u[:N].view(np.uint32)), int((ru != u[:N]).sum())
+    assert np.array_equal(rd.view(np.uint32), d[:N].view(np.uint32))
+    # the same pair held by two extractor handles (mpORBextractorLeft / mpORBextractorRight of the reference)
+    a = ob.RigExtractor(752, 480, 1, 1200); b2 = ob.RigExtractor(752, 480, 1, 1200)
+    a.extract([left], ob.make_params(1, 1200, 20, 7, (0, 0))); b2.extract([right], ob.make_params(1, 1200, 20, 7, (0, 0)))
+    n2, u2, d2 = a.compute_stereo_matches(0, 0, mb, mbf, right=b2)
+    assert n2 == n and np.array_equal(u2[:N].view(np.uint32), u[:N].view(np.uint32)) and np.array_equal(d2[:N].view(np.uint32), d[:N].view(np.uint32))

@@ -249,3 +249,20 @@ def test_popc_peak_reports_a_rate():
     if ob.device_count() == 0:
         pytest.fail('no CUDA device')
     assert ob.popc_peak() > 100.0
+
+
+# MapPoint::ComputeDistinctiveDescriptors batched over map points
+def test_distinctive_descriptors(M):
+    rng = np.random.default_rng(12)
+    sizes = np.concatenate([[0, 1, 2, 3, 33, 64, 130], rng.integers(1, 24, 400)]).astype(np.int32)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    base = synth_descriptors(len(sizes), 91)
+    desc = np.repeat(base, sizes, axis=0)
+    flips = np.packbits(rng.random((desc.shape[0], 256)) < 0.12, axis=1, bitorder='little')
+    desc ^= flips
+    desc[ptr[10]:ptr[11]] = desc[ptr[10]]                      # all-equal group: every median 0 -> first index
+    best = M.ComputeDistinctiveDescriptors(desc, ptr)
+    ref = np.zeros(len(sizes), np.int32)
+    O.lib().orc_distinctive_descriptors(O.p(desc), O.p(ptr), len(sizes), O.p(ref))
+    assert np.array_equal(best, ref)
+    assert best[0] == -1 and best[1] == 0 and best[10] == 0
