@@ -128,6 +128,66 @@ def cpu_oracle_run(frames, threads, rank=0):
     return frames / dt, dt, tot
 
 
+def guided_matchers(ob, device):
+    """Secondary numbers for the small matchers (report queries/s and latency): config-4 style SearchByProjection
+    (2 x 512x512, 1500 features / camera, 5000 map points), ComputeStereoMatches on a 752x480 pair, ComputeDistinctiveDescriptors on
+    2000 map points.  Wall-clock per call through the host-buffer C ABI (uploads and downloads included), median of 7."""
+    from openmavis_b200.synth import synth_image, synth_descriptors
+    rng = np.random.default_rng(7)
+    out = {}
+
+    def timed(fn, reps=7):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)) * 1e3
+
+    # ---- SearchByProjection (src/ORBmatcher.cc:23-340)
+    ncam, nmp, w = 2, 5000, 512
+    rig = ob.RigExtractor(w, w, ncam, 1500, device=device)
+    res = rig.extract([synth_image(w, w, 4300 + c) for c in range(ncam)], ob.make_params(ncam, 1500, 20, 7, (0, 511)))
+    kps = np.concatenate([r[1] for r in res]); desc = np.concatenate([r[2] for r in res])
+    cam_off = np.concatenate([[0], np.cumsum([len(r[1]) for r in res])]).astype(np.int32)
+    in_view = (rng.random((nmp, 4)) < np.array([0.9, 0.5, 0, 0])).astype(np.uint8)
+    src = np.stack([rng.integers(cam_off[c], cam_off[c + 1], nmp) for c in range(ncam)] + [np.zeros(nmp, np.int64)] * 2, 1)
+    px = (kps['x'][src] + rng.uniform(-3, 3, (nmp, 4))).astype(np.float32); py = (kps['y'][src] + rng.uniform(-3, 3, (nmp, 4))).astype(np.float32)
+    lvl = np.clip(kps['octave'][src] + rng.integers(0, 2, (nmp, 4)), 0, 7).astype(np.int32)
+    md = synth_descriptors(nmp, 8)
+    own = rng.random(nmp) < 0.7
+    md[own] = desc[src[own, 0]] ^ np.packbits(rng.random((int(own.sum()), 256)) < 0.06, axis=1, bitorder='little')
+    frame = dict(cam_off=cam_off, kps=kps, desc=desc, bounds=np.tile(np.array([0, w, 0, w], np.float32), (ncam, 1)), scale_factors=rig.scale)
+    points = dict(in_view=in_view, proj_x=px, proj_y=py, level=lvl, view_cos=np.full((nmp, 4), 0.999, np.float32), desc=md)
+    m = ob.ORBmatcher(0.8, device=device)
+    nm = [0]
+
+    def sbp():
+        nm[0] = m.SearchByProjection(frame, points, 3.0)[0]
+    ms = timed(sbp)
+    out['search_by_projection'] = {'map_points': nmp, 'cameras': ncam, 'keypoints': int(cam_off[-1]), 'matches': int(nm[0]), 'ms_per_call': ms,
+                                   'device_ms': m.last_ms(), 'map_points_per_s': nmp / (ms * 1e-3)}
+    # ---- ComputeStereoMatches (src/Frame.cc:1057-1219)
+    left = synth_image(752, 480, 2001)
+    xs = np.arange(752)
+    right = left[:, np.clip(xs + (19 + 16 * np.sin(xs / 90.0)).astype(np.int64), 0, 751)].copy()
+    st = ob.RigExtractor(752, 480, 2, 1200, device=device)
+    st.extract([left, right], ob.make_params(2, 1200, 20, 7, (0, 0)))
+    ns = [0]
+
+    def stereo():
+        ns[0] = st.compute_stereo_matches(0, 1, 0.11, 47.9)[0]
+    ms = timed(stereo)
+    out['compute_stereo_matches'] = {'image': '2x752x480', 'matches': int(ns[0]), 'ms_per_call': ms}
+    # ---- ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483)
+    sizes = rng.integers(2, 24, 2000).astype(np.int32)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    dd = np.repeat(synth_descriptors(2000, 9), sizes, axis=0) ^ np.packbits(rng.random((int(ptr[-1]), 256)) < 0.1, axis=1, bitorder='little')
+    ms = timed(lambda: m.ComputeDistinctiveDescriptors(dd, ptr))
+    out['distinctive_descriptors'] = {'map_points': 2000, 'descriptors': int(ptr[-1]), 'ms_per_call': ms, 'device_ms': m.last_ms(),
+                                      'map_points_per_s': 2000 / (ms * 1e-3)}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  Its sources need OpenCV/Eigen/Sophus headers
     that are not in this image, so the timed code is the oracle port, with all host threads."""
@@ -327,6 +387,10 @@ def main():
                     'ms': ms_knn, 'popc_gops_achieved': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world, 'popc_gops_peak_measured': popc,
                     'frac_of_popc_peak': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world / popc, 'n_gpus': world,
                     'collective': 'nccl all_gather of train rows' if world > 1 else None}
+        if rank == 0:
+            torch.cuda.set_stream(torch.cuda.default_stream(dev))
+            matching['guided'] = guided_matchers(ob, local)
+            torch.cuda.set_stream(stream)
         idx_h = d_idx.cpu().numpy(); dist_h = d_dist.cpu().numpy()
         chk = np.unpackbits(query[lo:hi][:256] ^ train[idx_h[:256, 0]], axis=1).sum(axis=1)
         assert np.array_equal(chk, dist_h[:256, 0])
