@@ -53,7 +53,6 @@ struct Geom {
     int fast_g;                // cells per FAST tile
     int fast_ip, fast_ymax;    // shared-memory row pitch (bytes, multiple of 32) and max tested rows of a FAST tile
     int fast_total_tiles;      // FAST tiles per image over all levels
-    int oct_scap;              // candidates of one level whose quadtree node labels fit in shared memory
     LevelGeom lv[kMaxLevels];
 };
 

@@ -167,9 +167,6 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     ex->oct_list_cap = max_list;
     ex->oct_smem = oct_work_bytes(max_list);
     if (ex->oct_smem > 200 * 1024) return fail(ORBX_ERR_INVALID, "nfeatures too large for the quadtree workspace");
-    // the rest of a 56 KB budget (4 CTAs per SM) holds the per-candidate node labels; larger levels use the global array
-    G.oct_scap = ex->oct_smem < 54 * 1024 ? (int)((56 * 1024 - ex->oct_smem) / 2) & ~63 : 0;
-    ex->oct_smem += (size_t)G.oct_scap * 2;
     int tiles = 0;
     for (int l = 0; l < nl; l++) {
         ex->blur_tiles.base[l] = tiles;
@@ -244,7 +241,7 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
     orbx_extractor *ex = new orbx_extractor();
     ex->device = device; ex->width = width; ex->height = height; ex->max_images = max_images;
     ex->max_nfeatures = max_nfeatures; ex->nlevels = nlevels; ex->scale_factor = scale_factor;
-    if (const char *t = getenv("ORBX_OCT_THREADS")) ex->oct_threads = std::max(32, std::min(512, atoi(t) & ~31));   // tuning knob
+    if (const char *t = getenv("ORBX_OCT_THREADS")) ex->oct_threads = std::max(32, std::min(256, atoi(t) & ~31));   // tuning knob
     int st = build_geometry(ex, fma_mode ? 1 : 0);
     if (st != ORBX_OK) { delete ex; return st; }
     const Geom &G = ex->G;
@@ -409,7 +406,7 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
     k_fast<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, ex->d_fast_tiles, i0);
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[3], sA));
-    k_octree<<<dim3(nl, cnt), ex->oct_threads, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
+    k_octree<<<dim3(cnt, nl), ex->oct_threads, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
                                                                    ex->d_lin_n, ex->d_node, ex->d_slot, ex->d_lvl_kp, ex->d_lvl_n,
                                                                    ex->oct_list_cap, i0);
     launches++;

@@ -635,14 +635,16 @@ struct DevCtx {
     }
 };
 
-__global__ void __launch_bounds__(512) k_octree(Geom G, const int *__restrict__ nfeat_lvl, const uint32_t *__restrict__ cells,
+__global__ void __launch_bounds__(256, 6) k_octree(Geom G, const int *__restrict__ nfeat_lvl, const uint32_t *__restrict__ cells,
                                                 const int *__restrict__ cell_cnt, int *__restrict__ cell_off,
                                                 uint32_t *__restrict__ lin, int *__restrict__ lin_n,
                                                 unsigned short *__restrict__ node, int *__restrict__ sel_tmp,
                                                 uint32_t *__restrict__ lvl_kp, int *__restrict__ lvl_n, int list_cap, int img0) {
     extern __shared__ __align__(16) unsigned char oct_smem[];
     __shared__ int s_total;
-    const int lvl = blockIdx.x, b = blockIdx.y + img0;
+    // grid = (images, levels): CTAs are dispatched level 0 first — the levels with the most candidates and the longest
+    // sequential phases start first, the short ones fill the tail
+    const int lvl = blockIdx.y, b = blockIdx.x + img0;
     const LevelGeom &L = G.lv[lvl];
     DevCtx cx; cx.tid = threadIdx.x; cx.nt = blockDim.x; cx.total = &s_total;
     const int ncell = L.n_cols * L.n_rows;
@@ -654,9 +656,7 @@ __global__ void __launch_bounds__(512) k_octree(Geom G, const int *__restrict__ 
     __syncthreads();
     const uint32_t *cs = cells + (long long)b * G.cand_per_image + L.cand_off;
     uint32_t *ln = lin + (long long)b * G.cand_per_image + L.cand_off;
-    // node labels are rewritten by every pass: keep them in shared memory when the level's candidates fit
-    unsigned short *nd = n <= G.oct_scap ? reinterpret_cast<unsigned short *>(oct_smem + oct_work_bytes(list_cap))
-                                         : node + (long long)b * G.cand_per_image + L.cand_off;
+    unsigned short *nd = node + (long long)b * G.cand_per_image + L.cand_off;
     const int lane = cx.tid & 31, wid = cx.tid >> 5, nw = cx.nt >> 5;
     for (int c = wid; c < ncell; c += nw) {
         const int k = cc[c], o = co[c];
