@@ -433,7 +433,7 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
 static int images_per_chunk(const orbx_extractor *ex, int n, bool host_io) {
     if (ex->chunk_images > 0) return std::min(n, ex->chunk_images);
     if (n <= 16) return n;
-    const int parts = host_io ? 4 : 2;     // measured on B200 (320 images of 720x540): 80-image chunks for host I/O, 160 otherwise
+    const int parts = host_io ? 4 : 1;     // measured on B200 (320 images of 720x540): 80-image chunks for host I/O, one chunk otherwise
     return std::max(16, (n + parts - 1) / parts);
 }
 
