@@ -57,7 +57,13 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ img,
     const int row_groups = (L.rows + kL0Rows - 1) / kL0Rows;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= chunks * row_groups) return;
-    const int rg = idx / chunks, c0 = (idx - rg * chunks) << 4;
+    // Work order: first every chunk that lies inside the image row (one aligned 128-bit load), then the few frame chunks
+    // per row (byte gathers with reflection) — otherwise every warp would contain a few frame chunks and run both paths.
+    const int c_int0 = kXO >> 4, n_int = L.w >> 4, n_frame = chunks - n_int;
+    int rg, c;
+    if (idx < n_int * row_groups) { rg = idx / n_int; c = c_int0 + (idx - rg * n_int); }
+    else { const int j = idx - n_int * row_groups; rg = j / n_frame; c = j - rg * n_frame; if (c >= c_int0) c += n_int; }
+    const int c0 = c << 4;
     const int b = blockIdx.y + img0;
     const uint8_t *src = img + (long long)blockIdx.y * img_bytes;
     uint4 v[kL0Rows];
