@@ -224,7 +224,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--frames', type=int, default=64, help='rig frames per step per GPU')
-    ap.add_argument('--ref-frames', type=int, default=8, help='rig frames per step of the CPU reference arm')
+    ap.add_argument('--ref-frames', type=int, default=32, help='rig frames per step of the CPU reference arm')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline sample')
     ap.add_argument('--no-matching', action='store_true')
     ap.add_argument('--knn-n', type=int, default=100000)
