@@ -62,6 +62,16 @@ __device__ __forceinline__ int hamming256(const uint4 &a0, const uint4 &a1, cons
     return (__popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z)) +
            (__popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y)) + (__popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w));
 }
+
+// Same distance with 6 POPC instead of 8: two carry-save adders (3 words -> ones + twos, 2 LOP3 each) move a quarter of the
+// popcount work from the XU pipe (POPC: 16 lanes / clk / SM, the bound of the brute-force matcher) to the 4x wider ALU pipe.
+__device__ __forceinline__ int hamming256_csa(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
+    const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+    const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+    const uint32_t sA = x0 ^ x1 ^ x2, cA = (x0 & x1) | (x2 & (x0 | x1));
+    const uint32_t sB = x3 ^ x4 ^ x5, cB = (x3 & x4) | (x5 & (x3 | x4));
+    return (__popc(sA) + __popc(sB)) + (__popc(x6) + __popc(x7)) + 2 * (__popc(cA) + __popc(cB));
+}
 #endif
 
 // Thread-local error string behind orbx_last_error().

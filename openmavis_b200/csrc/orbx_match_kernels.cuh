@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn2(const uint4 *__restrict__ 
             const uint32_t jj = (uint32_t)(base + j);
 #pragma unroll
             for (int u = 0; u < kKnnQPT; u++) {
-                const uint32_t d = (uint32_t)hamming256(qa[u], qb[u], ta, tb);
+                const uint32_t d = (uint32_t)hamming256_csa(qa[u], qb[u], ta, tb);
                 top2_insert(k0[u], k1[u], (d << kKeyShift) | jj);
             }
         }
