@@ -364,13 +364,22 @@ def main():
         d_idx = torch.empty((hi - lo, 2), dtype=torch.int32, device=dev)
         d_dist = torch.empty((hi - lo, 2), dtype=torch.int32, device=dev)
 
+        shared = ob.SharedRows(dist, local, n) if world > 1 else None
+        token = torch.zeros(1, device=dev)
+        step_no = [0]
+
         def knn_step():
-            if world > 1:    # the one real exchange step: NCCL all-gather of the train rows over NVLink
-                d_t = shard.gather_train_rows(d_local_train, n, dist)
+            if world > 1:
+                # The one real exchange step, fused with the compute: every rank publishes its train rows in a peer-mapped
+                # buffer and each rank's 2-NN kernels read all parts in place over NVLink (no all-gather, no staging copy);
+                # one tiny all-reduce per step is the stream-ordered barrier (see openmavis_b200.SharedRows).
+                buf = step_no[0] & 1
+                step_no[0] += 1
+                shared.fill(buf, d_local_train.data_ptr(), stream.cuda_stream)
+                dist.all_reduce(token)
+                m.knnMatch2_device_parts(d_q.data_ptr(), hi - lo, shared.ptrs[buf], shared.rows, d_idx.data_ptr(), d_dist.data_ptr())
             else:
-                d_t = d_local_train
-            m.knnMatch2_device(d_q.data_ptr(), hi - lo, d_t.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
-            return d_t
+                m.knnMatch2_device(d_q.data_ptr(), hi - lo, d_local_train.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
         for _ in range(2):
             knn_step()
         barrier()
@@ -386,7 +395,7 @@ def main():
         matching = {'metric': 'Hamming matches/sec (brute-force 2-NN %dx%d)' % (n, n), 'value': pairs / (ms_knn * 1e-3), 'unit': 'pairs/s',
                     'ms': ms_knn, 'popc_gops_achieved': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world, 'popc_gops_peak_measured': popc,
                     'frac_of_popc_peak': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world / popc, 'n_gpus': world,
-                    'collective': 'nccl all_gather of train rows' if world > 1 else None}
+                    'collective': 'none for the data: peer-mapped train rows read in place over NVLink (cudaIpc); one 4-byte all-reduce per step as barrier' if world > 1 else None}
         if rank == 0:
             torch.cuda.set_stream(torch.cuda.default_stream(dev))
             matching['guided'] = guided_matchers(ob, local)
@@ -394,6 +403,10 @@ def main():
         idx_h = d_idx.cpu().numpy(); dist_h = d_dist.cpu().numpy()
         chk = np.unpackbits(query[lo:hi][:256] ^ train[idx_h[:256, 0]], axis=1).sum(axis=1)
         assert np.array_equal(chk, dist_h[:256, 0])
+        assert (idx_h[:256, 0] >= 0).all() and (idx_h[:256, 0] < n).all()
+        if shared is not None:
+            torch.cuda.synchronize()
+            shared.close()
 
     # ---------------- CPU baseline (rank 0, N == 1 only; bounded sample) ----------------
     cpu = None

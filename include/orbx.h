@@ -166,6 +166,21 @@ int orbx_knn2(orbx_matcher *m, const uint8_t *query, int nq, const uint8_t *trai
 /* Same with DEVICE pointers, asynchronous on the matcher's stream (no host synchronisation). */
 int orbx_knn2_device(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_train, int nt, int *d_idx,
                      int *d_dist);
+/* Sharded brute-force 2-NN: the train set is the concatenation of nparts parts that live in DEVICE memory of
+ * this or of PEER GPUs (pointers obtained with orbx_shared_open): the matcher reads the peers' rows in place over NVLink —
+ * there is no all-gather step.  Indices are global (offset of part p = sum of part_rows[0..p)).  Asynchronous on the
+ * matcher's stream; the caller orders it after the peers have written their rows (a barrier). */
+int orbx_knn2_device_parts(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *const *d_train_parts,
+                           const int *part_rows, int nparts, int *d_idx, int *d_dist);
+/* Device buffers that other processes on the same node can map (cudaIpc): alloc in the owner (handle = 64 opaque bytes to
+ * send to the peers), open / close in a peer, free in the owner. */
+int orbx_shared_alloc(int device, size_t bytes, void **d_ptr, void *ipc_handle64);
+int orbx_shared_open(int device, const void *ipc_handle64, void **d_ptr);
+int orbx_shared_close(int device, void *d_ptr);
+int orbx_shared_free(int device, void *d_ptr);
+/* device-to-device copy on a CUDA stream (fills a shared buffer from any device memory). */
+int orbx_device_copy(int device, void *d_dst, const void *d_src, size_t bytes, void *cuda_stream);
+
 /* Lowe ratio test exactly as the callers evaluate it (src/Frame.cc:1434 ratio 0.7; :1491 ratio 0.8):
  * keep[i] = two neighbours exist && (float)d0 < (float)d1 * ratio (product in double). HOST, pure host code. */
 int orbx_ratio_test(const int *dist, int nq, double ratio, uint8_t *keep);

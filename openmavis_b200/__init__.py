@@ -317,6 +317,13 @@ class ORBmatcher:
         _check(self.L.orbx_knn2_device(self.h, C.c_void_p(d_query), int(nq), C.c_void_p(d_train), int(nt), C.c_void_p(d_idx),
                                        C.c_void_p(d_dist)))
 
+    def knnMatch2_device_parts(self, d_query, nq, part_ptrs, part_rows, d_idx, d_dist):
+        """2-NN against a train set given as parts in this GPU's or in peer GPUs' memory (read in place over NVLink)."""
+        n = len(part_ptrs)
+        ptrs = (C.c_void_p * n)(*[int(x) for x in part_ptrs])
+        rows = np.ascontiguousarray(part_rows, np.int32)
+        _check(self.L.orbx_knn2_device_parts(self.h, C.c_void_p(d_query), int(nq), ptrs, _p(rows), n, C.c_void_p(d_idx), C.c_void_p(d_dist)))
+
     @staticmethod
     def ratio_test(dist, ratio):
         dist = np.ascontiguousarray(dist, np.int32)
@@ -411,3 +418,54 @@ def popc_peak(device=0):
     v = C.c_double(0)
     _check(lib().orbx_popc_peak(int(device), C.byref(v)))
     return v.value
+
+
+class SharedRows:
+    """Train descriptor rows of the sharded brute-force matcher: every rank owns TWO device buffers that the other ranks of the
+    node map through CUDA IPC, so a rank's 2-NN kernels read all parts in place (peer loads over NVLink): no all-gather, no
+    staging copy.  Protocol per step k (everything stream-ordered, no host synchronisation):
+        fill(k & 1, my rows)  ->  one tiny all-reduce (a stream-ordered barrier)  ->  2-NN kernels read ptrs[k & 1] of all ranks.
+    The double buffer makes that single barrier sufficient: a rank can only pass barrier k after every rank has finished the
+    kernels of step k-1, so nobody still reads the buffer that step k+1 overwrites.
+    `dist` is an initialised torch.distributed module (used to exchange the 64-byte handles and for the barrier)."""
+
+    def __init__(self, dist, device, n_total):
+        from . import shard
+        self.L, self.device, self.dist = lib(), int(device), dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.rows = [shard.row_shard(n_total, r, self.world)[1] for r in range(self.world)]
+        self.L.orbx_shared_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+        self.L.orbx_shared_open.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        self.L.orbx_shared_close.argtypes = [C.c_int, C.c_void_p]
+        self.L.orbx_shared_free.argtypes = [C.c_int, C.c_void_p]
+        self.L.orbx_device_copy.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        self.own, self.ptrs = [], []
+        for _ in range(2):
+            own, handle = C.c_void_p(), C.create_string_buffer(64)
+            _check(self.L.orbx_shared_alloc(self.device, max(self.rows[self.rank], 1) * 32, C.byref(own), handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw)
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(own.value)
+                else:
+                    q = C.c_void_p()
+                    _check(self.L.orbx_shared_open(self.device, handles[r], C.byref(q)))
+                    ptrs.append(q.value)
+            self.own.append(own.value); self.ptrs.append(ptrs)
+
+    def fill(self, buf, d_local_rows_ptr, cuda_stream):
+        """Copies this rank's rows (device pointer) into its shared buffer `buf` on `cuda_stream`."""
+        _check(self.L.orbx_device_copy(self.device, C.c_void_p(self.own[buf]), C.c_void_p(d_local_rows_ptr), self.rows[self.rank] * 32,
+                                       C.c_void_p(cuda_stream)))
+
+    def close(self):
+        for buf in range(len(self.ptrs)):
+            for r, q in enumerate(self.ptrs[buf]):
+                if r != self.rank and q:
+                    self.L.orbx_shared_close(self.device, C.c_void_p(q))
+        self.dist.barrier()                      # nobody maps the buffers any more
+        for own in self.own:
+            self.L.orbx_shared_free(self.device, C.c_void_p(own))
+        self.ptrs, self.own = [], []

@@ -1,5 +1,6 @@
 // orbx_match.cu — host side of the matching C ABI (include/orbx.h).
 // Replaces the Hamming cores of ORBmatcher (src/ORBmatcher.cc) and cv::BFMatcher::knnMatch (src/Frame.cc:1427,1483).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -48,21 +49,45 @@ static int upload(orbx_matcher *m, DBuf &buf, const void *src, size_t bytes) {
     return ORBX_OK;
 }
 
-static int knn2_launch(orbx_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int *d_idx, int *d_dist) {
+// Train set = concatenation of `nparts` parts (one for the single-GPU call; one per rank, read through peer-mapped pointers over
+// NVLink, for the sharded matcher).  One k_knn2 launch per part, all writing slices of the same partial buffer, one merge.
+static int knn2_launch_parts(orbx_matcher *m, const uint8_t *d_q, int nq, const uint8_t *const *d_parts, const int *part_rows, int nparts,
+                             int *d_idx, int *d_dist) {
+    long long nt = 0;
+    for (int p = 0; p < nparts; p++) nt += part_rows[p];
     if (nt >= (1 << kKeyShift)) return fail(ORBX_ERR_INVALID, "knn2: more than 8388607 train rows are not supported");
     const int per_block = kKnnThreads * kKnnQPT;
     const int qblocks = (nq + per_block - 1) / per_block;
     // split the train set so that small problems still fill the machine (2 waves of 148 SMs x resident CTAs)
-    int slices = std::max(1, std::min((2 * m->sm_count * 4 + qblocks - 1) / qblocks, (nt + kKnnTile - 1) / kKnnTile));
-    int slice_rows = ((nt + slices - 1) / slices + kKnnTile - 1) / kKnnTile * kKnnTile;
-    slices = (nt + slice_rows - 1) / slice_rows;
-    M_CUDA(m->b[0].ensure((size_t)slices * nq * sizeof(uint2)));
-    k_knn2<<<dim3(qblocks, slices), kKnnThreads, 0, m->stream>>>((const uint4 *)d_q, nq, (const uint4 *)d_t, nt, slice_rows,
-                                                                 m->b[0].as<uint2>());
-    k_knn2_merge<<<(nq + 255) / 256, 256, 0, m->stream>>>(m->b[0].as<uint2>(), nq, slices, d_idx, d_dist);
-    m->last_launches += 2;
+    const int want = std::max(1, (2 * m->sm_count * 4 + qblocks - 1) / qblocks);
+    std::vector<int> slices(nparts), slice_rows(nparts);
+    int total_slices = 0;
+    for (int p = 0; p < nparts; p++) {
+        const int rows = part_rows[p];
+        if (rows <= 0) { slices[p] = 0; slice_rows[p] = kKnnTile; continue; }
+        int s = std::max(1, std::min((int)((long long)want * rows / std::max<long long>(nt, 1)) + 1, (rows + kKnnTile - 1) / kKnnTile));
+        slice_rows[p] = ((rows + s - 1) / s + kKnnTile - 1) / kKnnTile * kKnnTile;
+        slices[p] = (rows + slice_rows[p] - 1) / slice_rows[p];
+        total_slices += slices[p];
+    }
+    M_CUDA(m->b[0].ensure((size_t)std::max(total_slices, 1) * nq * sizeof(uint2)));
+    int slice_base = 0, row_off = 0;
+    for (int p = 0; p < nparts; p++) {
+        if (slices[p] > 0) {
+            k_knn2<<<dim3(qblocks, slices[p]), kKnnThreads, 0, m->stream>>>((const uint4 *)d_q, nq, (const uint4 *)d_parts[p], part_rows[p],
+                                                                            slice_rows[p], m->b[0].as<uint2>() + (size_t)slice_base * nq, row_off);
+            m->last_launches++;
+        }
+        slice_base += slices[p]; row_off += part_rows[p];
+    }
+    k_knn2_merge<<<(nq + 255) / 256, 256, 0, m->stream>>>(m->b[0].as<uint2>(), nq, total_slices, d_idx, d_dist);
+    m->last_launches++;
     M_CUDA(cudaGetLastError());
     return ORBX_OK;
+}
+
+static int knn2_launch(orbx_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt, int *d_idx, int *d_dist) {
+    return knn2_launch_parts(m, d_q, nq, &d_t, &nt, 1, d_idx, d_dist);
 }
 
 extern "C" {
@@ -146,6 +171,75 @@ int orbx_knn2_device(orbx_matcher *m, const uint8_t *d_query, int nq, const uint
     }
     M_CUDA(cudaEventRecord(m->ev1, m->stream));
     m->timed = true;
+    return ORBX_OK;
+}
+
+int orbx_knn2_device_parts(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *const *d_train_parts, const int *part_rows,
+                           int nparts, int *d_idx, int *d_dist) {
+    if (!m || nq < 0 || nparts < 1 || nparts > 64 || !d_train_parts || !part_rows || !d_idx || !d_dist) return fail(ORBX_ERR_INVALID, "bad arguments");
+    long long nt = 0;
+    for (int p = 0; p < nparts; p++) { if (part_rows[p] < 0 || (part_rows[p] && !d_train_parts[p])) return fail(ORBX_ERR_INVALID, "bad part"); nt += part_rows[p]; }
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    if (nq == 0) return ORBX_OK;
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    if (nt == 0) {
+        M_CUDA(cudaMemsetAsync(d_idx, 0xFF, (size_t)nq * 2 * sizeof(int), m->stream));
+        M_CUDA(cudaMemsetAsync(d_dist, 0xFF, (size_t)nq * 2 * sizeof(int), m->stream));
+    } else if (nparts == 1 || getenv("ORBX_KNN_NO_PULL")) {
+        int st = knn2_launch_parts(m, d_query, nq, d_train_parts, part_rows, nparts, d_idx, d_dist);
+        if (st != ORBX_OK) return st;
+    } else {
+        // pull the parts once into a contiguous local buffer (peer loads over NVLink, stream-ordered, no collective call),
+        // then match against the local copy: every peer row crosses the link once instead of once per query block
+        KnnParts P;
+        P.nparts = nparts; P.first_vec[0] = 0;
+        for (int p = 0; p < nparts; p++) { P.ptr[p] = (const uint4 *)d_train_parts[p]; P.first_vec[p + 1] = P.first_vec[p] + 2 * part_rows[p]; }
+        M_CUDA(m->b[2].ensure((size_t)nt * 32));
+        k_pull_parts<<<std::min(m->sm_count * 4, (P.first_vec[nparts] + 255) / 256), 256, 0, m->stream>>>(P, m->b[2].as<uint4>());
+        m->last_launches++;
+        int st = knn2_launch(m, d_query, nq, m->b[2].as<uint8_t>(), (int)nt, d_idx, d_dist);
+        if (st != ORBX_OK) return st;
+    }
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    return ORBX_OK;
+}
+
+// ---- device buffers that peer processes (one per GPU) can map: the train rows of the sharded brute-force matcher are read
+// in place over NVLink instead of being all-gathered first
+int orbx_shared_alloc(int device, size_t bytes, void **d_ptr, void *ipc_handle64) {
+    if (!d_ptr || !ipc_handle64 || bytes == 0) return fail(ORBX_ERR_INVALID, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    M_CUDA(cudaSetDevice(device));
+    M_CUDA(cudaMalloc(d_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return fail(ORBX_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(ipc_handle64, &h, 64);
+    return ORBX_OK;
+}
+int orbx_shared_open(int device, const void *ipc_handle64, void **d_ptr) {
+    if (!d_ptr || !ipc_handle64) return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, 64);
+    M_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ORBX_OK;
+}
+int orbx_shared_close(int device, void *d_ptr) {
+    M_CUDA(cudaSetDevice(device));
+    M_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return ORBX_OK;
+}
+int orbx_device_copy(int device, void *d_dst, const void *d_src, size_t bytes, void *cuda_stream) {
+    M_CUDA(cudaSetDevice(device));
+    M_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+    return ORBX_OK;
+}
+int orbx_shared_free(int device, void *d_ptr) {
+    M_CUDA(cudaSetDevice(device));
+    M_CUDA(cudaFree(d_ptr));
     return ORBX_OK;
 }
 

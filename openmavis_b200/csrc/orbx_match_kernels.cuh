@@ -31,8 +31,9 @@ __device__ __forceinline__ void top2_insert(uint32_t &k0, uint32_t &k1, uint32_t
     k0 = min(k0, k);
 }
 
+// t / nt: one part of the train set (possibly the mapped memory of a peer GPU); row_off = global index of its first row.
 __global__ void __launch_bounds__(kKnnThreads) k_knn2(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt,
-                                                      int slice_rows, uint2 *__restrict__ partial) {
+                                                      int slice_rows, uint2 *__restrict__ partial, int row_off) {
     __shared__ uint4 s_t[kKnnTile * 2];
     const int qbase = (blockIdx.x * kKnnThreads + threadIdx.x) * kKnnQPT;
     uint4 qa[kKnnQPT], qb[kKnnQPT];
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn2(const uint4 *__restrict__ 
 #pragma unroll 4
         for (int j = 0; j < rows; j++) {
             const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
-            const uint32_t jj = (uint32_t)(base + j);
+            const uint32_t jj = (uint32_t)(base + j + row_off);
 #pragma unroll
             for (int u = 0; u < kKnnQPT; u++) {
                 const uint32_t d = (uint32_t)hamming256_csa(qa[u], qb[u], ta, tb);
@@ -64,6 +65,19 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn2(const uint4 *__restrict__ 
 #pragma unroll
     for (int u = 0; u < kKnnQPT; u++)
         if (qbase + u < nq) partial[(long long)blockIdx.y * nq + qbase + u] = make_uint2(k0[u], k1[u]);
+}
+
+// Pull-style all-gather: copies the parts of a train set (local or peer-mapped pointers) into one contiguous local buffer with
+// 128-bit loads over NVLink.  3.2 MB for 100k rows: every peer row crosses the link once instead of once per query block.
+struct KnnParts { const uint4 *ptr[64]; int first_vec[65]; int nparts; };
+
+__global__ void __launch_bounds__(256) k_pull_parts(KnnParts P, uint4 *__restrict__ dst) {
+    const int total = P.first_vec[P.nparts];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int p = 0;
+        while (i >= P.first_vec[p + 1]) p++;
+        dst[i] = P.ptr[p][i - P.first_vec[p]];
+    }
 }
 
 __global__ void k_knn2_merge(const uint2 *__restrict__ partial, int nq, int nslices, int *__restrict__ idx, int *__restrict__ dist) {

@@ -266,3 +266,66 @@ def test_distinctive_descriptors(M):
     O.lib().orc_distinctive_descriptors(O.p(desc), O.p(ptr), len(sizes), O.p(ref))
     assert np.array_equal(best, ref)
     assert best[0] == -1 and best[1] == 0 and best[10] == 0
+
+
+def test_knn2_parts_equals_single_call(M):
+    """Train set given as parts (what the sharded matcher reads from peer GPUs) == one contiguous train set."""
+    import torch
+    t = synth_descriptors(5000, 21); q = synth_query_from_train(t, 22)[:1300]
+    dq = torch.from_numpy(q).cuda(); parts = [torch.from_numpy(t[a:b].copy()).cuda() for a, b in ((0, 1), (1, 1700), (1700, 1700), (1700, 5000))]
+    idx = torch.empty((1300, 2), dtype=torch.int32, device='cuda'); dd = torch.empty((1300, 2), dtype=torch.int32, device='cuda')
+    torch.cuda.synchronize()
+    M.knnMatch2_device_parts(dq.data_ptr(), 1300, [p.data_ptr() if p.numel() else 0 for p in parts], [p.shape[0] for p in parts],
+                             idx.data_ptr(), dd.data_ptr())
+    M.last_ms()                                  # synchronises on the matcher's stream
+    ridx, rdist = O.knn2(q, t)
+    assert np.array_equal(idx.cpu().numpy(), ridx) and np.array_equal(dd.cpu().numpy(), rdist)
+
+
+def _peer_worker(rank, world, port, n, out):
+    """One process per 'GPU' (all on device 0 when the box has a single GPU): publishes its train rows in a peer-mapped buffer,
+    reads everybody's rows in place, answers its own query shard."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from openmavis_b200 import shard
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        dev = rank % max(1, torch.cuda.device_count())
+        torch.cuda.set_device(dev)
+        train = synth_descriptors(n, 5); query = synth_query_from_train(train, 6)
+        lo, cnt = shard.row_shard(n, rank, world)
+        m = ob.ORBmatcher(0.8, device=dev)
+        shared = ob.SharedRows(dist, dev, n)
+        d_local = torch.from_numpy(train[lo:lo + cnt].copy()).cuda()
+        d_q = torch.from_numpy(query[lo:lo + cnt].copy()).cuda()
+        d_idx = torch.empty((cnt, 2), dtype=torch.int32, device='cuda'); d_dist = torch.empty((cnt, 2), dtype=torch.int32, device='cuda')
+        for step in range(3):                                    # exercises both buffers of the double buffer
+            shared.fill(step & 1, d_local.data_ptr(), 0)
+            torch.cuda.synchronize()
+            dist.barrier()                                       # (gloo here; bench.py uses a stream-ordered NCCL all-reduce)
+            m.knnMatch2_device_parts(d_q.data_ptr(), cnt, shared.ptrs[step & 1], shared.rows, d_idx.data_ptr(), d_dist.data_ptr())
+            m.last_ms()
+        full_idx, full_dist = shard.gather_results(d_idx.cpu().numpy(), d_dist.cpu().numpy(), n, dist)
+        if rank == 0:
+            np.savez(out, idx=full_idx, dist=full_dist)
+        torch.cuda.synchronize()
+        shared.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_knn2_over_peer_mapped_rows(tmp_path, world):
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    n, out = 3001, str(tmp_path / 'res.npz')
+    mp.spawn(_peer_worker, args=(world, port, n, out), nprocs=world, join=True)
+    got = np.load(out)
+    train = synth_descriptors(n, 5); query = synth_query_from_train(train, 6)
+    ridx, rdist = O.knn2(query, train)
+    assert np.array_equal(got['idx'], ridx) and np.array_equal(got['dist'], rdist)
