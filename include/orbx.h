@@ -95,6 +95,15 @@ int orbx_extract_batch(orbx_extractor *ex, int n_images, const uint8_t *const *i
                        const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp,
                        int *n_mono);
 
+/* Asynchronous form of orbx_extract_batch for throughput pipelines: submit enqueues the uploads, the kernels and the
+ * downloads of one batch and returns; orbx_extract_wait blocks until the outputs of the last submit are valid.  The host
+ * buffers (images, outputs) must stay valid until the wait and should be pinned, or the copies are not asynchronous.  Two handles
+ * used alternately (submit A, submit B, wait A, submit A, ...) overlap the copies of one batch with the kernels of the other. */
+int orbx_extract_batch_submit(orbx_extractor *ex, int n_images, const uint8_t *const *images, const int *strides,
+                              const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp,
+                              int *n_mono);
+int orbx_extract_wait(orbx_extractor *ex);
+
 /* Single image, reference-shaped: returns n_mono (>= 0) like operator(), or -1 for an empty image,
  * or another negative orbx_status. */
 int orbx_extract(orbx_extractor *ex, const uint8_t *image, int stride, const orbx_image_params *params,

@@ -147,6 +147,13 @@ class RigExtractor:
         """Zero-overhead variant for benchmarks: ctypes pointer array + preallocated outputs."""
         _check(self.L.orbx_extract_batch(self.h, n, ptrs, _p(strides), _p(params), _p(kps), _p(desc), self.cap, _p(nkp), _p(nmono)))
 
+    def submit_host_raw(self, ptrs, strides, params, kps, desc, nkp, nmono, n):
+        """Asynchronous extract_host_raw: returns after enqueueing; call wait() before reading the outputs."""
+        _check(self.L.orbx_extract_batch_submit(self.h, n, ptrs, _p(strides), _p(params), _p(kps), _p(desc), self.cap, _p(nkp), _p(nmono)))
+
+    def wait(self):
+        _check(self.L.orbx_extract_wait(self.h))
+
     def extract_device(self, d_images_ptr, n, params):
         """Device-resident input (n tightly packed images at device address d_images_ptr); asynchronous."""
         params = np.ascontiguousarray(params, PARAMS_DTYPE)

@@ -593,8 +593,8 @@ int orbx_extract_device_results(orbx_extractor *ex, const orbx_kp **d_kps, const
     return ORBX_OK;
 }
 
-int orbx_extract_batch(orbx_extractor *ex, int n_images, const uint8_t *const *images, const int *strides,
-                       const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono) {
+int orbx_extract_batch_submit(orbx_extractor *ex, int n_images, const uint8_t *const *images, const int *strides,
+                              const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono) {
     if (!ex || !images || !params) return fail(ORBX_ERR_INVALID, "NULL argument");
     if (n_images <= 0 || n_images > ex->max_images) return fail(ORBX_ERR_CAPACITY, "n_images exceeds the handle's max_images");
     if (cap < ex->G.out_cap && (kps || desc)) return fail(ORBX_ERR_CAPACITY, "cap smaller than orbx_extractor_capacity()");
@@ -603,10 +603,21 @@ int orbx_extract_batch(orbx_extractor *ex, int n_images, const uint8_t *const *i
         if (strides && strides[i] < ex->width) return fail(ORBX_ERR_INVALID, "stride smaller than width");
     }
     ORBX_CUDA(cudaSetDevice(ex->device));
-    int st = run_batch(ex, n_images, nullptr, images, strides, params, kps, desc, cap, n_kp, n_mono);
-    if (st != ORBX_OK) return st;
+    return run_batch(ex, n_images, nullptr, images, strides, params, kps, desc, cap, n_kp, n_mono);
+}
+
+int orbx_extract_wait(orbx_extractor *ex) {
+    if (!ex) return fail(ORBX_ERR_INVALID, "NULL handle");
+    ORBX_CUDA(cudaSetDevice(ex->device));
     ORBX_CUDA(cudaStreamSynchronize(ex->stream));
     return ORBX_OK;
+}
+
+int orbx_extract_batch(orbx_extractor *ex, int n_images, const uint8_t *const *images, const int *strides,
+                       const orbx_image_params *params, orbx_kp *kps, uint8_t *desc, int cap, int *n_kp, int *n_mono) {
+    int st = orbx_extract_batch_submit(ex, n_images, images, strides, params, kps, desc, cap, n_kp, n_mono);
+    if (st != ORBX_OK) return st;
+    return orbx_extract_wait(ex);
 }
 
 int orbx_extract(orbx_extractor *ex, const uint8_t *image, int stride, const orbx_image_params *params, orbx_kp *kps,
