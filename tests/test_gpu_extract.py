@@ -259,3 +259,22 @@ def test_compute_stereo_matches(bf):
     a.extract([left], ob.make_params(1, 1200, 20, 7, (0, 0))); b2.extract([right], ob.make_params(1, 1200, 20, 7, (0, 0)))
     n2, u2, d2 = a.compute_stereo_matches(0, 0, mb, mbf, right=b2)
     assert n2 == n and np.array_equal(u2[:N].view(np.uint32), u[:N].view(np.uint32)) and np.array_equal(d2[:N].view(np.uint32), d[:N].view(np.uint32))
+
+
+@pytest.mark.parametrize('w,h,nl,sf,nf', [(751, 479, 8, 1.2, 800), (333, 247, 5, 1.2, 500), (1000, 341, 6, 1.3, 900), (640, 480, 3, 2.0, 600)])
+def test_odd_geometries_and_pyramid_shapes(w, h, nl, sf, nf):
+    """Widths / strides that are not multiples of 4 or 16, wide aspect ratios (2-3 quadtree roots), other level counts and
+    scale factors: planes, tiles and taps are derived per handle, nothing may assume the benchmark geometry."""
+    _need_gpu()
+    img = synth_image(w, h, 9000 + w)
+    rig = ob.RigExtractor(w, h, 2, nf, sf, nl)
+    res = rig.extract([img, img[:, ::-1].copy()], ob.make_params(2, nf, 20, 7, [(0, 0), (w // 3, w // 2)]))
+    E = O.OracleExtractor(nf, sf, nl, 20, 7)
+    for b, (im, lap) in enumerate(((img, (0, 0)), (img[:, ::-1].copy(), (w // 3, w // 2)))):
+        mono, kps, desc = E(im, lap)
+        for l in range(nl):
+            assert np.array_equal(E.level(l), rig.pyramid_level(b, l, with_border=True)), (b, l)
+            xs, ys, sc = E.level_candidates(l)
+            gx, gy, gs = rig.debug_candidates(b, l)
+            assert np.array_equal(xs, gx) and np.array_equal(ys, gy) and np.array_equal(sc, gs), (b, l)
+        assert res[b][0] == mono and np.array_equal(res[b][1], kps) and np.array_equal(res[b][2], desc), b
