@@ -244,6 +244,19 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
  * median = sorted row [0.5 * (N - 1)]), -1 for an empty group.  HOST pointers. */
 int orbx_distinctive_descriptors(orbx_matcher *m, const uint8_t *desc, const int *ptr, int ngroups, int *best);
 
+/* DBoW2 vocabulary tree (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): node i has the children child[child_ptr[i] ..
+ * child_ptr[i+1]) in the order of Node::children, a 32-byte descriptor, and for leaves word_id / weight; node 0 is the root,
+ * levels = m_L.  orbx_vocabulary_transform = the per-feature descent of transform() (:1213-1259) for n descriptors: word_id[i],
+ * node_id[i] (node at level m_L - levelsup, as Frame::ComputeBoW uses it with levelsup = 4, src/Frame.cc:980-985) and, if not
+ * NULL, weight[i] of the word.  The BowVector / FeatureVector maps are then filled by the caller exactly as :1148-1160 does
+ * (addWeight / addFeature in feature order, normalize).  HOST pointers. */
+typedef struct orbx_vocabulary orbx_vocabulary;
+int orbx_vocabulary_create(orbx_vocabulary **out, int device, int n_nodes, const int *child_ptr, const int *child,
+                           const uint8_t *node_desc, const int *word_id, const double *weight, int levels);
+void orbx_vocabulary_destroy(orbx_vocabulary *v);
+int orbx_vocabulary_transform(orbx_matcher *m, const orbx_vocabulary *v, const uint8_t *desc, int n, int levelsup, int *word_id,
+                              int *node_id, double *weight);
+
 /* Launch count / device time of the matcher's last call (CUDA events on its stream). */
 int orbx_matcher_last_ms(orbx_matcher *m, float *ms);
 int orbx_matcher_last_launches(const orbx_matcher *m);

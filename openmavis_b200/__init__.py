@@ -421,6 +421,59 @@ class ORBmatcher:
         return nm.value, assigned[:N]
 
 
+class ORBVocabulary:
+    """DBoW2 TemplatedVocabulary<FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h) as flat arrays on the device; transform()
+    mirrors mpORBvocabulary->transform(features, BowVector, FeatureVector, levelsup) (src/Frame.cc:980-985)."""
+
+    def __init__(self, child_ptr, child, node_desc, word_id, weight, levels, device=0):
+        self.L = lib()
+        self.child_ptr = np.ascontiguousarray(child_ptr, np.int32); self.child = np.ascontiguousarray(child, np.int32)
+        self.node_desc = np.ascontiguousarray(node_desc, np.uint8).reshape(-1, 32)
+        self.word_id = np.ascontiguousarray(word_id, np.int32); self.weight = np.ascontiguousarray(weight, np.float64)
+        self.levels = int(levels)
+        h = C.c_void_p()
+        _check(self.L.orbx_vocabulary_create(C.byref(h), int(device), self.node_desc.shape[0], _p(self.child_ptr), _p(self.child),
+                                             _p(self.node_desc), _p(self.word_id), _p(self.weight), self.levels))
+        self.h = h
+        self.L.orbx_vocabulary_destroy.argtypes = [C.c_void_p]
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.L.orbx_vocabulary_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform(self, matcher, desc, levelsup=4):
+        """-> (BowVector as (word ids, L1-normalised tf-idf values), FeatureVector as (node ids, ptr, feature indices), word_id[n],
+        node_id[n]).  The tree descent runs on the device; the two std::map fills follow TemplatedVocabulary.h:1148-1160 in feature order."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = desc.shape[0]
+        word = np.zeros(n, np.int32); node = np.zeros(n, np.int32); w = np.zeros(n, np.float64)
+        _check(self.L.orbx_vocabulary_transform(matcher.h, self.h, _p(desc), n, int(levelsup), _p(word), _p(node), _p(w)))
+        bow = {}
+        fv = {}
+        for i in range(n):                       # v.addWeight(id, w); fv.addFeature(nid, i_feature)   (w > 0: not a stopped word)
+            if w[i] > 0:
+                bow[int(word[i])] = bow.get(int(word[i]), 0.0) + float(w[i])
+                fv.setdefault(int(node[i]), []).append(i)
+        ids = np.array(sorted(bow), np.int32)
+        vals = np.array([bow[k] for k in ids], np.float64)
+        norm = 0.0
+        for x in vals:                           # BowVector::normalize(L1): sum in key order
+            norm += abs(float(x))
+        if norm > 0.0:
+            vals = vals / norm
+        nodes = np.array(sorted(fv), np.int32)
+        ptr = np.concatenate([[0], np.cumsum([len(fv[k]) for k in nodes])]).astype(np.int32)
+        idx = np.array([i for k in nodes for i in fv[k]], np.int32)
+        return (ids, vals), (nodes, ptr, idx), word, node
+
+
 def popc_peak(device=0):
     v = C.c_double(0)
     _check(lib().orbx_popc_peak(int(device), C.byref(v)))

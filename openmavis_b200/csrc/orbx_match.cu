@@ -31,6 +31,14 @@ struct DBuf {
 };
 }  // namespace
 
+struct orbx_vocabulary {
+    int device = 0, n_nodes = 0, n_children = 0, levels = 0;
+    int *d_child_ptr = nullptr, *d_child = nullptr, *d_word = nullptr;
+    uint8_t *d_desc = nullptr;
+    std::vector<double> weight;      // per node (leaves); looked up on the host
+    std::vector<int> word;
+};
+
 struct orbx_matcher {
     int device = 0;
     int sm_count = 148;
@@ -584,6 +592,83 @@ int orbx_distinctive_descriptors(orbx_matcher *m, const uint8_t *desc, const int
     m->timed = true;
     M_CUDA(cudaMemcpyAsync(best, m->b[7].p, (size_t)ngroups * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_vocabulary_create(orbx_vocabulary **out, int device, int n_nodes, const int *child_ptr, const int *child, const uint8_t *node_desc,
+                           const int *word_id, const double *weight, int levels) {
+    if (!out || n_nodes < 1 || !child_ptr || !child || !node_desc || !word_id || !weight || levels < 1)
+        return fail(ORBX_ERR_INVALID, "bad vocabulary arguments");
+    *out = nullptr;
+    if (child_ptr[0] != 0) return fail(ORBX_ERR_INVALID, "child_ptr[0] must be 0");
+    for (int i = 0; i < n_nodes; i++)
+        if (child_ptr[i + 1] < child_ptr[i]) return fail(ORBX_ERR_INVALID, "child_ptr must be non-decreasing");
+    const int nch = child_ptr[n_nodes];
+    for (int k = 0; k < nch; k++)
+        if (child[k] <= 0 || child[k] >= n_nodes) return fail(ORBX_ERR_INVALID, "child id out of range");
+    if (child_ptr[1] == 0) return fail(ORBX_ERR_INVALID, "the root has no children");
+    const int ndev = orbx_device_count();
+    if (ndev <= 0) return fail(ORBX_ERR_NO_DEVICE, "no CUDA device (liborbx has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(ORBX_ERR_NO_DEVICE, "device index out of range");
+    M_CUDA(cudaSetDevice(device));
+    orbx_vocabulary *v = new orbx_vocabulary();
+    v->device = device; v->n_nodes = n_nodes; v->n_children = nch; v->levels = levels;
+    v->weight.assign(weight, weight + n_nodes); v->word.assign(word_id, word_id + n_nodes);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc((void **)&v->d_child_ptr, (size_t)(n_nodes + 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&v->d_child, (size_t)std::max(nch, 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&v->d_word, (size_t)n_nodes * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&v->d_desc, (size_t)n_nodes * 32);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_child_ptr, child_ptr, (size_t)(n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_child, child, (size_t)nch * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_word, word_id, (size_t)n_nodes * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->d_desc, node_desc, (size_t)n_nodes * 32, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { orbx_vocabulary_destroy(v); return fail(ORBX_ERR_CUDA, std::string("vocabulary upload: ") + cudaGetErrorString(e)); }
+    *out = v;
+    return ORBX_OK;
+}
+
+void orbx_vocabulary_destroy(orbx_vocabulary *v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaFree(v->d_child_ptr); cudaFree(v->d_child); cudaFree(v->d_word); cudaFree(v->d_desc);
+    delete v;
+}
+
+int orbx_vocabulary_transform(orbx_matcher *m, const orbx_vocabulary *v, const uint8_t *desc, int n, int levelsup, int *word_id,
+                              int *node_id, double *weight) {
+    if (!m || !v || n < 0 || !word_id || !node_id || (n && !desc)) return fail(ORBX_ERR_INVALID, "bad arguments");
+    if (m->device != v->device) return fail(ORBX_ERR_INVALID, "matcher and vocabulary live on different devices");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    if (n == 0) return ORBX_OK;
+    int st;
+    if ((st = upload(m, m->b[1], desc, (size_t)n * 32)) != ORBX_OK) return st;
+    M_CUDA(m->b[7].ensure((size_t)n * 2 * sizeof(int)));
+    int *o = m->b[7].as<int>();
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    k_vocab_transform<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, m->stream>>>(v->d_child_ptr, v->d_child, (const uint4 *)v->d_desc, v->d_word,
+                                                                                      v->levels - levelsup, (const uint4 *)m->b[1].p, n, o, o + n);
+    m->last_launches = 1;
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    M_CUDA(cudaMemcpyAsync(word_id, o, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(node_id, o + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    if (weight) {   // word id -> weight of the leaf (idf for TF_IDF vocabularies); a leaf's word id indexes m_words, keep a reverse map
+        static thread_local std::vector<int> leaf_of_word;
+        static thread_local const orbx_vocabulary *cached = nullptr;
+        if (cached != v) {
+            int maxw = -1;
+            for (int i = 0; i < v->n_nodes; i++) maxw = std::max(maxw, v->word[i]);
+            leaf_of_word.assign((size_t)maxw + 1, -1);
+            for (int i = 0; i < v->n_nodes; i++) if (v->word[i] >= 0) leaf_of_word[v->word[i]] = i;
+            cached = v;
+        }
+        for (int i = 0; i < n; i++) weight[i] = (word_id[i] >= 0 && word_id[i] < (int)leaf_of_word.size() && leaf_of_word[word_id[i]] >= 0)
+                                                    ? v->weight[leaf_of_word[word_id[i]]] : 0.0;
+    }
     return ORBX_OK;
 }
 

@@ -337,6 +337,43 @@ __global__ void __launch_bounds__(kDistWarps * 32) k_distinctive(const uint4 *__
     if (lane == 0) best[g] = best_idx;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// DBoW2 TemplatedVocabulary<FORB>::transform, per-feature tree descent
+// (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1213-1259, FORB::distance FORB.cpp:81-101).  One warp per feature: the lanes
+// take the children of the current node (k = 10 for ORBvoc), one Hamming distance each, warp arg-min with the FIRST
+// minimum winning (key = distance << 8 | position), until a leaf.  SURVEY.md §8(f) N3.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vocab_transform(const int *__restrict__ child_ptr, const int *__restrict__ child,
+                                                         const uint4 *__restrict__ node_desc, const int *__restrict__ word_id, int nid_level,
+                                                         const uint4 *__restrict__ feat, int n, int *__restrict__ out_word,
+                                                         int *__restrict__ out_node) {
+    const int lane = threadIdx.x & 31;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= n) return;
+    const uint4 qa = feat[2 * f], qb = feat[2 * f + 1];
+    int nid = 0, cur = 0, level = 0;
+    int b = child_ptr[0], e = child_ptr[1];
+    while (e > b) {
+        ++level;
+        uint32_t best = 0xFFFFFFFFu;
+        for (int k0 = b; k0 < e; k0 += 32) {          // 32 children per sweep; positions beyond 255 of a sweep cannot occur
+            const int k = k0 + lane;
+            uint32_t key = 0xFFFFFFFFu;
+            if (k < e) {
+                const int id = child[k];
+                key = ((uint32_t)hamming256(qa, qb, node_desc[2 * (long long)id], node_desc[2 * (long long)id + 1]) << 20) | (uint32_t)(k - b);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
+            best = min(best, key);                     // earlier sweeps hold smaller positions: strict first minimum overall
+        }
+        cur = child[b + (int)(best & 0xFFFFFu)];
+        if (level == nid_level) nid = cur;
+        b = child_ptr[cur]; e = child_ptr[cur + 1];
+    }
+    if (lane == 0) { out_word[f] = word_id[cur]; out_node[f] = nid; }
+}
+
 // popc.b32 issue-rate microbenchmark (roofline denominator of the matching kernels)
 __global__ void __launch_bounds__(256) k_popc_peak(uint32_t *out, int iters, uint32_t seed) {
     uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;

@@ -1088,4 +1088,63 @@ void orc_distinctive_descriptors(const uint8_t *desc, const int *ptr, int ngroup
     }
 }
 
+
+// ---- DBoW2 TemplatedVocabulary<FORB>::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259) ----------
+// Vocabulary tree as flat arrays: node i has children child[child_ptr[i] .. child_ptr[i+1]) (node ids, in the order of
+// Node::children), a 32-byte descriptor, and, for leaves (no children), word_id / weight.  Node 0 is the root.
+// Per feature (:1213-1259): descend taking the FIRST child of minimum FORB::distance (FORB.cpp:81-101 == popcount);
+// nid = node reached at level m_L - levelsup (0 if that level is <= 0 or never reached).
+void orc_vocab_transform(const int *child_ptr, const int *child, const uint8_t *node_desc, const int *word_id, int L, const uint8_t *feat,
+                         int n, int levelsup, int *out_word, int *out_node) {
+    const int nid_level = L - levelsup;
+    for (int f = 0; f < n; f++) {
+        const uint8_t *d = feat + (size_t)f * 32;
+        int nid = 0, final_id = 0, current_level = 0;
+        do {
+            ++current_level;
+            const int b = child_ptr[final_id], e = child_ptr[final_id + 1];
+            final_id = child[b];
+            double best_d = descriptor_distance(d, node_desc + (size_t)final_id * 32);
+            for (int k = b + 1; k < e; k++) {
+                const int id = child[k];
+                const double dd = descriptor_distance(d, node_desc + (size_t)id * 32);
+                if (dd < best_d) { best_d = dd; final_id = id; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (child_ptr[final_id + 1] > child_ptr[final_id]);
+        out_word[f] = word_id[final_id];
+        out_node[f] = nid;
+    }
+}
+
+// BowVector / FeatureVector of the batch transform (:1127-1193) for TF_IDF weighting + L1 scoring (the ORBvoc settings):
+// v.addWeight(id, w) in feature order, then v.normalize(L1) (BowVector.cpp:34-88); fv.addFeature(nid, i) (FeatureVector.cpp:31-45).
+// Outputs are the maps flattened in key order: bow_ids / bow_vals [return value], fv_nodes / fv_ptr / fv_idx.
+int orc_bow_from_words(const int *word, const int *node, const double *weight, int n, int *bow_ids, double *bow_vals, int *fv_nodes,
+                       int *fv_ptr, int *fv_idx, int *n_fv_nodes) {
+    std::vector<std::pair<int, double>> v;                     // sorted by id, like the std::map
+    std::vector<std::pair<int, std::vector<unsigned>>> fv;
+    for (int i = 0; i < n; i++) {
+        const double w = weight[i];
+        if (!(w > 0)) continue;                                // stopped word
+        auto it = std::lower_bound(v.begin(), v.end(), word[i], [](const std::pair<int, double> &a, int id) { return a.first < id; });
+        if (it != v.end() && it->first == word[i]) it->second += w; else v.insert(it, std::make_pair(word[i], w));
+        auto jt = std::lower_bound(fv.begin(), fv.end(), node[i], [](const std::pair<int, std::vector<unsigned>> &a, int id) { return a.first < id; });
+        if (jt == fv.end() || jt->first != node[i]) jt = fv.insert(jt, std::make_pair(node[i], std::vector<unsigned>()));
+        jt->second.push_back((unsigned)i);
+    }
+    double norm = 0.0;
+    for (auto &e : v) norm += fabs(e.second);
+    if (norm > 0.0) for (auto &e : v) e.second /= norm;
+    for (size_t k = 0; k < v.size(); k++) { bow_ids[k] = v[k].first; bow_vals[k] = v[k].second; }
+    int p = 0;
+    for (size_t k = 0; k < fv.size(); k++) {
+        fv_nodes[k] = fv[k].first; fv_ptr[k] = p;
+        for (unsigned x : fv[k].second) fv_idx[p++] = (int)x;
+    }
+    fv_ptr[fv.size()] = p;
+    *n_fv_nodes = (int)fv.size();
+    return (int)v.size();
+}
+
 }  // extern "C"

@@ -329,3 +329,57 @@ def test_sharded_knn2_over_peer_mapped_rows(tmp_path, world):
     train = synth_descriptors(n, 5); query = synth_query_from_train(train, 6)
     ridx, rdist = O.knn2(query, train)
     assert np.array_equal(got['idx'], ridx) and np.array_equal(got['dist'], rdist)
+
+
+def _synthetic_vocabulary(k, L, seed, irregular=False):
+    """Random DBoW2-shaped tree: node 0 = root, every inner node up to level L-1 has k children (or 1..k and early leaves when
+    irregular); leaves carry word ids in creation order and an idf-like weight (a few 0 = stopped words)."""
+    rng = np.random.default_rng(seed)
+    desc = [np.zeros(32, np.uint8)]; children = [[]]; level = [0]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            nk = int(rng.integers(1, k + 1)) if irregular else k
+            if irregular and lv > 1 and rng.random() < 0.15:
+                continue                                           # early leaf
+            for _ in range(nk):
+                base = desc[p] if p else rng.integers(0, 256, 32, dtype=np.uint8)
+                flips = np.packbits(rng.random(256) < (0.25 / lv), bitorder='little')
+                desc.append(base ^ flips); children.append([]); level.append(lv)
+                children[p].append(len(desc) - 1); nxt.append(len(desc) - 1)
+        frontier = nxt
+    n = len(desc)
+    child_ptr = np.concatenate([[0], np.cumsum([len(c) for c in children])]).astype(np.int32)
+    child = np.array([c for cs in children for c in cs], np.int32)
+    word = np.full(n, -1, np.int32); weight = np.zeros(n, np.float64)
+    leaves = [i for i in range(n) if not children[i]]
+    word[leaves] = np.arange(len(leaves), dtype=np.int32)
+    weight[leaves] = np.where(rng.random(len(leaves)) < 0.03, 0.0, rng.uniform(0.5, 9.0, len(leaves)))
+    return child_ptr, child, np.stack(desc), word, weight, leaves
+
+
+@pytest.mark.parametrize('k,L,irregular', [(10, 4, False), (10, 3, True), (40, 2, False), (3, 6, True)])
+def test_vocabulary_transform(M, k, L, irregular):
+    """SURVEY.md §8(f) N3: TemplatedVocabulary::transform (tree descent on the device) vs the oracle, incl. BowVector / FeatureVector."""
+    child_ptr, child, nd, word, weight, leaves = _synthetic_vocabulary(k, L, 100 + k + L, irregular)
+    rng = np.random.default_rng(5)
+    n = 1500
+    feat = nd[rng.choice(leaves, n)] ^ np.packbits(rng.random((n, 256)) < 0.08, axis=1, bitorder='little')
+    feat[::7] = synth_descriptors((n + 6) // 7, 17)                # unrelated features
+    feat[1] = feat[0]                                              # duplicates accumulate in the same word
+    voc = ob.ORBVocabulary(child_ptr, child, nd, word, weight, L)
+    levelsup = 4 if L > 4 else 1
+    (ids, vals), (nodes, ptr, idx), gw, gn = voc.transform(M, feat, levelsup)
+    rw = np.zeros(n, np.int32); rn = np.zeros(n, np.int32)
+    Lb = O.lib()
+    Lb.orc_vocab_transform(O.p(child_ptr), O.p(child), O.p(nd), O.p(word), L, O.p(feat), n, levelsup, O.p(rw), O.p(rn))
+    assert np.array_equal(gw, rw) and np.array_equal(gn, rn)
+    leaf_of_word = np.zeros(len(leaves), np.int64); leaf_of_word[word[leaves]] = leaves
+    w = weight[leaf_of_word[rw]]
+    bi = np.zeros(n, np.int32); bv = np.zeros(n, np.float64); fn = np.zeros(n, np.int32); fp = np.zeros(n + 1, np.int32); fi = np.zeros(n, np.int32)
+    nfn = C.c_int(0)
+    nb = Lb.orc_bow_from_words(O.p(rw), O.p(rn), O.p(w), n, O.p(bi), O.p(bv), O.p(fn), O.p(fp), O.p(fi), C.byref(nfn))
+    assert np.array_equal(ids, bi[:nb]) and np.array_equal(vals.view(np.uint64), bv[:nb].view(np.uint64))
+    assert np.array_equal(nodes, fn[:nfn.value]) and np.array_equal(ptr, fp[:nfn.value + 1]) and np.array_equal(idx, fi[:fp[nfn.value]])
+    assert nb >= 3
