@@ -236,17 +236,17 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
     const uint8_t *src = plane_ptr(pyr, L, b);
     // stage plane rows kYO + y0 - 3 .., plane columns kXO + x0 - 16 .. (16-byte aligned)
     const int rows_needed = min(kBlurSR, L.h + 3 - (y0 - 3));
-    __shared__ __align__(8) uint64_t s_bar;
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (threadIdx.x < 32) {   // one TMA bulk copy per source row (clipped to the plane pitch at the right edge)
+    {   // 16-byte cp.async (LDGSTS) copies of the source rows, clipped to the plane pitch at the right edge
         const int pc = kXO + x0 - 16;
-        const uint32_t row_bytes = (uint32_t)min(kBlurSP, L.pitch - pc);
+        const int nvec = min(kBlurSP, L.pitch - pc) >> 4;
         const uint8_t *g = src + (long long)(kYO + y0 - 3) * L.pitch + pc;
-        if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, row_bytes * rows_needed);
-        __syncwarp();
-        for (int r = threadIdx.x; r < rows_needed; r += 32) bulk_g2s(s_src + r * kBlurSP, g + (long long)r * L.pitch, row_bytes, &s_bar);
-        mbar_wait(&s_bar, 0);   // only the issuing warp polls the mbarrier; the others park on the hardware barrier below
+        const uint32_t d = smem_u32(s_src);
+        const int c = threadIdx.x & 15, r0 = threadIdx.x >> 4;           // 16 vector columns (10 used) x 8 rows per pass
+        if (c < nvec)
+            for (int r = r0; r < rows_needed; r += (kBlurWarps * 32) / 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + r * kBlurSP + 16 * c), "l"(g + (long long)r * L.pitch + 16 * c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
