@@ -57,6 +57,7 @@ struct orbx_extractor {
     float scale_factor = 1.2f;
     Geom G;
     BlurTiles blur_tiles;
+    BlurMaps blur_maps;
     int blur_total_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0, rsz_smem = 0;
     int rsz_rows = 0, rsz_pitch = 0;
@@ -337,6 +338,27 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
         EX_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fast_smem));
     if (ex->oct_smem > 48 * 1024)
         EX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->oct_smem));
+    {   // TMA tensor maps of the pyramid levels for the blur tiles (driver entry point through the runtime: no -lcuda)
+        memset(&ex->blur_maps, 0, sizeof(ex->blur_maps));
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        bool ok = !getenv("ORBX_NO_TMA") && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+                  qres == cudaDriverEntryPointSuccess && fn;
+        for (int l = 0; ok && l < nlevels; l++) {
+            const LevelGeom &L = G.lv[l];
+            const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)max_images};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.plane_bytes};
+            const cuuint32_t box[3] = {(cuuint32_t)kBlurSP, (cuuint32_t)kBlurSR, 1u}, estr[3] = {1u, 1u, 1u};
+            ok = ((encode_fn)fn)(&ex->blur_maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->d_pyr + L.plane_off, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        cudaGetLastError();
+        ex->blur_maps.use_tma = ok ? 1 : 0;      // otherwise the kernel stages the tile with cp.async
+    }
     EX_CUDA(cudaStreamSynchronize(ex->stream));
 #undef EX_CUDA
     *out = ex;
@@ -399,7 +421,7 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
         ORBX_CUDA(cudaEventRecord(ex->ev_pyr[lane], sA));
         ORBX_CUDA(cudaStreamWaitEvent(sB, ex->ev_pyr[lane], 0));
     }
-    k_blur<<<dim3(ex->blur_total_tiles, cnt), kBlurWarps * 32, kBlurSmem, sB>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles, i0);
+    k_blur<<<dim3(ex->blur_total_tiles, cnt), kBlurWarps * 32, kBlurSmem, sB>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles, ex->blur_maps, i0);
     launches++;
     if (sB != sA) ORBX_CUDA(cudaEventRecord(ex->ev_blur[lane], sB));
     if (ev) ORBX_CUDA(cudaEventRecord(ev[2], sA));

@@ -221,10 +221,12 @@ constexpr int kBlurSR = kBlurTH + 6;
 constexpr size_t kBlurSmem = (size_t)kBlurSP * kBlurSR;
 
 struct BlurTiles { int base[kMaxLevels + 1]; };
+// one tensor map per level over the pyramid arena: dims (pitch bytes, plane rows, images), box = the staged blur tile
+struct BlurMaps { CUtensorMap m[kMaxLevels]; int use_tma; };
 
 __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, Geom G,
-                                                          BlurTiles T, int img0) {
-    extern __shared__ __align__(16) uint8_t s_src[];   // [kBlurSR][kBlurSP]
+                                                          BlurTiles T, const __grid_constant__ BlurMaps maps, int img0) {
+    extern __shared__ __align__(128) uint8_t s_src[];   // [kBlurSR][kBlurSP]
     int lvl = 0;
     while (lvl + 1 < G.nlevels && (int)blockIdx.x >= T.base[lvl + 1]) lvl++;
     const LevelGeom &L = G.lv[lvl];
@@ -236,7 +238,17 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
     const uint8_t *src = plane_ptr(pyr, L, b);
     // stage plane rows kYO + y0 - 3 .., plane columns kXO + x0 - 16 .. (16-byte aligned)
     const int rows_needed = min(kBlurSR, L.h + 3 - (y0 - 3));
-    {   // 16-byte cp.async (LDGSTS) copies of the source rows, clipped to the plane pitch at the right edge
+    __shared__ __align__(8) uint64_t s_bar;
+    if (maps.use_tma) {
+        // ONE TMA tensor copy stages the whole 160 x 134 tile (UTMALDG); rows / columns beyond the plane are zero-filled
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)(kBlurSP * kBlurSR));
+            tma_load_3d(s_src, &maps.m[lvl], kXO + x0 - 16, kYO + y0 - 3, b, &s_bar);
+        }
+        if (threadIdx.x < 32) mbar_wait(&s_bar, 0);   // one warp polls the mbarrier; the others park on the hardware barrier below
+    } else {   // 16-byte cp.async (LDGSTS) copies of the source rows, clipped to the plane pitch at the right edge
         const int pc = kXO + x0 - 16;
         const int nvec = min(kBlurSP, L.pitch - pc) >> 4;
         const uint8_t *g = src + (long long)(kYO + y0 - 3) * L.pitch + pc;
