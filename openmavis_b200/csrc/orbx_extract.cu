@@ -58,6 +58,7 @@ struct orbx_extractor {
     Geom G;
     BlurTiles blur_tiles;
     BlurMaps blur_maps;
+    ResizeMap rsz_maps[kMaxLevels];                  // [l] = source level l - 1 of the resize that produces level l
     int blur_total_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0, rsz_smem = 0;
     int rsz_rows = 0, rsz_pitch = 0;
@@ -356,6 +357,18 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
+        bool ok2 = ok && ex->rsz_rows <= 256 && ex->rsz_pitch <= 256;
+        memset(ex->rsz_maps, 0, sizeof(ex->rsz_maps));
+        for (int l = 1; ok2 && l < nlevels; l++) {
+            const LevelGeom &L = G.lv[l - 1];
+            const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)max_images};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.plane_bytes};
+            const cuuint32_t box[3] = {(cuuint32_t)ex->rsz_pitch, (cuuint32_t)ex->rsz_rows, 1u}, estr[3] = {1u, 1u, 1u};
+            ok2 = ((encode_fn)fn)(&ex->rsz_maps[l].m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->d_pyr + L.plane_off, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        for (int l = 1; l < nlevels; l++) ex->rsz_maps[l].use_tma = ok2 ? 1 : 0;
         cudaGetLastError();
         ex->blur_maps.use_tma = ok ? 1 : 0;      // otherwise the kernel stages the tile with cp.async
     }
@@ -412,7 +425,7 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
         for (int l = 1; l < nl; l++) {
             const LevelGeom &D = G.lv[l];
             dim3 g((D.w + kRszTW - 1) / kRszTW, (D.h + kRszTH - 1) / kRszTH, cnt);
-            k_resize<<<g, kRszThreads, ex->rsz_smem, sA>>>(ex->d_pyr, G.lv[l - 1], D, ex->d_taps, ex->rsz_rows, ex->rsz_pitch, i0);
+            k_resize<<<g, kRszThreads, ex->rsz_smem, sA>>>(ex->d_pyr, G.lv[l - 1], D, ex->d_taps, ex->rsz_rows, ex->rsz_pitch, ex->rsz_maps[l], i0);
             launches++;
         }
     }

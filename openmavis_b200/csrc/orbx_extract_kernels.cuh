@@ -106,10 +106,14 @@ __device__ __forceinline__ int resize_row_mirror(int y, int h) {
     return INT_MIN;
 }
 
+// source level of one resize launch as a TMA tensor: dims (pitch bytes, plane rows, images), box = (src_pitch, src_rows, 1)
+struct ResizeMap { CUtensorMap m; int use_tma; };
+
 // grid = (tiles_x, tiles_y, images)
 __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ pyr, LevelGeom S, LevelGeom D,
-                                                        const ResizeTap *__restrict__ taps, int src_rows, int src_pitch, int img0) {
-    extern __shared__ __align__(16) uint8_t rsz_smem[];
+                                                        const ResizeTap *__restrict__ taps, int src_rows, int src_pitch,
+                                                        const __grid_constant__ ResizeMap map, int img0) {
+    extern __shared__ __align__(128) uint8_t rsz_smem[];
     uint8_t *s_src = rsz_smem;
     uint32_t *s_h = reinterpret_cast<uint32_t *>(rsz_smem + (size_t)src_rows * src_pitch);
     int4 *s_ty = reinterpret_cast<int4 *>(s_h + (size_t)src_rows * kRszTW);   // {row0 offset, row1 offset, b0 << 16, b1 << 16}
@@ -126,7 +130,18 @@ __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ py
         const ResizeTap t = tapy[tid];
         s_ty[tid] = make_int4((t.s0 - sy_lo) * kRszTW, (t.s1 - sy_lo) * kRszTW, (int)t.a0 << 16, (int)t.a1 << 16);
     }
-    {   // stage the source rows (16-byte loads; measured faster than TMA row copies for these small tiles)
+    __shared__ __align__(8) uint64_t s_bar;
+    if (map.use_tma) {
+        // ONE TMA tensor copy stages the source tile (box = src_pitch x src_rows from (sx_al, sy_lo); the part of the box beyond the
+        // rows / columns this tile needs is harmless, beyond the plane it is zero-filled)
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)(src_rows * src_pitch));
+            tma_load_3d(s_src, &map.m, kXO + sx_al, kYO + sy_lo, b, &s_bar);
+        }
+        if (tid < 32) mbar_wait(&s_bar, 0);
+    } else {   // 16-byte loads
         const uint8_t *src = plane_ptr((const uint8_t *)pyr, S, b) + (long long)(kYO + sy_lo) * S.pitch + kXO + sx_al;
         for (int c = tid & 7; c < nvec; c += 8)                 // 8 vectors (128 B) per row pass
             for (int r = tid >> 3; r < nrow; r += kRszThreads / 8)
