@@ -58,6 +58,7 @@ struct orbx_extractor {
     Geom G;
     BlurTiles blur_tiles;
     BlurMaps blur_maps;
+    FastMaps fast_maps;
     ResizeMap rsz_maps[kMaxLevels];                  // [l] = source level l - 1 of the resize that produces level l
     int blur_total_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0, rsz_smem = 0;
@@ -153,6 +154,7 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     // FAST tiles: fast_g adjacent cells of a cell row per CTA
     // entries of the survivor queue pack (row, column) into 16 bits: the staged tile must be at most 512 columns wide
     G.fast_g = std::max(1, std::min(kFastMaxG, (512 - 68) / std::max(1, max_cell_w - 6)));
+    if (const char *t = getenv("ORBX_FAST_G")) G.fast_g = std::max(1, std::min(G.fast_g, atoi(t)));   // tuning knob
     int ftiles = 0;
     for (int l = 0; l < nl; l++) {
         LevelGeom &L = G.lv[l];
@@ -357,6 +359,20 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
+        // FAST tiles are up to 512 bytes wide and a TMA box is at most 256 elements per dimension: the levels are described as
+        // tensors of 16-bit elements (x extent and coordinates in pixel pairs)
+        bool ok3 = ok && G.fast_ip / 2 <= 256 && G.fast_ymax + 6 <= 256;
+        memset(&ex->fast_maps, 0, sizeof(ex->fast_maps));
+        for (int l = 0; ok3 && l < nlevels; l++) {
+            const LevelGeom &L = G.lv[l];
+            const cuuint64_t dims[3] = {(cuuint64_t)L.pitch / 2, (cuuint64_t)L.rows, (cuuint64_t)max_images};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.plane_bytes};
+            const cuuint32_t box[3] = {(cuuint32_t)G.fast_ip / 2, (cuuint32_t)(G.fast_ymax + 6), 1u}, estr[3] = {1u, 1u, 1u};
+            ok3 = ((encode_fn)fn)(&ex->fast_maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, ex->d_pyr + L.plane_off, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        ex->fast_maps.use_tma = ok3 ? 1 : 0;
         bool ok2 = ok && ex->rsz_rows <= 256 && ex->rsz_pitch <= 256;
         memset(ex->rsz_maps, 0, sizeof(ex->rsz_maps));
         for (int l = 1; ok2 && l < nlevels; l++) {
@@ -438,7 +454,7 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
     launches++;
     if (sB != sA) ORBX_CUDA(cudaEventRecord(ex->ev_blur[lane], sB));
     if (ev) ORBX_CUDA(cudaEventRecord(ev[2], sA));
-    k_fast<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, ex->d_fast_tiles, i0);
+    k_fast<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, ex->d_fast_tiles, ex->fast_maps, i0);
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[3], sA));
     k_octree<<<dim3(cnt, nl), ex->oct_threads, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,

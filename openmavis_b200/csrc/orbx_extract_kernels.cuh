@@ -427,11 +427,14 @@ __device__ __forceinline__ void fast_nms_one(const uint8_t *sc1, uint32_t *bm, i
     }
 }
 
+// pyramid levels as TMA tensors of 16-bit elements for the FAST tiles: dims (pitch / 2, plane rows, images), box = (fast_ip / 2, fast_ymax + 6, 1)
+struct FastMaps { CUtensorMap m[kMaxLevels]; int use_tma; };
+
 __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restrict__ pyr, Geom G,
                                                        const orbx_image_params *__restrict__ params,
                                                        uint32_t *__restrict__ cells, int *__restrict__ cell_cnt,
-                                                       const int *__restrict__ tile_info, int img0) {
-    extern __shared__ __align__(16) uint8_t smem[];
+                                                       const int *__restrict__ tile_info, const __grid_constant__ FastMaps maps, int img0) {
+    extern __shared__ __align__(128) uint8_t smem[];
     const int b = blockIdx.y + img0;
     const int info = __ldg(tile_info + blockIdx.x);          // level | cell row << 4 | tile column << 16
     const LevelGeom &L = G.lv[info & 15];
@@ -465,9 +468,19 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
     const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
     __shared__ int s_qn[kFastWarps];                      // fill level of each warp's survivor queue
     int *qcnt = &s_qn[wid];
-    // 16-byte cp.async (LDGSTS) copies, in flight while the CTA clears the score map.  (Measured: one TMA bulk copy per
-    // tile row is slower here — ~190 small requests per tile time saturate the SM's TMA unit.)
-    if (lane < nvec) {
+    __shared__ __align__(8) uint64_t s_bar;
+    if (maps.use_tma) {
+        // ONE TMA tensor copy stages the tile (box = fast_ip x (fast_ymax + 6) from plane column pc0, row kYO + ty0 - 3; what lies
+        // beyond the columns / rows this tile needs is harmless), in flight while the CTA clears the score map
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)(ip * (G.fast_ymax + 6)));
+            tma_load_3d(img, &maps.m[info & 15], pc0 >> 1, kYO + ty0 - 3, b, &s_bar);   // x in 16-bit elements
+        }
+    } else if (lane < nvec) {
+        // 16-byte cp.async (LDGSTS) copies.  (One TMA bulk copy per tile ROW was measured slower than this: ~190 small requests
+        // per tile time saturate the SM's TMA unit; one tensor copy per TILE is faster than both.)
         const uint8_t *src = plane_ptr(pyr, L, b) + (long long)(kYO + ty0 - 3) * L.pitch + pc0 + 16 * lane;
         const uint32_t dst = smem_u32(img) + 16 * lane;
         for (int r = wid; r < Y + 6; r += kFastWarps)
@@ -483,6 +496,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restr
         if (lane == 0) s_qn[wid] = 0;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (maps.use_tma && tid < 32) mbar_wait(&s_bar, 0);
     __syncthreads();
     const orbx_image_params prm = params[b];
     const int t_ini = min(max(prm.ini_th_fast, 0), 255), t_min = min(max(prm.min_th_fast, 0), 255);
