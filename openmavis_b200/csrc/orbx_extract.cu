@@ -59,6 +59,8 @@ struct orbx_extractor {
     BlurTiles blur_tiles;
     BlurMaps blur_maps;
     FastMaps fast_maps;
+    PatchMaps patch_maps;
+    PatchMaps *d_patch_maps = nullptr;
     ResizeMap rsz_maps[kMaxLevels];                  // [l] = source level l - 1 of the resize that produces level l
     int blur_total_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0, rsz_smem = 0;
@@ -208,7 +210,7 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     cudaFree(ex->d_pattern); cudaFree(ex->d_cells); cudaFree(ex->d_lin); cudaFree(ex->d_lvl_kp); cudaFree(ex->d_node);
     cudaFree(ex->d_cell_cnt); cudaFree(ex->d_cell_off); cudaFree(ex->d_lin_n); cudaFree(ex->d_lvl_n); cudaFree(ex->d_slot);
     cudaFree(ex->d_n_kp); cudaFree(ex->d_n_mono); cudaFree(ex->d_nfeat); cudaFree(ex->d_lvl_angle); cudaFree(ex->d_out_kp);
-    cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles);
+    cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps);
     cudaFree(ex->d_st_uright); cudaFree(ex->d_st_depth); cudaFree(ex->d_st_sad); cudaFree(ex->d_st_kept);
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_params) cudaFreeHost(ex->h_params);
@@ -373,6 +375,24 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
         ex->fast_maps.use_tma = ok3 ? 1 : 0;
+        bool ok4 = ok;
+        memset(&ex->patch_maps, 0, sizeof(ex->patch_maps));
+        for (int l = 0; ok4 && l < nlevels; l++) {
+            const LevelGeom &L = G.lv[l];
+            const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)max_images};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.plane_bytes};
+            const cuuint32_t estr[3] = {1u, 1u, 1u};
+            const cuuint32_t box_o[3] = {(cuuint32_t)kOriW, (cuuint32_t)kOriH, 1u}, box_d[3] = {(cuuint32_t)kDescW, (cuuint32_t)kDescH, 1u};
+            ok4 = ((encode_fn)fn)(&ex->patch_maps.pyr[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->d_pyr + L.plane_off, dims, strides, box_o, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                  ((encode_fn)fn)(&ex->patch_maps.blur[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->d_blur + L.plane_off, dims, strides, box_d, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        ex->patch_maps.use_tma = (ok4 && !getenv("ORBX_NO_PATCH_TMA")) ? 1 : 0;
+        EX_CUDA(cudaMalloc((void **)&ex->d_patch_maps, sizeof(PatchMaps)));
+        EX_CUDA(cudaMemcpy(ex->d_patch_maps, &ex->patch_maps, sizeof(PatchMaps), cudaMemcpyHostToDevice));
         bool ok2 = ok && ex->rsz_rows <= 256 && ex->rsz_pitch <= 256;
         memset(ex->rsz_maps, 0, sizeof(ex->rsz_maps));
         for (int l = 1; ok2 && l < nlevels; l++) {
@@ -470,10 +490,10 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
         const dim3 grid((G.kp_per_image * 32 + 255) / 256, cnt);
         if (G.fma_mode)
             k_orient_desc<true><<<grid, 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,
-                                                      ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, i0);
+                                                      ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, ex->d_patch_maps, i0);
         else
             k_orient_desc<false><<<grid, 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,
-                                                       ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, i0);
+                                                       ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, ex->d_patch_maps, i0);
     }
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[6], sA));

@@ -780,13 +780,23 @@ __global__ void __launch_bounds__(256) k_slots(Geom G, const orbx_image_params *
 // Orientation: lane = column u of the 31-wide patch, loop over the 31 rows; int32 moments reduced with
 // shuffles (order-independent, exact).  Descriptor: lane = output byte, 16 rotated samples per lane.
 // ------------------------------------------------------------------------------------------------------
+// TMA tensor maps of the pyramid / blurred-pyramid levels with per-keypoint boxes: 32 x 31 (orientation patch) and 48 x 37
+// (descriptor reach +-18) bytes.  The x coordinate of a box is rounded down to 16 bytes (a misaligned inner coordinate raised an
+// illegal-instruction fault on B200), the remainder is added to the column index inside the staged patch.
+struct PatchMaps { CUtensorMap pyr[kMaxLevels], blur[kMaxLevels]; int use_tma; };
+constexpr int kOriW = 48, kOriH = 31, kDescW = 64, kDescH = 37;   // widths include up to 15 columns of 16-byte alignment slack
+constexpr int kOriBytes = kOriW * kOriH, kDescBytes = kDescW * kDescH;
+constexpr int kPatchStride = ((kOriBytes + 127) & ~127) + ((kDescBytes + 127) & ~127);      // per warp, 128-byte aligned parts
+
 template <bool kFma>
 __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, Geom G,
                                                      const signed char *__restrict__ pattern, const uint32_t *__restrict__ lvl_kp,
                                                      const int *__restrict__ lvl_n, const int *__restrict__ slot,
                                                      float *__restrict__ lvl_angle, orbx_kp *__restrict__ out_kp,
-                                                     uint8_t *__restrict__ out_desc, int img0) {
-    const int lane = threadIdx.x & 31;
+                                                     uint8_t *__restrict__ out_desc, const PatchMaps *__restrict__ maps, int img0) {
+    __shared__ __align__(128) uint8_t s_patch[8 * kPatchStride];
+    __shared__ __align__(8) uint64_t s_bar[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int b = blockIdx.y + img0;
     if (warp >= G.kp_per_image) return;
@@ -797,21 +807,45 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
     if (i >= lvl_n[b * G.nlevels + lvl]) return;
     const uint32_t kp = lvl_kp[(long long)b * G.kp_per_image + warp];
     const int x = cand_x(kp), y = cand_y(kp);
+    uint8_t *op = s_patch + wid * kPatchStride;                 // rows y-15..y+15, columns from (x-16) & ~15 of the level
+    uint8_t *dp = op + ((kOriBytes + 127) & ~127);              // rows y-18..y+18, columns from (x-24) & ~15 of the blurred level
+    const bool tma = maps->use_tma != 0;     // (the maps live in global memory: as kernel parameters they would push the
+                                             //  parameter block beyond 4 KB)
+    if (tma) {   // the warp fetches its two patches with two TMA tensor copies and waits on its own mbarrier
+        if (lane == 0) {
+            mbar_init(&s_bar[wid], 1);
+            mbar_arrive_expect_tx(&s_bar[wid], (uint32_t)(kOriBytes + kDescBytes));
+            tma_load_3d(op, &maps->pyr[lvl], (kXO + x - 16) & ~15, kYO + y - kHalfPatch, b, &s_bar[wid]);
+            tma_load_3d(dp, &maps->blur[lvl], (kXO + x - 24) & ~15, kYO + y - 18, b, &s_bar[wid]);
+        }
+        __syncwarp();
+        mbar_wait(&s_bar[wid], 0);
+    }
     // ---- orientation: lane = column u of the patch; the lane's column sum gives m10, the row-weighted sum m01
     const int u = lane - kHalfPatch;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int au = u < 0 ? -u : u;
         constexpr int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // src/ORBextractor.cc:399-413
-        const uint8_t *p = plane_ptr(pyr, L, b) + (long long)(kYO + y - kHalfPatch) * L.pitch + kXO + x + u;
         int colsum = 0;
+        if (tma) {
+            const uint8_t *p = op + ((kXO + x - 16) & 15) + lane + 1;   // column x + u of the staged patch
 #pragma unroll
-        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {   // fully unrolled: 31 independent loads in flight
-            if (au <= umax[v < 0 ? -v : v]) {
-                const int val = __ldg(p);
-                colsum += val; m01 += v * val;
+            for (int v = -kHalfPatch; v <= kHalfPatch; v++)
+                if (au <= umax[v < 0 ? -v : v]) {
+                    const int val = p[(v + kHalfPatch) * kOriW];
+                    colsum += val; m01 += v * val;
+                }
+        } else {
+            const uint8_t *p = plane_ptr(pyr, L, b) + (long long)(kYO + y - kHalfPatch) * L.pitch + kXO + x + u;
+#pragma unroll
+            for (int v = -kHalfPatch; v <= kHalfPatch; v++) {   // fully unrolled: 31 independent loads in flight
+                if (au <= umax[v < 0 ? -v : v]) {
+                    const int val = __ldg(p);
+                    colsum += val; m01 += v * val;
+                }
+                p += L.pitch;
             }
-            p += L.pitch;
         }
         m10 = u * colsum;
     }
@@ -822,10 +856,10 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
     const float rad = __fmul_rn(angle, 0.0174532924f);   // (float)(CV_PI/180.f)
     float sn, cs;
     orbx_sincosf(rad, &sn, &cs);
-    const uint8_t *cb = plane_ptr(blur, L, b) + (long long)(kYO + y) * L.pitch + kXO + x;
     const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(pattern) + 2 * lane), pb = __ldg(reinterpret_cast<const uint4 *>(pattern) + 2 * lane + 1);
     const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};   // word k = (x0, y0, x1, y1) of test k
-    const int pitch = L.pitch;
+    const uint8_t *cb = tma ? dp + 18 * kDescW + 24 + ((kXO + x - 24) & 15) : plane_ptr(blur, L, b) + (long long)(kYO + y) * L.pitch + kXO + x;
+    const int pitch = tma ? kDescW : L.pitch;
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -836,7 +870,7 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
             float fy, fx;
             if (kFma) { fy = __fmaf_rn(px, sn, __fmul_rn(py, cs)); fx = __fmaf_rn(px, cs, -__fmul_rn(py, sn)); }
             else { fy = __fadd_rn(__fmul_rn(px, sn), __fmul_rn(py, cs)); fx = __fsub_rn(__fmul_rn(px, cs), __fmul_rn(py, sn)); }
-            tv[e] = __ldg(cb + (__float2int_rn(fy) * pitch + __float2int_rn(fx)));
+            tv[e] = cb[__float2int_rn(fy) * pitch + __float2int_rn(fx)];
         }
         val |= (tv[0] < tv[1] ? 1 : 0) << k;
     }
