@@ -92,7 +92,8 @@ struct orbx_extractor {
     uint32_t *d_cells = nullptr, *d_lin = nullptr, *d_lvl_kp = nullptr;
     unsigned short *d_node = nullptr;
     int *d_cell_cnt = nullptr, *d_cell_off = nullptr, *d_lin_n = nullptr, *d_lvl_n = nullptr, *d_slot = nullptr;
-    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr, *d_fast_tiles = nullptr;
+    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr, *d_fast_tiles = nullptr, *d_desc_blocks = nullptr;
+    int desc_blocks = 0;
     float *d_lvl_angle = nullptr;
     orbx_kp *d_out_kp = nullptr;
     orbx_image_params *d_params = nullptr;
@@ -210,7 +211,7 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     cudaFree(ex->d_pattern); cudaFree(ex->d_cells); cudaFree(ex->d_lin); cudaFree(ex->d_lvl_kp); cudaFree(ex->d_node);
     cudaFree(ex->d_cell_cnt); cudaFree(ex->d_cell_off); cudaFree(ex->d_lin_n); cudaFree(ex->d_lvl_n); cudaFree(ex->d_slot);
     cudaFree(ex->d_n_kp); cudaFree(ex->d_n_mono); cudaFree(ex->d_nfeat); cudaFree(ex->d_lvl_angle); cudaFree(ex->d_out_kp);
-    cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps);
+    cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps); cudaFree(ex->d_desc_blocks);
     cudaFree(ex->d_st_uright); cudaFree(ex->d_st_depth); cudaFree(ex->d_st_sad); cudaFree(ex->d_st_kept);
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_params) cudaFreeHost(ex->h_params);
@@ -335,6 +336,12 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
                 for (int j = 0; j < G.lv[l].fast_tiles_x; j++) tinfo.push_back(l | (i << 4) | (j << 16));
         EX_CUDA(dalloc(&ex->d_fast_tiles, tinfo.size()));
         EX_CUDA(cudaMemcpy(ex->d_fast_tiles, tinfo.data(), tinfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<int> binfo;   // orientation / descriptor CTA -> level | first keypoint slot << 4  (8 slots per CTA)
+        for (int l = 0; l < nlevels; l++)
+            for (int i0 = 0; i0 < G.lv[l].kp_cap; i0 += 8) binfo.push_back(l | (i0 << 4));
+        ex->desc_blocks = (int)binfo.size();
+        EX_CUDA(dalloc(&ex->d_desc_blocks, binfo.size()));
+        EX_CUDA(cudaMemcpy(ex->d_desc_blocks, binfo.data(), binfo.size() * sizeof(int), cudaMemcpyHostToDevice));
         static const signed char pat[1024] = {ORBX_PATTERN_VALUES};
         EX_CUDA(dalloc(&ex->d_pattern, (size_t)1024));
         EX_CUDA(cudaMemcpy(ex->d_pattern, pat, 1024, cudaMemcpyHostToDevice));
@@ -487,13 +494,14 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
     if (ev) ORBX_CUDA(cudaEventRecord(ev[5], sA));
     if (sB != sA) ORBX_CUDA(cudaStreamWaitEvent(sA, ex->ev_blur[lane], 0));
     {
-        const dim3 grid((G.kp_per_image * 32 + 255) / 256, cnt);
-        if (G.fma_mode)
-            k_orient_desc<true><<<grid, 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,
-                                                      ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, ex->d_patch_maps, i0);
-        else
-            k_orient_desc<false><<<grid, 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,
-                                                       ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, ex->d_patch_maps, i0);
+        const dim3 grid(ex->desc_blocks, cnt);
+#define ORBX_LAUNCH_DESC(FMA, TMA)                                                                                             \
+    k_orient_desc<FMA, TMA><<<grid, 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot, \
+                                                  ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, ex->d_patch_maps, ex->d_desc_blocks, i0)
+        const bool tma = ex->patch_maps.use_tma != 0;
+        if (G.fma_mode) { if (tma) ORBX_LAUNCH_DESC(true, true); else ORBX_LAUNCH_DESC(true, false); }
+        else { if (tma) ORBX_LAUNCH_DESC(false, true); else ORBX_LAUNCH_DESC(false, false); }
+#undef ORBX_LAUNCH_DESC
     }
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[6], sA));

@@ -788,28 +788,29 @@ constexpr int kOriW = 48, kOriH = 31, kDescW = 64, kDescH = 37;   // widths incl
 constexpr int kOriBytes = kOriW * kOriH, kDescBytes = kDescW * kDescH;
 constexpr int kPatchStride = ((kOriBytes + 127) & ~127) + ((kDescBytes + 127) & ~127);      // per warp, 128-byte aligned parts
 
-template <bool kFma>
+// grid.x enumerates CTAs of 8 keypoint slots; a CTA belongs to one level: block_info[blockIdx.x] = level | first slot << 4
+template <bool kFma, bool kTma>
 __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, Geom G,
                                                      const signed char *__restrict__ pattern, const uint32_t *__restrict__ lvl_kp,
                                                      const int *__restrict__ lvl_n, const int *__restrict__ slot,
                                                      float *__restrict__ lvl_angle, orbx_kp *__restrict__ out_kp,
-                                                     uint8_t *__restrict__ out_desc, const PatchMaps *__restrict__ maps, int img0) {
-    __shared__ __align__(128) uint8_t s_patch[8 * kPatchStride];
+                                                     uint8_t *__restrict__ out_desc, const PatchMaps *__restrict__ maps,
+                                                     const int *__restrict__ block_info, int img0) {
+    __shared__ __align__(128) uint8_t s_patch[kTma ? 8 * kPatchStride : 128];
     __shared__ __align__(8) uint64_t s_bar[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int b = blockIdx.y + img0;
-    if (warp >= G.kp_per_image) return;
-    int lvl = 0;
-    while (lvl + 1 < G.nlevels && warp >= G.lv[lvl + 1].kp_off) lvl++;
+    const int info = __ldg(block_info + blockIdx.x);
+    const int lvl = info & 15;
     const LevelGeom &L = G.lv[lvl];
-    const int i = warp - L.kp_off;
+    const int i = (info >> 4) + wid;
+    const int warp = L.kp_off + i;                              // slot of this keypoint in the per-image level arena
     if (i >= lvl_n[b * G.nlevels + lvl]) return;
     const uint32_t kp = lvl_kp[(long long)b * G.kp_per_image + warp];
     const int x = cand_x(kp), y = cand_y(kp);
     uint8_t *op = s_patch + wid * kPatchStride;                 // rows y-15..y+15, columns from (x-16) & ~15 of the level
     uint8_t *dp = op + ((kOriBytes + 127) & ~127);              // rows y-18..y+18, columns from (x-24) & ~15 of the blurred level
-    const bool tma = maps->use_tma != 0;     // (the maps live in global memory: as kernel parameters they would push the
+    constexpr bool tma = kTma;               // (the maps live in global memory: as kernel parameters they would push the
                                              //  parameter block beyond 4 KB)
     if (tma) {   // the warp fetches its two patches with two TMA tensor copies and waits on its own mbarrier
         if (lane == 0) {
