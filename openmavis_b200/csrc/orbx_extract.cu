@@ -92,7 +92,7 @@ struct orbx_extractor {
     uint32_t *d_cells = nullptr, *d_lin = nullptr, *d_lvl_kp = nullptr;
     unsigned short *d_node = nullptr;
     int *d_cell_cnt = nullptr, *d_cell_off = nullptr, *d_lin_n = nullptr, *d_lvl_n = nullptr, *d_slot = nullptr;
-    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr, *d_fast_tiles = nullptr, *d_desc_blocks = nullptr;
+    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr, *d_fast_tiles = nullptr, *d_desc_blocks = nullptr, *d_blur_tiles = nullptr;
     int desc_blocks = 0;
     float *d_lvl_angle = nullptr;
     orbx_kp *d_out_kp = nullptr;
@@ -211,7 +211,7 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     cudaFree(ex->d_pattern); cudaFree(ex->d_cells); cudaFree(ex->d_lin); cudaFree(ex->d_lvl_kp); cudaFree(ex->d_node);
     cudaFree(ex->d_cell_cnt); cudaFree(ex->d_cell_off); cudaFree(ex->d_lin_n); cudaFree(ex->d_lvl_n); cudaFree(ex->d_slot);
     cudaFree(ex->d_n_kp); cudaFree(ex->d_n_mono); cudaFree(ex->d_nfeat); cudaFree(ex->d_lvl_angle); cudaFree(ex->d_out_kp);
-    cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps); cudaFree(ex->d_desc_blocks);
+    cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps); cudaFree(ex->d_desc_blocks); cudaFree(ex->d_blur_tiles);
     cudaFree(ex->d_st_uright); cudaFree(ex->d_st_depth); cudaFree(ex->d_st_sad); cudaFree(ex->d_st_kept);
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_params) cudaFreeHost(ex->h_params);
@@ -336,6 +336,13 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
                 for (int j = 0; j < G.lv[l].fast_tiles_x; j++) tinfo.push_back(l | (i << 4) | (j << 16));
         EX_CUDA(dalloc(&ex->d_fast_tiles, tinfo.size()));
         EX_CUDA(cudaMemcpy(ex->d_fast_tiles, tinfo.data(), tinfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<int> btiles;   // blur CTA -> level | tile row << 4 | tile column << 16
+        for (int l = 0; l < nlevels; l++)
+            for (int ty = 0; ty < (G.lv[l].h + kBlurTH - 1) / kBlurTH; ty++)
+                for (int tx = 0; tx < (G.lv[l].w + kBlurTW - 1) / kBlurTW; tx++) btiles.push_back(l | (ty << 4) | (tx << 16));
+        if ((int)btiles.size() != ex->blur_total_tiles) { orbx_extractor_destroy(ex); return fail(ORBX_ERR_INVALID, "internal: blur tile count"); }
+        EX_CUDA(dalloc(&ex->d_blur_tiles, btiles.size()));
+        EX_CUDA(cudaMemcpy(ex->d_blur_tiles, btiles.data(), btiles.size() * sizeof(int), cudaMemcpyHostToDevice));
         std::vector<int> binfo;   // orientation / descriptor CTA -> level | first keypoint slot << 4  (8 slots per CTA)
         for (int l = 0; l < nlevels; l++)
             for (int i0 = 0; i0 < G.lv[l].kp_cap; i0 += 8) binfo.push_back(l | (i0 << 4));
@@ -477,7 +484,7 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
         ORBX_CUDA(cudaEventRecord(ex->ev_pyr[lane], sA));
         ORBX_CUDA(cudaStreamWaitEvent(sB, ex->ev_pyr[lane], 0));
     }
-    k_blur<<<dim3(ex->blur_total_tiles, cnt), kBlurWarps * 32, kBlurSmem, sB>>>(ex->d_pyr, ex->d_blur, G, ex->blur_tiles, ex->blur_maps, i0);
+    k_blur<<<dim3(ex->blur_total_tiles, cnt), kBlurWarps * 32, kBlurSmem, sB>>>(ex->d_pyr, ex->d_blur, G, ex->d_blur_tiles, ex->blur_maps, i0);
     launches++;
     if (sB != sA) ORBX_CUDA(cudaEventRecord(ex->ev_blur[lane], sB));
     if (ev) ORBX_CUDA(cudaEventRecord(ev[2], sA));

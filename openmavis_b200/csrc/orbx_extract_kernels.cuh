@@ -240,15 +240,12 @@ struct BlurTiles { int base[kMaxLevels + 1]; };
 struct BlurMaps { CUtensorMap m[kMaxLevels]; int use_tma; };
 
 __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, Geom G,
-                                                          BlurTiles T, const __grid_constant__ BlurMaps maps, int img0) {
+                                                          const int *__restrict__ tile_info, const __grid_constant__ BlurMaps maps, int img0) {
     extern __shared__ __align__(128) uint8_t s_src[];   // [kBlurSR][kBlurSP]
-    int lvl = 0;
-    while (lvl + 1 < G.nlevels && (int)blockIdx.x >= T.base[lvl + 1]) lvl++;
+    const int info = __ldg(tile_info + blockIdx.x);            // level | tile row << 4 | tile column << 16
+    const int lvl = info & 15;
     const LevelGeom &L = G.lv[lvl];
-    const int tiles_x = (L.w + kBlurTW - 1) / kBlurTW;
-    const int t = blockIdx.x - T.base[lvl];
-    const int ty = t / tiles_x, tx = t - ty * tiles_x;
-    const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
+    const int x0 = (info >> 16) * kBlurTW, y0 = ((info >> 4) & 0xFFF) * kBlurTH;
     const int b = blockIdx.y + img0;
     const uint8_t *src = plane_ptr(pyr, L, b);
     // stage plane rows kYO + y0 - 3 .., plane columns kXO + x0 - 16 .. (16-byte aligned)
