@@ -174,6 +174,7 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     ex->oct_list_cap = max_list;
     ex->oct_smem = oct_work_bytes(max_list);
     if (ex->oct_smem > 200 * 1024) return fail(ORBX_ERR_INVALID, "nfeatures too large for the quadtree workspace");
+    if (const char *t = getenv("ORBX_OCT_SMEM_KB")) ex->oct_smem = std::max(ex->oct_smem, (size_t)atoi(t) * 1024);   // tuning knob: caps CTAs per SM
     int tiles = 0;
     for (int l = 0; l < nl; l++) {
         ex->blur_tiles.base[l] = tiles;
@@ -480,16 +481,24 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
         }
     }
     if (ev) ORBX_CUDA(cudaEventRecord(ev[1], sA));
-    if (sB != sA) {
-        ORBX_CUDA(cudaEventRecord(ex->ev_pyr[lane], sA));
-        ORBX_CUDA(cudaStreamWaitEvent(sB, ex->ev_pyr[lane], 0));
+    // The blur only needs the pyramid.  With overlapping lanes it runs on the aux stream NEXT TO THE QUADTREE (launched after FAST):
+    // the quadtree is latency-bound (about a fifth of the issue slots busy), the blur is issue-bound, so they share the SMs well;
+    // FAST and the blur would only compete for the same issue slots.
+    const bool overlap = sB != sA;
+    if (!overlap) {
+        k_blur<<<dim3(ex->blur_total_tiles, cnt), kBlurWarps * 32, kBlurSmem, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_blur_tiles, ex->blur_maps, i0);
+        launches++;
     }
-    k_blur<<<dim3(ex->blur_total_tiles, cnt), kBlurWarps * 32, kBlurSmem, sB>>>(ex->d_pyr, ex->d_blur, G, ex->d_blur_tiles, ex->blur_maps, i0);
-    launches++;
-    if (sB != sA) ORBX_CUDA(cudaEventRecord(ex->ev_blur[lane], sB));
     if (ev) ORBX_CUDA(cudaEventRecord(ev[2], sA));
     k_fast<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, ex->d_fast_tiles, ex->fast_maps, i0);
     launches++;
+    if (overlap) {
+        ORBX_CUDA(cudaEventRecord(ex->ev_pyr[lane], sA));                 // (FAST done)
+        ORBX_CUDA(cudaStreamWaitEvent(sB, ex->ev_pyr[lane], 0));
+        k_blur<<<dim3(ex->blur_total_tiles, cnt), kBlurWarps * 32, kBlurSmem, sB>>>(ex->d_pyr, ex->d_blur, G, ex->d_blur_tiles, ex->blur_maps, i0);
+        launches++;
+        ORBX_CUDA(cudaEventRecord(ex->ev_blur[lane], sB));
+    }
     if (ev) ORBX_CUDA(cudaEventRecord(ev[3], sA));
     k_octree<<<dim3(cnt, nl), ex->oct_threads, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
                                                                    ex->d_lin_n, ex->d_node, ex->d_slot, ex->d_lvl_kp, ex->d_lvl_n,
