@@ -278,3 +278,18 @@ def test_odd_geometries_and_pyramid_shapes(w, h, nl, sf, nf):
             gx, gy, gs = rig.debug_candidates(b, l)
             assert np.array_equal(xs, gx) and np.array_equal(ys, gy) and np.array_equal(sc, gs), (b, l)
         assert res[b][0] == mono and np.array_equal(res[b][1], kps) and np.array_equal(res[b][2], desc), b
+
+
+def test_staging_fallback_paths_without_tma(monkeypatch):
+    """The tiled kernels stage through TMA tensor copies when the driver provides cuTensorMapEncodeTiled and through cp.async /
+    vector loads otherwise (or for geometries wider than a TMA box): both paths must give the same bits."""
+    _need_gpu()
+    img = synth_image(720, 540, 8123)
+    p = ob.make_params(1, 1500, 20, 7, (0, 720))
+    a = ob.RigExtractor(720, 540, 1, 1500).extract([img], p)[0]
+    monkeypatch.setenv('ORBX_NO_TMA', '1')
+    monkeypatch.setenv('ORBX_NO_PATCH_TMA', '1')
+    rig = ob.RigExtractor(720, 540, 1, 1500)                     # the knobs are read when the handle is created
+    b = rig.extract([img], p)[0]
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    compare_image(rig, 0, img, 1500, 20, 7, (0, 720), b)
