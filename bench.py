@@ -387,12 +387,28 @@ def main():
         d_idx = torch.empty((hi - lo, 2), dtype=torch.int32, device=dev)
         d_dist = torch.empty((hi - lo, 2), dtype=torch.int32, device=dev)
 
-        shared = ob.SharedRows(dist, local, n) if world > 1 else None
+        shared = None
+        if world > 1:
+            ok = 1
+            try:
+                shared = ob.SharedRows(dist, local, n)
+            except Exception as ex:                      # e.g. CUDA IPC not permitted in this container
+                ok = 0
+                print('rank %d: peer mapping failed (%s); falling back to an NCCL all-gather' % (rank, ex), file=sys.stderr)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if shared is not None:
+                    shared.close(barrier=False)
+                shared = None
         token = torch.zeros(1, device=dev)
         step_no = [0]
 
         def knn_step():
-            if world > 1:
+            if world > 1 and shared is None:   # fallback: one NCCL all-gather of the train rows, then the local 2-NN
+                d_t = shard.gather_train_rows(d_local_train, n, dist)
+                m.knnMatch2_device(d_q.data_ptr(), hi - lo, d_t.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
+            elif world > 1:
                 # The one real exchange step, fused with the compute: every rank publishes its train rows in a peer-mapped
                 # buffer and each rank's 2-NN kernels read all parts in place over NVLink (no all-gather, no staging copy);
                 # one tiny all-reduce per step is the stream-ordered barrier (see openmavis_b200.SharedRows).
@@ -418,7 +434,7 @@ def main():
         matching = {'metric': 'Hamming matches/sec (brute-force 2-NN %dx%d)' % (n, n), 'value': pairs / (ms_knn * 1e-3), 'unit': 'pairs/s',
                     'ms': ms_knn, 'popc_gops_achieved': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world, 'popc_gops_peak_measured': popc,
                     'frac_of_popc_peak': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world / popc, 'n_gpus': world,
-                    'collective': 'none for the data: peer-mapped train rows read in place over NVLink (cudaIpc); one 4-byte all-reduce per step as barrier' if world > 1 else None}
+                    'collective': None if world == 1 else ('none for the data: peer-mapped train rows pulled over NVLink (cudaIpc); one 4-byte all-reduce per step as barrier' if shared is not None else 'nccl all_gather of the train rows (peer mapping unavailable)')}
         if rank == 0:
             torch.cuda.set_stream(torch.cuda.default_stream(dev))
             matching['guided'] = guided_matchers(ob, local)

@@ -500,32 +500,39 @@ class SharedRows:
         self.L.orbx_shared_free.argtypes = [C.c_int, C.c_void_p]
         self.L.orbx_device_copy.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         self.own, self.ptrs = [], []
+        # collectives first (allocation + handle exchange), then the purely local peer mappings: a rank whose mapping fails has
+        # no collective left to skip, so the caller can agree on a fallback with one more all-reduce
+        handles = []
         for _ in range(2):
             own, handle = C.c_void_p(), C.create_string_buffer(64)
             _check(self.L.orbx_shared_alloc(self.device, max(self.rows[self.rank], 1) * 32, C.byref(own), handle))
-            handles = [None] * self.world
-            dist.all_gather_object(handles, handle.raw)
+            self.own.append(own.value)
+            got = [None] * self.world
+            dist.all_gather_object(got, handle.raw)
+            handles.append(got)
+        for buf in range(2):
             ptrs = []
             for r in range(self.world):
                 if r == self.rank:
-                    ptrs.append(own.value)
+                    ptrs.append(self.own[buf])
                 else:
                     q = C.c_void_p()
-                    _check(self.L.orbx_shared_open(self.device, handles[r], C.byref(q)))
+                    _check(self.L.orbx_shared_open(self.device, handles[buf][r], C.byref(q)))
                     ptrs.append(q.value)
-            self.own.append(own.value); self.ptrs.append(ptrs)
+            self.ptrs.append(ptrs)
 
     def fill(self, buf, d_local_rows_ptr, cuda_stream):
         """Copies this rank's rows (device pointer) into its shared buffer `buf` on `cuda_stream`."""
         _check(self.L.orbx_device_copy(self.device, C.c_void_p(self.own[buf]), C.c_void_p(d_local_rows_ptr), self.rows[self.rank] * 32,
                                        C.c_void_p(cuda_stream)))
 
-    def close(self):
+    def close(self, barrier=True):
         for buf in range(len(self.ptrs)):
             for r, q in enumerate(self.ptrs[buf]):
                 if r != self.rank and q:
                     self.L.orbx_shared_close(self.device, C.c_void_p(q))
-        self.dist.barrier()                      # nobody maps the buffers any more
+        if barrier:
+            self.dist.barrier()                  # nobody maps the buffers any more
         for own in self.own:
             self.L.orbx_shared_free(self.device, C.c_void_p(own))
         self.ptrs, self.own = [], []
