@@ -179,6 +179,95 @@ OCT_HD void oct_std_sort(uint64_t *a, int n) {
     }
 }
 
+// ---- the same std::sort, restructured for a thread block -----------------------------------------------------------------
+// libstdc++'s sort = introsort loop (partitions down to ranges of <= 16) + one final insertion sort.  Two facts make it parallel
+// without changing a single comparison result:
+//  * a partition leaves [first, cut) <= pivot <= [cut, last), and the two ranges are processed independently afterwards, so all
+//    ranges of one recursion depth can be partitioned at the same time, one thread each (breadth-first instead of depth-first);
+//  * the final insertion sort never moves an element across a range boundary (val < a[boundary - 1] is false), and an insertion
+//    sort is a STABLE sort: the final pass is a stable sort of every leaf range, i.e. a rank computation per element
+//    (#smaller keys + #equal keys in front of it), fully parallel.  A range that hit the depth limit is heap-sorted by its thread
+//    (already ordered -> the final pass leaves it alone).
+// Scratch: rf/rl/rd = two range lists (first, last, depth) of `cap` entries each, lohi[cap] = leaf bounds per element,
+// tmp[cap] = output of the rank pass, cnt[2] = list / work counters.  Every thread of the block calls this.
+struct OctSortScratch { int *rf[2], *rl[2], *rd[2]; int *lohi; uint64_t *tmp; int *cnt; };
+
+OCT_HD int oct_partition_range(uint64_t *a, int first, int last) {   // __unguarded_partition_pivot(first, last)
+    const int mid = first + (last - first) / 2;
+    {   // __move_median_to_first(first, first+1, mid, last-1)
+        const int ia = first + 1, ib = mid, ic = last - 1;
+        if (oct_lt(a[ia], a[ib])) {
+            if (oct_lt(a[ib], a[ic])) oct_swap(a, first, ib);
+            else if (oct_lt(a[ia], a[ic])) oct_swap(a, first, ic);
+            else oct_swap(a, first, ia);
+        } else if (oct_lt(a[ia], a[ic])) oct_swap(a, first, ia);
+        else if (oct_lt(a[ib], a[ic])) oct_swap(a, first, ic);
+        else oct_swap(a, first, ib);
+    }
+    int f = first + 1, l = last;   // __unguarded_partition(first+1, last, pivot=first)
+    const uint64_t piv = a[first];  // the pivot slot is never swapped inside the loop (f > first)
+    for (;;) {
+        f = oct_scan_up(a, f, piv);
+        l = oct_scan_down(a, l - 1, piv);
+        if (!(f < l)) break;
+        oct_swap(a, f, l);
+        ++f;
+    }
+    return f;
+}
+
+template <class Ctx>
+OCT_HD void oct_std_sort_block(Ctx &cx, uint64_t *a, int n, OctSortScratch &S) {
+    if (n <= 1) return;
+    if (cx.tid == 0) {
+        int lg = 0;
+        while ((n >> (lg + 1)) > 0) lg++;
+        S.rf[0][0] = 0; S.rl[0][0] = n; S.rd[0][0] = 2 * lg;
+        S.cnt[0] = 1; S.cnt[1] = 0;
+    }
+    cx.sync();
+    int cur = 0;
+    for (;;) {
+        const int nr = S.cnt[cur];
+        if (nr == 0) break;
+        cx.sync();                                   // everybody has read the count before it is reset below
+        if (cx.tid == 0) S.cnt[cur ^ 1] = 0;
+        cx.sync();
+        for (int r = cx.tid; r < nr; r += cx.nt) {
+            const int first = S.rf[cur][r], last = S.rl[cur][r];
+            int depth = S.rd[cur][r];
+            if (last - first > 16 && depth > 0) {
+                --depth;
+                const int cut = oct_partition_range(a, first, last);
+                const int o = cx.atomic_add(&S.cnt[cur ^ 1], 2);
+                S.rf[cur ^ 1][o] = cut; S.rl[cur ^ 1][o] = last; S.rd[cur ^ 1][o] = depth;
+                S.rf[cur ^ 1][o + 1] = first; S.rl[cur ^ 1][o + 1] = cut; S.rd[cur ^ 1][o + 1] = depth;
+            } else if (last - first > 16) {          // depth limit: std::__partial_sort(first, last, last)
+                oct_heapsort(a, first, last);
+                for (int e = first; e < last; e++) S.lohi[e] = e | ((e + 1) << 16);
+            } else {                                 // leaf: the final insertion sort orders it stably
+                for (int e = first; e < last; e++) S.lohi[e] = first | (last << 16);
+            }
+        }
+        cx.sync();
+        cur ^= 1;
+    }
+    cx.sync();
+    for (int e = cx.tid; e < n; e += cx.nt) {        // stable rank inside the leaf range
+        const int lo = S.lohi[e] & 0xFFFF, hi = S.lohi[e] >> 16;
+        const uint64_t v = a[e];
+        int rank = 0;
+        for (int j = lo; j < hi; j++) {
+            const uint64_t u = a[j];
+            rank += (oct_lt(u, v) || (j < e && !oct_lt(v, u))) ? 1 : 0;
+        }
+        S.tmp[lo + rank] = v;
+    }
+    cx.sync();
+    for (int e = cx.tid; e < n; e += cx.nt) a[e] = S.tmp[e];
+    cx.sync();
+}
+
 // ---- node tables (one block's shared memory, or host arrays) ----------------------------------------------
 struct OctBox { short x0, x1, y0, y1; };   // UL.x, UR.x, UL.y, BR.y
 
@@ -261,6 +350,8 @@ OCT_HD OctBox oct_child_box(const OctBox &b, int q) {
 }
 
 // Ctx requirements: int tid, nt; void sync(); int atomic_add(int*, int); void atomic_max(unsigned*, unsigned);
+//                   void hist_add(int *cnt, int key, bool valid, int nkeys) — ++cnt[key] for the valid callers; called by EVERY thread of
+//                   the block in lock step; with few keys (nkeys <= 32) most callers share a counter: aggregate per warp first
 //                   int excl_scan(int *arr, int n)  — block-wide, in place, returns the total to every thread
 //                   (callers bracket it with sync()).
 //
@@ -276,10 +367,19 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
     // ---- roots (:505-542)
     for (int r = cx.tid; r < n_ini; r += cx.nt) w.child_cnt[r] = 0;
     cx.sync();
-    for (int i = cx.tid; i < n; i += cx.nt) {
-        const int r = (int)((float)cand_x(cand[i]) / h_x);
-        node[i] = (unsigned short)r;
-        cx.atomic_add(&w.child_cnt[r], 1);
+    // (all sweeps over the candidates: uniform trip count — hist_add is a whole-block call — and 4 independent loads in flight)
+    for (int base = 0; base < n; base += 4 * cx.nt) {
+        uint32_t cd[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = base + u * cx.nt + cx.tid; cd[u] = i < n ? cand[i] : 0u; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * cx.nt + cx.tid;
+            const bool v = i < n;
+            const int r = v ? (int)((float)cand_x(cd[u]) / h_x) : 0;
+            if (v) node[i] = (unsigned short)r;
+            cx.hist_add(w.child_cnt, r, v, n_ini);          // a handful of counters shared by every candidate
+        }
     }
     cx.sync();
     if (cx.tid == 0) {
@@ -297,7 +397,8 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
         V[0] = ls; V[1] = 0; V[2] = 0; V[3] = -1;
     }
     cx.sync();
-    for (int i = cx.tid; i < n; i += cx.nt) node[i] = (unsigned short)w.remap[node[i]];
+    if (V[0] != n_ini)   // (identity unless a root is empty)
+        for (int i = cx.tid; i < n; i += cx.nt) node[i] = (unsigned short)w.remap[node[i]];
     cx.sync();
     (void)x_span;
 
@@ -311,9 +412,20 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
             // ------------------------------------------------ full pass (:551-613)
             for (int k = cx.tid; k < 4 * ls; k += cx.nt) w.child_cnt[k] = 0;
             cx.sync();
-            for (int i = cx.tid; i < n; i += cx.nt) {
-                const int p = node[i];
-                if (!T.nomore[p]) cx.atomic_add(&w.child_cnt[4 * p + oct_quadrant(T.box[p], cand[i])], 1);
+            for (int base = 0; base < n; base += 4 * cx.nt) {
+                uint32_t cd[4]; int pn[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * cx.nt + cx.tid;
+                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int p = pn[u];
+                    const bool v = p >= 0 && !T.nomore[p];
+                    const int key = v ? 4 * p + oct_quadrant(T.box[p], cd[u]) : 0;
+                    cx.hist_add(w.child_cnt, key, v, 4 * ls);
+                }
             }
             cx.sync();
             for (int p = cx.tid; p < ls; p += cx.nt) {
@@ -348,9 +460,20 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
                 }
             }
             cx.sync();
-            for (int i = cx.tid; i < n; i += cx.nt) {
-                const int p = node[i];
-                node[i] = (unsigned short)(T.nomore[p] ? w.remap[p] : w.child_pos[4 * p + oct_quadrant(T.box[p], cand[i])]);
+            for (int base = 0; base < n; base += 4 * cx.nt) {
+                uint32_t cd[4]; int pn[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * cx.nt + cx.tid;
+                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int p = pn[u];
+                    if (p >= 0)
+                        node[base + u * cx.nt + cx.tid] =
+                            (unsigned short)(T.nomore[p] ? w.remap[p] : w.child_pos[4 * p + oct_quadrant(T.box[p], cd[u])]);
+                }
             }
             cx.sync();
             if (cx.tid == 0) {
@@ -374,19 +497,28 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
                 w.srt[c] = ((uint64_t)(((uint32_t)T.cnt[p] << 13) | (uint32_t)T.box[p].x0) << 32) | (uint64_t)c;
             }
             cx.sync();
-            // thread 0 runs the sequential std::sort emulation; the other warps build the child histogram meanwhile
-            {
-                const bool split = cx.nt > 32;
-                const int wt = split ? cx.nt - 32 : cx.nt, wi = split ? cx.tid - 32 : cx.tid;
-                if (wi >= 0)
-                    for (int i = wi; i < n; i += wt) {
-                        const int p = node[i];
-                        const int c = w.cidx[p];
-                        if (c >= 0) cx.atomic_add(&w.child_cnt[4 * c + oct_quadrant(T.box[p], cand[i])], 1);
-                    }
+            for (int base = 0; base < n; base += 4 * cx.nt) {
+                uint32_t cd[4]; int pn[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * cx.nt + cx.tid;
+                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int p = pn[u];
+                    const int c = p >= 0 ? w.cidx[p] : -1;
+                    const bool v = c >= 0;
+                    cx.hist_add(w.child_cnt, v ? 4 * c + oct_quadrant(T.box[p], cd[u]) : 0, v, 4 * m);
+                }
             }
-            if (cx.tid == 0) oct_std_sort(w.srt, m);
-            cx.sync();
+            {   // exact std::sort of the candidates, block-parallel; scratch = arrays that are dead until the tables are rebuilt
+                OctSortScratch S;
+                S.rf[0] = w.scan_a; S.rl[0] = w.scan_b; S.rd[0] = w.scan_c;
+                S.rf[1] = w.remap; S.rl[1] = w.order; S.rd[1] = (int *)w.best;
+                S.lohi = w.child_pos; S.tmp = (uint64_t *)(w.child_pos + 2 * ((w.cap + 1) / 2)); S.cnt = V + 8;
+                oct_std_sort_block(cx, w.srt, m, S);
+            }
             if (cx.tid == 0) {
                 int size = ls, np = 0, A = 0, E = 0;
                 for (int j = m - 1; j >= 0; j--) {
@@ -433,14 +565,20 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
                 }
             }
             cx.sync();
-            for (int i = cx.tid; i < n; i += cx.nt) {
-                const int p = node[i];
-                const int ci = w.cidx[p];
-                if (ci <= -2) {
-                    const int c = w.order[-2 - ci];
-                    node[i] = (unsigned short)w.child_pos[4 * c + oct_quadrant(T.box[p], cand[i])];
-                } else {
-                    node[i] = (unsigned short)w.remap[p];
+            for (int base = 0; base < n; base += 4 * cx.nt) {
+                uint32_t cd[4]; int pn[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * cx.nt + cx.tid;
+                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int p = pn[u];
+                    if (p < 0) continue;
+                    const int ci = w.cidx[p];
+                    node[base + u * cx.nt + cx.tid] = (unsigned short)(ci <= -2 ? w.child_pos[4 * w.order[-2 - ci] + oct_quadrant(T.box[p], cd[u])]
+                                                                                 : w.remap[p]);
                 }
             }
             cx.sync();
@@ -458,8 +596,17 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
     const int ls = V[0];
     for (int p = cx.tid; p < ls; p += cx.nt) w.best[p] = 0;
     cx.sync();
-    for (int i = cx.tid; i < n; i += cx.nt)
-        cx.atomic_max(&w.best[node[i]], ((uint32_t)cand_score(cand[i]) << 24) | (uint32_t)(0xFFFFFF - i));
+    for (int base = 0; base < n; base += 4 * cx.nt) {
+        uint32_t cd[4]; int pn[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * cx.nt + cx.tid;
+            cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (pn[u] >= 0) cx.atomic_max(&w.best[pn[u]], ((uint32_t)cand_score(cd[u]) << 24) | (uint32_t)(0xFFFFFF - (base + u * cx.nt + cx.tid)));
+    }
     cx.sync();
     for (int p = cx.tid; p < ls; p += cx.nt) sel[p] = 0xFFFFFF - (int)(w.best[p] & 0xFFFFFF);
     cx.sync();

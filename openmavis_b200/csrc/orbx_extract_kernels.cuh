@@ -660,6 +660,16 @@ struct DevCtx {
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
     __device__ __forceinline__ void atomic_max(unsigned *p, unsigned v) { atomicMax(p, v); }
+    __device__ __forceinline__ void hist_add(int *cnt, int key, bool valid, int nkeys) {
+        if (nkeys <= 32) {   // one ballot per key, one atomic per (warp, key): thousands of candidates share these few counters
+            for (int k = 0; k < nkeys; k++) {
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, valid && key == k);
+                if (m && (tid & 31) == 0) atomicAdd(&cnt[k], __popc(m));
+            }
+        } else if (valid) {
+            atomicAdd(&cnt[key], 1);
+        }
+    }
     __device__ int excl_scan(int *a, int n) {
         if (tid < 32) {
             int carry = 0;

@@ -32,6 +32,9 @@ def test_std_sort_emulation_matches_libstdcxx(hc):
         got = np.zeros(n, np.int32)
         hc.hc_std_sort(O.p(sizes), O.p(ulx), n, O.p(got))
         assert np.array_equal(ref, got), trial
+        got2 = np.zeros(n, np.int32)
+        hc.hc_std_sort_block(O.p(sizes), O.p(ulx), n, O.p(got2))       # block-parallel formulation used by the kernel
+        assert np.array_equal(ref, got2), trial
 
 
 def _distribute_both(hc, xs, ys, sc, minX, maxX, minY, maxY, N):
