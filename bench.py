@@ -131,7 +131,7 @@ def cpu_oracle_run(frames, threads, rank=0):
 def guided_matchers(ob, device):
     """Secondary numbers for the small matchers (report queries/s and latency): config-4 style SearchByProjection
     (2 x 512x512, 1500 features / camera, 5000 map points), ComputeStereoMatches on a 752x480 pair, ComputeDistinctiveDescriptors on
-    2000 map points.  Wall-clock per call through the host-buffer C ABI (uploads and downloads included), median of 7."""
+    2000 map points, ComputeStereoFishEyeMatches on 2 x 1500 keypoints.  Wall-clock per call through the host-buffer C ABI (uploads and downloads included), median of 7."""
     from openmavis_b200.synth import synth_image, synth_descriptors
     rng = np.random.default_rng(7)
     out = {}
@@ -185,6 +185,25 @@ def guided_matchers(ob, device):
     ms = timed(lambda: m.ComputeDistinctiveDescriptors(dd, ptr))
     out['distinctive_descriptors'] = {'map_points': 2000, 'descriptors': int(ptr[-1]), 'ms_per_call': ms, 'device_ms': m.last_ms(),
                                       'map_points_per_s': 2000 / (ms * 1e-3)}
+    # ---- ComputeStereoFishEyeMatches (src/Frame.cc:1409-1459): 2-NN + ratio + KannalaBrandt8::TriangulateMatches
+    from openmavis_b200.synth import synth_fisheye_pairs
+    nk = 1500
+    fs = synth_fisheye_pairs(nk, 77)
+    kp_dt = ob.KP_DTYPE
+    kl = np.zeros(nk, kp_dt); kr = np.zeros(nk, kp_dt)
+    kl['x'], kl['y'], kl['octave'] = fs['xy1'][:, 0], fs['xy1'][:, 1], fs['octave1']
+    perm = rng.permutation(nk)
+    kr['x'][perm], kr['y'][perm], kr['octave'][perm] = fs['xy2'][:, 0], fs['xy2'][:, 1], fs['octave2']
+    dl = synth_descriptors(nk, 78); dr = np.zeros_like(dl)
+    dr[perm] = dl ^ np.packbits(rng.random((nk, 256)) < 0.06, axis=1, bitorder='little')
+    frig = ob.kb8_stereo(fs['cam1'], fs['cam2'], fs['R12'], fs['t12'])
+    sig = np.array([np.float32(1.2) ** (2 * l) for l in range(8)], np.float32)
+    nf = [0]
+
+    def fisheye():
+        nf[0] = m.ComputeStereoFishEyeMatches(frig, kl, dl, 0, kr, dr, 0, sig, 0.7)['nMatches']
+    ms = timed(fisheye)
+    out['stereo_fisheye_matches'] = {'keypoints': [nk, nk], 'matches': int(nf[0]), 'ms_per_call': ms, 'queries_per_s': nk / (ms * 1e-3)}
     return out
 
 

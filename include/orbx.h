@@ -238,6 +238,31 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
                               const uint8_t *mp_desc, float th, int far_points, float th_far_points, float nnratio,
                               int *assigned, int *nmatches);
 
+/* Fisheye stereo post-filter.  Camera pair of a Kannala-Brandt rig: cam = {fx, fy, cx, cy, k0, k1, k2, k3}
+ * (KannalaBrandt8::mvParameters), R12 / t12 = Frame::mRlr / mtlr (row-major rotation, translation), precision = the Newton
+ * stopping threshold of KannalaBrandt8::unproject (1e-6 in the reference). */
+typedef struct orbx_kb8_stereo {
+    float cam1[8], cam2[8];
+    float R12[9], t12[3];
+    float precision1, precision2;
+} orbx_kb8_stereo;
+/* KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:319-388) for n independent keypoint pairs:
+ * xy1 / xy2 = kp.pt of the two cameras ([n][2]), sigma1 / sigma2 = the two reprojection gates (mvLevelSigma2 of the octaves).
+ * depth[i] = z1 > 0, or the reference's reject code (-1 parallax, -2 / -3 behind a camera, -4 / -5 reprojection error);
+ * p3d[i] = the triangulated point in camera-1 coordinates (zeros when rejected).  HOST pointers. */
+int orbx_kb8_triangulate_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, const float *xy1, const float *xy2, const float *sigma1,
+                                 const float *sigma2, int n, float *depth, float *p3d);
+/* Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1409-1459, ratio 0.7) / ComputeMultiFishEyeMatches (:1461-1525, ratio 0.8) in
+ * one call: brute-force 2-NN of the left lapping block [mono_left, n_left) in the right lapping block [mono_right, n_right),
+ * Lowe ratio test, TriangulateMatches, depth > 0.0001.  left_to_right[n_left] / right_to_left[n_right] = mvLeftToRightMatch /
+ * mvRightToLeftMatch (-1 = none; a right keypoint chosen by several left ones keeps the last, as the reference's loop does),
+ * depth[n_left] = mvDepth (-1), p3d[n_left][3] = mvStereo3Dpoints; counts[0] = nMatches, counts[1] = descMatches (may be NULL).
+ * HOST pointers. */
+int orbx_stereo_fisheye_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, const orbx_kp *kps_left, const uint8_t *desc_left,
+                                int n_left, int mono_left, const orbx_kp *kps_right, const uint8_t *desc_right, int n_right,
+                                int mono_right, const float *level_sigma2, int nlevels, double ratio, int *left_to_right,
+                                int *right_to_left, float *depth, float *p3d, int *counts);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483), batched over map points: group g = descriptor rows
  * [ptr[g], ptr[g+1]) of desc (the observations of one map point, in the order the reference collects them).
  * best[g] = index inside the group of the descriptor with the least median Hamming distance to the rest (first minimum,

@@ -53,6 +53,19 @@ def lib():
     return _lib
 
 
+KB8_STEREO_DTYPE = np.dtype([('cam1', 'f4', 8), ('cam2', 'f4', 8), ('R12', 'f4', 9), ('t12', 'f4', 3), ('precision1', 'f4'),
+                             ('precision2', 'f4')])   # orbx_kb8_stereo
+
+
+def kb8_stereo(cam1, cam2, R12, t12, precision=1e-6):
+    """orbx_kb8_stereo: cam = (fx, fy, cx, cy, k0..k3) of KannalaBrandt8::mvParameters, R12 / t12 = Frame::mRlr / mtlr."""
+    r = np.zeros(1, KB8_STEREO_DTYPE)
+    r['cam1'][0] = np.asarray(cam1, np.float32); r['cam2'][0] = np.asarray(cam2, np.float32)
+    r['R12'][0] = np.asarray(R12, np.float32).reshape(9); r['t12'][0] = np.asarray(t12, np.float32).reshape(3)
+    r['precision1'] = np.float32(precision); r['precision2'] = np.float32(precision)
+    return r
+
+
 def _check(status):
     if status < 0:
         raise OrbxError('orbx status %d: %s' % (status, lib().orbx_last_error().decode()))
@@ -376,6 +389,33 @@ class ORBmatcher:
         best = np.full(ptr.size - 1, -1, np.int32)
         _check(self.L.orbx_distinctive_descriptors(self.h, _p(desc), _p(ptr), ptr.size - 1, _p(best)))
         return best
+
+    def TriangulateMatches(self, rig, xy1, xy2, sigma1, sigma2):
+        """KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:319-388) for n keypoint pairs.
+        rig = kb8_stereo(...); returns (depth_or_code[n], p3d[n,3])."""
+        xy1 = np.ascontiguousarray(xy1, np.float32).reshape(-1, 2); xy2 = np.ascontiguousarray(xy2, np.float32).reshape(-1, 2)
+        n = xy1.shape[0]
+        s1 = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma1, np.float32), (n,)))
+        s2 = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma2, np.float32), (n,)))
+        depth = np.zeros(n, np.float32); p3d = np.zeros((n, 3), np.float32)
+        _check(self.L.orbx_kb8_triangulate_matches(self.h, _p(rig), _p(xy1), _p(xy2), _p(s1), _p(s2), n, _p(depth), _p(p3d)))
+        return depth, p3d
+
+    def ComputeStereoFishEyeMatches(self, rig, kps_left, desc_left, mono_left, kps_right, desc_right, mono_right, level_sigma2,
+                                    ratio=0.7):
+        """Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1409-1459; ratio 0.7) / ComputeMultiFishEyeMatches (:1461-1525; ratio
+        0.8): 2-NN of the lapping blocks + ratio test + TriangulateMatches on the device.
+        Returns dict(nMatches, descMatches, mvLeftToRightMatch, mvRightToLeftMatch, mvDepth, mvStereo3Dpoints)."""
+        kl = np.ascontiguousarray(kps_left, KP_DTYPE); kr = np.ascontiguousarray(kps_right, KP_DTYPE)
+        dl = np.ascontiguousarray(desc_left, np.uint8).reshape(-1, 32); dr = np.ascontiguousarray(desc_right, np.uint8).reshape(-1, 32)
+        sg = np.ascontiguousarray(level_sigma2, np.float32)
+        l2r = np.full(kl.size, -1, np.int32); r2l = np.full(kr.size, -1, np.int32)
+        depth = np.full(kl.size, -1, np.float32); p3d = np.zeros((kl.size, 3), np.float32); cnt = np.zeros(2, np.int32)
+        _check(self.L.orbx_stereo_fisheye_matches(self.h, _p(rig), _p(kl), _p(dl), kl.size, int(mono_left), _p(kr), _p(dr), kr.size,
+                                                  int(mono_right), _p(sg), sg.size, C.c_double(ratio), _p(l2r), _p(r2l), _p(depth),
+                                                  _p(p3d), _p(cnt)))
+        return dict(nMatches=int(cnt[0]), descMatches=int(cnt[1]), mvLeftToRightMatch=l2r, mvRightToLeftMatch=r2l, mvDepth=depth,
+                    mvStereo3Dpoints=p3d)
 
     def grid_candidates(self, kps, bounds, qx, qy, qr, min_level, max_level, cand_cap=None):
         kps = np.ascontiguousarray(kps, KP_DTYPE)

@@ -9,6 +9,7 @@
 
 #include "orbx_match_kernels.cuh"
 #include "orbx_sbp_kernels.cuh"
+#include "orbx_fisheye_kernels.cuh"
 
 using namespace orbx;
 
@@ -567,6 +568,91 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     M_CUDA(cudaMemcpyAsync(assigned, R.assigned, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaMemcpyAsync(nmatches, R.nmatches, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+// ---- fisheye stereo post-filter
+int orbx_kb8_triangulate_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, const float *xy1, const float *xy2, const float *sigma1,
+                                 const float *sigma2, int n, float *depth, float *p3d) {
+    if (!m || !rig || n < 0 || (n && (!xy1 || !xy2 || !sigma1 || !sigma2 || !depth || !p3d))) return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    if (n == 0) return ORBX_OK;
+    int st;
+    if ((st = upload(m, m->b[1], xy1, (size_t)n * 2 * sizeof(float))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], xy2, (size_t)n * 2 * sizeof(float))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[3], sigma1, (size_t)n * sizeof(float))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[4], sigma2, (size_t)n * sizeof(float))) != ORBX_OK) return st;
+    M_CUDA(m->b[5].ensure((size_t)n * sizeof(float)));
+    M_CUDA(m->b[6].ensure((size_t)n * 3 * sizeof(float)));
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    k_kb8_triangulate<<<(n + 127) / 128, 128, 0, m->stream>>>(*rig, m->b[1].as<float>(), m->b[2].as<float>(), m->b[3].as<float>(),
+                                                            m->b[4].as<float>(), n, m->b[5].as<float>(), m->b[6].as<float>());
+    m->last_launches = 1;
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    M_CUDA(cudaMemcpyAsync(depth, m->b[5].p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(p3d, m->b[6].p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_stereo_fisheye_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, const orbx_kp *kps_left, const uint8_t *desc_left,
+                                int n_left, int mono_left, const orbx_kp *kps_right, const uint8_t *desc_right, int n_right,
+                                int mono_right, const float *level_sigma2, int nlevels, double ratio, int *left_to_right,
+                                int *right_to_left, float *depth, float *p3d, int *counts) {
+    if (!m || !rig || n_left < 0 || n_right < 0 || mono_left < 0 || mono_left > n_left || mono_right < 0 || mono_right > n_right ||
+        !level_sigma2 || nlevels < 1 || nlevels > 16 || (n_left && (!kps_left || !desc_left || !left_to_right || !depth || !p3d)) ||
+        (n_right && (!kps_right || !desc_right || !right_to_left)))
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    for (int i = 0; i < n_left; i++) { left_to_right[i] = -1; depth[i] = -1.0f; p3d[3 * i] = p3d[3 * i + 1] = p3d[3 * i + 2] = 0.0f; }
+    for (int i = 0; i < n_right; i++) right_to_left[i] = -1;
+    if (counts) counts[0] = counts[1] = 0;
+    const int nq = n_left - mono_left, nt = n_right - mono_right;
+    if (nq == 0 || nt < 2) return ORBX_OK;                                            // knnMatch returns fewer than 2 neighbours
+    for (int i = mono_left; i < n_left; i++)
+        if (kps_left[i].octave < 0 || kps_left[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "keypoint octave outside the level table");
+    for (int i = mono_right; i < n_right; i++)
+        if (kps_right[i].octave < 0 || kps_right[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "keypoint octave outside the level table");
+    int st;
+    if ((st = upload(m, m->b[1], desc_left + (size_t)mono_left * 32, (size_t)nq * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], desc_right + (size_t)mono_right * 32, (size_t)nt * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[5], kps_left, (size_t)n_left * sizeof(orbx_kp))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[6], kps_right, (size_t)n_right * sizeof(orbx_kp))) != ORBX_OK) return st;
+    M_CUDA(m->b[3].ensure((size_t)nq * 2 * sizeof(int)));
+    M_CUDA(m->b[4].ensure((size_t)nq * 2 * sizeof(int)));
+    // outputs: l2r [n_left] | r2l [n_right] | depth [n_left] | p3d [3 n_left] | counters [2], pre-filled from the host copies
+    const size_t o_r2l = (size_t)n_left, o_depth = o_r2l + n_right, o_p3d = o_depth + n_left, o_cnt = o_p3d + 3 * (size_t)n_left;
+    M_CUDA(m->b[7].ensure((o_cnt + 2) * 4));
+    int *d_out = m->b[7].as<int>();
+    M_CUDA(cudaMemcpyAsync(d_out, left_to_right, (size_t)n_left * 4, cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(cudaMemcpyAsync(d_out + o_r2l, right_to_left, (size_t)n_right * 4, cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(cudaMemcpyAsync(d_out + o_depth, depth, (size_t)n_left * 4, cudaMemcpyHostToDevice, m->stream));
+    M_CUDA(cudaMemsetAsync(d_out + o_p3d, 0, (3 * (size_t)n_left + 2) * 4, m->stream));
+    st = orbx_knn2_device(m, m->b[1].as<uint8_t>(), nq, m->b[2].as<uint8_t>(), nt, m->b[3].as<int>(), m->b[4].as<int>());
+    if (st != ORBX_OK) return st;
+    FisheyeArgs A;
+    A.kpL = m->b[5].as<orbx_kp>(); A.kpR = m->b[6].as<orbx_kp>();
+    A.nL = n_left; A.nR = n_right; A.monoL = mono_left; A.monoR = mono_right;
+    A.idx = m->b[3].as<int>(); A.dist = m->b[4].as<int>();
+    for (int l = 0; l < 16; l++) A.sigma2[l] = l < nlevels ? level_sigma2[l] : 0.0f;
+    A.ratio = ratio;
+    A.l2r = d_out; A.r2l = d_out + o_r2l; A.depth = (float *)(d_out + o_depth); A.p3d = (float *)(d_out + o_p3d); A.counters = d_out + o_cnt;
+    k_fisheye_matches<<<(nq + 127) / 128, 128, 0, m->stream>>>(*rig, A);
+    m->last_launches++;
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    M_CUDA(cudaMemcpyAsync(left_to_right, d_out, (size_t)n_left * 4, cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(right_to_left, d_out + o_r2l, (size_t)n_right * 4, cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(depth, d_out + o_depth, (size_t)n_left * 4, cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(p3d, d_out + o_p3d, 3 * (size_t)n_left * 4, cudaMemcpyDeviceToHost, m->stream));
+    int cnt[2] = {0, 0};
+    M_CUDA(cudaMemcpyAsync(cnt, d_out + o_cnt, 2 * 4, cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    if (counts) { counts[0] = cnt[0]; counts[1] = cnt[1]; }
     return ORBX_OK;
 }
 

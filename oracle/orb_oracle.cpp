@@ -1147,4 +1147,172 @@ int orc_bow_from_words(const int *word, const int *node, const double *weight, i
     return (int)v.size();
 }
 
+// ---- Fisheye stereo post-filter: KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:319-388) and its
+// caller Frame::ComputeStereoFishEyeMatches / ComputeMultiFishEyeMatches (src/Frame.cc:1409-1459, 1461-1525) ---------------------
+// fp32 as written in the reference (this file is built with -ffp-contract=off).  The one third-party piece is
+// Eigen::JacobiSVD<Matrix4f>(A, ComputeFullV).matrixV().col(3) (:422-424; Eigen is not in this image): restated as the
+// eigenvector of the smallest eigenvalue of A^T A by cyclic Jacobi in fp64 (pinned against numpy.linalg.svd in
+// tests/test_oracle_fisheye.py), rounded to fp32.
+struct OrcKb8Stereo { float cam1[8], cam2[8], R12[9], t12[3], precision1, precision2; };
+
+static void kb8_unproject(const float *P, float precision, float u, float v, float ray[3]) {   // :96-126
+    const float pwx = (u - P[2]) / P[0], pwy = (v - P[3]) / P[1];
+    float scale = 1.f;
+    float theta_d = sqrtf(pwx * pwx + pwy * pwy);
+    theta_d = fminf(fmaxf((float)(-M_PI / 2.f), theta_d), (float)(M_PI / 2.f));
+    if (theta_d > 1e-8) {
+        float theta = theta_d;
+        for (int j = 0; j < 10; j++) {
+            float theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta4 * theta2, theta8 = theta4 * theta4;
+            float k0_theta2 = P[4] * theta2, k1_theta4 = P[5] * theta4;
+            float k2_theta6 = P[6] * theta6, k3_theta8 = P[7] * theta8;
+            float theta_fix = (theta * (1 + k0_theta2 + k1_theta4 + k2_theta6 + k3_theta8) - theta_d) /
+                              (1 + 3 * k0_theta2 + 5 * k1_theta4 + 7 * k2_theta6 + 9 * k3_theta8);
+            theta = theta - theta_fix;
+            if (fabsf(theta_fix) < precision) break;
+        }
+        scale = tanf(theta) / theta_d;
+    }
+    ray[0] = pwx * scale; ray[1] = pwy * scale; ray[2] = 1.f;
+}
+
+static void kb8_project(const float *P, const float X[3], float uv[2]) {   // :48-65
+    const float x2_plus_y2 = X[0] * X[0] + X[1] * X[1];
+    const float theta = atan2f(sqrtf(x2_plus_y2), X[2]);
+    const float psi = atan2f(X[1], X[0]);
+    const float theta2 = theta * theta, theta3 = theta * theta2, theta5 = theta3 * theta2, theta7 = theta5 * theta2, theta9 = theta7 * theta2;
+    const float r = theta + P[4] * theta3 + P[5] * theta5 + P[6] * theta7 + P[7] * theta9;
+    uv[0] = P[0] * r * cosf(psi) + P[2];
+    uv[1] = P[1] * r * sinf(psi) + P[3];
+}
+
+// v4 = unit right singular vector of the smallest singular value of the row-major 4x4 matrix a
+static void null_vector4(const float *a, double v4[4]) {
+    double M[4][4], V[4][4];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            double s = 0;
+            for (int k = 0; k < 4; k++) s += (double)a[4 * k + i] * (double)a[4 * k + j];
+            M[i][j] = s; V[i][j] = i == j ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0;
+        for (int p = 0; p < 4; p++) for (int q = p + 1; q < 4; q++) off += M[p][q] * M[p][q];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 3; p++)
+            for (int q = p + 1; q < 4; q++) {
+                if (M[p][q] == 0.0) continue;
+                const double th = (M[q][q] - M[p][p]) / (2.0 * M[p][q]);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 4; k++) { const double kp = M[k][p], kq = M[k][q]; M[k][p] = c * kp - sn * kq; M[k][q] = sn * kp + c * kq; }
+                for (int k = 0; k < 4; k++) { const double pk = M[p][k], qk = M[q][k]; M[p][k] = c * pk - sn * qk; M[q][k] = sn * pk + c * qk; }
+                for (int k = 0; k < 4; k++) { const double kp = V[k][p], kq = V[k][q]; V[k][p] = c * kp - sn * kq; V[k][q] = sn * kp + c * kq; }
+            }
+    }
+    int best = 0;
+    for (int j = 1; j < 4; j++) if (M[j][j] < M[best][best]) best = j;
+    for (int i = 0; i < 4; i++) v4[i] = V[i][best];
+}
+
+// returns z1 or the reject code; margin (if not NULL) = smallest relative distance of a tested quantity from its gate
+static float kb8_triangulate_matches(const OrcKb8Stereo &S, float u1, float v1, float u2, float v2, float sigmaLevel, float unc,
+                                     float p3D[3], float *margin) {
+    float mg = 1e30f;
+    auto gate = [&](double value, double limit) { const float m = (float)(fabs(value - limit) / (fabs(limit) + 1e-12)); if (m < mg) mg = m; };
+    auto done = [&](float code) { if (margin) *margin = mg; return code; };
+    float r1[3], r2[3];
+    kb8_unproject(S.cam1, S.precision1, u1, v1, r1);
+    kb8_unproject(S.cam2, S.precision2, u2, v2, r2);
+    const float *R = S.R12;
+    float r21[3];
+    for (int i = 0; i < 3; i++) r21[i] = R[3 * i] * r2[0] + R[3 * i + 1] * r2[1] + R[3 * i + 2] * r2[2];
+    const float n1 = sqrtf(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]), n21 = sqrtf(r21[0] * r21[0] + r21[1] * r21[1] + r21[2] * r21[2]);
+    const float cosParallaxRays = (r1[0] * r21[0] + r1[1] * r21[1] + r1[2] * r21[2]) / (n1 * n21);
+    gate(1.0 - (double)cosParallaxRays, 1.0 - 0.9998);
+    if (cosParallaxRays > 0.9998) return done(-1);
+    float Tcw2[3][4];
+    for (int i = 0; i < 3; i++) {
+        Tcw2[i][0] = R[i]; Tcw2[i][1] = R[3 + i]; Tcw2[i][2] = R[6 + i];
+        Tcw2[i][3] = -R[i] * S.t12[0] + -R[3 + i] * S.t12[1] + -R[6 + i] * S.t12[2];
+    }
+    float A[16] = {-1.f, 0.f, r1[0], 0.f, 0.f, -1.f, r1[1], 0.f};                       // p1 * Tcw1.row(2) - Tcw1.row(0 / 1), Tcw1 = [I|0]
+    for (int j = 0; j < 4; j++) {
+        A[8 + j] = r2[0] * Tcw2[2][j] - Tcw2[0][j];
+        A[12 + j] = r2[1] * Tcw2[2][j] - Tcw2[1][j];
+    }
+    double v4[4];
+    null_vector4(A, v4);
+    const float hw = (float)v4[3];
+    float x3D[3] = {(float)v4[0] / hw, (float)v4[1] / hw, (float)v4[2] / hw};
+    const float z1 = x3D[2];
+    if (z1 <= 0) return done(-2);
+    const float z2 = Tcw2[2][0] * x3D[0] + Tcw2[2][1] * x3D[1] + Tcw2[2][2] * x3D[2] + Tcw2[2][3];
+    if (z2 <= 0) return done(-3);
+    float uv1[2];
+    kb8_project(S.cam1, x3D, uv1);
+    const float errX1 = uv1[0] - u1, errY1 = uv1[1] - v1;
+    gate(errX1 * errX1 + errY1 * errY1, 5.991 * sigmaLevel);
+    if ((errX1 * errX1 + errY1 * errY1) > 5.991 * sigmaLevel) return done(-4);
+    float x3D2[3] = {Tcw2[0][0] * x3D[0] + Tcw2[0][1] * x3D[1] + Tcw2[0][2] * x3D[2] + Tcw2[0][3],
+                     Tcw2[1][0] * x3D[0] + Tcw2[1][1] * x3D[1] + Tcw2[1][2] * x3D[2] + Tcw2[1][3], z2};
+    float uv2[2];
+    kb8_project(S.cam2, x3D2, uv2);
+    const float errX2 = uv2[0] - u2, errY2 = uv2[1] - v2;
+    gate(errX2 * errX2 + errY2 * errY2, 5.991 * unc);
+    if ((errX2 * errX2 + errY2 * errY2) > 5.991 * unc) return done(-5);
+    gate(z1, 0.0001);
+    p3D[0] = x3D[0]; p3D[1] = x3D[1]; p3D[2] = x3D[2];
+    return done(z1);
+}
+
+void orc_null_vector4(const float *a16, double *v4) { null_vector4(a16, v4); }
+
+void orc_kb8_unproject(const float *cam8, float precision, const float *xy, int n, float *rays) {
+    for (int i = 0; i < n; i++) kb8_unproject(cam8, precision, xy[2 * i], xy[2 * i + 1], rays + 3 * i);
+}
+void orc_kb8_project(const float *cam8, const float *xyz, int n, float *uv) {
+    for (int i = 0; i < n; i++) kb8_project(cam8, xyz + 3 * i, uv + 2 * i);
+}
+
+void orc_kb8_triangulate_matches(const OrcKb8Stereo *rig, const float *xy1, const float *xy2, const float *sigma1, const float *sigma2,
+                                 int n, float *depth, float *p3d, float *margin) {
+    for (int i = 0; i < n; i++) {
+        float p[3] = {0.f, 0.f, 0.f};
+        depth[i] = kb8_triangulate_matches(*rig, xy1[2 * i], xy1[2 * i + 1], xy2[2 * i], xy2[2 * i + 1], sigma1[i], sigma2[i], p,
+                                           margin ? margin + i : nullptr);
+        p3d[3 * i] = p[0]; p3d[3 * i + 1] = p[1]; p3d[3 * i + 2] = p[2];
+    }
+}
+
+// Frame::ComputeStereoFishEyeMatches (:1409-1459).  margin[n_left]: gate margin of the query's triangulation (1e30 where the
+// ratio test already failed).  Returns nMatches; *desc_matches = descMatches.
+int orc_stereo_fisheye_matches(const OrcKb8Stereo *rig, const orc_kp *kpsL, const uint8_t *descL, int nL, int monoL, const orc_kp *kpsR,
+                               const uint8_t *descR, int nR, int monoR, const float *levelSigma2, double ratio, int *l2r, int *r2l,
+                               float *depth, float *p3d, float *margin, int *desc_matches) {
+    for (int i = 0; i < nL; i++) { l2r[i] = -1; depth[i] = -1.0f; p3d[3 * i] = p3d[3 * i + 1] = p3d[3 * i + 2] = 0.f; if (margin) margin[i] = 1e30f; }
+    for (int i = 0; i < nR; i++) r2l[i] = -1;
+    int nMatches = 0, descMatches = 0;
+    const int nq = nL - monoL, nt = nR - monoR;
+    std::vector<int> idx((size_t)nq * 2 + 2), dist((size_t)nq * 2 + 2);
+    if (nq > 0) orc_knn2(descL + (size_t)monoL * 32, nq, descR + (size_t)monoR * 32, nt, idx.data(), dist.data(), 1);
+    for (int q = 0; q < nq; q++) {
+        if (idx[2 * q] < 0 || idx[2 * q + 1] < 0) continue;                                         // (*it).size() >= 2
+        if (!((float)dist[2 * q] < (float)dist[2 * q + 1] * ratio)) continue;                        // :1434 (float * double)
+        descMatches++;
+        const int iL = q + monoL, iR = idx[2 * q] + monoR;
+        const float sigma1 = levelSigma2[kpsL[iL].octave], sigma2 = levelSigma2[kpsR[iR].octave];
+        float p[3];
+        const float d = kb8_triangulate_matches(*rig, kpsL[iL].x, kpsL[iL].y, kpsR[iR].x, kpsR[iR].y, sigma1, sigma2, p, margin ? margin + iL : nullptr);
+        if (d > 0.0001f) {
+            l2r[iL] = iR; r2l[iR] = iL;
+            p3d[3 * iL] = p[0]; p3d[3 * iL + 1] = p[1]; p3d[3 * iL + 2] = p[2];
+            depth[iL] = d;
+            nMatches++;
+        }
+    }
+    if (desc_matches) *desc_matches = descMatches;
+    return nMatches;
+}
+
 }  // extern "C"
