@@ -238,6 +238,27 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
                               const uint8_t *mp_desc, float th, int far_points, float th_far_points, float nnratio,
                               int *assigned, int *nmatches);
 
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1985-2413): the
+ * frame-to-frame tracking matcher.  Frame side as in orbx_search_by_projection; u_right = CurrentFrame.mvuRight (only read when
+ * ncam == 1; may be NULL).  Per last-frame keypoint i with a usable map point (valid[i]: pMP set, not an outlier, invzc >= 0 and
+ * the camera-0 projection inside the image bounds, :2008-2026): proj_x/proj_y[i][c] = the projection searched in camera c (the
+ * caller passes what the reference passes — for the side cameras that is the LEFT projection, :2250-2271), proj_ur[i] = uv.x -
+ * mbf * invzc, last_octave / last_angle = octave and angle of the last frame's keypoint, has_obs[i] = Observations() > 0,
+ * pt_desc = GetDescriptor().  forward / backward = bForward / bBackward (:2003-2004).  Window th * sf[octave], level gate by
+ * direction, best Hamming distance <= max_dist (TH_HIGH = 100 here) among the keypoints not claimed by an earlier point; an empty camera-0 window skips the
+ * point's other cameras (:2062); with check_orientation the rotation-histogram filter (:2392-2410) clears the assignments outside
+ * the three fullest bins.  assigned[N] = i written to CurrentFrame.mvpMapPoints (or -1), *nmatches = the return value.
+ * The relocalisation overload SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist) (:2415-2535) is the
+ * same call with ncam = 1 (it searches camera 0 only), valid[i] = its own early `continue`s (:2433-2459), last_octave =
+ * nPredictedLevel, last_angle = pKF->mvKeysUn[i].angle, occupied = (mvpMapPoints[idx] != NULL), has_obs = NULL (every claim is
+ * visible, :2478), forward = backward = 0 and max_dist = ORBdist.  HOST pointers. */
+int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
+                                   const float *grid_bounds, const float *scale_factors, int nlevels, const uint8_t *occupied,
+                                   const float *u_right, int npts, const uint8_t *valid, const float *proj_x, const float *proj_y,
+                                   const float *proj_ur, const int *last_octave, const float *last_angle, const uint8_t *has_obs,
+                                   const uint8_t *pt_desc, float th, int forward, int backward, int check_orientation, int max_dist,
+                                   int *assigned, int *nmatches);
+
 /* Fisheye stereo post-filter.  Camera pair of a Kannala-Brandt rig: cam = {fx, fy, cx, cy, k0, k1, k2, k3}
  * (KannalaBrandt8::mvParameters), R12 / t12 = Frame::mRlr / mtlr (row-major rotation, translation), precision = the Newton
  * stopping threshold of KannalaBrandt8::unproject (1e-6 in the reference). */

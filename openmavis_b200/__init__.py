@@ -461,6 +461,34 @@ class ORBmatcher:
         return nm.value, assigned[:N]
 
 
+    def SearchByProjectionLast(self, frame, last, th, forward=False, backward=False, max_dist=TH_HIGH):
+        """ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1985-2413).
+        frame: as in SearchByProjection (+ optional u_right[N] for the rectified-stereo layout, ncam == 1)
+        last : dict(valid[n], proj_x[n,4], proj_y[n,4], octave[n], angle[n], desc[n,32], has_obs?, proj_ur?)
+        forward / backward = bForward / bBackward.  The relocalisation overload SearchByProjection(Frame, KeyFrame, sAlreadyFound, th,
+        ORBdist) (:2415-2535) is the same call with max_dist = ORBdist (see include/orbx.h).  Returns (nmatches, assigned[N])."""
+        cam_off = np.ascontiguousarray(frame['cam_off'], np.int32)
+        ncam = cam_off.size - 1
+        N = int(cam_off[-1])
+        kps = np.ascontiguousarray(frame['kps'], KP_DTYPE); desc = np.ascontiguousarray(frame['desc'], np.uint8)
+        bounds = np.ascontiguousarray(frame['bounds'], np.float32).reshape(ncam, 4)
+        sf = np.ascontiguousarray(frame['scale_factors'], np.float32)
+        occ = None if frame.get('occupied') is None else np.ascontiguousarray(frame['occupied'], np.uint8)
+        ur = None if frame.get('u_right') is None else np.ascontiguousarray(frame['u_right'], np.float32)
+        n = int(np.asarray(last['valid']).shape[0])
+        valid = np.ascontiguousarray(last['valid'], np.uint8)
+        px = np.ascontiguousarray(last['proj_x'], np.float32).reshape(n, 4); py = np.ascontiguousarray(last['proj_y'], np.float32).reshape(n, 4)
+        octv = np.ascontiguousarray(last['octave'], np.int32); ang = np.ascontiguousarray(last['angle'], np.float32)
+        pd = np.ascontiguousarray(last['desc'], np.uint8).reshape(n, 32)
+        ho = None if last.get('has_obs') is None else np.ascontiguousarray(last['has_obs'], np.uint8)
+        pur = None if last.get('proj_ur') is None else np.ascontiguousarray(last['proj_ur'], np.float32)
+        assigned = np.full(max(N, 1), -1, np.int32); nm = C.c_int(0)
+        _check(self.L.orbx_search_by_projection_last(self.h, ncam, _p(cam_off), _p(kps), _p(desc), _p(bounds), _p(sf), sf.size, _p(occ),
+                                                     _p(ur), n, _p(valid), _p(px), _p(py), _p(pur), _p(octv), _p(ang), _p(ho), _p(pd),
+                                                     C.c_float(th), int(bool(forward)), int(bool(backward)),
+                                                     int(self.mbCheckOrientation), int(max_dist), _p(assigned), C.byref(nm)))
+        return nm.value, assigned[:N]
+
 class ORBVocabulary:
     """DBoW2 TemplatedVocabulary<FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h) as flat arrays on the device; transform()
     mirrors mpORBvocabulary->transform(features, BowVector, FeatureVector, levelsup) (src/Frame.cc:980-985)."""

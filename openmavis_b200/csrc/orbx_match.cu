@@ -456,27 +456,13 @@ int orbx_grid_candidates(orbx_matcher *m, const orbx_kp *kps, int n, float min_x
     return ORBX_OK;
 }
 
-int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
-                              const float *grid_bounds, const float *scale_factors, int nlevels, const uint8_t *occupied,
-                              const int *l2r, const int *r2l, int nmp, const uint8_t *in_view, const float *proj_x,
-                              const float *proj_y, const int *level, const float *view_cos, const float *depth, const uint8_t *bad,
-                              const uint8_t *has_obs, const uint8_t *mp_desc, float th, int far_points, float th_far_points,
-                              float nnratio, int *assigned, int *nmatches) {
-    if (!m || !cam_off || !kps || !desc || !grid_bounds || !scale_factors || !assigned || !nmatches || nmp < 0 ||
-        !(ncam == 1 || ncam == 2 || ncam == 4) || nlevels < 1 || nlevels > 32)
-        return fail(ORBX_ERR_INVALID, "bad arguments");
-    M_CUDA(cudaSetDevice(m->device));
-    m->last_launches = 0;
+// frame side of the projection matchers: keypoints, descriptors, one 64x48 grid per camera, occupancy, stereo mirror tables
+static int sbp_setup_frame(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc, const float *grid_bounds,
+                           const float *scale_factors, int nlevels, const uint8_t *occupied, const int *l2r, const int *r2l, SbpFrame &F) {
     const int N = cam_off[ncam];
-    for (int i = 0; i < N; i++) assigned[i] = -1;
-    *nmatches = 0;
-    if (nmp == 0 || N == 0) return ORBX_OK;
-    if (N >= 65535) return fail(ORBX_ERR_INVALID, "more than 65534 keypoints per frame are not supported");
     int st;
-    // ---- frame side
     if ((st = upload(m, m->b[1], kps, (size_t)N * sizeof(orbx_kp))) != ORBX_OK) return st;
     if ((st = upload(m, m->b[2], desc, (size_t)N * 32)) != ORBX_OK) return st;
-    SbpFrame F;
     memset(&F, 0, sizeof(F));
     F.ncam = ncam; F.n_total = N;
     F.kps = m->b[1].as<orbx_kp>(); F.desc = (const uint4 *)m->b[2].p;
@@ -523,6 +509,28 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     M_CUDA(cudaMemcpyAsync(m->b[21].p, lr.data(), lr.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
     M_CUDA(cudaMemcpyAsync(m->b[21].as<int>() + lr.size(), rl.data(), rl.size() * sizeof(int), cudaMemcpyHostToDevice, m->stream));
     F.l2r = m->b[21].as<int>(); F.r2l = m->b[21].as<int>() + lr.size();
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
+                              const float *grid_bounds, const float *scale_factors, int nlevels, const uint8_t *occupied,
+                              const int *l2r, const int *r2l, int nmp, const uint8_t *in_view, const float *proj_x,
+                              const float *proj_y, const int *level, const float *view_cos, const float *depth, const uint8_t *bad,
+                              const uint8_t *has_obs, const uint8_t *mp_desc, float th, int far_points, float th_far_points,
+                              float nnratio, int *assigned, int *nmatches) {
+    if (!m || !cam_off || !kps || !desc || !grid_bounds || !scale_factors || !assigned || !nmatches || nmp < 0 ||
+        !(ncam == 1 || ncam == 2 || ncam == 4) || nlevels < 1 || nlevels > 32)
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    const int N = cam_off[ncam];
+    for (int i = 0; i < N; i++) assigned[i] = -1;
+    *nmatches = 0;
+    if (nmp == 0 || N == 0) return ORBX_OK;
+    if (N >= 65535) return fail(ORBX_ERR_INVALID, "more than 65534 keypoints per frame are not supported");
+    int st;
+    SbpFrame F;
+    if ((st = sbp_setup_frame(m, ncam, cam_off, kps, desc, grid_bounds, scale_factors, nlevels, occupied, l2r, r2l, F)) != ORBX_OK) return st;
     // ---- map-point side: one query per (map point, camera) in reference order
     const size_t q = (size_t)nmp * 4;
     const size_t bytes = q * (1 + 4 + 4 + 4 + 4) + (size_t)nmp * (4 + 1 + 1 + 32);
@@ -556,6 +564,7 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     P.has_obs = (const uint8_t *)put(hobs.data(), nmp);
     M_CUDA(cudaGetLastError());
     P.th = th; P.nnratio = nnratio;
+    P.mode = 0; P.forward = P.backward = P.check_ori = 0; P.max_dist = 100; P.angle = nullptr; P.u_right = P.proj_ur = nullptr;
     // ---- device work buffers
     M_CUDA(m->b[23].ensure(sbp_work_bytes(nmp, N)));
     M_CUDA(cudaEventRecord(m->ev0, m->stream));
@@ -565,6 +574,80 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     m->timed = true;
     SbpResult R;
     sbp_result_ptrs(m->b[23].as<uint8_t>(), nmp, N, &R);
+    M_CUDA(cudaMemcpyAsync(assigned, R.assigned, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(nmatches, R.nmatches, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
+                                   const float *grid_bounds, const float *scale_factors, int nlevels, const uint8_t *occupied,
+                                   const float *u_right, int npts, const uint8_t *valid, const float *proj_x, const float *proj_y,
+                                   const float *proj_ur, const int *last_octave, const float *last_angle, const uint8_t *has_obs,
+                                   const uint8_t *pt_desc, float th, int forward, int backward, int check_orientation, int max_dist,
+                                   int *assigned, int *nmatches) {
+    if (!m || !cam_off || !kps || !desc || !grid_bounds || !scale_factors || !assigned || !nmatches || npts < 0 ||
+        !(ncam == 1 || ncam == 2 || ncam == 4) || nlevels < 1 || nlevels > 32 || max_dist < 0 || max_dist > 255 ||
+        (npts && (!valid || !proj_x || !proj_y || !last_octave || !last_angle || !pt_desc)) || (u_right && !proj_ur))
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    const int N = cam_off[ncam];
+    for (int i = 0; i < N; i++) assigned[i] = -1;
+    *nmatches = 0;
+    if (npts == 0 || N == 0) return ORBX_OK;
+    if (N >= 65535) return fail(ORBX_ERR_INVALID, "more than 65534 keypoints per frame are not supported");
+    for (int i = 0; i < npts; i++)
+        if (valid[i] && (last_octave[i] < 0 || last_octave[i] >= nlevels)) return fail(ORBX_ERR_INVALID, "keypoint octave outside the level table");
+    int st;
+    SbpFrame F;
+    if ((st = sbp_setup_frame(m, ncam, cam_off, kps, desc, grid_bounds, scale_factors, nlevels, occupied, nullptr, nullptr, F)) != ORBX_OK) return st;
+    const size_t q = (size_t)npts * 4;
+    const size_t bytes = q * (1 + 4 + 4 + 4) + (size_t)npts * (4 + 4 + 1 + 1 + 32) + (size_t)N * 4;
+    M_CUDA(m->b[22].ensure(bytes + 16 * 16));
+    uint8_t *base = m->b[22].as<uint8_t>();
+    size_t off = 0;
+    auto put = [&](const void *src, size_t nb) -> void * {
+        void *d = base + off;
+        cudaMemcpyAsync(d, src, nb, cudaMemcpyHostToDevice, m->stream);
+        off += (nb + 15) & ~(size_t)15;
+        return d;
+    };
+    // per-(point, camera) arrays of the shared machinery: every camera of a point uses the octave of the last keypoint and the
+    // point's validity (the reference tests the image bounds on camera 0 only, src/ORBmatcher.cc:2021-2026)
+    std::vector<int> lvl4(q);
+    std::vector<uint8_t> view4(q), act(npts), hobs(npts);
+    for (int i = 0; i < npts; i++) {
+        for (int c = 0; c < 4; c++) { lvl4[4 * (size_t)i + c] = last_octave[i]; view4[4 * (size_t)i + c] = valid[i] ? 1 : 0; }
+        act[i] = valid[i] ? 1 : 0; hobs[i] = has_obs ? has_obs[i] : 1;
+    }
+    SbpPoints P;
+    P.nmp = npts;
+    P.proj_x = (const float *)put(proj_x, q * 4);
+    P.proj_y = (const float *)put(proj_y, q * 4);
+    P.level = (const int *)put(lvl4.data(), q * 4);
+    P.view_cos = nullptr;
+    P.desc = (const uint4 *)put(pt_desc, (size_t)npts * 32);
+    P.in_view = (const uint8_t *)put(view4.data(), q);
+    P.active = (const uint8_t *)put(act.data(), npts);
+    P.has_obs = (const uint8_t *)put(hobs.data(), npts);
+    P.angle = (const float *)put(last_angle, (size_t)npts * 4);
+    P.u_right = P.proj_ur = nullptr;
+    if (u_right && ncam == 1) {
+        P.u_right = (const float *)put(u_right, (size_t)N * 4);
+        P.proj_ur = (const float *)put(proj_ur, (size_t)npts * 4);
+    }
+    M_CUDA(cudaGetLastError());
+    P.th = th; P.nnratio = 0.0f;
+    P.mode = 1; P.forward = forward ? 1 : 0; P.backward = backward ? 1 : 0; P.check_ori = check_orientation ? 1 : 0; P.max_dist = max_dist;
+    M_CUDA(m->b[23].ensure(sbp_work_bytes(npts, N)));
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    st = sbp_run(F, P, m->b[23].as<uint8_t>(), m->b[0], m->stream, &m->last_launches);
+    if (st != ORBX_OK) return st;
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    SbpResult R;
+    sbp_result_ptrs(m->b[23].as<uint8_t>(), npts, N, &R);
     M_CUDA(cudaMemcpyAsync(assigned, R.assigned, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaMemcpyAsync(nmatches, R.nmatches, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaStreamSynchronize(m->stream));

@@ -11,6 +11,11 @@
 //            :195-201).  Final points of a round touch disjoint keypoints, so they are applied in parallel and
 //            the result equals the sequential walk.  The smallest unresolved point is always final, so the
 //            loop terminates.
+//
+// mode 1 = the frame-to-frame tracking matcher ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th,
+// bMono) (src/ORBmatcher.cc:1985-2413) on the same machinery: radius th * sf[octave of the last keypoint] for every camera,
+// level gate by bForward / bBackward, best candidate only (<= TH_HIGH), no stereo mirrors, an empty camera-0 window skips the
+// point's other cameras (the `continue` at :2062), then the rotation-histogram filter (ComputeThreeMaxima :2537-2573).
 #pragma once
 
 #include "orbx_match_kernels.cuh"
@@ -38,6 +43,10 @@ struct SbpPoints {
     const uint8_t *active, *has_obs;           // [nmp]
     const uint4 *desc;                         // [nmp][2]
     float th, nnratio;
+    // mode 1 (SearchByProjection(CurrentFrame, LastFrame)): level[q] = octave of the last keypoint, in_view[q] = projection usable
+    int mode, forward, backward, check_ori, max_dist;
+    const float *angle;                        // [nmp] kpLF.angle
+    const float *u_right, *proj_ur;            // mvuRight [N] / uv.x - mbf * invzc [nmp] (rectified stereo, ncam == 1), or NULL
 };
 
 struct SbpWork {
@@ -47,12 +56,13 @@ struct SbpWork {
     int *occ;         // [N]
     int *assigned;    // [N]
     int *resolved;    // [nmp]
-    int *nmatches;    // [4]: nmatches, unresolved count, scratch
+    int *nmatches;    // [8]: nmatches, scratch
+    int *events;      // [nmp * 4] mode 1: keypoint | rotation bin << 16 of every accepted assignment, -1 = none
 };
 struct SbpResult { const int *assigned; const int *nmatches; };
 
 inline size_t sbp_work_bytes(int nmp, int N) {
-    return ((size_t)nmp * 4 * 2 + 1 + (size_t)N * 3 + nmp + 8) * sizeof(int) + 256;
+    return ((size_t)nmp * 4 * 3 + 1 + (size_t)N * 3 + nmp + 8) * sizeof(int) + 256;
 }
 inline void sbp_carve(uint8_t *base, int nmp, int N, SbpWork *w) {
     int *p = (int *)base;
@@ -63,7 +73,8 @@ inline void sbp_carve(uint8_t *base, int nmp, int N, SbpWork *w) {
     w->occ = p; p += N;
     w->assigned = p; p += N;
     w->resolved = p; p += nmp;
-    w->nmatches = p;
+    w->nmatches = p; p += 8;
+    w->events = p;
 }
 inline void sbp_result_ptrs(uint8_t *base, int nmp, int N, SbpResult *r) {
     SbpWork w; sbp_carve(base, nmp, N, &w);
@@ -71,28 +82,43 @@ inline void sbp_result_ptrs(uint8_t *base, int nmp, int N, SbpResult *r) {
 }
 
 __device__ __forceinline__ bool sbp_query(const SbpFrame &F, const SbpPoints &P, int q, int &c, float &x, float &y, float &rr,
-                                          int &lvl) {
+                                          int &min_lvl, int &max_lvl) {
     const int mp = q >> 2;
     c = q & 3;
     if (!P.active[mp] || !P.in_view[q]) return false;
     if (c >= 1 && F.ncam < 2) return false;     // F.Nleft == -1
     if (c >= 2 && F.ncam < 4) return false;     // F.Nsideleft == -1
-    lvl = P.level[q];
+    const int lvl = P.level[q];
     if (lvl < 0) return false;                  // :142 nPredictedLevel != -1 (camera 0 assumes a valid level)
+    x = P.proj_x[q]; y = P.proj_y[q];
+    if (P.mode == 1) {
+        rr = __fmul_rn(P.th, F.scale_factors[lvl]);                            // :2040
+        if (P.forward) { min_lvl = lvl; max_lvl = -1; }                        // :2044-2056
+        else if (P.backward) { min_lvl = 0; max_lvl = lvl; }
+        else { min_lvl = lvl - 1; max_lvl = lvl + 1; }
+        return true;
+    }
     float r = ((double)P.view_cos[q] > 0.998) ? 2.5f : 4.0f;    // RadiusByViewingCos :342-347
     if (c == 0 && P.th != 1.0f) r = __fmul_rn(r, P.th);         // only camera 0 applies th (:51-52)
     rr = __fmul_rn(r, F.scale_factors[lvl]);
-    x = P.proj_x[q]; y = P.proj_y[q];
+    min_lvl = lvl - 1; max_lvl = lvl;
     return true;
+}
+
+__device__ __forceinline__ int sbp_window_count(const SbpFrame &F, const SbpPoints &P, int q) {
+    int c, mn, mx, n = 0; float x, y, rr;
+    if (sbp_query(F, P, q, c, x, y, rr, mn, mx))
+        grid_query(F.kps + F.cam_off[c], F.cell_start[c], F.cell_items[c], F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], x, y, rr, mn, mx,
+                   [&](int) { n++; });
+    return n;
 }
 
 __global__ void k_sbp_count(SbpFrame F, SbpPoints P, int *__restrict__ counts) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.nmp * 4) return;
-    int c, lvl, n = 0; float x, y, rr;
-    if (sbp_query(F, P, q, c, x, y, rr, lvl))
-        grid_query(F.kps + F.cam_off[c], F.cell_start[c], F.cell_items[c], F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], x, y, rr,
-                   lvl - 1, lvl, [&](int) { n++; });
+    int n = sbp_window_count(F, P, q);
+    // mode 1: `if (vIndices2.empty()) continue;` on camera 0 (:2062) leaves the point's other cameras unsearched
+    if (P.mode == 1 && (q & 3) != 0 && n > 0 && sbp_window_count(F, P, q & ~3) == 0) n = 0;
     counts[q] = n;
 }
 
@@ -100,28 +126,30 @@ __global__ void k_sbp_count(SbpFrame F, SbpPoints P, int *__restrict__ counts) {
 __global__ void k_sbp_fill(SbpFrame F, SbpPoints P, const int *__restrict__ q_ptr, uint32_t *__restrict__ cand) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.nmp * 4) return;
-    int c, lvl; float x, y, rr;
-    if (!sbp_query(F, P, q, c, x, y, rr, lvl)) return;
+    int c, mn, mx; float x, y, rr;
+    if (q_ptr[q + 1] == q_ptr[q] || !sbp_query(F, P, q, c, x, y, rr, mn, mx)) return;
     const int mp = q >> 2;
+    const bool ur_check = P.mode == 1 && c == 0 && F.ncam == 1 && P.u_right != nullptr;
     const uint4 qa = P.desc[2 * mp], qb = P.desc[2 * mp + 1];
     int o = q_ptr[q];
     const orbx_kp *ck = F.kps + F.cam_off[c];
     const uint4 *cd = F.desc + 2 * (long long)F.cam_off[c];
-    grid_query(ck, F.cell_start[c], F.cell_items[c], F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], x, y, rr, lvl - 1, lvl,
+    grid_query(ck, F.cell_start[c], F.cell_items[c], F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], x, y, rr, mn, mx,
                [&](int idx) {
-                   const int d = hamming256(qa, qb, cd[2 * idx], cd[2 * idx + 1]);
+                   int d = hamming256(qa, qb, cd[2 * idx], cd[2 * idx + 1]);
+                   if (ur_check && P.u_right[idx] > 0.0f && fabsf(__fsub_rn(P.proj_ur[mp], P.u_right[idx])) > rr) d = 511;   // :2079-2084
                    cand[o++] = (uint32_t)idx | ((uint32_t)d << 16) | ((uint32_t)(ck[idx].octave & 0x7F) << 25);
                });
 }
 
 template <class Fn>
-__device__ __forceinline__ void sbp_for_touch(const SbpFrame &F, const int *q_ptr, const uint32_t *cand, int mp, Fn fn) {
+__device__ __forceinline__ void sbp_for_touch(const SbpFrame &F, bool mirrors, const int *q_ptr, const uint32_t *cand, int mp, Fn fn) {
     for (int c = 0; c < 4; c++) {
         const int q = mp * 4 + c;
         for (int k = q_ptr[q]; k < q_ptr[q + 1]; k++) {
             const int idx = (int)(cand[k] & 0xFFFF);
             fn(idx + F.cam_off[c]);
-            if (F.ncam >= 2) {
+            if (mirrors && F.ncam >= 2) {
                 if (c == 0 && F.l2r[idx] != -1) fn(F.l2r[idx] + F.cam_off[1]);
                 if (c == 1 && F.r2l[idx] != -1) fn(F.r2l[idx]);
             }
@@ -135,6 +163,8 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
     for (int g = threadIdx.x; g < N; g += blockDim.x) { W.occ[g] = F.occupied0[g]; W.assigned[g] = -1; }
     for (int u = threadIdx.x; u < nmp; u += blockDim.x) W.resolved[u] = (W.q_ptr[4 * u + 4] == W.q_ptr[4 * u]) ? 1 : 0;
     if (threadIdx.x == 0) W.nmatches[0] = 0;
+    if (P.mode == 1)
+        for (int e = threadIdx.x; e < 4 * nmp; e += blockDim.x) W.events[e] = -1;
     __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) s_left = 0;
@@ -142,13 +172,13 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
         __syncthreads();
         for (int u = threadIdx.x; u < nmp; u += blockDim.x) {
             if (W.resolved[u]) continue;
-            sbp_for_touch(F, W.q_ptr, cand, u, [&](int g) { atomicMin(&W.tmin[g], u); });
+            sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, [&](int g) { atomicMin(&W.tmin[g], u); });
         }
         __syncthreads();
         for (int u = threadIdx.x; u < nmp; u += blockDim.x) {
             if (W.resolved[u]) continue;
             bool fin = true;
-            sbp_for_touch(F, W.q_ptr, cand, u, [&](int g) { if (W.tmin[g] != u) fin = false; });
+            sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, [&](int g) { if (W.tmin[g] != u) fin = false; });
             if (!fin) { atomicAdd(&s_left, 1); continue; }
             // ---- sequential body of the reference for map point u
             int nm = 0;
@@ -156,6 +186,27 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
                 const int q = u * 4 + c;
                 const int b = W.q_ptr[q], e = W.q_ptr[q + 1];
                 if (b == e) continue;
+                if (P.mode == 1) {   // best candidate only, every camera on its own (:2068-2100 and the per-camera clones)
+                    int bestDist = 256, bestIdx = -1;
+                    for (int k = b; k < e; k++) {
+                        const uint32_t r = cand[k];
+                        const int idx = (int)(r & 0xFFFF), dist = (int)((r >> 16) & 0x1FF);
+                        if (W.occ[idx + F.cam_off[c]]) continue;
+                        if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+                    }
+                    if (bestDist <= P.max_dist) {   // TH_HIGH (:2103), ORBdist in the relocalisation overload (:2487)
+                        const int g = bestIdx + F.cam_off[c];
+                        W.assigned[g] = u; W.occ[g] = P.has_obs[u]; nm++;
+                        if (P.check_ori) {   // :2121-2128
+                            float rot = __fsub_rn(P.angle[u], F.kps[g].angle);
+                            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                            int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30.0f));
+                            if (bin == 30) bin = 0;
+                            W.events[q] = g | (bin << 16);
+                        }
+                    }
+                    continue;
+                }
                 int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
                 for (int k = b; k < e; k++) {
                     const uint32_t r = cand[k];
@@ -189,6 +240,33 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
         __syncthreads();
         if (s_left == 0) break;
         __syncthreads();
+    }
+    if (P.mode != 1 || !P.check_ori) return;
+    // ---- rotation consistency (:2392-2410): keep the assignments of the three fullest histogram bins
+    __shared__ int s_hist[32], s_ind[3];
+    if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * nmp; e += blockDim.x)
+        if (W.events[e] >= 0) atomicAdd(&s_hist[(W.events[e] >> 16) & 31], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {   // ComputeThreeMaxima (:2537-2573)
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; i++) {
+            const int sz = s_hist[i];
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+        s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * nmp; e += blockDim.x) {
+        const int ev = W.events[e];
+        if (ev < 0) continue;
+        const int bin = (ev >> 16) & 31;
+        if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { W.assigned[ev & 0xFFFF] = -1; atomicSub(&W.nmatches[0], 1); }
     }
 }
 

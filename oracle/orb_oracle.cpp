@@ -924,6 +924,80 @@ int orc_search_by_projection(int ncam, const int *cam_off, const orc_kp *kps, co
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), ORBmatcher.cc:1985-2413, over plain
+// arrays (frame side as in orc_search_by_projection).  Per last-frame keypoint i: valid[i] (pMP && !outlier && invzc >= 0 && camera-0
+// projection in bounds, :2008-2026), proj_x / proj_y [npts][4] (what the reference hands to GetFeaturesInArea for camera c: the side
+// cameras get the LEFT uv, :2250-2271), proj_ur[i] = uv.x - mbf * invzc, octave / angle of the last keypoint, has_obs, descriptor.
+// Output: assigned[idx] = i written to CurrentFrame.mvpMapPoints[idx] (-1 = untouched or cleared by the rotation filter).
+int orc_search_by_projection_last(int ncam, const int *cam_off, const orc_kp *kps, const uint8_t *desc, void **grids, const float *sf,
+                                  const uint8_t *occupied, const float *u_right, int npts, const uint8_t *valid, const float *proj_x,
+                                  const float *proj_y, const float *proj_ur, const int *last_octave, const float *last_angle,
+                                  const uint8_t *has_obs, const uint8_t *pt_desc, float th, int bForward, int bBackward,
+                                  int checkOrientation, int maxDist, int *assigned) {
+    // maxDist = TH_HIGH (:2103); the relocalisation overload (Frame, KeyFrame, sAlreadyFound, th, ORBdist) (:2415-2535) has the same
+    // body for one camera with ORBdist in its place (:2487)
+    const int N = cam_off[ncam];
+    const int HISTO_LENGTH = 30;
+    std::vector<uint8_t> occ(N, 0);
+    if (occupied) occ.assign(occupied, occupied + N);
+    for (int i = 0; i < N; i++) assigned[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> cand;
+    for (int i = 0; i < npts; i++) {
+        if (!valid[i]) continue;
+        const int nLastOctave = last_octave[i];
+        const float radius = th * sf[nLastOctave];                                              // :2040
+        for (int c = 0; c < ncam; c++) {
+            const KeyPt *ck = (const KeyPt *)kps + cam_off[c];
+            const float u = proj_x[4 * i + c], v = proj_y[4 * i + c];
+            if (bForward) features_in_area(*(Grid *)grids[c], ck, u, v, radius, nLastOctave, -1, cand);
+            else if (bBackward) features_in_area(*(Grid *)grids[c], ck, u, v, radius, 0, nLastOctave, cand);
+            else features_in_area(*(Grid *)grids[c], ck, u, v, radius, nLastOctave - 1, nLastOctave + 1, cand);
+            if (c == 0 && cand.empty()) break;                                                  // :2062 `continue` of the point loop
+            int bestDist = 256, bestIdx2 = -1;
+            for (int i2 : cand) {
+                const int g = i2 + cam_off[c];
+                if (occ[g]) continue;
+                if (c == 0 && ncam == 1 && u_right && u_right[i2] > 0) {                          // :2079-2084
+                    const float er = fabsf(proj_ur[i] - u_right[i2]);
+                    if (er > radius) continue;
+                }
+                const int dist = descriptor_distance(pt_desc + (size_t)i * 32, desc + (size_t)g * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+            }
+            if (bestDist <= maxDist) {
+                const int g = bestIdx2 + cam_off[c];
+                assigned[g] = i; occ[g] = has_obs ? has_obs[i] : 1;
+                nmatches++;
+                if (checkOrientation) {
+                    float rot = last_angle[i] - ck[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(g);
+                }
+            }
+        }
+    }
+    if (checkOrientation) {                                                                     // :2392-2410 + ComputeThreeMaxima :2537-2573
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int g : rotHist[i]) { assigned[g] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
 // ORBmatcher::SearchForTriangulation Hamming core, ORBmatcher.cc:1218-1427, with the vocabulary FeatureVectors
 // given as CSR (sorted node ids + index lists) and the geometry test as an optional pair mask.
 //   nodes1[nn1], ptr1[nn1+1], idx1[...] : KF1 feature vector ; same for KF2

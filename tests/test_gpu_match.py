@@ -245,6 +245,110 @@ def test_search_by_projection(ncam, th, far):
     assert nm > 500
 
 
+def _sbp_last_case(ncam, seed, n=4000):
+    """Current frame = keypoints extracted from `ncam` 512x512 synthetic images; last-frame keypoints with map points observe
+    current keypoints (+-3 px, octave +-1, angle = current + 20 deg +- 3 for 85 %, random otherwise)."""
+    rng = np.random.default_rng(seed)
+    w = h = 512
+    rig, res = _extract_frame(w, h, 1500, [4700 + seed * 10 + c for c in range(ncam)], (0, 511))
+    kps = np.concatenate([r[1] for r in res]); desc = np.concatenate([r[2] for r in res])
+    cam_off = np.concatenate([[0], np.cumsum([len(r[1]) for r in res])]).astype(np.int32)
+    N = int(cam_off[-1])
+    valid = (rng.random(n) < 0.93).astype(np.uint8)
+    px = np.zeros((n, 4), np.float32); py = np.zeros((n, 4), np.float32)
+    octv = np.zeros(n, np.int32); ang = np.zeros(n, np.float32); pd = synth_descriptors(n, seed + 1)
+    for i in range(n):
+        k = int(rng.integers(0, N))
+        cam = int(np.searchsorted(cam_off, k, side='right') - 1)
+        if rng.random() < 0.75:
+            pd[i] = desc[k] ^ np.packbits(rng.random(256) < 0.06, bitorder='little')
+        for c in range(ncam):
+            if c == cam or (c >= 2 and cam == 0):        # the side cameras are searched around the LEFT projection (D6)
+                px[i, c] = kps['x'][k] + rng.uniform(-3, 3); py[i, c] = kps['y'][k] + rng.uniform(-3, 3)
+            elif c == 0 and rng.random() < 0.5:
+                px[i, c] = rng.uniform(-40, 560); py[i, c] = rng.uniform(-40, 560)     # often an empty camera-0 window
+            else:
+                kk = int(rng.integers(cam_off[c], cam_off[c + 1]))
+                px[i, c] = kps['x'][kk] + rng.uniform(-3, 3); py[i, c] = kps['y'][kk] + rng.uniform(-3, 3)
+        octv[i] = min(7, max(0, int(kps['octave'][k]) + int(rng.integers(-1, 2))))
+        ang[i] = (kps['angle'][k] + (20 + rng.uniform(-3, 3) if rng.random() < 0.85 else rng.uniform(0, 360))) % 360.0
+    frame = dict(cam_off=cam_off, kps=kps, desc=desc, bounds=np.tile(np.array([0, w, 0, h], np.float32), (ncam, 1)),
+                 scale_factors=rig.scale, occupied=(rng.random(N) < 0.05).astype(np.uint8))
+    last = dict(valid=valid, proj_x=px, proj_y=py, octave=octv, angle=ang, desc=pd, has_obs=(rng.random(n) < 0.85).astype(np.uint8))
+    if ncam == 1:
+        frame['u_right'] = np.where(rng.random(N) < 0.4, kps['x'] - rng.uniform(2, 40, N), -1).astype(np.float32)
+        last['proj_ur'] = (px[:, 0] - rng.uniform(0, 45, n)).astype(np.float32)
+    return frame, last
+
+
+def _oracle_sbp_last(frame, last, th, fwd, bwd, check, max_dist=100):
+    L = O.lib()
+    cam_off = frame['cam_off']; ncam = len(cam_off) - 1; N = int(cam_off[-1])
+    kps = np.ascontiguousarray(frame['kps']); desc = np.ascontiguousarray(frame['desc'])
+    grids = (C.c_void_p * 4)()
+    for c in range(ncam):
+        b = frame['bounds'][c]
+        sub = np.ascontiguousarray(kps[cam_off[c]:cam_off[c + 1]])
+        grids[c] = L.orc_grid_create(O.p(sub), sub.size, C.c_float(b[0]), C.c_float(b[1]), C.c_float(b[2]), C.c_float(b[3]))
+    assigned = np.zeros(N, np.int32)
+    opt = lambda a: None if a is None else O.p(a)
+    n = L.orc_search_by_projection_last(ncam, O.p(cam_off), O.p(kps), O.p(desc), grids, O.p(frame['scale_factors']), O.p(frame['occupied']),
+                                        opt(frame.get('u_right')), last['valid'].size, O.p(last['valid']), O.p(last['proj_x']),
+                                        O.p(last['proj_y']), opt(last.get('proj_ur')), O.p(last['octave']), O.p(last['angle']),
+                                        opt(last.get('has_obs')), O.p(last['desc']), C.c_float(th), int(fwd), int(bwd), int(check), int(max_dist), O.p(assigned))
+    for c in range(ncam):
+        L.orc_grid_destroy(C.c_void_p(grids[c]))
+    return n, assigned
+
+
+@pytest.mark.parametrize('ncam,th,fwd,bwd,check', [(1, 15.0, False, False, True), (1, 7.0, True, False, True), (2, 15.0, False, True, True),
+                                                   (2, 7.0, False, False, False), (4, 15.0, False, False, True), (4, 7.0, True, False, True)])
+def test_search_by_projection_last_frame(ncam, th, fwd, bwd, check):
+    """src/ORBmatcher.cc:1985-2413: claims in point order, empty camera-0 window skips the point, rotation-histogram filter."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    frame, last = _sbp_last_case(ncam, seed=ncam * 5 + int(th))
+    M = ob.ORBmatcher(0.9, checkOri=check)
+    nm, assigned = M.SearchByProjectionLast(frame, last, th, fwd, bwd)
+    rn, rassigned = _oracle_sbp_last(frame, last, th, fwd, bwd, check)
+    assert rn == nm, (rn, nm)
+    assert np.array_equal(assigned, rassigned), int((assigned != rassigned).sum())
+    assert nm > 300
+    if check:   # the filter did remove something: without it there are more matches
+        n_all, _ = _oracle_sbp_last(frame, last, th, fwd, bwd, False)
+        assert n_all > rn
+
+
+@pytest.mark.parametrize('orb_dist,th', [(100, 10.0), (64, 15.0)])
+def test_search_by_projection_relocalisation_overload(orb_dist, th):
+    """SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:2415-2535) through the same entry point:
+    camera 0 only, every claim visible, gate [l-1, l+1], ORBdist."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    frame, last = _sbp_last_case(1, seed=21 + orb_dist)
+    frame.pop('u_right'); last.pop('proj_ur'); last['has_obs'] = None
+    M = ob.ORBmatcher(0.9)
+    nm, assigned = M.SearchByProjectionLast(frame, last, th, max_dist=orb_dist)
+    rn, rassigned = _oracle_sbp_last(frame, last, th, False, False, True, orb_dist)
+    assert rn == nm and np.array_equal(assigned, rassigned)
+    assert nm > 300
+    # every claim is visible: no current keypoint receives two map points, none of the pre-occupied ones is touched
+    assert (assigned[frame['occupied'] == 1] == -1).all()
+
+
+def test_search_by_projection_last_frame_degenerate():
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    frame, last = _sbp_last_case(2, seed=3, n=50)
+    M = ob.ORBmatcher(0.9)
+    last0 = {k: (v[:0] if isinstance(v, np.ndarray) else v) for k, v in last.items()}
+    nm, assigned = M.SearchByProjectionLast(frame, last0, 7.0)
+    assert nm == 0 and (assigned == -1).all()
+    last['valid'][:] = 0
+    nm, assigned = M.SearchByProjectionLast(frame, last, 7.0)
+    assert nm == 0 and (assigned == -1).all()
+
+
 def test_popc_peak_reports_a_rate():
     if ob.device_count() == 0:
         pytest.fail('no CUDA device')
