@@ -217,6 +217,26 @@ int orbx_search_for_triangulation(orbx_matcher *m, int nn1, const int *nodes1, c
                                   const uint8_t *desc1, int n1, const uint8_t *desc2, int n2, const uint8_t *skip1,
                                   const uint8_t *skip2, int *match12, int *nmatches);
 
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vpMapPointMatches) (src/ORBmatcher.cc:349-666), the whole function: the two
+ * FeatureVectors as CSR (ascending node ids, feature index lists in insertion order); skip_kf[i] = the KeyFrame feature has no
+ * usable MapPoint (:377-380); angle_kf / angle_f = keypoint angles by feature index (only read with check_orientation);
+ * ncam_f = 1 for F.Nleft == -1, else 2 or 4 with the camera blocks cam_off_f[0..ncam_f] of F's feature indices (:406-452).
+ * Per shared node and KeyFrame feature, in order: best / second-best distance per camera over the F features not matched yet;
+ * camera 0 needs dist <= TH_LOW and the mfNNratio test, cameras 1-3 only dist <= TH_LOW (the reference's `|| true`), all nested in
+ * camera 0's TH_LOW test (:456); then the rotation-histogram filter (:637-663).  match_f[n_f] = KeyFrame feature index whose
+ * MapPoint goes to vpMapPointMatches[i] (or -1), *nmatches = the return value.  HOST pointers. */
+int orbx_search_by_bow_frame(orbx_matcher *m, int nn_kf, const int *nodes_kf, const int *ptr_kf, const int *idx_kf, int nn_f,
+                             const int *nodes_f, const int *ptr_f, const int *idx_f, const uint8_t *desc_kf, int n_kf,
+                             const uint8_t *desc_f, int n_f, const uint8_t *skip_kf, const float *angle_kf, const float *angle_f,
+                             int ncam_f, const int *cam_off_f, float nnratio, int check_orientation, int *match_f, int *nmatches);
+/* ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vpMatches12) (src/ORBmatcher.cc:1006-1129): skip1 / skip2 = feature
+ * without usable MapPoint or beyond N (:1036-1044, 1052-1061); best < TH_LOW (strict) and the mfNNratio test; vbMatched2 keeps a
+ * second-list feature from being matched twice; rotation-histogram filter.  match12[n1] = idx2 (or -1).  HOST pointers. */
+int orbx_search_by_bow_keyframes(orbx_matcher *m, int nn1, const int *nodes1, const int *ptr1, const int *idx1, int nn2, const int *nodes2,
+                                 const int *ptr2, const int *idx2, const uint8_t *desc1, int n1, const uint8_t *desc2, int n2,
+                                 const uint8_t *skip1, const uint8_t *skip2, const float *angle1, const float *angle2, float nnratio,
+                                 int check_orientation, int *match12, int *nmatches);
+
 /* Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea (src/Frame.cc:541-582, 890-967, 969-978) for one
  * camera: builds the 64x48 grid of `kps` on the device and answers nq window queries, producing CSR
  * candidate lists in the reference's order (cell column-major, insertion order inside a cell).

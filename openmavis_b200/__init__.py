@@ -382,6 +382,40 @@ class ORBmatcher:
         pairs = [(int(i), int(m12[i])) for i in np.nonzero(m12 >= 0)[0]]
         return nm.value, pairs, m12
 
+    def SearchByBoW(self, fv_kf, fv_f, desc_kf, desc_f, skip_kf=None, angle_kf=None, angle_f=None, cam_off_f=None):
+        """ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vpMapPointMatches) (src/ORBmatcher.cc:349-666), whole function.
+        fv = (nodes, ptr, idx) CSR of a DBoW2 FeatureVector; cam_off_f = None (F.Nleft == -1) or the 3 / 5 camera block offsets.
+        Returns (nmatches, match_f[n_f]) — match_f[i] = KeyFrame feature whose MapPoint goes to vpMapPointMatches[i]."""
+        n1n, p1, i1 = (np.ascontiguousarray(x, np.int32) for x in fv_kf)
+        n2n, p2, i2 = (np.ascontiguousarray(x, np.int32) for x in fv_f)
+        d1 = np.ascontiguousarray(desc_kf, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc_f, np.uint8).reshape(-1, 32)
+        s1 = None if skip_kf is None else np.ascontiguousarray(skip_kf, np.uint8)
+        a1 = None if angle_kf is None else np.ascontiguousarray(angle_kf, np.float32)
+        a2 = None if angle_f is None else np.ascontiguousarray(angle_f, np.float32)
+        co = None if cam_off_f is None else np.ascontiguousarray(cam_off_f, np.int32)
+        ncam = 1 if co is None else co.size - 1
+        match = np.full(max(d2.shape[0], 1), -1, np.int32); nm = C.c_int(0)
+        _check(self.L.orbx_search_by_bow_frame(self.h, n1n.size, _p(n1n), _p(p1), _p(i1), n2n.size, _p(n2n), _p(p2), _p(i2), _p(d1),
+                                               d1.shape[0], _p(d2), d2.shape[0], _p(s1), _p(a1), _p(a2), ncam, _p(co),
+                                               C.c_float(self.mfNNratio), int(self.mbCheckOrientation), _p(match), C.byref(nm)))
+        return nm.value, match[:d2.shape[0]]
+
+    def SearchByBoWKeyFrames(self, fv1, fv2, desc1, desc2, skip1=None, skip2=None, angle1=None, angle2=None):
+        """ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vpMatches12) (src/ORBmatcher.cc:1006-1129), whole function.
+        Returns (nmatches, match12[n1]) — match12[idx1] = idx2 whose MapPoint goes to vpMatches12[idx1]."""
+        n1n, p1, i1 = (np.ascontiguousarray(x, np.int32) for x in fv1)
+        n2n, p2, i2 = (np.ascontiguousarray(x, np.int32) for x in fv2)
+        d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        s1 = None if skip1 is None else np.ascontiguousarray(skip1, np.uint8)
+        s2 = None if skip2 is None else np.ascontiguousarray(skip2, np.uint8)
+        a1 = None if angle1 is None else np.ascontiguousarray(angle1, np.float32)
+        a2 = None if angle2 is None else np.ascontiguousarray(angle2, np.float32)
+        match = np.full(max(d1.shape[0], 1), -1, np.int32); nm = C.c_int(0)
+        _check(self.L.orbx_search_by_bow_keyframes(self.h, n1n.size, _p(n1n), _p(p1), _p(i1), n2n.size, _p(n2n), _p(p2), _p(i2), _p(d1),
+                                                   d1.shape[0], _p(d2), d2.shape[0], _p(s1), _p(s2), _p(a1), _p(a2),
+                                                   C.c_float(self.mfNNratio), int(self.mbCheckOrientation), _p(match), C.byref(nm)))
+        return nm.value, match[:d1.shape[0]]
+
     def ComputeDistinctiveDescriptors(self, desc, ptr):
         """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483) for many map points: desc[total,32], ptr[ngroups+1]
         -> best index inside each group (-1 for an empty group)."""

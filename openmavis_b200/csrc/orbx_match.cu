@@ -10,6 +10,7 @@
 #include "orbx_match_kernels.cuh"
 #include "orbx_sbp_kernels.cuh"
 #include "orbx_fisheye_kernels.cuh"
+#include "orbx_bow_kernels.cuh"
 
 using namespace orbx;
 
@@ -387,6 +388,105 @@ int orbx_search_for_triangulation(orbx_matcher *m, int nn1, const int *nodes1, c
     for (int i = 0; i < n1; i++) nm += match12[i] >= 0;
     if (nmatches) *nmatches = nm;
     return ORBX_OK;
+}
+
+// ---- SearchByBoW (src/ORBmatcher.cc:349-666, 1006-1129)
+static int search_by_bow_impl(orbx_matcher *m, int variant, int nn1, const int *nodes1, const int *ptr1, const int *idx1, int nn2,
+                              const int *nodes2, const int *ptr2, const int *idx2, const uint8_t *desc1, int n1, const uint8_t *desc2,
+                              int n2, const uint8_t *skip1, const uint8_t *skip2, const float *angle1, const float *angle2, int ncam2,
+                              const int *cam_off2, float nnratio, int check_orientation, int *match, int *nmatches) {
+    const int nout = variant == 0 ? n2 : n1;
+    if (!m || !match || !nmatches || n1 < 0 || n2 < 0 || nn1 < 0 || nn2 < 0 || (nn1 && (!nodes1 || !ptr1 || !idx1)) ||
+        (nn2 && (!nodes2 || !ptr2 || !idx2)) || (n1 && !desc1) || (n2 && !desc2) || (check_orientation && n1 && n2 && (!angle1 || !angle2)) ||
+        (variant == 0 && !(ncam2 == 1 || ((ncam2 == 2 || ncam2 == 4) && cam_off2))))
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    for (int i = 0; i < nout; i++) match[i] = -1;
+    *nmatches = 0;
+    if (n1 == 0 || n2 == 0 || nn1 == 0 || nn2 == 0) return ORBX_OK;
+    if (n1 >= 65535 || n2 >= 65535) return fail(ORBX_ERR_INVALID, "more than 65534 features per frame are not supported");
+    const int tot1 = ptr1[nn1], tot2 = ptr2[nn2];
+    for (int k = 0; k < tot1; k++)
+        if (idx1[k] < 0 || idx1[k] >= n1) return fail(ORBX_ERR_INVALID, "idx1 out of range");
+    for (int k = 0; k < tot2; k++)
+        if (idx2[k] < 0 || idx2[k] >= n2) return fail(ORBX_ERR_INVALID, "idx2 out of range");
+    // merge-walk of the two FeatureVectors (:363-369, 626-634): the shared nodes
+    std::vector<int> pa, pb;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) { pa.push_back(a); pb.push_back(b); a++; b++; }
+        else if (nodes1[a] < nodes2[b]) a = (int)(std::lower_bound(nodes1 + a, nodes1 + nn1, nodes2[b]) - nodes1);
+        else b = (int)(std::lower_bound(nodes2 + b, nodes2 + nn2, nodes1[a]) - nodes2);
+    }
+    const int npairs = (int)pa.size();
+    if (npairs == 0) return ORBX_OK;
+    std::vector<uint8_t> s1(n1, 0), s2(n2, 0);
+    if (skip1) memcpy(s1.data(), skip1, n1);
+    if (skip2) memcpy(s2.data(), skip2, n2);
+    std::vector<float> zero;
+    if (!check_orientation) { zero.assign(std::max(n1, n2), 0.0f); angle1 = angle2 = zero.data(); }
+    int st;
+    if ((st = upload(m, m->b[1], desc1, (size_t)n1 * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], desc2, (size_t)n2 * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[3], pa.data(), (size_t)npairs * 4)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[4], pb.data(), (size_t)npairs * 4)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[5], ptr1, (size_t)(nn1 + 1) * 4)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[6], idx1, (size_t)tot1 * 4)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[7], ptr2, (size_t)(nn2 + 1) * 4)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[8], idx2, (size_t)tot2 * 4)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[9], s1.data(), (size_t)n1)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[10], s2.data(), (size_t)n2)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[11], angle1, (size_t)n1 * 4)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[12], angle2, (size_t)n2 * 4)) != ORBX_OK) return st;
+    // work: match [nout] | events [4 n1] (both -1) | claimed2 [n2] | nmatches [1] (both 0)
+    const size_t o_ev = (size_t)nout, o_cl = o_ev + 4 * (size_t)n1, o_nm = o_cl + n2;
+    M_CUDA(m->b[13].ensure((o_nm + 1) * 4));
+    int *w = m->b[13].as<int>();
+    M_CUDA(cudaMemsetAsync(w, 0xFF, o_cl * 4, m->stream));
+    M_CUDA(cudaMemsetAsync(w + o_cl, 0, ((size_t)n2 + 1) * 4, m->stream));
+    BowArgs A;
+    A.variant = variant; A.npairs = npairs;
+    A.pair_a = m->b[3].as<int>(); A.pair_b = m->b[4].as<int>();
+    A.ptr1 = m->b[5].as<int>(); A.idx1 = m->b[6].as<int>(); A.ptr2 = m->b[7].as<int>(); A.idx2 = m->b[8].as<int>();
+    A.desc1 = (const uint4 *)m->b[1].p; A.desc2 = (const uint4 *)m->b[2].p;
+    A.skip1 = m->b[9].as<uint8_t>(); A.skip2 = m->b[10].as<uint8_t>();
+    A.angle1 = m->b[11].as<float>(); A.angle2 = m->b[12].as<float>();
+    A.ncam2 = variant == 0 ? ncam2 : 1;
+    for (int c = 0; c < 5; c++) A.cam_off2[c] = (variant == 0 && ncam2 > 1 && c <= ncam2) ? cam_off2[c] : n2;
+    A.nnratio = nnratio; A.check_ori = check_orientation ? 1 : 0;
+    A.match = w; A.events = w + o_ev; A.claimed2 = w + o_cl; A.nmatches = w + o_nm;
+    A.n1 = n1; A.n2 = n2;
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    k_bow_match<<<(npairs + 3) / 4, 128, 0, m->stream>>>(A);
+    m->last_launches = 1;
+    if (check_orientation) {
+        k_rot_filter<<<1, 1024, 0, m->stream>>>(A.events, 4 * n1, A.match, A.nmatches);
+        m->last_launches++;
+    }
+    M_CUDA(cudaGetLastError());
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    M_CUDA(cudaMemcpyAsync(match, w, (size_t)nout * 4, cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(nmatches, w + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_search_by_bow_frame(orbx_matcher *m, int nn_kf, const int *nodes_kf, const int *ptr_kf, const int *idx_kf, int nn_f,
+                             const int *nodes_f, const int *ptr_f, const int *idx_f, const uint8_t *desc_kf, int n_kf,
+                             const uint8_t *desc_f, int n_f, const uint8_t *skip_kf, const float *angle_kf, const float *angle_f,
+                             int ncam_f, const int *cam_off_f, float nnratio, int check_orientation, int *match_f, int *nmatches) {
+    return search_by_bow_impl(m, 0, nn_kf, nodes_kf, ptr_kf, idx_kf, nn_f, nodes_f, ptr_f, idx_f, desc_kf, n_kf, desc_f, n_f, skip_kf, nullptr,
+                              angle_kf, angle_f, ncam_f, cam_off_f, nnratio, check_orientation, match_f, nmatches);
+}
+
+int orbx_search_by_bow_keyframes(orbx_matcher *m, int nn1, const int *nodes1, const int *ptr1, const int *idx1, int nn2, const int *nodes2,
+                                 const int *ptr2, const int *idx2, const uint8_t *desc1, int n1, const uint8_t *desc2, int n2,
+                                 const uint8_t *skip1, const uint8_t *skip2, const float *angle1, const float *angle2, float nnratio,
+                                 int check_orientation, int *match12, int *nmatches) {
+    return search_by_bow_impl(m, 1, nn1, nodes1, ptr1, idx1, nn2, nodes2, ptr2, idx2, desc1, n1, desc2, n2, skip1, skip2, angle1, angle2, 1,
+                              nullptr, nnratio, check_orientation, match12, nmatches);
 }
 
 // builds the device grid of one camera into buffers b[base .. base+3]; returns device pointers

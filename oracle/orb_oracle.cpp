@@ -1039,6 +1039,126 @@ int orc_search_for_triangulation(int nn1, const int *nodes1, const int *ptr1, co
 }
 
 
+// ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), ORBmatcher.cc:349-666, over plain arrays ------------------------
+// FeatureVectors as CSR (sorted node ids, index lists); skipKF[i] = !pMP || pMP->isBad(); angles by feature index; ncamF = 1 for
+// F.Nleft == -1, else 2 / 4 with camOffF = {0, Nleft, Nleft+Nright, +Nsideleft, +Nsideright}.  matchF[nF] = realIdxKF or -1.
+static int three_maxima_filter(std::vector<int> *rotHist, int *match) {   // :637-663 + ComputeThreeMaxima :2537-2573
+    const int L = 30;
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1, removed = 0;
+    for (int i = 0; i < L; i++) {
+        const int sz = (int)rotHist[i].size();
+        if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+        else if (sz > max3) { max3 = sz; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        if (i == ind1 || i == ind2 || i == ind3) continue;
+        for (int j : rotHist[i]) { match[j] = -1; removed++; }
+    }
+    return removed;
+}
+static int rot_bin(float a1, float a2) {
+    const float factor = 1.0f / 30;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == 30) bin = 0;
+    return bin;
+}
+
+int orc_search_by_bow_frame(int nnKF, const int *nodesKF, const int *ptrKF, const int *idxKF, int nnF, const int *nodesF, const int *ptrF,
+                            const int *idxF, const uint8_t *descKF, const uint8_t *descF, int nF, const uint8_t *skipKF, const float *angleKF,
+                            const float *angleF, int ncamF, const int *camOffF, float nnratio, int checkOrientation, int *matchF) {
+    const int TH_LOW = 50;
+    for (int i = 0; i < nF; i++) matchF[i] = -1;
+    std::vector<int> rotHist[30];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nnKF && b < nnF) {
+        if (nodesKF[a] == nodesF[b]) {
+            for (int iKF = ptrKF[a]; iKF < ptrKF[a + 1]; iKF++) {
+                const int realIdxKF = idxKF[iKF];
+                if (skipKF && skipKF[realIdxKF]) continue;
+                const uint8_t *dKF = descKF + (size_t)realIdxKF * 32;
+                int bestDist1[4] = {256, 256, 256, 256}, bestIdx[4] = {-1, -1, -1, -1}, bestDist2[4] = {256, 256, 256, 256};
+                for (int iF = ptrF[b]; iF < ptrF[b + 1]; iF++) {
+                    const int realIdxF = idxF[iF];
+                    if (matchF[realIdxF] >= 0) continue;
+                    const int dist = descriptor_distance(dKF, descF + (size_t)realIdxF * 32);
+                    int c = 0;
+                    if (ncamF > 1) {
+                        c = -1;
+                        for (int k = 0; k < ncamF; k++) if (realIdxF >= camOffF[k] && realIdxF < camOffF[k + 1]) c = k;
+                        if (c < 0) continue;
+                    }
+                    if (dist < bestDist1[c]) { bestDist2[c] = bestDist1[c]; bestDist1[c] = dist; bestIdx[c] = realIdxF; }
+                    else if (dist < bestDist2[c]) bestDist2[c] = dist;
+                }
+                if (bestDist1[0] <= TH_LOW) {
+                    for (int c = 0; c < (ncamF > 1 ? ncamF : 1); c++) {
+                        if (c == 0) { if (!((float)bestDist1[0] < nnratio * (float)bestDist2[0])) continue; }
+                        else if (!(bestDist1[c] <= TH_LOW)) continue;                       // ratio test disabled by `|| true`
+                        matchF[bestIdx[c]] = realIdxKF;
+                        if (checkOrientation) rotHist[rot_bin(angleKF[realIdxKF], angleF[bestIdx[c]])].push_back(bestIdx[c]);
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (nodesKF[a] < nodesF[b]) {
+            while (a < nnKF && nodesKF[a] < nodesF[b]) a++;                                 // lower_bound
+        } else {
+            while (b < nnF && nodesF[b] < nodesKF[a]) b++;
+        }
+    }
+    if (checkOrientation) nmatches -= three_maxima_filter(rotHist, matchF);
+    return nmatches;
+}
+
+// ---- ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), ORBmatcher.cc:1006-1129 -------------------------------------------
+int orc_search_by_bow_keyframes(int nn1, const int *nodes1, const int *ptr1, const int *idx1v, int nn2, const int *nodes2, const int *ptr2,
+                                const int *idx2v, const uint8_t *desc1, int n1, const uint8_t *desc2, int n2, const uint8_t *skip1,
+                                const uint8_t *skip2, const float *angle1, const float *angle2, float nnratio, int checkOrientation,
+                                int *match12) {
+    const int TH_LOW = 50;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    std::vector<uint8_t> vbMatched2(n2, 0);
+    std::vector<int> rotHist[30];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int i1 = ptr1[a]; i1 < ptr1[a + 1]; i1++) {
+                const int idx1 = idx1v[i1];
+                if (skip1 && skip1[idx1]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = ptr2[b]; i2 < ptr2[b + 1]; i2++) {
+                    const int idx2 = idx2v[i2];
+                    if (vbMatched2[idx2] || (skip2 && skip2[idx2])) continue;
+                    const int dist = descriptor_distance(desc1 + (size_t)idx1 * 32, desc2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        match12[idx1] = bestIdx2;
+                        vbMatched2[bestIdx2] = 1;
+                        if (checkOrientation) rotHist[rot_bin(angle1[idx1], angle2[bestIdx2])].push_back(idx1);
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (nodes1[a] < nodes2[b]) {
+            while (a < nn1 && nodes1[a] < nodes2[b]) a++;
+        } else {
+            while (b < nn2 && nodes2[b] < nodes1[a]) b++;
+        }
+    }
+    if (checkOrientation) nmatches -= three_maxima_filter(rotHist, match12);
+    return nmatches;
+}
+
 // ---- Frame::ComputeStereoMatches (src/Frame.cc:1057-1219) -------------------------------------------------------
 // hL / hR: oracle extractors that hold the last extraction of the (rectified) left / right image: mvKeys = out_kps of hL,
 // mvKeysRight = out_kps of hR, mDescriptors(Right) = out_desc, mvImagePyramid = lv[].  mb = baseline, mbf = baseline * fx.

@@ -142,6 +142,83 @@ def test_search_for_triangulation(M):
     assert pairs == [(int(i), int(ref[i])) for i in np.nonzero(ref >= 0)[0]]
 
 
+def _bow_case(seed, n1, n2, nbits):
+    """Two feature sets sharing vocabulary nodes: 70 % of set 1 are noisy copies of set-2 rows (node bits kept), several copies of
+    the same row compete for it (the already-matched rule), exact duplicates in set 2 tie on distance."""
+    rng = np.random.default_rng(seed)
+    d2 = synth_descriptors(n2, seed + 1)
+    d2[50:58] = d2[50]
+    src = rng.integers(0, n2, n1)
+    flips = np.packbits(rng.random((n1, 256)) < 0.04, axis=1, bitorder='little')
+    flips[:, 0] &= ~np.uint8((1 << nbits) - 1)
+    d1 = d2[src] ^ flips
+    fresh = rng.random(n1) < 0.3
+    d1[fresh] = synth_descriptors(int(fresh.sum()), seed + 2)
+    a2 = rng.uniform(0, 360, n2).astype(np.float32)
+    a1 = ((a2[src] + np.where(rng.random(n1) < 0.8, 40 + rng.uniform(-4, 4, n1), rng.uniform(0, 360, n1))) % 360).astype(np.float32)
+    fv1, fv2 = _feature_vector(d1, nbits), _feature_vector(d2, nbits)
+    # drop every third node of list 1 so that the merge walk has to skip on both sides
+    keep = [i for i in range(len(fv1[0])) if i % 3 != 1]
+    fv1 = (fv1[0][keep].copy(), np.concatenate([[0], np.cumsum(np.diff(fv1[1])[keep])]).astype(np.int32),
+           np.concatenate([fv1[2][fv1[1][i]:fv1[1][i + 1]] for i in keep]).astype(np.int32))
+    skip1 = (rng.random(n1) < 0.2).astype(np.uint8); skip2 = (rng.random(n2) < 0.15).astype(np.uint8)
+    return d1, d2, a1, a2, fv1, fv2, skip1, skip2
+
+
+@pytest.mark.parametrize('ncam,nnratio,check,nbits', [(1, 0.7, True, 5), (2, 0.7, True, 5), (4, 0.75, True, 6), (4, 0.9, False, 4), (1, 0.6, True, 2)])
+def test_search_by_bow_keyframe_frame(ncam, nnratio, check, nbits):
+    """src/ORBmatcher.cc:349-666: per-camera best / second, ratio only on camera 0, already-matched rule, rotation filter."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    n_kf, n_f = 2500, 3000
+    d1, d2, a1, a2, fv1, fv2, skip1, _ = _bow_case(60 + ncam, n_kf, n_f, nbits)
+    cam_off = None if ncam == 1 else np.array([0, 1100, 2000, 2600, 2950][:ncam + 1], np.int32)   # features beyond the last block are ignored
+    M = ob.ORBmatcher(nnratio, checkOri=check)
+    nm, match = M.SearchByBoW(fv1, fv2, d1, d2, skip1, a1, a2, cam_off)
+    ref = np.zeros(n_f, np.int32)
+    L = O.lib()
+    rn = L.orc_search_by_bow_frame(len(fv1[0]), O.p(fv1[0]), O.p(fv1[1]), O.p(fv1[2]), len(fv2[0]), O.p(fv2[0]), O.p(fv2[1]), O.p(fv2[2]),
+                                   O.p(d1), O.p(d2), n_f, O.p(skip1), O.p(a1), O.p(a2), ncam, None if cam_off is None else O.p(cam_off),
+                                   C.c_float(np.float32(nnratio)), int(check), O.p(ref))
+    assert rn == nm, (rn, nm)
+    assert np.array_equal(ref, match), int((ref != match).sum())
+    assert nm > 150
+    assert (skip1[match[match >= 0]] == 0).all()
+
+
+@pytest.mark.parametrize('nnratio,check,nbits', [(0.8, True, 5), (0.6, False, 6), (0.9, True, 1)])
+def test_search_by_bow_keyframes(nnratio, check, nbits):
+    """src/ORBmatcher.cc:1006-1129: strict < TH_LOW, ratio test, vbMatched2, rotation filter."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    n1, n2 = 2200, 2000
+    d1, d2, a1, a2, fv1, fv2, skip1, skip2 = _bow_case(80 + nbits, n1, n2, nbits)
+    M = ob.ORBmatcher(nnratio, checkOri=check)
+    nm, m12 = M.SearchByBoWKeyFrames(fv1, fv2, d1, d2, skip1, skip2, a1, a2)
+    ref = np.zeros(n1, np.int32)
+    L = O.lib()
+    rn = L.orc_search_by_bow_keyframes(len(fv1[0]), O.p(fv1[0]), O.p(fv1[1]), O.p(fv1[2]), len(fv2[0]), O.p(fv2[0]), O.p(fv2[1]), O.p(fv2[2]),
+                                       O.p(d1), n1, O.p(d2), n2, O.p(skip1), O.p(skip2), O.p(a1), O.p(a2), C.c_float(np.float32(nnratio)),
+                                       int(check), O.p(ref))
+    assert rn == nm, (rn, nm)
+    assert np.array_equal(ref, m12), int((ref != m12).sum())
+    assert nm > 200
+    used = m12[m12 >= 0]
+    assert np.unique(used).size == used.size and (skip2[used] == 0).all()
+
+
+def test_search_by_bow_degenerate(M):
+    d = synth_descriptors(10, 1)
+    fv = _feature_vector(d, 2)
+    empty = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    nm, match = M.SearchByBoW(empty, fv, np.zeros((0, 32), np.uint8), d)
+    assert nm == 0 and (match == -1).all() and match.size == 10
+    nm, m12 = M.SearchByBoWKeyFrames(fv, fv, d, d, angle1=np.zeros(10, np.float32), angle2=np.zeros(10, np.float32))
+    assert nm == 10 and np.array_equal(m12, np.arange(10))          # identical sets match themselves (distance 0)
+    with pytest.raises(ob.OrbxError):
+        M.SearchByBoWKeyFrames((fv[0], fv[1], fv[2] + 5), fv, d, d, angle1=np.zeros(10, np.float32), angle2=np.zeros(10, np.float32))
+
+
 def _extract_frame(w, h, nf, seeds, lap):
     rig = ob.RigExtractor(w, h, len(seeds), nf)
     imgs = [synth_image(w, h, s) for s in seeds]
