@@ -264,20 +264,50 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
  * the camera-0 projection inside the image bounds, :2008-2026): proj_x/proj_y[i][c] = the projection searched in camera c (the
  * caller passes what the reference passes — for the side cameras that is the LEFT projection, :2250-2271), proj_ur[i] = uv.x -
  * mbf * invzc, last_octave / last_angle = octave and angle of the last frame's keypoint, has_obs[i] = Observations() > 0,
- * pt_desc = GetDescriptor().  forward / backward = bForward / bBackward (:2003-2004).  Window th * sf[octave], level gate by
- * direction, best Hamming distance <= max_dist (TH_HIGH = 100 here) among the keypoints not claimed by an earlier point; an empty camera-0 window skips the
+ * pt_desc = GetDescriptor().  level_gate = ORBX_GATE_FORWARD / _BACKWARD for bForward / bBackward (:2003-2004), else _AROUND.
+ * Window th * sf[octave], level gate by direction, best Hamming distance <= max_dist (TH_HIGH = 100 here) among the keypoints not claimed by an earlier point; an empty camera-0 window skips the
  * point's other cameras (:2062); with check_orientation the rotation-histogram filter (:2392-2410) clears the assignments outside
  * the three fullest bins.  assigned[N] = i written to CurrentFrame.mvpMapPoints (or -1), *nmatches = the return value.
  * The relocalisation overload SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist) (:2415-2535) is the
  * same call with ncam = 1 (it searches camera 0 only), valid[i] = its own early `continue`s (:2433-2459), last_octave =
  * nPredictedLevel, last_angle = pKF->mvKeysUn[i].angle, occupied = (mvpMapPoints[idx] != NULL), has_obs = NULL (every claim is
- * visible, :2478), forward = backward = 0 and max_dist = ORBdist.  HOST pointers. */
+ * visible, :2478), ORBX_GATE_AROUND and max_dist = ORBdist.  The loop-closing overloads SearchByProjection(KeyFrame *pKF, Sim3 Scw,
+ * vpPoints, vpMatched, th, ratioHamming, cameraID) (:668-774) and its vpMatchedKF twin (:776-893) are the same call on the chosen
+ * camera's block of the KeyFrame (ncam = 1): occupied = (vpMatched[idx] != NULL), ORBX_GATE_BELOW, check_orientation = 0,
+ * max_dist = (int)floorf(TH_LOW * ratioHamming) (:767).  HOST pointers. */
+#define ORBX_GATE_AROUND 0   /* [l - 1, l + 1] */
+#define ORBX_GATE_FORWARD 1  /* [l, inf)       */
+#define ORBX_GATE_BACKWARD 2 /* [0, l]         */
+#define ORBX_GATE_BELOW 3    /* [l - 1, l]     */
 int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
                                    const float *grid_bounds, const float *scale_factors, int nlevels, const uint8_t *occupied,
                                    const float *u_right, int npts, const uint8_t *valid, const float *proj_x, const float *proj_y,
                                    const float *proj_ur, const int *last_octave, const float *last_angle, const uint8_t *has_obs,
-                                   const uint8_t *pt_desc, float th, int forward, int backward, int check_orientation, int max_dist,
+                                   const uint8_t *pt_desc, float th, int level_gate, int check_orientation, int max_dist,
                                    int *assigned, int *nmatches);
+
+/* Window search without the "already matched" rule — the search loop of Fuse (src/ORBmatcher.cc:1458-1640 and :1642-1769) and of
+ * both directions of SearchBySim3 (:1771-1983) over one camera of a KeyFrame: kps / desc = that camera's keypoints (camera-local
+ * indices), grid_bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}.  Per query q with valid[q] (the caller's projection tests): the
+ * keypoints of KeyFrame::GetFeaturesInArea(qx, qy, radius) (src/KeyFrame.cc:771-834) with skip[idx] == 0, octave in
+ * [min_level, max_level], and — when inv_level_sigma2 is given (Fuse, :1571-1592) — squared reprojection error * invSigma2[octave]
+ * <= 5.99, or <= 7.8 including (q_ur - u_right[idx])^2 where u_right[idx] >= 0.  best_idx[q] = first minimum of the Hamming
+ * distance (-1 if none), best_dist[q] (256 if none); the caller applies its threshold (TH_LOW / TH_HIGH) and graph updates.
+ * skip, u_right, q_ur, inv_level_sigma2 may be NULL.  HOST pointers. */
+int orbx_window_best(orbx_matcher *m, const orbx_kp *kps, const uint8_t *desc, int n, const float *grid_bounds, const uint8_t *skip,
+                     const float *u_right, const float *inv_level_sigma2, int nlevels, int nq, const uint8_t *valid, const float *qx,
+                     const float *qy, const float *q_ur, const float *radius, const int *min_level, const int *max_level,
+                     const uint8_t *q_desc, int *best_idx, int *best_dist);
+/* ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1771-1983): both window searches (orbx_window_best semantics, level gate
+ * [l - 1, l], best <= TH_HIGH) and the agreement check (:1968-1980).  Side 1 queries = the map points of KeyFrame 1 projected into
+ * KeyFrame 2 (valid1[i1] = 0 for !pMP, vbAlreadyMatched1, bad, behind the camera, outside the image or the scale range), searched in
+ * KeyFrame 2's keypoints with mp_desc1[i1] = pMP->GetDescriptor(); side 2 likewise.  match12[n1] = idx2 with vnMatch1[i1] == idx2 && vnMatch2[idx2] == i1, else -1;
+ * *nfound = the return value.  HOST pointers. */
+int orbx_search_by_sim3(orbx_matcher *m, const orbx_kp *kps1, const uint8_t *desc1, int n1, const float *grid_bounds1,
+                        const orbx_kp *kps2, const uint8_t *desc2, int n2, const float *grid_bounds2, const uint8_t *valid1,
+                        const float *u1, const float *v1, const float *radius1, const int *level1, const uint8_t *mp_desc1,
+                        const uint8_t *valid2, const float *u2, const float *v2, const float *radius2, const int *level2,
+                        const uint8_t *mp_desc2, int *match12, int *nfound);
 
 /* Fisheye stereo post-filter.  Camera pair of a Kannala-Brandt rig: cam = {fx, fy, cx, cy, k0, k1, k2, k3}
  * (KannalaBrandt8::mvParameters), R12 / t12 = Frame::mRlr / mtlr (row-major rotation, translation), precision = the Newton

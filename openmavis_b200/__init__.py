@@ -26,6 +26,7 @@ NUM_STAGES = 7
 STAGE_NAMES = ('pyramid', 'blur', 'fast', 'octree', 'slots', 'orient_desc', 'total')
 
 TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30     # src/ORBmatcher.cc:15-17
+GATE_AROUND, GATE_FORWARD, GATE_BACKWARD, GATE_BELOW = 0, 1, 2, 3   # ORBX_GATE_*
 
 
 class OrbxError(RuntimeError):
@@ -382,6 +383,43 @@ class ORBmatcher:
         pairs = [(int(i), int(m12[i])) for i in np.nonzero(m12 >= 0)[0]]
         return nm.value, pairs, m12
 
+    def window_best(self, kps, desc, bounds, qx, qy, radius, min_level, max_level, q_desc, valid=None, skip=None, u_right=None,
+                    q_ur=None, inv_level_sigma2=None):
+        """Search loop of Fuse (src/ORBmatcher.cc:1549-1601, 1719-1738) / SearchBySim3 (:1837-1861) over one KeyFrame camera: window,
+        level gate, optional reprojection gate, first minimum.  Returns (best_idx[nq], best_dist[nq])."""
+        kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(bounds, np.float32)
+        qx, qy, radius = (np.ascontiguousarray(a, np.float32) for a in (qx, qy, radius))
+        nq = qx.size
+        mn = np.ascontiguousarray(min_level, np.int32); mx = np.ascontiguousarray(max_level, np.int32)
+        qd = np.ascontiguousarray(q_desc, np.uint8).reshape(-1, 32)
+        va = np.ones(nq, np.uint8) if valid is None else np.ascontiguousarray(valid, np.uint8)
+        sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        qur = None if q_ur is None else np.ascontiguousarray(q_ur, np.float32)
+        isg = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        bi = np.full(nq, -1, np.int32); bd = np.full(nq, 256, np.int32)
+        _check(self.L.orbx_window_best(self.h, _p(kps), _p(desc), kps.size, _p(b), _p(sk), _p(ur), _p(isg), 0 if isg is None else isg.size, nq,
+                                       _p(va), _p(qx), _p(qy), _p(qur), _p(radius), _p(mn), _p(mx), _p(qd), _p(bi), _p(bd)))
+        return bi, bd
+
+    def SearchBySim3(self, kf1, kf2, side1, side2):
+        """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1771-1983).  kf = dict(kps, desc, bounds); side = dict(valid, u, v, radius,
+        level, desc) — the KeyFrame's map points projected into the other KeyFrame.  Returns (nFound, match12[n1])."""
+        k1 = np.ascontiguousarray(kf1['kps'], KP_DTYPE); k2 = np.ascontiguousarray(kf2['kps'], KP_DTYPE)
+        d1 = np.ascontiguousarray(kf1['desc'], np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(kf2['desc'], np.uint8).reshape(-1, 32)
+        b1 = np.ascontiguousarray(kf1['bounds'], np.float32); b2 = np.ascontiguousarray(kf2['bounds'], np.float32)
+
+        def side(sd):
+            return (np.ascontiguousarray(sd['valid'], np.uint8), np.ascontiguousarray(sd['u'], np.float32), np.ascontiguousarray(sd['v'], np.float32),
+                    np.ascontiguousarray(sd['radius'], np.float32), np.ascontiguousarray(sd['level'], np.int32),
+                    np.ascontiguousarray(sd['desc'], np.uint8).reshape(-1, 32))
+        s1, s2 = side(side1), side(side2)
+        m12 = np.full(max(k1.size, 1), -1, np.int32); nf = C.c_int(0)
+        _check(self.L.orbx_search_by_sim3(self.h, _p(k1), _p(d1), k1.size, _p(b1), _p(k2), _p(d2), k2.size, _p(b2), *[_p(a) for a in s1],
+                                          *[_p(a) for a in s2], _p(m12), C.byref(nf)))
+        return nf.value, m12[:k1.size]
+
     def SearchByBoW(self, fv_kf, fv_f, desc_kf, desc_f, skip_kf=None, angle_kf=None, angle_f=None, cam_off_f=None):
         """ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vpMapPointMatches) (src/ORBmatcher.cc:349-666), whole function.
         fv = (nodes, ptr, idx) CSR of a DBoW2 FeatureVector; cam_off_f = None (F.Nleft == -1) or the 3 / 5 camera block offsets.
@@ -495,12 +533,14 @@ class ORBmatcher:
         return nm.value, assigned[:N]
 
 
-    def SearchByProjectionLast(self, frame, last, th, forward=False, backward=False, max_dist=TH_HIGH):
+    def SearchByProjectionLast(self, frame, last, th, forward=False, backward=False, max_dist=TH_HIGH, level_gate=None):
         """ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1985-2413).
         frame: as in SearchByProjection (+ optional u_right[N] for the rectified-stereo layout, ncam == 1)
         last : dict(valid[n], proj_x[n,4], proj_y[n,4], octave[n], angle[n], desc[n,32], has_obs?, proj_ur?)
         forward / backward = bForward / bBackward.  The relocalisation overload SearchByProjection(Frame, KeyFrame, sAlreadyFound, th,
-        ORBdist) (:2415-2535) is the same call with max_dist = ORBdist (see include/orbx.h).  Returns (nmatches, assigned[N])."""
+        ORBdist) (:2415-2535) is the same call with max_dist = ORBdist, SearchByProjection(KeyFrame, Sim3, ...) (:668-893) with
+        level_gate = GATE_BELOW and checkOri off (see include/orbx.h).  Returns (nmatches, assigned[N])."""
+        gate = level_gate if level_gate is not None else (GATE_FORWARD if forward else GATE_BACKWARD if backward else GATE_AROUND)
         cam_off = np.ascontiguousarray(frame['cam_off'], np.int32)
         ncam = cam_off.size - 1
         N = int(cam_off[-1])
@@ -519,8 +559,7 @@ class ORBmatcher:
         assigned = np.full(max(N, 1), -1, np.int32); nm = C.c_int(0)
         _check(self.L.orbx_search_by_projection_last(self.h, ncam, _p(cam_off), _p(kps), _p(desc), _p(bounds), _p(sf), sf.size, _p(occ),
                                                      _p(ur), n, _p(valid), _p(px), _p(py), _p(pur), _p(octv), _p(ang), _p(ho), _p(pd),
-                                                     C.c_float(th), int(bool(forward)), int(bool(backward)),
-                                                     int(self.mbCheckOrientation), int(max_dist), _p(assigned), C.byref(nm)))
+                                                     C.c_float(th), int(gate), int(self.mbCheckOrientation), int(max_dist), _p(assigned), C.byref(nm)))
         return nm.value, assigned[:N]
 
 class ORBVocabulary:

@@ -556,6 +556,110 @@ int orbx_grid_candidates(orbx_matcher *m, const orbx_kp *kps, int n, float min_x
     return ORBX_OK;
 }
 
+// ---- window search without claims (Fuse, SearchBySim3)
+// device-side: grid of `n` uploaded keypoints in b[base .. base + 3], results in d_idx / d_dist (device)
+static int window_best_device(orbx_matcher *m, int base, const orbx_kp *d_kps, const uint4 *d_desc, int n, const float *gb, const uint8_t *d_skip,
+                              const float *d_uright, const float *d_inv_sigma2, int nq, const uint8_t *d_valid, const float *d_qx,
+                              const float *d_qy, const float *d_qur, const float *d_radius, const int *d_min, const int *d_max,
+                              const uint4 *d_qdesc, int *d_idx, int *d_dist) {
+    WindowArgs A;
+    A.kps = d_kps; A.desc = d_desc;
+    A.min_x = gb[0]; A.min_y = gb[2];
+    A.inv_w = (float)kGridCols / (gb[1] - gb[0]); A.inv_h = (float)kGridRows / (gb[3] - gb[2]);
+    int *cs, *ci, st;
+    if ((st = grid_build(m, base, d_kps, n, A.min_x, A.min_y, A.inv_w, A.inv_h, &cs, &ci)) != ORBX_OK) return st;
+    A.cell_start = cs; A.cell_items = ci;
+    A.skip = d_skip; A.u_right = d_uright; A.inv_sigma2 = d_inv_sigma2;
+    A.nq = nq; A.valid = d_valid; A.qx = d_qx; A.qy = d_qy; A.q_ur = d_qur; A.radius = d_radius; A.min_level = d_min; A.max_level = d_max;
+    A.q_desc = d_qdesc; A.best_idx = d_idx; A.best_dist = d_dist;
+    k_window_best<<<(nq + 127) / 128, 128, 0, m->stream>>>(A);
+    m->last_launches++;
+    M_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbx_window_best(orbx_matcher *m, const orbx_kp *kps, const uint8_t *desc, int n, const float *grid_bounds, const uint8_t *skip,
+                     const float *u_right, const float *inv_level_sigma2, int nlevels, int nq, const uint8_t *valid, const float *qx,
+                     const float *qy, const float *q_ur, const float *radius, const int *min_level, const int *max_level,
+                     const uint8_t *q_desc, int *best_idx, int *best_dist) {
+    if (!m || n < 0 || nq < 0 || !grid_bounds || !(grid_bounds[1] > grid_bounds[0]) || !(grid_bounds[3] > grid_bounds[2]) ||
+        (n && (!kps || !desc)) || (nq && (!valid || !qx || !qy || !radius || !min_level || !max_level || !q_desc || !best_idx || !best_dist)) ||
+        (u_right && (!q_ur || !inv_level_sigma2)) || (inv_level_sigma2 && (nlevels < 1 || nlevels > 32)))
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    if (nq == 0) return ORBX_OK;
+    if (inv_level_sigma2)
+        for (int i = 0; i < n; i++)
+            if (kps[i].octave < 0 || kps[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "keypoint octave outside the level table");
+    int st;
+    if ((st = upload(m, m->b[1], kps, (size_t)n * sizeof(orbx_kp))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], desc, (size_t)n * 32)) != ORBX_OK) return st;
+    const size_t fb = (size_t)nq * 4;
+    M_CUDA(m->b[5].ensure(16 * 16 + 6 * fb + (size_t)nq * 33 + (size_t)n * 5 + 32 * 4));
+    uint8_t *base = m->b[5].as<uint8_t>();
+    size_t off = 0;
+    auto put = [&](const void *src, size_t nb) -> void * {
+        if (!src) return nullptr;
+        void *d = base + off;
+        cudaMemcpyAsync(d, src, nb, cudaMemcpyHostToDevice, m->stream);
+        off += (nb + 15) & ~(size_t)15;
+        return d;
+    };
+    const float *d_qx = (const float *)put(qx, fb), *d_qy = (const float *)put(qy, fb), *d_qur = (const float *)put(q_ur, fb);
+    const float *d_r = (const float *)put(radius, fb);
+    const int *d_mn = (const int *)put(min_level, fb), *d_mx = (const int *)put(max_level, fb);
+    const uint4 *d_qd = (const uint4 *)put(q_desc, (size_t)nq * 32);
+    const uint8_t *d_valid = (const uint8_t *)put(valid, nq), *d_skip = (const uint8_t *)put(skip, n);
+    const float *d_ur = (const float *)put(u_right, (size_t)n * 4), *d_is = (const float *)put(inv_level_sigma2, (size_t)nlevels * 4);
+    M_CUDA(cudaGetLastError());
+    M_CUDA(m->b[6].ensure(2 * fb));
+    int *d_idx = m->b[6].as<int>(), *d_dist = d_idx + nq;
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    st = window_best_device(m, 15, m->b[1].as<orbx_kp>(), (const uint4 *)m->b[2].p, n, grid_bounds, d_skip, d_ur, d_is, nq, d_valid, d_qx, d_qy,
+                            d_qur, d_r, d_mn, d_mx, d_qd, d_idx, d_dist);
+    if (st != ORBX_OK) return st;
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    M_CUDA(cudaMemcpyAsync(best_idx, d_idx, fb, cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(best_dist, d_dist, fb, cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_search_by_sim3(orbx_matcher *m, const orbx_kp *kps1, const uint8_t *desc1, int n1, const float *grid_bounds1,
+                        const orbx_kp *kps2, const uint8_t *desc2, int n2, const float *grid_bounds2, const uint8_t *valid1,
+                        const float *u1, const float *v1, const float *radius1, const int *level1, const uint8_t *mp_desc1,
+                        const uint8_t *valid2, const float *u2, const float *v2, const float *radius2, const int *level2,
+                        const uint8_t *mp_desc2, int *match12, int *nfound) {
+    if (!m || n1 < 0 || n2 < 0 || !match12 || !nfound || (n1 && (!kps1 || !desc1 || !valid1 || !u1 || !v1 || !radius1 || !level1 || !mp_desc1)) ||
+        (n2 && (!kps2 || !desc2 || !valid2 || !u2 || !v2 || !radius2 || !level2 || !mp_desc2)) || !grid_bounds1 || !grid_bounds2)
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    *nfound = 0;
+    if (n1 == 0 || n2 == 0) return ORBX_OK;
+    std::vector<int> mn1(n1), mn2(n2), b1(n1), d1(n1), b2(n2), d2(n2);
+    for (int i = 0; i < n1; i++) mn1[i] = level1[i] - 1;      // kp.octave < nPredictedLevel - 1 || kp.octave > nPredictedLevel (:1851, 1925)
+    for (int i = 0; i < n2; i++) mn2[i] = level2[i] - 1;
+    int st;
+    // KF1's map points searched in KF2 (:1805-1866), then KF2's in KF1 (:1869-1940)
+    if ((st = orbx_window_best(m, kps2, desc2, n2, grid_bounds2, nullptr, nullptr, nullptr, 0, n1, valid1, u1, v1, nullptr, radius1, mn1.data(),
+                               level1, mp_desc1, b1.data(), d1.data())) != ORBX_OK) return st;
+    const int l1 = m->last_launches;
+    if ((st = orbx_window_best(m, kps1, desc1, n1, grid_bounds1, nullptr, nullptr, nullptr, 0, n2, valid2, u2, v2, nullptr, radius2, mn2.data(),
+                               level2, mp_desc2, b2.data(), d2.data())) != ORBX_OK) return st;
+    m->last_launches += l1;
+    int nf = 0;
+    for (int i1 = 0; i1 < n1; i1++) {   // agreement (:1968-1980), TH_HIGH = 100 (:1863, 1937)
+        const int idx2 = d1[i1] <= 100 ? b1[i1] : -1;
+        if (idx2 < 0) continue;
+        const int idx1 = d2[idx2] <= 100 ? b2[idx2] : -1;
+        if (idx1 == i1) { match12[i1] = idx2; nf++; }
+    }
+    *nfound = nf;
+    return ORBX_OK;
+}
+
 // frame side of the projection matchers: keypoints, descriptors, one 64x48 grid per camera, occupancy, stereo mirror tables
 static int sbp_setup_frame(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc, const float *grid_bounds,
                            const float *scale_factors, int nlevels, const uint8_t *occupied, const int *l2r, const int *r2l, SbpFrame &F) {
@@ -664,7 +768,7 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     P.has_obs = (const uint8_t *)put(hobs.data(), nmp);
     M_CUDA(cudaGetLastError());
     P.th = th; P.nnratio = nnratio;
-    P.mode = 0; P.forward = P.backward = P.check_ori = 0; P.max_dist = 100; P.angle = nullptr; P.u_right = P.proj_ur = nullptr;
+    P.mode = 0; P.level_gate = 0; P.check_ori = 0; P.max_dist = 100; P.angle = nullptr; P.u_right = P.proj_ur = nullptr;
     // ---- device work buffers
     M_CUDA(m->b[23].ensure(sbp_work_bytes(nmp, N)));
     M_CUDA(cudaEventRecord(m->ev0, m->stream));
@@ -684,10 +788,10 @@ int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off
                                    const float *grid_bounds, const float *scale_factors, int nlevels, const uint8_t *occupied,
                                    const float *u_right, int npts, const uint8_t *valid, const float *proj_x, const float *proj_y,
                                    const float *proj_ur, const int *last_octave, const float *last_angle, const uint8_t *has_obs,
-                                   const uint8_t *pt_desc, float th, int forward, int backward, int check_orientation, int max_dist,
+                                   const uint8_t *pt_desc, float th, int level_gate, int check_orientation, int max_dist,
                                    int *assigned, int *nmatches) {
     if (!m || !cam_off || !kps || !desc || !grid_bounds || !scale_factors || !assigned || !nmatches || npts < 0 ||
-        !(ncam == 1 || ncam == 2 || ncam == 4) || nlevels < 1 || nlevels > 32 || max_dist < 0 || max_dist > 255 ||
+        !(ncam == 1 || ncam == 2 || ncam == 4) || nlevels < 1 || nlevels > 32 || max_dist < 0 || max_dist > 255 || level_gate < 0 || level_gate > 3 || (level_gate == ORBX_GATE_BELOW && ncam != 1) ||
         (npts && (!valid || !proj_x || !proj_y || !last_octave || !last_angle || !pt_desc)) || (u_right && !proj_ur))
         return fail(ORBX_ERR_INVALID, "bad arguments");
     M_CUDA(cudaSetDevice(m->device));
@@ -739,7 +843,7 @@ int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off
     }
     M_CUDA(cudaGetLastError());
     P.th = th; P.nnratio = 0.0f;
-    P.mode = 1; P.forward = forward ? 1 : 0; P.backward = backward ? 1 : 0; P.check_ori = check_orientation ? 1 : 0; P.max_dist = max_dist;
+    P.mode = 1; P.level_gate = level_gate; P.check_ori = check_orientation ? 1 : 0; P.max_dist = max_dist;
     M_CUDA(m->b[23].ensure(sbp_work_bytes(npts, N)));
     M_CUDA(cudaEventRecord(m->ev0, m->stream));
     st = sbp_run(F, P, m->b[23].as<uint8_t>(), m->b[0], m->stream, &m->last_launches);

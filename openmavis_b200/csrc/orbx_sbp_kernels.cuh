@@ -44,7 +44,7 @@ struct SbpPoints {
     const uint4 *desc;                         // [nmp][2]
     float th, nnratio;
     // mode 1 (SearchByProjection(CurrentFrame, LastFrame)): level[q] = octave of the last keypoint, in_view[q] = projection usable
-    int mode, forward, backward, check_ori, max_dist;
+    int mode, level_gate, check_ori, max_dist;   // level_gate: ORBX_GATE_*
     const float *angle;                        // [nmp] kpLF.angle
     const float *u_right, *proj_ur;            // mvuRight [N] / uv.x - mbf * invzc [nmp] (rectified stereo, ncam == 1), or NULL
 };
@@ -93,8 +93,9 @@ __device__ __forceinline__ bool sbp_query(const SbpFrame &F, const SbpPoints &P,
     x = P.proj_x[q]; y = P.proj_y[q];
     if (P.mode == 1) {
         rr = __fmul_rn(P.th, F.scale_factors[lvl]);                            // :2040
-        if (P.forward) { min_lvl = lvl; max_lvl = -1; }                        // :2044-2056
-        else if (P.backward) { min_lvl = 0; max_lvl = lvl; }
+        if (P.level_gate == ORBX_GATE_FORWARD) { min_lvl = lvl; max_lvl = -1; }            // :2044-2056
+        else if (P.level_gate == ORBX_GATE_BACKWARD) { min_lvl = 0; max_lvl = lvl; }
+        else if (P.level_gate == ORBX_GATE_BELOW) { min_lvl = lvl - 1; max_lvl = lvl; }      // the KeyFrame / Sim3 overloads (:759)
         else { min_lvl = lvl - 1; max_lvl = lvl + 1; }
         return true;
     }
@@ -268,6 +269,54 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
         const int bin = (ev >> 16) & 31;
         if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { W.assigned[ev & 0xFFFF] = -1; atomicSub(&W.nmatches[0], 1); }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Window search without claims: the search loop shared by Fuse (src/ORBmatcher.cc:1549-1601, 1719-1738) and SearchBySim3
+// (:1837-1861, 1911-1935): KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:771-834) window, level gate, optional reprojection gate
+// (:1571-1592), first minimum of the Hamming distance.  One thread per query.
+// ------------------------------------------------------------------------------------------------------
+struct WindowArgs {
+    const orbx_kp *kps; const uint4 *desc;
+    const int *cell_start, *cell_items;
+    float min_x, min_y, inv_w, inv_h;
+    const uint8_t *skip;                 // [n] or null
+    const float *u_right;                // [n] or null (mvuRight, stereo gate)
+    const float *inv_sigma2;             // [nlevels] or null (no reprojection gate)
+    int nq;
+    const uint8_t *valid;
+    const float *qx, *qy, *q_ur, *radius;
+    const int *min_level, *max_level;
+    const uint4 *q_desc;
+    int *best_idx, *best_dist;
+};
+
+__global__ void __launch_bounds__(128) k_window_best(const __grid_constant__ WindowArgs A) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.nq) return;
+    int best = 256, bi = -1;
+    if (A.valid[q]) {
+        const float x = A.qx[q], y = A.qy[q];
+        const int mn = A.min_level[q], mx = A.max_level[q];
+        const uint4 qa = A.q_desc[2 * q], qb = A.q_desc[2 * q + 1];
+        grid_query(A.kps, A.cell_start, A.cell_items, A.min_x, A.min_y, A.inv_w, A.inv_h, x, y, A.radius[q], -1, -1, [&](int idx) {
+            if (A.skip && A.skip[idx]) return;
+            const orbx_kp kp = A.kps[idx];
+            if (kp.octave < mn || kp.octave > mx) return;
+            if (A.inv_sigma2) {
+                const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                if (A.u_right && A.u_right[idx] >= 0.0f) {
+                    const float er = __fsub_rn(A.q_ur[q], A.u_right[idx]);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    if ((double)__fmul_rn(e2, A.inv_sigma2[kp.octave]) > 7.8) return;
+                } else if ((double)__fmul_rn(e2, A.inv_sigma2[kp.octave]) > 5.99) return;
+            }
+            const int d = hamming256(qa, qb, A.desc[2 * idx], A.desc[2 * idx + 1]);
+            if (d < best) { best = d; bi = idx; }
+        });
+    }
+    A.best_idx[q] = bi; A.best_dist[q] = best;
 }
 
 // host driver (orbx_match.cu)

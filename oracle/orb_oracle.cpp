@@ -932,8 +932,10 @@ int orc_search_by_projection(int ncam, const int *cam_off, const orc_kp *kps, co
 int orc_search_by_projection_last(int ncam, const int *cam_off, const orc_kp *kps, const uint8_t *desc, void **grids, const float *sf,
                                   const uint8_t *occupied, const float *u_right, int npts, const uint8_t *valid, const float *proj_x,
                                   const float *proj_y, const float *proj_ur, const int *last_octave, const float *last_angle,
-                                  const uint8_t *has_obs, const uint8_t *pt_desc, float th, int bForward, int bBackward,
+                                  const uint8_t *has_obs, const uint8_t *pt_desc, float th, int levelGate,
                                   int checkOrientation, int maxDist, int *assigned) {
+    // levelGate: 1 = bForward, 2 = bBackward, 0 = neither; 3 = [l - 1, l], the gate of the KeyFrame / Sim3 overloads (:668-893)
+    const int bForward = levelGate == 1, bBackward = levelGate == 2;
     // maxDist = TH_HIGH (:2103); the relocalisation overload (Frame, KeyFrame, sAlreadyFound, th, ORBdist) (:2415-2535) has the same
     // body for one camera with ORBdist in its place (:2487)
     const int N = cam_off[ncam];
@@ -954,6 +956,12 @@ int orc_search_by_projection_last(int ncam, const int *cam_off, const orc_kp *kp
             const float u = proj_x[4 * i + c], v = proj_y[4 * i + c];
             if (bForward) features_in_area(*(Grid *)grids[c], ck, u, v, radius, nLastOctave, -1, cand);
             else if (bBackward) features_in_area(*(Grid *)grids[c], ck, u, v, radius, 0, nLastOctave, cand);
+            else if (levelGate == 3) {   // KeyFrame::GetFeaturesInArea has no level arguments; the loop gates kpLevel itself (:759); ncam == 1
+                std::vector<int> all;
+                features_in_area(*(Grid *)grids[c], ck, u, v, radius, -1, -1, all);
+                cand.clear();
+                for (int i2 : all) if (!(ck[i2].octave < nLastOctave - 1 || ck[i2].octave > nLastOctave)) cand.push_back(i2);
+            }
             else features_in_area(*(Grid *)grids[c], ck, u, v, radius, nLastOctave - 1, nLastOctave + 1, cand);
             if (c == 0 && cand.empty()) break;                                                  // :2062 `continue` of the point loop
             int bestDist = 256, bestIdx2 = -1;
@@ -996,6 +1004,79 @@ int orc_search_by_projection_last(int ncam, const int *cam_off, const orc_kp *kp
                 for (int g : rotHist[i]) { assigned[g] = -1; nmatches--; }
     }
     return nmatches;
+}
+
+// ---- window search without claims: the search loop of Fuse (ORBmatcher.cc:1549-1601, 1719-1738) and SearchBySim3 (:1837-1861, 1911-1935)
+// grid / kps: one camera of the KeyFrame; KeyFrame::GetFeaturesInArea (KeyFrame.cc:771-834) = the Frame query without level gate.
+void orc_window_best(void *grid, const orc_kp *kps, const uint8_t *desc, const uint8_t *skip, const float *u_right, const float *invSigma2,
+                     int nq, const uint8_t *valid, const float *qx, const float *qy, const float *q_ur, const float *radius,
+                     const int *min_level, const int *max_level, const uint8_t *q_desc, int *best_idx, int *best_dist) {
+    const KeyPt *ck = (const KeyPt *)kps;
+    std::vector<int> cand;
+    for (int q = 0; q < nq; q++) {
+        int bestDist = 256, bestIdx = -1;
+        if (valid[q]) {
+            features_in_area(*(Grid *)grid, ck, qx[q], qy[q], radius[q], -1, -1, cand);
+            for (int idx : cand) {
+                if (skip && skip[idx]) continue;
+                const int kpLevel = ck[idx].octave;
+                if (kpLevel < min_level[q] || kpLevel > max_level[q]) continue;
+                if (invSigma2) {
+                    if (u_right && u_right[idx] >= 0) {                                  // :1571-1583
+                        const float ex = qx[q] - ck[idx].x, ey = qy[q] - ck[idx].y, er = q_ur[q] - u_right[idx];
+                        const float e2 = ex * ex + ey * ey + er * er;
+                        if (e2 * invSigma2[kpLevel] > 7.8) continue;
+                    } else {                                                             // :1584-1592
+                        const float ex = qx[q] - ck[idx].x, ey = qy[q] - ck[idx].y;
+                        const float e2 = ex * ex + ey * ey;
+                        if (e2 * invSigma2[kpLevel] > 5.99) continue;
+                    }
+                }
+                const int dist = descriptor_distance(q_desc + (size_t)q * 32, desc + (size_t)idx * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+            }
+        }
+        best_idx[q] = bestIdx; best_dist[q] = bestDist;
+    }
+}
+
+// ---- ORBmatcher::SearchBySim3, ORBmatcher.cc:1771-1983: the two searches and the agreement check over plain arrays
+int orc_search_by_sim3(void *grid1, const orc_kp *kps1, const uint8_t *desc1, int n1, void *grid2, const orc_kp *kps2, const uint8_t *desc2,
+                       int n2, const uint8_t *valid1, const float *u1, const float *v1, const float *radius1, const int *level1,
+                       const uint8_t *mpdesc1, const uint8_t *valid2, const float *u2, const float *v2, const float *radius2,
+                       const int *level2, const uint8_t *mpdesc2, int *match12) {
+    const int TH_HIGH = 100;
+    std::vector<int> vnMatch1(n1, -1), vnMatch2(n2, -1), cand;
+    const KeyPt *k1 = (const KeyPt *)kps1, *k2 = (const KeyPt *)kps2;
+    for (int i1 = 0; i1 < n1; i1++) {
+        if (!valid1[i1]) continue;
+        features_in_area(*(Grid *)grid2, k2, u1[i1], v1[i1], radius1[i1], -1, -1, cand);
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int idx : cand) {
+            if (k2[idx].octave < level1[i1] - 1 || k2[idx].octave > level1[i1]) continue;
+            const int dist = descriptor_distance(mpdesc1 + (size_t)i1 * 32, desc2 + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_HIGH) vnMatch1[i1] = bestIdx;
+    }
+    for (int i2 = 0; i2 < n2; i2++) {
+        if (!valid2[i2]) continue;
+        features_in_area(*(Grid *)grid1, k1, u2[i2], v2[i2], radius2[i2], -1, -1, cand);
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int idx : cand) {
+            if (k1[idx].octave < level2[i2] - 1 || k1[idx].octave > level2[i2]) continue;
+            const int dist = descriptor_distance(mpdesc2 + (size_t)i2 * 32, desc1 + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_HIGH) vnMatch2[i2] = bestIdx;
+    }
+    int nFound = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        match12[i1] = -1;
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+    }
+    return nFound;
 }
 
 // ORBmatcher::SearchForTriangulation Hamming core, ORBmatcher.cc:1218-1427, with the vocabulary FeatureVectors

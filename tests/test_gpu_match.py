@@ -358,7 +358,7 @@ def _sbp_last_case(ncam, seed, n=4000):
     return frame, last
 
 
-def _oracle_sbp_last(frame, last, th, fwd, bwd, check, max_dist=100):
+def _oracle_sbp_last(frame, last, th, fwd, bwd, check, max_dist=100, gate=None):
     L = O.lib()
     cam_off = frame['cam_off']; ncam = len(cam_off) - 1; N = int(cam_off[-1])
     kps = np.ascontiguousarray(frame['kps']); desc = np.ascontiguousarray(frame['desc'])
@@ -372,7 +372,7 @@ def _oracle_sbp_last(frame, last, th, fwd, bwd, check, max_dist=100):
     n = L.orc_search_by_projection_last(ncam, O.p(cam_off), O.p(kps), O.p(desc), grids, O.p(frame['scale_factors']), O.p(frame['occupied']),
                                         opt(frame.get('u_right')), last['valid'].size, O.p(last['valid']), O.p(last['proj_x']),
                                         O.p(last['proj_y']), opt(last.get('proj_ur')), O.p(last['octave']), O.p(last['angle']),
-                                        opt(last.get('has_obs')), O.p(last['desc']), C.c_float(th), int(fwd), int(bwd), int(check), int(max_dist), O.p(assigned))
+                                        opt(last.get('has_obs')), O.p(last['desc']), C.c_float(th), (gate if gate is not None else 1 if fwd else 2 if bwd else 0), int(check), int(max_dist), O.p(assigned))
     for c in range(ncam):
         L.orc_grid_destroy(C.c_void_p(grids[c]))
     return n, assigned
@@ -411,6 +411,123 @@ def test_search_by_projection_relocalisation_overload(orb_dist, th):
     assert nm > 300
     # every claim is visible: no current keypoint receives two map points, none of the pre-occupied ones is touched
     assert (assigned[frame['occupied'] == 1] == -1).all()
+
+
+@pytest.mark.parametrize('ratio_hamming,th', [(1.0, 6.0), (0.8, 10.0)])
+def test_search_by_projection_keyframe_sim3_overloads(ratio_hamming, th):
+    """SearchByProjection(KeyFrame, Sim3, vpPoints, vpMatched, th, ratioHamming, cameraID) (src/ORBmatcher.cc:668-893) through the
+    same entry point: one camera block, gate [l-1, l], vpMatched as occupancy, TH_LOW * ratioHamming, no rotation filter."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    frame, last = _sbp_last_case(1, seed=31 + int(th))
+    frame.pop('u_right'); last.pop('proj_ur'); last['has_obs'] = None
+    max_dist = int(np.floor(np.float32(50) * np.float32(ratio_hamming)))
+    M = ob.ORBmatcher(0.9, checkOri=False)
+    nm, assigned = M.SearchByProjectionLast(frame, last, th, max_dist=max_dist, level_gate=ob.GATE_BELOW)
+    rn, rassigned = _oracle_sbp_last(frame, last, th, False, False, False, max_dist, gate=3)
+    assert rn == nm and np.array_equal(assigned, rassigned)
+    assert nm > 200
+    k = np.nonzero(assigned >= 0)[0]
+    d = frame['kps']['octave'][k] - last['octave'][assigned[k]]
+    assert ((d == 0) | (d == -1)).all()
+
+
+def _window_case(seed, nq=3000, stereo=True):
+    rng = np.random.default_rng(seed)
+    rig, res = _extract_frame(512, 512, 1500, [5100 + seed], (0, 511))
+    kps = res[0][1].copy(); desc = res[0][2].copy()
+    n = kps.size
+    k = rng.integers(0, n, nq)
+    qx = (kps['x'][k] + rng.uniform(-4, 4, nq)).astype(np.float32); qy = (kps['y'][k] + rng.uniform(-4, 4, nq)).astype(np.float32)
+    lvl = np.clip(kps['octave'][k] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
+    radius = (np.float32(3.0) * rig.scale[lvl]).astype(np.float32)
+    qd = desc[k] ^ np.packbits(rng.random((nq, 256)) < 0.07, axis=1, bitorder='little')
+    qd[::7] = synth_descriptors(len(qd[::7]), seed + 3)
+    valid = (rng.random(nq) < 0.9).astype(np.uint8)
+    skip = (rng.random(n) < 0.1).astype(np.uint8)
+    u_right = np.where(rng.random(n) < 0.5, kps['x'] - rng.uniform(1, 30, n), -1).astype(np.float32) if stereo else None
+    q_ur = (qx - rng.uniform(0, 32, nq)).astype(np.float32) if stereo else None
+    inv_sigma2 = (1.0 / (rig.scale.astype(np.float32) ** 2)).astype(np.float32)
+    return rig, kps, desc, (0.0, 512.0, 0.0, 512.0), qx, qy, radius, lvl, qd, valid, skip, u_right, q_ur, inv_sigma2
+
+
+def _oracle_window(kps, desc, bounds, qx, qy, radius, mn, mx, qd, valid, skip, u_right, q_ur, inv_sigma2):
+    L = O.lib()
+    kps = np.ascontiguousarray(kps)
+    g = L.orc_grid_create(O.p(kps), kps.size, C.c_float(bounds[0]), C.c_float(bounds[1]), C.c_float(bounds[2]), C.c_float(bounds[3]))
+    bi = np.zeros(qx.size, np.int32); bd = np.zeros(qx.size, np.int32)
+    opt = lambda a: None if a is None else O.p(a)
+    L.orc_window_best(C.c_void_p(g), O.p(kps), O.p(desc), opt(skip), opt(u_right), opt(inv_sigma2), qx.size, O.p(valid), O.p(qx), O.p(qy),
+                      opt(q_ur), O.p(radius), O.p(mn), O.p(mx), O.p(qd), O.p(bi), O.p(bd))
+    L.orc_grid_destroy(C.c_void_p(g))
+    return bi, bd
+
+
+@pytest.mark.parametrize('mode', ['fuse_stereo', 'fuse_mono', 'fuse_sim3'])
+def test_window_best_fuse_loops(M, mode):
+    """Search loops of both Fuse overloads (src/ORBmatcher.cc:1549-1601 with the reprojection gates, :1719-1738 without)."""
+    rig, kps, desc, bounds, qx, qy, radius, lvl, qd, valid, skip, u_right, q_ur, inv_sigma2 = _window_case(7, stereo=mode == 'fuse_stereo')
+    mn = (lvl - 1).astype(np.int32)
+    kw = dict(valid=valid)
+    if mode != 'fuse_sim3':
+        kw.update(u_right=u_right, q_ur=q_ur, inv_level_sigma2=inv_sigma2)
+    bi, bd = M.window_best(kps, desc, bounds, qx, qy, radius, mn, lvl, qd, **kw)
+    ri, rd = _oracle_window(kps, desc, bounds, qx, qy, radius, mn, lvl, qd, valid, None, kw.get('u_right'), kw.get('q_ur'), kw.get('inv_level_sigma2'))
+    assert np.array_equal(bi, ri) and np.array_equal(bd, rd)
+    assert (bd <= 50).sum() > 1000 and (bi[valid == 0] == -1).all()
+    if mode != 'fuse_sim3':   # the reprojection gate does reject candidates
+        bi2, _ = M.window_best(kps, desc, bounds, qx, qy, radius, mn, lvl, qd, valid=valid)
+        assert (bi2 != bi).any()
+
+
+def test_window_best_skip_mask_and_empty(M):
+    rig, kps, desc, bounds, qx, qy, radius, lvl, qd, valid, skip, *_ = _window_case(9, nq=500, stereo=False)
+    mn = (lvl - 1).astype(np.int32)
+    bi, bd = M.window_best(kps, desc, bounds, qx, qy, radius, mn, lvl, qd, valid=valid, skip=skip)
+    ri, rd = _oracle_window(kps, desc, bounds, qx, qy, radius, mn, lvl, qd, valid, skip, None, None, None)
+    assert np.array_equal(bi, ri) and np.array_equal(bd, rd)
+    assert (skip[bi[bi >= 0]] == 0).all()
+    bi, bd = M.window_best(kps[:0], desc[:0], bounds, qx, qy, radius, mn, lvl, qd)
+    assert (bi == -1).all() and (bd == 256).all()
+    bi, bd = M.window_best(kps, desc, bounds, qx[:0], qy[:0], radius[:0], mn[:0], lvl[:0], qd[:0])
+    assert bi.size == 0
+
+
+def test_search_by_sim3(M):
+    """src/ORBmatcher.cc:1771-1983: two window searches + agreement."""
+    rng = np.random.default_rng(12)
+    rig, res = _extract_frame(512, 512, 1500, [5301, 5302], (0, 511))
+    (_, k1, d1), (_, k2, d2) = [(r[0], r[1].copy(), r[2].copy()) for r in res]
+    n1, n2 = k1.size, k2.size
+    bounds = np.array([0, 512, 0, 512], np.float32)
+    pair = rng.integers(0, n2, n1)                                    # map point of KF1 feature i1 is seen near KF2 feature pair[i1]
+
+    def side(n_self, k_other, d_other, target):
+        u = (k_other['x'][target] + rng.uniform(-2, 2, n_self)).astype(np.float32); v = (k_other['y'][target] + rng.uniform(-2, 2, n_self)).astype(np.float32)
+        lvl = np.clip(k_other['octave'][target] + rng.integers(0, 2, n_self), 0, 7).astype(np.int32)
+        desc = d_other[target] ^ np.packbits(rng.random((n_self, 256)) < 0.05, axis=1, bitorder='little')
+        return dict(valid=(rng.random(n_self) < 0.85).astype(np.uint8), u=u, v=v, radius=(np.float32(7.5) * rig.scale[lvl]).astype(np.float32),
+                    level=lvl, desc=desc)
+    s1 = side(n1, k2, d2, pair)
+    back = rng.integers(0, n1, n2)
+    first = {}
+    for i1 in range(n1):
+        first.setdefault(int(pair[i1]), i1)
+    for i2, i1 in first.items():
+        if rng.random() < 0.8:
+            back[i2] = i1                                             # mutual correspondences
+    s2 = side(n2, k1, d1, back)
+    nf, m12 = M.SearchBySim3(dict(kps=k1, desc=d1, bounds=bounds), dict(kps=k2, desc=d2, bounds=bounds), s1, s2)
+    L = O.lib()
+    g1 = L.orc_grid_create(O.p(k1), n1, C.c_float(0), C.c_float(512), C.c_float(0), C.c_float(512))
+    g2 = L.orc_grid_create(O.p(k2), n2, C.c_float(0), C.c_float(512), C.c_float(0), C.c_float(512))
+    ref = np.zeros(n1, np.int32)
+    rn = L.orc_search_by_sim3(C.c_void_p(g1), O.p(k1), O.p(d1), n1, C.c_void_p(g2), O.p(k2), O.p(d2), n2, O.p(s1['valid']), O.p(s1['u']), O.p(s1['v']),
+                              O.p(s1['radius']), O.p(s1['level']), O.p(s1['desc']), O.p(s2['valid']), O.p(s2['u']), O.p(s2['v']), O.p(s2['radius']),
+                              O.p(s2['level']), O.p(s2['desc']), O.p(ref))
+    L.orc_grid_destroy(C.c_void_p(g1)); L.orc_grid_destroy(C.c_void_p(g2))
+    assert rn == nf and np.array_equal(ref, m12)
+    assert nf > 100
 
 
 def test_search_by_projection_last_frame_degenerate():
