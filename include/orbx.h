@@ -286,6 +286,16 @@ int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off
                                    const uint8_t *pt_desc, float th, int level_gate, int check_orientation, int max_dist,
                                    int *assigned, int *nmatches);
 
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:895-1004), whole
+ * function: kps / desc = mvKeysUn / mDescriptors of the two frames, grid_bounds2 = F2's {mnMinX, mnMaxX, mnMinY, mnMaxY};
+ * prev_matched [n1][2] = vbPrevMatched (in: search centres; out: updated with the matched F2 positions, :992-995).  Level-0
+ * keypoints of F1 only, window = windowSize at level 0, per F2 keypoint the smallest distance so far wins and evicts the previous
+ * owner (vMatchedDistance / vnMatches21, :927, 941-947), TH_LOW, bestDist < bestDist2 * mfNNratio, rotation-histogram filter.
+ * matches12[n1] = vnMatches12, *nmatches = the return value.  HOST pointers. */
+int orbx_search_for_initialization(orbx_matcher *m, const orbx_kp *kps1, const uint8_t *desc1, int n1, const orbx_kp *kps2,
+                                   const uint8_t *desc2, int n2, const float *grid_bounds2, float *prev_matched, int window_size,
+                                   float nnratio, int check_orientation, int *matches12, int *nmatches);
+
 /* Window search without the "already matched" rule — the search loop of Fuse (src/ORBmatcher.cc:1458-1640 and :1642-1769) and of
  * both directions of SearchBySim3 (:1771-1983) over one camera of a KeyFrame: kps / desc = that camera's keypoints (camera-local
  * indices), grid_bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}.  Per query q with valid[q] (the caller's projection tests): the

@@ -420,6 +420,20 @@ class ORBmatcher:
                                           *[_p(a) for a in s2], _p(m12), C.byref(nf)))
         return nf.value, m12[:k1.size]
 
+    def SearchForInitialization(self, kps1, desc1, kps2, desc2, bounds2, prev_matched, windowSize=10):
+        """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:895-1004), whole function.  prev_matched [n1,2] is updated in
+        place like vbPrevMatched.  Returns (nmatches, vnMatches12[n1])."""
+        k1 = np.ascontiguousarray(kps1, KP_DTYPE); k2 = np.ascontiguousarray(kps2, KP_DTYPE)
+        d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        b2 = np.ascontiguousarray(bounds2, np.float32)
+        if not (isinstance(prev_matched, np.ndarray) and prev_matched.dtype == np.float32 and prev_matched.flags.c_contiguous):
+            raise TypeError('prev_matched must be a C-contiguous float32 array (updated in place)')
+        m12 = np.full(max(k1.size, 1), -1, np.int32); nm = C.c_int(0)
+        _check(self.L.orbx_search_for_initialization(self.h, _p(k1), _p(d1), k1.size, _p(k2), _p(d2), k2.size, _p(b2), _p(prev_matched),
+                                                     int(windowSize), C.c_float(self.mfNNratio), int(self.mbCheckOrientation), _p(m12),
+                                                     C.byref(nm)))
+        return nm.value, m12[:k1.size]
+
     def SearchByBoW(self, fv_kf, fv_f, desc_kf, desc_f, skip_kf=None, angle_kf=None, angle_f=None, cam_off_f=None):
         """ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vpMapPointMatches) (src/ORBmatcher.cc:349-666), whole function.
         fv = (nodes, ptr, idx) CSR of a DBoW2 FeatureVector; cam_off_f = None (F.Nleft == -1) or the 3 / 5 camera block offsets.

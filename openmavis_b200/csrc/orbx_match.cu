@@ -858,6 +858,74 @@ int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off
     return ORBX_OK;
 }
 
+int orbx_search_for_initialization(orbx_matcher *m, const orbx_kp *kps1, const uint8_t *desc1, int n1, const orbx_kp *kps2,
+                                   const uint8_t *desc2, int n2, const float *grid_bounds2, float *prev_matched, int window_size,
+                                   float nnratio, int check_orientation, int *matches12, int *nmatches) {
+    if (!m || n1 < 0 || n2 < 0 || !matches12 || !nmatches || !grid_bounds2 || (n1 && (!kps1 || !desc1 || !prev_matched)) ||
+        (n2 && (!kps2 || !desc2)))
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    *nmatches = 0;
+    if (n1 == 0 || n2 == 0) return ORBX_OK;
+    if (n1 >= 65535 || n2 >= 65535) return fail(ORBX_ERR_INVALID, "more than 65534 keypoints per frame are not supported");
+    int st;
+    SbpFrame F;
+    const int cam_off[2] = {0, n2};
+    const float sf1[1] = {1.0f};
+    if ((st = sbp_setup_frame(m, 1, cam_off, kps2, desc2, grid_bounds2, sf1, 1, nullptr, nullptr, nullptr, F)) != ORBX_OK) return st;
+    const size_t q = (size_t)n1 * 4;
+    M_CUDA(m->b[22].ensure(q * (1 + 4 + 4 + 4) + (size_t)n1 * (4 + 1 + 1 + 32) + 16 * 16));
+    uint8_t *base = m->b[22].as<uint8_t>();
+    size_t off = 0;
+    auto put = [&](const void *src, size_t nb) -> void * {
+        void *d = base + off;
+        cudaMemcpyAsync(d, src, nb, cudaMemcpyHostToDevice, m->stream);
+        off += (nb + 15) & ~(size_t)15;
+        return d;
+    };
+    std::vector<float> px(q, 0.0f), py(q, 0.0f), ang(n1);
+    std::vector<int> lvl4(q, 0);
+    std::vector<uint8_t> view4(q, 0), act(n1), hobs(n1, 1);
+    for (int i = 0; i < n1; i++) {
+        px[4 * (size_t)i] = prev_matched[2 * i]; py[4 * (size_t)i] = prev_matched[2 * i + 1];
+        lvl4[4 * (size_t)i] = kps1[i].octave;
+        act[i] = kps1[i].octave > 0 ? 0 : 1;                       // `if (level1 > 0) continue;` (:912-913)
+        view4[4 * (size_t)i] = act[i] && kps1[i].octave == 0;       // (a negative octave finds nothing: kp.octave < minLevel never false... gate [l, l])
+        ang[i] = kps1[i].angle;
+    }
+    SbpPoints P;
+    P.nmp = n1;
+    P.proj_x = (const float *)put(px.data(), q * 4);
+    P.proj_y = (const float *)put(py.data(), q * 4);
+    P.level = (const int *)put(lvl4.data(), q * 4);
+    P.view_cos = nullptr;
+    P.desc = (const uint4 *)put(desc1, (size_t)n1 * 32);
+    P.in_view = (const uint8_t *)put(view4.data(), q);
+    P.active = (const uint8_t *)put(act.data(), n1);
+    P.has_obs = (const uint8_t *)put(hobs.data(), n1);
+    P.angle = (const float *)put(ang.data(), (size_t)n1 * 4);
+    P.u_right = P.proj_ur = nullptr;
+    M_CUDA(cudaGetLastError());
+    P.th = (float)window_size; P.nnratio = nnratio;
+    P.mode = 2; P.level_gate = 0; P.check_ori = check_orientation ? 1 : 0; P.max_dist = 50;
+    M_CUDA(m->b[23].ensure(sbp_work_bytes(n1, n2)));
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    st = sbp_run(F, P, m->b[23].as<uint8_t>(), m->b[0], m->stream, &m->last_launches);
+    if (st != ORBX_OK) return st;
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    SbpResult R;
+    sbp_result_ptrs(m->b[23].as<uint8_t>(), n1, n2, &R);
+    M_CUDA(cudaMemcpyAsync(matches12, R.match12, (size_t)n1 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaMemcpyAsync(nmatches, R.nmatches, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < n1; i++)                                    // update prev matched (:992-995)
+        if (matches12[i] >= 0) { prev_matched[2 * i] = kps2[matches12[i]].x; prev_matched[2 * i + 1] = kps2[matches12[i]].y; }
+    return ORBX_OK;
+}
+
 // ---- fisheye stereo post-filter
 int orbx_kb8_triangulate_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, const float *xy1, const float *xy2, const float *sigma1,
                                  const float *sigma2, int n, float *depth, float *p3d) {

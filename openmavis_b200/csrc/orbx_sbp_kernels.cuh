@@ -16,6 +16,10 @@
 // bMono) (src/ORBmatcher.cc:1985-2413) on the same machinery: radius th * sf[octave of the last keypoint] for every camera,
 // level gate by bForward / bBackward, best candidate only (<= TH_HIGH), no stereo mirrors, an empty camera-0 window skips the
 // point's other cameras (the `continue` at :2062), then the rotation-histogram filter (ComputeThreeMaxima :2537-2573).
+//
+// mode 2 = ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:895-1004): level-0 keypoints of F1 search a fixed window of F2
+// around vbPrevMatched; a keypoint of F2 goes to the F1 keypoint with the smallest distance so far (vMatchedDistance, :927) and the
+// previous owner is evicted (:941-944).  In the resolve phase occ[] holds vMatchedDistance and assigned[] holds vnMatches21.
 #pragma once
 
 #include "orbx_match_kernels.cuh"
@@ -58,11 +62,12 @@ struct SbpWork {
     int *resolved;    // [nmp]
     int *nmatches;    // [8]: nmatches, scratch
     int *events;      // [nmp * 4] mode 1: keypoint | rotation bin << 16 of every accepted assignment, -1 = none
+    int *match12;     // [nmp] mode 2: vnMatches12
 };
-struct SbpResult { const int *assigned; const int *nmatches; };
+struct SbpResult { const int *assigned; const int *nmatches; const int *match12; };
 
 inline size_t sbp_work_bytes(int nmp, int N) {
-    return ((size_t)nmp * 4 * 3 + 1 + (size_t)N * 3 + nmp + 8) * sizeof(int) + 256;
+    return ((size_t)nmp * 4 * 3 + 1 + (size_t)N * 3 + 2 * (size_t)nmp + 8) * sizeof(int) + 256;
 }
 inline void sbp_carve(uint8_t *base, int nmp, int N, SbpWork *w) {
     int *p = (int *)base;
@@ -74,11 +79,12 @@ inline void sbp_carve(uint8_t *base, int nmp, int N, SbpWork *w) {
     w->assigned = p; p += N;
     w->resolved = p; p += nmp;
     w->nmatches = p; p += 8;
-    w->events = p;
+    w->events = p; p += nq;
+    w->match12 = p;
 }
 inline void sbp_result_ptrs(uint8_t *base, int nmp, int N, SbpResult *r) {
     SbpWork w; sbp_carve(base, nmp, N, &w);
-    r->assigned = w.assigned; r->nmatches = w.nmatches;
+    r->assigned = w.assigned; r->nmatches = w.nmatches; r->match12 = w.match12;
 }
 
 __device__ __forceinline__ bool sbp_query(const SbpFrame &F, const SbpPoints &P, int q, int &c, float &x, float &y, float &rr,
@@ -91,6 +97,7 @@ __device__ __forceinline__ bool sbp_query(const SbpFrame &F, const SbpPoints &P,
     const int lvl = P.level[q];
     if (lvl < 0) return false;                  // :142 nPredictedLevel != -1 (camera 0 assumes a valid level)
     x = P.proj_x[q]; y = P.proj_y[q];
+    if (P.mode == 2) { rr = P.th; min_lvl = lvl; max_lvl = lvl; return true; }    // GetFeaturesInArea(x, y, windowSize, level1, level1) :915-920
     if (P.mode == 1) {
         rr = __fmul_rn(P.th, F.scale_factors[lvl]);                            // :2040
         if (P.level_gate == ORBX_GATE_FORWARD) { min_lvl = lvl; max_lvl = -1; }            // :2044-2056
@@ -161,10 +168,12 @@ __device__ __forceinline__ void sbp_for_touch(const SbpFrame &F, bool mirrors, c
 __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, SbpWork W, const uint32_t *__restrict__ cand) {
     __shared__ int s_left;
     const int N = F.n_total, nmp = P.nmp;
-    for (int g = threadIdx.x; g < N; g += blockDim.x) { W.occ[g] = F.occupied0[g]; W.assigned[g] = -1; }
+    for (int g = threadIdx.x; g < N; g += blockDim.x) { W.occ[g] = P.mode == 2 ? 0x7FFFFFFF : (int)F.occupied0[g]; W.assigned[g] = -1; }
+    if (P.mode == 2)
+        for (int u = threadIdx.x; u < nmp; u += blockDim.x) W.match12[u] = -1;
     for (int u = threadIdx.x; u < nmp; u += blockDim.x) W.resolved[u] = (W.q_ptr[4 * u + 4] == W.q_ptr[4 * u]) ? 1 : 0;
     if (threadIdx.x == 0) W.nmatches[0] = 0;
-    if (P.mode == 1)
+    if (P.mode >= 1)
         for (int e = threadIdx.x; e < 4 * nmp; e += blockDim.x) W.events[e] = -1;
     __syncthreads();
     for (;;) {
@@ -187,6 +196,29 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
                 const int q = u * 4 + c;
                 const int b = W.q_ptr[q], e = W.q_ptr[q + 1];
                 if (b == e) continue;
+                if (P.mode == 2) {   // :923-961 (camera 0 only)
+                    int bestDist = 0x7FFFFFFF, bestDist2 = 0x7FFFFFFF, bestIdx = -1;
+                    for (int k = b; k < e; k++) {
+                        const uint32_t r = cand[k];
+                        const int idx = (int)(r & 0xFFFF), dist = (int)((r >> 16) & 0x1FF);
+                        if (W.occ[idx] <= dist) continue;                                  // vMatchedDistance[i2] <= dist
+                        if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx = idx; }
+                        else if (dist < bestDist2) bestDist2 = dist;
+                    }
+                    if (bestDist <= 50 && (float)bestDist < __fmul_rn((float)bestDist2, P.nnratio)) {
+                        const int old = W.assigned[bestIdx];                              // vnMatches21
+                        if (old >= 0) { W.match12[old] = -1; nm--; }
+                        W.match12[u] = bestIdx; W.assigned[bestIdx] = u; W.occ[bestIdx] = bestDist; nm++;
+                        if (P.check_ori) {
+                            float rot = __fsub_rn(P.angle[u], F.kps[bestIdx].angle);
+                            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                            int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30.0f));
+                            if (bin == 30) bin = 0;
+                            W.events[q] = u | (bin << 16);
+                        }
+                    }
+                    break;
+                }
                 if (P.mode == 1) {   // best candidate only, every camera on its own (:2068-2100 and the per-camera clones)
                     int bestDist = 256, bestIdx = -1;
                     for (int k = b; k < e; k++) {
@@ -242,7 +274,7 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
         if (s_left == 0) break;
         __syncthreads();
     }
-    if (P.mode != 1 || !P.check_ori) return;
+    if (P.mode == 0 || !P.check_ori) return;
     // ---- rotation consistency (:2392-2410): keep the assignments of the three fullest histogram bins
     __shared__ int s_hist[32], s_ind[3];
     if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
@@ -267,7 +299,10 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
         const int ev = W.events[e];
         if (ev < 0) continue;
         const int bin = (ev >> 16) & 31;
-        if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { W.assigned[ev & 0xFFFF] = -1; atomicSub(&W.nmatches[0], 1); }
+        if (bin == s_ind[0] || bin == s_ind[1] || bin == s_ind[2]) continue;
+        if (P.mode == 2) {   // :982-985: only matches that were not evicted meanwhile
+            if (W.match12[ev & 0xFFFF] >= 0) { W.match12[ev & 0xFFFF] = -1; atomicSub(&W.nmatches[0], 1); }
+        } else { W.assigned[ev & 0xFFFF] = -1; atomicSub(&W.nmatches[0], 1); }
     }
 }
 

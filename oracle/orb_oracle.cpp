@@ -1240,6 +1240,57 @@ int orc_search_by_bow_keyframes(int nn1, const int *nodes1, const int *ptr1, con
     return nmatches;
 }
 
+// ---- ORBmatcher::SearchForInitialization, ORBmatcher.cc:895-1004, over plain arrays (grid2 = orc_grid_create of F2.mvKeysUn) -------
+int orc_search_for_initialization(const orc_kp *kps1, const uint8_t *desc1, int n1, void *grid2, const orc_kp *kps2, const uint8_t *desc2,
+                                  int n2, float *vbPrevMatched, int windowSize, float nnratio, int checkOrientation, int *vnMatches12) {
+    const int TH_LOW = 50;
+    const KeyPt *k1 = (const KeyPt *)kps1, *k2 = (const KeyPt *)kps2;
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) vnMatches12[i] = -1;
+    std::vector<int> rotHist[30];
+    std::vector<int> vMatchedDistance(n2, INT_MAX), vnMatches21(n2, -1), vIndices2;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = k1[i1].octave;
+        if (level1 > 0) continue;
+        features_in_area(*(Grid *)grid2, k2, vbPrevMatched[2 * i1], vbPrevMatched[2 * i1 + 1], (float)windowSize, level1, level1, vIndices2);
+        if (vIndices2.empty()) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = descriptor_distance(desc1 + (size_t)i1 * 32, desc2 + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2; vnMatches21[bestIdx2] = i1; vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOrientation) rotHist[rot_bin(k1[i1].angle, k2[bestIdx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (checkOrientation) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < 30; i++) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < 30; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (vnMatches12[i1] >= 0) { vbPrevMatched[2 * i1] = k2[vnMatches12[i1]].x; vbPrevMatched[2 * i1 + 1] = k2[vnMatches12[i1]].y; }
+    return nmatches;
+}
+
 // ---- Frame::ComputeStereoMatches (src/Frame.cc:1057-1219) -------------------------------------------------------
 // hL / hR: oracle extractors that hold the last extraction of the (rectified) left / right image: mvKeys = out_kps of hL,
 // mvKeysRight = out_kps of hR, mDescriptors(Right) = out_desc, mvImagePyramid = lv[].  mb = baseline, mbf = baseline * fx.

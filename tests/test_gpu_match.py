@@ -530,6 +530,41 @@ def test_search_by_sim3(M):
     assert nf > 100
 
 
+@pytest.mark.parametrize('window,nnratio,check', [(10, 0.9, True), (25, 0.9, True), (40, 0.8, False)])
+def test_search_for_initialization(window, nnratio, check):
+    """src/ORBmatcher.cc:895-1004: level-0 windows, smallest-distance-so-far ownership with eviction, rotation filter."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    rng = np.random.default_rng(window)
+    rig, res = _extract_frame(512, 512, 1500, [5400 + window], (0, 511))
+    k2 = res[0][1].copy(); d2 = res[0][2].copy()
+    n2 = k2.size
+    n1 = 1400
+    src = rng.integers(0, n2, n1)                                      # several F1 keypoints compete for the same F2 keypoint
+    k1 = k2[src].copy()
+    k1['x'] += rng.uniform(-6, 6, n1).astype(np.float32); k1['y'] += rng.uniform(-6, 6, n1).astype(np.float32)
+    k1['angle'] = ((k2['angle'][src] + np.where(rng.random(n1) < 0.85, 15 + rng.uniform(-3, 3, n1), rng.uniform(0, 360, n1))) % 360).astype(np.float32)
+    d1 = d2[src] ^ np.packbits(rng.random((n1, 256)) < rng.uniform(0.01, 0.08, (n1, 1)), axis=1, bitorder='little')
+    d1[::9] = synth_descriptors(len(d1[::9]), 77)
+    prev = np.ascontiguousarray(np.stack([k1['x'], k1['y']], 1).astype(np.float32))
+    prev_ref = prev.copy()
+    M = ob.ORBmatcher(nnratio, checkOri=check)
+    nm, m12 = M.SearchForInitialization(k1, d1, k2, d2, (0, 512, 0, 512), prev, window)
+    L = O.lib()
+    g2 = L.orc_grid_create(O.p(k2), n2, C.c_float(0), C.c_float(512), C.c_float(0), C.c_float(512))
+    ref = np.zeros(n1, np.int32)
+    rn = L.orc_search_for_initialization(O.p(k1), O.p(d1), n1, C.c_void_p(g2), O.p(k2), O.p(d2), n2, O.p(prev_ref), window,
+                                         C.c_float(np.float32(nnratio)), int(check), O.p(ref))
+    L.orc_grid_destroy(C.c_void_p(g2))
+    assert rn == nm, (rn, nm)
+    assert np.array_equal(ref, m12), int((ref != m12).sum())
+    assert np.array_equal(prev, prev_ref)
+    lvl0 = int((k1['octave'] == 0).sum())
+    assert nm > 0.25 * lvl0 and (k1['octave'][m12 >= 0] == 0).all()
+    used = m12[m12 >= 0]
+    assert np.unique(used).size == used.size                           # eviction keeps one owner per F2 keypoint
+
+
 def test_search_by_projection_last_frame_degenerate():
     if ob.device_count() == 0:
         pytest.fail('no CUDA device')
