@@ -70,4 +70,34 @@ int ORBmatcher::MatchCandidates(const cv::Mat &query, const cv::Mat &train, cons
     return (int)nq;
 }
 
+int ORBmatcher::SearchByBoW(const std::vector<int> &nodes1, const std::vector<int> &ptr1, const std::vector<int> &idx1,
+                            const std::vector<int> &nodes2, const std::vector<int> &ptr2, const std::vector<int> &idx2, const cv::Mat &desc1,
+                            const cv::Mat &desc2, const std::vector<unsigned char> &skip1, const std::vector<unsigned char> &skip2,
+                            const std::vector<float> &angle1, const std::vector<float> &angle2, std::vector<int> &match12) {
+    match12.assign((size_t)desc1.rows, -1);
+    int nm = 0;
+    if (orbx_search_by_bow_keyframes(mHandle, (int)nodes1.size(), nodes1.data(), ptr1.data(), idx1.data(), (int)nodes2.size(), nodes2.data(),
+                                     ptr2.data(), idx2.data(), desc1.ptr<unsigned char>(), desc1.rows, desc2.ptr<unsigned char>(), desc2.rows,
+                                     skip1.empty() ? nullptr : skip1.data(), skip2.empty() ? nullptr : skip2.data(), angle1.data(),
+                                     angle2.data(), mfNNratio, mbCheckOrientation ? 1 : 0, match12.data(), &nm) != ORBX_OK)
+        die("SearchByBoW");
+    return nm;
+}
+
+int ORBmatcher::SearchForInitialization(const std::vector<cv::KeyPoint> &keys1, const cv::Mat &desc1, const std::vector<cv::KeyPoint> &keys2,
+                                        const cv::Mat &desc2, float minX, float maxX, float minY, float maxY,
+                                        std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize) {
+    static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_kp), "cv::KeyPoint and orbx_kp must have the same layout");
+    static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "cv::Point2f must be two packed floats");
+    vnMatches12.assign(keys1.size(), -1);                               // :902
+    const float gb[4] = {minX, maxX, minY, maxY};
+    int nm = 0;
+    if (orbx_search_for_initialization(mHandle, (const orbx_kp *)keys1.data(), desc1.ptr<unsigned char>(), (int)keys1.size(),
+                                       (const orbx_kp *)keys2.data(), desc2.ptr<unsigned char>(), (int)keys2.size(), gb,
+                                       (float *)vbPrevMatched.data(), windowSize, mfNNratio, mbCheckOrientation ? 1 : 0, vnMatches12.data(),
+                                       &nm) != ORBX_OK)
+        die("SearchForInitialization");
+    return nm;
+}
+
 }  // namespace ORB_SLAM3

@@ -46,6 +46,22 @@ public:
                         std::vector<int> &bestIdx, std::vector<int> &bestDist, std::vector<int> &secondDist, std::vector<int> &bestPos,
                         std::vector<int> &secondPos);
 
+    // ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vpMatches12) (src/ORBmatcher.cc:1006-1129), whole function:
+    // FeatureVectors as CSR, skip = feature without usable MapPoint, angles = mvKeysUn[i].angle.  match12[idx1] = idx2 or -1.
+    int SearchByBoW(const std::vector<int> &nodes1, const std::vector<int> &ptr1, const std::vector<int> &idx1,
+                    const std::vector<int> &nodes2, const std::vector<int> &ptr2, const std::vector<int> &idx2, const cv::Mat &desc1,
+                    const cv::Mat &desc2, const std::vector<unsigned char> &skip1, const std::vector<unsigned char> &skip2,
+                    const std::vector<float> &angle1, const std::vector<float> &angle2, std::vector<int> &match12);
+
+    // ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:895-1004), whole function, on the two frames' mvKeysUn / mDescriptors.
+    int SearchForInitialization(const std::vector<cv::KeyPoint> &keys1, const cv::Mat &desc1, const std::vector<cv::KeyPoint> &keys2,
+                                const cv::Mat &desc2, float minX, float maxX, float minY, float maxY,
+                                std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize = 10);
+
+    // The C-ABI handle: every other matcher (orbx_search_by_projection, orbx_search_by_projection_last, orbx_search_by_bow_frame,
+    // orbx_window_best, orbx_search_by_sim3, orbx_stereo_fisheye_matches, ... — include/orbx.h) takes it as its first argument.
+    orbx_matcher *Handle() const { return mHandle; }
+
     float mfNNratio;
     bool mbCheckOrientation;
 

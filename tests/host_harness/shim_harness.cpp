@@ -57,4 +57,19 @@ int shim_knn_ratio(unsigned char *q, int nq, unsigned char *t, int nt, double ra
     return ORB_SLAM3::ORBmatcher::TH_LOW * 1000 + ORB_SLAM3::ORBmatcher::TH_HIGH;
 }
 
+// SearchForInitialization through the shim class (std::vector<cv::KeyPoint> / cv::Point2f in, vnMatches12 out)
+int shim_search_for_initialization(float *kps1_28, unsigned char *d1, int n1, float *kps2_28, unsigned char *d2, int n2, float *prev_xy,
+                                   int window, float nnratio, int check, int *m12) {
+    ORB_SLAM3::ORBmatcher matcher(nnratio, check != 0);
+    std::vector<cv::KeyPoint> k1(n1), k2(n2);
+    memcpy((void *)k1.data(), kps1_28, (size_t)n1 * 28); memcpy((void *)k2.data(), kps2_28, (size_t)n2 * 28);
+    cv::Mat m1(n1, 32, CV_8U, d1, 32), m2(n2, 32, CV_8U, d2, 32);
+    std::vector<cv::Point2f> prev(n1);
+    memcpy((void *)prev.data(), prev_xy, (size_t)n1 * 8);
+    std::vector<int> v12;
+    const int nm = matcher.SearchForInitialization(k1, m1, k2, m2, 0.f, 512.f, 0.f, 512.f, prev, v12, window);
+    memcpy(m12, v12.data(), (size_t)n1 * 4); memcpy(prev_xy, prev.data(), (size_t)n1 * 8);
+    return nm;
+}
+
 }  // extern "C"

@@ -78,3 +78,27 @@ def test_shim_matcher_matches_oracle(shim):
     ridx, rdist = O.knn2(q, t)
     assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
     assert np.array_equal(keep.astype(bool), O.ratio_test(rdist, 0.8))
+
+
+@pytest.mark.gpu
+def test_shim_search_for_initialization_matches_oracle(shim):
+    """The shim class method (std::vector<cv::KeyPoint>, cv::Point2f) against the oracle restatement of src/ORBmatcher.cc:895-1004."""
+    import openmavis_b200 as ob
+    from openmavis_b200.synth import synth_image
+    rng = np.random.default_rng(5)
+    rig = ob.RigExtractor(512, 512, 1, 1200)
+    res = rig.extract([synth_image(512, 512, 6100)], ob.make_params(1, 1200, 20, 7, (0, 511)))
+    k2 = res[0][1].copy(); d2 = res[0][2].copy()
+    n2 = k2.size; n1 = 900
+    src = rng.integers(0, n2, n1)
+    k1 = k2[src].copy()
+    k1['x'] += rng.uniform(-5, 5, n1).astype(np.float32); k1['y'] += rng.uniform(-5, 5, n1).astype(np.float32)
+    d1 = d2[src] ^ np.packbits(rng.random((n1, 256)) < 0.05, axis=1, bitorder='little')
+    prev = np.ascontiguousarray(np.stack([k1['x'], k1['y']], 1).astype(np.float32)); prev_ref = prev.copy()
+    m12 = np.zeros(n1, np.int32); ref = np.zeros(n1, np.int32)
+    nm = shim.shim_search_for_initialization(O.p(k1), O.p(d1), n1, O.p(k2), O.p(d2), n2, O.p(prev), 20, C.c_float(0.9), 1, O.p(m12))
+    L = O.lib()
+    g2 = L.orc_grid_create(O.p(k2), n2, C.c_float(0), C.c_float(512), C.c_float(0), C.c_float(512))
+    rn = L.orc_search_for_initialization(O.p(k1), O.p(d1), n1, C.c_void_p(g2), O.p(k2), O.p(d2), n2, O.p(prev_ref), 20, C.c_float(0.9), 1, O.p(ref))
+    L.orc_grid_destroy(C.c_void_p(g2))
+    assert nm == rn and np.array_equal(m12, ref) and np.array_equal(prev, prev_ref) and nm > 50
