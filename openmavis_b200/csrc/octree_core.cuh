@@ -397,8 +397,10 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
         V[0] = ls; V[1] = 0; V[2] = 0; V[3] = -1;
     }
     cx.sync();
-    if (V[0] != n_ini)   // (identity unless a root is empty)
-        for (int i = cx.tid; i < n; i += cx.nt) node[i] = (unsigned short)w.remap[node[i]];
+    // Labels: node[i] is a KEY, the candidate's list position is map[node[i]] with map = w.child_pos.  Every round stores the key
+    // 4 * position + quadrant while it counts, and publishes the map of those keys when the new list is known — one sweep over
+    // the candidates per round instead of two.
+    for (int r = cx.tid; r < n_ini; r += cx.nt) w.child_pos[r] = w.remap[r];
     cx.sync();
     (void)x_span;
 
@@ -417,13 +419,14 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int i = base + u * cx.nt + cx.tid;
-                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
+                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? w.child_pos[node[i]] : -1;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int p = pn[u];
                     const bool v = p >= 0 && !T.nomore[p];
-                    const int key = v ? 4 * p + oct_quadrant(T.box[p], cd[u]) : 0;
+                    const int key = v ? 4 * p + oct_quadrant(T.box[p], cd[u]) : (p > 0 ? 4 * p : 0);
+                    if (p >= 0) node[base + u * cx.nt + cx.tid] = (unsigned short)key;
                     cx.hist_add(w.child_cnt, key, v, 4 * ls);
                 }
             }
@@ -444,7 +447,7 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
             for (int p = cx.tid; p < ls; p += cx.nt) {
                 if (T.nomore[p]) {
                     const int np = A + w.scan_b[p];
-                    w.remap[p] = np;
+                    w.child_pos[4 * p] = np;
                     U.box[np] = T.box[p]; U.cnt[np] = T.cnt[p]; U.nomore[np] = 1;
                 } else {
                     int j = 0, jj = 0;
@@ -457,22 +460,6 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
                         if (c > 1) { w.clist[w.scan_c[p] + jj] = np; jj++; }
                         j++;
                     }
-                }
-            }
-            cx.sync();
-            for (int base = 0; base < n; base += 4 * cx.nt) {
-                uint32_t cd[4]; int pn[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = base + u * cx.nt + cx.tid;
-                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int p = pn[u];
-                    if (p >= 0)
-                        node[base + u * cx.nt + cx.tid] =
-                            (unsigned short)(T.nomore[p] ? w.remap[p] : w.child_pos[4 * p + oct_quadrant(T.box[p], cd[u])]);
                 }
             }
             cx.sync();
@@ -502,16 +489,19 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int i = base + u * cx.nt + cx.tid;
-                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
+                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? w.child_pos[node[i]] : -1;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int p = pn[u];
                     const int c = p >= 0 ? w.cidx[p] : -1;
                     const bool v = c >= 0;
-                    cx.hist_add(w.child_cnt, v ? 4 * c + oct_quadrant(T.box[p], cd[u]) : 0, v, 4 * m);
+                    const int q = v ? oct_quadrant(T.box[p], cd[u]) : 0;
+                    if (p >= 0) node[base + u * cx.nt + cx.tid] = (unsigned short)(4 * p + q);
+                    cx.hist_add(w.child_cnt, 4 * c + q, v, 4 * m);
                 }
             }
+            cx.sync();   // (the old map is dead: the sort below uses its storage)
             {   // exact std::sort of the candidates, block-parallel; scratch = arrays that are dead until the tables are rebuilt
                 OctSortScratch S;
                 S.rf[0] = w.scan_a; S.rl[0] = w.scan_b; S.rd[0] = w.scan_c;
@@ -546,7 +536,7 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
             for (int p = cx.tid; p < ls; p += cx.nt) {
                 if (w.cidx[p] <= -2) continue;
                 const int q = A + w.scan_b[p];
-                w.remap[p] = q;
+                w.child_pos[4 * p] = q; w.child_pos[4 * p + 1] = q; w.child_pos[4 * p + 2] = q; w.child_pos[4 * p + 3] = q;
                 U.box[q] = T.box[p]; U.cnt[q] = T.cnt[p]; U.nomore[q] = T.nomore[p];
             }
             // new candidate list is written to scan-free storage: reuse `remap`-independent array w.best as temp
@@ -558,27 +548,10 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
                     const int cc = w.child_cnt[4 * c + q];
                     if (cc == 0) continue;
                     const int q2 = A - 1 - (w.scan_a[k] + j);
-                    w.child_pos[4 * c + q] = q2;
+                    w.child_pos[4 * p + q] = q2;
                     U.box[q2] = oct_child_box(T.box[p], q); U.cnt[q2] = cc; U.nomore[q2] = cc == 1;
                     if (cc > 1) { w.best[w.scan_c[k] + jj] = (unsigned)q2; jj++; }
                     j++;
-                }
-            }
-            cx.sync();
-            for (int base = 0; base < n; base += 4 * cx.nt) {
-                uint32_t cd[4]; int pn[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int i = base + u * cx.nt + cx.tid;
-                    cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int p = pn[u];
-                    if (p < 0) continue;
-                    const int ci = w.cidx[p];
-                    node[base + u * cx.nt + cx.tid] = (unsigned short)(ci <= -2 ? w.child_pos[4 * w.order[-2 - ci] + oct_quadrant(T.box[p], cd[u])]
-                                                                                 : w.remap[p]);
                 }
             }
             cx.sync();
@@ -601,7 +574,7 @@ OCT_HD int oct_distribute(Ctx &cx, OctWork &w, const uint32_t *cand, unsigned sh
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int i = base + u * cx.nt + cx.tid;
-            cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? (int)node[i] : -1;
+            cd[u] = i < n ? cand[i] : 0u; pn[u] = i < n ? w.child_pos[node[i]] : -1;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
