@@ -56,10 +56,10 @@ struct SbpPoints {
 struct SbpWork {
     int *counts;      // [nq]
     int *q_ptr;       // [nq+1]
-    int *tmin;        // [N]
+    int *tmin;        // [2 N] 64-bit (round, point) stamps
     int *occ;         // [N]
     int *assigned;    // [N]
-    int *resolved;    // [nmp]
+    int *resolved;    // [nmp] (unused)
     int *nmatches;    // [8]: nmatches, scratch
     int *events;      // [nmp * 4] mode 1: keypoint | rotation bin << 16 of every accepted assignment, -1 = none
     int *match12;     // [nmp] mode 2: vnMatches12
@@ -67,14 +67,14 @@ struct SbpWork {
 struct SbpResult { const int *assigned; const int *nmatches; const int *match12; };
 
 inline size_t sbp_work_bytes(int nmp, int N) {
-    return ((size_t)nmp * 4 * 3 + 1 + (size_t)N * 3 + 2 * (size_t)nmp + 8) * sizeof(int) + 256;
+    return ((size_t)nmp * 4 * 3 + 2 + (size_t)N * 4 + 2 * (size_t)nmp + 8) * sizeof(int) + 256;
 }
 inline void sbp_carve(uint8_t *base, int nmp, int N, SbpWork *w) {
     int *p = (int *)base;
     const size_t nq = (size_t)nmp * 4;
+    w->tmin = p; p += 2 * (size_t)N;       // 64-bit stamps (base is 256-byte aligned)
     w->counts = p; p += nq;
     w->q_ptr = p; p += nq + 1;
-    w->tmin = p; p += N;
     w->occ = p; p += N;
     w->assigned = p; p += N;
     w->resolved = p; p += nmp;
@@ -165,31 +165,54 @@ __device__ __forceinline__ void sbp_for_touch(const SbpFrame &F, bool mirrors, c
     }
 }
 
+constexpr int kSbpTouchCap = 12;
+
+// Resolve rounds.  Thread t owns the points t, t + 1024, ...; `mine` is its smallest unresolved one.  A round looks only at the WINDOW
+// [lo, lo + 1024) of point indices, lo = the smallest unresolved point of the block: every point outside it is larger than every
+// point inside, so "smallest unresolved point on each keypoint it touches" can be decided among the window's points alone — at
+// most one point per thread and round.  The per-keypoint minimum is an atomicMax of (round << 32 | ~point): a new round's
+// stamp outranks every older value, so the array is never cleared.
 __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, SbpWork W, const uint32_t *__restrict__ cand) {
-    __shared__ int s_left;
+    __shared__ int s_lo;
     const int N = F.n_total, nmp = P.nmp;
-    for (int g = threadIdx.x; g < N; g += blockDim.x) { W.occ[g] = P.mode == 2 ? 0x7FFFFFFF : (int)F.occupied0[g]; W.assigned[g] = -1; }
+    unsigned long long *tmin = reinterpret_cast<unsigned long long *>(W.tmin);
+    for (int g = threadIdx.x; g < N; g += blockDim.x) {
+        W.occ[g] = P.mode == 2 ? 0x7FFFFFFF : (int)F.occupied0[g]; W.assigned[g] = -1; tmin[g] = 0ull;
+    }
     if (P.mode == 2)
         for (int u = threadIdx.x; u < nmp; u += blockDim.x) W.match12[u] = -1;
-    for (int u = threadIdx.x; u < nmp; u += blockDim.x) W.resolved[u] = (W.q_ptr[4 * u + 4] == W.q_ptr[4 * u]) ? 1 : 0;
     if (threadIdx.x == 0) W.nmatches[0] = 0;
     if (P.mode >= 1)
         for (int e = threadIdx.x; e < 4 * nmp; e += blockDim.x) W.events[e] = -1;
-    __syncthreads();
-    for (;;) {
-        if (threadIdx.x == 0) s_left = 0;
-        for (int g = threadIdx.x; g < N; g += blockDim.x) W.tmin[g] = 0x7FFFFFFF;
-        __syncthreads();
-        for (int u = threadIdx.x; u < nmp; u += blockDim.x) {
-            if (W.resolved[u]) continue;
-            sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, [&](int g) { atomicMin(&W.tmin[g], u); });
+    // a thread's current point stays the same for many rounds: its touch set (keypoints it may read or write) is cached in shared memory
+    __shared__ unsigned short s_touch[kSbpTouchCap][1024];
+    int mine = threadIdx.x, nm_total = 0, loaded = -1, nt = 0;
+    for (unsigned round = 1;; round++) {
+        if (threadIdx.x == 0) s_lo = 0x7FFFFFFF;
+        __syncthreads();                                              // (also orders the previous round's claims before this round's reads)
+        while (mine < nmp && W.q_ptr[4 * mine + 4] == W.q_ptr[4 * mine]) mine += blockDim.x;   // points without candidates
+        if (mine < nmp) atomicMin(&s_lo, mine);
+        if (mine < nmp && loaded != mine) {
+            nt = 0;
+            sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, mine, [&](int g) { if (nt < kSbpTouchCap) s_touch[nt][threadIdx.x] = (unsigned short)g; nt++; });
+            loaded = mine;
         }
         __syncthreads();
-        for (int u = threadIdx.x; u < nmp; u += blockDim.x) {
-            if (W.resolved[u]) continue;
+        const int lo = s_lo;
+        if (lo == 0x7FFFFFFF) break;
+        const bool active = mine < nmp && mine < lo + (int)blockDim.x;
+        const int u = mine;
+        const unsigned long long key = ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)u);
+        if (active) {
+            if (nt <= kSbpTouchCap) for (int j = 0; j < nt; j++) atomicMax(&tmin[s_touch[j][threadIdx.x]], key);
+            else sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, [&](int g) { atomicMax(&tmin[g], key); });
+        }
+        __syncthreads();
+        if (active) {
             bool fin = true;
-            sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, [&](int g) { if (W.tmin[g] != u) fin = false; });
-            if (!fin) { atomicAdd(&s_left, 1); continue; }
+            if (nt <= kSbpTouchCap) { for (int j = 0; j < nt; j++) if (__ldcg(&tmin[s_touch[j][threadIdx.x]]) != key) fin = false; }   // (L2: the atomics do not update this SM's L1)
+            else sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, [&](int g) { if (__ldcg(&tmin[g]) != key) fin = false; });
+            if (fin) {
             // ---- sequential body of the reference for map point u
             int nm = 0;
             for (int c = 0; c < 4; c++) {
@@ -267,13 +290,13 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
                     }
                 }
             }
-            if (nm) atomicAdd(&W.nmatches[0], nm);
-            W.resolved[u] = 1;
+            nm_total += nm;
+            mine += blockDim.x;
+            }
         }
-        __syncthreads();
-        if (s_left == 0) break;
-        __syncthreads();
     }
+    if (nm_total) atomicAdd(&W.nmatches[0], nm_total);
+    __syncthreads();
     if (P.mode == 0 || !P.check_ori) return;
     // ---- rotation consistency (:2392-2410): keep the assignments of the three fullest histogram bins
     __shared__ int s_hist[32], s_ind[3];
