@@ -829,38 +829,58 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
         __syncwarp();
         mbar_wait(&s_bar[wid], 0);
     }
-    // ---- orientation: lane = column u of the patch; the lane's column sum gives m10, the row-weighted sum m01
-    const int u = lane - kHalfPatch;
+    // ---- orientation (IC_Angle): m10 = sum u I, m01 = sum v I over the disc |u| <= umax[|v|]
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
+    if (tma) {
+        // lane = row v of the staged patch: its 31 bytes u = -15..15 are 8 funnel-shifted words; the disc is a byte mask, the two
+        // sums are IDP.4A with the weights u (signed) and 1
+        if (lane < 31) {
+            const int v = lane - kHalfPatch, av = v < 0 ? -v : v;
+            const int m = (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15);                      // umax[|v|], src/ORBextractor.cc:399-413
+            const uint32_t bits = ((2u << (2 * m)) - 1u) << (kHalfPatch - m);                    // bytes 15 - m .. 15 + m of the row
+            const int c0 = ((kXO + x - 16) & 15) + 1;                                            // byte of column x - 15 in the staged row
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(op + lane * kOriW + (c0 & ~3));
+            const int sh = 8 * (c0 & 3);
+            uint32_t w[9];
+#pragma unroll
+            for (int j = 0; j < 9; j++) w[j] = rw[j];
+            int rowsum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t px4 = __funnelshift_r(w[j], w[j + 1], sh);
+                const uint32_t nib = (bits >> (4 * j)) & 0xFu;
+                const uint32_t msk = ((nib * 0x00204081u) & 0x01010101u) * 0xFFu;
+                const uint32_t a = px4 & msk;
+                const int u0 = 4 * j - kHalfPatch;                                               // weights u0 .. u0 + 3 as signed bytes
+                const uint32_t wu = (uint32_t)(u0 & 0xFF) | ((uint32_t)((u0 + 1) & 0xFF) << 8) | ((uint32_t)((u0 + 2) & 0xFF) << 16) |
+                                    ((uint32_t)((u0 + 3) & 0xFF) << 24);
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(a), "r"(wu));
+                rowsum = (int)__dp4a(a, 0x01010101u, (uint32_t)rowsum);
+            }
+            m01 = v * rowsum;
+        }
+    } else if (lane < 31) {
+        // lane = column u of the patch; the lane's column sum gives m10, the row-weighted sum m01
+        const int u = lane - kHalfPatch;
         const int au = u < 0 ? -u : u;
         constexpr int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // src/ORBextractor.cc:399-413
         int colsum = 0;
-        if (tma) {
-            const uint8_t *p = op + ((kXO + x - 16) & 15) + lane + 1;   // column x + u of the staged patch
+        const uint8_t *p = plane_ptr(pyr, L, b) + (long long)(kYO + y - kHalfPatch) * L.pitch + kXO + x + u;
 #pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; v++)
-                if (au <= umax[v < 0 ? -v : v]) {
-                    const int val = p[(v + kHalfPatch) * kOriW];
-                    colsum += val; m01 += v * val;
-                }
-        } else {
-            const uint8_t *p = plane_ptr(pyr, L, b) + (long long)(kYO + y - kHalfPatch) * L.pitch + kXO + x + u;
-#pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; v++) {   // fully unrolled: 31 independent loads in flight
-                if (au <= umax[v < 0 ? -v : v]) {
-                    const int val = __ldg(p);
-                    colsum += val; m01 += v * val;
-                }
-                p += L.pitch;
+        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {   // fully unrolled: 31 independent loads in flight
+            if (au <= umax[v < 0 ? -v : v]) {
+                const int val = __ldg(p);
+                colsum += val; m01 += v * val;
             }
+            p += L.pitch;
         }
         m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
     const float angle = orbx_fast_atan2((float)m01, (float)m10);
-    // ---- descriptor: lane = output byte; its 16 pattern points are 32 signed bytes = two 128-bit loads
+    // ---- descriptor: lane = output byte; its 16 pattern points are 32 signed bytes = two 128-bit loads (a float table — 8 float4
+    //      per lane — was measured 2x slower: 128 B per lane of strided L1 traffic)
     const float rad = __fmul_rn(angle, 0.0174532924f);   // (float)(CV_PI/180.f)
     float sn, cs;
     orbx_sincosf(rad, &sn, &cs);
@@ -874,6 +894,8 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
         int tv[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
+            // (int8 -> float and cvRound through the 1.5 * 2^23 magic constant — PRMT + IADD + FADD instead of I2F / F2I — was measured
+            //  slower: the kernel is bound by issue slots, not by the conversion pipe)
             const float px = (float)(signed char)(pw[k] >> (16 * e)), py = (float)(signed char)(pw[k] >> (16 * e + 8));
             float fy, fx;
             if (kFma) { fy = __fmaf_rn(px, sn, __fmul_rn(py, cs)); fx = __fmaf_rn(px, cs, -__fmul_rn(py, sn)); }
