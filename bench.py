@@ -246,6 +246,7 @@ def main():
     ap.add_argument('--ref-frames', type=int, default=32, help='rig frames per step of the CPU reference arm')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline sample')
     ap.add_argument('--no-matching', action='store_true')
+    ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the rank to the CPU cores next to its GPU')
     ap.add_argument('--knn-n', type=int, default=100000)
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -261,6 +262,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
     torch.cuda.set_device(local)
+    # one process per GPU: run it (and first-touch its pinned staging buffers) on the NUMA node the GPU hangs off
+    affinity0 = os.sched_getaffinity(0)
+    numa_node = None
+    if not args.no_numa_bind:
+        from openmavis_b200.shard import bind_to_gpu_numa
+        pr = torch.cuda.get_device_properties(local)
+        if all(hasattr(pr, a) for a in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
+            numa_node = bind_to_gpu_numa('%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
@@ -482,6 +491,7 @@ def main():
     # ---------------- CPU baseline (rank 0, N == 1 only; bounded sample) ----------------
     cpu = None
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        os.sched_setaffinity(0, affinity0)             # the CPU arm uses every host core again
         threads = os.cpu_count() or 1
         cpu_oracle_run(2, threads)                      # warm-up (page in, thread pool)
         nfr, done, spent = 32, 0, 0.0
@@ -500,6 +510,7 @@ def main():
             'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'frames_per_step_per_gpu': frames, 'images_per_step_per_gpu': n_img,
                        'features_per_camera': NFEAT, 'fast_thresholds': [INI, MIN], 'levels': 8, 'scale_factor': 1.2,
                        'keypoints_per_image': kp_per_image, 'pipeline': 'two extractor handles alternate over the steps (one stream each)',
+                       'host_numa_node': numa_node,
                        'l2': 'inputs+pyramids per step (%.0f MB) exceed the 126 MB L2' % ((px * 1.0 + px * 3.7 * 2) / 1e6)},
             'e2e': {'value': e2e_value, 'unit': 'rig-frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps, 'timing': 'host wall clock between barrier + synchronize',

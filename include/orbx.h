@@ -344,6 +344,15 @@ int orbx_stereo_fisheye_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, con
                                 int mono_right, const float *level_sigma2, int nlevels, double ratio, int *left_to_right,
                                 int *right_to_left, float *depth, float *p3d, int *counts);
 
+/* Same with the keypoints and descriptors of the two cameras already in DEVICE memory — the rows the extraction left there
+ * (orbx_extract_device_results: d_kps + image * cap, d_desc + image * cap * 32, with n_left / mono_left = the n_kp / n_mono the
+ * extraction call returned for the image): no descriptor leaves the GPU between extraction and stereo matching.  The caller orders
+ * the call after the extraction (same stream via orbx_matcher_set_stream, or a synchronisation).  Results: HOST pointers. */
+int orbx_stereo_fisheye_matches_device(orbx_matcher *m, const orbx_kb8_stereo *rig, const orbx_kp *d_kps_left, const uint8_t *d_desc_left,
+                                       int n_left, int mono_left, const orbx_kp *d_kps_right, const uint8_t *d_desc_right, int n_right,
+                                       int mono_right, const float *level_sigma2, int nlevels, double ratio, int *left_to_right,
+                                       int *right_to_left, float *depth, float *p3d, int *counts);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483), batched over map points: group g = descriptor rows
  * [ptr[g], ptr[g+1]) of desc (the observations of one map point, in the order the reference collects them).
  * best[g] = index inside the group of the descriptor with the least median Hamming distance to the rest (first minimum,

@@ -183,6 +183,23 @@ class RigExtractor:
         _check(self.L.orbx_extract_device_results(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return a.value, b.value, c.value, d.value
 
+    def compute_stereo_fisheye_matches(self, matcher, rig, img_left, img_right, counts_left, counts_right, level_sigma2=None, ratio=0.7):
+        """Frame::ComputeStereoFishEyeMatches / ComputeMultiFishEyeMatches (src/Frame.cc:1409-1525) on two images of the last call,
+        reading keypoints and descriptors where the extraction left them on the device.  counts_* = (n_kp, n_mono) the extraction
+        returned for the image.  Returns the dict of ORBmatcher.ComputeStereoFishEyeMatches."""
+        d_kps, d_desc, _, _ = self.device_results()
+        nl, ml = int(counts_left[0]), int(counts_left[1]); nr, mr = int(counts_right[0]), int(counts_right[1])
+        sg = np.ascontiguousarray(self.sigma2 if level_sigma2 is None else level_sigma2, np.float32)
+        l2r = np.full(max(nl, 1), -1, np.int32); r2l = np.full(max(nr, 1), -1, np.int32)
+        depth = np.full(max(nl, 1), -1, np.float32); p3d = np.zeros((max(nl, 1), 3), np.float32); cnt = np.zeros(2, np.int32)
+        kp_b = KP_DTYPE.itemsize
+        _check(self.L.orbx_stereo_fisheye_matches_device(
+            matcher.h, _p(rig), C.c_void_p(d_kps + img_left * self.cap * kp_b), C.c_void_p(d_desc + img_left * self.cap * 32), nl, ml,
+            C.c_void_p(d_kps + img_right * self.cap * kp_b), C.c_void_p(d_desc + img_right * self.cap * 32), nr, mr, _p(sg), sg.size,
+            C.c_double(ratio), _p(l2r), _p(r2l), _p(depth), _p(p3d), _p(cnt)))
+        return dict(nMatches=int(cnt[0]), descMatches=int(cnt[1]), mvLeftToRightMatch=l2r[:nl], mvRightToLeftMatch=r2l[:nr],
+                    mvDepth=depth[:nl], mvStereo3Dpoints=p3d[:nl])
+
     def compute_stereo_matches(self, img_left, img_right, mb, mbf, right=None):
         """Frame::ComputeStereoMatches (src/Frame.cc:1057-1219) on two images of the last call(s) -> (n, mvuRight, mvDepth).
         right: the RigExtractor that holds the right image (default: this one)."""

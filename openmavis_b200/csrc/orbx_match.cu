@@ -953,30 +953,16 @@ int orbx_kb8_triangulate_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, co
     return ORBX_OK;
 }
 
-int orbx_stereo_fisheye_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, const orbx_kp *kps_left, const uint8_t *desc_left,
-                                int n_left, int mono_left, const orbx_kp *kps_right, const uint8_t *desc_right, int n_right,
-                                int mono_right, const float *level_sigma2, int nlevels, double ratio, int *left_to_right,
-                                int *right_to_left, float *depth, float *p3d, int *counts) {
-    if (!m || !rig || n_left < 0 || n_right < 0 || mono_left < 0 || mono_left > n_left || mono_right < 0 || mono_right > n_right ||
-        !level_sigma2 || nlevels < 1 || nlevels > 16 || (n_left && (!kps_left || !desc_left || !left_to_right || !depth || !p3d)) ||
-        (n_right && (!kps_right || !desc_right || !right_to_left)))
-        return fail(ORBX_ERR_INVALID, "bad arguments");
-    M_CUDA(cudaSetDevice(m->device));
-    m->last_launches = 0;
+// device core: keypoints / descriptors already on the device (all rows of both cameras; the lapping blocks start at mono_*)
+static int fisheye_core(orbx_matcher *m, const orbx_kb8_stereo *rig, const orbx_kp *d_kps_left, const uint8_t *d_desc_left, int n_left,
+                        int mono_left, const orbx_kp *d_kps_right, const uint8_t *d_desc_right, int n_right, int mono_right,
+                        const float *level_sigma2, int nlevels, double ratio, int *left_to_right, int *right_to_left, float *depth,
+                        float *p3d, int *counts) {
     for (int i = 0; i < n_left; i++) { left_to_right[i] = -1; depth[i] = -1.0f; p3d[3 * i] = p3d[3 * i + 1] = p3d[3 * i + 2] = 0.0f; }
     for (int i = 0; i < n_right; i++) right_to_left[i] = -1;
     if (counts) counts[0] = counts[1] = 0;
     const int nq = n_left - mono_left, nt = n_right - mono_right;
     if (nq == 0 || nt < 2) return ORBX_OK;                                            // knnMatch returns fewer than 2 neighbours
-    for (int i = mono_left; i < n_left; i++)
-        if (kps_left[i].octave < 0 || kps_left[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "keypoint octave outside the level table");
-    for (int i = mono_right; i < n_right; i++)
-        if (kps_right[i].octave < 0 || kps_right[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "keypoint octave outside the level table");
-    int st;
-    if ((st = upload(m, m->b[1], desc_left + (size_t)mono_left * 32, (size_t)nq * 32)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[2], desc_right + (size_t)mono_right * 32, (size_t)nt * 32)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[5], kps_left, (size_t)n_left * sizeof(orbx_kp))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[6], kps_right, (size_t)n_right * sizeof(orbx_kp))) != ORBX_OK) return st;
     M_CUDA(m->b[3].ensure((size_t)nq * 2 * sizeof(int)));
     M_CUDA(m->b[4].ensure((size_t)nq * 2 * sizeof(int)));
     // outputs: l2r [n_left] | r2l [n_right] | depth [n_left] | p3d [3 n_left] | counters [2], pre-filled from the host copies
@@ -987,10 +973,11 @@ int orbx_stereo_fisheye_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, con
     M_CUDA(cudaMemcpyAsync(d_out + o_r2l, right_to_left, (size_t)n_right * 4, cudaMemcpyHostToDevice, m->stream));
     M_CUDA(cudaMemcpyAsync(d_out + o_depth, depth, (size_t)n_left * 4, cudaMemcpyHostToDevice, m->stream));
     M_CUDA(cudaMemsetAsync(d_out + o_p3d, 0, (3 * (size_t)n_left + 2) * 4, m->stream));
-    st = orbx_knn2_device(m, m->b[1].as<uint8_t>(), nq, m->b[2].as<uint8_t>(), nt, m->b[3].as<int>(), m->b[4].as<int>());
+    int st = orbx_knn2_device(m, d_desc_left + (size_t)mono_left * 32, nq, d_desc_right + (size_t)mono_right * 32, nt, m->b[3].as<int>(),
+                              m->b[4].as<int>());
     if (st != ORBX_OK) return st;
     FisheyeArgs A;
-    A.kpL = m->b[5].as<orbx_kp>(); A.kpR = m->b[6].as<orbx_kp>();
+    A.kpL = d_kps_left; A.kpR = d_kps_right;
     A.nL = n_left; A.nR = n_right; A.monoL = mono_left; A.monoR = mono_right;
     A.idx = m->b[3].as<int>(); A.dist = m->b[4].as<int>();
     for (int l = 0; l < 16; l++) A.sigma2[l] = l < nlevels ? level_sigma2[l] : 0.0f;
@@ -1009,6 +996,48 @@ int orbx_stereo_fisheye_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, con
     M_CUDA(cudaStreamSynchronize(m->stream));
     if (counts) { counts[0] = cnt[0]; counts[1] = cnt[1]; }
     return ORBX_OK;
+}
+
+static bool fisheye_args_ok(orbx_matcher *m, const orbx_kb8_stereo *rig, const void *kl, const void *dl, int n_left, int mono_left,
+                            const void *kr, const void *dr, int n_right, int mono_right, const float *level_sigma2, int nlevels,
+                            const int *l2r, const int *r2l, const float *depth, const float *p3d) {
+    return m && rig && n_left >= 0 && n_right >= 0 && mono_left >= 0 && mono_left <= n_left && mono_right >= 0 && mono_right <= n_right &&
+           level_sigma2 && nlevels >= 1 && nlevels <= 16 && (!n_left || (kl && dl && l2r && depth && p3d)) && (!n_right || (kr && dr && r2l));
+}
+
+int orbx_stereo_fisheye_matches(orbx_matcher *m, const orbx_kb8_stereo *rig, const orbx_kp *kps_left, const uint8_t *desc_left,
+                                int n_left, int mono_left, const orbx_kp *kps_right, const uint8_t *desc_right, int n_right,
+                                int mono_right, const float *level_sigma2, int nlevels, double ratio, int *left_to_right,
+                                int *right_to_left, float *depth, float *p3d, int *counts) {
+    if (!fisheye_args_ok(m, rig, kps_left, desc_left, n_left, mono_left, kps_right, desc_right, n_right, mono_right, level_sigma2, nlevels,
+                         left_to_right, right_to_left, depth, p3d))
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    for (int i = mono_left; i < n_left; i++)
+        if (kps_left[i].octave < 0 || kps_left[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "keypoint octave outside the level table");
+    for (int i = mono_right; i < n_right; i++)
+        if (kps_right[i].octave < 0 || kps_right[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "keypoint octave outside the level table");
+    int st;
+    if ((st = upload(m, m->b[1], desc_left, (size_t)n_left * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], desc_right, (size_t)n_right * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[5], kps_left, (size_t)n_left * sizeof(orbx_kp))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[6], kps_right, (size_t)n_right * sizeof(orbx_kp))) != ORBX_OK) return st;
+    return fisheye_core(m, rig, m->b[5].as<orbx_kp>(), m->b[1].as<uint8_t>(), n_left, mono_left, m->b[6].as<orbx_kp>(), m->b[2].as<uint8_t>(),
+                        n_right, mono_right, level_sigma2, nlevels, ratio, left_to_right, right_to_left, depth, p3d, counts);
+}
+
+int orbx_stereo_fisheye_matches_device(orbx_matcher *m, const orbx_kb8_stereo *rig, const orbx_kp *d_kps_left, const uint8_t *d_desc_left,
+                                       int n_left, int mono_left, const orbx_kp *d_kps_right, const uint8_t *d_desc_right, int n_right,
+                                       int mono_right, const float *level_sigma2, int nlevels, double ratio, int *left_to_right,
+                                       int *right_to_left, float *depth, float *p3d, int *counts) {
+    if (!fisheye_args_ok(m, rig, d_kps_left, d_desc_left, n_left, mono_left, d_kps_right, d_desc_right, n_right, mono_right, level_sigma2,
+                         nlevels, left_to_right, right_to_left, depth, p3d))
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    return fisheye_core(m, rig, d_kps_left, d_desc_left, n_left, mono_left, d_kps_right, d_desc_right, n_right, mono_right, level_sigma2,
+                        nlevels, ratio, left_to_right, right_to_left, depth, p3d, counts);
 }
 
 int orbx_distinctive_descriptors(orbx_matcher *m, const uint8_t *desc, const int *ptr, int ngroups, int *best) {

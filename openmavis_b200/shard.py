@@ -55,3 +55,29 @@ def gather_results(idx_local, dist_local, n_total, dist):
     dist.all_gather(parts, buf)
     out = torch.cat([p[:c] for p, c in zip(parts, counts)]).numpy()
     return out[:, :2].copy(), out[:, 2:].copy()
+
+
+def bind_to_gpu_numa(pci_bus_id):
+    """Pin this process (one per GPU) to the CPU cores of the NUMA node its GPU hangs off, so that the pinned staging buffers it
+    allocates afterwards are first-touched on that node and the host<->device copies do not cross the socket interconnect.
+    pci_bus_id: 'dddd:bb:dd.f' (e.g. from torch.cuda.get_device_properties(i): '%04x:%02x:%02x.0' % (pci_domain_id, pci_bus_id,
+    pci_device_id)).  Returns the node number, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        with open('/sys/bus/pci/devices/%s/numa_node' % pci_bus_id.lower()) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None

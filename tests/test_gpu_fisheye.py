@@ -87,3 +87,24 @@ def test_stereo_fisheye_matches_degenerate(M):
     with pytest.raises(ob.OrbxError):
         bad = f['kl'].copy(); bad['octave'][5] = 9
         M.ComputeStereoFishEyeMatches(rig_of(f['s']), bad, f['dl'], 0, f['kr'], f['dr'], 0, f['sigma2'], 0.7)
+
+
+def test_device_resident_chain_equals_host_call(M):
+    """Extraction -> stereo matching without the descriptors leaving the GPU (orbx_stereo_fisheye_matches_device on the rows the
+    extraction left on the device) gives exactly what the host-pointer call gives on the fetched rows."""
+    from openmavis_b200.synth import synth_image
+    w = h = 512
+    rig_x = ob.RigExtractor(w, h, 2, 1500)
+    left = synth_image(w, h, 7100)
+    xs = np.arange(w)
+    right = left[:, np.clip(xs + (9 + 6 * np.sin(xs / 70.0)).astype(np.int64), 0, w - 1)].copy()
+    res = rig_x.extract([left, right], ob.make_params(2, 1500, 20, 7, (0, w - 1)))       # lapping area = the whole image
+    (ml, kl, dl), (mr, kr, dr) = res[0][:3], res[1][:3]
+    s = synth_fisheye_pairs(4, 3)
+    rig = ob.kb8_stereo(s['cam1'], s['cam1'], np.eye(3, dtype=np.float32), np.array([0.1, 0, 0], np.float32))
+    g_dev = rig_x.compute_stereo_fisheye_matches(M, rig, 0, 1, (kl.size, ml), (kr.size, mr), ratio=0.8)
+    g_host = M.ComputeStereoFishEyeMatches(rig, kl, dl, ml, kr, dr, mr, rig_x.sigma2, 0.8)
+    assert g_dev['descMatches'] == g_host['descMatches'] > 100
+    for k in ('mvLeftToRightMatch', 'mvRightToLeftMatch', 'mvDepth', 'mvStereo3Dpoints'):
+        assert np.array_equal(g_dev[k], g_host[k]), k
+    assert g_dev['nMatches'] == g_host['nMatches']
