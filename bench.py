@@ -166,6 +166,38 @@ def guided_matchers(ob, device):
     ms = timed(sbp)
     out['search_by_projection'] = {'map_points': nmp, 'cameras': ncam, 'keypoints': int(cam_off[-1]), 'matches': int(nm[0]), 'ms_per_call': ms,
                                    'device_ms': m.last_ms(), 'map_points_per_s': nmp / (ms * 1e-3)}
+    # ---- SearchByProjection(CurrentFrame, LastFrame) (src/ORBmatcher.cc:1985-2413): the per-frame tracking matcher
+    nlast = cam_off[-1]
+    lsrc = rng.integers(0, nlast, nlast)
+    lpx = np.zeros((nlast, 4), np.float32); lpy = np.zeros((nlast, 4), np.float32)
+    for c in range(ncam):
+        pick = np.where((lsrc >= cam_off[c]) & (lsrc < cam_off[c + 1]), lsrc, rng.integers(cam_off[c], cam_off[c + 1], nlast))
+        lpx[:, c] = kps['x'][pick] + rng.uniform(-4, 4, nlast); lpy[:, c] = kps['y'][pick] + rng.uniform(-4, 4, nlast)
+    last = dict(valid=np.ones(nlast, np.uint8), proj_x=lpx, proj_y=lpy, octave=kps['octave'][lsrc].astype(np.int32),
+                angle=((kps['angle'][lsrc] + 10) % 360).astype(np.float32),
+                desc=desc[lsrc] ^ np.packbits(rng.random((nlast, 256)) < 0.05, axis=1, bitorder='little'))
+
+    def sbp_last():
+        nm[0] = m.SearchByProjectionLast(frame, last, 7.0)[0]
+    ms = timed(sbp_last)
+    out['search_by_projection_last_frame'] = {'points': int(nlast), 'cameras': ncam, 'matches': int(nm[0]), 'ms_per_call': ms,
+                                              'device_ms': m.last_ms(), 'points_per_s': nlast / (ms * 1e-3)}
+    # ---- SearchByBoW(KeyFrame, Frame) (src/ORBmatcher.cc:349-666): 64 shared vocabulary nodes
+    def fvec(d):
+        node = d[:, 0].astype(np.int32) & 63
+        order = np.argsort(node, kind='stable')
+        nodes, counts = np.unique(node, return_counts=True)
+        return nodes.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), order.astype(np.int32)
+    flips = np.packbits(rng.random((nlast, 256)) < 0.04, axis=1, bitorder='little'); flips[:, 0] &= 0xC0
+    dkf = desc[lsrc] ^ flips
+    akf = ((kps['angle'][lsrc] + 25) % 360).astype(np.float32)
+    fv_kf, fv_f = fvec(dkf), fvec(desc)
+
+    def bow():
+        nm[0] = m.SearchByBoW(fv_kf, fv_f, dkf, desc, None, akf, kps['angle'], cam_off)[0]
+    ms = timed(bow)
+    out['search_by_bow'] = {'keyframe_features': int(nlast), 'frame_features': int(nlast), 'matches': int(nm[0]), 'ms_per_call': ms,
+                            'device_ms': m.last_ms()}
     # ---- ComputeStereoMatches (src/Frame.cc:1057-1219)
     left = synth_image(752, 480, 2001)
     xs = np.arange(752)
