@@ -148,18 +148,36 @@ __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ py
                 *reinterpret_cast<uint4 *>(s_src + r * src_pitch + 16 * c) = __ldg(reinterpret_cast<const uint4 *>(src + (long long)r * S.pitch + 16 * c));
     }
     __syncthreads();
-    {   // phase H: thread = one output column, rows strided by 4:  r[sy][d] >> 4
-        const int c = tid & (kRszTW - 1), rg = tid >> 6;
-        if (c < ow) {
-            const ResizeTap t = tapx[c];
-            const uint8_t *sr = s_src + rg * src_pitch + (t.s0 - sx_al);
-            const int d1 = t.s1 - t.s0, a0 = t.a0, a1 = t.a1;
-            uint32_t *hp = s_h + rg * kRszTW + c;
-            const int step = (kRszThreads / kRszTW) * src_pitch;
+    {   // phase H: thread = two adjacent output columns, rows strided by 8:  r[sy][d] >> 4.  Both columns' taps lie within 8 staged
+        // bytes from the word that holds the first one (scale factors up to 3): two 32-bit loads per row, the byte pairs are
+        // funnel-shifted into place and each column is ONE IDP.2A with its (a0, a1) coefficient pair.
+        const int c2 = 2 * (tid & 31), rg = tid >> 5;
+        if (c2 < ow) {
+            const ResizeTap t0 = tapx[c2], t1 = tapx[min(c2 + 1, ow - 1)];
+            const int o0 = (t0.s0 - sx_al) & 3, o1 = t1.s0 - ((t0.s0 - sx_al) & ~3) - sx_al;      // byte offsets from the first word
+            const uint32_t k0 = (uint32_t)(unsigned short)t0.a0 | ((uint32_t)(unsigned short)t0.a1 << 16);
+            const uint32_t k1 = (uint32_t)(unsigned short)t1.a0 | ((uint32_t)(unsigned short)t1.a1 << 16);
+            uint32_t *hp = s_h + rg * kRszTW + c2;
+            constexpr int kRows = kRszThreads / 32;
+            if (o1 <= 6) {
+                const uint8_t *sr = s_src + rg * src_pitch + ((t0.s0 - sx_al) & ~3);
+                const int sh0 = 8 * o0, sh1a = min(8 * o1, 32), sh1b = max(8 * o1 - 32, 0);
+                const int step = kRows * src_pitch;
 #pragma unroll 4
-            for (int r = rg; r < nrow; r += kRszThreads / kRszTW) {
-                *hp = (uint32_t)(((int)sr[0] * a0 + (int)sr[d1] * a1) >> 4);
-                sr += step; hp += (kRszThreads / kRszTW) * kRszTW;
+                for (int r = rg; r < nrow; r += kRows) {
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(sr), w1 = *reinterpret_cast<const uint32_t *>(sr + 4);
+                    const uint32_t p0 = __funnelshift_r(w0, w1, sh0), p1 = __funnelshift_rc(w0, w1, sh1a) >> sh1b;
+                    *reinterpret_cast<uint2 *>(hp) = make_uint2(__dp2a_lo(k0, p0, 0u) >> 4, __dp2a_lo(k1, p1, 0u) >> 4);
+                    sr += step; hp += kRows * kRszTW;
+                }
+            } else {   // wider tap spacing: byte loads
+                const uint8_t *sa = s_src + rg * src_pitch + (t0.s0 - sx_al), *sb = s_src + rg * src_pitch + (t1.s0 - sx_al);
+                const int da = t0.s1 - t0.s0, db = t1.s1 - t1.s0;
+                for (int r = rg; r < nrow; r += kRows) {
+                    hp[0] = (uint32_t)(((int)sa[0] * t0.a0 + (int)sa[da] * t0.a1) >> 4);
+                    hp[1] = (uint32_t)(((int)sb[0] * t1.a0 + (int)sb[db] * t1.a1) >> 4);
+                    sa += kRows * src_pitch; sb += kRows * src_pitch; hp += kRows * kRszTW;
+                }
             }
         }
     }
