@@ -298,34 +298,42 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
     const uint8_t *sp = s_src + (wid * kBlurStrip) * kBlurSP + 12 + 4 * lane;
     uint8_t *dst = plane_ptr(blur, L, b) + (long long)(kYO + ys) * L.pitch + kXO + xb;
     const int nrows = min(kBlurStrip, L.h - ys);       // output rows of the strip
-    uint32_t hw[7][4];
+    // register window: the horizontal sums (<= 65280, 16 bits) of the last rows, packed in pairs  pr[j] = h[row - 1] | h[row] << 16,
+    // so that the vertical pass is 3 IDP.2A (two taps each) + 1 multiply-add per pixel
+    uint32_t pr[6][4], hprev[4];
 #pragma unroll
-    for (int j = 0; j < 7; j++)
+    for (int k = 0; k < 4; k++) {
+        hprev[k] = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) hw[j][k] = 0;
+        for (int j = 0; j < 6; j++) pr[j][k] = 0;
+    }
     // Fully unrolled with no control flow around the register window (rows below the strip compute on stale shared memory
-    // and are simply not stored), so the 7-row window is pure register renaming.
+    // and are simply not stored), so the window is pure register renaming.
 #pragma unroll
     for (int r = 0; r < kBlurStrip + 6; r++) {
         const uint32_t wl = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP);
         const uint32_t wc = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 4);
         const uint32_t wr = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 8);
-#pragma unroll
-        for (int j = 0; j < 6; j++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) hw[j][k] = hw[j + 1][k];
+        uint32_t h[4];
         // pixel k needs bytes k+1 .. k+7 of the 12-byte window (wl, wc, wr)
-        hw[6][0] = __dp4a(__funnelshift_r(wl, wc, 8), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 8), 0x00122230u, 0u));
-        hw[6][1] = __dp4a(__funnelshift_r(wl, wc, 16), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 16), 0x00122230u, 0u));
-        hw[6][2] = __dp4a(__funnelshift_r(wl, wc, 24), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 24), 0x00122230u, 0u));
-        hw[6][3] = __dp4a(wc, 0x38302212u, __dp4a(wr, 0x00122230u, 0u));
+        h[0] = __dp4a(__funnelshift_r(wl, wc, 8), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 8), 0x00122230u, 0u));
+        h[1] = __dp4a(__funnelshift_r(wl, wc, 16), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 16), 0x00122230u, 0u));
+        h[2] = __dp4a(__funnelshift_r(wl, wc, 24), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 24), 0x00122230u, 0u));
+        h[3] = __dp4a(wc, 0x38302212u, __dp4a(wr, 0x00122230u, 0u));
         if (r >= 6) {
             uint32_t v[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                v[k] = 18u * (hw[0][k] + hw[6][k]) + 34u * (hw[1][k] + hw[5][k]) + 48u * (hw[2][k] + hw[4][k]) + 56u * hw[3][k] + 32768u;
+            for (int k = 0; k < 4; k++)   // rows r-6 .. r with weights 18 34 48 56 48 34 18: pairs (r-6, r-5), (r-4, r-3), (r-2, r-1), and row r
+                v[k] = __dp2a_lo(pr[1][k], 0x2212u, __dp2a_lo(pr[3][k], 0x3830u, __dp2a_lo(pr[5][k], 0x2230u, 18u * h[k] + 32768u)));
             const uint32_t lo = __byte_perm(v[0], v[1], 0x0062), hi = __byte_perm(v[2], v[3], 0x0062);
             if (r - 6 < nrows) *reinterpret_cast<uint32_t *>(dst + (long long)(r - 6) * L.pitch) = __byte_perm(lo, hi, 0x5410);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {   // pr[j] holds the pair that ends at row r - 5 + j
+#pragma unroll
+            for (int j = 0; j < 5; j++) pr[j][k] = pr[j + 1][k];
+            pr[5][k] = hprev[k] | (h[k] << 16);
+            hprev[k] = h[k];
         }
     }
 }
