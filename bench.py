@@ -413,6 +413,16 @@ def main():
         rig.extract_host_raw(ptrs, strides, params, kps_np, desc_np, nkp_np, nmono_np, n_img)
     barrier()
     ms_sync_call = max_over_ranks((time.perf_counter() - t0) * 1e3) / 5
+    # latency of ONE rig frame (5 images) through the same synchronous host-buffer call: what a live tracker sees per frame
+    one = (C.c_void_p * NCAM)(*[ptrs[i] for i in range(NCAM)])
+    for _ in range(5):
+        rig.extract_host_raw(one, strides, params, kps_np, desc_np, nkp_np, nmono_np, NCAM)
+    lat = []
+    for _ in range(40):
+        t0 = time.perf_counter()
+        rig.extract_host_raw(one, strides, params, kps_np, desc_np, nkp_np, nmono_np, NCAM)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    ms_one_frame = float(np.median(lat))
     rig.set_stream(stream.cuda_stream)
     h2d = n_img * W * H + n_img * (20 + 32)
     d2h = n_img * cap * (28 + 32) + 2 * 4 * n_img
@@ -547,7 +557,8 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'rig-frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps, 'timing': 'host wall clock between barrier + synchronize',
                     'pipeline': 'two handles alternating (orbx_extract_batch_submit / orbx_extract_wait)',
-                    'sync_call_ms_per_step': ms_sync_call, 'sync_call_value': world * frames / (ms_sync_call * 1e-3)},
+                    'sync_call_ms_per_step': ms_sync_call, 'sync_call_value': world * frames / (ms_sync_call * 1e-3),
+                    'one_rig_frame_latency_ms': ms_one_frame},
             'gpu_launches': launches_per_step * args.steps,
             'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'matching': matching,
         }

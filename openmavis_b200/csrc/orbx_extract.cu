@@ -66,6 +66,7 @@ struct orbx_extractor {
     size_t fast_smem = 0, oct_smem = 0, rsz_smem = 0;
     int rsz_rows = 0, rsz_pitch = 0;
     int oct_list_cap = 0, oct_threads = 256;
+    int oct_wide_max = 148;              // (image, level) pairs up to which the quadtree runs as 1024-thread CTAs (one per SM)
     long long pyr_bytes_per_batch = 0;
     std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
 
@@ -249,6 +250,7 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
     orbx_extractor *ex = new orbx_extractor();
     ex->device = device; ex->width = width; ex->height = height; ex->max_images = max_images;
     ex->max_nfeatures = max_nfeatures; ex->nlevels = nlevels; ex->scale_factor = scale_factor;
+    if (const char *t = getenv("ORBX_OCT_WIDE")) ex->oct_wide_max = atoi(t);   // tuning knob
     if (const char *t = getenv("ORBX_OCT_THREADS")) ex->oct_threads = std::max(32, std::min(256, atoi(t) & ~31));   // tuning knob
     int st = build_geometry(ex, fma_mode ? 1 : 0);
     if (st != ORBX_OK) { delete ex; return st; }
@@ -357,7 +359,10 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
     if (ex->fast_smem > 48 * 1024)
         EX_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fast_smem));
     if (ex->oct_smem > 48 * 1024)
+    {
         EX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->oct_smem));
+        EX_CUDA(cudaFuncSetAttribute(k_octree_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->oct_smem));
+    }
     {   // TMA tensor maps of the pyramid levels for the blur tiles (driver entry point through the runtime: no -lcuda)
         memset(&ex->blur_maps, 0, sizeof(ex->blur_maps));
         typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -500,9 +505,14 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
         ORBX_CUDA(cudaEventRecord(ex->ev_blur[lane], sB));
     }
     if (ev) ORBX_CUDA(cudaEventRecord(ev[3], sA));
-    k_octree<<<dim3(cnt, nl), ex->oct_threads, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
-                                                                   ex->d_lin_n, ex->d_node, ex->d_slot, ex->d_lvl_kp, ex->d_lvl_n,
-                                                                   ex->oct_list_cap, i0);
+    if (cnt * nl <= ex->oct_wide_max)   // few (image, level) pairs: one wide CTA each (latency), else the throughput shape
+        k_octree_wide<<<dim3(cnt, nl), 1024, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
+                                                                 ex->d_lin_n, ex->d_node, ex->d_slot, ex->d_lvl_kp, ex->d_lvl_n,
+                                                                 ex->oct_list_cap, i0);
+    else
+        k_octree<<<dim3(cnt, nl), ex->oct_threads, ex->oct_smem, sA>>>(G, ex->d_nfeat, ex->d_cells, ex->d_cell_cnt, ex->d_cell_off, ex->d_lin,
+                                                                       ex->d_lin_n, ex->d_node, ex->d_slot, ex->d_lvl_kp, ex->d_lvl_n,
+                                                                       ex->oct_list_cap, i0);
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[4], sA));
     k_slots<<<cnt, 256, 0, sA>>>(G, ex->d_params, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot, ex->d_n_kp, ex->d_n_mono, i0);

@@ -715,11 +715,11 @@ struct DevCtx {
     }
 };
 
-__global__ void __launch_bounds__(256, 6) k_octree(Geom G, const int *__restrict__ nfeat_lvl, const uint32_t *__restrict__ cells,
-                                                const int *__restrict__ cell_cnt, int *__restrict__ cell_off,
-                                                uint32_t *__restrict__ lin, int *__restrict__ lin_n,
-                                                unsigned short *__restrict__ node, int *__restrict__ sel_tmp,
-                                                uint32_t *__restrict__ lvl_kp, int *__restrict__ lvl_n, int list_cap, int img0) {
+__device__ __forceinline__ void octree_body(const Geom &G, const int *__restrict__ nfeat_lvl, const uint32_t *__restrict__ cells,
+                                            const int *__restrict__ cell_cnt, int *__restrict__ cell_off,
+                                            uint32_t *__restrict__ lin, int *__restrict__ lin_n,
+                                            unsigned short *__restrict__ node, int *__restrict__ sel_tmp,
+                                            uint32_t *__restrict__ lvl_kp, int *__restrict__ lvl_n, int list_cap, int img0) {
     extern __shared__ __align__(16) unsigned char oct_smem[];
     __shared__ int s_total;
     // grid = (images, levels): CTAs are dispatched level 0 first — the levels with the most candidates and the longest
@@ -758,6 +758,24 @@ __global__ void __launch_bounds__(256, 6) k_octree(Geom G, const int *__restrict
         kp[p] = cand_pack(cand_x(c) + kFastBorder, cand_y(c) + kFastBorder, cand_score(c));
     }
     if (cx.tid == 0) { lvl_n[b * G.nlevels + lvl] = k; lin_n[b * G.nlevels + lvl] = n; }
+}
+
+// throughput shape: 256 threads, 6 CTAs per SM (large batches keep every SM busy with independent (image, level) pairs)
+__global__ void __launch_bounds__(256, 6) k_octree(Geom G, const int *__restrict__ nfeat_lvl, const uint32_t *__restrict__ cells,
+                                                const int *__restrict__ cell_cnt, int *__restrict__ cell_off,
+                                                uint32_t *__restrict__ lin, int *__restrict__ lin_n,
+                                                unsigned short *__restrict__ node, int *__restrict__ sel_tmp,
+                                                uint32_t *__restrict__ lvl_kp, int *__restrict__ lvl_n, int list_cap, int img0) {
+    octree_body(G, nfeat_lvl, cells, cell_cnt, cell_off, lin, lin_n, node, sel_tmp, lvl_kp, lvl_n, list_cap, img0);
+}
+// latency shape: 1024 threads per (image, level) for batches that leave most SMs idle (one rig frame): the candidate sweeps of
+// the long level-0 chain get four times the threads
+__global__ void __launch_bounds__(1024, 1) k_octree_wide(Geom G, const int *__restrict__ nfeat_lvl, const uint32_t *__restrict__ cells,
+                                                      const int *__restrict__ cell_cnt, int *__restrict__ cell_off,
+                                                      uint32_t *__restrict__ lin, int *__restrict__ lin_n,
+                                                      unsigned short *__restrict__ node, int *__restrict__ sel_tmp,
+                                                      uint32_t *__restrict__ lvl_kp, int *__restrict__ lvl_n, int list_cap, int img0) {
+    octree_body(G, nfeat_lvl, cells, cell_cnt, cell_off, lin, lin_n, node, sel_tmp, lvl_kp, lvl_n, list_cap, img0);
 }
 
 // ------------------------------------------------------------------------------------------------------
