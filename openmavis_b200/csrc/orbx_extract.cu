@@ -5,7 +5,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/orbx_pattern.h"
@@ -66,6 +68,11 @@ struct orbx_extractor {
     size_t fast_smem = 0, oct_smem = 0, rsz_smem = 0;
     int rsz_rows = 0, rsz_pitch = 0;
     int oct_list_cap = 0, oct_threads = 256;
+    // small chunks (one rig frame) are launch-bound: their ~15 launches and the two-stream fork / join are captured once per
+    // (lane, first image, count, pixels) into a CUDA graph and replayed with one launch
+    struct ChunkGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
+    std::map<std::tuple<int, int, int, const void *>, ChunkGraph> graphs;
+    bool use_graphs = true;
     int oct_wide_max = 148;              // (image, level) pairs up to which the quadtree runs as 1024-thread CTAs (one per SM)
     long long pyr_bytes_per_batch = 0;
     std::vector<float> sf, inv_sf, sigma2, inv_sigma2;
@@ -218,6 +225,7 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_params) cudaFreeHost(ex->h_params);
     if (ex->h_nfeat) cudaFreeHost(ex->h_nfeat);
+    for (auto &g : ex->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (auto &r : ex->ev) for (auto &e : r) if (e) cudaEventDestroy(e);
     if (ex->ev_staging) cudaEventDestroy(ex->ev_staging);
     for (int i = 0; i < orbx_extractor::kLanes; i++) {
@@ -251,6 +259,7 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
     ex->device = device; ex->width = width; ex->height = height; ex->max_images = max_images;
     ex->max_nfeatures = max_nfeatures; ex->nlevels = nlevels; ex->scale_factor = scale_factor;
     if (const char *t = getenv("ORBX_OCT_WIDE")) ex->oct_wide_max = atoi(t);   // tuning knob
+    if (const char *t = getenv("ORBX_NO_GRAPH")) ex->use_graphs = atoi(t) == 0;
     if (const char *t = getenv("ORBX_OCT_THREADS")) ex->oct_threads = std::max(32, std::min(256, atoi(t) & ~31));   // tuning knob
     int st = build_geometry(ex, fma_mode ? 1 : 0);
     if (st != ORBX_OK) { delete ex; return st; }
@@ -535,6 +544,44 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
     return ORBX_OK;
 }
 
+// enqueue_chunk through a cached CUDA graph for chunks that leave most of the GPU idle (their launches, not their kernels, set the
+// pace).  Everything a launch captures by value is constant for the handle (geometry, arenas, tensor maps) or part of the key.
+static int enqueue_chunk_graphed(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_img, cudaStream_t sA, cudaStream_t sB, int lane) {
+    if (!ex->use_graphs || sA == sB || cnt * ex->nlevels > ex->oct_wide_max) return enqueue_chunk(ex, i0, cnt, d_img, sA, sB, lane, nullptr);
+    if (ex->graphs.size() >= 64 && !ex->graphs.count(std::make_tuple(lane, i0, cnt, (const void *)d_img))) {   // callers that keep changing buffers
+        for (auto &g : ex->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        ex->graphs.clear();
+    }
+    orbx_extractor::ChunkGraph &cg = ex->graphs[std::make_tuple(lane, i0, cnt, (const void *)d_img)];
+    if (!cg.exec) {
+        const int before = ex->last_launches;
+        cudaGraph_t graph = nullptr;
+        ORBX_CUDA(cudaStreamBeginCapture(sA, cudaStreamCaptureModeThreadLocal));
+        const int st = enqueue_chunk(ex, i0, cnt, d_img, sA, sB, lane, nullptr);
+        const cudaError_t ce = cudaStreamEndCapture(sA, &graph);
+        cg.launches = ex->last_launches - before;
+        ex->last_launches = before;
+        if (st != ORBX_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ex->graphs.erase(std::make_tuple(lane, i0, cnt, (const void *)d_img));
+            ex->use_graphs = false;                                  // fall back to plain launches for this handle
+            return enqueue_chunk(ex, i0, cnt, d_img, sA, sB, lane, nullptr);
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&cg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            cudaGetLastError();
+            ex->graphs.erase(std::make_tuple(lane, i0, cnt, (const void *)d_img));
+            ex->use_graphs = false;
+            return enqueue_chunk(ex, i0, cnt, d_img, sA, sB, lane, nullptr);
+        }
+    }
+    ORBX_CUDA(cudaGraphLaunch(cg.exec, sA));
+    ex->last_launches += cg.launches;
+    return ORBX_OK;
+}
+
 static int images_per_chunk(const orbx_extractor *ex, int n, bool host_io) {
     if (ex->chunk_images > 0) return std::min(n, ex->chunk_images);
     if (n <= 16) return n;
@@ -652,7 +699,7 @@ static int run_batch(orbx_extractor *ex, int n, const uint8_t *d_images, const u
             ORBX_CUDA(cudaEventRecord(ex->ev_in[k], ex->s_h2d));
             ORBX_CUDA(cudaStreamWaitEvent(sA, ex->ev_in[k], 0));
         }
-        if ((st = enqueue_chunk(ex, i0, cnt, (host_io ? ex->d_in : d_images) + i0 * img_bytes, sA, sB, lane, nullptr)) != ORBX_OK) return st;
+        if ((st = enqueue_chunk_graphed(ex, i0, cnt, (host_io ? ex->d_in : d_images) + i0 * img_bytes, sA, sB, lane)) != ORBX_OK) return st;
         if (host_io) {
             ORBX_CUDA(cudaEventRecord(ex->ev_out[k], sA));
             ORBX_CUDA(cudaStreamWaitEvent(ex->s_d2h, ex->ev_out[k], 0));
