@@ -293,3 +293,41 @@ def test_staging_fallback_paths_without_tma(monkeypatch):
     b = rig.extract([img], p)[0]
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     compare_image(rig, 0, img, 1500, 20, 7, (0, 720), b)
+
+
+def test_concurrent_extractor_threads_reference_usage():
+    """The reference calls operator() from 2-4 std::threads, one per extractor instance (src/Frame.cc:1841-1862): four handles,
+    four host threads, repeated small calls (the cached CUDA-graph path with thread-local capture) - every result must equal the
+    result of the same call made alone."""
+    import threading
+    _need_gpu()
+    w, h, nf = 720, 540, 1500
+    imgs = [synth_image(w, h, 3300 + c) for c in range(4)]
+    params = ob.make_params(1, nf, 20, 7, (0, 0))
+    alone = []
+    for c in range(4):
+        rig = ob.RigExtractor(w, h, 1, nf)
+        alone.append(rig.extract([imgs[c]], params)[0])
+    rigs = [ob.RigExtractor(w, h, 1, nf) for _ in range(4)]
+    out = [[None] * 6 for _ in range(4)]
+    errors = []
+
+    def worker(c):
+        try:
+            for it in range(6):
+                out[c][it] = rigs[c].extract([imgs[(c + it) % 4]], params)[0]
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+    ts = [threading.Thread(target=worker, args=(c,)) for c in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for c in range(4):
+        for it in range(6):
+            mono, kps, desc = out[c][it]
+            rmono, rkps, rdesc = alone[(c + it) % 4]
+            assert mono == rmono and np.array_equal(desc, rdesc)
+            for f in KPF:
+                assert np.array_equal(kps[f].view(np.uint32), rkps[f].view(np.uint32)), f
