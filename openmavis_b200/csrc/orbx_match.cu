@@ -779,8 +779,11 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     SbpResult R;
     sbp_result_ptrs(m->b[23].as<uint8_t>(), nmp, N, &R);
     M_CUDA(cudaMemcpyAsync(assigned, R.assigned, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    M_CUDA(cudaMemcpyAsync(nmatches, R.nmatches, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    int nm_st[2] = {0, 0};
+    M_CUDA(cudaMemcpyAsync(nm_st, R.nmatches, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaStreamSynchronize(m->stream));
+    *nmatches = nm_st[0];
+    if (nm_st[1] != 0) return fail(ORBX_ERR_CUDA, "ordered resolver did not converge (internal error)");
     return ORBX_OK;
 }
 
@@ -853,8 +856,11 @@ int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off
     SbpResult R;
     sbp_result_ptrs(m->b[23].as<uint8_t>(), npts, N, &R);
     M_CUDA(cudaMemcpyAsync(assigned, R.assigned, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    M_CUDA(cudaMemcpyAsync(nmatches, R.nmatches, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    int nm_st[2] = {0, 0};
+    M_CUDA(cudaMemcpyAsync(nm_st, R.nmatches, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaStreamSynchronize(m->stream));
+    *nmatches = nm_st[0];
+    if (nm_st[1] != 0) return fail(ORBX_ERR_CUDA, "ordered resolver did not converge (internal error)");
     return ORBX_OK;
 }
 
@@ -919,8 +925,11 @@ int orbx_search_for_initialization(orbx_matcher *m, const orbx_kp *kps1, const u
     SbpResult R;
     sbp_result_ptrs(m->b[23].as<uint8_t>(), n1, n2, &R);
     M_CUDA(cudaMemcpyAsync(matches12, R.match12, (size_t)n1 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    M_CUDA(cudaMemcpyAsync(nmatches, R.nmatches, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    int nm_st[2] = {0, 0};
+    M_CUDA(cudaMemcpyAsync(nm_st, R.nmatches, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaStreamSynchronize(m->stream));
+    *nmatches = nm_st[0];
+    if (nm_st[1] != 0) return fail(ORBX_ERR_CUDA, "ordered resolver did not converge (internal error)");
     for (int i = 0; i < n1; i++)                                    // update prev matched (:992-995)
         if (matches12[i] >= 0) { prev_matched[2 * i] = kps2[matches12[i]].x; prev_matched[2 * i + 1] = kps2[matches12[i]].y; }
     return ORBX_OK;

@@ -181,12 +181,12 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
     }
     if (P.mode == 2)
         for (int u = threadIdx.x; u < nmp; u += blockDim.x) W.match12[u] = -1;
-    if (threadIdx.x == 0) W.nmatches[0] = 0;
+    if (threadIdx.x == 0) { W.nmatches[0] = 0; W.nmatches[1] = 0; }
     if (P.mode >= 1)
         for (int e = threadIdx.x; e < 4 * nmp; e += blockDim.x) W.events[e] = -1;
     // a thread's current point stays the same for many rounds: its touch set (keypoints it may read or write) is cached in shared memory
     __shared__ unsigned short s_touch[kSbpTouchCap][1024];
-    int mine = threadIdx.x, nm_total = 0, loaded = -1, nt = 0;
+    int mine = threadIdx.x, nm_total = 0, loaded = -1, nt = 0, done = 0;
     for (unsigned round = 1;; round++) {
         if (threadIdx.x == 0) s_lo = 0x7FFFFFFF;
         __syncthreads();                                              // (also orders the previous round's claims before this round's reads)
@@ -200,15 +200,60 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
         __syncthreads();
         const int lo = s_lo;
         if (lo == 0x7FFFFFFF) break;
+        if (round > 4u * (unsigned)nmp + 16u) {   // every round resolves at least one (point, camera): more rounds = an internal error
+            if (threadIdx.x == 0) W.nmatches[1] = -1;
+            break;
+        }
         const bool active = mine < nmp && mine < lo + (int)blockDim.x;
         const int u = mine;
         const unsigned long long key = ((unsigned long long)round << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)u);
         if (active) {
-            if (nt <= kSbpTouchCap) for (int j = 0; j < nt; j++) atomicMax(&tmin[s_touch[j][threadIdx.x]], key);
-            else sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, [&](int g) { atomicMax(&tmin[g], key); });
+            // (mode 1: the cameras of a point are independent claim processes; a camera that is done no longer holds its keypoints back)
+            auto stamp = [&](int g) {
+                if (P.mode == 1) {
+                    int c = 0;
+                    for (int k = 1; k < F.ncam; k++) c += g >= F.cam_off[k];
+                    if ((done >> c) & 1) return;
+                }
+                atomicMax(&tmin[g], key);
+            };
+            if (nt <= kSbpTouchCap) for (int j = 0; j < nt; j++) stamp(s_touch[j][threadIdx.x]);
+            else sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, stamp);
         }
         __syncthreads();
-        if (active) {
+        if (active && P.mode == 1) {
+            // Frame-to-frame matcher: a camera's decision depends only on its best unoccupied candidate — better ones are occupied for
+            // good (occupancy only grows in this mode), worse ones do not matter — so the point may claim it as soon as it is the
+            // smallest unresolved point that has this ONE keypoint in a list, instead of waiting for all its candidates.
+            bool all_done = true;
+            int nm = 0;
+            for (int c = 0; c < 4; c++) {
+                if ((done >> c) & 1) continue;
+                const int q = u * 4 + c;
+                const int b = W.q_ptr[q], e = W.q_ptr[q + 1];
+                int bestDist = 256, bestIdx = -1;
+                for (int k = b; k < e; k++) {
+                    const uint32_t r = cand[k];
+                    const int idx = (int)(r & 0xFFFF), dist = (int)((r >> 16) & 0x1FF);
+                    if (__ldcg(&W.occ[idx + F.cam_off[c]])) continue;
+                    if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+                }
+                if (bestDist > P.max_dist) { done |= 1 << c; continue; }          // nothing (left) to claim: final, occupancy only grows
+                const int g = bestIdx + F.cam_off[c];
+                if (__ldcg(&tmin[g]) != key) { all_done = false; continue; }     // an earlier point may still take it
+                W.assigned[g] = u; W.occ[g] = P.has_obs[u]; nm++;                 // TH_HIGH (:2103), ORBdist (:2487), TH_LOW * ratioHamming (:767)
+                if (P.check_ori) {   // :2121-2128
+                    float rot = __fsub_rn(P.angle[u], F.kps[g].angle);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30.0f));
+                    if (bin == 30) bin = 0;
+                    W.events[q] = g | (bin << 16);
+                }
+                done |= 1 << c;
+            }
+            nm_total += nm;
+            if (all_done) { mine += blockDim.x; done = 0; }
+        } else if (active) {
             bool fin = true;
             if (nt <= kSbpTouchCap) { for (int j = 0; j < nt; j++) if (__ldcg(&tmin[s_touch[j][threadIdx.x]]) != key) fin = false; }   // (L2: the atomics do not update this SM's L1)
             else sbp_for_touch(F, P.mode == 0, W.q_ptr, cand, u, [&](int g) { if (__ldcg(&tmin[g]) != key) fin = false; });
