@@ -716,3 +716,104 @@ def test_vocabulary_transform(M, k, L, irregular):
     assert np.array_equal(ids, bi[:nb]) and np.array_equal(vals.view(np.uint64), bv[:nb].view(np.uint64))
     assert np.array_equal(nodes, fn[:nfn.value]) and np.array_equal(ptr, fp[:nfn.value + 1]) and np.array_equal(idx, fi[:fp[nfn.value]])
     assert nb >= 3
+
+
+def _random_frame(rng, ncam, n_per_cam, size=200.0, pool=6):
+    """Keypoints without an extraction: random positions / octaves, descriptors from a tiny pool with a few flipped bits (many
+    equal distances, dense windows, long claim chains)."""
+    ns = [int(rng.integers(max(1, n_per_cam // 2), n_per_cam + 1)) for _ in range(ncam)]
+    cam_off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    N = int(cam_off[-1])
+    kps = np.zeros(N, ob.KP_DTYPE)
+    kps['x'] = rng.uniform(0, size, N); kps['y'] = rng.uniform(0, size, N)
+    kps['octave'] = rng.integers(0, 8, N); kps['angle'] = rng.uniform(0, 360, N); kps['size'] = 31; kps['class_id'] = -1
+    base = synth_descriptors(pool, int(rng.integers(1 << 30)))
+    desc = base[rng.integers(0, pool, N)] ^ np.packbits(rng.random((N, 256)) < 0.03, axis=1, bitorder='little')
+    sf = np.array([np.float32(1.2) ** l for l in range(8)], np.float32)
+    frame = dict(cam_off=cam_off, kps=kps, desc=desc, bounds=np.tile(np.array([0, size, 0, size], np.float32), (ncam, 1)), scale_factors=sf,
+                 occupied=(rng.random(N) < 0.1).astype(np.uint8))
+    return frame, base
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_ordered_resolver_stress(seed):
+    """Many small, dense, adversarial cases of the three ordered matchers (claims in point order, eviction, mirrors): every one must
+    equal the sequential oracle.  Sizes straddle the resolver's 1024-point window and its 12-entry touch cache."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    rng = np.random.default_rng(1000 + seed)
+    L = O.lib()
+    for rep in range(4):
+        ncam = int(rng.choice([1, 2, 4]))
+        frame, base = _random_frame(rng, ncam, int(rng.choice([8, 60, 400])))
+        cam_off, kps, N = frame['cam_off'], frame['kps'], int(frame['cam_off'][-1])
+        n = int(rng.choice([3, 200, 1100, 2500]))
+        tgt = rng.integers(0, N, n)
+        spread = float(rng.choice([0.5, 4.0, 15.0]))
+        px = np.zeros((n, 4), np.float32); py = np.zeros((n, 4), np.float32)
+        for c in range(ncam):
+            kk = np.where((tgt >= cam_off[c]) & (tgt < cam_off[c + 1]), tgt, rng.integers(cam_off[c], cam_off[c + 1], n))
+            px[:, c] = kps['x'][kk] + rng.uniform(-spread, spread, n); py[:, c] = kps['y'][kk] + rng.uniform(-spread, spread, n)
+        pdesc = base[rng.integers(0, base.shape[0], n)] ^ np.packbits(rng.random((n, 256)) < 0.03, axis=1, bitorder='little')
+        octv = np.clip(kps['octave'][tgt] + rng.integers(-1, 2, n), 0, 7).astype(np.int32)
+        has_obs = (rng.random(n) < float(rng.choice([0.5, 0.9, 1.0]))).astype(np.uint8)
+        # ---- mode 1: SearchByProjection(CurrentFrame, LastFrame) and its overloads
+        last = dict(valid=(rng.random(n) < 0.9).astype(np.uint8), proj_x=px, proj_y=py, octave=octv,
+                    angle=rng.uniform(0, 360, n).astype(np.float32), desc=pdesc, has_obs=has_obs)
+        th = float(rng.choice([2.0, 7.0, 15.0])); gate = int(rng.integers(0, 4)) if ncam == 1 else int(rng.integers(0, 3))
+        check = bool(rng.integers(0, 2)); md = int(rng.choice([100, 50, 20]))
+        M1 = ob.ORBmatcher(0.9, checkOri=check)
+        nm, assigned = M1.SearchByProjectionLast(frame, last, th, max_dist=md, level_gate=gate)
+        rn, rassigned = _oracle_sbp_last(frame, last, th, False, False, check, md, gate=gate)
+        assert rn == nm and np.array_equal(assigned, rassigned), ('mode 1', seed, rep, ncam, n, N, th, gate, check, md)
+    # ---- mode 0 (SearchByProjection(Frame, MapPoints) with stereo mirror tables) and mode 2 (SearchForInitialization)
+    rng = np.random.default_rng(2000 + seed)
+    for rep in range(3):
+        ncam = int(rng.choice([1, 2, 4]))
+        frame, base = _random_frame(rng, ncam, int(rng.choice([8, 60, 400])))
+        cam_off, kps, N = frame['cam_off'], frame['kps'], int(frame['cam_off'][-1])
+        n = int(rng.choice([3, 200, 1100, 2500]))
+        tgt = rng.integers(0, N, n)
+        spread = float(rng.choice([0.5, 4.0, 15.0]))
+        px = np.zeros((n, 4), np.float32); py = np.zeros((n, 4), np.float32)
+        for c in range(ncam):
+            kk = np.where((tgt >= cam_off[c]) & (tgt < cam_off[c + 1]), tgt, rng.integers(cam_off[c], cam_off[c + 1], n))
+            px[:, c] = kps['x'][kk] + rng.uniform(-spread, spread, n); py[:, c] = kps['y'][kk] + rng.uniform(-spread, spread, n)
+        pdesc = base[rng.integers(0, base.shape[0], n)] ^ np.packbits(rng.random((n, 256)) < 0.03, axis=1, bitorder='little')
+        octv = np.clip(kps['octave'][tgt] + rng.integers(-1, 2, n), 0, 7).astype(np.int32)
+        l2r = r2l = None
+        if ncam >= 2:
+            nl, nr = int(cam_off[1]), int(cam_off[2] - cam_off[1])
+            l2r = np.full(nl, -1, np.int32); r2l = np.full(nr, -1, np.int32)
+            k = min(nl, nr) // 2
+            for a, b in zip(rng.permutation(nl)[:k], rng.permutation(nr)[:k]):
+                l2r[a] = b; r2l[b] = a
+        f0 = dict(frame, l2r=l2r, r2l=r2l)
+        in_view = (rng.random((n, 4)) < 0.8).astype(np.uint8); in_view[:, ncam:] = 0
+        points = dict(in_view=in_view, proj_x=px, proj_y=py, level=np.repeat(octv[:, None], 4, 1).astype(np.int32),
+                      view_cos=rng.choice([0.9990, 0.99], (n, 4)).astype(np.float32), desc=pdesc, depth=rng.uniform(1, 80, n).astype(np.float32),
+                      bad=(rng.random(n) < 0.05).astype(np.uint8), has_obs=(rng.random(n) < float(rng.choice([0.5, 0.9, 1.0]))).astype(np.uint8))
+        nnr = float(rng.choice([0.6, 0.8, 1.0])); th = float(rng.choice([1.0, 3.0, 6.0])); far = bool(rng.integers(0, 2))
+        M0 = ob.ORBmatcher(nnr)
+        nm, assigned = M0.SearchByProjection(f0, points, th, far, 40.0)
+        rn, rassigned = _oracle_sbp(f0, points, th, np.float32(nnr), far, 40.0)
+        assert rn == nm and np.array_equal(assigned, rassigned), ('mode 0', seed, rep, ncam, n, N, th, nnr, far)
+        # ---- mode 2: SearchForInitialization on camera 0's keypoints
+        k2 = np.ascontiguousarray(kps[:cam_off[1]]); d2 = np.ascontiguousarray(frame['desc'][:cam_off[1]])
+        k2['octave'] = np.where(rng.random(k2.size) < 0.7, 0, k2['octave'])
+        n1 = min(n, 1500)
+        src = rng.integers(0, k2.size, n1)
+        k1 = k2[src].copy()
+        k1['x'] += rng.uniform(-spread, spread, n1).astype(np.float32); k1['y'] += rng.uniform(-spread, spread, n1).astype(np.float32)
+        k1['angle'] = rng.uniform(0, 360, n1).astype(np.float32)
+        d1 = np.ascontiguousarray(pdesc[:n1])
+        prev = np.ascontiguousarray(np.stack([k1['x'], k1['y']], 1).astype(np.float32)); prev_ref = prev.copy()
+        win = int(rng.choice([3, 10, 30])); check = bool(rng.integers(0, 2))
+        M2 = ob.ORBmatcher(float(rng.choice([0.7, 0.9, 1.0])), checkOri=check)
+        nm, m12 = M2.SearchForInitialization(k1, d1, k2, d2, (0, 200, 0, 200), prev, win)
+        g2 = L.orc_grid_create(O.p(k2), k2.size, C.c_float(0), C.c_float(200), C.c_float(0), C.c_float(200))
+        ref = np.zeros(n1, np.int32)
+        rn = L.orc_search_for_initialization(O.p(k1), O.p(d1), n1, C.c_void_p(g2), O.p(k2), O.p(d2), k2.size, O.p(prev_ref), win,
+                                             C.c_float(np.float32(M2.mfNNratio)), int(check), O.p(ref))
+        L.orc_grid_destroy(C.c_void_p(g2))
+        assert rn == nm and np.array_equal(ref, m12) and np.array_equal(prev, prev_ref), ('mode 2', seed, rep, n1, k2.size, win, check)
