@@ -78,3 +78,12 @@ def test_octree_on_real_fast_candidates(hc, w, h, nf):
         ref, got = _distribute_both(hc, xs, ys, sc, 16, lw - 16, 16, lh - 16, int(t['nfeat'][l]))
         assert np.array_equal(ref, got), l
         assert len(got) <= max(int(t['nfeat'][l]) + 2, 8)
+
+
+def test_numa_binding_helper_is_harmless_without_topology():
+    """openmavis_b200.shard.bind_to_gpu_numa: unknown device / unreadable sysfs -> None and the affinity is left alone."""
+    import os
+    from openmavis_b200.shard import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa('ffff:ff:1f.0') is None
+    assert os.sched_getaffinity(0) == before
