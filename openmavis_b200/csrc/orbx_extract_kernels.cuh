@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ py
 // no index arithmetic.
 // CTA tile = 128 x 128 outputs staged once in shared memory (16-byte loads); each warp owns a 128 x 32 strip and
 // MARCHES down it: a lane holds 4 adjacent columns, computes the horizontal sums of one source row with
-// 8 IDP.4A on funnel-shifted words and keeps the last 7 rows of sums in registers, so the vertical pass is
-// 3 adds + 4 multiply-adds per pixel with no intermediate buffer.  One 32-bit store per lane and row.
+// 10 IDP.4A (the taps are shifted inside the weight words) and keeps the last rows of sums in registers as packed row pairs, so
+// the vertical pass is 3 IDP.2A + 1 multiply-add per pixel with no intermediate buffer.  One 32-bit store per lane and row.
 // ------------------------------------------------------------------------------------------------------
 constexpr int kBlurTW = 128, kBlurTH = 128;
 constexpr int kBlurStrip = 32;                      // rows marched by one warp
@@ -315,10 +315,11 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
         const uint32_t wc = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 4);
         const uint32_t wr = *reinterpret_cast<const uint32_t *>(sp + r * kBlurSP + 8);
         uint32_t h[4];
-        // pixel k needs bytes k+1 .. k+7 of the 12-byte window (wl, wc, wr)
-        h[0] = __dp4a(__funnelshift_r(wl, wc, 8), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 8), 0x00122230u, 0u));
-        h[1] = __dp4a(__funnelshift_r(wl, wc, 16), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 16), 0x00122230u, 0u));
-        h[2] = __dp4a(__funnelshift_r(wl, wc, 24), 0x38302212u, __dp4a(__funnelshift_r(wc, wr, 24), 0x00122230u, 0u));
+        // pixel k needs bytes k+1 .. k+7 of the 12-byte window (wl, wc, wr): instead of shifting the pixels into place, the
+        // kernel {18,34,48,56,48,34,18} is shifted inside the weight words (10 IDP.4A, no funnel shifts)
+        h[0] = __dp4a(wl, 0x30221200u, __dp4a(wc, 0x12223038u, 0u));
+        h[1] = __dp4a(wl, 0x22120000u, __dp4a(wc, 0x22303830u, __dp4a(wr, 0x00000012u, 0u)));
+        h[2] = __dp4a(wl, 0x12000000u, __dp4a(wc, 0x30383022u, __dp4a(wr, 0x00001222u, 0u)));
         h[3] = __dp4a(wc, 0x38302212u, __dp4a(wr, 0x00122230u, 0u));
         if (r >= 6) {
             uint32_t v[4];
