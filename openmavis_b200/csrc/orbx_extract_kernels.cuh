@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
 constexpr int kFastThreads = 256;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastQueue = 320;               // per-warp survivor queue (u16 entries): < 64 left + up to 256 new
-constexpr int kFastMaxG = 8;
+constexpr int kFastMaxG = 10;
 constexpr int kFastCorners = 3072;            // dense corner list of a tile; a tile with more corners falls back to a sweep
 constexpr int kFastColBits = 9;               // queue / list entry = (img row << 9) | img column  (ip <= 512, rows < 128)
 
