@@ -1,0 +1,350 @@
+"""CPU: a second, independent restatement (plain Python, written from the reference text) of the ordered matchers, compared with the
+C++ oracle on small dense cases.  The reference holds no tests for these functions, so two independent readings
+that agree are the pin for the oracle that the GPU parity tests then use:
+  SearchByProjection(CurrentFrame, LastFrame)   src/ORBmatcher.cc:1985-2413 (+ the relocalisation / KeyFrame-Sim3 overloads)
+  SearchByBoW(KeyFrame, Frame)                  :349-666
+  SearchByBoW(KeyFrame, KeyFrame)               :1006-1129
+  SearchForInitialization                       :895-1004
+  Frame::AssignFeaturesToGrid / GetFeaturesInArea  src/Frame.cc:541-582, 890-978"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from openmavis_b200.synth import synth_descriptors
+
+f32 = np.float32
+COLS, ROWS = 64, 48
+
+
+class PyGrid:
+    def __init__(self, kps, bounds):
+        self.kps = kps
+        self.mn_x, self.mx_x, self.mn_y, self.mx_y = (f32(b) for b in bounds)
+        self.inv_w = f32(COLS) / (self.mx_x - self.mn_x); self.inv_h = f32(ROWS) / (self.mx_y - self.mn_y)
+        self.cells = [[[] for _ in range(ROWS)] for _ in range(COLS)]
+        for i in range(kps.size):                                             # AssignFeaturesToGrid + PosInGrid (round())
+            px = int(math.floor(float(f32((f32(kps['x'][i]) - self.mn_x) * self.inv_w)) + 0.5))
+            py = int(math.floor(float(f32((f32(kps['y'][i]) - self.mn_y) * self.inv_h)) + 0.5))
+            if 0 <= px < COLS and 0 <= py < ROWS:
+                self.cells[px][py].append(i)
+
+    def area(self, x, y, r, min_level, max_level):                            # GetFeaturesInArea
+        x, y, r = f32(x), f32(y), f32(r)
+        c0 = max(0, int(math.floor(float(f32(f32(f32(x - self.mn_x) - r) * self.inv_w)))))
+        if c0 >= COLS:
+            return []
+        c1 = min(COLS - 1, int(math.ceil(float(f32(f32(f32(x - self.mn_x) + r) * self.inv_w)))))
+        if c1 < 0:
+            return []
+        r0 = max(0, int(math.floor(float(f32(f32(f32(y - self.mn_y) - r) * self.inv_h)))))
+        if r0 >= ROWS:
+            return []
+        r1 = min(ROWS - 1, int(math.ceil(float(f32(f32(f32(y - self.mn_y) + r) * self.inv_h)))))
+        if r1 < 0:
+            return []
+        check = (min_level > 0) or (max_level >= 0)
+        out = []
+        for ix in range(c0, c1 + 1):
+            for iy in range(r0, r1 + 1):
+                for i in self.cells[ix][iy]:
+                    o = int(self.kps['octave'][i])
+                    if check and (o < min_level or (max_level >= 0 and o > max_level)):
+                        continue
+                    if abs(f32(self.kps['x'][i]) - x) < r and abs(f32(self.kps['y'][i]) - y) < r:
+                        out.append(i)
+        return out
+
+
+def hamming(a, b):
+    return int(np.unpackbits(a ^ b).sum())
+
+
+def rot_bin(a1, a2):
+    rot = f32(a1) - f32(a2)
+    if rot < 0.0:
+        rot = f32(rot + f32(360.0))
+    v = float(f32(rot * f32(f32(1.0) / f32(30))))
+    b = int(math.floor(v + 0.5))                                              # round(): half away from zero, v >= 0
+    return 0 if b == 30 else b
+
+
+def three_maxima_filter(hist):
+    """ComputeThreeMaxima (:2537-2573) -> set of kept bins."""
+    m1 = m2 = m3 = 0; i1 = i2 = i3 = -1
+    for i in range(30):
+        s = len(hist[i])
+        if s > m1:
+            m3, m2, m1 = m2, m1, s; i3, i2, i1 = i2, i1, i
+        elif s > m2:
+            m3, m2 = m2, s; i3, i2 = i2, i
+        elif s > m3:
+            m3 = s; i3 = i
+    if m2 < float(f32(0.1) * f32(m1)):
+        i2 = i3 = -1
+    elif m3 < float(f32(0.1) * f32(m1)):
+        i3 = -1
+    return {i1, i2, i3}
+
+
+def random_kps(rng, n, size=120.0):
+    k = np.zeros(n, O.KP_DTYPE)
+    k['x'] = rng.uniform(0, size, n); k['y'] = rng.uniform(0, size, n); k['octave'] = rng.integers(0, 4, n)
+    k['angle'] = rng.uniform(0, 360, n); k['class_id'] = -1
+    return k
+
+
+def pooled_desc(rng, n, pool):
+    return pool[rng.integers(0, pool.shape[0], n)] ^ np.packbits(rng.random((n, 256)) < 0.03, axis=1, bitorder='little')
+
+
+@pytest.mark.parametrize('seed,gate,check,max_dist', [(1, 0, True, 100), (2, 1, True, 100), (3, 2, False, 100), (4, 3, False, 40), (5, 0, True, 64)])
+def test_search_by_projection_last_frame_two_restatements(seed, gate, check, max_dist):
+    rng = np.random.default_rng(seed)
+    ncam = 1 if gate == 3 else int(rng.choice([1, 2]))
+    ns = [int(rng.integers(40, 90)) for _ in range(ncam)]
+    cam_off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    N = int(cam_off[-1])
+    kps = random_kps(rng, N); pool = synth_descriptors(5, seed)
+    desc = pooled_desc(rng, N, pool)
+    sf = np.array([f32(1.2) ** l for l in range(8)], np.float32)
+    occupied = (rng.random(N) < 0.1).astype(np.uint8)
+    n = 150
+    tgt = rng.integers(0, N, n)
+    px = np.zeros((n, 4), np.float32); py = np.zeros((n, 4), np.float32)
+    for c in range(ncam):
+        kk = np.where((tgt >= cam_off[c]) & (tgt < cam_off[c + 1]), tgt, rng.integers(cam_off[c], cam_off[c + 1], n))
+        px[:, c] = kps['x'][kk] + rng.uniform(-3, 3, n); py[:, c] = kps['y'][kk] + rng.uniform(-3, 3, n)
+    empty0 = rng.random(n) < 0.1
+    px[empty0, 0] = 5000                                                       # empty camera-0 window: the point's other cameras are skipped
+    valid = (rng.random(n) < 0.9).astype(np.uint8)
+    octv = np.clip(kps['octave'][tgt] + rng.integers(-1, 2, n), 0, 3).astype(np.int32)
+    ang = ((kps['angle'][tgt] + np.where(rng.random(n) < 0.8, 25.0, rng.uniform(0, 360, n))) % 360).astype(np.float32)
+    pdesc = pooled_desc(rng, n, pool)
+    has_obs = (rng.random(n) < 0.8).astype(np.uint8)
+    th = f32(4.0)
+    # ---- Python restatement
+    grids = [PyGrid(kps[cam_off[c]:cam_off[c + 1]], (0, 120, 0, 120)) for c in range(ncam)]
+    occ = occupied.copy(); assigned = np.full(N, -1, np.int32); hist = [[] for _ in range(30)]; nm = 0
+    for i in range(n):
+        if not valid[i]:
+            continue
+        lvl = int(octv[i]); radius = f32(th * sf[lvl])
+        for c in range(ncam):
+            ck = kps[cam_off[c]:cam_off[c + 1]]
+            if gate == 1:
+                cand = grids[c].area(px[i, c], py[i, c], radius, lvl, -1)
+            elif gate == 2:
+                cand = grids[c].area(px[i, c], py[i, c], radius, 0, lvl)
+            elif gate == 3:
+                cand = [j for j in grids[c].area(px[i, c], py[i, c], radius, -1, -1) if lvl - 1 <= ck['octave'][j] <= lvl]
+            else:
+                cand = grids[c].area(px[i, c], py[i, c], radius, lvl - 1, lvl + 1)
+            if c == 0 and not cand:
+                break
+            best, bi = 256, -1
+            for j in cand:
+                g = j + cam_off[c]
+                if occ[g]:
+                    continue
+                d = hamming(pdesc[i], desc[g])
+                if d < best:
+                    best, bi = d, j
+            if best <= max_dist:
+                g = bi + cam_off[c]
+                assigned[g] = i; occ[g] = has_obs[i]; nm += 1
+                if check:
+                    hist[rot_bin(ang[i], ck['angle'][bi])].append(g)
+    if check:
+        keep = three_maxima_filter(hist)
+        for b in range(30):
+            if b not in keep:
+                for g in hist[b]:
+                    assigned[g] = -1; nm -= 1
+    # ---- C++ oracle
+    L = O.lib()
+    cg = (C.c_void_p * 4)()
+    for c in range(ncam):
+        sub = np.ascontiguousarray(kps[cam_off[c]:cam_off[c + 1]])
+        cg[c] = L.orc_grid_create(O.p(sub), sub.size, C.c_float(0), C.c_float(120), C.c_float(0), C.c_float(120))
+    ref = np.zeros(N, np.int32)
+    rn = L.orc_search_by_projection_last(ncam, O.p(cam_off), O.p(kps), O.p(desc), cg, O.p(sf), O.p(occupied), None, n, O.p(valid), O.p(px), O.p(py),
+                                         None, O.p(octv), O.p(ang), O.p(has_obs), O.p(pdesc), C.c_float(th), gate, int(check), max_dist, O.p(ref))
+    for c in range(ncam):
+        L.orc_grid_destroy(C.c_void_p(cg[c]))
+    assert rn == nm and np.array_equal(ref, assigned)
+    assert nm > 10
+
+
+def feature_vector(desc, nbits):
+    node = desc[:, 0].astype(np.int32) & ((1 << nbits) - 1)
+    order = np.argsort(node, kind='stable')
+    nodes, counts = np.unique(node, return_counts=True)
+    return nodes.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), order.astype(np.int32)
+
+
+def bow_case(seed, n1, n2, nbits=3):
+    rng = np.random.default_rng(seed)
+    d2 = synth_descriptors(n2, seed + 1); d2[5:9] = d2[5]
+    src = rng.integers(0, n2, n1)
+    flips = np.packbits(rng.random((n1, 256)) < 0.04, axis=1, bitorder='little'); flips[:, 0] &= ~np.uint8((1 << nbits) - 1)
+    d1 = d2[src] ^ flips
+    fresh = rng.random(n1) < 0.3
+    d1[fresh] = synth_descriptors(int(fresh.sum()), seed + 2)
+    a2 = rng.uniform(0, 360, n2).astype(np.float32)
+    a1 = ((a2[src] + np.where(rng.random(n1) < 0.8, 40 + rng.uniform(-4, 4, n1), rng.uniform(0, 360, n1))) % 360).astype(np.float32)
+    fv1, fv2 = feature_vector(d1, nbits), feature_vector(d2, nbits)
+    keep = [i for i in range(len(fv1[0])) if i % 3 != 1]
+    fv1 = (fv1[0][keep].copy(), np.concatenate([[0], np.cumsum(np.diff(fv1[1])[keep])]).astype(np.int32),
+           np.concatenate([fv1[2][fv1[1][i]:fv1[1][i + 1]] for i in keep]).astype(np.int32))
+    return d1, d2, a1, a2, fv1, fv2, (rng.random(n1) < 0.2).astype(np.uint8), (rng.random(n2) < 0.15).astype(np.uint8)
+
+
+def shared_nodes(fv1, fv2):
+    pos2 = {int(v): k for k, v in enumerate(fv2[0])}
+    return [(a, pos2[int(v)]) for a, v in enumerate(fv1[0]) if int(v) in pos2]
+
+
+@pytest.mark.parametrize('seed,nnratio,check', [(11, 0.8, True), (12, 0.6, False), (13, 0.95, True)])
+def test_search_by_bow_keyframes_two_restatements(seed, nnratio, check):
+    n1, n2 = 260, 240
+    d1, d2, a1, a2, fv1, fv2, skip1, skip2 = bow_case(seed, n1, n2)
+    match = np.full(n1, -1, np.int32); matched2 = np.zeros(n2, bool); hist = [[] for _ in range(30)]; nm = 0
+    for a, b in shared_nodes(fv1, fv2):
+        for i1 in fv1[2][fv1[1][a]:fv1[1][a + 1]]:
+            if skip1[i1]:
+                continue
+            b1 = b2 = 256; bi = -1
+            for i2 in fv2[2][fv2[1][b]:fv2[1][b + 1]]:
+                if matched2[i2] or skip2[i2]:
+                    continue
+                d = hamming(d1[i1], d2[i2])
+                if d < b1:
+                    b2, b1, bi = b1, d, i2
+                elif d < b2:
+                    b2 = d
+            if b1 < 50 and f32(b1) < f32(nnratio) * f32(b2):
+                match[i1] = bi; matched2[bi] = True; nm += 1
+                if check:
+                    hist[rot_bin(a1[i1], a2[bi])].append(i1)
+    if check:
+        keep = three_maxima_filter(hist)
+        for bn in range(30):
+            if bn not in keep:
+                for i1 in hist[bn]:
+                    match[i1] = -1; nm -= 1
+    ref = np.zeros(n1, np.int32)
+    rn = O.lib().orc_search_by_bow_keyframes(len(fv1[0]), O.p(fv1[0]), O.p(fv1[1]), O.p(fv1[2]), len(fv2[0]), O.p(fv2[0]), O.p(fv2[1]), O.p(fv2[2]),
+                                             O.p(d1), n1, O.p(d2), n2, O.p(skip1), O.p(skip2), O.p(a1), O.p(a2), C.c_float(f32(nnratio)), int(check),
+                                             O.p(ref))
+    assert rn == nm and np.array_equal(ref, match) and nm > 30
+
+
+@pytest.mark.parametrize('seed,ncam,nnratio,check', [(21, 1, 0.7, True), (22, 2, 0.7, True), (23, 4, 0.9, False)])
+def test_search_by_bow_keyframe_frame_two_restatements(seed, ncam, nnratio, check):
+    n_kf, n_f = 260, 300
+    d1, d2, a1, a2, fv1, fv2, skip1, _ = bow_case(seed, n_kf, n_f)
+    cam_off = None if ncam == 1 else np.array([0, 110, 200, 260, 290][:ncam + 1], np.int32)
+    match = np.full(n_f, -1, np.int32); hist = [[] for _ in range(30)]; nm = 0
+
+    def cam_of(i):
+        if ncam == 1:
+            return 0
+        for c in range(ncam):
+            if cam_off[c] <= i < cam_off[c + 1]:
+                return c
+        return -1
+    for a, b in shared_nodes(fv1, fv2):
+        for ikf in fv1[2][fv1[1][a]:fv1[1][a + 1]]:
+            if skip1[ikf]:
+                continue
+            b1 = [256] * 4; b2 = [256] * 4; bi = [-1] * 4
+            for i_f in fv2[2][fv2[1][b]:fv2[1][b + 1]]:
+                if match[i_f] >= 0:
+                    continue
+                c = cam_of(int(i_f))
+                if c < 0:
+                    continue
+                d = hamming(d1[ikf], d2[i_f])
+                if d < b1[c]:
+                    b2[c], b1[c], bi[c] = b1[c], d, int(i_f)
+                elif d < b2[c]:
+                    b2[c] = d
+            if b1[0] <= 50:
+                for c in range(ncam):
+                    ok = (f32(b1[0]) < f32(nnratio) * f32(b2[0])) if c == 0 else (b1[c] <= 50)    # `|| true` for cameras 1-3
+                    if not ok:
+                        continue
+                    match[bi[c]] = ikf; nm += 1
+                    if check:
+                        hist[rot_bin(a1[ikf], a2[bi[c]])].append(bi[c])
+    if check:
+        keep = three_maxima_filter(hist)
+        for bn in range(30):
+            if bn not in keep:
+                for i_f in hist[bn]:
+                    match[i_f] = -1; nm -= 1
+    ref = np.zeros(n_f, np.int32)
+    rn = O.lib().orc_search_by_bow_frame(len(fv1[0]), O.p(fv1[0]), O.p(fv1[1]), O.p(fv1[2]), len(fv2[0]), O.p(fv2[0]), O.p(fv2[1]), O.p(fv2[2]),
+                                         O.p(d1), O.p(d2), n_f, O.p(skip1), O.p(a1), O.p(a2), ncam, None if cam_off is None else O.p(cam_off),
+                                         C.c_float(f32(nnratio)), int(check), O.p(ref))
+    assert rn == nm and np.array_equal(ref, match) and nm > 20
+
+
+@pytest.mark.parametrize('seed,window,nnratio,check', [(31, 6, 0.9, True), (32, 15, 0.8, False), (33, 30, 1.0, True)])
+def test_search_for_initialization_two_restatements(seed, window, nnratio, check):
+    rng = np.random.default_rng(seed)
+    n2, n1 = 150, 200
+    k2 = random_kps(rng, n2); k2['octave'] = np.where(rng.random(n2) < 0.7, 0, k2['octave'])
+    pool = synth_descriptors(5, seed)
+    d2 = pooled_desc(rng, n2, pool)
+    src = rng.integers(0, n2, n1)
+    k1 = k2[src].copy()
+    k1['x'] += rng.uniform(-4, 4, n1).astype(np.float32); k1['y'] += rng.uniform(-4, 4, n1).astype(np.float32)
+    k1['angle'] = ((k2['angle'][src] + np.where(rng.random(n1) < 0.8, 15.0, rng.uniform(0, 360, n1))) % 360).astype(np.float32)
+    d1 = pooled_desc(rng, n1, pool)
+    prev = np.ascontiguousarray(np.stack([k1['x'], k1['y']], 1).astype(np.float32)); prev_ref = prev.copy()
+    grid = PyGrid(k2, (0, 120, 0, 120))
+    m12 = np.full(n1, -1, np.int32); m21 = np.full(n2, -1, np.int32); mdist = np.full(n2, 2 ** 31 - 1, np.int64)
+    hist = [[] for _ in range(30)]; nm = 0
+    for i1 in range(n1):
+        l1 = int(k1['octave'][i1])
+        if l1 > 0:
+            continue
+        cand = grid.area(prev[i1, 0], prev[i1, 1], f32(window), l1, l1)
+        if not cand:
+            continue
+        b1 = b2 = 2 ** 31 - 1; bi = -1
+        for i2 in cand:
+            d = hamming(d1[i1], d2[i2])
+            if mdist[i2] <= d:
+                continue
+            if d < b1:
+                b2, b1, bi = b1, d, i2
+            elif d < b2:
+                b2 = d
+        if b1 <= 50 and b1 < float(f32(b2) * f32(nnratio)):
+            if m21[bi] >= 0:
+                m12[m21[bi]] = -1; nm -= 1
+            m12[i1] = bi; m21[bi] = i1; mdist[bi] = b1; nm += 1
+            if check:
+                hist[rot_bin(k1['angle'][i1], k2['angle'][bi])].append(i1)
+    if check:
+        keep = three_maxima_filter(hist)
+        for bn in range(30):
+            if bn not in keep:
+                for i1 in hist[bn]:
+                    if m12[i1] >= 0:
+                        m12[i1] = -1; nm -= 1
+    for i1 in range(n1):
+        if m12[i1] >= 0:
+            prev[i1] = (k2['x'][m12[i1]], k2['y'][m12[i1]])
+    L = O.lib()
+    g2 = L.orc_grid_create(O.p(k2), n2, C.c_float(0), C.c_float(120), C.c_float(0), C.c_float(120))
+    ref = np.zeros(n1, np.int32)
+    rn = L.orc_search_for_initialization(O.p(k1), O.p(d1), n1, C.c_void_p(g2), O.p(k2), O.p(d2), n2, O.p(prev_ref), window,
+                                         C.c_float(f32(nnratio)), int(check), O.p(ref))
+    L.orc_grid_destroy(C.c_void_p(g2))
+    assert rn == nm and np.array_equal(ref, m12) and np.array_equal(prev, prev_ref) and nm > 5
