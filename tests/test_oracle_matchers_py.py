@@ -348,3 +348,92 @@ def test_search_for_initialization_two_restatements(seed, window, nnratio, check
                                          C.c_float(f32(nnratio)), int(check), O.p(ref))
     L.orc_grid_destroy(C.c_void_p(g2))
     assert rn == nm and np.array_equal(ref, m12) and np.array_equal(prev, prev_ref) and nm > 5
+
+
+@pytest.mark.parametrize('seed,ncam,th,nnratio,far', [(41, 1, 1.0, 0.8, False), (42, 2, 3.0, 0.8, True), (43, 4, 3.0, 0.6, False), (44, 2, 6.0, 1.0, False)])
+def test_search_by_projection_map_points_two_restatements(seed, ncam, th, nnratio, far):
+    """SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints) src/ORBmatcher.cc:23-340: radius by viewing cosine
+    (th only on camera 0), best / second with levels, the ratio-test `continue` that skips the remaining cameras, stereo mirrors."""
+    rng = np.random.default_rng(seed)
+    ns = [int(rng.integers(40, 90)) for _ in range(ncam)]
+    cam_off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    N = int(cam_off[-1])
+    kps = random_kps(rng, N); pool = synth_descriptors(5, seed)
+    desc = pooled_desc(rng, N, pool)
+    sf = np.array([f32(1.2) ** l for l in range(8)], np.float32)
+    occupied = (rng.random(N) < 0.1).astype(np.uint8)
+    n = 160
+    tgt = rng.integers(0, N, n)
+    px = np.zeros((n, 4), np.float32); py = np.zeros((n, 4), np.float32)
+    for c in range(ncam):
+        kk = np.where((tgt >= cam_off[c]) & (tgt < cam_off[c + 1]), tgt, rng.integers(cam_off[c], cam_off[c + 1], n))
+        px[:, c] = kps['x'][kk] + rng.uniform(-2, 2, n); py[:, c] = kps['y'][kk] + rng.uniform(-2, 2, n)
+    in_view = (rng.random((n, 4)) < 0.8).astype(np.uint8); in_view[:, ncam:] = 0
+    level = np.repeat(np.clip(kps['octave'][tgt] + rng.integers(0, 2, n), 0, 3)[:, None], 4, 1).astype(np.int32)
+    level[rng.random((n, 4)) < 0.05] = -1
+    level[:, 0] = np.maximum(level[:, 0], 0)                                   # camera 0 assumes a valid level
+    vc = rng.choice([0.9990, 0.99], (n, 4)).astype(np.float32)
+    depth = rng.uniform(1, 80, n).astype(np.float32); bad = (rng.random(n) < 0.05).astype(np.uint8)
+    has_obs = (rng.random(n) < 0.8).astype(np.uint8); pdesc = pooled_desc(rng, n, pool)
+    l2r = r2l = None
+    if ncam >= 2:
+        nl, nr = int(cam_off[1]), int(cam_off[2] - cam_off[1])
+        l2r = np.full(nl, -1, np.int32); r2l = np.full(nr, -1, np.int32)
+        k = min(nl, nr) // 2
+        for a, b in zip(rng.permutation(nl)[:k], rng.permutation(nr)[:k]):
+            l2r[a] = b; r2l[b] = a
+    # ---- Python restatement
+    grids = [PyGrid(kps[cam_off[c]:cam_off[c + 1]], (0, 120, 0, 120)) for c in range(ncam)]
+    occ = occupied.copy(); assigned = np.full(N, -1, np.int32); nm = 0
+    for m in range(n):
+        if not in_view[m].any() or (far and depth[m] > f32(40.0)) or bad[m]:
+            continue
+        for c in range(4):
+            if not in_view[m, c] or c >= ncam:
+                continue
+            lvl = int(level[m, c])
+            if c >= 1 and lvl == -1:
+                continue
+            r = f32(2.5) if float(vc[m, c]) > 0.998 else f32(4.0)
+            if c == 0 and th != 1.0:
+                r = f32(r * f32(th))
+            ck = kps[cam_off[c]:cam_off[c + 1]]
+            cand = grids[c].area(px[m, c], py[m, c], f32(r * sf[lvl]), lvl - 1, lvl)
+            if not cand:
+                continue
+            b1 = b2 = 256; l1 = l2 = -1; bi = -1
+            for j in cand:
+                if occ[j + cam_off[c]]:
+                    continue
+                d = hamming(pdesc[m], desc[j + cam_off[c]])
+                if d < b1:
+                    b2, b1, l2, l1, bi = b1, d, l1, int(ck['octave'][j]), j
+                elif d < b2:
+                    l2, b2 = int(ck['octave'][j]), d
+            if b1 <= 100:
+                if l1 == l2 and b1 > float(f32(nnratio) * f32(b2)):
+                    break                                                      # `continue` of the map-point loop
+                g = bi + cam_off[c]
+                assigned[g] = m; occ[g] = has_obs[m]; nm += 1
+                if c == 0 and ncam >= 2 and l2r[bi] != -1:
+                    gr = l2r[bi] + cam_off[1]
+                    assigned[gr] = m; occ[gr] = has_obs[m]; nm += 1
+                if c == 1 and r2l[bi] != -1:
+                    gl = r2l[bi]
+                    assigned[gl] = m; occ[gl] = has_obs[m]; nm += 1
+    # ---- C++ oracle
+    L = O.lib()
+    cg = (C.c_void_p * 4)()
+    for c in range(ncam):
+        sub = np.ascontiguousarray(kps[cam_off[c]:cam_off[c + 1]])
+        cg[c] = L.orc_grid_create(O.p(sub), sub.size, C.c_float(0), C.c_float(120), C.c_float(0), C.c_float(120))
+    ref = np.zeros(N, np.int32)
+    L.orc_search_by_projection.restype = C.c_int
+    rn = L.orc_search_by_projection(ncam, O.p(cam_off), O.p(kps), O.p(desc), cg, O.p(sf), O.p(occupied), None if l2r is None else O.p(l2r),
+                                    None if r2l is None else O.p(r2l), None, n, O.p(in_view), O.p(px), O.p(py), O.p(level), O.p(vc), None,
+                                    O.p(depth), O.p(bad), O.p(has_obs), O.p(pdesc), C.c_float(th), int(far), C.c_float(40.0),
+                                    C.c_float(f32(nnratio)), O.p(ref))
+    for c in range(ncam):
+        L.orc_grid_destroy(C.c_void_p(cg[c]))
+    assert rn == nm and np.array_equal(ref, assigned)
+    assert nm > 10
