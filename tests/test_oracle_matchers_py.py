@@ -437,3 +437,146 @@ def test_search_by_projection_map_points_two_restatements(seed, ncam, th, nnrati
         L.orc_grid_destroy(C.c_void_p(cg[c]))
     assert rn == nm and np.array_equal(ref, assigned)
     assert nm > 10
+
+
+@pytest.mark.parametrize('mb,mbf', [(0.11, 47.9), (0.05, 20.0)])
+def test_compute_stereo_matches_two_restatements(mb, mbf):
+    """Frame::ComputeStereoMatches src/Frame.cc:1057-1219 restated in Python (float32 step by step) against the C++ oracle, on an
+    oracle-extracted synthetic stereo pair."""
+    from openmavis_b200.synth import synth_image
+    w, h = 376, 240
+    left = synth_image(w, h, 2101)
+    xs = np.arange(w)
+    right = left[:, np.clip(xs + (9 + 6 * np.sin(xs / 60.0)).astype(np.int64), 0, w - 1)].copy()
+    EL = O.OracleExtractor(600, 1.2, 8, 20, 7); ER = O.OracleExtractor(600, 1.2, 8, 20, 7)
+    _, kl, dl = EL(left, (0, 0)); _, kr, dr = ER(right, (0, 0))
+    tab = EL.tables()
+    sf, inv_sf = tab['sf'], tab['inv_sf']
+    pyrL = [EL.level(l) for l in range(8)]; pyrR = [ER.level(l) for l in range(8)]
+    N = kl.size
+    u_right = np.full(N, -1, np.float32); depth = np.full(N, -1, np.float32)
+    rows = [[] for _ in range(h)]
+    for iR in range(kr.size):
+        r = f32(f32(2.0) * sf[kr['octave'][iR]])
+        maxr = int(math.ceil(float(f32(kr['y'][iR] + r)))); minr = int(math.floor(float(f32(kr['y'][iR] - r))))
+        for yi in range(minr, maxr + 1):
+            rows[yi].append(iR)
+    maxD = f32(f32(mbf) / f32(mb))
+    dist_idx = []
+
+    def c_round(v):
+        v = float(v)
+        return f32(math.floor(v + 0.5) if v >= 0 else -math.floor(-v + 0.5))
+    with np.errstate(all='ignore'):
+        for iL in range(N):
+            lvl = int(kl['octave'][iL]); vL = kl['y'][iL]; uL = kl['x'][iL]
+            cands = rows[int(vL)]
+            if not cands:
+                continue
+            minU = f32(uL - maxD); maxU = uL
+            if maxU < 0:
+                continue
+            best, best_r = 100, 0
+            for iR in cands:
+                if kr['octave'][iR] < lvl - 1 or kr['octave'][iR] > lvl + 1:
+                    continue
+                if minU <= kr['x'][iR] <= maxU:
+                    d = hamming(dl[iL], dr[iR])
+                    if d < best:
+                        best, best_r = d, iR
+            if best >= (100 + 50) // 2:
+                continue
+            uR0 = kr['x'][best_r]; s = inv_sf[lvl]
+            su = c_round(f32(uL * s)); sv = c_round(f32(vL * s)); sr0 = c_round(f32(uR0 * s))
+            wdw, L = 5, 5
+            IL_ = pyrL[lvl][19 + int(sv) - wdw:19 + int(sv) + wdw + 1, 19 + int(su) - wdw:19 + int(su) + wdw + 1].astype(np.int64)
+            cols = pyrR[lvl].shape[1] - 38
+            iniu = f32(sr0 + f32(L) - f32(wdw)); endu = f32(sr0 + f32(L) + f32(wdw) + f32(1))
+            if iniu < 0 or endu >= cols:
+                continue
+            bestd, bestinc = 2 ** 31 - 1, 0
+            vd = np.zeros(2 * L + 1, np.float32)
+            for inc in range(-L, L + 1):
+                x0 = 19 + int(sr0) + inc - wdw
+                IR_ = pyrR[lvl][19 + int(sv) - wdw:19 + int(sv) + wdw + 1, x0:x0 + 2 * wdw + 1].astype(np.int64)
+                dist = f32(np.abs(IL_ - IR_).sum())
+                if dist < f32(bestd):
+                    bestd, bestinc = int(dist), inc
+                vd[L + inc] = dist
+            if bestinc in (-L, L):
+                continue
+            d1, d2, d3 = vd[L + bestinc - 1], vd[L + bestinc], vd[L + bestinc + 1]
+            delta = f32(f32(d1 - d3) / f32(f32(2.0) * f32(f32(d1 + d3) - f32(f32(2.0) * d2))))
+            if delta < -1 or delta > 1:
+                continue
+            best_u = f32(sf[lvl] * f32(f32(sr0 + f32(bestinc)) + delta))
+            disp = f32(uL - best_u)
+            if disp >= 0 and disp < maxD:
+                if disp <= 0:
+                    disp = f32(0.01); best_u = f32(float(uL) - 0.01)
+                depth[iL] = f32(f32(mbf) / disp); u_right[iL] = best_u
+                dist_idx.append((bestd, iL))
+    dist_idx.sort()
+    median = f32(dist_idx[len(dist_idx) // 2][0])
+    th = f32(f32(f32(1.5) * f32(1.4)) * median)
+    for d, i in reversed(dist_idx):
+        if f32(d) < th:
+            break
+        u_right[i] = -1; depth[i] = -1
+    ru = np.zeros(N, np.float32); rd = np.zeros(N, np.float32)
+    L_ = O.lib()
+    L_.orc_compute_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    n = L_.orc_compute_stereo_matches(EL.h, ER.h, mb, mbf, O.p(ru), O.p(rd))
+    assert n == int((depth > 0).sum()) and n > 60
+    assert np.array_equal(ru.view(np.uint32), u_right.view(np.uint32)) and np.array_equal(rd.view(np.uint32), depth.view(np.uint32))
+
+
+def test_distinctive_descriptors_and_vocabulary_two_restatements():
+    """MapPoint::ComputeDistinctiveDescriptors src/MapPoint.cc:405-483 and the DBoW2 descent (TemplatedVocabulary.h:1213-1259)."""
+    rng = np.random.default_rng(7)
+    sizes = rng.integers(0, 14, 120).astype(np.int32); sizes[::11] = 1
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    pool = synth_descriptors(120, 3)
+    desc = np.repeat(pool, sizes, axis=0) ^ np.packbits(rng.random((int(ptr[-1]), 256)) < 0.1, axis=1, bitorder='little')
+    best = np.zeros(120, np.int32)
+    O.lib().orc_distinctive_descriptors(O.p(desc), O.p(ptr), 120, O.p(best))
+    for g in range(120):
+        n = int(sizes[g])
+        if n == 0:
+            assert best[g] == -1
+            continue
+        rows = desc[ptr[g]:ptr[g + 1]]
+        D = np.array([[hamming(a, b) for b in rows] for a in rows])
+        med = [sorted(D[i])[int(0.5 * (n - 1))] for i in range(n)]
+        assert best[g] == int(np.argmin(med))                                  # first minimum
+    # vocabulary: k-ary tree with random node descriptors; the descent takes the FIRST child with the least distance
+    k, Lv = 5, 3
+    # (breadth-first numbering)
+    nodes = [dict(children=[], desc=np.zeros(32, np.uint8), word=-1)]
+    frontier = [0]
+    for lev in range(Lv):
+        nxt = []
+        for nid in frontier:
+            for _ in range(k):
+                nodes.append(dict(children=[], desc=synth_descriptors(1, len(nodes) + 100)[0], word=-1))
+                nodes[nid]['children'].append(len(nodes) - 1); nxt.append(len(nodes) - 1)
+        frontier = nxt
+    for wid, nid in enumerate(frontier):
+        nodes[nid]['word'] = wid
+    nodes[3]['desc'] = nodes[2]['desc'].copy()                                  # a tie between siblings
+    child_ptr = np.zeros(len(nodes) + 1, np.int32); child = []
+    for i, nd in enumerate(nodes):
+        child += nd['children']; child_ptr[i + 1] = len(child)
+    child = np.array(child, np.int32); ndesc = np.stack([nd['desc'] for nd in nodes]); word = np.array([nd['word'] for nd in nodes], np.int32)
+    feats = synth_descriptors(300, 9); feats[:20] = ndesc[rng.integers(1, len(nodes), 20)]
+    ow = np.zeros(300, np.int32); on = np.zeros(300, np.int32)
+    O.lib().orc_vocab_transform(O.p(child_ptr), O.p(child), O.p(ndesc), O.p(word), Lv, O.p(feats), 300, 2, O.p(ow), O.p(on))
+    for i in range(300):
+        nid, lev, node_at = 0, 0, 0
+        while nodes[nid]['children']:
+            ch = nodes[nid]['children']
+            ds = [hamming(feats[i], nodes[c]['desc']) for c in ch]
+            nid = ch[int(np.argmin(ds))]; lev += 1
+            if lev == Lv - 2:
+                node_at = nid
+        assert ow[i] == nodes[nid]['word'] and on[i] == node_at
