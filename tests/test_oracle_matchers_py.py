@@ -580,3 +580,105 @@ def test_distinctive_descriptors_and_vocabulary_two_restatements():
             if lev == Lv - 2:
                 node_at = nid
         assert ow[i] == nodes[nid]['word'] and on[i] == node_at
+
+
+def test_fuse_search_loop_sim3_and_triangulation_two_restatements():
+    """Fuse's search loop (src/ORBmatcher.cc:1549-1601 with the 5.99 / 7.8 reprojection gates), SearchBySim3 (:1771-1983) and the
+    Hamming core of SearchForTriangulation (:1238-1290, bCoarse: LAST minimum within TH_LOW)."""
+    rng = np.random.default_rng(51)
+    L = O.lib()
+    n, nq = 140, 160
+    kps = random_kps(rng, n); pool = synth_descriptors(5, 51); desc = pooled_desc(rng, n, pool)
+    sf = np.array([f32(1.2) ** l for l in range(8)], np.float32)
+    inv_s2 = (f32(1.0) / (sf * sf)).astype(np.float32)
+    tgt = rng.integers(0, n, nq)
+    qx = (kps['x'][tgt] + rng.uniform(-3, 3, nq)).astype(np.float32); qy = (kps['y'][tgt] + rng.uniform(-3, 3, nq)).astype(np.float32)
+    lvl = np.clip(kps['octave'][tgt] + rng.integers(0, 2, nq), 0, 3).astype(np.int32); mn = (lvl - 1).astype(np.int32)
+    radius = (f32(3.0) * sf[lvl]).astype(np.float32)
+    qd = pooled_desc(rng, nq, pool); valid = (rng.random(nq) < 0.9).astype(np.uint8)
+    u_right = np.where(rng.random(n) < 0.5, kps['x'] - rng.uniform(1, 20, n), -1).astype(np.float32)
+    q_ur = (qx - rng.uniform(0, 22, nq)).astype(np.float32)
+    grid = PyGrid(kps, (0, 120, 0, 120))
+    g = L.orc_grid_create(O.p(kps), n, C.c_float(0), C.c_float(120), C.c_float(0), C.c_float(120))
+    for gates in (True, False):
+        bi = np.full(nq, -1, np.int32); bd = np.full(nq, 256, np.int32)
+        for q in range(nq):
+            if not valid[q]:
+                continue
+            for j in grid.area(qx[q], qy[q], radius[q], -1, -1):
+                o = int(kps['octave'][j])
+                if o < mn[q] or o > lvl[q]:
+                    continue
+                if gates:
+                    ex = f32(qx[q] - kps['x'][j]); ey = f32(qy[q] - kps['y'][j])
+                    if u_right[j] >= 0:
+                        er = f32(q_ur[q] - u_right[j])
+                        e2 = f32(f32(f32(ex * ex) + f32(ey * ey)) + f32(er * er))
+                        if float(f32(e2 * inv_s2[o])) > 7.8:
+                            continue
+                    else:
+                        e2 = f32(f32(ex * ex) + f32(ey * ey))
+                        if float(f32(e2 * inv_s2[o])) > 5.99:
+                            continue
+                d = hamming(qd[q], desc[j])
+                if d < bd[q]:
+                    bd[q], bi[q] = d, j
+        ri = np.zeros(nq, np.int32); rd = np.zeros(nq, np.int32)
+        L.orc_window_best(C.c_void_p(g), O.p(kps), O.p(desc), None, O.p(u_right) if gates else None, O.p(inv_s2) if gates else None, nq,
+                          O.p(valid), O.p(qx), O.p(qy), O.p(q_ur) if gates else None, O.p(radius), O.p(mn), O.p(lvl), O.p(qd), O.p(ri), O.p(rd))
+        assert np.array_equal(ri, bi) and np.array_equal(rd, bd)
+    # ---- SearchBySim3 on (kps, desc) x (kps2, desc2)
+    n2 = 130
+    k2 = random_kps(rng, n2); d2 = pooled_desc(rng, n2, pool); grid2 = PyGrid(k2, (0, 120, 0, 120))
+    g2 = L.orc_grid_create(O.p(k2), n2, C.c_float(0), C.c_float(120), C.c_float(0), C.c_float(120))
+
+    def side(n_self, k_other, target):
+        u = (k_other['x'][target] + rng.uniform(-2, 2, n_self)).astype(np.float32); v = (k_other['y'][target] + rng.uniform(-2, 2, n_self)).astype(np.float32)
+        lv = np.clip(k_other['octave'][target] + rng.integers(0, 2, n_self), 0, 3).astype(np.int32)
+        return dict(valid=(rng.random(n_self) < 0.85).astype(np.uint8), u=u, v=v, radius=(f32(7.5) * sf[lv]).astype(np.float32), level=lv,
+                    desc=pooled_desc(rng, n_self, pool))
+    s1 = side(n, k2, rng.integers(0, n2, n)); s2 = side(n2, kps, rng.integers(0, n, n2))
+
+    def one_way(s, grid_o, k_o, d_o):
+        out = np.full(s['u'].size, -1, np.int64)
+        for i in range(s['u'].size):
+            if not s['valid'][i]:
+                continue
+            best, bj = 2 ** 31 - 1, -1
+            for j in grid_o.area(s['u'][i], s['v'][i], s['radius'][i], -1, -1):
+                if k_o['octave'][j] < s['level'][i] - 1 or k_o['octave'][j] > s['level'][i]:
+                    continue
+                d = hamming(s['desc'][i], d_o[j])
+                if d < best:
+                    best, bj = d, j
+            if best <= 100:
+                out[i] = bj
+        return out
+    m1 = one_way(s1, grid2, k2, d2); m2 = one_way(s2, grid, kps, desc)
+    m12 = np.array([m1[i] if m1[i] >= 0 and m2[m1[i]] == i else -1 for i in range(n)], np.int32)
+    ref = np.zeros(n, np.int32)
+    rn = L.orc_search_by_sim3(C.c_void_p(g), O.p(kps), O.p(desc), n, C.c_void_p(g2), O.p(k2), O.p(d2), n2, O.p(s1['valid']), O.p(s1['u']), O.p(s1['v']),
+                              O.p(s1['radius']), O.p(s1['level']), O.p(s1['desc']), O.p(s2['valid']), O.p(s2['u']), O.p(s2['v']), O.p(s2['radius']),
+                              O.p(s2['level']), O.p(s2['desc']), O.p(ref))
+    L.orc_grid_destroy(C.c_void_p(g)); L.orc_grid_destroy(C.c_void_p(g2))
+    assert rn == int((m12 >= 0).sum()) and np.array_equal(ref, m12)
+    # ---- SearchForTriangulation core
+    d1, dd2, _, _, fv1, fv2, skip1, skip2 = bow_case(61, 220, 200)
+    match = np.full(220, -1, np.int32)
+    for a, b in shared_nodes(fv1, fv2):
+        for i1 in fv1[2][fv1[1][a]:fv1[1][a + 1]]:
+            if skip1[i1]:
+                continue
+            best, bj = 50, -1
+            for i2 in fv2[2][fv2[1][b]:fv2[1][b + 1]]:
+                if skip2[i2]:
+                    continue
+                d = hamming(d1[i1], dd2[i2])
+                if d > 50 or d > best:
+                    continue
+                bj, best = int(i2), d
+            match[i1] = bj
+    ref = np.zeros(220, np.int32)
+    rn = L.orc_search_for_triangulation(len(fv1[0]), O.p(fv1[0]), O.p(fv1[1]), O.p(fv1[2]), len(fv2[0]), O.p(fv2[0]), O.p(fv2[1]), O.p(fv2[2]),
+                                        O.p(d1), 220, O.p(dd2), O.p(skip1), O.p(skip2), None, None, O.p(ref))
+    assert rn == int((match >= 0).sum()) and np.array_equal(ref, match) and rn > 20
