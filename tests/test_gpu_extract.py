@@ -331,3 +331,24 @@ def test_concurrent_extractor_threads_reference_usage():
             assert mono == rmono and np.array_equal(desc, rdesc)
             for f in KPF:
                 assert np.array_equal(kps[f].view(np.uint32), rkps[f].view(np.uint32)), f
+
+
+def test_graph_cache_survives_many_device_buffers():
+    """Small device-resident calls replay a CUDA graph cached per input buffer; a caller that keeps handing in new buffers (80
+    distinct ones here, more than the cache holds) must keep getting the same results."""
+    _need_gpu()
+    import torch
+    w, h = 512, 384
+    imgs = np.stack([synth_image(w, h, 3500 + c) for c in range(2)])
+    rig = ob.RigExtractor(w, h, 2, 500)
+    p = ob.make_params(2, 500, 20, 7, (0, 0))
+    ref = [(m, k.copy(), d.copy()) for m, k, d in rig.extract(list(imgs), p)]
+    rig.set_stream(torch.cuda.current_stream().cuda_stream)
+    base = torch.from_numpy(imgs).cuda()
+    keep = []
+    for it in range(80):
+        t = base.clone(); keep.append(t)                  # a new device address every call
+        rig.extract_device(t.data_ptr(), 2, p)
+        if it % 9 == 0 or it == 79:
+            for (m0, k0, d0), (m1, k1, d1) in zip(ref, rig.fetch(2)):
+                assert m0 == m1 and np.array_equal(k0, k1) and np.array_equal(d0, d1)
