@@ -287,27 +287,6 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
                     }
                     break;
                 }
-                if (P.mode == 1) {   // best candidate only, every camera on its own (:2068-2100 and the per-camera clones)
-                    int bestDist = 256, bestIdx = -1;
-                    for (int k = b; k < e; k++) {
-                        const uint32_t r = cand[k];
-                        const int idx = (int)(r & 0xFFFF), dist = (int)((r >> 16) & 0x1FF);
-                        if (W.occ[idx + F.cam_off[c]]) continue;
-                        if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
-                    }
-                    if (bestDist <= P.max_dist) {   // TH_HIGH (:2103), ORBdist in the relocalisation overload (:2487)
-                        const int g = bestIdx + F.cam_off[c];
-                        W.assigned[g] = u; W.occ[g] = P.has_obs[u]; nm++;
-                        if (P.check_ori) {   // :2121-2128
-                            float rot = __fsub_rn(P.angle[u], F.kps[g].angle);
-                            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                            int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30.0f));
-                            if (bin == 30) bin = 0;
-                            W.events[q] = g | (bin << 16);
-                        }
-                    }
-                    continue;
-                }
                 int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
                 for (int k = b; k < e; k++) {
                     const uint32_t r = cand[k];
