@@ -255,10 +255,10 @@ def run_reference(args):
         vals.append(v); tot_t += dt
     value = frames * args.steps / tot_t
     line = {
-        'impl': 'reference', 'metric': 'rig-frames/sec ORB extract (5x720x540, 1500 kp/cam)', 'value': value, 'unit': 'rig-frames/s',
+        'impl': 'reference', 'metric': 'rig-frames/sec ORB extract (5×720×540, 1500 kp/cam)', 'value': value, 'unit': 'rig-frames/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'frames_per_step': frames, 'features_per_camera': NFEAT,
+        'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'baseline_config': 'BASELINE.json configs[2]: Hilti-2022 5-camera rig 5×720×540, 1500 features/camera, per-rig-frame batched extraction', 'frames_per_step': frames, 'features_per_camera': NFEAT,
                    'fast_thresholds': [INI, MIN], 'levels': 8, 'scale_factor': 1.2},
         'cpu_baseline': {'value': value, 'unit': 'rig-frames/s', 'cores': threads, 'kind': 'port',
                          'sample': '%d rig frames x %d steps, %d host threads (one image per thread)' % (frames, args.steps, threads)},
@@ -546,10 +546,10 @@ def main():
 
     if rank == 0:
         line = {
-            'metric': 'rig-frames/sec ORB extract (5x720x540, 1500 kp/cam)', 'value': value, 'unit': 'rig-frames/s', 'n_gpus': world,
+            'metric': 'rig-frames/sec ORB extract (5×720×540, 1500 kp/cam)', 'value': value, 'unit': 'rig-frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'frames_per_step_per_gpu': frames, 'images_per_step_per_gpu': n_img,
+            'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'baseline_config': 'BASELINE.json configs[2]: Hilti-2022 5-camera rig 5×720×540, 1500 features/camera, per-rig-frame batched extraction', 'frames_per_step_per_gpu': frames, 'images_per_step_per_gpu': n_img,
                        'features_per_camera': NFEAT, 'fast_thresholds': [INI, MIN], 'levels': 8, 'scale_factor': 1.2,
                        'keypoints_per_image': kp_per_image, 'pipeline': 'two extractor handles alternate over the steps (one stream each)',
                        'host_numa_node': numa_node,
