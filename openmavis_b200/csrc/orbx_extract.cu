@@ -338,8 +338,6 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
         }
         ex->rsz_smem = resize_smem_bytes(ex->rsz_rows, ex->rsz_pitch);
         if (ex->rsz_smem > 200 * 1024) { orbx_extractor_destroy(ex); return fail(ORBX_ERR_INVALID, "scale factor too large for the resize tile"); }
-        if (ex->rsz_smem > 48 * 1024)
-            EX_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->rsz_smem));
         EX_CUDA(dalloc(&ex->d_taps, (size_t)ntap));
         EX_CUDA(cudaMemcpy(ex->d_taps, taps.data(), ntap * sizeof(ResizeTap), cudaMemcpyHostToDevice));
         std::vector<int> tinfo;   // FAST tile -> level | cell row << 4 | tile column << 16
@@ -365,12 +363,21 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
         EX_CUDA(dalloc(&ex->d_pattern, (size_t)1024));
         EX_CUDA(cudaMemcpy(ex->d_pattern, pat, 1024, cudaMemcpyHostToDevice));
     }
-    if (ex->fast_smem > 48 * 1024)
-        EX_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fast_smem));
-    if (ex->oct_smem > 48 * 1024)
     {
-        EX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->oct_smem));
-        EX_CUDA(cudaFuncSetAttribute(k_octree_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->oct_smem));
+        // Dynamic shared memory limits.  The attribute is per kernel and per process, not per handle, and the kernels also hold a few
+        // bytes of static shared memory: every handle raises the limit to the device's opt-in maximum, so a handle whose tiles stay
+        // just under 48 KB, or one created after a handle with larger tiles, never runs into another handle's setting.
+        int optin = 0;
+        EX_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        if ((size_t)optin < std::max(std::max(ex->fast_smem, ex->oct_smem), ex->rsz_smem) + 1024) {
+            orbx_extractor_destroy(ex);
+            return fail(ORBX_ERR_INVALID, "the tiles of this geometry do not fit in the device's shared memory");
+        }
+        EX_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+        EX_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+        EX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+        EX_CUDA(cudaFuncSetAttribute(k_octree_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+        EX_CUDA(cudaFuncSetAttribute(k_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
     }
     {   // TMA tensor maps of the pyramid levels for the blur tiles (driver entry point through the runtime: no -lcuda)
         memset(&ex->blur_maps, 0, sizeof(ex->blur_maps));

@@ -1,5 +1,7 @@
 """GPU parity tests (run on the B200 box): the CUDA extraction path through the C ABI vs the CPU oracle,
 stage by stage and end to end, bit-exact.  Reference path: src/ORBextractor.cc:987-1071."""
+import os
+
 import numpy as np
 import pytest
 
@@ -352,3 +354,22 @@ def test_graph_cache_survives_many_device_buffers():
         if it % 9 == 0 or it == 79:
             for (m0, k0, d0), (m1, k1, d1) in zip(ref, rig.fetch(2)):
                 assert m0 == m1 and np.array_equal(k0, k1) and np.array_equal(d0, d1)
+
+
+@pytest.mark.parametrize('w,h,nf', [(1280, 1024, 2000), (752, 480, 1000)])
+def test_first_handle_of_a_process_at_any_geometry(w, h, nf):
+    """Shared-memory opt-in limits are per kernel and per PROCESS: a geometry whose tiles sit just under 48 KB must also work as the
+    first handle of a fresh process (no earlier handle has raised the limit)."""
+    import subprocess
+    import sys
+    _need_gpu()
+    code = ('import numpy as np, openmavis_b200 as ob\n'
+            'from openmavis_b200.synth import synth_image\n'
+            'rig = ob.RigExtractor(%d, %d, 2, %d)\n'
+            'res = rig.extract([synth_image(%d, %d, 5000), synth_image(%d, %d, 5001)], ob.make_params(2, %d, 20, 7, (0, 0)))\n'
+            'print(len(res[0][1]), len(res[1][1]))\n' % (w, h, nf, w, h, w, h, nf))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-c', code], cwd=root, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-800:]
+    a, b = (int(x) for x in out.stdout.split())
+    assert a >= nf * 0.9 and b >= nf * 0.9
