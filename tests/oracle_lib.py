@@ -180,3 +180,103 @@ def libm_sincosf(x):
     s = np.zeros_like(x); c = np.zeros_like(x)
     lib().orc_libm_sincosf_n(p(x), p(s), p(c), x.size)
     return s, c
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own src/ORBextractor.cc, compiled unmodified against oracle/cvshim (oracle/Makefile).
+# ---------------------------------------------------------------------------------------------------------------------
+_ref_libs = {}
+
+
+def ref_lib(fma=False):
+    """oracle/_ref/libref_orb.so (-ffp-contract=off) or libref_orb_fma.so (the reference's own flags: contraction allowed).
+    Built from /root/reference when that mount exists (the build container); on the GPU box the prebuilt file must have
+    travelled with the snapshot — a missing file is an error, not a skip."""
+    if fma not in _ref_libs:
+        so = os.path.join(ROOT, 'oracle', '_ref', 'libref_orb_fma.so' if fma else 'libref_orb.so')
+        if not os.path.exists(so):
+            import subprocess
+            subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')])
+        if not os.path.exists(so):
+            raise RuntimeError('%s is missing and /root/reference is not mounted to build it' % so)
+        lib()   # liborb_oracle.so carries the cv2-pinned primitives the shim delegates to
+        L = C.CDLL(so)
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_extract_batch.restype = C.c_double
+        _ref_libs[fma] = L
+    return _ref_libs[fma]
+
+
+class RefExtractor:
+    """ORB_SLAM3::ORBextractor itself (reference object code), same call shape as OracleExtractor."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, fma=False):
+        self.L = ref_lib(fma)
+        self.nlevels = nlevels
+        self.h = C.c_void_p(self.L.ref_create(nfeatures, C.c_float(scaleFactor), nlevels, iniThFAST, minThFAST))
+
+    def __del__(self):
+        try:
+            self.L.ref_destroy(self.h)
+        except Exception:
+            pass
+
+    def tables(self):
+        n = self.nlevels
+        sf, isf, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        nf = np.zeros(n, np.int32); um = np.zeros(16, np.int32)
+        self.L.ref_tables(self.h, p(sf), p(isf), p(s2), p(is2), p(nf), p(um))
+        return dict(sf=sf, inv_sf=isf, sigma2=s2, inv_sigma2=is2, nfeat=nf, umax=um)
+
+    def __call__(self, image, lapping=(0, 0)):
+        if image is None or image.size == 0:
+            mono = self.L.ref_extract(self.h, None, 0, 0, 0, int(lapping[0]), int(lapping[1]))
+            return mono, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2 and image.strides[1] == 1
+        hh, w = image.shape
+        mono = self.L.ref_extract(self.h, p(image), w, hh, image.strides[0], int(lapping[0]), int(lapping[1]))
+        n = self.L.ref_num_keypoints(self.h)
+        kps = np.zeros(n, KP_DTYPE); desc = np.zeros((n, 32), np.uint8)
+        if n:
+            self.L.ref_result(self.h, p(kps), p(desc))
+        return mono, kps, desc
+
+    def level(self, l):
+        w, hh = C.c_int(), C.c_int()
+        self.L.ref_level_size(self.h, l, C.byref(w), C.byref(hh))
+        buf = np.zeros((hh.value + 38, w.value + 38), np.uint8)
+        self.L.ref_level_bordered(self.h, l, p(buf))
+        return buf
+
+    def stages(self, image):
+        """ComputePyramid + ComputeKeyPointsOctTree; per-level keypoints (level coordinates, angles set)"""
+        img = np.ascontiguousarray(image)
+        self.L.ref_stages(self.h, p(img), img.shape[1], img.shape[0], img.strides[0])
+        out = []
+        for l in range(self.nlevels):
+            n = self.L.ref_level_num_keypoints(self.h, l)
+            k = np.zeros(n, KP_DTYPE)
+            if n:
+                self.L.ref_level_keypoints(self.h, l, p(k))
+            out.append(k)
+        return out
+
+    def distribute(self, xs, ys, scores, minX, maxX, minY, maxY, N):
+        xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32)
+        scores = np.ascontiguousarray(scores, np.int32)
+        cap = max(1, xs.size)
+        ox, oy, osc = (np.zeros(cap, np.int32) for _ in range(3))
+        n = self.L.ref_distribute(self.h, p(xs), p(ys), p(scores), xs.size, minX, maxX, minY, maxY, N, p(ox), p(oy), p(osc), cap)
+        return ox[:n], oy[:n], osc[:n]
+
+
+def ref_extract_batch(imgs, nfeatures, sf, nlevels, ini, mn, lapping, nthreads, fma=True):
+    """seconds, keypoints: the reference extractor over a (n, h, w) stack with `nthreads` workers (CPU baseline)"""
+    imgs = np.ascontiguousarray(imgs)
+    n, hh, w = imgs.shape
+    nkp = C.c_longlong(0)
+    dt = ref_lib(fma).ref_extract_batch(n, p(imgs), w, hh, nfeatures, C.c_float(sf), nlevels, ini, mn, int(lapping[0]), int(lapping[1]),
+                                        nthreads, C.byref(nkp))
+    return dt, nkp.value

@@ -45,7 +45,29 @@ def compare_image(rig, b, img, nf, ini, mn, lap, result, fma_mode=0, stages=True
     for f in KPF:
         assert np.array_equal(kps[f].view(np.uint32), gk[f].view(np.uint32)), 'final keypoint field %s' % f
     assert np.array_equal(desc, gd), '%d descriptor rows differ' % int((desc != gd).any(axis=1).sum())
+    compare_with_reference(rig, b, img, nf, ini, mn, lap, result, fma_mode, stages)
     return len(kps)
+
+
+def compare_with_reference(rig, b, img, nf, ini, mn, lap, result, fma_mode=0, stages=True):
+    """The CUDA result against oracle/_ref — the reference's own src/ORBextractor.cc compiled unmodified (oracle/Makefile):
+    operator() outputs, and with `stages` the public mvImagePyramid planes incl. their 19-px frame and the per-level
+    keypoints ComputeKeyPointsOctTree leaves (position, response, octave, size, angle bits)."""
+    R = O.RefExtractor(nf, 1.2, 8, ini, mn, fma=bool(fma_mode))
+    rmono, rk, rd = R(img, lap)
+    gmono, gk, gd = result
+    assert gmono == rmono and len(gk) == len(rk), 'reference: %d/%d keypoints, mono %d/%d' % (len(gk), len(rk), gmono, rmono)
+    for f in KPF:
+        assert np.array_equal(rk[f].view(np.uint32), gk[f].view(np.uint32)), 'reference: final keypoint field %s' % f
+    assert np.array_equal(rd, gd), 'reference: %d descriptor rows differ' % int((rd != gd).any(axis=1).sum())
+    if stages:
+        for l in range(8):
+            assert np.array_equal(R.level(l), rig.pyramid_level(b, l, with_border=True)), 'reference: pyramid level %d' % l
+        for l, rkl in enumerate(R.stages(img)):
+            gkl = rig.debug_level_keypoints(b, l)
+            assert len(rkl) == len(gkl), 'reference: level %d keypoint count' % l
+            for f in ('x', 'y', 'response', 'octave', 'size', 'angle'):
+                assert np.array_equal(rkl[f].view(np.uint32), gkl[f].view(np.uint32)), 'reference: level %d field %s' % (l, f)
 
 
 KPF = ('x', 'y', 'size', 'angle', 'response', 'octave', 'class_id')
