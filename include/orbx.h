@@ -152,6 +152,9 @@ int orbx_debug_level_keypoints(orbx_extractor *ex, int image, int level, orbx_kp
 #define ORBX_NUM_STAGES 7
 int orbx_extractor_set_profiling(orbx_extractor *ex, int enabled);
 int orbx_extractor_stage_ms(orbx_extractor *ex, float *ms);
+/* FAST counters accumulated over the profiled calls since profiling was switched on (profiling mode only):
+ * out6 = tested pixels, quick-test survivors, corners (score >= threshold), kept after NMS, retried cells, tiles. */
+int orbx_extractor_fast_stats(orbx_extractor *ex, unsigned long long *out6);
 /* Number of kernel launches enqueued by the last call. */
 int orbx_extractor_last_launches(const orbx_extractor *ex);
 

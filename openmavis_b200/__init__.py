@@ -136,6 +136,12 @@ class RigExtractor:
         _check(self.L.orbx_extractor_stage_ms(self.h, _p(ms)))
         return dict(zip(STAGE_NAMES, ms.tolist()))
 
+    def fast_stats(self):
+        """FAST counters over the profiled calls since set_profiling(True): tested pixels, quick-test survivors, corners, kept, ..."""
+        st = np.zeros(6, np.uint64)
+        _check(self.L.orbx_extractor_fast_stats(self.h, _p(st)))
+        return dict(zip(('tested_pixels', 'quick_survivors', 'corners', 'kept_after_nms', 'retried_cells', 'tiles'), (int(x) for x in st)))
+
     def last_launches(self):
         return self.L.orbx_extractor_last_launches(self.h)
 

@@ -100,18 +100,41 @@ struct orbx_extractor {
     uint32_t *d_cells = nullptr, *d_lin = nullptr, *d_lvl_kp = nullptr;
     unsigned short *d_node = nullptr;
     int *d_cell_cnt = nullptr, *d_cell_off = nullptr, *d_lin_n = nullptr, *d_lvl_n = nullptr, *d_slot = nullptr;
-    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr, *d_fast_tiles = nullptr, *d_desc_blocks = nullptr, *d_blur_tiles = nullptr;
+    int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr, *d_desc_blocks = nullptr, *d_blur_tiles = nullptr;
     int desc_blocks = 0;
     float *d_lvl_angle = nullptr;
     orbx_kp *d_out_kp = nullptr;
     orbx_image_params *d_params = nullptr;
     float *d_st_uright = nullptr, *d_st_depth = nullptr;   // ComputeStereoMatches outputs (allocated on first use)
     int *d_st_sad = nullptr, *d_st_kept = nullptr;
+    FastTile *d_fast_tiles = nullptr;
+    FastStats *d_fast_stats = nullptr;                     // k_fast counters, accumulated while profiling is on
     // pinned staging
     uint8_t *h_in = nullptr;
     orbx_image_params *h_params = nullptr;
     int *h_nfeat = nullptr;
 };
+
+// k_fast is compiled for the shared-memory row pitches a geometry can ask for: 16 x odd bytes up to 336
+typedef void (*fast_kernel_t)(const uint8_t *, const FastTile *, const FastArgs, const orbx_image_params *, uint32_t *, int *, const FastMaps, FastStats *);
+static const int kFastPitches[] = {80, 112, 144, 176, 208, 240, 272, 304, 336};
+static int fast_pitch_for(int need) {
+    for (int p : kFastPitches) if (p >= need) return p;
+    return 0;
+}
+static fast_kernel_t fast_kernel(int ip) {
+    switch (ip) {
+        case 80: return k_fast<80>;
+        case 112: return k_fast<112>;
+        case 144: return k_fast<144>;
+        case 176: return k_fast<176>;
+        case 208: return k_fast<208>;
+        case 240: return k_fast<240>;
+        case 272: return k_fast<272>;
+        case 304: return k_fast<304>;
+        default: return k_fast<336>;
+    }
+}
 
 static int build_geometry(orbx_extractor *ex, int fma_mode) {
     Geom &G = ex->G;
@@ -162,22 +185,28 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     }
     G.total_cells = cell_base; G.cand_per_image = cand_off; G.kp_per_image = kp_off; G.out_cap = kp_off;
     ex->pyr_bytes_per_batch = plane_off;
-    // FAST tiles: fast_g adjacent cells of a cell row per CTA
-    // entries of the survivor queue pack (row, column) into 16 bits: the staged tile must be at most 512 columns wide
-    G.fast_g = std::max(1, std::min(kFastMaxG, (512 - 68) / std::max(1, max_cell_w - 6)));
-    if (const char *t = getenv("ORBX_FAST_G")) G.fast_g = std::max(1, std::min(G.fast_g, atoi(t)));   // tuning knob
+    // FAST tiles: up to kFastMaxG adjacent cells of a cell row per CTA (one warp per cell).  The shared-memory row pitch is a template
+    // constant of k_fast: 16 x odd bytes (strips of 7 rows then start in different banks), sized for level 0's cells; levels whose
+    // cells are wider (ceil() makes the small levels' cells a few pixels wider) put fewer cells into a tile.
+    int want_g = kFastMaxG;
+    if (const char *t = getenv("ORBX_FAST_G")) want_g = std::max(1, std::min(want_g, atoi(t)));   // tuning knob
+    G.fast_g = want_g;
+    G.fast_ip = fast_pitch_for(want_g * G.lv[0].w_cell + 36);
+    if (G.fast_ip == 0) { G.fast_g = 1; G.fast_ip = fast_pitch_for(max_cell_w - 6 + 36); }
+    if (G.fast_ip == 0) return fail(ORBX_ERR_INVALID, "FAST cells wider than 300 px are not supported");
     int ftiles = 0;
     for (int l = 0; l < nl; l++) {
         LevelGeom &L = G.lv[l];
-        L.fast_tiles_x = (L.n_cols + G.fast_g - 1) / G.fast_g;
+        const int g = std::max(1, std::min(G.fast_g, (G.fast_ip - 36) / L.w_cell));
+        if (L.w_cell + 36 > G.fast_ip) return fail(ORBX_ERR_INVALID, "FAST cell does not fit the tile pitch");
+        L.fast_tiles_x = (L.n_cols + g - 1) / g;
         L.fast_tile_base = ftiles;
         ftiles += L.fast_tiles_x * L.n_rows;
     }
     G.fast_total_tiles = ftiles;
     G.fast_ymax = max_cell_h - 6;
-    G.fast_ip = (std::min(G.fast_g, 64) * (max_cell_w - 6) + 21 + 15 + 31) & ~31;
     ex->fast_smem = fast_smem_bytes(G.fast_ip, G.fast_ymax);
-    if (ex->fast_smem > 200 * 1024 || G.fast_ip > (1 << kFastColBits) || G.fast_ymax + 6 >= 128)
+    if (ex->fast_smem > 200 * 1024 || G.fast_ip > 512 || (G.fast_ymax + 6 + kFastStrip) * G.fast_ip > 65535)
         return fail(ORBX_ERR_INVALID, "FAST tile does not fit in shared memory");
     ex->oct_list_cap = max_list;
     ex->oct_smem = oct_work_bytes(max_list);
@@ -220,7 +249,7 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     cudaFree(ex->d_pattern); cudaFree(ex->d_cells); cudaFree(ex->d_lin); cudaFree(ex->d_lvl_kp); cudaFree(ex->d_node);
     cudaFree(ex->d_cell_cnt); cudaFree(ex->d_cell_off); cudaFree(ex->d_lin_n); cudaFree(ex->d_lvl_n); cudaFree(ex->d_slot);
     cudaFree(ex->d_n_kp); cudaFree(ex->d_n_mono); cudaFree(ex->d_nfeat); cudaFree(ex->d_lvl_angle); cudaFree(ex->d_out_kp);
-    cudaFree(ex->d_params); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps); cudaFree(ex->d_desc_blocks); cudaFree(ex->d_blur_tiles);
+    cudaFree(ex->d_params); cudaFree(ex->d_fast_stats); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps); cudaFree(ex->d_desc_blocks); cudaFree(ex->d_blur_tiles);
     cudaFree(ex->d_st_uright); cudaFree(ex->d_st_depth); cudaFree(ex->d_st_sad); cudaFree(ex->d_st_kept);
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_params) cudaFreeHost(ex->h_params);
@@ -340,12 +369,34 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
         if (ex->rsz_smem > 200 * 1024) { orbx_extractor_destroy(ex); return fail(ORBX_ERR_INVALID, "scale factor too large for the resize tile"); }
         EX_CUDA(dalloc(&ex->d_taps, (size_t)ntap));
         EX_CUDA(cudaMemcpy(ex->d_taps, taps.data(), ntap * sizeof(ResizeTap), cudaMemcpyHostToDevice));
-        std::vector<int> tinfo;   // FAST tile -> level | cell row << 4 | tile column << 16
-        for (int l = 0; l < nlevels; l++)
-            for (int i = 0; i < G.lv[l].n_rows; i++)
-                for (int j = 0; j < G.lv[l].fast_tiles_x; j++) tinfo.push_back(l | (i << 4) | (j << 16));
+        std::vector<FastTile> tinfo;   // FAST tiles (CTAs) of one image: a cell row is cut into equal tiles of at most fast_g cells
+        for (int l = 0; l < nlevels; l++) {
+            const LevelGeom &L = G.lv[l];
+            const int cpt = (L.n_cols + L.fast_tiles_x - 1) / L.fast_tiles_x;
+            for (int i = 0; i < L.n_rows; i++)
+                for (int j = 0; j < L.fast_tiles_x; j++) {
+                    FastTile T;
+                    memset(&T, 0, sizeof(T));
+                    const int j0 = j * cpt, j1 = std::min(j0 + cpt, L.n_cols);
+                    T.lvl = l; T.ncell = j1 - j0; T.wc = L.w_cell; T.cell_cap = L.cell_cap;
+                    // tested area of the tile in level coordinates (see the header comment of k_fast)
+                    T.tx0 = kEdge + j0 * L.w_cell; T.ty0 = kEdge + i * L.h_cell;
+                    T.X = std::max(0, std::min(kEdge + j1 * L.w_cell, L.w - kEdge) - T.tx0);
+                    T.Y = std::max(0, std::min(T.ty0 + L.h_cell, L.h - kEdge) - T.ty0);
+                    T.pc0 = (kXO + T.tx0 - 3) & ~15; T.prow0 = kYO + T.ty0 - 3; T.c0 = kXO + T.tx0 - T.pc0;
+                    T.cell0 = L.cell_base + i * L.n_cols + j0;
+                    T.nstr = std::max(1, (T.Y + kFastStrip - 1) / kFastStrip); T.rs = (T.Y + T.nstr - 1) / T.nstr;
+                    const long long cand0 = L.cand_off + (long long)(i * L.n_cols + j0) * L.cell_cap;
+                    T.cand0_lo = (int)(unsigned)(cand0 & 0xFFFFFFFFll); T.cand0_hi = (int)(cand0 >> 32);
+                    T.plane_off = L.plane_off; T.plane_bytes = L.plane_bytes; T.pitch = L.pitch;
+                    tinfo.push_back(T);
+                }
+        }
+        if ((int)tinfo.size() != G.fast_total_tiles) { orbx_extractor_destroy(ex); return fail(ORBX_ERR_INVALID, "internal: FAST tile count"); }
+        EX_CUDA(dalloc(&ex->d_fast_stats, (size_t)1));
+        EX_CUDA(cudaMemset(ex->d_fast_stats, 0, sizeof(FastStats)));
         EX_CUDA(dalloc(&ex->d_fast_tiles, tinfo.size()));
-        EX_CUDA(cudaMemcpy(ex->d_fast_tiles, tinfo.data(), tinfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+        EX_CUDA(cudaMemcpy(ex->d_fast_tiles, tinfo.data(), tinfo.size() * sizeof(FastTile), cudaMemcpyHostToDevice));
         std::vector<int> btiles;   // blur CTA -> level | tile row << 4 | tile column << 16
         for (int l = 0; l < nlevels; l++)
             for (int ty = 0; ty < (G.lv[l].h + kBlurTH - 1) / kBlurTH; ty++)
@@ -374,7 +425,7 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
             return fail(ORBX_ERR_INVALID, "the tiles of this geometry do not fit in the device's shared memory");
         }
         EX_CUDA(cudaFuncSetAttribute(k_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
-        EX_CUDA(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+        EX_CUDA(cudaFuncSetAttribute(fast_kernel(G.fast_ip), cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
         EX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
         EX_CUDA(cudaFuncSetAttribute(k_octree_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
         EX_CUDA(cudaFuncSetAttribute(k_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
@@ -475,6 +526,20 @@ int orbx_extractor_tables(const orbx_extractor *ex, float *scale, float *inv_sca
 int orbx_extractor_set_profiling(orbx_extractor *ex, int enabled) {
     if (!ex) return fail(ORBX_ERR_INVALID, "NULL handle");
     ex->profiling = enabled != 0; ex->have_times = false; ex->prof_calls = 0;
+    if (enabled && ex->d_fast_stats) {
+        ORBX_CUDA(cudaSetDevice(ex->device));
+        ORBX_CUDA(cudaMemsetAsync(ex->d_fast_stats, 0, sizeof(FastStats), ex->stream));
+    }
+    return ORBX_OK;
+}
+
+// FAST counters accumulated over the profiled calls since profiling was switched on: tested pixels, quick-test survivors, corners
+// (score >= threshold), kept after non-max suppression, retried cells (minThFAST), tiles (CTAs).
+int orbx_extractor_fast_stats(orbx_extractor *ex, unsigned long long *out6) {
+    if (!ex || !out6) return fail(ORBX_ERR_INVALID, "NULL argument");
+    ORBX_CUDA(cudaSetDevice(ex->device));
+    ORBX_CUDA(cudaStreamSynchronize(ex->stream));
+    ORBX_CUDA(cudaMemcpy(out6, ex->d_fast_stats, sizeof(FastStats), cudaMemcpyDeviceToHost));
     return ORBX_OK;
 }
 
@@ -511,7 +576,9 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
         launches++;
     }
     if (ev) ORBX_CUDA(cudaEventRecord(ev[2], sA));
-    k_fast<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, G, ex->d_params, ex->d_cells, ex->d_cell_cnt, ex->d_fast_tiles, ex->fast_maps, i0);
+    const FastArgs fa = {G.fast_ymax, G.total_cells, i0, 0, G.cand_per_image};
+    fast_kernel(G.fast_ip)<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, ex->d_fast_tiles, fa, ex->d_params, ex->d_cells, ex->d_cell_cnt, ex->fast_maps,
+                                                                                ex->profiling ? ex->d_fast_stats : nullptr);
     launches++;
     if (overlap) {
         ORBX_CUDA(cudaEventRecord(ex->ev_pyr[lane], sA));                 // (FAST done)

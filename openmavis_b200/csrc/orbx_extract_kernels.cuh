@@ -353,52 +353,61 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
 // the tested area of the SAME cell ROI (outside it the score buffer is 0), so
 //     keypoints of a cell at threshold t  =  { p : S(p) >= t, S(p) > S(q) for the neighbours q of the cell }.
 // The tested areas of the cells tile the level without gaps or overlap, which makes the work regular:
-// one CTA = one tile of up to G adjacent cells of a cell row, staged once in shared memory.
-//   1. quick reject, 4 pixels per thread with byte-SIMD (VABSDIFF4): a corner needs |v - r| > t on at least one
-//      of the ring pixels {0, 8} and one of {4, 12};
-//   2. survivors are compacted into a per-warp queue and scored two at a time with packed u16x2 3-input
-//      min/max (VIMNMX3.U16x2): no divergence, no per-threshold corner test;
-//   3. sparse sweep of the score map: strict 3x3 maximum inside the cell -> keep bitmap;
-//   4. cells without a keypoint repeat 1-3 with minThFAST (block-uniform, rare);
-//   5. one warp per cell emits the kept pixels in row-major order (the order of cv::FAST) from the bitmap.
+// one CTA = one tile of up to G adjacent cells of a cell row, staged once in shared memory, one warp per cell.
+//   0. the tile (4 cells) is staged once (one TMA tensor copy); from then on every WARP works alone on its own cell — no CTA barriers, no
+//      shared counters, no atomics except the keep bitmap words two neighbouring cells share;
+//   1. quick reject with byte-SIMD (VABSDIFF4): a corner needs |v - r| > t on at least one of the ring pixels {0, 8} and one of
+//      {4, 12}.  One lane marches down up to 8 rows of one 4-pixel word column with the column in registers (no index arithmetic
+//      in the loop); the 32 survivor flags of a lane end up in one register;
+//   2. survivors are compacted into the warp's queue (one warp scan per 512 pixels) and scored two at a time with packed
+//      u16x2 3-input min/max (VIMNMX3.U16x2): no divergence, no per-threshold corner test;
+//   3. strict 3x3 maximum inside the cell over the warp's corner list -> keep bitmap;
+//   4. a cell without a keypoint repeats 1-3 with minThFAST (only its own warp, rare);
+//   5. emission in row-major order (the order of cv::FAST): lane = row, 64-bit row masks, one warp scan.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 256;
-constexpr int kFastWarps = kFastThreads / 32;
-constexpr int kFastQueue = 320;               // per-warp survivor queue (u16 entries): < 64 left + up to 256 new
-constexpr int kFastMaxG = 10;
-constexpr int kFastCorners = 3072;            // dense corner list of a tile; a tile with more corners falls back to a sweep
-constexpr int kFastColBits = 9;               // queue / list entry = (img row << 9) | img column  (ip <= 512, rows < 128)
+constexpr int kFastWarps = 4;                 // warps per CTA = cells per tile (one warp per cell)
+constexpr int kFastThreads = kFastWarps * 32;
+constexpr int kFastStrip = 7;                 // rows a lane marches through per work item (one 4-pixel word wide); odd, and the row pitch
+                                              // is 16 x odd bytes, so that the strips of one warp iteration fall into different banks
+constexpr int kFastQueue = 64 + 32 * 16;      // per-warp survivor queue (u16 entries): < 64 left + up to 512 new (half a strip item per lane)
+constexpr int kFastMaxG = kFastWarps;
+constexpr int kFastCorners = 256;             // corner list of one cell (per warp); a cell with more corners falls back to a sweep
+constexpr int kFastMaxY = 64;                 // rows / columns of a cell the fast emission path handles (two rows per lane, 64-bit row masks)
 
-// shared memory of one CTA:
+// One FAST tile (CTA) of an image: up to kFastMaxG adjacent cells of one cell row; built on the host once per handle.
+struct __align__(16) FastTile {
+    int lvl, ncell, wc, cell_cap;      // level, cells in this tile, nominal cell width, candidate slots per cell
+    int tx0, ty0, X, Y;                // tested area in level coordinates: x in [tx0, tx0 + X), y in [ty0, ty0 + Y)
+    int pc0, prow0, c0, cell0;         // staged tile: plane column (16-B aligned) and plane row of its corner; smem column of tx0; first cell index
+    int nstr, rs, cand0_lo, cand0_hi;  // strips of rs <= 8 rows; slot offset of the first cell's candidate slots in an image's arena
+    long long plane_off, plane_bytes;  // (cp.async fallback) byte offset of image 0's plane, bytes per plane
+    int pitch, pad0, pad1, pad2;
+};
+
+// shared memory of one CTA (ip = row pitch in bytes, a template constant so that every row offset is an immediate):
 //   img [(ymax + 6)][ip]  level pixels, row 0 = tile row -3, column 0 = plane column pc0 (16-byte aligned)
 //   sc  [(ymax + 2)][ip]  scores, same column indexing, rows 0 and Y+1 stay zero
-//   bm  [ymax][ip / 32]   keep bitmap (rounded up to 16 bytes)
-//   q   [kFastWarps][kFastQueue] u16, cl [kFastCorners] u16, has [kFastMaxG] int, ncl int
-__host__ __device__ inline size_t fast_zero_bytes(int ip, int ymax) { return ((size_t)(ymax + 2) * ip + (size_t)ymax * (ip >> 5) * 4 + 15) & ~(size_t)15; }
+//   bm  [ymax][ceil(ip / 32)]   keep bitmap (rounded up to 16 bytes)
+//   q   [kFastWarps][kFastQueue] u16 survivor queues (entries = byte offsets into img), cl [kFastWarps][kFastCorners] u16 corner lists
+__host__ __device__ inline int fast_zero_bytes(int ip, int ymax) { return ((ymax + 2) * ip + ymax * ((ip + 31) >> 5) * 4 + 15) & ~15; }
 __host__ __device__ inline size_t fast_smem_bytes(int ip, int ymax) {
-    return (size_t)(ymax + 6) * ip + fast_zero_bytes(ip, ymax) + (size_t)(kFastWarps * kFastQueue + kFastCorners) * 2 + (kFastMaxG + 4) * sizeof(int);
+    return (size_t)(ymax + 6 + kFastStrip) * ip + fast_zero_bytes(ip, ymax) + (size_t)kFastWarps * (kFastQueue + kFastCorners) * 2;
 }
 
-__device__ __forceinline__ uint32_t bytes_gt(uint32_t ad, uint32_t t1x4) {
-    // per byte: 0x80 where ad > t (t1x4 = (t + 1) * 0x01010101, t <= 126)
-    return (ad | ((ad | 0x80808080u) - t1x4)) & 0x80808080u;
-}
-
-// exact x / d for 0 <= x < 4096, 8 <= d: (x + 0.5) / d is at least 0.5 / d away from an integer, far above fp32 error
+// exact x / d for 0 <= x < 65536, 8 <= d: (x + 0.5) / d is at least 0.5 / d away from an integer, far above fp32 error
 __device__ __forceinline__ int small_div(int x, float inv_d) { return (int)(((float)x + 0.5f) * inv_d); }
 
-// Scores the centre pixels e0 / e1 (queue entries) with packed u16x2 arithmetic, stores S where S >= t and appends those
-// pixels to the tile's corner list.
-__device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *sc1, int ip, int e0, int e1, bool ok0, bool ok1, int t,
-                                                unsigned short *cl, int *ncl, int lane) {
-    const int a0 = (e0 >> kFastColBits) * ip + (e0 & ((1 << kFastColBits) - 1));
-    const int a1 = (e1 >> kFastColBits) * ip + (e1 & ((1 << kFastColBits) - 1));
+// Scores the centre pixels at img offsets a0 / a1 (queue entries) with packed u16x2 arithmetic, stores S where S >= t and
+// appends those pixels to the warp's corner list (ncl = warp-uniform fill level).  scb[a] is the score of the pixel at img offset a.
+template <int IP>
+__device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *scb, int a0, int a1, bool ok0, bool ok1, int t,
+                                                unsigned short *cl, int &ncl, unsigned lt_mask) {
     const uint8_t *p0 = img + a0, *p1 = img + a1;
-    const int o[16] = {3 * ip, 3 * ip + 1, 2 * ip + 2, ip + 3, 3, -ip + 3, -2 * ip + 2, -3 * ip + 1,
-                       -3 * ip, -3 * ip - 1, -2 * ip - 2, -ip - 3, -3, ip - 3, 2 * ip - 2, 3 * ip - 1};
+    constexpr int o[16] = {3 * IP, 3 * IP + 1, 2 * IP + 2, IP + 3, 3, -IP + 3, -2 * IP + 2, -3 * IP + 1,
+                           -3 * IP, -3 * IP - 1, -2 * IP - 2, -IP - 3, -3, IP - 3, 2 * IP - 2, 3 * IP - 1};
     uint32_t r[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) r[k] = (uint32_t)p0[o[k]] | ((uint32_t)p1[o[k]] << 16);
+    for (int k = 0; k < 16; k++) r[k] = __byte_perm((uint32_t)p0[o[k]], (uint32_t)p1[o[k]], 0x7470);
     uint32_t mx3[16], mn3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -415,265 +424,303 @@ __device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *sc1
         const uint32_t y1 = __vimin3_u16x2(mn3[k + 1], mn3[(k + 4) & 15], mn3[(k + 7) & 15]);
         B = __vimax3_u16x2(B, y0, y1);
     }
+    // S = max(v - A, B - v) - 1 for both halves at once: v - A and B - v never wrap when they matter (A <= v or B >= v for a corner),
+    // a wrapped half is > 255 as u16 only if it was negative, in which case the other term or the threshold test discards it
     const int v0 = p0[0], v1 = p1[0];
     const int s0 = max(v0 - (int)(A & 0xFFFFu), (int)(B & 0xFFFFu) - v0) - 1;
     const int s1 = max(v1 - (int)(A >> 16), (int)(B >> 16) - v1) - 1;
     const bool c0 = ok0 && s0 >= t, c1 = ok1 && s1 >= t;
-    // score map: same column indexing as img, tile row = img row - 3
-    if (c0) sc1[a0 - 3 * ip] = (uint8_t)s0;
-    if (c1) sc1[a1 - 3 * ip] = (uint8_t)s1;
+    if (c0) scb[a0] = (uint8_t)s0;
+    if (c1) scb[a1] = (uint8_t)s1;
     const unsigned b0 = __ballot_sync(0xFFFFFFFFu, c0), b1 = __ballot_sync(0xFFFFFFFFu, c1);
-    const int n0 = __popc(b0), n = n0 + __popc(b1);
-    if (n) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(ncl, n);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        const unsigned lm = (1u << lane) - 1;
-        if (c0) { const int p = base + __popc(b0 & lm); if (p < kFastCorners) cl[p] = (unsigned short)e0; }
-        if (c1) { const int p = base + n0 + __popc(b1 & lm); if (p < kFastCorners) cl[p] = (unsigned short)e1; }
-    }
+    const int n0 = __popc(b0);
+    if (c0) { const int p = ncl + __popc(b0 & lt_mask); if (p < kFastCorners) cl[p] = (unsigned short)a0; }
+    if (c1) { const int p = ncl + n0 + __popc(b1 & lt_mask); if (p < kFastCorners) cl[p] = (unsigned short)a1; }
+    ncl += n0 + __popc(b1);
 }
 
-// strict 3x3 maximum of the score at (tile row, img column) inside its cell -> keep bitmap
-__device__ __forceinline__ void fast_nms_one(const uint8_t *sc1, uint32_t *bm, int *has, int ip, int bw, int row, int col, int c0,
-                                             int wc, float inv_wc, unsigned retry) {
-    const uint8_t *n = sc1 + row * ip + col;
+// strict 3x3 maximum of the score at (tile row, img column) inside its cell (columns [cx0, cx0 + wc)) -> keep bitmap
+template <int IP>
+__device__ __forceinline__ bool fast_nms_one(const uint8_t *sc1, uint32_t *bm, int row, int col, int cx0, int wc) {
+    const uint8_t *n = sc1 + row * IP + col;
     const int s = n[0];
-    const int xt = col - c0;
-    const int cj = small_div(xt, inv_wc), xl = xt - cj * wc;
-    if (retry && !((retry >> cj) & 1u)) return;
-    bool keep = s > n[-ip] && s > n[ip];
-    if (xl > 0) keep = keep && s > n[-1] && s > n[-ip - 1] && s > n[ip - 1];
-    if (xl < wc - 1) keep = keep && s > n[1] && s > n[-ip + 1] && s > n[ip + 1];
-    if (keep) {
-        atomicOr(&bm[row * bw + (col >> 5)], 1u << (col & 31));
-        has[cj] = 1;
-    }
+    const int xl = col - cx0;
+    // all eight neighbours are loaded before the first compare (independent loads instead of a short-circuit chain)
+    const int u = n[-IP], d = n[IP], l = n[-1], ul = n[-IP - 1], dl = n[IP - 1], r = n[1], ur = n[-IP + 1], dr = n[IP + 1];
+    const int ml = xl > 0 ? max(l, max(ul, dl)) : -1, mr = xl < wc - 1 ? max(r, max(ur, dr)) : -1;
+    const bool keep = s > max(max(u, d), max(ml, mr));
+    if (keep) atomicOr(&bm[row * ((IP + 31) >> 5) + (col >> 5)], 1u << (col & 31));
+    return keep;
 }
 
 // pyramid levels as TMA tensors of 16-bit elements for the FAST tiles: dims (pitch / 2, plane rows, images), box = (fast_ip / 2, fast_ymax + 6, 1)
 struct FastMaps { CUtensorMap m[kMaxLevels]; int use_tma; };
 
-__global__ void __launch_bounds__(kFastThreads, 4) k_fast(const uint8_t *__restrict__ pyr, Geom G,
+// optional per-launch statistics (profiling mode only): tested pixels, quick-test survivors, corners, kept after NMS, retried cells, tiles
+struct FastStats { unsigned long long tested, survivors, corners, kept, retry_cells, tiles; };
+
+struct FastArgs { int ymax, total_cells, img0, pad; long long cand_per_image; };
+
+template <int IP>
+__global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restrict__ pyr, const FastTile *__restrict__ tiles, const FastArgs A,
                                                        const orbx_image_params *__restrict__ params,
                                                        uint32_t *__restrict__ cells, int *__restrict__ cell_cnt,
-                                                       const int *__restrict__ tile_info, const __grid_constant__ FastMaps maps, int img0) {
+                                                       const __grid_constant__ FastMaps maps, FastStats *__restrict__ stats) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int b = blockIdx.y + img0;
-    const int info = __ldg(tile_info + blockIdx.x);          // level | cell row << 4 | tile column << 16
-    const LevelGeom &L = G.lv[info & 15];
-    const int ci = (info >> 4) & 0xFFF, jt = info >> 16;
-    const int j0 = jt * G.fast_g, j1 = min(j0 + G.fast_g, L.n_cols);
-    const int ncell = j1 - j0;
-    const int wc = L.w_cell;
-    const float inv_wc = 1.0f / (float)wc;
-    // tested area of the tile in level coordinates (see the header comment of this kernel)
-    const int tx0 = kEdge + j0 * wc, tx1 = min(kEdge + j1 * wc, L.w - kEdge);
-    const int ty0 = kEdge + ci * L.h_cell, ty1 = min(ty0 + L.h_cell, L.h - kEdge);
-    int *cnt_out = cell_cnt + (long long)b * G.total_cells + L.cell_base + ci * L.n_cols + j0;
+    constexpr int bw = (IP + 31) >> 5;
+    const int b = blockIdx.y + A.img0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tx1 <= tx0 || ty1 <= ty0) {
-        if (tid < ncell) cnt_out[tid] = 0;
+    // tile descriptor: the same for every thread (broadcast loads)
+    const int4 *tp = reinterpret_cast<const int4 *>(tiles + blockIdx.x);
+    const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
+    const int lvl = t0.x, ncell = t0.y, wc = t0.z, cell_cap = t0.w;
+    const int tx0 = t1.x, ty0 = t1.y, X = t1.z, Y = t1.w;
+    const int pc0 = t2.x, prow0 = t2.y, c0 = t2.z, cell0 = t2.w;
+    const int nstr = t3.x, rs = t3.y;
+    if (X <= 0 || Y <= 0) {                              // nothing to test (degenerate last cell row / column)
+        if (tid < ncell) cell_cnt[(long long)b * A.total_cells + cell0 + tid] = 0;
         return;
     }
-    const int X = tx1 - tx0, Y = ty1 - ty0;
-    const int ip = G.fast_ip, bw = ip >> 5;
+    const int img_bytes = IP * (A.ymax + 6), zero_bytes = fast_zero_bytes(IP, A.ymax);
     uint8_t *img = smem;
-    uint8_t *sc = img + (size_t)ip * (G.fast_ymax + 6);
-    uint32_t *bm = reinterpret_cast<uint32_t *>(sc + (size_t)ip * (G.fast_ymax + 2));
-    unsigned short *q0 = reinterpret_cast<unsigned short *>(sc + fast_zero_bytes(ip, G.fast_ymax));
-    unsigned short *q = q0 + wid * kFastQueue;
-    unsigned short *cl = q0 + kFastWarps * kFastQueue;
-    int *has = reinterpret_cast<int *>(cl + kFastCorners);
-    int *ncl = has + kFastMaxG;
-    // ---- stage the tile: plane rows kYO + ty0 - 3 .. kYO + ty1 + 3, 16-byte columns from pc0
-    const int pc0 = (kXO + tx0 - 3) & ~15;
-    const int c0 = kXO + tx0 - pc0;                 // smem column of level column tx0 (>= 3)
-    const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
-    __shared__ int s_qn[kFastWarps];                      // fill level of each warp's survivor queue
-    int *qcnt = &s_qn[wid];
+    uint8_t *sc = img + img_bytes + kFastStrip * IP;      // (the quick test may read up to 8 rows past the staged ones; their flags are masked)
+    uint32_t *bm = reinterpret_cast<uint32_t *>(sc + IP * (A.ymax + 2));
+    unsigned short *q = reinterpret_cast<unsigned short *>(sc + zero_bytes) + wid * kFastQueue;
+    unsigned short *cl = reinterpret_cast<unsigned short *>(sc + zero_bytes) + kFastWarps * kFastQueue + wid * kFastCorners;
+    // ---- stage the tile: plane rows prow0 .. prow0 + Y + 5, 16-byte columns from pc0
     __shared__ __align__(8) uint64_t s_bar;
     if (maps.use_tma) {
-        // ONE TMA tensor copy stages the tile (box = fast_ip x (fast_ymax + 6) from plane column pc0, row kYO + ty0 - 3; what lies
+        // ONE TMA tensor copy stages the tile (box = fast_ip x (fast_ymax + 6) from plane column pc0, row prow0; what lies
         // beyond the columns / rows this tile needs is harmless), in flight while the CTA clears the score map
         if (tid == 0) mbar_init(&s_bar, 1);
         __syncthreads();
         if (tid == 0) {
-            mbar_arrive_expect_tx(&s_bar, (uint32_t)(ip * (G.fast_ymax + 6)));
-            tma_load_3d(img, &maps.m[info & 15], pc0 >> 1, kYO + ty0 - 3, b, &s_bar);   // x in 16-bit elements
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)img_bytes);
+            tma_load_3d(img, &maps.m[lvl], pc0 >> 1, prow0, b, &s_bar);   // x in 16-bit elements
         }
-    } else if (lane < nvec) {
+    } else {
         // 16-byte cp.async (LDGSTS) copies.  (One TMA bulk copy per tile ROW was measured slower than this: ~190 small requests
         // per tile time saturate the SM's TMA unit; one tensor copy per TILE is faster than both.)
-        const uint8_t *src = plane_ptr(pyr, L, b) + (long long)(kYO + ty0 - 3) * L.pitch + pc0 + 16 * lane;
-        const uint32_t dst = smem_u32(img) + 16 * lane;
-        for (int r = wid; r < Y + 6; r += kFastWarps)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * ip), "l"(src + (long long)r * L.pitch) : "memory");
+        const int4 t4 = __ldg(tp + 4), t5 = __ldg(tp + 5);
+        const long long plane_off = ((long long)(unsigned)t4.x) | ((long long)t4.y << 32), plane_bytes = ((long long)(unsigned)t4.z) | ((long long)t4.w << 32);
+        const int pitch = t5.x;
+        const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
+        if (lane < nvec) {
+            const uint8_t *src = pyr + plane_off + (long long)b * plane_bytes + (long long)prow0 * pitch + pc0 + 16 * lane;
+            const uint32_t dst = smem_u32(img) + 16 * lane;
+            for (int r = wid; r < Y + 6; r += kFastWarps)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * IP), "l"(src + (long long)r * pitch) : "memory");
+        }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     {
         uint4 *z = reinterpret_cast<uint4 *>(sc);             // score map and bitmap are contiguous
-        const int nz = (int)(fast_zero_bytes(ip, G.fast_ymax) >> 4);
+        const int nz = zero_bytes >> 4;
         for (int i = tid; i < nz; i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
-        if (tid < kFastMaxG) has[tid] = 0;
-        if (tid == 0) *ncl = 0;
-        if (lane == 0) s_qn[wid] = 0;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (maps.use_tma && tid < 32) mbar_wait(&s_bar, 0);
     __syncthreads();
-    const orbx_image_params prm = params[b];
-    const int t_ini = min(max(prm.ini_th_fast, 0), 255), t_min = min(max(prm.min_th_fast, 0), 255);
-    const int w0 = c0 >> 2, w1 = (c0 + X - 1) >> 2;    // words of a row that hold tested pixels
-    const int nw = w1 - w0 + 1;
-    const float inv_nw = 1.0f / (float)nw;
-    // the quick test walks aligned word pairs (8 pixels per lane)
-    const int p0w = w0 & ~1, nw2 = ((w1 | 1) - p0w + 1) >> 1, items2 = Y * nw2;
-    const float inv_nw2 = 1.0f / (float)nw2;
-    unsigned retry = 0;                                 // cells (bit k = cell j0 + k) processed in this pass; 0 = all
-    uint8_t *sc1 = sc + ip;                             // score row of tile row 0
-    const int items = Y * nw;
-    for (int pass = 0; pass < 2; pass++) {
-        const int t = pass == 0 ? t_ini : t_min;
-        const uint32_t t1x4 = (uint32_t)(min(t, 126) + 1) * 0x01010101u;
-        // ---- 1 + 2: quick reject and pair scoring, warp-local.  One lane = 8 consecutive pixels (an aligned word pair).
-        for (int it0 = wid * 32; it0 < items2; it0 += kFastWarps * 32) {
-            const int it = it0 + lane;
-            uint32_t m8 = 0;                               // bit k = pixel k of the pair survives
-            int row = 0, wi = 0;
-            if (it < items2) {
-                row = small_div(it, inv_nw2); wi = p0w + 2 * (it - row * nw2);
-                const uint8_t *cr = img + (row + 3) * ip + 4 * wi;
-                const uint2 v = *reinterpret_cast<const uint2 *>(cr);
-                const uint32_t pv = *reinterpret_cast<const uint32_t *>(cr - 4), nx = *reinterpret_cast<const uint32_t *>(cr + 8);
-                const uint2 up = *reinterpret_cast<const uint2 *>(cr - 3 * ip), dn = *reinterpret_cast<const uint2 *>(cr + 3 * ip);
-                const uint32_t lf0 = __byte_perm(pv, v.x, 0x4321), rt0 = __byte_perm(v.x, v.y, 0x6543);
-                const uint32_t lf1 = __byte_perm(v.x, v.y, 0x4321), rt1 = __byte_perm(v.y, nx, 0x6543);
-                uint32_t m0 = (bytes_gt(__vabsdiffu4(v.x, up.x), t1x4) | bytes_gt(__vabsdiffu4(v.x, dn.x), t1x4)) &
-                              (bytes_gt(__vabsdiffu4(v.x, lf0), t1x4) | bytes_gt(__vabsdiffu4(v.x, rt0), t1x4));
-                uint32_t m1 = (bytes_gt(__vabsdiffu4(v.y, up.y), t1x4) | bytes_gt(__vabsdiffu4(v.y, dn.y), t1x4)) &
-                              (bytes_gt(__vabsdiffu4(v.y, lf1), t1x4) | bytes_gt(__vabsdiffu4(v.y, rt1), t1x4));
-                // gather the 0x80 flags of the 8 bytes into 8 bits
-                m8 = ((m0 >> 7) * 0x00204081u >> 21 & 0xFu) | (((m1 >> 7) * 0x00204081u >> 21 & 0xFu) << 4);
-                // pixels left / right of the tested columns
-                const int first = c0 - 4 * wi, last = c0 + X - 1 - 4 * wi;     // valid bit range [first, last]
-                if (first > 0) m8 &= 0xFFu << first;
-                if (last < 7) m8 &= 0xFFu >> (7 - last);
-                if (retry) {                               // second pass: only the cells that are retried
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int xt = min(max(4 * wi + k - c0, 0), X - 1);
-                        if (!((retry >> small_div(xt, inv_wc)) & 1u)) m8 &= ~(1u << k);
-                    }
-                }
-            }
-            // append the survivors to the warp queue (order inside the queue is irrelevant).  Each lane reserves its slots with one
-            // shared-memory atomic on the warp's counter: the kernel is issue-bound, so one ATOMS (serialised in the LSU, not in the
-            // issue stage) is cheaper than a ballot/popc prefix over the lane counts.
-            const int cnt = __popc(m8);
-            int pos = 0;
-            if (cnt) pos = atomicAdd(qcnt, cnt);
-            const int ebase = ((row + 3) << kFastColBits) | (4 * wi);
-            while (m8) {
-                const int k = __ffs(m8) - 1;
-                m8 &= m8 - 1;
-                q[pos++] = (unsigned short)(ebase + k);
-            }
-            __syncwarp();
-            int qn = *reinterpret_cast<volatile int *>(qcnt);
-            if (qn >= 64) {
-                do {
-                    qn -= 64;
-                    fast_score_pair(img, sc1, ip, q[qn + lane], q[qn + 32 + lane], true, true, t, cl, ncl, lane);
-                } while (qn >= 64);
-                __syncwarp();
-                if (lane == 0) *qcnt = qn;
-                __syncwarp();
-            }
-        }
-        {
-            const int qn = *reinterpret_cast<volatile int *>(qcnt);
-            if (qn > 0) {
-                const bool ok0 = lane < qn, ok1 = lane + 32 < qn;
-                fast_score_pair(img, sc1, ip, q[ok0 ? lane : 0], q[ok1 ? lane + 32 : 0], ok0, ok1, t, cl, ncl, lane);
-            }
-            __syncwarp();
-            if (lane == 0) *qcnt = 0;
-        }
-        __syncthreads();
-        // ---- 3: strict 3x3 maximum inside the cell, over the dense corner list (or a sweep of the score map if it overflowed)
-        const int nc = *ncl;
-        if (nc <= kFastCorners) {
-            for (int i = tid; i < nc; i += kFastThreads) {
-                const int e = cl[i];
-                fast_nms_one(sc1, bm, has, ip, bw, (e >> kFastColBits) - 3, e & ((1 << kFastColBits) - 1), c0, wc, inv_wc, retry);
-            }
-        } else {
-            for (int it = tid; it < items; it += kFastThreads) {
-                const int row = small_div(it, inv_nw), wi = w0 + (it - row * nw);
-                const uint32_t wv = *(reinterpret_cast<const uint32_t *>(sc1 + row * ip) + wi);
-                if (wv == 0) continue;
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if ((wv >> (8 * k)) & 0xFF) fast_nms_one(sc1, bm, has, ip, bw, row, 4 * wi + k, c0, wc, inv_wc, retry);
-            }
-        }
-        __syncthreads();
-        // ---- 4: cells that found nothing are repeated with minThFAST (src/ORBextractor.cc:760-782)
-        if (pass == 0) {
-            retry = 0;
-            for (int k = 0; k < ncell; k++) if (!has[k]) retry |= 1u << k;
-            if (retry == 0 || t_min >= t_ini) break;
-            __syncthreads();
-            if (tid == 0) *ncl = 0;
-            __syncthreads();
-        }
-    }
-    // ---- 5: one warp per cell, one lane per row: row-major emission (the order of cv::FAST) from the keep bitmap
+    // ---- from here on every warp works alone on its own cells: quick test -> queue -> scores -> NMS -> (retry) -> emission.
+    //      Cells only share the read-only image tile; scores and keep bits of a cell are written and read by its warp only.
+    const int t_ini = min(max(__ldg(&params[b].ini_th_fast), 0), 255), t_min = min(max(__ldg(&params[b].min_th_fast), 0), 255);
+    uint8_t *sc1 = sc + IP;                             // score row of tile row 0
+    uint8_t *scb = sc - 2 * IP;                         // scb[img offset] = score of that pixel (img row = tile row + 3)
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long st_surv = 0, st_corn = 0, st_kept = 0, st_retry = 0;
     for (int k = wid; k < ncell; k += kFastWarps) {
-        const int cx0 = c0 + k * wc, cx1 = min(cx0 + wc, c0 + X);    // smem columns of the cell
-        int total = 0;
-        if (cx1 > cx0 && has[k]) {
-            uint32_t *out = cells + (long long)b * G.cand_per_image + L.cand_off + (long long)(ci * L.n_cols + j0 + k) * L.cell_cap;
-            const int wa = cx0 >> 5, nwords = ((cx1 - 1) >> 5) - wa + 1;          // a cell spans at most 4 bitmap words
-            const uint32_t m_lo = 0xFFFFFFFFu << (cx0 & 31), m_hi = (cx1 & 31) ? (1u << (cx1 & 31)) - 1 : 0xFFFFFFFFu;
-            for (int r0 = 0; r0 < Y; r0 += 32) {
-                const int row = r0 + lane;
-                uint32_t bits[4] = {0, 0, 0, 0};
-                int n = 0;
-                if (row < Y) {
+        int *cnt_out = cell_cnt + (long long)b * A.total_cells + cell0 + k;
+        const int cx0 = c0 + k * wc, cx1 = min(cx0 + wc, c0 + X);   // smem columns of the cell's tested pixels
+        if (cx1 <= cx0) { if (lane == 0) *cnt_out = 0; continue; }
+        const int w0 = cx0 >> 2, w1 = (cx1 - 1) >> 2;   // words of a row that hold tested pixels of this cell
+        const int nw = w1 - w0 + 1;
+        const float inv_nw = 1.0f / (float)nw;
+        const int nflat = nstr * nw;                    // work items: (strip of rs rows) x (word column)
+        bool any_kept = false;
+        for (int pass = 0; pass < 2; pass++) {
+            const int t = pass == 0 ? t_ini : t_min;
+            // per byte: x + cadd has bit 7 set iff x > t for x < 128 (x >= 128 > t is caught by OR-ing x itself, t <= 126).  A carry out
+            // of a byte can only turn |d| == t of the next byte into a survivor: the quick test is a necessary condition, scoring is exact.
+            const uint32_t cadd = (uint32_t)(0x80 - (min(t, 126) + 1)) * 0x01010101u;
+            // ---- 1 + 2: quick reject and pair scoring.  One lane marches down the rs rows of one word column (4 pixels) with the column's
+            //      words in registers; a corner needs |v - r| > t on at least one of the ring pixels {0, 8} (rows +-3) and one of {4, 12}
+            //      (columns +-3).  The survivor flags of the 32 pixels end up in one register (byte = pixel, bit = row).
+            int qn = 0, ncl = 0;                        // fill levels of this warp's queue and corner list (warp-uniform)
+            for (int f0 = 0; f0 < nflat; f0 += 32) {
+                const int f = f0 + lane;
+                uint32_t m = 0;
+                int abase = 0;
+                if (f < nflat) {
+                    const int strip = small_div(f, inv_nw), wi = w0 + (f - strip * nw), r0 = strip * rs;
+                    // pixels of this word that belong to the cell
+                    const int first = max(cx0 - 4 * wi, 0), last = min(cx1 - 1 - 4 * wi, 3);
+                    const uint32_t cm = (0xFFFFFFFFu << (8 * first)) & (0xFFFFFFFFu >> (8 * (3 - last)));
+                    abase = (r0 + 3) * IP + 4 * wi;
+                    const uint8_t *col = img + r0 * IP + 4 * wi;
+                    uint32_t cw[kFastStrip + 6];
 #pragma unroll
-                    for (int w = 0; w < 4; w++)
-                        if (w < nwords) {
-                            uint32_t v = bm[row * bw + wa + w];
-                            if (w == 0) v &= m_lo;
-                            if (w == nwords - 1) v &= m_hi;
-                            bits[w] = v; n += __popc(v);
+                    for (int j = 0; j < kFastStrip + 6; j++) cw[j] = *reinterpret_cast<const uint32_t *>(col + j * IP);
+#pragma unroll
+                    for (int i = 0; i < kFastStrip; i++) {
+                        if (i < rs) {
+                            const uint8_t *cr = col + (i + 3) * IP;
+                            const uint32_t v = cw[i + 3];
+                            const uint32_t pv = *reinterpret_cast<const uint32_t *>(cr - 4), nx = *reinterpret_cast<const uint32_t *>(cr + 4);
+                            const uint32_t dl = __vabsdiffu4(v, __byte_perm(pv, v, 0x4321)), dr = __vabsdiffu4(v, __byte_perm(v, nx, 0x6543));
+                            const uint32_t du = __vabsdiffu4(v, cw[i]), dd = __vabsdiffu4(v, cw[i + 6]);
+                            const uint32_t ud = du | dd | (du + cadd) | (dd + cadd);
+                            const uint32_t lr = dl | dr | (dl + cadd) | (dr + cadd);
+                            m |= ((ud & lr) >> (7 - i)) & (0x01010101u << i);
                         }
+                    }
+                    const int nr = min(rs, Y - r0);
+                    m &= cm & (0x01010101u * ((1u << nr) - 1u));
                 }
-                int inc = n;
+                if (stats) st_surv += __popc(m);
+                // append the survivors to the warp's queue in two halves (rows 0-3, rows 4-6) so that the queue stays small; entries are img
+                // byte offsets, the order inside the queue is irrelevant
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
-                int pos = total + inc - n;
-                total += __shfl_sync(0xFFFFFFFFu, inc, 31);
-                if (n) {
-                    const uint8_t *srow = sc1 + row * ip;
-                    const uint32_t ybits = (uint32_t)(ty0 + row - kFastBorder) << 12;
+                for (int half = 0; half < 2; half++) {
+                    uint32_t mh = m & (half ? 0xF0F0F0F0u : 0x0F0F0F0Fu);
+                    if (!__any_sync(0xFFFFFFFFu, mh != 0)) continue;
+                    const int cnt = __popc(mh);
+                    int inc = cnt;
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {
-                        uint32_t v = bits[w];
-                        while (v) {
-                            const int col = 32 * (wa + w) + __ffs(v) - 1;
-                            v &= v - 1;
-                            // border-relative coordinates (src/ORBextractor.cc:784-791): level coordinate - 16
-                            if (pos < L.cell_cap) out[pos] = (uint32_t)(tx0 + (col - c0) - kFastBorder) | ybits | ((uint32_t)srow[col] << 24);
-                            pos++;
+                    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
+                    unsigned short *qp = q + qn + inc - cnt;
+                    qn += __shfl_sync(0xFFFFFFFFu, inc, 31);
+                    while (mh) {                         // two survivors per trip: the highest and the lowest flag
+                        const int kh = 31 - __clz(mh), kl = __ffs(mh) - 1;
+                        qp[0] = (unsigned short)(abase + (kh & 7) * IP + (kh >> 3));
+                        if (kh != kl) qp[1] = (unsigned short)(abase + (kl & 7) * IP + (kl >> 3));
+                        qp += kh != kl ? 2 : 1;
+                        mh &= ~((1u << kh) | (1u << kl));
+                    }
+                    __syncwarp();
+                    while (qn >= 64) {
+                        qn -= 64;
+                        fast_score_pair<IP>(img, scb, q[qn + lane], q[qn + 32 + lane], true, true, t, cl, ncl, lt_mask);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (qn > 0) {                               // the last, partial round
+                const bool ok0 = lane < qn, ok1 = lane + 32 < qn;
+                fast_score_pair<IP>(img, scb, q[ok0 ? lane : 0], q[ok1 ? lane + 32 : 0], ok0, ok1, t, cl, ncl, lt_mask);
+            }
+            __syncwarp();
+            // ---- 3: strict 3x3 maximum inside the cell, over the corner list (or a sweep of the cell's score map if it overflowed)
+            bool kept = false;
+            if (ncl <= kFastCorners) {
+                for (int i = lane; i < ncl; i += 32) {
+                    const int a = cl[i];
+                    const int ri = a / IP;
+                    kept |= fast_nms_one<IP>(sc1, bm, ri - 3, a - ri * IP, cx0, wc);
+                }
+            } else {
+                const int items = Y * nw;
+                for (int it = lane; it < items; it += 32) {
+                    const int row = small_div(it, inv_nw), wi = w0 + (it - row * nw);
+                    const uint32_t wv = *(reinterpret_cast<const uint32_t *>(sc1 + row * IP) + wi);
+                    if (wv == 0) continue;
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+                        if (((wv >> (8 * kk)) & 0xFF) && 4 * wi + kk >= cx0 && 4 * wi + kk < cx1)
+                            kept |= fast_nms_one<IP>(sc1, bm, row, 4 * wi + kk, cx0, wc);
+                }
+            }
+            any_kept = __any_sync(0xFFFFFFFFu, kept);
+            __syncwarp();
+            if (stats) st_corn += ncl;
+            // ---- 4: a cell that found nothing is repeated with minThFAST (src/ORBextractor.cc:760-782)
+            if (any_kept || t_min >= t_ini) break;
+            if (pass == 0 && stats) st_retry++;
+        }
+        // ---- 5: emission in cv::FAST order (row-major inside the cell) from the keep bitmap: lane = row (two rows per lane)
+        const long long cand0 = ((long long)(unsigned)t3.z) | ((long long)t3.w << 32);
+        uint32_t *out = cells + (long long)b * A.cand_per_image + cand0 + (long long)k * cell_cap;
+        int total = 0;
+        if (any_kept) {
+            const int wdt = cx1 - cx0;
+            if (Y <= kFastMaxY && wdt <= 64) {
+                uint32_t vlo[2], vhi[2];
+                int n[2];
+                const int wa = cx0 >> 5, sh = cx0 & 31;
+                const uint32_t mlo = wdt >= 32 ? 0xFFFFFFFFu : (1u << wdt) - 1u, mhi = wdt >= 64 ? 0xFFFFFFFFu : wdt > 32 ? (1u << (wdt - 32)) - 1u : 0u;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int row = lane + 32 * h;
+                    vlo[h] = vhi[h] = 0;
+                    if (row < Y) {
+                        const uint32_t *br = bm + row * bw;
+                        const uint32_t a = br[wa], b2 = wa + 1 < bw ? br[wa + 1] : 0u, c2 = wa + 2 < bw ? br[wa + 2] : 0u;
+                        vlo[h] = __funnelshift_r(a, b2, sh) & mlo; vhi[h] = __funnelshift_r(b2, c2, sh) & mhi;
+                    }
+                    n[h] = __popc(vlo[h]) + __popc(vhi[h]);
+                }
+                int i0 = n[0], i1 = n[1];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u0 = __shfl_up_sync(0xFFFFFFFFu, i0, o), u1 = __shfl_up_sync(0xFFFFFFFFu, i1, o);
+                    if (lane >= o) { i0 += u0; i1 += u1; }
+                }
+                const int tot0 = __shfl_sync(0xFFFFFFFFu, i0, 31);
+                total = tot0 + __shfl_sync(0xFFFFFFFFu, i1, 31);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (!(vlo[h] | vhi[h])) continue;
+                    const int row = lane + 32 * h;
+                    uint32_t *op = out + (h ? tot0 + i1 - n[1] : i0 - n[0]);
+                    uint32_t *const oend = out + cell_cap;
+                    const uint8_t *srow = sc1 + row * IP + cx0;
+                    // border-relative coordinates (src/ORBextractor.cc:784-791): level coordinate - 16
+                    const uint32_t base = (uint32_t)(tx0 + k * wc - kFastBorder) | ((uint32_t)(ty0 + row - kFastBorder) << 12);
+#pragma unroll
+                    for (int part = 0; part < 2; part++) {
+                        uint32_t vv = part ? vhi[h] : vlo[h];
+                        while (vv) {
+                            const int i = __ffs(vv) - 1 + 32 * part;
+                            vv &= vv - 1;
+                            if (op < oend) *op = (base + (uint32_t)i) | ((uint32_t)srow[i] << 24);
+                            op++;
                         }
+                    }
+                }
+            } else {
+                // general geometry (very tall or wide cells): one lane per row, bit by bit
+                for (int r0 = 0; r0 < Y; r0 += 32) {
+                    const int row = r0 + lane;
+                    int n = 0;
+                    if (row < Y) for (int c = cx0; c < cx1; c++) n += (bm[row * bw + (c >> 5)] >> (c & 31)) & 1u;
+                    int inc = n;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
+                    int pos = total + inc - n;
+                    total += __shfl_sync(0xFFFFFFFFu, inc, 31);
+                    if (n) {
+                        const uint8_t *srow = sc1 + row * IP;
+                        const uint32_t ybits = (uint32_t)(ty0 + row - kFastBorder) << 12;
+                        for (int c = cx0; c < cx1; c++)
+                            if ((bm[row * bw + (c >> 5)] >> (c & 31)) & 1u) {
+                                if (pos < cell_cap) out[pos] = (uint32_t)(tx0 + (c - c0) - kFastBorder) | ybits | ((uint32_t)srow[c] << 24);
+                                pos++;
+                            }
                     }
                 }
             }
         }
-        if (lane == 0) cnt_out[k] = min(total, L.cell_cap);
+        if (lane == 0) *cnt_out = min(total, cell_cap);
+        st_kept += total;
+    }
+    if (stats) {
+        st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 16); st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 8);
+        st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 4); st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 2);
+        st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 1);
+        if (lane == 0) {
+            atomicAdd(&stats->survivors, st_surv); atomicAdd(&stats->corners, st_corn); atomicAdd(&stats->kept, st_kept);
+            atomicAdd(&stats->retry_cells, st_retry);
+        }
+        if (tid == 0) { atomicAdd(&stats->tested, (unsigned long long)X * Y); atomicAdd(&stats->tiles, 1ull); }
     }
 }
 
