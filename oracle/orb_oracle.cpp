@@ -1120,6 +1120,88 @@ int orc_search_for_triangulation(int nn1, const int *nodes1, const int *ptr1, co
 }
 
 
+// ---- ORBmatcher::SearchForTriangulation with every gate of the candidate loop, ORBmatcher.cc:1131-1456 (the variant LocalMapping
+// calls: bCoarse = false, src/LocalMapping.cc:465-468) ---------------------------------------------------------------------------------
+// ncam = 1 (NLeft == -1: monocular / rectified stereo, no mpCamera2), 2 (left + right) or 4 (+ side-left, side-right); camera c of
+// keyframe k owns the feature indices [cam_offk[c], cam_offk[c+1]).  has_mp = GetMapPoint(idx) != NULL; u_right = mvuRight (only read
+// when ncam == 1; NULL = all -1); ep = epipole of KF1's centre in KF2's first camera (:1141-1147); sf2 = pKF2->mvScaleFactors.
+// The reference carries (pCamera1, pCamera2, R12, t12) ACROSS candidates: a camera pair without a branch in :1301-1378 keeps what the
+// previous candidate that got that far had set.  `state` numbers the pairs: 0 = the single pair of the ncam == 1 case (T12, :1156-1160),
+// 1 ll, 2 lr, 3 rl, 4 rr (:1301-1330), 5 l-sl, 6 sl-l, 7 sl-sl, 8 r-sr, 9 sr-r, 10 sr-sr (:1332-1377).  With ncam >= 2 the reference
+// starts with pCamera1/2 = the two left cameras and R12 / t12 UNINITIALISED (:1152-1154): here the initial state is 1 (ll), which is
+// what the reference computes whenever the first candidate that reaches the epipolar test has a branch of its own.
+// pred(idx1, idx2, state, user) stands for pCamera1->epipolarConstrain(pCamera2, kp1, kp2, R12, t12, sigma1, sigma2) (:1380-1387).
+// match12[n1] = idx2 or -1.  Returns nmatches.
+typedef int (*orc_pair_state_pred)(int idx1, int idx2, int state, void *user);
+static int three_maxima_filter(std::vector<int> *rotHist, int *match);
+static int rot_bin(float a1, float a2);
+int orc_search_for_triangulation_full(int ncam, const int *cam_off1, const orc_kp *kps1, const uint8_t *desc1, const uint8_t *has_mp1,
+                                      const float *u_right1, int nn1, const int *nodes1, const int *ptr1, const int *idx1v,
+                                      const int *cam_off2, const orc_kp *kps2, const uint8_t *desc2, const uint8_t *has_mp2,
+                                      const float *u_right2, int nn2, const int *nodes2, const int *ptr2, const int *idx2v, const float *ep,
+                                      const float *sf2, int bOnlyStereo, int bCoarse, int checkOrientation, orc_pair_state_pred pred, void *user,
+                                      int *match12) {
+    const int TH_LOW = 50;
+    const KeyPt *k1 = (const KeyPt *)kps1, *k2 = (const KeyPt *)kps2;
+    const int n1 = cam_off1[ncam];
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    auto cam_of = [&](const int *off, int idx) { int c = 0; while (c + 1 < ncam && idx >= off[c + 1]) c++; return c; };
+    std::vector<int> rotHist[30];
+    int nmatches = 0, a = 0, b = 0;
+    int state = ncam == 1 ? 0 : 1;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int i1 = ptr1[a]; i1 < ptr1[a + 1]; i1++) {
+                const int id1 = idx1v[i1];
+                if (has_mp1[id1]) continue;
+                const bool bStereo1 = ncam == 1 && u_right1 && u_right1[id1] >= 0;     // (!pKF1->mpCamera2 && mvuRight >= 0) :1228
+                if (bOnlyStereo && !bStereo1) continue;
+                const int cam1 = cam_of(cam_off1, id1);
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = ptr2[b]; i2 < ptr2[b + 1]; i2++) {
+                    const int id2 = idx2v[i2];
+                    if (has_mp2[id2]) continue;                                          // vbMatched2 is never set (:1204, 1261)
+                    const bool bStereo2 = ncam == 1 && u_right2 && u_right2[id2] >= 0;
+                    if (bOnlyStereo && !bStereo2) continue;
+                    const int dist = descriptor_distance(desc1 + (size_t)id1 * 32, desc2 + (size_t)id2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const int cam2 = cam_of(cam_off2, id2);
+                    if (!bStereo1 && !bStereo2 && ncam == 1) {                            // :1292-1299
+                        const float distex = ep[0] - k2[id2].x, distey = ep[1] - k2[id2].y;
+                        if (distex * distex + distey * distey < 100 * sf2[k2[id2].octave]) continue;
+                    }
+                    if (ncam >= 2) {                                                      // :1301-1378
+                        if (cam1 == 1 && cam2 == 1) state = 4;
+                        else if (cam1 == 1 && cam2 == 0) state = 3;
+                        else if (cam1 == 0 && cam2 == 1) state = 2;
+                        else if (cam1 == 0 && cam2 == 0) state = 1;
+                        if (ncam >= 4) {
+                            if (cam1 == 0 && cam2 == 2) state = 5;
+                            else if (cam1 == 2 && cam2 == 0) state = 6;
+                            else if (cam1 == 2 && cam2 == 2) state = 7;
+                            else if (cam1 == 1 && cam2 == 3) state = 8;
+                            else if (cam1 == 3 && cam2 == 1) state = 9;
+                            else if (cam1 == 3 && cam2 == 3) state = 10;
+                        }
+                    }
+                    if (bCoarse || pred(id1, id2, state, user)) { bestIdx2 = id2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[id1] = bestIdx2; nmatches++;
+                    if (checkOrientation) rotHist[rot_bin(k1[id1].angle, k2[bestIdx2].angle)].push_back(id1);
+                }
+            }
+            a++; b++;
+        } else if (nodes1[a] < nodes2[b]) {
+            while (a < nn1 && nodes1[a] < nodes2[b]) a++;   // lower_bound
+        } else {
+            while (b < nn2 && nodes2[b] < nodes1[a]) b++;
+        }
+    }
+    if (checkOrientation) nmatches -= three_maxima_filter(rotHist, match12);
+    return nmatches;
+}
+
 // ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), ORBmatcher.cc:349-666, over plain arrays ------------------------
 // FeatureVectors as CSR (sorted node ids, index lists); skipKF[i] = !pMP || pMP->isBad(); angles by feature index; ncamF = 1 for
 // F.Nleft == -1, else 2 / 4 with camOffF = {0, Nleft, Nleft+Nright, +Nsideleft, +Nsideright}.  matchF[nF] = realIdxKF or -1.
@@ -1147,6 +1229,20 @@ static int rot_bin(float a1, float a2) {
     int bin = (int)roundf(rot * factor);
     if (bin == 30) bin = 0;
     return bin;
+}
+
+// ORBmatcher::ComputeThreeMaxima (:2537-2573) on a histogram given by its bin sizes
+void orc_three_maxima(const int *sizes, int L, int *ind3) {
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3v = -1;
+    for (int i = 0; i < L; i++) {
+        const int sz = sizes[i];
+        if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3v = ind2; ind2 = ind1; ind1 = i; }
+        else if (sz > max2) { max3 = max2; max2 = sz; ind3v = ind2; ind2 = i; }
+        else if (sz > max3) { max3 = sz; ind3v = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3v = -1; }
+    else if (max3 < 0.1f * (float)max1) ind3v = -1;
+    ind3[0] = ind1; ind3[1] = ind2; ind3[2] = ind3v;
 }
 
 int orc_search_by_bow_frame(int nnKF, const int *nodesKF, const int *ptrKF, const int *idxKF, int nnF, const int *nodesF, const int *ptrF,

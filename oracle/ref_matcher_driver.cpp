@@ -1,0 +1,256 @@
+// oracle/ref_matcher_driver.cpp — TEST INFRASTRUCTURE.  C entry points around the UNMODIFIED reference class
+// ORB_SLAM3::ORBmatcher (oracle/Makefile compiles /root/reference/src/ORBmatcher.cc against oracle/refstub + oracle/cvshim) and the
+// grid functions of Frame / KeyFrame, whose bodies the Makefile lifts from src/Frame.cc / src/KeyFrame.cc at build time into
+// oracle/_ref/gen/*.inc (included below; never stored in the repo).  Every entry point takes the same flat arrays as the matching
+// orc_* function of oracle/orb_oracle.cpp, builds stub Frame / KeyFrame / MapPoint objects from them and calls the reference's own
+// member function; tests compare reference == oracle == CUDA on the same inputs.
+// Geometry is injected (oracle/refstub/orb_slam3_stubs.h): identity poses and a "pixel camera" (project(X) = (X.x, X.y)), so the
+// projections the reference computes are exactly the numbers the array-level interfaces take as inputs.
+#include <stdint.h>
+#include <string.h>
+
+#include <memory>
+#include <vector>
+
+#include "ORBmatcher.h"
+
+namespace ORB_SLAM3 {
+float Frame::fx = 1, Frame::fy = 1, Frame::cx = 0, Frame::cy = 0, Frame::invfx = 1, Frame::invfy = 1;
+float Frame::mnMinX = 0, Frame::mnMaxX = 0, Frame::mnMinY = 0, Frame::mnMaxY = 0;
+float Frame::mfGridElementWidthInv = 0, Frame::mfGridElementHeightInv = 0;
+// reference bodies, lifted at build time (oracle/Makefile: sed -n '<range>p' of the mounted sources)
+#include "_ref/gen/frame_grid.inc"      // src/Frame.cc:541-582 AssignFeaturesToGrid, :890-967 GetFeaturesInArea, :969-978 PosInGrid
+#include "_ref/gen/keyframe_grid.inc"   // src/KeyFrame.cc:769-834 GetFeaturesInArea
+}  // namespace ORB_SLAM3
+
+using namespace ORB_SLAM3;
+
+namespace {
+
+struct ref_kp { float x, y, size, angle, response; int octave, class_id; };
+
+// project(X) = (X.x, X.y); epipolarConstrain = a deterministic hash of the two keypoints and the two camera ids, so that a test sees
+// WHICH camera pair the reference's carried (pCamera1, pCamera2, R12, t12) state held when it evaluated a candidate
+// (src/ORBmatcher.cc:1301-1390)
+struct PixelCamera : GeometricCamera {
+    int id;
+    explicit PixelCamera(int i) : id(i) {}
+    Eigen::Vector2f project(const Eigen::Vector3f &v) override { return Eigen::Vector2f(v(0), v(1)); }
+    bool epipolarConstrain(GeometricCamera *c2, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const Eigen::Matrix3f &, const Eigen::Vector3f &,
+                           const float, const float) override {
+        return pair_hash(kp1.pt.x, kp1.pt.y, kp2.pt.x, kp2.pt.y, id, static_cast<PixelCamera *>(c2)->id);
+    }
+    static bool pair_hash(float x1, float y1, float x2, float y2, int id1, int id2) {
+        uint32_t a, b, c, d;
+        memcpy(&a, &x1, 4); memcpy(&b, &y1, 4); memcpy(&c, &x2, 4); memcpy(&d, &y2, 4);
+        uint32_t h = a * 0x9E3779B1u ^ b * 0x85EBCA77u ^ c * 0xC2B2AE3Du ^ d * 0x27D4EB2Fu ^ (uint32_t)(id1 * 4 + id2) * 0x165667B1u;
+        h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+        return (h & 3u) != 0;       // three out of four pairs pass
+    }
+};
+
+cv::KeyPoint to_cv(const ref_kp &k) { return cv::KeyPoint(k.x, k.y, k.size, k.angle, k.response, k.octave, k.class_id); }
+
+cv::Mat desc_mat(const uint8_t *d, int n) {
+    cv::Mat m(n, 32, CV_8U);
+    if (n) memcpy(m.data, d, (size_t)n * 32);
+    return m;
+}
+
+void set_bounds(const float *b) {
+    Frame::mnMinX = b[0]; Frame::mnMaxX = b[1]; Frame::mnMinY = b[2]; Frame::mnMaxY = b[3];
+    // src/Frame.cc (constructors): mfGridElementWidthInv = FRAME_GRID_COLS / (mnMaxX - mnMinX), static_cast<float> on both
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+}
+
+// Frame with ncam cameras (1: the Nleft == -1 layout, keypoints in mvKeysUn; 2 / 4: the multi-camera layout)
+void fill_frame(Frame &F, int ncam, const int *cam_off, const ref_kp *kps, const uint8_t *desc, const float *sf, int nsf) {
+    F.N = cam_off[ncam];
+    if (ncam == 1) {
+        F.Nleft = F.Nright = F.Nsideleft = F.Nsideright = -1;
+        for (int i = 0; i < F.N; i++) F.mvKeysUn.push_back(to_cv(kps[i]));
+        F.mvKeys = F.mvKeysUn;
+    } else {
+        F.Nleft = cam_off[1] - cam_off[0]; F.Nright = cam_off[2] - cam_off[1];
+        F.Nsideleft = ncam >= 4 ? cam_off[3] - cam_off[2] : -1; F.Nsideright = ncam >= 4 ? cam_off[4] - cam_off[3] : -1;
+        for (int i = cam_off[0]; i < cam_off[1]; i++) F.mvKeys.push_back(to_cv(kps[i]));
+        for (int i = cam_off[1]; i < cam_off[2]; i++) F.mvKeysRight.push_back(to_cv(kps[i]));
+        if (ncam >= 4) {
+            for (int i = cam_off[2]; i < cam_off[3]; i++) F.mvKeysSideLeft.push_back(to_cv(kps[i]));
+            for (int i = cam_off[3]; i < cam_off[4]; i++) F.mvKeysSideRight.push_back(to_cv(kps[i]));
+        }
+        F.mvKeysUn = F.mvKeys;
+    }
+    F.mDescriptors = desc_mat(desc, F.N);
+    F.mvpMapPoints.assign(F.N, nullptr);
+    F.mvbOutlier.assign(F.N, false);
+    F.mvuRight.assign(F.N, -1.f);
+    F.mvDepth.assign(F.N, -1.f);
+    F.mvScaleFactors.assign(sf, sf + nsf);
+    F.AssignFeaturesToGrid();
+}
+
+class MatcherProbe : public ORBmatcher {
+  public:
+    using ORBmatcher::ORBmatcher;
+    void three_maxima(std::vector<int> *h, int L, int &a, int &b, int &c) { ComputeThreeMaxima(h, L, a, b, c); }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2577-2591)
+int refm_descriptor_distance(const uint8_t *a, const uint8_t *b) {
+    cv::Mat ma(1, 32, CV_8U, (void *)a), mb(1, 32, CV_8U, (void *)b);
+    return ORBmatcher::DescriptorDistance(ma, mb);
+}
+
+// ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:2537-2573) on a histogram given by its bin sizes
+void refm_three_maxima(const int *sizes, int L, int *ind3) {
+    std::vector<std::vector<int>> h(L);
+    for (int i = 0; i < L; i++) h[i].assign(sizes[i], 0);
+    MatcherProbe m(0.6f, true);
+    ind3[0] = ind3[1] = ind3[2] = -1;
+    m.three_maxima(h.data(), L, ind3[0], ind3[1], ind3[2]);
+}
+
+// Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea (src/Frame.cc:541-582, 890-978) of one camera's keypoints
+int refm_grid_query(const ref_kp *kps, int n, const float *bounds, float x, float y, float r, int minLevel, int maxLevel, int *out, int cap) {
+    set_bounds(bounds);
+    Frame F;
+    const int cam_off[2] = {0, n};
+    const float sf1[1] = {1.f};
+    fill_frame(F, 1, cam_off, kps, std::vector<uint8_t>((size_t)n * 32 + 1).data(), sf1, 1);
+    std::vector<size_t> v = F.GetFeaturesInArea(x, y, r, minLevel, maxLevel);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = (int)v[i];
+    return (int)v.size();
+}
+
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &, th, bFarPoints, thFarPoints) (src/ORBmatcher.cc:23-340); same
+// arrays as orc_search_by_projection, `bounds` = {mnMinX, mnMaxX, mnMinY, mnMaxY} instead of prebuilt grids
+int refm_search_by_projection(int ncam, const int *cam_off, const ref_kp *kps, const uint8_t *desc, const float *bounds, const float *sf, int nsf,
+                              const uint8_t *occupied, const int *l2r, const int *r2l, const float *u_right, int nmp, const uint8_t *in_view,
+                              const float *proj_x, const float *proj_y, const int *level, const float *view_cos, const float *proj_xr,
+                              const float *depth, const uint8_t *bad, const uint8_t *has_obs, const uint8_t *mp_desc, float th, int bFarPoints,
+                              float thFarPoints, float nnratio, int *assigned) {
+    set_bounds(bounds);
+    Frame F;
+    fill_frame(F, ncam, cam_off, kps, desc, sf, nsf);
+    const int N = F.N;
+    MapPoint holder;                     // stands for "a map point with Observations() > 0 already sits here"
+    holder.n_obs = 1;
+    for (int i = 0; i < N; i++) if (occupied[i]) F.mvpMapPoints[i] = &holder;
+    if (ncam >= 2) {
+        F.mvLeftToRightMatch.assign(F.Nleft, -1); F.mvRightToLeftMatch.assign(F.Nright, -1);
+        if (l2r) F.mvLeftToRightMatch.assign(l2r, l2r + F.Nleft);
+        if (r2l) F.mvRightToLeftMatch.assign(r2l, r2l + F.Nright);
+    }
+    if (u_right && ncam == 1) F.mvuRight.assign(u_right, u_right + N);
+    std::vector<MapPoint> mps(nmp);
+    std::vector<MapPoint *> vp(nmp);
+    for (int m = 0; m < nmp; m++) {
+        MapPoint &P = mps[m];
+        P.mbTrackInView = in_view[4 * m] != 0; P.mbTrackInViewR = in_view[4 * m + 1] != 0;
+        P.mbTrackInViewSL = in_view[4 * m + 2] != 0; P.mbTrackInViewSR = in_view[4 * m + 3] != 0;
+        P.mTrackProjX = proj_x[4 * m]; P.mTrackProjXR = ncam == 1 ? (proj_xr ? proj_xr[m] : 0.f) : proj_x[4 * m + 1];
+        P.mTrackProjXSL = proj_x[4 * m + 2]; P.mTrackProjXSR = proj_x[4 * m + 3];
+        P.mTrackProjY = proj_y[4 * m]; P.mTrackProjYR = proj_y[4 * m + 1]; P.mTrackProjYSL = proj_y[4 * m + 2]; P.mTrackProjYSR = proj_y[4 * m + 3];
+        P.mnTrackScaleLevel = level[4 * m]; P.mnTrackScaleLevelR = level[4 * m + 1];
+        P.mnTrackScaleLevelSL = level[4 * m + 2]; P.mnTrackScaleLevelSR = level[4 * m + 3];
+        P.mTrackViewCos = view_cos[4 * m]; P.mTrackViewCosR = view_cos[4 * m + 1];
+        P.mTrackViewCosSL = view_cos[4 * m + 2]; P.mTrackViewCosSR = view_cos[4 * m + 3];
+        P.mTrackDepth = depth ? depth[m] : 0.f;
+        P.bad = bad && bad[m];
+        P.n_obs = has_obs ? has_obs[m] : 1;
+        P.descriptor = desc_mat(mp_desc + (size_t)m * 32, 1);
+        vp[m] = &P;
+    }
+    ORBmatcher matcher(nnratio, true);
+    const int n = matcher.SearchByProjection(F, vp, th, bFarPoints != 0, thFarPoints);
+    for (int i = 0; i < N; i++) {
+        MapPoint *p = F.mvpMapPoints[i];
+        assigned[i] = (p && p != &holder) ? (int)(p - mps.data()) : -1;
+    }
+    return n;
+}
+
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:895-1004); same arrays as orc_search_for_initialization
+int refm_search_for_initialization(const ref_kp *kps1, const uint8_t *desc1, int n1, const ref_kp *kps2, const uint8_t *desc2, int n2,
+                                   const float *bounds, float *vbPrevMatched, int windowSize, float nnratio, int checkOrientation, int *vnMatches12) {
+    set_bounds(bounds);
+    Frame F1, F2;
+    const int o1[2] = {0, n1}, o2[2] = {0, n2};
+    const float sf1[1] = {1.f};
+    fill_frame(F1, 1, o1, kps1, desc1, sf1, 1);
+    fill_frame(F2, 1, o2, kps2, desc2, sf1, 1);
+    std::vector<cv::Point2f> prev(n1);
+    for (int i = 0; i < n1; i++) prev[i] = cv::Point2f(vbPrevMatched[2 * i], vbPrevMatched[2 * i + 1]);
+    std::vector<int> m12;
+    ORBmatcher matcher(nnratio, checkOrientation != 0);
+    const int n = matcher.SearchForInitialization(F1, F2, prev, m12, windowSize);
+    for (int i = 0; i < n1; i++) { vnMatches12[i] = m12[i]; vbPrevMatched[2 * i] = prev[i].x; vbPrevMatched[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:1131-1456).
+// FeatureVectors as CSR (node ids ascending); ncam = 1 (mono / rectified stereo: NLeft == -1), 2 or 4; has_mp[idx] = GetMapPoint(idx)
+// != NULL; u_right (ncam == 1 only, may be NULL = all -1); ep = the epipole the reference computes (pKF2->mpCamera->project(T2w * Cw)):
+// the driver places KF1's camera centre so that the pixel camera projects it to `ep`; sf2 = pKF2->mvScaleFactors.
+// match12[n1] = idx2 or -1 (from vMatchedPairs).  Returns nmatches.
+int refm_search_for_triangulation(int ncam, const int *cam_off1, const ref_kp *kps1, const uint8_t *desc1, const uint8_t *has_mp1, const float *u_right1,
+                                  int nn1, const int *nodes1, const int *ptr1, const int *idx1v, const int *cam_off2, const ref_kp *kps2,
+                                  const uint8_t *desc2, const uint8_t *has_mp2, const float *u_right2, int nn2, const int *nodes2, const int *ptr2,
+                                  const int *idx2v, const float *ep, const float *sf2, int nsf, int bOnlyStereo, int bCoarse, int checkOrientation,
+                                  int *match12) {
+    KeyFrame K1, K2;
+    PixelCamera c1[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
+    PixelCamera c2[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
+    MapPoint holder;
+    auto fill = [&](KeyFrame &K, const int *cam_off, const ref_kp *kps, const uint8_t *desc, const uint8_t *has_mp, const float *u_right, int nn,
+                    const int *nodes, const int *ptr, const int *idxv, PixelCamera *cams) {
+        K.N = cam_off[ncam];
+        if (ncam == 1) {
+            for (int i = 0; i < K.N; i++) K.mvKeysUn.push_back(to_cv(kps[i]));
+            K.mvKeys = K.mvKeysUn;
+        } else {
+            K.NLeft = cam_off[1] - cam_off[0]; K.NRight = cam_off[2] - cam_off[1];
+            K.NSideLeft = ncam >= 4 ? cam_off[3] - cam_off[2] : -1; K.NSideRight = ncam >= 4 ? cam_off[4] - cam_off[3] : -1;
+            for (int i = cam_off[0]; i < cam_off[1]; i++) K.mvKeys.push_back(to_cv(kps[i]));
+            for (int i = cam_off[1]; i < cam_off[2]; i++) K.mvKeysRight.push_back(to_cv(kps[i]));
+            if (ncam >= 4) {
+                for (int i = cam_off[2]; i < cam_off[3]; i++) K.mvKeysSideLeft.push_back(to_cv(kps[i]));
+                for (int i = cam_off[3]; i < cam_off[4]; i++) K.mvKeysSideRight.push_back(to_cv(kps[i]));
+            }
+        }
+        K.mDescriptors = desc_mat(desc, K.N);
+        K.map_points.assign(K.N, nullptr);
+        for (int i = 0; i < K.N; i++) if (has_mp[i]) K.map_points[i] = &holder;
+        K.mvuRight.assign(K.N, -1.f);
+        if (u_right && ncam == 1) K.mvuRight.assign(u_right, u_right + K.N);
+        K.mvScaleFactors.assign(sf2, sf2 + nsf);
+        K.mvLevelSigma2.assign(nsf, 1.f);
+        for (int i = 0; i < nsf; i++) K.mvLevelSigma2[i] = sf2[i] * sf2[i];
+        K.mpCamera = &cams[0];
+        if (ncam >= 2) K.mpCamera2 = &cams[1];
+        if (ncam >= 4) { K.mpCamera3 = &cams[2]; K.mpCamera4 = &cams[3]; }
+        for (int a = 0; a < nn; a++)
+            for (int j = ptr[a]; j < ptr[a + 1]; j++) K.mFeatVec[(unsigned)nodes[a]].push_back((unsigned)idxv[j]);
+    };
+    fill(K1, cam_off1, kps1, desc1, has_mp1, u_right1, nn1, nodes1, ptr1, idx1v, c1);
+    fill(K2, cam_off2, kps2, desc2, has_mp2, u_right2, nn2, nodes2, ptr2, idx2v, c2);
+    // KF2 at the origin; KF1's camera centre Cw = (ep.x, ep.y, 1): T1w = [I | -Cw], so C2 = T2w * Cw = Cw and project(C2) = ep exactly
+    K1.Tcw = Sophus::SE3f(Eigen::Matrix3f::Identity(), Eigen::Vector3f(-ep[0], -ep[1], -1.f));
+    std::vector<std::pair<size_t, size_t>> pairs;
+    ORBmatcher matcher(0.6f, checkOrientation != 0);
+    const int n = matcher.SearchForTriangulation(&K1, &K2, pairs, bOnlyStereo != 0, bCoarse != 0);
+    for (int i = 0; i < K1.N; i++) match12[i] = -1;
+    for (auto &p : pairs) match12[p.first] = (int)p.second;
+    return n;
+}
+
+// the pixel camera's epipolar predicate, for the oracle-side callback of the same test
+int refm_pair_hash(float x1, float y1, float x2, float y2, int id1, int id2) { return PixelCamera::pair_hash(x1, y1, x2, y2, id1, id2) ? 1 : 0; }
+
+}  // extern "C"

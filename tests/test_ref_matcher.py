@@ -1,0 +1,244 @@
+"""oracle/_ref/libref_matcher.so — the reference's OWN src/ORBmatcher.cc (unmodified) plus the grid functions of src/Frame.cc, compiled
+against oracle/refstub (oracle/Makefile) — against the restated oracle (oracle/orb_oracle.cpp) on the same flat arrays.  This pins the
+matcher restatements (selection order, gates, best / second bookkeeping, claims, rotation histogram, carried camera-pair state) to the
+reference's object code.  CPU only; tests/test_gpu_match.py compares the CUDA path with the same oracle functions."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from openmavis_b200.synth import synth_descriptors
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KP = O.KP_DTYPE
+_lib = None
+
+
+def RM():
+    global _lib
+    if _lib is None:
+        so = os.path.join(ROOT, 'oracle', '_ref', 'libref_matcher.so')
+        if not os.path.exists(so):
+            O.ref_lib()                                      # runs make when /root/reference is mounted
+        if not os.path.exists(so):
+            raise RuntimeError('%s is missing and /root/reference is not mounted to build it' % so)
+        O.lib()
+        _lib = C.CDLL(so)
+    return _lib
+
+
+def p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_kps(n, rng, w=640, h=480, levels=8, lattice=None):
+    k = np.zeros(n, KP)
+    if lattice:
+        k['x'] = rng.integers(0, w // lattice, n) * lattice; k['y'] = rng.integers(0, h // lattice, n) * lattice
+    else:
+        k['x'] = rng.uniform(0, w, n).astype(np.float32); k['y'] = rng.uniform(0, h, n).astype(np.float32)
+    k['octave'] = rng.integers(0, levels, n); k['angle'] = rng.uniform(0, 360, n).astype(np.float32)
+    k['size'] = 31; k['class_id'] = -1
+    return k
+
+
+def test_descriptor_distance():
+    a = synth_descriptors(2000, 1); b = synth_descriptors(2000, 2)
+    b[:10] = a[:10]; b[10:20] = ~a[10:20]
+    L = RM()
+    for i in range(2000):
+        assert L.refm_descriptor_distance(p(a[i]), p(b[i])) == O.hamming(a[i], b[i]) == int(np.unpackbits(a[i] ^ b[i]).sum())
+
+
+def test_three_maxima():
+    rng = np.random.default_rng(5)
+    L = RM()
+    O.lib().orc_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    for trial in range(400):
+        sizes = rng.integers(0, [3, 10, 60][trial % 3], 30).astype(np.int32)
+        if trial % 7 == 0:
+            sizes[rng.integers(0, 30, 3)] = sizes.max()       # ties between the maxima
+        a = np.zeros(3, np.int32); b = np.zeros(3, np.int32)
+        L.refm_three_maxima(p(sizes), 30, p(a))
+        O.lib().orc_three_maxima(p(sizes), 30, p(b))
+        assert np.array_equal(a, b), (trial, sizes, a, b)
+
+
+def test_frame_grid_get_features_in_area():
+    rng = np.random.default_rng(6)
+    L = RM()
+    for trial in range(60):
+        n = int(rng.integers(1, 1500))
+        k = make_kps(n, rng, lattice=4 if trial % 3 == 0 else None)
+        bounds = np.array([0, 640, 0, 480], np.float32) if trial % 2 else np.array([-13.5, 655.25, -9.0, 489.75], np.float32)
+        g = O.lib().orc_grid_create(p(k), n, C.c_float(bounds[0]), C.c_float(bounds[1]), C.c_float(bounds[2]), C.c_float(bounds[3]))
+        for qi in range(40):
+            x, y = np.float32(rng.uniform(-30, 670)), np.float32(rng.uniform(-30, 510))
+            r = np.float32(rng.choice([2.5, 4.0, 7.5, 15.0, 42.0, 200.0]))
+            lo, hi = [(-1, -1), (0, 0), (2, 3), (0, 7), (3, -1)][qi % 5]
+            a = np.zeros(n, np.int32); b = np.zeros(n, np.int32)
+            na = L.refm_grid_query(p(k), n, p(bounds), C.c_float(x), C.c_float(y), C.c_float(r), lo, hi, p(a), n)
+            nb = O.lib().orc_grid_query(C.c_void_p(g), p(k), C.c_float(x), C.c_float(y), C.c_float(r), lo, hi, p(b), n)
+            assert na == nb and np.array_equal(a[:na], b[:nb]), (trial, qi)
+        O.lib().orc_grid_destroy(C.c_void_p(g))
+
+
+def sbp_scenario(rng, ncam, nmp, crowded):
+    w, h = 512, 512
+    per = [int(rng.integers(200, 700)) for _ in range(ncam)]
+    cam_off = np.concatenate([[0], np.cumsum(per)]).astype(np.int32)
+    N = int(cam_off[-1])
+    k = make_kps(N, rng, w, h, lattice=8 if crowded else None)
+    desc = synth_descriptors(N, int(rng.integers(1 << 30)))
+    sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+    in_view = (rng.random((nmp, 4)) < np.array([0.9, 0.6, 0.5, 0.5])).astype(np.uint8)
+    src = np.stack([rng.integers(cam_off[min(c, ncam - 1)], cam_off[min(c, ncam - 1) + 1], nmp) for c in range(4)], 1)
+    px = (k['x'][src] + rng.uniform(-3, 3, (nmp, 4))).astype(np.float32); py = (k['y'][src] + rng.uniform(-3, 3, (nmp, 4))).astype(np.float32)
+    lvl = np.clip(k['octave'][src] + rng.integers(0, 2, (nmp, 4)), 0, 7).astype(np.int32)
+    lvl[rng.random((nmp, 4)) < 0.05] = 0
+    vc = rng.choice(np.array([0.9990, 0.99], np.float32), (nmp, 4)).astype(np.float32)
+    md = synth_descriptors(nmp, int(rng.integers(1 << 30)))
+    own = rng.random(nmp) < 0.7
+    md[own] = desc[src[own, 0]] ^ np.packbits(rng.random((int(own.sum()), 256)) < 0.08, axis=1, bitorder='little')
+    if crowded:
+        md[: nmp // 4] = md[0]                               # equal descriptors: ties and claims on the same keypoints
+    occupied = (rng.random(N) < 0.1).astype(np.uint8)
+    l2r = r2l = None
+    if ncam >= 2:
+        nl, nr = per[0], per[1]
+        l2r = np.full(nl, -1, np.int32); r2l = np.full(nr, -1, np.int32)
+        m = min(nl, nr) // 3
+        a = rng.permutation(nl)[:m]; b = rng.permutation(nr)[:m]
+        l2r[a] = b; r2l[b] = a
+    u_right = None; pxr = np.zeros(nmp, np.float32)
+    if ncam == 1:
+        u_right = np.where(rng.random(N) < 0.5, k['x'] - rng.uniform(1, 30, N), -1).astype(np.float32)
+        pxr = (px[:, 0] - rng.uniform(0, 40, nmp)).astype(np.float32)
+    depth = rng.uniform(1, 80, nmp).astype(np.float32)
+    bad = (rng.random(nmp) < 0.05).astype(np.uint8); has_obs = (rng.random(nmp) < 0.9).astype(np.uint8)
+    return dict(ncam=ncam, cam_off=cam_off, k=k, desc=desc, sf=sf, occupied=occupied, l2r=l2r, r2l=r2l, u_right=u_right, nmp=nmp, in_view=in_view,
+                px=px, py=py, lvl=lvl, vc=vc, pxr=pxr, depth=depth, bad=bad, has_obs=has_obs, md=md, bounds=np.array([0, w, 0, h], np.float32))
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+def test_search_by_projection_frame_mappoints(ncam):
+    """SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints), src/ORBmatcher.cc:23-340, incl. the sequential
+    already-claimed rule, the ratio-test `continue` of the MapPoint loop, the camera-0-only th, the rectified-stereo gate (:81-85)
+    and the left/right mirror writes."""
+    rng = np.random.default_rng(100 + ncam)
+    L = RM(); Lo = O.lib()
+    for trial in range(12):
+        S = sbp_scenario(rng, ncam, int(rng.integers(200, 1500)), crowded=trial % 2 == 1)
+        th = float([1.0, 3.0, 6.0][trial % 3]); far = trial % 4 == 3; nnr = 0.8
+        N = int(S['cam_off'][-1])
+        a = np.zeros(N, np.int32); b = np.zeros(N, np.int32)
+        na = L.refm_search_by_projection(ncam, p(S['cam_off']), p(S['k']), p(S['desc']), p(S['bounds']), p(S['sf']), 8, p(S['occupied']), p(S['l2r']),
+                                         p(S['r2l']), p(S['u_right']), S['nmp'], p(S['in_view']), p(S['px']), p(S['py']), p(S['lvl']), p(S['vc']),
+                                         p(S['pxr']), p(S['depth']), p(S['bad']), p(S['has_obs']), p(S['md']), C.c_float(th), int(far),
+                                         C.c_float(40.0), C.c_float(nnr), p(a))
+        grids = (C.c_void_p * ncam)()
+        for c in range(ncam):
+            kc = S['k'][S['cam_off'][c]:S['cam_off'][c + 1]]
+            grids[c] = Lo.orc_grid_create(p(np.ascontiguousarray(kc)), len(kc), C.c_float(0), C.c_float(512), C.c_float(0), C.c_float(512))
+        nb = Lo.orc_search_by_projection(ncam, p(S['cam_off']), p(S['k']), p(S['desc']), grids, p(S['sf']), p(S['occupied']), p(S['l2r']), p(S['r2l']),
+                                         p(S['u_right']), S['nmp'], p(S['in_view']), p(S['px']), p(S['py']), p(S['lvl']), p(S['vc']), p(S['pxr']),
+                                         p(S['depth']), p(S['bad']), p(S['has_obs']), p(S['md']), C.c_float(th), int(far), C.c_float(40.0),
+                                         C.c_float(nnr), p(b))
+        for c in range(ncam):
+            Lo.orc_grid_destroy(C.c_void_p(grids[c]))
+        assert na == nb and na > 20, (trial, na, nb)
+        assert np.array_equal(a, b), (trial, int((a != b).sum()))
+
+
+def test_search_for_initialization():
+    rng = np.random.default_rng(8)
+    L = RM(); Lo = O.lib()
+    for trial in range(20):
+        n1, n2 = int(rng.integers(100, 1500)), int(rng.integers(100, 1500))
+        k2 = make_kps(n2, rng, lattice=6 if trial % 2 else None); k2['octave'][rng.random(n2) < 0.6] = 0
+        d2 = synth_descriptors(n2, 900 + trial)
+        src = rng.integers(0, n2, n1)
+        k1 = k2[src].copy(); k1['x'] += rng.uniform(-6, 6, n1).astype(np.float32); k1['y'] += rng.uniform(-6, 6, n1).astype(np.float32)
+        k1['angle'] = (k1['angle'] + rng.choice([0, 0, 0, 45, 200], n1)) % 360
+        d1 = d2[src] ^ np.packbits(rng.random((n1, 256)) < 0.06, axis=1, bitorder='little')
+        if trial % 3 == 0:
+            d1[: n1 // 3] = d1[0]; d2[: n2 // 3] = d1[0]     # many equal distances: eviction / ownership bookkeeping
+        bounds = np.array([0, 640, 0, 480], np.float32)
+        prev = np.stack([k1['x'], k1['y']], 1).astype(np.float32)
+        for chk in (0, 1):
+            pa, pb = prev.copy(), prev.copy()
+            a = np.zeros(n1, np.int32); b = np.zeros(n1, np.int32)
+            na = L.refm_search_for_initialization(p(k1), p(d1), n1, p(k2), p(d2), n2, p(bounds), p(pa), 10 + 30 * (trial % 2), C.c_float(0.9), chk, p(a))
+            g = Lo.orc_grid_create(p(k2), n2, C.c_float(0), C.c_float(640), C.c_float(0), C.c_float(480))
+            nb = Lo.orc_search_for_initialization(p(k1), p(d1), n1, C.c_void_p(g), p(k2), p(d2), n2, p(pb), 10 + 30 * (trial % 2), C.c_float(0.9), chk, p(b))
+            Lo.orc_grid_destroy(C.c_void_p(g))
+            assert na == nb, (trial, chk, na, nb)
+            assert np.array_equal(a, b) and np.array_equal(pa, pb), (trial, chk)
+
+
+def _feature_vector(desc, nbits=5):
+    node = desc[:, 0].astype(np.int32) & ((1 << nbits) - 1)
+    order = np.argsort(node, kind='stable')
+    nodes, counts = np.unique(node, return_counts=True)
+    return nodes.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), order.astype(np.int32)
+
+
+PRED = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p)
+# camera ids (KF1, KF2) of the carried pair states of orc_search_for_triangulation_full
+STATE_CAMS = {0: (0, 0), 1: (0, 0), 2: (0, 1), 3: (1, 0), 4: (1, 1), 5: (0, 2), 6: (2, 0), 7: (2, 2), 8: (1, 3), 9: (3, 1), 10: (3, 3)}
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+@pytest.mark.parametrize('coarse', [0, 1])
+def test_search_for_triangulation(ncam, coarse):
+    """SearchForTriangulation (src/ORBmatcher.cc:1131-1456) with every gate: bOnlyStereo, the epipole-distance reject of the monocular
+    case, the camera-pair choice whose (pCamera1, pCamera2, R12, t12) is CARRIED across candidates when a pair has no branch, the
+    last-minimum tie rule, the rotation histogram.  The reference's camera is the pixel camera of oracle/ref_matcher_driver.cpp whose
+    epipolarConstrain is a hash of the keypoints and of the two camera ids, i.e. of the carried state."""
+    rng = np.random.default_rng(40 + 10 * ncam + coarse)
+    L = RM(); Lo = O.lib()
+    L.refm_pair_hash.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+    for trial in range(10):
+        per1 = [int(rng.integers(150, 500)) for _ in range(ncam)]; per2 = [int(rng.integers(150, 500)) for _ in range(ncam)]
+        off1 = np.concatenate([[0], np.cumsum(per1)]).astype(np.int32); off2 = np.concatenate([[0], np.cumsum(per2)]).astype(np.int32)
+        n1, n2 = int(off1[-1]), int(off2[-1])
+        k2 = make_kps(n2, rng); d2 = synth_descriptors(n2, 4000 + trial)
+        d2[10:60] = d2[10]                                   # exact duplicates -> last-minimum tie rule
+        src = rng.integers(0, n2, n1)
+        flips = np.packbits(rng.random((n1, 256)) < 0.05, axis=1, bitorder='little'); flips[:, 0] &= 0xE0
+        d1 = d2[src] ^ flips
+        d1[::6] = synth_descriptors(len(d1[::6]), 43 + trial)
+        k1 = make_kps(n1, rng)
+        fv1, fv2 = _feature_vector(d1), _feature_vector(d2)
+        fv1 = (fv1[0][::2].copy(), np.concatenate([[0], np.cumsum(np.diff(fv1[1])[::2])]).astype(np.int32),
+               np.concatenate([fv1[2][fv1[1][i]:fv1[1][i + 1]] for i in range(0, len(fv1[0]), 2)]).astype(np.int32))   # some nodes only in KF2
+        mp1 = (rng.random(n1) < 0.3).astype(np.uint8); mp2 = (rng.random(n2) < 0.3).astype(np.uint8)
+        ur1 = ur2 = None; only_stereo = 0
+        if ncam == 1 and trial % 2 == 1:
+            ur1 = np.where(rng.random(n1) < 0.5, 10.0, -1.0).astype(np.float32); ur2 = np.where(rng.random(n2) < 0.5, 10.0, -1.0).astype(np.float32)
+            only_stereo = int(trial % 4 == 3)
+        ep = k2[['x', 'y']][int(rng.integers(0, n2))]; ep = np.array([ep['x'] + 2.0, ep['y'] - 1.0], np.float32)
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        chk = trial % 2
+        a = np.zeros(n1, np.int32); b = np.zeros(n1, np.int32)
+        na = L.refm_search_for_triangulation(ncam, p(off1), p(k1), p(d1), p(mp1), p(ur1), len(fv1[0]), p(fv1[0]), p(fv1[1]), p(fv1[2]), p(off2), p(k2),
+                                             p(d2), p(mp2), p(ur2), len(fv2[0]), p(fv2[0]), p(fv2[1]), p(fv2[2]), p(ep), p(sf), 8, only_stereo, coarse,
+                                             chk, p(a))
+        states = []
+
+        def pred(i1, i2, state, user):
+            states.append(state)
+            c1, c2 = STATE_CAMS[state]
+            return L.refm_pair_hash(k1['x'][i1], k1['y'][i1], k2['x'][i2], k2['y'][i2], c1, c2)
+        cb = PRED(pred)
+        nb = Lo.orc_search_for_triangulation_full(ncam, p(off1), p(k1), p(d1), p(mp1), p(ur1), len(fv1[0]), p(fv1[0]), p(fv1[1]), p(fv1[2]), p(off2),
+                                                  p(k2), p(d2), p(mp2), p(ur2), len(fv2[0]), p(fv2[0]), p(fv2[1]), p(fv2[2]), p(ep), p(sf),
+                                                  only_stereo, coarse, chk, cb, None, p(b))
+        assert na == nb, (trial, na, nb)
+        assert np.array_equal(a, b), (trial, int((a != b).sum()))
+        if not only_stereo:
+            assert na > 5
+        if ncam == 4 and not coarse:
+            assert len(set(states)) >= 8                      # the scenario exercises the carried camera-pair states
