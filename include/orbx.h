@@ -330,6 +330,43 @@ typedef struct orbx_kb8_stereo {
     float R12[9], t12[3];
     float precision1, precision2;
 } orbx_kb8_stereo;
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:1131-1456), the WHOLE
+ * function incl. bCoarse = false (what LocalMapping::CreateNewMapPoints calls, src/LocalMapping.cc:465-468): descriptor gate, the
+ * epipole-distance reject of the monocular case (:1292-1299), the camera-pair choice whose (pCamera1, pCamera2, R12, t12) is carried
+ * across candidates when a pair of cameras has no branch (:1301-1378), pCamera1->epipolarConstrain (:1380-1387), the last-minimum rule,
+ * the rotation histogram (only with check_orientation).
+ *   ncam            1 (NLeft == -1: monocular / rectified stereo, no mpCamera2), 2 (left + right) or 4 (+ side-left, side-right);
+ *                   camera c of keyframe k owns the feature indices [cam_offk[c], cam_offk[c + 1])
+ *   kpsK / descK    keypoints (pt, octave, angle are read) and descriptors by feature index; has_mpK[idx] = GetMapPoint(idx) != NULL
+ *   u_rightK        mvuRight (only read when ncam == 1; NULL = no stereo observations)
+ *   FeatureVectors  as CSR: ascending node ids, feature index lists in insertion order
+ *   ep              the epipole pKF2->mpCamera->project(T2w * Cw1) (:1141-1147); sf2 = pKF2->mvScaleFactors;
+ *                   sigma2_1 / sigma2_2 = mvLevelSigma2 of the two keyframes; nlevels <= 16
+ *   pairs[11]       the camera pairs the reference prepares (:1156-1198): [0] = T12 of the ncam == 1 case, [1] ll, [2] lr, [3] rl, [4] rr,
+ *                   [5] l-sl, [6] sl-l, [7] sl-sl, [8] r-sr, [9] sr-r, [10] sr-sr.  Pinhole pairs carry F12 = K1^-T [t12]x R12 K2^-1 as
+ *                   Pinhole::epipolarConstrain computes it (src/CameraModels/Pinhole.cpp:112-115; evaluated once per pair by the caller
+ *                   with the reference's own expression); Kannala-Brandt pairs carry the two parameter vectors, R12, t12 and the
+ *                   unproject precision (KannalaBrandt8::epipolarConstrain = TriangulateMatches(...) > 0.0001).  NULL with coarse != 0.
+ *                   With ncam >= 2 the reference enters the loop with R12 / t12 uninitialised (:1152-1154): a first candidate whose
+ *                   cameras have no branch is tested with pair [1] here.
+ * match12[n1] = idx2 or -1 (vMatchedPairs lists them by ascending idx1); *nmatches = the return value.  HOST pointers. */
+#define ORBX_CAM_PINHOLE 0
+#define ORBX_CAM_KB8 1
+typedef struct orbx_epipolar_pair {
+    int model;                 /* ORBX_CAM_PINHOLE or ORBX_CAM_KB8 (both cameras of a pair) */
+    int reserved;
+    float F12[9];              /* pinhole: row-major fundamental matrix */
+    struct orbx_kb8_stereo kb8; /* Kannala-Brandt: cam1 / cam2 parameters, R12, t12, unproject precision */
+} orbx_epipolar_pair;
+int orbx_search_for_triangulation_full(orbx_matcher *m, int ncam, const int *cam_off1, const orbx_kp *kps1, const uint8_t *desc1,
+                                       const uint8_t *has_mp1, const float *u_right1, int nn1, const int *nodes1, const int *ptr1,
+                                       const int *idx1, const int *cam_off2, const orbx_kp *kps2, const uint8_t *desc2,
+                                       const uint8_t *has_mp2, const float *u_right2, int nn2, const int *nodes2, const int *ptr2,
+                                       const int *idx2, const float *ep, const float *sf2, const float *sigma2_1, const float *sigma2_2,
+                                       int nlevels, int only_stereo, int coarse, int check_orientation, const orbx_epipolar_pair *pairs,
+                                       int *match12, int *nmatches);
+
 /* KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:319-388) for n independent keypoint pairs:
  * xy1 / xy2 = kp.pt of the two cameras ([n][2]), sigma1 / sigma2 = the two reprojection gates (mvLevelSigma2 of the octaves).
  * depth[i] = z1 > 0, or the reference's reject code (-1 parallax, -2 / -3 behind a camera, -4 / -5 reprojection error);

@@ -58,6 +58,16 @@ KB8_STEREO_DTYPE = np.dtype([('cam1', 'f4', 8), ('cam2', 'f4', 8), ('R12', 'f4',
                              ('precision2', 'f4')])   # orbx_kb8_stereo
 
 
+EPIPOLAR_PAIR_DTYPE = np.dtype([('model', 'i4'), ('reserved', 'i4'), ('F12', 'f4', (9,)), ('kb8', KB8_STEREO_DTYPE)])
+CAM_PINHOLE, CAM_KB8 = 0, 1
+
+
+def epipolar_pairs():
+    """11 x orbx_epipolar_pair (include/orbx.h): [0] the single pair of a monocular keyframe pair, [1] ll, [2] lr, [3] rl, [4] rr,
+    [5] l-sl, [6] sl-l, [7] sl-sl, [8] r-sr, [9] sr-r, [10] sr-sr.  Fill ['model'] and ['F12'] (pinhole) or ['kb8'] (kb8_stereo())."""
+    return np.zeros(11, EPIPOLAR_PAIR_DTYPE)
+
+
 def kb8_stereo(cam1, cam2, R12, t12, precision=1e-6):
     """orbx_kb8_stereo: cam = (fx, fy, cx, cy, k0..k3) of KannalaBrandt8::mvParameters, R12 / t12 = Frame::mRlr / mtlr."""
     r = np.zeros(1, KB8_STEREO_DTYPE)
@@ -405,6 +415,32 @@ class ORBmatcher:
                                                     C.byref(nm)))
         pairs = [(int(i), int(m12[i])) for i in np.nonzero(m12 >= 0)[0]]
         return nm.value, pairs, m12
+
+    def SearchForTriangulationFull(self, kf1, kf2, ep, scale_factors2, sigma2_1, sigma2_2, pairs=None, only_stereo=False, coarse=False,
+                                   check_orientation=False):
+        """ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), src/ORBmatcher.cc:1131-1456, the whole
+        function (orbx_search_for_triangulation_full).  kf = dict(cam_off, kps, desc, has_mp, u_right (or None), fv = (nodes, ptr, idx));
+        pairs = epipolar_pairs() filled for the rig (None only with coarse).  Returns (nmatches, [(idx1, idx2)...], match12)."""
+        def side(kf):
+            off = np.ascontiguousarray(kf['cam_off'], np.int32)
+            k = np.ascontiguousarray(kf['kps'], KP_DTYPE); d = np.ascontiguousarray(kf['desc'], np.uint8).reshape(-1, 32)
+            mp = np.zeros(len(k), np.uint8) if kf.get('has_mp') is None else np.ascontiguousarray(kf['has_mp'], np.uint8)
+            ur = None if kf.get('u_right') is None else np.ascontiguousarray(kf['u_right'], np.float32)
+            nodes, ptr, idx = (np.ascontiguousarray(x, np.int32) for x in kf['fv'])
+            return off, k, d, mp, ur, nodes, ptr, idx
+        o1, k1, d1, mp1, ur1, n1n, p1, i1 = side(kf1)
+        o2, k2, d2, mp2, ur2, n2n, p2, i2 = side(kf2)
+        ncam = o1.size - 1
+        ep = np.ascontiguousarray(ep, np.float32); sf2 = np.ascontiguousarray(scale_factors2, np.float32)
+        s1 = np.ascontiguousarray(sigma2_1, np.float32); s2 = np.ascontiguousarray(sigma2_2, np.float32)
+        pr = None if pairs is None else np.ascontiguousarray(pairs, EPIPOLAR_PAIR_DTYPE)
+        m12 = np.full(len(k1), -1, np.int32)
+        nm = C.c_int(0)
+        _check(self.L.orbx_search_for_triangulation_full(self.h, ncam, _p(o1), _p(k1), _p(d1), _p(mp1), _p(ur1), n1n.size, _p(n1n), _p(p1), _p(i1),
+                                                         _p(o2), _p(k2), _p(d2), _p(mp2), _p(ur2), n2n.size, _p(n2n), _p(p2), _p(i2), _p(ep), _p(sf2),
+                                                         _p(s1), _p(s2), sf2.size, int(only_stereo), int(coarse), int(check_orientation), _p(pr),
+                                                         _p(m12), C.byref(nm)))
+        return nm.value, [(int(i), int(m12[i])) for i in np.nonzero(m12 >= 0)[0]], m12
 
     def window_best(self, kps, desc, bounds, qx, qy, radius, min_level, max_level, q_desc, valid=None, skip=None, u_right=None,
                     q_ur=None, inv_level_sigma2=None):

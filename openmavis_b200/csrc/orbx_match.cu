@@ -11,6 +11,7 @@
 #include "orbx_sbp_kernels.cuh"
 #include "orbx_fisheye_kernels.cuh"
 #include "orbx_bow_kernels.cuh"
+#include "orbx_sft_kernels.cuh"
 
 using namespace orbx;
 
@@ -387,6 +388,120 @@ int orbx_search_for_triangulation(orbx_matcher *m, int nn1, const int *nodes1, c
     int nm = 0;
     for (int i = 0; i < n1; i++) nm += match12[i] >= 0;
     if (nmatches) *nmatches = nm;
+    return ORBX_OK;
+}
+
+// ---- SearchForTriangulation, the whole function incl. bCoarse = false (src/ORBmatcher.cc:1131-1456); kernels in orbx_sft_kernels.cuh
+int orbx_search_for_triangulation_full(orbx_matcher *m, int ncam, const int *cam_off1, const orbx_kp *kps1, const uint8_t *desc1,
+                                       const uint8_t *has_mp1, const float *u_right1, int nn1, const int *nodes1, const int *ptr1,
+                                       const int *idx1, const int *cam_off2, const orbx_kp *kps2, const uint8_t *desc2,
+                                       const uint8_t *has_mp2, const float *u_right2, int nn2, const int *nodes2, const int *ptr2,
+                                       const int *idx2, const float *ep, const float *sf2, const float *sigma2_1, const float *sigma2_2,
+                                       int nlevels, int only_stereo, int coarse, int check_orientation, const orbx_epipolar_pair *pairs,
+                                       int *match12, int *nmatches) {
+    if (!m || !match12 || !nmatches || !(ncam == 1 || ncam == 2 || ncam == 4) || !cam_off1 || !cam_off2 || nn1 < 0 || nn2 < 0 ||
+        nlevels < 1 || nlevels > 16 || !sf2 || !sigma2_1 || !sigma2_2 || !ep || (!coarse && !pairs) || (nn1 && (!nodes1 || !ptr1 || !idx1)) ||
+        (nn2 && (!nodes2 || !ptr2 || !idx2)))
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    const int n1 = cam_off1[ncam], n2 = cam_off2[ncam];
+    if (n1 < 0 || n2 < 0 || (n1 && (!kps1 || !desc1)) || (n2 && (!kps2 || !desc2))) return fail(ORBX_ERR_INVALID, "bad arguments");
+    for (int c = 0; c < ncam; c++)
+        if (cam_off1[c] > cam_off1[c + 1] || cam_off2[c] > cam_off2[c + 1]) return fail(ORBX_ERR_INVALID, "camera offsets must ascend");
+    for (int i = 0; i < n1; i++) if (kps1[i].octave < 0 || kps1[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "kps1: octave out of range");
+    for (int i = 0; i < n2; i++) if (kps2[i].octave < 0 || kps2[i].octave >= nlevels) return fail(ORBX_ERR_INVALID, "kps2: octave out of range");
+    if (!coarse)
+        for (int s = (ncam == 1 ? 0 : 1); s < (ncam == 1 ? 1 : ncam == 2 ? 5 : kSftStates); s++)
+            if (pairs[s].model != ORBX_CAM_PINHOLE && pairs[s].model != ORBX_CAM_KB8) return fail(ORBX_ERR_INVALID, "pairs: unknown camera model");
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    *nmatches = 0;
+    // bStereo / skip flags (:1225-1236, 1258-1269)
+    std::vector<uint8_t> st1(std::max(n1, 1), 0), st2(std::max(n2, 1), 0), skip2(std::max(n2, 1), 0);
+    if (ncam == 1) {
+        if (u_right1) for (int i = 0; i < n1; i++) st1[i] = u_right1[i] >= 0;
+        if (u_right2) for (int i = 0; i < n2; i++) st2[i] = u_right2[i] >= 0;
+    }
+    for (int i = 0; i < n2; i++) skip2[i] = (has_mp2 && has_mp2[i]) || (only_stereo && !st2[i]);
+    // merge-walk of the two FeatureVectors (:1218-1222, 1420-1427) — host, O(nn1 + nn2); rows in the reference's visiting order
+    std::vector<int> row_q, row_begin, row_len;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (nodes1[a] == nodes2[b]) {
+            for (int k = ptr1[a]; k < ptr1[a + 1]; k++) {
+                const int i1 = idx1[k];
+                if (i1 < 0 || i1 >= n1) return fail(ORBX_ERR_INVALID, "idx1 out of range");
+                if ((has_mp1 && has_mp1[i1]) || (only_stereo && !st1[i1])) continue;
+                row_q.push_back(i1); row_begin.push_back(ptr2[b]); row_len.push_back(ptr2[b + 1] - ptr2[b]);
+            }
+            a++; b++;
+        } else if (nodes1[a] < nodes2[b]) {
+            a = (int)(std::lower_bound(nodes1 + a, nodes1 + nn1, nodes2[b]) - nodes1);
+        } else {
+            b = (int)(std::lower_bound(nodes2 + b, nodes2 + nn2, nodes1[a]) - nodes2);
+        }
+    }
+    const int nrows = (int)row_q.size();
+    if (nrows == 0) return ORBX_OK;
+    const int tot2 = ptr2[nn2];
+    for (int k = 0; k < tot2; k++)
+        if (idx2[k] < 0 || idx2[k] >= n2) return fail(ORBX_ERR_INVALID, "idx2 out of range");
+    int st;
+    if ((st = upload(m, m->b[1], desc1, (size_t)n1 * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[2], desc2, (size_t)n2 * 32)) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[3], kps1, (size_t)n1 * sizeof(orbx_kp))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[4], kps2, (size_t)n2 * sizeof(orbx_kp))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[5], st1.data(), (size_t)std::max(n1, 1))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[6], st2.data(), (size_t)std::max(n2, 1))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[9], row_q.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[10], row_begin.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[11], row_len.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[12], idx2, (size_t)tot2 * sizeof(int))) != ORBX_OK) return st;
+    if ((st = upload(m, m->b[13], skip2.data(), (size_t)std::max(n2, 1))) != ORBX_OK) return st;
+    std::vector<orbx_epipolar_pair> pz(kSftStates);
+    memset(pz.data(), 0, pz.size() * sizeof(orbx_epipolar_pair));
+    if ((st = upload(m, m->b[7], pairs ? pairs : pz.data(), kSftStates * sizeof(orbx_epipolar_pair))) != ORBX_OK) return st;
+    M_CUDA(m->b[14].ensure((size_t)n1 * sizeof(int)));
+    M_CUDA(m->b[15].ensure((size_t)nrows * sizeof(int)));
+    M_CUDA(m->b[16].ensure((size_t)(nrows + 1) * sizeof(int)));
+    M_CUDA(cudaMemsetAsync(m->b[14].p, 0xFF, (size_t)n1 * sizeof(int), m->stream));
+    M_CUDA(cudaMemsetAsync(m->b[16].p, 0, (size_t)(nrows + 1) * sizeof(int), m->stream));
+    SftArgs A;
+    memset(&A, 0, sizeof(A));
+    A.d1 = (const uint4 *)m->b[1].p; A.d2 = (const uint4 *)m->b[2].p; A.k1 = m->b[3].as<orbx_kp>(); A.k2 = m->b[4].as<orbx_kp>();
+    A.nrows = nrows; A.row_q = m->b[9].as<int>(); A.row_begin = m->b[10].as<int>(); A.row_len = m->b[11].as<int>(); A.idx2 = m->b[12].as<int>();
+    A.skip2 = m->b[13].as<uint8_t>(); A.st1 = m->b[5].as<uint8_t>(); A.st2 = m->b[6].as<uint8_t>(); A.ncam = ncam;
+    for (int c = 0; c <= 4; c++) { A.off1[c] = cam_off1[std::min(c, ncam)]; A.off2[c] = cam_off2[std::min(c, ncam)]; }
+    A.ep[0] = ep[0]; A.ep[1] = ep[1];
+    for (int l = 0; l < 16; l++) { const int k = std::min(l, nlevels - 1); A.sf2[l] = sf2[k]; A.sigma1[l] = sigma2_1[k]; A.sigma2[l] = sigma2_2[k]; }
+    A.coarse = coarse != 0; A.pairs = m->b[7].as<orbx_epipolar_pair>();
+    A.match12 = m->b[14].as<int>(); A.exit_state = m->b[15].as<int>(); A.unresolved = m->b[16].as<int>();
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    k_sft_rows<<<(nrows + 127) / 128, 128, 0, m->stream>>>(A);
+    m->last_launches = 1;
+    M_CUDA(cudaGetLastError());
+    if (ncam >= 2) {     // the carried camera pair only matters when pairs without a branch exist
+        int any = 0;
+        M_CUDA(cudaMemcpyAsync(&any, m->b[16].as<int>() + nrows, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        M_CUDA(cudaStreamSynchronize(m->stream));
+        if (any) {
+            k_sft_fix<<<1, 32, 0, m->stream>>>(A);
+            m->last_launches++;
+            M_CUDA(cudaGetLastError());
+        }
+    }
+    if (check_orientation) {
+        k_sft_rot<<<1, 256, 0, m->stream>>>(A.k1, A.k2, n1, A.match12);
+        m->last_launches++;
+        M_CUDA(cudaGetLastError());
+    }
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    M_CUDA(cudaMemcpyAsync(match12, m->b[14].p, (size_t)n1 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    M_CUDA(cudaStreamSynchronize(m->stream));
+    int nm = 0;
+    for (int i = 0; i < n1; i++) nm += match12[i] >= 0;
+    *nmatches = nm;
     return ORBX_OK;
 }
 

@@ -1737,4 +1737,49 @@ int orc_stereo_fisheye_matches(const OrcKb8Stereo *rig, const orc_kp *kpsL, cons
     return nMatches;
 }
 
+
+// ---- SearchForTriangulation with the reference's two epipolar predicates built in (test counterpart of
+// orbx_search_for_triangulation_full): pairs[11] = {model (0 pinhole, 1 Kannala-Brandt), reserved, F12[9], OrcKb8Stereo} per carried
+// state of orc_search_for_triangulation_full.
+struct OrcEpipolarPair { int model, reserved; float F12[9]; OrcKb8Stereo kb8; };
+// Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:103-132) given F12 = K1^-T [t12]x R12 K2^-1 (:112-115)
+static bool pinhole_epipolar(const float *F, float x1, float y1, float x2, float y2, float unc) {
+    const float a = x1 * F[0] + y1 * F[3] + F[6];
+    const float b = x1 * F[1] + y1 * F[4] + F[7];
+    const float c = x1 * F[2] + y1 * F[5] + F[8];
+    const float num = a * x2 + b * y2 + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * unc;
+}
+int orc_pinhole_epipolar(const float *F, float x1, float y1, float x2, float y2, float unc) { return pinhole_epipolar(F, x1, y1, x2, y2, unc) ? 1 : 0; }
+struct SftCamsCtx { const OrcEpipolarPair *pairs; const KeyPt *k1, *k2; const float *s1, *s2; std::vector<float> *margins; };
+static int sft_cams_pred(int i1, int i2, int state, void *user) {
+    SftCamsCtx &C = *(SftCamsCtx *)user;
+    const OrcEpipolarPair &P = C.pairs[state];
+    const KeyPt &a = C.k1[i1], &b = C.k2[i2];
+    if (P.model == 1) {     // KannalaBrandt8::epipolarConstrain (src/CameraModels/KannalaBrandt8.cpp:219-230)
+        float p3[3]; float margin = 0;
+        const float z = kb8_triangulate_matches(P.kb8, a.x, a.y, b.x, b.y, C.s1[a.octave], C.s2[b.octave], p3, &margin);
+        if (C.margins) C.margins->push_back(margin);
+        return z > 0.0001f;
+    }
+    return pinhole_epipolar(P.F12, a.x, a.y, b.x, b.y, C.s2[b.octave]);
+}
+int orc_search_for_triangulation_cams(int ncam, const int *cam_off1, const orc_kp *kps1, const uint8_t *desc1, const uint8_t *has_mp1,
+                                      const float *u_right1, int nn1, const int *nodes1, const int *ptr1, const int *idx1v,
+                                      const int *cam_off2, const orc_kp *kps2, const uint8_t *desc2, const uint8_t *has_mp2,
+                                      const float *u_right2, int nn2, const int *nodes2, const int *ptr2, const int *idx2v, const float *ep,
+                                      const float *sf2, const float *sigma2_1, const float *sigma2_2, int bOnlyStereo, int bCoarse,
+                                      int checkOrientation, const OrcEpipolarPair *pairs, int *match12, float *min_margin) {
+    std::vector<float> margins;
+    SftCamsCtx C{pairs, (const KeyPt *)kps1, (const KeyPt *)kps2, sigma2_1, sigma2_2, min_margin ? &margins : nullptr};
+    const int n = orc_search_for_triangulation_full(ncam, cam_off1, kps1, desc1, has_mp1, u_right1, nn1, nodes1, ptr1, idx1v, cam_off2, kps2, desc2,
+                                                    has_mp2, u_right2, nn2, nodes2, ptr2, idx2v, ep, sf2, bOnlyStereo, bCoarse, checkOrientation,
+                                                    sft_cams_pred, &C, match12);
+    if (min_margin) { float mm = 1e30f; for (float v : margins) mm = std::min(mm, v); *min_margin = mm; }
+    return n;
+}
+
 }  // extern "C"

@@ -817,3 +817,127 @@ def test_ordered_resolver_stress(seed):
                                              C.c_float(np.float32(M2.mfNNratio)), int(check), O.p(ref))
         L.orc_grid_destroy(C.c_void_p(g2))
         assert rn == nm and np.array_equal(ref, m12) and np.array_equal(prev, prev_ref), ('mode 2', seed, rep, n1, k2.size, win, check)
+
+
+# ---- SearchForTriangulation, the whole function incl. bCoarse = false (src/ORBmatcher.cc:1131-1456) ----------------------------------
+def _sft_scenario(rng, ncam, trial):
+    per1 = [int(rng.integers(150, 500)) for _ in range(ncam)]; per2 = [int(rng.integers(150, 500)) for _ in range(ncam)]
+    off1 = np.concatenate([[0], np.cumsum(per1)]).astype(np.int32); off2 = np.concatenate([[0], np.cumsum(per2)]).astype(np.int32)
+    n1, n2 = int(off1[-1]), int(off2[-1])
+    k2 = np.zeros(n2, ob.KP_DTYPE)
+    k2['x'] = rng.uniform(20, 620, n2); k2['y'] = rng.uniform(20, 460, n2); k2['octave'] = rng.integers(0, 8, n2); k2['angle'] = rng.uniform(0, 360, n2)
+    d2 = synth_descriptors(n2, 4000 + trial)
+    d2[10:60] = d2[10]                                       # exact duplicates -> last-minimum tie rule
+    src = rng.integers(0, n2, n1)
+    flips = np.packbits(rng.random((n1, 256)) < 0.05, axis=1, bitorder='little'); flips[:, 0] &= 0xE0
+    d1 = d2[src] ^ flips
+    d1[::6] = synth_descriptors(len(d1[::6]), 43 + trial)
+    k1 = k2[src].copy()
+    k1['x'] += rng.uniform(-30, 30, n1).astype(np.float32); k1['y'] += rng.uniform(-2.5, 2.5, n1).astype(np.float32)   # near the epipolar line y2 = y1
+    k1['angle'] = (k1['angle'] + rng.choice([0, 0, 0, 45, 200], n1)) % 360
+
+    def fvec(desc, nbits=5):
+        node = desc[:, 0].astype(np.int32) & ((1 << nbits) - 1)
+        order = np.argsort(node, kind='stable')
+        nodes, counts = np.unique(node, return_counts=True)
+        return nodes.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), order.astype(np.int32)
+    fv1, fv2 = fvec(d1), fvec(d2)
+    fv1 = (fv1[0][::2].copy(), np.concatenate([[0], np.cumsum(np.diff(fv1[1])[::2])]).astype(np.int32),
+           np.concatenate([fv1[2][fv1[1][i]:fv1[1][i + 1]] for i in range(0, len(fv1[0]), 2)]).astype(np.int32))   # some nodes only in KF2
+    kf1 = dict(cam_off=off1, kps=k1, desc=d1, has_mp=(rng.random(n1) < 0.3).astype(np.uint8), u_right=None, fv=fv1)
+    kf2 = dict(cam_off=off2, kps=k2, desc=d2, has_mp=(rng.random(n2) < 0.3).astype(np.uint8), u_right=None, fv=fv2)
+    only_stereo = False
+    if ncam == 1 and trial % 2 == 1:
+        kf1['u_right'] = np.where(rng.random(n1) < 0.5, 10.0, -1.0).astype(np.float32)
+        kf2['u_right'] = np.where(rng.random(n2) < 0.5, 10.0, -1.0).astype(np.float32)
+        only_stereo = trial % 4 == 3
+    e = int(rng.integers(0, n2))
+    ep = np.array([k2['x'][e] + 2.0, k2['y'][e] - 1.0], np.float32)
+    return kf1, kf2, ep, only_stereo
+
+
+def _oracle_sft(kf1, kf2, ep, sf, s1, s2, pairs, only_stereo, coarse, chk, want_margin=False):
+    L = O.lib()
+    n1 = len(kf1['kps'])
+    ref = np.zeros(n1, np.int32)
+    mm = C.c_float(0)
+    fv1, fv2 = kf1['fv'], kf2['fv']
+    rn = L.orc_search_for_triangulation_cams(len(kf1['cam_off']) - 1, O.p(kf1['cam_off']), O.p(kf1['kps']), O.p(kf1['desc']), O.p(kf1['has_mp']),
+                                             None if kf1['u_right'] is None else O.p(kf1['u_right']), len(fv1[0]), O.p(fv1[0]), O.p(fv1[1]),
+                                             O.p(fv1[2]), O.p(kf2['cam_off']), O.p(kf2['kps']), O.p(kf2['desc']), O.p(kf2['has_mp']),
+                                             None if kf2['u_right'] is None else O.p(kf2['u_right']), len(fv2[0]), O.p(fv2[0]), O.p(fv2[1]),
+                                             O.p(fv2[2]), O.p(ep), O.p(sf), O.p(s1), O.p(s2), int(only_stereo), int(coarse), int(chk),
+                                             None if pairs is None else O.p(pairs), O.p(ref), C.byref(mm) if want_margin else None)
+    return rn, ref, mm.value
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+def test_search_for_triangulation_full_pinhole(M, ncam):
+    """bCoarse = false with Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:103-132): every camera pair gets its own F12 (epipolar
+    line y2 = y1 + offset, a different offset per pair), so a candidate whose cameras have no branch in :1301-1378 passes or fails
+    depending on the carried pair.  Bit-exact match lists; also bCoarse = true and the rotation filter through the same entry point."""
+    rng = np.random.default_rng(70 + ncam)
+    sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+    s1 = (sf * sf).astype(np.float32); s2 = (sf * sf * np.float32(1.0)).astype(np.float32)
+    pairs = ob.epipolar_pairs()
+    for s in range(11):
+        pairs['model'][s] = ob.CAM_PINHOLE
+        pairs['F12'][s] = np.array([0, 0, 0, 0, 0, -1, 0, 1, -(s % 4 - 1.5) * 1.25], np.float32)
+    total = 0
+    for trial in range(8):
+        kf1, kf2, ep, only_stereo = _sft_scenario(rng, ncam, trial)
+        for coarse in (False, True):
+            chk = (trial + coarse) % 2 == 1
+            nm, prs, m12 = M.SearchForTriangulationFull(kf1, kf2, ep, sf, s1, s2, pairs, only_stereo, coarse, chk)
+            rn, ref, _ = _oracle_sft(kf1, kf2, ep, sf, s1, s2, pairs, only_stereo, coarse, chk)
+            assert nm == rn, (trial, coarse, nm, rn)
+            assert np.array_equal(m12, ref), (trial, coarse, int((m12 != ref).sum()))
+            assert prs == [(int(i), int(ref[i])) for i in np.nonzero(ref >= 0)[0]]
+            total += nm
+        # the coarse result through the array-level entry point of round 1 must agree as well (no rotation filter there)
+        if not only_stereo and kf1['u_right'] is None:
+            nm0, _, m0 = M.SearchForTriangulation(kf1['fv'], kf2['fv'], kf1['desc'], kf2['desc'], kf1['has_mp'], kf2['has_mp'])
+            _, _, mc = M.SearchForTriangulationFull(kf1, kf2, ep, sf, s1, s2, None, False, True, False)
+            if ncam > 1:                                        # with ncam == 1 the epipole gate also applies to bCoarse
+                assert np.array_equal(m0, mc)
+    assert total > 200
+
+
+def test_search_for_triangulation_full_kb8(M):
+    """bCoarse = false on a 4-camera Kannala-Brandt rig: KannalaBrandt8::epipolarConstrain = TriangulateMatches(...) > 0.0001
+    (src/CameraModels/KannalaBrandt8.cpp:219-230).  Float geometry (atan2f / tanf / 4x4 null vector): tolerance-based as DESIGN.md §2
+    states — the match lists must be identical whenever no tested quantity of the oracle run lies within 1e-3 (relative) of its gate."""
+    from openmavis_b200.synth import synth_fisheye_pairs
+    rng = np.random.default_rng(91)
+    sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+    s1 = (sf * sf).astype(np.float32); s2 = s1.copy()
+    checked = 0
+    for trial in range(12):
+        fs = synth_fisheye_pairs(1200, 500 + trial, outlier_frac=0.3)
+        pairs = ob.epipolar_pairs()
+        for s in range(11):
+            pairs['model'][s] = ob.CAM_KB8
+            t12 = fs['t12'] * np.float32(1.0 + 0.02 * (s % 3))          # the pairs differ a little: the carried state changes outcomes
+            pairs['kb8'][s] = ob.kb8_stereo(fs['cam1'], fs['cam2'], fs['R12'], t12)[0]
+        kf1, kf2, ep, _ = _sft_scenario(rng, 4, trial)
+        n1, n2 = len(kf1['kps']), len(kf2['kps'])
+        # keypoints: observations of the same 3-D points in the two cameras (planted partner of idx1 is found through the descriptors)
+        pick2 = rng.integers(0, 1200, n2)
+        kf2['kps']['x'], kf2['kps']['y'] = fs['xy2'][pick2, 0], fs['xy2'][pick2, 1]
+        d2 = kf2['desc']
+        src = rng.integers(0, n2, n1)
+        flips = np.packbits(rng.random((n1, 256)) < 0.05, axis=1, bitorder='little'); flips[:, 0] &= 0xE0
+        d1 = d2[src] ^ flips
+        kf1['desc'] = d1
+        kf1['kps']['x'], kf1['kps']['y'] = fs['xy1'][pick2[src], 0], fs['xy1'][pick2[src], 1]
+        node = d1[:, 0].astype(np.int32) & 31
+        order = np.argsort(node, kind='stable'); nodes, counts = np.unique(node, return_counts=True)
+        kf1['fv'] = (nodes.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), order.astype(np.int32))
+        rn, ref, margin = _oracle_sft(kf1, kf2, ep, sf, s1, s2, pairs, False, False, False, want_margin=True)
+        if margin < 1e-3:
+            continue                                                    # a gate is too close to call in float: not a parity case
+        nm, prs, m12 = M.SearchForTriangulationFull(kf1, kf2, ep, sf, s1, s2, pairs, False, False, False)
+        assert nm == rn and np.array_equal(m12, ref), (trial, nm, rn, int((m12 != ref).sum()))
+        assert nm > 50
+        checked += 1
+    assert checked >= 4
