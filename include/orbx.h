@@ -30,7 +30,8 @@ typedef enum orbx_status {
     ORBX_ERR_NO_DEVICE = -2,   /* no CUDA device / device index out of range */
     ORBX_ERR_CUDA = -3,        /* CUDA runtime error (message in orbx_last_error) */
     ORBX_ERR_CAPACITY = -4,    /* caller buffer too small / batch larger than the handle was created for */
-    ORBX_ERR_EMPTY = -5        /* empty image: the reference returns -1 (src/ORBextractor.cc:994-995) */
+    ORBX_ERR_EMPTY = -5,       /* empty image: the reference returns -1 (src/ORBextractor.cc:994-995) */
+    ORBX_ERR_ARGUMENT = -6     /* orbx_extract only: bad argument (its -1 is the reference's return value for an empty image) */
 } orbx_status;
 
 /* Field-for-field cv::KeyPoint (pt.x, pt.y, size, angle, response, octave, class_id): 28 bytes. */
@@ -252,12 +253,15 @@ int orbx_grid_candidates(orbx_matcher *m, const orbx_kp *kps, int n, float min_x
  * (src/ORBmatcher.cc:23-340) over plain arrays; argument meaning as in oracle/orb_oracle.cpp
  * (orc_search_by_projection).  Candidate generation, Hamming distances, best/second selection and the ordered
  * claim resolution (a keypoint claimed by an earlier map point is skipped by later ones, :77-79) all run on
- * the device; assigned[N] receives the map-point index written to F.mvpMapPoints (or -1). HOST pointers. */
+ * the device; assigned[N] receives the map-point index written to F.mvpMapPoints (or -1).
+ * u_right[N] = F.mvuRight and proj_xr[nmp] = MapPoint::mTrackProjXR: the rectified-stereo gate of :81-85 (only applied with
+ * ncam == 1, i.e. F.Nleft == -1; both NULL = monocular frame without right observations).
+ * Returns ORBX_ERR_INVALID for NULL inputs or a predicted level outside [0, nlevels) on an in-view entry.  HOST pointers. */
 int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
                               const float *grid_bounds /* [ncam][4] minX,maxX,minY,maxY */, const float *scale_factors,
-                              int nlevels, const uint8_t *occupied, const int *l2r, const int *r2l, int nmp,
+                              int nlevels, const uint8_t *occupied, const int *l2r, const int *r2l, const float *u_right, int nmp,
                               const uint8_t *in_view, const float *proj_x, const float *proj_y, const int *level,
-                              const float *view_cos, const float *depth, const uint8_t *bad, const uint8_t *has_obs,
+                              const float *view_cos, const float *proj_xr, const float *depth, const uint8_t *bad, const uint8_t *has_obs,
                               const uint8_t *mp_desc, float th, int far_points, float th_far_points, float nnratio,
                               int *assigned, int *nmatches);
 

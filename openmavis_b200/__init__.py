@@ -576,8 +576,9 @@ class ORBmatcher:
 
     def SearchByProjection(self, frame, points, th=3.0, bFarPoints=False, thFarPoints=50.0):
         """src/ORBmatcher.cc:23-340 over plain arrays.
-        frame : dict(cam_off[ncam+1], kps, desc, bounds[ncam,4], scale_factors, occupied?, l2r?, r2l?)
-        points: dict(in_view[n,4], proj_x[n,4], proj_y[n,4], level[n,4], view_cos[n,4], desc[n,32], depth?, bad?, has_obs?)
+        frame : dict(cam_off[ncam+1], kps, desc, bounds[ncam,4], scale_factors, occupied?, l2r?, r2l?, u_right? (mvuRight, ncam == 1))
+        points: dict(in_view[n,4], proj_x[n,4], proj_y[n,4], level[n,4], view_cos[n,4], desc[n,32], depth?, bad?, has_obs?,
+                     proj_xr? (mTrackProjXR, with frame['u_right']: the rectified-stereo gate of :81-85))
         Returns (nmatches, assigned[N])  — assigned[idx] = index of the map point written to F.mvpMapPoints[idx]."""
         cam_off = np.ascontiguousarray(frame['cam_off'], np.int32)
         ncam = cam_off.size - 1
@@ -598,9 +599,11 @@ class ORBmatcher:
         depth = None if points.get('depth') is None else np.ascontiguousarray(points['depth'], np.float32)
         bad = None if points.get('bad') is None else np.ascontiguousarray(points['bad'], np.uint8)
         ho = None if points.get('has_obs') is None else np.ascontiguousarray(points['has_obs'], np.uint8)
+        ur = None if frame.get('u_right') is None else np.ascontiguousarray(frame['u_right'], np.float32)
+        pxr = None if points.get('proj_xr') is None else np.ascontiguousarray(points['proj_xr'], np.float32)
         assigned = np.full(max(N, 1), -1, np.int32); nm = C.c_int(0)
         _check(self.L.orbx_search_by_projection(self.h, ncam, _p(cam_off), _p(kps), _p(desc), _p(bounds), _p(sf), sf.size, _p(occ),
-                                                _p(l2r), _p(r2l), nmp, _p(iv), _p(px), _p(py), _p(lv), _p(vc), _p(depth), _p(bad),
+                                                _p(l2r), _p(r2l), _p(ur), nmp, _p(iv), _p(px), _p(py), _p(lv), _p(vc), _p(pxr), _p(depth), _p(bad),
                                                 _p(ho), _p(md), C.c_float(th), int(bool(bFarPoints)), C.c_float(thFarPoints),
                                                 C.c_float(self.mfNNratio), _p(assigned), C.byref(nm)))
         return nm.value, assigned[:N]

@@ -22,10 +22,14 @@ ORBmatcher::ORBmatcher(float nnratio, bool checkOri, int device) : mfNNratio(nnr
 }
 ORBmatcher::~ORBmatcher() { orbx_matcher_destroy(mHandle); }
 
+// One pair: 8 popcounts on the host.  This static member is the API's host side (the reference's remaining host callers —
+// MapPoint::ComputeDistinctiveDescriptors, LoopClosing — call it per pair): a kernel launch plus two copies per 256-bit popcount
+// would be thousands of times slower than the arithmetic.  Every batch path (orbx_descriptor_distance, the matchers) is on the device.
 int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b) {
-    int d = 0;
-    if (orbx_descriptor_distance(0, a.ptr<unsigned char>(), b.ptr<unsigned char>(), 1, &d) != ORBX_OK) die("DescriptorDistance");
-    return d;
+    const unsigned int *pa = a.ptr<unsigned int>(), *pb = b.ptr<unsigned int>();   // rows are 4-byte aligned, as in src/ORBmatcher.cc:2578-2579
+    int dist = 0;
+    for (int i = 0; i < 8; i++) dist += __builtin_popcount(pa[i] ^ pb[i]);
+    return dist;
 }
 
 void ORBmatcher::KnnMatch2(const cv::Mat &query, const cv::Mat &train, std::vector<int> &idx, std::vector<int> &dist) {

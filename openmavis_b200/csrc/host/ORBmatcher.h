@@ -25,6 +25,8 @@ public:
 
     ORBmatcher(float nnratio = 0.6, bool checkOri = true, int device = 0);   // include/ORBmatcher.h:21
     ~ORBmatcher();
+    ORBmatcher(const ORBmatcher &) = delete;              // owns a device handle
+    ORBmatcher &operator=(const ORBmatcher &) = delete;
 
     // Computes the Hamming distance between two ORB descriptors (src/ORBmatcher.cc:2577-2591).  Each row: 32 bytes.
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);

@@ -848,10 +848,12 @@ int orbx_extract_batch(orbx_extractor *ex, int n_images, const uint8_t *const *i
 
 int orbx_extract(orbx_extractor *ex, const uint8_t *image, int stride, const orbx_image_params *params, orbx_kp *kps,
                  uint8_t *desc, int cap, int *n_kp) {
+    if (!ex || !params) { fail(ORBX_ERR_INVALID, "NULL handle or parameters"); return ORBX_ERR_ARGUMENT; }
     if (!image) return -1;   // src/ORBextractor.cc:994-995
     int mono = 0, nk = 0;
     const uint8_t *imgs[1] = {image};
     int st = orbx_extract_batch(ex, 1, imgs, &stride, params, kps, desc, cap, &nk, &mono);
+    if (st == ORBX_ERR_INVALID) return ORBX_ERR_ARGUMENT;     // -1 is taken by the empty-image return value above
     if (st != ORBX_OK) return st;
     if (n_kp) *n_kp = nk;
     return mono;

@@ -40,6 +40,7 @@ struct orbx_vocabulary {
     uint8_t *d_desc = nullptr;
     std::vector<double> weight;      // per node (leaves); looked up on the host
     std::vector<int> word;
+    std::vector<int> leaf_of_word;   // word id -> leaf node (m_words order), built once in orbx_vocabulary_create
 };
 
 struct orbx_matcher {
@@ -154,16 +155,19 @@ int orbx_descriptor_distance(int device, const uint8_t *a, const uint8_t *b, int
     if (orbx_device_count() <= device || device < 0) return fail(ORBX_ERR_NO_DEVICE, "no such CUDA device");
     if (n == 0) return ORBX_OK;
     M_CUDA(cudaSetDevice(device));
-    uint8_t *da = nullptr, *db = nullptr; int *dd = nullptr;
-    M_CUDA(cudaMalloc((void **)&da, (size_t)n * 32));
-    M_CUDA(cudaMalloc((void **)&db, (size_t)n * 32));
-    M_CUDA(cudaMalloc((void **)&dd, (size_t)n * sizeof(int)));
-    M_CUDA(cudaMemcpy(da, a, (size_t)n * 32, cudaMemcpyHostToDevice));
-    M_CUDA(cudaMemcpy(db, b, (size_t)n * 32, cudaMemcpyHostToDevice));
-    k_pair_distance<<<(n + 255) / 256, 256>>>((const uint4 *)da, (const uint4 *)db, n, dd);
-    M_CUDA(cudaGetLastError());
-    M_CUDA(cudaMemcpy(dist, dd, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(da); cudaFree(db); cudaFree(dd);
+    // one allocation for the three arrays: nothing to leak on an error path
+    uint8_t *buf = nullptr;
+    const size_t nb = (size_t)n * 32;
+    M_CUDA(cudaMalloc((void **)&buf, 2 * nb + (size_t)n * sizeof(int)));
+    cudaError_t e = cudaMemcpy(buf, a, nb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(buf + nb, b, nb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_pair_distance<<<(n + 255) / 256, 256>>>((const uint4 *)buf, (const uint4 *)(buf + nb), n, (int *)(buf + 2 * nb));
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(dist, buf + 2 * nb, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    M_CUDA(e);
     return ORBX_OK;
 }
 
@@ -833,13 +837,18 @@ static int sbp_setup_frame(orbx_matcher *m, int ncam, const int *cam_off, const 
 
 int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, const orbx_kp *kps, const uint8_t *desc,
                               const float *grid_bounds, const float *scale_factors, int nlevels, const uint8_t *occupied,
-                              const int *l2r, const int *r2l, int nmp, const uint8_t *in_view, const float *proj_x,
-                              const float *proj_y, const int *level, const float *view_cos, const float *depth, const uint8_t *bad,
+                              const int *l2r, const int *r2l, const float *u_right, int nmp, const uint8_t *in_view, const float *proj_x,
+                              const float *proj_y, const int *level, const float *view_cos, const float *proj_xr, const float *depth, const uint8_t *bad,
                               const uint8_t *has_obs, const uint8_t *mp_desc, float th, int far_points, float th_far_points,
                               float nnratio, int *assigned, int *nmatches) {
     if (!m || !cam_off || !kps || !desc || !grid_bounds || !scale_factors || !assigned || !nmatches || nmp < 0 ||
         !(ncam == 1 || ncam == 2 || ncam == 4) || nlevels < 1 || nlevels > 32)
         return fail(ORBX_ERR_INVALID, "bad arguments");
+    if (nmp > 0 && (!in_view || !proj_x || !proj_y || !level || !view_cos || !mp_desc)) return fail(ORBX_ERR_INVALID, "NULL map-point array");
+    if ((u_right != nullptr) != (proj_xr != nullptr)) return fail(ORBX_ERR_INVALID, "u_right and proj_xr go together");
+    for (int i = 0; i < nmp * 4; i++)      // sbp_query indexes scale_factors[level]: validate what it will read
+        if (in_view[i] && (i & 3) < ncam && !((i & 3) >= 1 && level[i] == -1) && (level[i] < 0 || level[i] >= nlevels))
+            return fail(ORBX_ERR_INVALID, "predicted level out of range");
     M_CUDA(cudaSetDevice(m->device));
     m->last_launches = 0;
     const int N = cam_off[ncam];
@@ -852,14 +861,16 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     if ((st = sbp_setup_frame(m, ncam, cam_off, kps, desc, grid_bounds, scale_factors, nlevels, occupied, l2r, r2l, F)) != ORBX_OK) return st;
     // ---- map-point side: one query per (map point, camera) in reference order
     const size_t q = (size_t)nmp * 4;
-    const size_t bytes = q * (1 + 4 + 4 + 4 + 4) + (size_t)nmp * (4 + 1 + 1 + 32);
+    const size_t bytes = q * (1 + 4 + 4 + 4 + 4) + (size_t)nmp * (4 + 4 + 1 + 1 + 32) + (size_t)N * 4;
     uint8_t *base = nullptr;
     SbpPoints P;
     P.nmp = nmp;
     size_t off = 0;
+    cudaError_t put_err = cudaSuccess;
     auto put = [&](const void *src, size_t nb) -> void * {
         void *d = base + off;
-        cudaMemcpyAsync(d, src, nb, cudaMemcpyHostToDevice, m->stream);
+        const cudaError_t e = cudaMemcpyAsync(d, src, nb, cudaMemcpyHostToDevice, m->stream);
+        if (e != cudaSuccess && put_err == cudaSuccess) put_err = e;
         off += (nb + 15) & ~(size_t)15;
         return d;
     };
@@ -881,9 +892,15 @@ int orbx_search_by_projection(orbx_matcher *m, int ncam, const int *cam_off, con
     }
     P.active = (const uint8_t *)put(active.data(), nmp);
     P.has_obs = (const uint8_t *)put(hobs.data(), nmp);
+    P.u_right = P.proj_ur = nullptr;
+    if (u_right && ncam == 1) {               // rectified-stereo gate (:81-85)
+        P.u_right = (const float *)put(u_right, (size_t)N * 4);
+        P.proj_ur = (const float *)put(proj_xr, (size_t)nmp * 4);
+    }
+    M_CUDA(put_err);
     M_CUDA(cudaGetLastError());
     P.th = th; P.nnratio = nnratio;
-    P.mode = 0; P.level_gate = 0; P.check_ori = 0; P.max_dist = 100; P.angle = nullptr; P.u_right = P.proj_ur = nullptr;
+    P.mode = 0; P.level_gate = 0; P.check_ori = 0; P.max_dist = 100; P.angle = nullptr;
     // ---- device work buffers
     M_CUDA(m->b[23].ensure(sbp_work_bytes(nmp, N)));
     M_CUDA(cudaEventRecord(m->ev0, m->stream));
@@ -1208,6 +1225,13 @@ int orbx_vocabulary_create(orbx_vocabulary **out, int device, int n_nodes, const
     orbx_vocabulary *v = new orbx_vocabulary();
     v->device = device; v->n_nodes = n_nodes; v->n_children = nch; v->levels = levels;
     v->weight.assign(weight, weight + n_nodes); v->word.assign(word_id, word_id + n_nodes);
+    {   // word id -> leaf node: owned by the vocabulary (a per-thread cache keyed by the handle's address would go stale when a
+        // destroyed vocabulary's address is reused by the next one)
+        int maxw = -1;
+        for (int i = 0; i < n_nodes; i++) maxw = std::max(maxw, word_id[i]);
+        v->leaf_of_word.assign((size_t)maxw + 1, -1);
+        for (int i = 0; i < n_nodes; i++) if (word_id[i] >= 0) v->leaf_of_word[word_id[i]] = i;
+    }
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc((void **)&v->d_child_ptr, (size_t)(n_nodes + 1) * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void **)&v->d_child, (size_t)std::max(nch, 1) * sizeof(int));
@@ -1251,15 +1275,7 @@ int orbx_vocabulary_transform(orbx_matcher *m, const orbx_vocabulary *v, const u
     M_CUDA(cudaMemcpyAsync(node_id, o + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     M_CUDA(cudaStreamSynchronize(m->stream));
     if (weight) {   // word id -> weight of the leaf (idf for TF_IDF vocabularies); a leaf's word id indexes m_words, keep a reverse map
-        static thread_local std::vector<int> leaf_of_word;
-        static thread_local const orbx_vocabulary *cached = nullptr;
-        if (cached != v) {
-            int maxw = -1;
-            for (int i = 0; i < v->n_nodes; i++) maxw = std::max(maxw, v->word[i]);
-            leaf_of_word.assign((size_t)maxw + 1, -1);
-            for (int i = 0; i < v->n_nodes; i++) if (v->word[i] >= 0) leaf_of_word[v->word[i]] = i;
-            cached = v;
-        }
+        const std::vector<int> &leaf_of_word = v->leaf_of_word;
         for (int i = 0; i < n; i++) weight[i] = (word_id[i] >= 0 && word_id[i] < (int)leaf_of_word.size() && leaf_of_word[word_id[i]] >= 0)
                                                     ? v->weight[leaf_of_word[word_id[i]]] : 0.0;
     }

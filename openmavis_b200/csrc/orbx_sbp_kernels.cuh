@@ -137,7 +137,7 @@ __global__ void k_sbp_fill(SbpFrame F, SbpPoints P, const int *__restrict__ q_pt
     int c, mn, mx; float x, y, rr;
     if (q_ptr[q + 1] == q_ptr[q] || !sbp_query(F, P, q, c, x, y, rr, mn, mx)) return;
     const int mp = q >> 2;
-    const bool ur_check = P.mode == 1 && c == 0 && F.ncam == 1 && P.u_right != nullptr;
+    const bool ur_check = P.mode <= 1 && c == 0 && F.ncam == 1 && P.u_right != nullptr;   // mode 0: :81-85, mode 1: :2079-2084
     const uint4 qa = P.desc[2 * mp], qb = P.desc[2 * mp + 1];
     int o = q_ptr[q];
     const orbx_kp *ck = F.kps + F.cam_off[c];
@@ -145,7 +145,7 @@ __global__ void k_sbp_fill(SbpFrame F, SbpPoints P, const int *__restrict__ q_pt
     grid_query(ck, F.cell_start[c], F.cell_items[c], F.min_x[c], F.min_y[c], F.inv_w[c], F.inv_h[c], x, y, rr, mn, mx,
                [&](int idx) {
                    int d = hamming256(qa, qb, cd[2 * idx], cd[2 * idx + 1]);
-                   if (ur_check && P.u_right[idx] > 0.0f && fabsf(__fsub_rn(P.proj_ur[mp], P.u_right[idx])) > rr) d = 511;   // :2079-2084
+                   if (ur_check && P.u_right[idx] > 0.0f && fabsf(__fsub_rn(P.proj_ur[mp], P.u_right[idx])) > rr) d = 511;
                    cand[o++] = (uint32_t)idx | ((uint32_t)d << 16) | ((uint32_t)(ck[idx].octave & 0x7F) << 25);
                });
 }

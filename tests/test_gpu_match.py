@@ -300,8 +300,9 @@ def _oracle_sbp(frame, points, th, nnratio, far, thfar):
     L.orc_search_by_projection.restype = C.c_int
     n = L.orc_search_by_projection(ncam, O.p(cam_off), O.p(kps), O.p(desc), grids, O.p(frame['scale_factors']), O.p(frame['occupied']),
                                    None if frame['l2r'] is None else O.p(frame['l2r']), None if frame['r2l'] is None else O.p(frame['r2l']),
-                                   None, points['in_view'].shape[0], O.p(points['in_view']), O.p(points['proj_x']), O.p(points['proj_y']),
-                                   O.p(points['level']), O.p(points['view_cos']), None, O.p(points['depth']), O.p(points['bad']),
+                                   None if frame.get('u_right') is None else O.p(frame['u_right']), points['in_view'].shape[0],
+                                   O.p(points['in_view']), O.p(points['proj_x']), O.p(points['proj_y']), O.p(points['level']), O.p(points['view_cos']),
+                                   None if points.get('proj_xr') is None else O.p(points['proj_xr']), O.p(points['depth']), O.p(points['bad']),
                                    O.p(points['has_obs']), O.p(points['desc']), C.c_float(th), int(far), C.c_float(thfar),
                                    C.c_float(nnratio), O.p(assigned))
     for c in range(ncam):
@@ -394,6 +395,31 @@ def test_search_by_projection_last_frame(ncam, th, fwd, bwd, check):
     if check:   # the filter did remove something: without it there are more matches
         n_all, _ = _oracle_sbp_last(frame, last, th, fwd, bwd, False)
         assert n_all > rn
+
+
+@pytest.mark.parametrize('th', [1.0, 3.0])
+def test_search_by_projection_rectified_stereo_gate(th):
+    """SearchByProjection(Frame, MapPoints) on a stereo / RGB-D frame (F.Nleft == -1, mvuRight > 0): candidates whose right
+    coordinate is further than the window radius from mTrackProjXR are skipped (src/ORBmatcher.cc:81-85)."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    frame, points, _, nnratio = _sbp_case(1, seed=31 + int(th))
+    rng = np.random.default_rng(5)
+    N = len(frame['kps']); nmp = len(points['desc'])
+    frame['u_right'] = np.where(rng.random(N) < 0.6, frame['kps']['x'] - rng.uniform(1, 30, N), -1).astype(np.float32)
+    # half of the predicted right coordinates agree with the keypoint the point was planted on, half are off by up to 40 px
+    points['proj_xr'] = (points['proj_x'][:, 0] - rng.uniform(0, 40, nmp)).astype(np.float32)
+    M = ob.ORBmatcher(nnratio)
+    nm, assigned = M.SearchByProjection(frame, points, th, False, 40.0)
+    rn, rassigned = _oracle_sbp(frame, points, th, np.float32(nnratio), False, 40.0)
+    assert rn == nm and np.array_equal(assigned, rassigned), (rn, nm, int((assigned != rassigned).sum()))
+    # the gate did something: without it the result differs
+    f2 = dict(frame); f2.pop('u_right'); p2 = dict(points); p2.pop('proj_xr')
+    n0, a0 = M.SearchByProjection(f2, p2, th, False, 40.0)
+    assert n0 > nm and not np.array_equal(a0, assigned)
+    with pytest.raises(ob.OrbxError):                       # validation: predicted level out of range on an in-view entry
+        bad = dict(points); bad['level'] = points['level'].copy(); bad['level'][np.nonzero(points['in_view'][:, 0])[0][0], 0] = 99
+        M.SearchByProjection(frame, bad, th, False, 40.0)
 
 
 @pytest.mark.parametrize('orb_dist,th', [(100, 10.0), (64, 15.0)])
@@ -716,6 +742,31 @@ def test_vocabulary_transform(M, k, L, irregular):
     assert np.array_equal(ids, bi[:nb]) and np.array_equal(vals.view(np.uint64), bv[:nb].view(np.uint64))
     assert np.array_equal(nodes, fn[:nfn.value]) and np.array_equal(ptr, fp[:nfn.value + 1]) and np.array_equal(idx, fi[:fp[nfn.value]])
     assert nb >= 3
+
+
+def test_vocabulary_objects_created_one_after_another(M):
+    """Vocabularies created and destroyed in sequence (the allocator hands out the same address again): the word -> weight map
+    belongs to each vocabulary, the weights of the second one must not come from the first."""
+    rng = np.random.default_rng(9)
+    outs = []
+    for round_ in range(3):
+        child_ptr, child, nd, word, weight, leaves = _synthetic_vocabulary(6, 3, 300 + round_)
+        weight = weight * (1.0 + round_)                               # same tree shape, different weights / word numbering
+        word = word.copy(); word[leaves] = rng.permutation(len(leaves)).astype(word.dtype)
+        feat = nd[rng.choice(leaves, 400)]
+        voc = ob.ORBVocabulary(child_ptr, child, nd, word, weight, 3)
+        (ids, vals), _, gw, gn = voc.transform(M, feat, 1)
+        leaf_of_word = np.zeros(len(leaves), np.int64); leaf_of_word[word[leaves]] = leaves
+        exp = {}
+        for wd in gw:
+            if weight[leaf_of_word[wd]] > 0:                          # stopped words carry no weight
+                exp[int(wd)] = exp.get(int(wd), 0.0) + weight[leaf_of_word[wd]]
+        norm = sum(exp[k_] for k_ in sorted(exp))                     # BowVector::normalize(L1)
+        got = dict(zip(ids.tolist(), vals.tolist()))
+        assert set(got) == set(exp) and len(exp) > 20
+        for k_ in exp:
+            assert abs(got[k_] - exp[k_] / norm) <= 1e-12, (round_, k_)
+        del voc
 
 
 def _random_frame(rng, ncam, n_per_cam, size=200.0, pool=6):
