@@ -14,8 +14,14 @@ One JSON line is printed by rank 0:
   e2e       rig-frames/s through the host-buffer C-ABI call orbx_extract_batch (pinned host images in, keypoints +
             descriptors out, copies inside the timed region)
   roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM peak
-  cpu_baseline  the CPU oracle (oracle/liborb_oracle.so, a port of the reference's CPU path) on the host cores
-  matching  secondary metric: brute-force Hamming 2-NN pairs/s vs the measured popc issue rate
+            + e2e.copy_roofline: the same pinned buffers moved by plain cudaMemcpyAsync alone (what the host link allows)
+  roofline  dominant kernel: algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  sustained the device pipeline repeated for >= 2 s with its clock record
+  cpu_baseline  the reference's own src/ORBextractor.cc (compiled unmodified, oracle/_ref/libref_orb_fma.so) on the host cores:
+            all host threads (value), one std::thread per camera per rig frame as src/Frame.cc:1841-1862 does, the oracle port,
+            and a cv2-primitive sanity line
+  secondary device-resident extraction on the other BASELINE.json configurations (1, 2, 4, 5)
+  matching  secondary metric: brute-force Hamming 2-NN pairs/s vs the measured popc issue rate; guided matchers with CPU timings
 """
 import argparse
 import json
@@ -35,6 +41,12 @@ LAPS = [(0, 720), (0, 720), (0, 0), (0, 0), (0, 0)]
 # algorithmic bytes per level-0 pixel: pyramid 7.1, FAST 3.1, blur 6.2  => 16.4 per image pixel
 ALG_BYTES_PER_PX = {'pyramid': 7.12, 'fast': 3.095, 'blur': 6.19, 'total': 16.4}
 
+
+# `config` is the same object in both arms (ours / --impl reference): the driver compares it key by key
+CONFIG = {'workload': 'hilti_rig_5x720x540_nf1500',
+          'baseline_config': 'BASELINE.json configs[2]: Hilti-2022 5-camera rig 5×720×540, 1500 features/camera, per-rig-frame batched extraction',
+          'cameras': NCAM, 'image': [W, H], 'features_per_camera': NFEAT, 'fast_thresholds': [INI, MIN], 'levels': 8, 'scale_factor': 1.2,
+          'lapping': LAPS, 'l2': 'GPU arm: the inputs + pyramids of one step (about 1 GB) exceed the 126 MB L2, no flush needed'}
 
 _BATCH_CACHE = {}
 
@@ -110,22 +122,101 @@ def measured_peaks():
         return {'hbm_gbs': 6650.0}, 'fallback'
 
 
-def cpu_oracle_run(frames, threads, rank=0):
-    """Times the CPU oracle (port of the reference's ORBextractor) on `frames` rig frames with `threads` host threads."""
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import oracle_lib as O
+    return O
+
+
+def _front_side(frames, rank):
+    imgs = make_batch(frames, rank)[: frames * NCAM].reshape(frames, NCAM, H, W)
+    return np.ascontiguousarray(imgs[:, :2].reshape(-1, H, W)), np.ascontiguousarray(imgs[:, 2:].reshape(-1, H, W))
+
+
+def cpu_reference_run(frames, threads, rank=0):
+    """The reference's own ORBextractor (src/ORBextractor.cc compiled unmodified with the reference's flags: oracle/_ref/libref_orb_fma.so)
+    on `frames` rig frames, `threads` workers each owning one extractor, images in parallel.  -> (rig-frames/s, seconds, keypoints)"""
+    O = _oracle()
+    front, side = _front_side(frames, rank)           # lapping differs per camera: two groups, same total work
+    t_f, k_f = O.ref_extract_batch(front, NFEAT, 1.2, 8, INI, MIN, (0, 720), threads, fma=True)
+    t_s, k_s = O.ref_extract_batch(side, NFEAT, 1.2, 8, INI, MIN, (0, 0), threads, fma=True)
+    return frames / (t_f + t_s), t_f + t_s, k_f + k_s
+
+
+def cpu_reference_thread_per_camera(frames, rank=0):
+    """Reference-faithful threading (src/Frame.cc:1841-1862): rig frames one after the other, one std::thread per camera per frame."""
+    O = _oracle()
     imgs = make_batch(frames, rank)[: frames * NCAM]
+    dt, nk = O.ref_extract_rig_frames(imgs, NCAM, NFEAT, 1.2, 8, INI, MIN, LAPS, fma=True)
+    return frames / dt, dt, nk
+
+
+def cpu_oracle_run(frames, threads, rank=0):
+    """Times the CPU oracle (port of the reference's ORBextractor) on `frames` rig frames with `threads` host threads."""
+    O = _oracle()
     L = O.lib()
-    n = imgs.shape[0]
+    front, side = _front_side(frames, rank)
+    n = frames * NCAM
     nkp = np.zeros(n, np.int32); nm = np.zeros(n, np.int32)
-    # lapping differs per camera; the oracle batch call takes one pair -> run the two groups separately (same total work)
     t0 = time.perf_counter()
-    front = np.ascontiguousarray(imgs.reshape(frames, NCAM, H, W)[:, :2].reshape(-1, H, W))
-    side = np.ascontiguousarray(imgs.reshape(frames, NCAM, H, W)[:, 2:].reshape(-1, H, W))
     tot = L.orc_extract_batch(front.shape[0], O.p(front), W, H, NFEAT, O.C.c_float(1.2), 8, INI, MIN, 0, 720, 0, threads, O.p(nkp), O.p(nm))
     tot += L.orc_extract_batch(side.shape[0], O.p(side), W, H, NFEAT, O.C.c_float(1.2), 8, INI, MIN, 0, 0, 0, threads, O.p(nkp), O.p(nm))
     dt = time.perf_counter() - t0
     return frames / dt, dt, tot
+
+
+def cv2_primitive_line(n_images=3):
+    """Sanity line: the OpenCV primitives the reference calls (cv::resize, copyMakeBorder, FAST, GaussianBlur — SIMD builds in the cv2
+    wheel), one OpenCV thread, driven from Python: per-image ms of each stage.  The per-cell FAST loop pays ~900 Python -> C calls per
+    image; the whole-level FAST figure is the SIMD lower bound of the same pixels (not the reference's per-cell semantics)."""
+    try:
+        import cv2
+    except Exception as ex:   # noqa: BLE001
+        return {'unavailable': 'cv2 not importable: %s' % ex}
+    cv2.setNumThreads(1)
+    O = _oracle()
+    inv = O.OracleExtractor(NFEAT, 1.2, 8, INI, MIN).tables()['inv_sf']
+    imgs = make_batch(2, 0)[:n_images]
+    t = {'pyramid': 0.0, 'fast_per_cell': 0.0, 'fast_whole_level': 0.0, 'blur': 0.0}
+    det_i = cv2.FastFeatureDetector_create(INI, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    det_m = cv2.FastFeatureDetector_create(MIN, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    for img in imgs:
+        t0 = time.perf_counter()
+        levels = [img]
+        for l in range(1, 8):
+            dw, dh = int(np.rint(np.float32(W) * inv[l])), int(np.rint(np.float32(H) * inv[l]))
+            levels.append(cv2.resize(levels[-1], (dw, dh), interpolation=cv2.INTER_LINEAR))
+        for L in levels:
+            cv2.copyMakeBorder(L, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+        t1 = time.perf_counter()
+        for L in levels:                                  # src/ORBextractor.cc:709-794
+            hh, ww = L.shape
+            maxbx, maxby = ww - 16, hh - 16
+            ncols, nrows = int((maxbx - 16) / 35.0), int((maxby - 16) / 35.0)
+            wc, hc = int(np.ceil((maxbx - 16) / ncols)), int(np.ceil((maxby - 16) / nrows))
+            for i in range(nrows):
+                y0 = 16 + i * hc
+                if y0 >= maxby - 3:
+                    continue
+                y1 = min(y0 + hc + 6, maxby)
+                for j in range(ncols):
+                    x0 = 16 + j * wc
+                    if x0 >= maxbx - 6:
+                        continue
+                    cell = L[y0:y1, x0:min(x0 + wc + 6, maxbx)]
+                    if not det_i.detect(cell):
+                        det_m.detect(cell)
+        t2 = time.perf_counter()
+        for L in levels:
+            det_i.detect(L)
+        t3 = time.perf_counter()
+        for L in levels:
+            cv2.GaussianBlur(L, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+        t4 = time.perf_counter()
+        t['pyramid'] += t1 - t0; t['fast_per_cell'] += t2 - t1; t['fast_whole_level'] += t3 - t2; t['blur'] += t4 - t3
+    out = {k + '_ms_per_image': 1e3 * v / len(imgs) for k, v in t.items()}
+    out.update({'opencv': cv2.__version__, 'threads': 1, 'images': len(imgs)})
+    return out
 
 
 def guided_matchers(ob, device):
@@ -142,6 +233,12 @@ def guided_matchers(ob, device):
         for _ in range(reps):
             t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
         return float(np.median(ts)) * 1e3
+
+    # CPU side of every number below: the oracle's restatement of the same reference function (one host thread, as the reference
+    # runs it) on the same inputs; the grid build is inside the timed call on both sides
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import oracle_lib as O
+    import test_gpu_match as T
 
     # ---- SearchByProjection (src/ORBmatcher.cc:23-340)
     ncam, nmp, w = 2, 5000, 512
@@ -164,8 +261,11 @@ def guided_matchers(ob, device):
     def sbp():
         nm[0] = m.SearchByProjection(frame, points, 3.0)[0]
     ms = timed(sbp)
+    frame.update(occupied=np.zeros(int(cam_off[-1]), np.uint8), l2r=None, r2l=None)
+    points.update(depth=np.zeros(nmp, np.float32), bad=np.zeros(nmp, np.uint8), has_obs=np.ones(nmp, np.uint8))
+    cpu_ms = timed(lambda: T._oracle_sbp(frame, points, 3.0, np.float32(0.8), False, 50.0), reps=3)
     out['search_by_projection'] = {'map_points': nmp, 'cameras': ncam, 'keypoints': int(cam_off[-1]), 'matches': int(nm[0]), 'ms_per_call': ms,
-                                   'device_ms': m.last_ms(), 'map_points_per_s': nmp / (ms * 1e-3)}
+                                   'device_ms': m.last_ms(), 'map_points_per_s': nmp / (ms * 1e-3), 'cpu_ms_per_call': cpu_ms}
     # ---- SearchByProjection(CurrentFrame, LastFrame) (src/ORBmatcher.cc:1985-2413): the per-frame tracking matcher
     nlast = cam_off[-1]
     lsrc = rng.integers(0, nlast, nlast)
@@ -180,8 +280,9 @@ def guided_matchers(ob, device):
     def sbp_last():
         nm[0] = m.SearchByProjectionLast(frame, last, 7.0)[0]
     ms = timed(sbp_last)
+    cpu_ms = timed(lambda: T._oracle_sbp_last(frame, last, 7.0, False, False, True), reps=3)
     out['search_by_projection_last_frame'] = {'points': int(nlast), 'cameras': ncam, 'matches': int(nm[0]), 'ms_per_call': ms,
-                                              'device_ms': m.last_ms(), 'points_per_s': nlast / (ms * 1e-3)}
+                                              'device_ms': m.last_ms(), 'points_per_s': nlast / (ms * 1e-3), 'cpu_ms_per_call': cpu_ms}
     # ---- SearchByBoW(KeyFrame, Frame) (src/ORBmatcher.cc:349-666): 64 shared vocabulary nodes
     def fvec(d):
         node = d[:, 0].astype(np.int32) & 63
@@ -196,8 +297,16 @@ def guided_matchers(ob, device):
     def bow():
         nm[0] = m.SearchByBoW(fv_kf, fv_f, dkf, desc, None, akf, kps['angle'], cam_off)[0]
     ms = timed(bow)
+    Lo = O.lib()
+    skip0 = np.zeros(nlast, np.uint8); mref = np.zeros(nlast, np.int32)
+
+    def bow_cpu():
+        Lo.orc_search_by_bow_frame(len(fv_kf[0]), O.p(fv_kf[0]), O.p(fv_kf[1]), O.p(fv_kf[2]), len(fv_f[0]), O.p(fv_f[0]), O.p(fv_f[1]), O.p(fv_f[2]),
+                                   O.p(dkf), O.p(desc), int(nlast), O.p(skip0), O.p(akf), O.p(np.ascontiguousarray(kps['angle'])), ncam, O.p(cam_off),
+                                   O.C.c_float(0.8), 1, O.p(mref))
+    cpu_ms = timed(bow_cpu, reps=3)
     out['search_by_bow'] = {'keyframe_features': int(nlast), 'frame_features': int(nlast), 'matches': int(nm[0]), 'ms_per_call': ms,
-                            'device_ms': m.last_ms()}
+                            'device_ms': m.last_ms(), 'cpu_ms_per_call': cpu_ms}
     # ---- ComputeStereoMatches (src/Frame.cc:1057-1219)
     left = synth_image(752, 480, 2001)
     xs = np.arange(752)
@@ -209,14 +318,21 @@ def guided_matchers(ob, device):
     def stereo():
         ns[0] = st.compute_stereo_matches(0, 1, 0.11, 47.9)[0]
     ms = timed(stereo)
-    out['compute_stereo_matches'] = {'image': '2x752x480', 'matches': int(ns[0]), 'ms_per_call': ms}
+    EL = O.OracleExtractor(1200, 1.2, 8, 20, 7); ER = O.OracleExtractor(1200, 1.2, 8, 20, 7)
+    EL(left, (0, 0)); ER(right, (0, 0))
+    ru = np.zeros(4000, np.float32); rd = np.zeros(4000, np.float32)
+    Lo.orc_compute_stereo_matches.argtypes = [O.C.c_void_p, O.C.c_void_p, O.C.c_float, O.C.c_float, O.C.c_void_p, O.C.c_void_p]
+    cpu_ms = timed(lambda: Lo.orc_compute_stereo_matches(EL.h, ER.h, 0.11, 47.9, O.p(ru), O.p(rd)), reps=3)
+    out['compute_stereo_matches'] = {'image': '2x752x480', 'matches': int(ns[0]), 'ms_per_call': ms, 'cpu_ms_per_call': cpu_ms}
     # ---- ComputeDistinctiveDescriptors (src/MapPoint.cc:405-483)
     sizes = rng.integers(2, 24, 2000).astype(np.int32)
     ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     dd = np.repeat(synth_descriptors(2000, 9), sizes, axis=0) ^ np.packbits(rng.random((int(ptr[-1]), 256)) < 0.1, axis=1, bitorder='little')
     ms = timed(lambda: m.ComputeDistinctiveDescriptors(dd, ptr))
+    bref = np.zeros(2000, np.int32)
+    cpu_ms = timed(lambda: Lo.orc_distinctive_descriptors(O.p(dd), O.p(ptr), 2000, O.p(bref)), reps=3)
     out['distinctive_descriptors'] = {'map_points': 2000, 'descriptors': int(ptr[-1]), 'ms_per_call': ms, 'device_ms': m.last_ms(),
-                                      'map_points_per_s': 2000 / (ms * 1e-3)}
+                                      'map_points_per_s': 2000 / (ms * 1e-3), 'cpu_ms_per_call': cpu_ms}
     # ---- ComputeStereoFishEyeMatches (src/Frame.cc:1409-1459): 2-NN + ratio + KannalaBrandt8::TriangulateMatches
     from openmavis_b200.synth import synth_fisheye_pairs
     nk = 1500
@@ -239,29 +355,71 @@ def guided_matchers(ob, device):
     return out
 
 
+def secondary_configs(ob, torch, dev, local, stream):
+    """Device-resident extraction throughput on the other BASELINE.json configurations (parity for them is covered by tests/): batch of
+    synthetic images of the configuration's geometry, 2 warm-up + 5 timed steps, CUDA events on `stream`."""
+    from openmavis_b200.synth import synth_image
+    out = {}
+    cases = [('config1_euroc_mono_752x480_nf1000', 752, 480, 1, 1000, 256, [(0, 1000)]),
+             ('config2_euroc_stereo_2x752x480_nf1200', 752, 480, 2, 1200, 128, [(0, 0), (0, 0)]),
+             ('config4_tumvi_stereo_2x512x512_nf1500', 512, 512, 2, 1500, 128, [(0, 511), (0, 511)]),
+             ('config5_sweep_64x5x1280x1024_nf2000', 1280, 1024, 5, 2000, 64, [(0, 1280), (0, 1280), (0, 0), (0, 0), (0, 0)])]
+    for name, w, h, ncam, nf, frames, laps in cases:
+        n_img = frames * ncam
+        base = [synth_image(w, h, 7000 + 10 * ncam + i) for i in range(4)]
+        rng = np.random.default_rng(ncam)
+        host = np.empty((n_img, h, w), np.uint8)
+        for i in range(n_img):
+            im = base[i % 4]
+            if i >= 4:
+                im = np.roll(im, (int(rng.integers(1, h)), int(rng.integers(1, w))), axis=(0, 1))
+            host[i] = im
+        d = torch.from_numpy(host).to(dev)
+        rig = ob.RigExtractor(w, h, n_img, nf, 1.2, 8, device=local)
+        rig.set_stream(stream.cuda_stream)
+        prm = ob.make_params(n_img, nf, INI, MIN, laps * frames)
+        for _ in range(2):
+            rig.extract_device(d.data_ptr(), n_img, prm)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(5):
+            rig.extract_device(d.data_ptr(), n_img, prm)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        res = rig.fetch(n_img)
+        out[name] = {'cameras': ncam, 'image': [w, h], 'features_per_camera': nf, 'frames_per_step': frames, 'ms_per_step': ms,
+                     'frames_per_s': frames / (ms * 1e-3), 'images_per_s': n_img / (ms * 1e-3),
+                     'level0_gpixel_per_s': n_img * w * h / (ms * 1e-3) / 1e9, 'keypoints_per_image': float(np.mean([len(r[1]) for r in res]))}
+        rig.close()
+        del d
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  Its sources need OpenCV/Eigen/Sophus headers
-    that are not in this image, so the timed code is the oracle port, with all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path — src/ORBextractor.cc compiled unmodified from the reference
+    checkout with its own flags (oracle/_ref/libref_orb_fma.so; OpenCV primitives from the cv2-pinned oracle functions), all host threads."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     frames = max(1, min(args.ref_frames, 64))
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_oracle_run(1, threads)
-    vals, tot_t = [], 0.0
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_run(max(2, threads // NCAM + 1), threads)
+    tot_t = 0.0
     for _ in range(args.steps):
-        v, dt, _ = cpu_oracle_run(frames, threads)
-        vals.append(v); tot_t += dt
+        _, dt, _ = cpu_reference_run(frames, threads)
+        tot_t += dt
     value = frames * args.steps / tot_t
     line = {
         'impl': 'reference', 'metric': 'rig-frames/sec ORB extract (5×720×540, 1500 kp/cam)', 'value': value, 'unit': 'rig-frames/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'baseline_config': 'BASELINE.json configs[2]: Hilti-2022 5-camera rig 5×720×540, 1500 features/camera, per-rig-frame batched extraction', 'frames_per_step': frames, 'features_per_camera': NFEAT,
-                   'fast_thresholds': [INI, MIN], 'levels': 8, 'scale_factor': 1.2},
-        'cpu_baseline': {'value': value, 'unit': 'rig-frames/s', 'cores': threads, 'kind': 'port',
-                         'sample': '%d rig frames x %d steps, %d host threads (one image per thread)' % (frames, args.steps, threads)},
+        'config': CONFIG, 'run': {'frames_per_step': frames},
+        'cpu_baseline': {'value': value, 'unit': 'rig-frames/s', 'cores': threads, 'kind': 'reference',
+                         'sample': '%d rig frames x %d steps, %d host threads (one image per thread at a time); src/ORBextractor.cc compiled '
+                                   'unmodified (oracle/_ref/libref_orb_fma.so)' % (frames, args.steps, threads)},
         'e2e': {'value': value, 'unit': 'rig-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -280,6 +438,8 @@ def main():
     ap.add_argument('--no-matching', action='store_true')
     ap.add_argument('--no-numa-bind', action='store_true', help='do not pin the rank to the CPU cores next to its GPU')
     ap.add_argument('--knn-n', type=int, default=100000)
+    ap.add_argument('--sustain-seconds', type=float, default=2.0, help='length of the sustained-rate run (0 = skip)')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the other BASELINE.json configurations')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -296,9 +456,10 @@ def main():
     torch.cuda.set_device(local)
     # one process per GPU: run it (and first-touch its pinned staging buffers) on the NUMA node the GPU hangs off
     affinity0 = os.sched_getaffinity(0)
-    numa_node = None
+    numa_node, numa_nodes = None, None
+    from openmavis_b200.shard import bind_to_gpu_numa, host_numa_nodes
+    numa_nodes = host_numa_nodes()
     if not args.no_numa_bind:
-        from openmavis_b200.shard import bind_to_gpu_numa
         pr = torch.cuda.get_device_properties(local)
         if all(hasattr(pr, a) for a in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
             numa_node = bind_to_gpu_numa('%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
@@ -365,8 +526,34 @@ def main():
     barrier()
     clocks = sampler.stop(t_wall0, time.perf_counter()) if sampler else None
     stage = rig.stage_ms()
+    fast_stats = rig.fast_stats()                    # k_fast counters over the profiled calls
+    fast_stats['profiled_calls'] = min(args.steps, 16)
     rig.set_profiling(False)
     value = world * frames * args.steps / (ms_total * 1e-3)
+    # ---------------- sustained rate: the same device pipeline for >= sustain-seconds, with its own clock record ----------------
+    sustained = None
+    if args.sustain_seconds > 0:
+        rig_b2 = ob.RigExtractor(W, H, n_img, NFEAT, 1.2, 8, device=local)
+        rig_b2.set_stream(stream_b.cuda_stream)
+        pair2 = (rig, rig_b2)
+        n_sus = max(args.steps, int(np.ceil(args.sustain_seconds * 1e3 / (ms_total / args.steps))))
+        for k in range(2):
+            pair2[k & 1].extract_device(d_imgs.data_ptr(), n_img, params)
+        barrier()
+        samp2 = ClockSampler(local) if rank == 0 else None
+        tw0 = time.perf_counter()
+        e0.record(stream)
+        stream_b.wait_event(e0)
+        for k in range(n_sus):
+            pair2[k & 1].extract_device(d_imgs.data_ptr(), n_img, params)
+        stream.wait_stream(stream_b)
+        e1.record(stream)
+        barrier()
+        tw1 = time.perf_counter()
+        ms_sus = max_over_ranks(e0.elapsed_time(e1))
+        sustained = {'value': world * frames * n_sus / (ms_sus * 1e-3), 'unit': 'rig-frames/s', 'steps': n_sus, 'seconds': ms_sus * 1e-3,
+                     'ms_per_step': ms_sus / n_sus, 'clocks': samp2.stop(tw0, tw1) if samp2 else None}
+        rig_b2.close()
     res = rig.fetch(n_img)
     for i in (0, n_img - 1):                         # both handles of the timed pipeline produced the same results
         assert np.array_equal(res[i][1], res_b[i][1]) and np.array_equal(res[i][2], res_b[i][2])
@@ -405,6 +592,28 @@ def main():
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * frames * e2e_steps / (ms_e2e * 1e-3)
+    # copy roofline: what the host link alone allows — every rank moves the same bytes (pinned images in, keypoints + descriptors +
+    # counts out) with plain asynchronous copies on two streams (both directions at once), no kernels
+    cr_in = torch.empty((n_img, H, W), dtype=torch.uint8, device=dev)
+    cr_out_d = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in lanes[0][5]]
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def copy_run(k_steps):
+        for _ in range(k_steps):
+            with torch.cuda.stream(s_in):
+                cr_in.copy_(pinned, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                for hbuf, dbuf in zip(lanes[0][5], cr_out_d):
+                    hbuf.copy_(dbuf, non_blocking=True)
+        s_in.synchronize(); s_out.synchronize()
+    copy_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    copy_run(e2e_steps)
+    barrier()
+    ms_copy = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    copy_value = world * frames * e2e_steps / (ms_copy * 1e-3)
+    del cr_in, cr_out_d
     # latency-oriented variant: one synchronous orbx_extract_batch call per step
     kps_np, desc_np, nkp_np, nmono_np = lanes[0][1], lanes[0][2], lanes[0][3], lanes[0][4]
     barrier()
@@ -516,7 +725,10 @@ def main():
         popc = ob.popc_peak(local)
         matching = {'metric': 'Hamming matches/sec (brute-force 2-NN %dx%d)' % (n, n), 'value': pairs / (ms_knn * 1e-3), 'unit': 'pairs/s',
                     'ms': ms_knn, 'popc_gops_achieved': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world, 'popc_gops_peak_measured': popc,
-                    'frac_of_popc_peak': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world / popc, 'n_gpus': world,
+                    'frac_of_popc_peak': 8 * pairs / (ms_knn * 1e-3) / 1e9 / world / popc,
+                    'executed_popc_per_pair': 6, 'executed_popc_frac_of_peak': 6 * pairs / (ms_knn * 1e-3) / 1e9 / world / popc,
+                    'note': 'algorithmic work = 8 popc.b32 per pair (SURVEY.md 8d); the kernel executes 6 (two carry-save adders per pair), so the '
+                            'XU-pipe utilisation is the executed figure', 'n_gpus': world,
                     'collective': None if world == 1 else ('none for the data: peer-mapped train rows pulled over NVLink (cudaIpc); one 4-byte all-reduce per step as barrier' if shared is not None else 'nccl all_gather of the train rows (peer mapping unavailable)')}
         if rank == 0:
             torch.cuda.set_stream(torch.cuda.default_stream(dev))
@@ -530,37 +742,53 @@ def main():
             torch.cuda.synchronize()
             shared.close()
 
+    # ---------------- the other BASELINE.json configurations (rank 0, N == 1 only) ----------------
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = secondary_configs(ob, torch, dev, local, stream)
+
     # ---------------- CPU baseline (rank 0, N == 1 only; bounded sample) ----------------
     cpu = None
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
         os.sched_setaffinity(0, affinity0)             # the CPU arm uses every host core again
         threads = os.cpu_count() or 1
-        cpu_oracle_run(2, threads)                      # warm-up (page in, thread pool)
+        cpu_reference_run(max(2, threads // NCAM + 1), threads)       # warm-up (page in, malloc arenas of the worker threads)
         nfr, done, spent = 32, 0, 0.0
         while spent < args.cpu_seconds:                 # bounded sample: repeat a 32-rig-frame batch for ~cpu_seconds
-            _, dt, _ = cpu_oracle_run(nfr, threads)
+            _, dt, _ = cpu_reference_run(nfr, threads)
             done += nfr; spent += dt
-        cpu = {'value': done / spent, 'unit': 'rig-frames/s', 'cores': threads, 'kind': 'port',
-               'sample': '%d rig frames (%d images) of the same workload, %.1f s of extraction, %d host threads' % (
-                   done, done * NCAM, spent, threads)}
+        v_tpc, dt_tpc, _ = cpu_reference_thread_per_camera(max(4, int(4.0 * done / spent / max(1, threads // NCAM))))
+        v_port, dt_port, _ = cpu_oracle_run(32, threads)
+        cpu = {'value': done / spent, 'unit': 'rig-frames/s', 'cores': threads, 'kind': 'reference',
+               'sample': '%d rig frames (%d images) of the same workload, %.1f s of extraction, %d host threads; src/ORBextractor.cc compiled '
+                         'unmodified with the reference flags (oracle/_ref/libref_orb_fma.so), OpenCV primitives from the cv2-pinned oracle' % (
+                             done, done * NCAM, spent, threads),
+               'thread_per_camera': {'value': v_tpc, 'unit': 'rig-frames/s', 'threads': NCAM, 'seconds': dt_tpc,
+                                     'what': 'rig frames one after the other, one std::thread per camera per frame (src/Frame.cc:1841-1862)'},
+               'oracle_port': {'value': v_port, 'unit': 'rig-frames/s', 'cores': threads, 'seconds': dt_port},
+               'cv2_primitives': cv2_primitive_line()}
 
     if rank == 0:
         line = {
             'metric': 'rig-frames/sec ORB extract (5×720×540, 1500 kp/cam)', 'value': value, 'unit': 'rig-frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': 'hilti_rig_5x720x540_nf1500', 'baseline_config': 'BASELINE.json configs[2]: Hilti-2022 5-camera rig 5×720×540, 1500 features/camera, per-rig-frame batched extraction', 'frames_per_step_per_gpu': frames, 'images_per_step_per_gpu': n_img,
-                       'features_per_camera': NFEAT, 'fast_thresholds': [INI, MIN], 'levels': 8, 'scale_factor': 1.2,
-                       'keypoints_per_image': kp_per_image, 'pipeline': 'two extractor handles alternate over the steps (one stream each)',
-                       'host_numa_node': numa_node,
-                       'l2': 'inputs+pyramids per step (%.0f MB) exceed the 126 MB L2' % ((px * 1.0 + px * 3.7 * 2) / 1e6)},
+            'config': CONFIG,
+            'run': {'frames_per_step_per_gpu': frames, 'images_per_step_per_gpu': n_img, 'keypoints_per_image': kp_per_image,
+                    'pipeline': 'two extractor handles alternate over the steps (one stream each)',
+                    'host_numa_node': numa_node, 'host_numa_nodes': numa_nodes, 'host_cpus': len(affinity0),
+                    'bytes_per_step_mb': (px * 1.0 + px * 3.7 * 2) / 1e6, 'fast_counters': fast_stats},
             'e2e': {'value': e2e_value, 'unit': 'rig-frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / e2e_steps, 'steps': e2e_steps, 'timing': 'host wall clock between barrier + synchronize',
                     'pipeline': 'two handles alternating (orbx_extract_batch_submit / orbx_extract_wait)',
                     'sync_call_ms_per_step': ms_sync_call, 'sync_call_value': world * frames / (ms_sync_call * 1e-3),
-                    'one_rig_frame_latency_ms': ms_one_frame},
+                    'one_rig_frame_latency_ms': ms_one_frame,
+                    'copy_roofline': {'value': copy_value, 'unit': 'rig-frames/s', 'ms_per_step': ms_copy / e2e_steps,
+                                      'h2d_gb_per_s_per_gpu': h2d / (ms_copy / e2e_steps * 1e-3) / 1e9, 'd2h_gb_per_s_per_gpu': d2h / (ms_copy / e2e_steps * 1e-3) / 1e9,
+                                      'what': 'the same pinned buffers moved by plain cudaMemcpyAsync on two streams, all ranks at once, no kernels'},
+                    'frac_of_copy_roofline': e2e_value / copy_value},
             'gpu_launches': launches_per_step * args.steps,
-            'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'matching': matching,
+            'clocks': clocks, 'roofline': roofline, 'sustained': sustained, 'cpu_baseline': cpu, 'secondary': secondary, 'matching': matching,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

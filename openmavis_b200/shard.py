@@ -57,6 +57,15 @@ def gather_results(idx_local, dist_local, n_total, dist):
     return out[:, :2].copy(), out[:, 2:].copy()
 
 
+def host_numa_nodes():
+    """Number of NUMA nodes the host exposes (1 on a single-socket or virtualised box), or None when /sys cannot be read."""
+    import os
+    try:
+        return len([d for d in os.listdir('/sys/devices/system/node') if d.startswith('node') and d[4:].isdigit()])
+    except OSError:
+        return None
+
+
 def bind_to_gpu_numa(pci_bus_id):
     """Pin this process (one per GPU) to the CPU cores of the NUMA node its GPU hangs off, so that the pinned staging buffers it
     allocates afterwards are first-touched on that node and the host<->device copies do not cross the socket interconnect.
@@ -67,7 +76,21 @@ def bind_to_gpu_numa(pci_bus_id):
         with open('/sys/bus/pci/devices/%s/numa_node' % pci_bus_id.lower()) as f:
             node = int(f.read().strip())
         if node < 0:
-            return None
+            # the device reports no node (virtual machines do): with a single node there is nothing to bind — report node 0;
+            # otherwise fall back to the CPU list the PCI device names as local
+            if host_numa_nodes() == 1:
+                return 0
+            with open('/sys/bus/pci/devices/%s/local_cpulist' % pci_bus_id.lower()) as f:
+                spec = f.read().strip()
+            cpus = set()
+            for part in spec.split(','):
+                a, _, b = part.partition('-')
+                cpus.update(range(int(a), int(b or a) + 1))
+            allowed = os.sched_getaffinity(0) & cpus
+            if not allowed or allowed == os.sched_getaffinity(0):
+                return None
+            os.sched_setaffinity(0, allowed)
+            return -1
         with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
             spec = f.read().strip()
         cpus = set()

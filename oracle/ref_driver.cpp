@@ -10,6 +10,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -134,6 +135,33 @@ double ref_extract_batch(int nimg, const uint8_t *imgs, int w, int hh, int nfeat
     long long s = 0;
     for (auto c : cnt) s += c;
     if (nkp) *nkp = s;
+    return dt;
+}
+
+// CPU baseline, reference-faithful threading: rig frames one after the other, each with one std::thread per camera created and joined
+// per frame around persistent extractor objects (src/Frame.cc:1841-1862 + mpORBextractorLeft ... of src/Tracking.cc:572-587).
+// imgs = [nframes][ncam][h][w]; laps = [ncam][2].  Returns seconds.
+double ref_extract_rig_frames(int nframes, int ncam, const uint8_t *imgs, int w, int hh, int nfeatures, float sf, int nlevels, int iniTh, int minTh,
+                              const int *laps, long long *nkp) {
+    std::vector<std::unique_ptr<ORB_SLAM3::ORBextractor>> ex;
+    for (int c = 0; c < ncam; c++) ex.emplace_back(new ORB_SLAM3::ORBextractor(nfeatures, sf, nlevels, iniTh, minTh));
+    std::vector<std::vector<cv::KeyPoint>> kps(ncam);
+    std::vector<cv::Mat> desc(ncam);
+    long long total = 0;
+    const double t0 = now_s();
+    for (int f = 0; f < nframes; f++) {
+        std::vector<std::thread> th;
+        for (int c = 0; c < ncam; c++)
+            th.emplace_back([&, c]() {
+                cv::Mat image(hh, w, CV_8UC1, (void *)(imgs + ((size_t)f * ncam + c) * w * hh), (size_t)w);
+                std::vector<int> lap = {laps[2 * c], laps[2 * c + 1]};
+                (*ex[c])(image, cv::Mat(), kps[c], desc[c], lap);
+            });
+        for (auto &t : th) t.join();
+        for (int c = 0; c < ncam; c++) total += (long long)kps[c].size();
+    }
+    const double dt = now_s() - t0;
+    if (nkp) *nkp = total;
     return dt;
 }
 

@@ -205,6 +205,7 @@ def ref_lib(fma=False):
         L.ref_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_extract_batch.restype = C.c_double
+        L.ref_extract_rig_frames.restype = C.c_double
         _ref_libs[fma] = L
     return _ref_libs[fma]
 
@@ -279,4 +280,14 @@ def ref_extract_batch(imgs, nfeatures, sf, nlevels, ini, mn, lapping, nthreads, 
     nkp = C.c_longlong(0)
     dt = ref_lib(fma).ref_extract_batch(n, p(imgs), w, hh, nfeatures, C.c_float(sf), nlevels, ini, mn, int(lapping[0]), int(lapping[1]),
                                         nthreads, C.byref(nkp))
+    return dt, nkp.value
+
+
+def ref_extract_rig_frames(imgs, ncam, nfeatures, sf, nlevels, ini, mn, laps, fma=True):
+    """seconds, keypoints: rig frames one after the other, one std::thread per camera per frame (src/Frame.cc:1841-1862)"""
+    imgs = np.ascontiguousarray(imgs)
+    n, hh, w = imgs.shape
+    lp = np.ascontiguousarray(laps, np.int32).reshape(ncam, 2)
+    nkp = C.c_longlong(0)
+    dt = ref_lib(fma).ref_extract_rig_frames(n // ncam, ncam, p(imgs), w, hh, nfeatures, C.c_float(sf), nlevels, ini, mn, p(lp), C.byref(nkp))
     return dt, nkp.value

@@ -17,8 +17,8 @@ fi
 # profiler passes: one per call (NCU=launches or NCU=full), never together with the timed runs above
 if [ "$NCU" = "launches" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 2 --warmup 1 --frames 64 --knn-n 100000 --cpu-seconds 0 > gpurun_out/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
+    python bench.py --steps 2 --warmup 1 --frames 64 --knn-n 100000 --cpu-seconds 0 --no-secondary --sustain-seconds 0 > gpurun_out/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
 elif [ "$NCU" = "full" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KREGEX" -c 30 -o gpurun_out/full_$TAG -f \
-    python bench.py --steps 1 --warmup 1 --frames 64 --knn-n 100000 --cpu-seconds 0 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+    python bench.py --steps 1 --warmup 1 --frames 64 --knn-n 100000 --cpu-seconds 0 --no-secondary --sustain-seconds 0 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 fi
