@@ -1,0 +1,214 @@
+// ORBmatcher_glue.cc — ORB_SLAM3::ORBmatcher methods with the REFERENCE's signatures (include/ORBmatcher.h:17-123, unmodified) on the
+// C ABI of liborbx.so: the marshalling a maintainer puts in place of the corresponding bodies of src/ORBmatcher.cc.
+//
+// Compiled against the integrator's own headers (ORBmatcher.h, Frame.h, KeyFrame.h, MapPoint.h): it only touches the members the
+// reference bodies touch.  Every search runs on the device; what stays here is what the reference does around it on the host —
+// reading Frame / KeyFrame / MapPoint members into flat arrays and writing the matches back into F.mvpMapPoints / the output vectors.
+// Methods not listed here keep their reference bodies (their device entry points are documented in INTEGRATION.md).
+//
+//   ORBmatcher::DescriptorDistance                                   src/ORBmatcher.cc:2577-2591   host popcount (8 words)
+//   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, ...)  src/ORBmatcher.cc:23-340      orbx_search_by_projection
+//   ORBmatcher::SearchForInitialization(F1, F2, ...)                 src/ORBmatcher.cc:895-1004    orbx_search_for_initialization
+//   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)                  src/ORBmatcher.cc:349-666     orbx_search_by_bow_frame
+//
+// tests/host_harness builds this file against oracle/refstub (stub Frame / KeyFrame / MapPoint with the reference's member names) and
+// tests/test_matcher_glue.py compares it, call by call, with the reference's own object code (oracle/_ref/libref_matcher.so).
+#include <ORBmatcher.h>   // the REFERENCE's include/ORBmatcher.h from the include path (not the array-level header next to this file)
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "orbx.h"
+
+namespace ORB_SLAM3 {
+
+const int ORBmatcher::TH_HIGH = 100;
+const int ORBmatcher::TH_LOW = 50;
+const int ORBmatcher::HISTO_LENGTH = 30;
+
+namespace {
+
+[[noreturn]] void die(const char *what) {   // no CPU fallback: fail loudly
+    fprintf(stderr, "ORBmatcher::%s: %s\n", what, orbx_last_error());
+    abort();
+}
+
+// ORBmatcher objects are stack objects created at every call site (src/Tracking.cc:2828 ...): the device handle (stream, events,
+// staging buffers) is per host thread instead, created on first use.  ORBX_DEVICE selects the GPU of the process (default 0).
+orbx_matcher *handle() {
+    thread_local orbx_matcher *h = nullptr;
+    if (!h) {
+        const char *d = getenv("ORBX_DEVICE");
+        if (orbx_matcher_create(&h, d ? atoi(d) : 0) != ORBX_OK) die("orbx_matcher_create");
+    }
+    return h;
+}
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_kp), "cv::KeyPoint and orbx_kp must have the same layout");
+
+// keypoints of a Frame in global feature order: [mvKeysUn] (Nleft == -1) or [mvKeys | mvKeysRight | mvKeysSideLeft | mvKeysSideRight]
+int frame_layout(const Frame &F, std::vector<orbx_kp> &kps, int cam_off[5]) {
+    auto add = [&](const std::vector<cv::KeyPoint> &v, int n) { kps.insert(kps.end(), (const orbx_kp *)v.data(), (const orbx_kp *)v.data() + n); };
+    kps.clear();
+    cam_off[0] = 0;
+    if (F.Nleft == -1) {
+        add(F.mvKeysUn, F.N);
+        for (int c = 1; c <= 4; c++) cam_off[c] = F.N;
+        return 1;
+    }
+    add(F.mvKeys, F.Nleft); cam_off[1] = F.Nleft;
+    add(F.mvKeysRight, F.Nright); cam_off[2] = F.Nleft + F.Nright;
+    if (F.Nsideleft == -1 && F.Nsideright == -1) { cam_off[3] = cam_off[4] = cam_off[2]; return 2; }
+    add(F.mvKeysSideLeft, F.Nsideleft); cam_off[3] = cam_off[2] + F.Nsideleft;
+    add(F.mvKeysSideRight, F.Nsideright); cam_off[4] = cam_off[3] + F.Nsideright;
+    return 4;
+}
+
+// descriptor rows as one contiguous N x 32 block (cv::Mat rows may be strided)
+const unsigned char *desc_rows(const cv::Mat &m, std::vector<unsigned char> &tmp) {
+    if (m.rows == 0) { tmp.assign(32, 0); return tmp.data(); }
+    if (m.isContinuous()) return m.ptr<unsigned char>(0);
+    tmp.resize((size_t)m.rows * 32);
+    for (int r = 0; r < m.rows; r++) memcpy(&tmp[(size_t)r * 32], m.ptr<unsigned char>(r), 32);
+    return tmp.data();
+}
+
+// DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) -> CSR
+void feature_vector_csr(const DBoW2::FeatureVector &fv, std::vector<int> &nodes, std::vector<int> &ptr, std::vector<int> &idx) {
+    nodes.clear(); idx.clear(); ptr.assign(1, 0);
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        nodes.push_back((int)it->first);
+        for (size_t k = 0; k < it->second.size(); k++) idx.push_back((int)it->second[k]);
+        ptr.push_back((int)idx.size());
+    }
+}
+
+}  // namespace
+
+ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+
+// One pair: eight popcounts on the host (the remaining host callers — MapPoint::ComputeDistinctiveDescriptors, LoopClosing — call this
+// per pair; a kernel launch per 256-bit popcount would be absurd).  Batches go through orbx_descriptor_distance / the matchers.
+int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b) {
+    const unsigned int *pa = a.ptr<unsigned int>(), *pb = b.ptr<unsigned int>();
+    int dist = 0;
+    for (int i = 0; i < 8; i++) dist += __builtin_popcount(pa[i] ^ pb[i]);
+    return dist;
+}
+
+// src/ORBmatcher.cc:23-340
+int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th, const bool bFarPoints,
+                                   const float thFarPoints) {
+    std::vector<orbx_kp> kps;
+    int cam_off[5];
+    const int ncam = frame_layout(F, kps, cam_off);
+    const int N = F.N, nmp = (int)vpMapPoints.size();
+    if (N == 0 || nmp == 0) return 0;
+    std::vector<unsigned char> dtmp;
+    const unsigned char *desc = desc_rows(F.mDescriptors, dtmp);
+    float bounds[16];
+    for (int c = 0; c < 4; c++) { bounds[4 * c] = F.mnMinX; bounds[4 * c + 1] = F.mnMaxX; bounds[4 * c + 2] = F.mnMinY; bounds[4 * c + 3] = F.mnMaxY; }
+    std::vector<unsigned char> occupied(N, 0);
+    for (int i = 0; i < N; i++) occupied[i] = F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0;     // :77-79
+    std::vector<unsigned char> in_view((size_t)nmp * 4, 0), bad(nmp, 0), has_obs(nmp, 0), mp_desc((size_t)nmp * 32, 0);
+    std::vector<float> px((size_t)nmp * 4, 0.f), py((size_t)nmp * 4, 0.f), vc((size_t)nmp * 4, 0.f), pxr(nmp, 0.f), depth(nmp, 0.f);
+    std::vector<int> level((size_t)nmp * 4, 0);
+    for (int m = 0; m < nmp; m++) {
+        MapPoint *p = vpMapPoints[m];
+        in_view[4 * m] = p->mbTrackInView; in_view[4 * m + 1] = p->mbTrackInViewR; in_view[4 * m + 2] = p->mbTrackInViewSL; in_view[4 * m + 3] = p->mbTrackInViewSR;
+        px[4 * m] = p->mTrackProjX; px[4 * m + 1] = p->mTrackProjXR; px[4 * m + 2] = p->mTrackProjXSL; px[4 * m + 3] = p->mTrackProjXSR;
+        py[4 * m] = p->mTrackProjY; py[4 * m + 1] = p->mTrackProjYR; py[4 * m + 2] = p->mTrackProjYSL; py[4 * m + 3] = p->mTrackProjYSR;
+        level[4 * m] = p->mnTrackScaleLevel; level[4 * m + 1] = p->mnTrackScaleLevelR; level[4 * m + 2] = p->mnTrackScaleLevelSL;
+        level[4 * m + 3] = p->mnTrackScaleLevelSR;
+        vc[4 * m] = p->mTrackViewCos; vc[4 * m + 1] = p->mTrackViewCosR; vc[4 * m + 2] = p->mTrackViewCosSL; vc[4 * m + 3] = p->mTrackViewCosSR;
+        pxr[m] = p->mTrackProjXR; depth[m] = p->mTrackDepth;
+        bad[m] = p->isBad(); has_obs[m] = p->Observations() > 0;
+        if (in_view[4 * m] | in_view[4 * m + 1] | in_view[4 * m + 2] | in_view[4 * m + 3]) {
+            const cv::Mat d = p->GetDescriptor();
+            memcpy(&mp_desc[(size_t)m * 32], d.ptr<unsigned char>(0), 32);
+        }
+    }
+    std::vector<int> assigned(N, -1);
+    int nmatches = 0;
+    const bool stereo = ncam == 1 && (int)F.mvuRight.size() == N;
+    if (orbx_search_by_projection(handle(), ncam, cam_off, kps.data(), desc, bounds, F.mvScaleFactors.data(), (int)F.mvScaleFactors.size(),
+                                  occupied.data(), ncam >= 2 ? F.mvLeftToRightMatch.data() : nullptr, ncam >= 2 ? F.mvRightToLeftMatch.data() : nullptr,
+                                  stereo ? F.mvuRight.data() : nullptr, nmp, in_view.data(), px.data(), py.data(), level.data(), vc.data(),
+                                  stereo ? pxr.data() : nullptr, depth.data(), bad.data(), has_obs.data(), mp_desc.data(), th, bFarPoints ? 1 : 0,
+                                  thFarPoints, mfNNratio, assigned.data(), &nmatches) != ORBX_OK)
+        die("SearchByProjection(Frame, MapPoints)");
+    for (int i = 0; i < N; i++)
+        if (assigned[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[assigned[i]];          // :122, 127, 195-199, 267, 332
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:895-1004
+int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize) {
+    static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "cv::Point2f must be two packed floats");
+    const int n1 = (int)F1.mvKeysUn.size(), n2 = (int)F2.mvKeysUn.size();
+    vnMatches12 = std::vector<int>(n1, -1);                                           // :902
+    if (n1 == 0 || n2 == 0) return 0;
+    std::vector<unsigned char> t1, t2;
+    const unsigned char *d1 = desc_rows(F1.mDescriptors, t1), *d2 = desc_rows(F2.mDescriptors, t2);
+    const float bounds[4] = {F2.mnMinX, F2.mnMaxX, F2.mnMinY, F2.mnMaxY};
+    int nmatches = 0;
+    if (orbx_search_for_initialization(handle(), (const orbx_kp *)F1.mvKeysUn.data(), d1, n1, (const orbx_kp *)F2.mvKeysUn.data(), d2, n2, bounds,
+                                       (float *)vbPrevMatched.data(), windowSize, mfNNratio, mbCheckOrientation ? 1 : 0, vnMatches12.data(),
+                                       &nmatches) != ORBX_OK)
+        die("SearchForInitialization");
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:349-666
+int ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint *> &vpMapPointMatches) {
+    const std::vector<MapPoint *> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint *>(F.N, static_cast<MapPoint *>(NULL));
+    const int nKF = (int)vpMapPointsKF.size(), nF = F.N;
+    if (nKF == 0 || nF == 0) return 0;
+    std::vector<int> nk, pk, ik, nf, pf, iff;
+    feature_vector_csr(pKF->mFeatVec, nk, pk, ik);
+    feature_vector_csr(F.mFeatVec, nf, pf, iff);
+    std::vector<unsigned char> skip(nKF, 0), t1, t2;
+    for (int i = 0; i < nKF; i++) skip[i] = !vpMapPointsKF[i] || vpMapPointsKF[i]->isBad();     // :377-380
+    // keypoint angles by feature index, chosen as :484-505 choose kp / Fkp
+    std::vector<float> aKF(nKF, 0.f), aF(nF, 0.f);
+    if (mbCheckOrientation) {
+        for (int i = 0; i < nKF; i++) {
+            const cv::KeyPoint &kp = (!pKF->mpCamera2)                              ? pKF->mvKeysUn[i]
+                                     : (i < pKF->NLeft)                            ? pKF->mvKeys[i]
+                                     : (i < pKF->NLeft + pKF->NRight)              ? pKF->mvKeysRight[i - pKF->NLeft]
+                                     : (i < pKF->NLeft + pKF->NRight + pKF->NSideLeft) ? pKF->mvKeysSideLeft[i - pKF->NLeft - pKF->NRight]
+                                                                                   : pKF->mvKeysSideRight[i - pKF->NLeft - pKF->NRight - pKF->NSideLeft];
+            aKF[i] = kp.angle;
+        }
+        for (int i = 0; i < nF; i++) {
+            const cv::KeyPoint &kp = (!pKF->mpCamera2 || i < F.Nleft)              ? F.mvKeys[i]
+                                     : (i < F.Nleft + F.Nright)                    ? F.mvKeysRight[i - F.Nleft]
+                                     : (i < F.Nleft + F.Nright + F.Nsideleft)      ? F.mvKeysSideLeft[i - F.Nleft - F.Nright]
+                                                                                   : F.mvKeysSideRight[i - F.Nleft - F.Nright - F.Nsideleft];
+            aF[i] = kp.angle;
+        }
+    }
+    int cam_off[5] = {0, nF, nF, nF, nF};
+    int ncam = 1;
+    if (F.Nleft != -1) {
+        cam_off[1] = F.Nleft; cam_off[2] = F.Nleft + F.Nright;
+        ncam = 2;
+        if (F.Nsideleft != -1 || F.Nsideright != -1) { cam_off[3] = cam_off[2] + F.Nsideleft; cam_off[4] = cam_off[3] + F.Nsideright; ncam = 4; }
+        else cam_off[3] = cam_off[4] = cam_off[2];
+    }
+    std::vector<int> matchF(nF, -1);
+    int nmatches = 0;
+    if (orbx_search_by_bow_frame(handle(), (int)nk.size(), nk.data(), pk.data(), ik.data(), (int)nf.size(), nf.data(), pf.data(), iff.data(),
+                                 desc_rows(pKF->mDescriptors, t1), nKF, desc_rows(F.mDescriptors, t2), nF, skip.data(), aKF.data(), aF.data(), ncam,
+                                 cam_off, mfNNratio, mbCheckOrientation ? 1 : 0, matchF.data(), &nmatches) != ORBX_OK)
+        die("SearchByBoW(KeyFrame, Frame)");
+    for (int i = 0; i < nF; i++)
+        if (matchF[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[matchF[i]];
+    return nmatches;
+}
+
+}  // namespace ORB_SLAM3

@@ -91,11 +91,13 @@ void fill_frame(Frame &F, int ncam, const int *cam_off, const ref_kp *kps, const
     F.AssignFeaturesToGrid();
 }
 
+#ifndef ORBX_GLUE_BUILD
 class MatcherProbe : public ORBmatcher {
   public:
     using ORBmatcher::ORBmatcher;
     void three_maxima(std::vector<int> *h, int L, int &a, int &b, int &c) { ComputeThreeMaxima(h, L, a, b, c); }
 };
+#endif
 
 }  // namespace
 
@@ -107,6 +109,7 @@ int refm_descriptor_distance(const uint8_t *a, const uint8_t *b) {
     return ORBmatcher::DescriptorDistance(ma, mb);
 }
 
+#ifndef ORBX_GLUE_BUILD
 // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:2537-2573) on a histogram given by its bin sizes
 void refm_three_maxima(const int *sizes, int L, int *ind3) {
     std::vector<std::vector<int>> h(L);
@@ -115,6 +118,7 @@ void refm_three_maxima(const int *sizes, int L, int *ind3) {
     ind3[0] = ind3[1] = ind3[2] = -1;
     m.three_maxima(h.data(), L, ind3[0], ind3[1], ind3[2]);
 }
+#endif
 
 // Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea (src/Frame.cc:541-582, 890-978) of one camera's keypoints
 int refm_grid_query(const ref_kp *kps, int n, const float *bounds, float x, float y, float r, int minLevel, int maxLevel, int *out, int cap) {
@@ -194,6 +198,58 @@ int refm_search_for_initialization(const ref_kp *kps1, const uint8_t *desc1, int
     return n;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, vpMapPointMatches) (src/ORBmatcher.cc:349-666); same arrays as orc_search_by_bow_frame
+// plus the camera blocks of the KeyFrame's features (cam_off_kf, only the keypoint angles depend on them).  match_f[nF] = KeyFrame
+// feature whose MapPoint ended up in vpMapPointMatches[i], or -1.
+int refm_search_by_bow_frame(int nnKF, const int *nodesKF, const int *ptrKF, const int *idxKF, int nnF, const int *nodesF, const int *ptrF,
+                             const int *idxF, const uint8_t *descKF, int nKF, const uint8_t *descF, int nF, const uint8_t *skipKF,
+                             const float *angleKF, const float *angleF, int ncam, const int *camOffKF, const int *camOffF, float nnratio,
+                             int checkOrientation, int *matchF) {
+    const float bounds[4] = {0.f, 1000.f, 0.f, 1000.f};
+    set_bounds(bounds);
+    std::vector<ref_kp> kf(nKF), ff(nF);
+    memset(kf.data(), 0, kf.size() * sizeof(ref_kp)); memset(ff.data(), 0, ff.size() * sizeof(ref_kp));
+    for (int i = 0; i < nKF; i++) { kf[i].x = kf[i].y = 10.f; kf[i].angle = angleKF ? angleKF[i] : 0.f; }
+    for (int i = 0; i < nF; i++) { ff[i].x = ff[i].y = 10.f; ff[i].angle = angleF ? angleF[i] : 0.f; }
+    const float sf1[1] = {1.f};
+    Frame F;
+    fill_frame(F, ncam, camOffF, ff.data(), descF, sf1, 1);
+    F.mvKeys = ncam == 1 ? F.mvKeysUn : F.mvKeys;
+    for (int a = 0; a < nnF; a++)
+        for (int j = ptrF[a]; j < ptrF[a + 1]; j++) F.mFeatVec[(unsigned)nodesF[a]].push_back((unsigned)idxF[j]);
+    KeyFrame K;
+    PixelCamera cams[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
+    K.N = nKF;
+    K.mpCamera = &cams[0];
+    if (ncam == 1) {
+        for (int i = 0; i < nKF; i++) K.mvKeysUn.push_back(to_cv(kf[i]));
+        K.mvKeys = K.mvKeysUn;
+    } else {
+        K.mpCamera2 = &cams[1];
+        K.NLeft = camOffKF[1] - camOffKF[0]; K.NRight = camOffKF[2] - camOffKF[1];
+        K.NSideLeft = ncam >= 4 ? camOffKF[3] - camOffKF[2] : -1; K.NSideRight = ncam >= 4 ? camOffKF[4] - camOffKF[3] : -1;
+        for (int i = camOffKF[0]; i < camOffKF[1]; i++) K.mvKeys.push_back(to_cv(kf[i]));
+        for (int i = camOffKF[1]; i < camOffKF[2]; i++) K.mvKeysRight.push_back(to_cv(kf[i]));
+        if (ncam >= 4) {
+            K.mpCamera3 = &cams[2]; K.mpCamera4 = &cams[3];
+            for (int i = camOffKF[2]; i < camOffKF[3]; i++) K.mvKeysSideLeft.push_back(to_cv(kf[i]));
+            for (int i = camOffKF[3]; i < camOffKF[4]; i++) K.mvKeysSideRight.push_back(to_cv(kf[i]));
+        }
+    }
+    K.mDescriptors = desc_mat(descKF, nKF);
+    std::vector<MapPoint> mps(nKF);
+    K.map_points.assign(nKF, nullptr);
+    for (int i = 0; i < nKF; i++) if (!skipKF[i]) K.map_points[i] = &mps[i];
+    for (int a = 0; a < nnKF; a++)
+        for (int j = ptrKF[a]; j < ptrKF[a + 1]; j++) K.mFeatVec[(unsigned)nodesKF[a]].push_back((unsigned)idxKF[j]);
+    std::vector<MapPoint *> out;
+    ORBmatcher matcher(nnratio, checkOrientation != 0);
+    const int n = matcher.SearchByBoW(&K, F, out);
+    for (int i = 0; i < nF; i++) matchF[i] = out[i] ? (int)(out[i] - mps.data()) : -1;
+    return n;
+}
+
+#ifndef ORBX_GLUE_BUILD
 // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:1131-1456).
 // FeatureVectors as CSR (node ids ascending); ncam = 1 (mono / rectified stereo: NLeft == -1), 2 or 4; has_mp[idx] = GetMapPoint(idx)
 // != NULL; u_right (ncam == 1 only, may be NULL = all -1); ep = the epipole the reference computes (pKF2->mpCamera->project(T2w * Cw)):
@@ -249,6 +305,7 @@ int refm_search_for_triangulation(int ncam, const int *cam_off1, const ref_kp *k
     for (auto &p : pairs) match12[p.first] = (int)p.second;
     return n;
 }
+#endif
 
 // the pixel camera's epipolar predicate, for the oracle-side callback of the same test
 int refm_pair_hash(float x1, float y1, float x2, float y2, int id1, int id2) { return PixelCamera::pair_hash(x1, y1, x2, y2, id1, id2) ? 1 : 0; }

@@ -242,3 +242,36 @@ def test_search_for_triangulation(ncam, coarse):
             assert na > 5
         if ncam == 4 and not coarse:
             assert len(set(states)) >= 8                      # the scenario exercises the carried camera-pair states
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+def test_search_by_bow_keyframe_frame(ncam):
+    """SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), src/ORBmatcher.cc:349-666: per-camera best / second, the `|| true` ratio tests of
+    cameras 1-3 nested in camera 0's TH_LOW test, already-matched rule, rotation histogram."""
+    rng = np.random.default_rng(300 + ncam)
+    L = RM(); Lo = O.lib()
+    for trial in range(10):
+        nF = int(rng.integers(300, 1500)); nKF = int(rng.integers(300, 1500))
+        dF = synth_descriptors(nF, 2900 + trial)
+        dF[5:40] = dF[5]
+        src = rng.integers(0, nF, nKF)
+        flips = np.packbits(rng.random((nKF, 256)) < 0.05, axis=1, bitorder='little'); flips[:, 0] &= 0xE0
+        dKF = dF[src] ^ flips
+        dKF[::7] = synth_descriptors(len(dKF[::7]), 77 + trial)
+        aF = rng.uniform(0, 360, nF).astype(np.float32)
+        aKF = ((aF[src] + rng.choice([0, 0, 0, 30, 95, 190, 250], nKF)) % 360).astype(np.float32)
+        fvK, fvF = _feature_vector(dKF), _feature_vector(dF)
+        skip = (rng.random(nKF) < 0.25).astype(np.uint8)
+
+        def split(n):
+            cuts = np.sort(rng.integers(0, n + 1, ncam - 1)) if ncam > 1 else np.zeros(0, np.int64)
+            return np.concatenate([[0], cuts, [n]]).astype(np.int32)
+        offK, offF = split(nKF), split(nF)
+        for chk in (0, 1):
+            a = np.zeros(nF, np.int32); b = np.zeros(nF, np.int32)
+            na = L.refm_search_by_bow_frame(len(fvK[0]), p(fvK[0]), p(fvK[1]), p(fvK[2]), len(fvF[0]), p(fvF[0]), p(fvF[1]), p(fvF[2]), p(dKF), nKF,
+                                            p(dF), nF, p(skip), p(aKF), p(aF), ncam, p(offK), p(offF), C.c_float(0.7), chk, p(a))
+            nb = Lo.orc_search_by_bow_frame(len(fvK[0]), p(fvK[0]), p(fvK[1]), p(fvK[2]), len(fvF[0]), p(fvF[0]), p(fvF[1]), p(fvF[2]), p(dKF), p(dF), nF,
+                                            p(skip), p(aKF), p(aF), ncam, p(offF), C.c_float(0.7), chk, p(b))
+            assert na == nb, (trial, chk, na, nb)
+            assert np.array_equal(a, b), (trial, chk, int((a != b).sum()))
