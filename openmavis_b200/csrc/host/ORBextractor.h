@@ -5,6 +5,7 @@
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
+#include <memory>
 #include <vector>
 
 #include "orbx_cv_compat.h"
@@ -20,6 +21,8 @@ public:
     // include/ORBextractor.h:33-35, src/ORBextractor.cc:351-414
     ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
     ~ORBextractor();
+    ORBextractor(const ORBextractor &) = delete;
+    ORBextractor &operator=(const ORBextractor &) = delete;
 
     // Compute the ORB features and descriptors on an image; mask is ignored (src/ORBextractor.cc:987-1071).
     // Returns the number of keypoints outside the lapping area, -1 for an empty image.
@@ -33,8 +36,9 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    // Host mirrors of the pyramid levels of the last call (read by src/Frame.cc:1063,1147,1163).  They are downloaded after
-    // every call unless switched off (the 4-camera fisheye path never reads them).
+    // Host mirrors of the pyramid levels of the last call.  The only reader in the reference is Frame::ComputeStereoMatches
+    // (src/Frame.cc:1063,1147,1163), which has a device entry point of its own (orbx_compute_stereo_matches reads the device-resident
+    // pyramids): the mirrors are 3.7x the image bytes per call over PCIe, so they are NOT downloaded unless switched on.
     std::vector<cv::Mat> mvImagePyramid;
     void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
     // extension: CUDA device of this extractor (default 0) — call before the first operator()
@@ -49,9 +53,9 @@ protected:
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
 
 private:
-    orbx_extractor *mHandle = nullptr;
+    std::shared_ptr<void> mRig;        // rig context shared by the extractors of one geometry (one batch-capable device handle)
     int mWidth = 0, mHeight = 0, mDevice = 0;
-    bool mbDownloadPyramid = true;
+    bool mbDownloadPyramid = false;
     std::vector<unsigned char> mKpBuf, mDescBuf;
 };
 

@@ -2,6 +2,7 @@
 // ORB_SLAM3::ORBextractor / ORBmatcher exactly the way src/Frame.cc does.  Test infrastructure.
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 #include "../../openmavis_b200/csrc/host/ORBextractor.h"
@@ -32,6 +33,39 @@ int shim_extract(void *e, unsigned char *img, int w, int h, int stride, int lap0
     if (m > 0) memcpy(kps28, keys.data(), (size_t)m * sizeof(cv::KeyPoint));
     for (int i = 0; i < m; i++) memcpy(desc + (size_t)i * 32, descriptors.ptr<unsigned char>(i), 32);
     return mono;
+}
+
+void shim_set_pyramid_download(void *e, int on) { ((ORB_SLAM3::ORBextractor *)e)->SetPyramidDownload(on != 0); }
+
+extern "C" void orbx_shim_rig_stats(long long *batches, long long *images);
+void shim_rig_stats(long long *batches, long long *images) { orbx_shim_rig_stats(batches, images); }
+
+// The multi-camera Frame constructor (src/Frame.cc:1841-1862): per rig frame one std::thread per camera, each calling operator() of its
+// own extractor object, joined right away.  imgs = [frames][ncam][h][w]; nf / laps per camera; outputs of the LAST frame:
+// kps28 [ncam][cap], desc [ncam][cap][32], n [ncam], mono [ncam].
+void shim_extract_rig(int ncam, int frames, unsigned char *imgs, int w, int h, const int *nf, const int *laps, int ini, int mn, float *kps28,
+                      unsigned char *desc, int cap, int *n, int *mono) {
+    std::vector<ORB_SLAM3::ORBextractor *> ex;
+    for (int c = 0; c < ncam; c++) ex.push_back(new ORB_SLAM3::ORBextractor(nf[c], 1.2f, 8, ini, mn));
+    std::vector<std::vector<cv::KeyPoint>> keys(ncam);
+    std::vector<cv::Mat> descs(ncam);
+    for (int f = 0; f < frames; f++) {
+        std::vector<std::thread> th;
+        for (int c = 0; c < ncam; c++)
+            th.emplace_back([&, c]() {
+                cv::Mat image(h, w, CV_8UC1, imgs + ((size_t)f * ncam + c) * w * h, (size_t)w);
+                std::vector<int> lap = {laps[2 * c], laps[2 * c + 1]};
+                mono[c] = (*ex[c])(image, cv::Mat(), keys[c], descs[c], lap);
+            });
+        for (auto &t : th) t.join();
+    }
+    for (int c = 0; c < ncam; c++) {
+        n[c] = (int)keys[c].size();
+        const int m = n[c] < cap ? n[c] : cap;
+        if (m > 0) memcpy(kps28 + (size_t)c * cap * 7, keys[c].data(), (size_t)m * sizeof(cv::KeyPoint));
+        for (int i = 0; i < m; i++) memcpy(desc + ((size_t)c * cap + i) * 32, descs[c].ptr<unsigned char>(i), 32);
+        delete ex[c];
+    }
 }
 
 // copies mvImagePyramid[level] (interior) into dst (tightly packed); returns 0 if the level is empty

@@ -52,6 +52,7 @@ def test_shim_operator_matches_oracle(shim, lap):
     img = synth_image(752, 480, 77)
     padded = np.zeros((480, 800), np.uint8); padded[:, :752] = img       # non-continuous cv::Mat (row stride 800)
     e = shim.shim_extractor_new(1000, 1.2, 8, 20, 7)
+    shim.shim_set_pyramid_download(C.c_void_p(e), 1)                      # off by default (only Frame::ComputeStereoMatches reads them)
     cap = 1200
     kps = np.zeros(cap, O.KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int(0)
     mono = shim.shim_extract(e, O.p(padded), 752, 480, 800, lap[0], lap[1], O.p(kps), O.p(desc), cap, C.byref(n))
@@ -102,3 +103,29 @@ def test_shim_search_for_initialization_matches_oracle(shim):
     rn = L.orc_search_for_initialization(O.p(k1), O.p(d1), n1, C.c_void_p(g2), O.p(k2), O.p(d2), n2, O.p(prev_ref), 20, C.c_float(0.9), 1, O.p(ref))
     L.orc_grid_destroy(C.c_void_p(g2))
     assert nm == rn and np.array_equal(m12, ref) and np.array_equal(prev, prev_ref) and nm > 50
+
+
+@pytest.mark.gpu
+def test_shim_rig_rendezvous_four_camera_threads(shim):
+    """src/Frame.cc:1841-1862: four extractor objects (500 / 500 / 1000 / 1000 features as src/Tracking.cc:583-587 creates them), one
+    std::thread per camera per rig frame.  Every camera's result must equal the reference's, and after the first frames the four
+    calls of a rig frame must travel as ONE device batch (the rendezvous learns how many calls arrive together)."""
+    w, h, ncam, frames = 720, 540, 4, 12
+    nf = np.array([500, 500, 1000, 1000], np.int32)
+    laps = np.array([[0, 720], [0, 720], [0, 0], [0, 0]], np.int32)
+    imgs = np.stack([synth_image(w, h, 3400 + (f % 3) * 10 + c) for f in range(frames) for c in range(ncam)])
+    cap = 1200
+    kps = np.zeros((ncam, cap), O.KP_DTYPE); desc = np.zeros((ncam, cap, 32), np.uint8)
+    n = np.zeros(ncam, np.int32); mono = np.zeros(ncam, np.int32)
+    b0, i0, b1, i1 = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+    shim.shim_rig_stats(C.byref(b0), C.byref(i0))
+    shim.shim_extract_rig(ncam, frames, O.p(imgs), w, h, O.p(nf), O.p(laps), 15, 7, O.p(kps), O.p(desc), cap, O.p(n), O.p(mono))
+    shim.shim_rig_stats(C.byref(b1), C.byref(i1))
+    last = imgs[(frames - 1) * ncam:]
+    for c in range(ncam):
+        rm, rk, rd = O.RefExtractor(int(nf[c]), 1.2, 8, 15, 7)(last[c], tuple(laps[c]))
+        assert mono[c] == rm and n[c] == len(rk), (c, mono[c], rm, n[c], len(rk))
+        assert np.array_equal(kps[c, :n[c]], rk) and np.array_equal(desc[c, :n[c]], rd), c
+    images, batches = i1.value - i0.value, b1.value - b0.value
+    assert images == ncam * frames
+    assert batches <= frames + 6, (batches, images)          # one batch per rig frame once learned (the first frame may take up to 4)
