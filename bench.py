@@ -283,6 +283,17 @@ def guided_matchers(ob, device):
     cpu_ms = timed(lambda: T._oracle_sbp_last(frame, last, 7.0, False, False, True), reps=3)
     out['search_by_projection_last_frame'] = {'points': int(nlast), 'cameras': ncam, 'matches': int(nm[0]), 'ms_per_call': ms,
                                               'device_ms': m.last_ms(), 'points_per_s': nlast / (ms * 1e-3), 'cpu_ms_per_call': cpu_ms}
+    # ---- the same matchers batched across frames (orbx_matcher_pool, 16 lanes): F frames per call, F = 1, 8, 64
+    pool = ob.MatcherPool(lanes=16, device=device)
+    batched = {}
+    for F_ in (1, 8, 64):
+        ms_a = timed(lambda: pool.SearchByProjectionBatch([frame] * F_, [points] * F_, 3.0, False, 50.0, 0.8), reps=5)
+        ms_b = timed(lambda: pool.SearchByProjectionLastBatch([frame] * F_, [last] * F_, 7.0), reps=5)
+        batched['F%d' % F_] = {
+            'search_by_projection': {'ms_per_batch': ms_a, 'ms_per_frame': ms_a / F_, 'map_points_per_s': F_ * nmp / (ms_a * 1e-3),
+                                     'vs_cpu': out['search_by_projection']['cpu_ms_per_call'] * F_ / ms_a},
+            'search_by_projection_last_frame': {'ms_per_batch': ms_b, 'ms_per_frame': ms_b / F_, 'points_per_s': F_ * int(nlast) / (ms_b * 1e-3),
+                                                'vs_cpu': out['search_by_projection_last_frame']['cpu_ms_per_call'] * F_ / ms_b}}
     # ---- SearchByBoW(KeyFrame, Frame) (src/ORBmatcher.cc:349-666): 64 shared vocabulary nodes
     def fvec(d):
         node = d[:, 0].astype(np.int32) & 63
@@ -307,6 +318,14 @@ def guided_matchers(ob, device):
     cpu_ms = timed(bow_cpu, reps=3)
     out['search_by_bow'] = {'keyframe_features': int(nlast), 'frame_features': int(nlast), 'matches': int(nm[0]), 'ms_per_call': ms,
                             'device_ms': m.last_ms(), 'cpu_ms_per_call': cpu_ms}
+    for F_ in (1, 8, 64):
+        ms_c = timed(lambda: pool.SearchByBoWBatch([fv_kf] * F_, [fv_f] * F_, [dkf] * F_, [desc] * F_, [None] * F_, [akf] * F_, [kps['angle']] * F_,
+                                                   [cam_off] * F_, 0.8, True), reps=5)
+        batched['F%d' % F_]['search_by_bow'] = {'ms_per_batch': ms_c, 'ms_per_frame': ms_c / F_, 'vs_cpu': cpu_ms * F_ / ms_c}
+    batched['what'] = ('F frames per call on a pool of 16 lanes (handle + stream + host worker each); vs_cpu = F x the one-thread CPU time of the '
+                       'oracle restatement / the batch time; the Python-side marshalling of the F argument sets is inside the timed call')
+    out['batched_across_frames'] = batched
+    pool.close()
     # ---- ComputeStereoMatches (src/Frame.cc:1057-1219)
     left = synth_image(752, 480, 2001)
     xs = np.arange(752)

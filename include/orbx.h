@@ -417,6 +417,39 @@ int orbx_vocabulary_transform(orbx_matcher *m, const orbx_vocabulary *v, const u
                               int *node_id, double *weight);
 
 /* Launch count / device time of the matcher's last call (CUDA events on its stream). */
+/* ---- Guided matchers batched across frames ("report queries/s and latency, batch across frames") -------------------
+ * The guided matchers of one frame are latency-bound (a few thousand Hamming distances followed by an ordered, single-CTA claim
+ * resolution).  A pool holds `lanes` matcher handles (own stream, events and device buffers each) and as many host worker threads:
+ * the calls of a batch are distributed over the lanes and run concurrently, so the device executes the resolvers of up to `lanes` frames
+ * side by side while the workers marshal the next ones.  Results are those of the single-frame entry points, call by call.
+ * orbx_*_call structs carry exactly the arguments of the corresponding single-frame function; status[i] receives its return value. */
+typedef struct orbx_matcher_pool orbx_matcher_pool;
+int orbx_matcher_pool_create(orbx_matcher_pool **out, int device, int lanes);
+void orbx_matcher_pool_destroy(orbx_matcher_pool *p);
+typedef struct orbx_sbp_call {            /* orbx_search_by_projection */
+    int ncam; const int *cam_off; const orbx_kp *kps; const uint8_t *desc; const float *grid_bounds; const float *scale_factors; int nlevels;
+    const uint8_t *occupied; const int *l2r; const int *r2l; const float *u_right; int nmp; const uint8_t *in_view; const float *proj_x;
+    const float *proj_y; const int *level; const float *view_cos; const float *proj_xr; const float *depth; const uint8_t *bad;
+    const uint8_t *has_obs; const uint8_t *mp_desc; float th; int far_points; float th_far_points; float nnratio;
+    int *assigned; int nmatches;          /* outputs */
+} orbx_sbp_call;
+typedef struct orbx_sbp_last_call {       /* orbx_search_by_projection_last */
+    int ncam; const int *cam_off; const orbx_kp *kps; const uint8_t *desc; const float *grid_bounds; const float *scale_factors; int nlevels;
+    const uint8_t *occupied; const float *u_right; int npts; const uint8_t *valid; const float *proj_x; const float *proj_y;
+    const float *proj_ur; const int *last_octave; const float *last_angle; const uint8_t *has_obs; const uint8_t *pt_desc; float th;
+    int level_gate; int check_orientation; int max_dist;
+    int *assigned; int nmatches;          /* outputs */
+} orbx_sbp_last_call;
+typedef struct orbx_bow_call {            /* orbx_search_by_bow_frame */
+    int nn_kf; const int *nodes_kf; const int *ptr_kf; const int *idx_kf; int nn_f; const int *nodes_f; const int *ptr_f; const int *idx_f;
+    const uint8_t *desc_kf; int n_kf; const uint8_t *desc_f; int n_f; const uint8_t *skip_kf; const float *angle_kf; const float *angle_f;
+    int ncam_f; const int *cam_off_f; float nnratio; int check_orientation;
+    int *match_f; int nmatches;           /* outputs */
+} orbx_bow_call;
+int orbx_search_by_projection_batch(orbx_matcher_pool *p, int ncalls, orbx_sbp_call *calls, int *status);
+int orbx_search_by_projection_last_batch(orbx_matcher_pool *p, int ncalls, orbx_sbp_last_call *calls, int *status);
+int orbx_search_by_bow_frame_batch(orbx_matcher_pool *p, int ncalls, orbx_bow_call *calls, int *status);
+
 int orbx_matcher_last_ms(orbx_matcher *m, float *ms);
 int orbx_matcher_last_launches(const orbx_matcher *m);
 

@@ -638,6 +638,134 @@ class ORBmatcher:
                                                      C.c_float(th), int(gate), int(self.mbCheckOrientation), int(max_dist), _p(assigned), C.byref(nm)))
         return nm.value, assigned[:N]
 
+class _SbpCall(C.Structure):
+    _fields_ = [('ncam', C.c_int), ('cam_off', C.c_void_p), ('kps', C.c_void_p), ('desc', C.c_void_p), ('grid_bounds', C.c_void_p),
+                ('scale_factors', C.c_void_p), ('nlevels', C.c_int), ('occupied', C.c_void_p), ('l2r', C.c_void_p), ('r2l', C.c_void_p),
+                ('u_right', C.c_void_p), ('nmp', C.c_int), ('in_view', C.c_void_p), ('proj_x', C.c_void_p), ('proj_y', C.c_void_p),
+                ('level', C.c_void_p), ('view_cos', C.c_void_p), ('proj_xr', C.c_void_p), ('depth', C.c_void_p), ('bad', C.c_void_p),
+                ('has_obs', C.c_void_p), ('mp_desc', C.c_void_p), ('th', C.c_float), ('far_points', C.c_int), ('th_far_points', C.c_float),
+                ('nnratio', C.c_float), ('assigned', C.c_void_p), ('nmatches', C.c_int)]
+
+
+class _SbpLastCall(C.Structure):
+    _fields_ = [('ncam', C.c_int), ('cam_off', C.c_void_p), ('kps', C.c_void_p), ('desc', C.c_void_p), ('grid_bounds', C.c_void_p),
+                ('scale_factors', C.c_void_p), ('nlevels', C.c_int), ('occupied', C.c_void_p), ('u_right', C.c_void_p), ('npts', C.c_int),
+                ('valid', C.c_void_p), ('proj_x', C.c_void_p), ('proj_y', C.c_void_p), ('proj_ur', C.c_void_p), ('last_octave', C.c_void_p),
+                ('last_angle', C.c_void_p), ('has_obs', C.c_void_p), ('pt_desc', C.c_void_p), ('th', C.c_float), ('level_gate', C.c_int),
+                ('check_orientation', C.c_int), ('max_dist', C.c_int), ('assigned', C.c_void_p), ('nmatches', C.c_int)]
+
+
+class _BowCall(C.Structure):
+    _fields_ = [('nn_kf', C.c_int), ('nodes_kf', C.c_void_p), ('ptr_kf', C.c_void_p), ('idx_kf', C.c_void_p), ('nn_f', C.c_int),
+                ('nodes_f', C.c_void_p), ('ptr_f', C.c_void_p), ('idx_f', C.c_void_p), ('desc_kf', C.c_void_p), ('n_kf', C.c_int),
+                ('desc_f', C.c_void_p), ('n_f', C.c_int), ('skip_kf', C.c_void_p), ('angle_kf', C.c_void_p), ('angle_f', C.c_void_p),
+                ('ncam_f', C.c_int), ('cam_off_f', C.c_void_p), ('nnratio', C.c_float), ('check_orientation', C.c_int),
+                ('match_f', C.c_void_p), ('nmatches', C.c_int)]
+
+
+def _addr(a):
+    return None if a is None else a.ctypes.data
+
+
+class MatcherPool:
+    """orbx_matcher_pool (include/orbx.h): the guided matchers of MANY frames at once — `lanes` matcher handles (stream + buffers) and
+    host workers; the device runs the frames' single-CTA resolvers side by side.  Each method takes lists of the per-frame arguments of
+    the corresponding ORBmatcher method and returns the per-frame results."""
+
+    def __init__(self, lanes=16, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        _check(self.L.orbx_matcher_pool_create(C.byref(h), int(device), int(lanes)))
+        self.h = h
+        self.L.orbx_matcher_pool_destroy.argtypes = [C.c_void_p]
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.L.orbx_matcher_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def SearchByProjectionBatch(self, frames, points, th=3.0, bFarPoints=False, thFarPoints=50.0, nnratio=0.8):
+        n = len(frames)
+        calls = (_SbpCall * n)(); status = (C.c_int * n)(); keep = []; outs = []
+        for i, (f, pt) in enumerate(zip(frames, points)):
+            cam_off = np.ascontiguousarray(f['cam_off'], np.int32); ncam = cam_off.size - 1; N = int(cam_off[-1])
+            nmp = int(np.asarray(pt['in_view']).shape[0])
+            a = dict(cam_off=cam_off, kps=np.ascontiguousarray(f['kps'], KP_DTYPE), desc=np.ascontiguousarray(f['desc'], np.uint8),
+                     grid_bounds=np.ascontiguousarray(f['bounds'], np.float32), scale_factors=np.ascontiguousarray(f['scale_factors'], np.float32),
+                     in_view=np.ascontiguousarray(pt['in_view'], np.uint8), proj_x=np.ascontiguousarray(pt['proj_x'], np.float32),
+                     proj_y=np.ascontiguousarray(pt['proj_y'], np.float32), level=np.ascontiguousarray(pt['level'], np.int32),
+                     view_cos=np.ascontiguousarray(pt['view_cos'], np.float32), mp_desc=np.ascontiguousarray(pt['desc'], np.uint8))
+            for k_, src, dt in (('occupied', f, np.uint8), ('l2r', f, np.int32), ('r2l', f, np.int32), ('u_right', f, np.float32),
+                                ('proj_xr', pt, np.float32), ('depth', pt, np.float32), ('bad', pt, np.uint8), ('has_obs', pt, np.uint8)):
+                a[k_] = None if src.get(k_) is None else np.ascontiguousarray(src[k_], dt)
+            out = np.full(max(N, 1), -1, np.int32)
+            keep.append(a); outs.append((out, N))
+            c = calls[i]
+            c.ncam, c.nlevels, c.nmp = ncam, a['scale_factors'].size, nmp
+            for k_ in ('cam_off', 'kps', 'desc', 'grid_bounds', 'scale_factors', 'occupied', 'l2r', 'r2l', 'u_right', 'in_view', 'proj_x', 'proj_y', 'level',
+                       'view_cos', 'proj_xr', 'depth', 'bad', 'has_obs', 'mp_desc'):
+                setattr(c, k_, _addr(a[k_]))
+            c.th, c.far_points, c.th_far_points, c.nnratio, c.assigned = th, int(bool(bFarPoints)), thFarPoints, nnratio, out.ctypes.data
+        _check(self.L.orbx_search_by_projection_batch(self.h, n, calls, status))
+        for i in range(n):
+            _check(status[i])
+        return [(calls[i].nmatches, outs[i][0][:outs[i][1]]) for i in range(n)]
+
+    def SearchByProjectionLastBatch(self, frames, lasts, th, level_gate=None, check_orientation=True, max_dist=TH_HIGH):
+        n = len(frames)
+        calls = (_SbpLastCall * n)(); status = (C.c_int * n)(); keep = []; outs = []
+        for i, (f, la) in enumerate(zip(frames, lasts)):
+            cam_off = np.ascontiguousarray(f['cam_off'], np.int32); ncam = cam_off.size - 1; N = int(cam_off[-1])
+            a = dict(cam_off=cam_off, kps=np.ascontiguousarray(f['kps'], KP_DTYPE), desc=np.ascontiguousarray(f['desc'], np.uint8),
+                     grid_bounds=np.ascontiguousarray(f['bounds'], np.float32), scale_factors=np.ascontiguousarray(f['scale_factors'], np.float32),
+                     valid=np.ascontiguousarray(la['valid'], np.uint8), proj_x=np.ascontiguousarray(la['proj_x'], np.float32),
+                     proj_y=np.ascontiguousarray(la['proj_y'], np.float32), last_octave=np.ascontiguousarray(la['octave'], np.int32),
+                     last_angle=np.ascontiguousarray(la['angle'], np.float32), pt_desc=np.ascontiguousarray(la['desc'], np.uint8))
+            for k_, src, key, dt in (('occupied', f, 'occupied', np.uint8), ('u_right', f, 'u_right', np.float32), ('proj_ur', la, 'proj_ur', np.float32),
+                                     ('has_obs', la, 'has_obs', np.uint8)):
+                a[k_] = None if src.get(key) is None else np.ascontiguousarray(src[key], dt)
+            out = np.full(max(N, 1), -1, np.int32)
+            keep.append(a); outs.append((out, N))
+            c = calls[i]
+            c.ncam, c.nlevels, c.npts = ncam, a['scale_factors'].size, int(a['valid'].size)
+            for k_ in ('cam_off', 'kps', 'desc', 'grid_bounds', 'scale_factors', 'occupied', 'u_right', 'valid', 'proj_x', 'proj_y', 'proj_ur', 'last_octave',
+                       'last_angle', 'has_obs', 'pt_desc'):
+                setattr(c, k_, _addr(a[k_]))
+            c.th, c.level_gate, c.check_orientation, c.max_dist, c.assigned = th, int(GATE_AROUND if level_gate is None else level_gate), int(check_orientation), int(max_dist), out.ctypes.data
+        _check(self.L.orbx_search_by_projection_last_batch(self.h, n, calls, status))
+        for i in range(n):
+            _check(status[i])
+        return [(calls[i].nmatches, outs[i][0][:outs[i][1]]) for i in range(n)]
+
+    def SearchByBoWBatch(self, fv_kfs, fv_fs, desc_kfs, desc_fs, skip_kfs, angle_kfs, angle_fs, cam_off_fs, nnratio=0.7, check_orientation=True):
+        n = len(fv_kfs)
+        calls = (_BowCall * n)(); status = (C.c_int * n)(); keep = []; outs = []
+        for i in range(n):
+            nk, pk, ik = (np.ascontiguousarray(x, np.int32) for x in fv_kfs[i]); nf, pf, iff = (np.ascontiguousarray(x, np.int32) for x in fv_fs[i])
+            dk = np.ascontiguousarray(desc_kfs[i], np.uint8).reshape(-1, 32); df = np.ascontiguousarray(desc_fs[i], np.uint8).reshape(-1, 32)
+            sk = np.zeros(dk.shape[0], np.uint8) if skip_kfs[i] is None else np.ascontiguousarray(skip_kfs[i], np.uint8)
+            ak = np.ascontiguousarray(angle_kfs[i], np.float32); af = np.ascontiguousarray(angle_fs[i], np.float32)
+            co = np.ascontiguousarray(cam_off_fs[i], np.int32)
+            out = np.full(max(df.shape[0], 1), -1, np.int32)
+            keep.append((nk, pk, ik, nf, pf, iff, dk, df, sk, ak, af, co)); outs.append((out, df.shape[0]))
+            c = calls[i]
+            c.nn_kf, c.nodes_kf, c.ptr_kf, c.idx_kf = nk.size, nk.ctypes.data, pk.ctypes.data, ik.ctypes.data
+            c.nn_f, c.nodes_f, c.ptr_f, c.idx_f = nf.size, nf.ctypes.data, pf.ctypes.data, iff.ctypes.data
+            c.desc_kf, c.n_kf, c.desc_f, c.n_f = dk.ctypes.data, dk.shape[0], df.ctypes.data, df.shape[0]
+            c.skip_kf, c.angle_kf, c.angle_f, c.ncam_f, c.cam_off_f = sk.ctypes.data, ak.ctypes.data, af.ctypes.data, co.size - 1, co.ctypes.data
+            c.nnratio, c.check_orientation, c.match_f = nnratio, int(check_orientation), out.ctypes.data
+        _check(self.L.orbx_search_by_bow_frame_batch(self.h, n, calls, status))
+        for i in range(n):
+            _check(status[i])
+        return [(calls[i].nmatches, outs[i][0][:outs[i][1]]) for i in range(n)]
+
+
 class ORBVocabulary:
     """DBoW2 TemplatedVocabulary<FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h) as flat arrays on the device; transform()
     mirrors mpORBvocabulary->transform(features, BowVector, FeatureVector, levelsup) (src/Frame.cc:980-985)."""

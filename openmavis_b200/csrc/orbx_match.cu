@@ -4,6 +4,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -1308,6 +1313,107 @@ int orbx_popc_peak(int device, double *gpopc_per_s) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *gpopc_per_s = (double)blocks * 256 * iters * 8 / (best * 1e-3) * 1e-9;
     return ORBX_OK;
+}
+
+
+// ---- guided matchers batched across frames: a pool of lanes (matcher handle + host worker thread each) ---------------------------
+}  // extern "C"
+
+struct orbx_matcher_pool {
+    int device = 0;
+    std::vector<orbx_matcher *> lanes;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(orbx_matcher *, int)> job;      // job(lane handle, call index)
+    int n_calls = 0, generation = 0, running = 0;
+    std::atomic<int> next{0};
+    bool stop = false;
+};
+
+static void pool_worker(orbx_matcher_pool *p, int lane) {
+    int seen = 0;
+    cudaSetDevice(p->device);
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_work.wait(lk, [&] { return p->stop || p->generation != seen; });
+            if (p->stop) return;
+            seen = p->generation;
+        }
+        for (int i = p->next.fetch_add(1); i < p->n_calls; i = p->next.fetch_add(1)) p->job(p->lanes[lane], i);
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            if (--p->running == 0) p->cv_done.notify_all();
+        }
+    }
+}
+
+static int pool_run(orbx_matcher_pool *p, int n, std::function<void(orbx_matcher *, int)> job) {
+    if (!p || n < 0) return fail(ORBX_ERR_INVALID, "bad arguments");
+    if (n == 0) return ORBX_OK;
+    std::unique_lock<std::mutex> lk(p->mu);
+    p->job = std::move(job); p->n_calls = n; p->next = 0; p->running = (int)p->workers.size(); p->generation++;
+    p->cv_work.notify_all();
+    p->cv_done.wait(lk, [&] { return p->running == 0; });
+    return ORBX_OK;
+}
+
+extern "C" {
+
+int orbx_matcher_pool_create(orbx_matcher_pool **out, int device, int lanes) {
+    if (!out || lanes < 1 || lanes > 64) return fail(ORBX_ERR_INVALID, "bad arguments");
+    *out = nullptr;
+    orbx_matcher_pool *p = new orbx_matcher_pool();
+    p->device = device;
+    for (int l = 0; l < lanes; l++) {
+        orbx_matcher *m = nullptr;
+        const int st = orbx_matcher_create(&m, device);
+        if (st != ORBX_OK) { for (auto *x : p->lanes) orbx_matcher_destroy(x); delete p; return st; }
+        p->lanes.push_back(m);
+    }
+    for (int l = 0; l < lanes; l++) p->workers.emplace_back(pool_worker, p, l);
+    *out = p;
+    return ORBX_OK;
+}
+
+void orbx_matcher_pool_destroy(orbx_matcher_pool *p) {
+    if (!p) return;
+    { std::lock_guard<std::mutex> lk(p->mu); p->stop = true; }
+    p->cv_work.notify_all();
+    for (auto &t : p->workers) t.join();
+    for (auto *m : p->lanes) orbx_matcher_destroy(m);
+    delete p;
+}
+
+int orbx_search_by_projection_batch(orbx_matcher_pool *p, int ncalls, orbx_sbp_call *c, int *status) {
+    if (ncalls > 0 && (!c || !status)) return fail(ORBX_ERR_INVALID, "NULL argument");
+    return pool_run(p, ncalls, [c, status](orbx_matcher *m, int i) {
+        orbx_sbp_call &a = c[i];
+        status[i] = orbx_search_by_projection(m, a.ncam, a.cam_off, a.kps, a.desc, a.grid_bounds, a.scale_factors, a.nlevels, a.occupied, a.l2r, a.r2l,
+                                              a.u_right, a.nmp, a.in_view, a.proj_x, a.proj_y, a.level, a.view_cos, a.proj_xr, a.depth, a.bad, a.has_obs,
+                                              a.mp_desc, a.th, a.far_points, a.th_far_points, a.nnratio, a.assigned, &a.nmatches);
+    });
+}
+
+int orbx_search_by_projection_last_batch(orbx_matcher_pool *p, int ncalls, orbx_sbp_last_call *c, int *status) {
+    if (ncalls > 0 && (!c || !status)) return fail(ORBX_ERR_INVALID, "NULL argument");
+    return pool_run(p, ncalls, [c, status](orbx_matcher *m, int i) {
+        orbx_sbp_last_call &a = c[i];
+        status[i] = orbx_search_by_projection_last(m, a.ncam, a.cam_off, a.kps, a.desc, a.grid_bounds, a.scale_factors, a.nlevels, a.occupied, a.u_right,
+                                                   a.npts, a.valid, a.proj_x, a.proj_y, a.proj_ur, a.last_octave, a.last_angle, a.has_obs, a.pt_desc, a.th,
+                                                   a.level_gate, a.check_orientation, a.max_dist, a.assigned, &a.nmatches);
+    });
+}
+
+int orbx_search_by_bow_frame_batch(orbx_matcher_pool *p, int ncalls, orbx_bow_call *c, int *status) {
+    if (ncalls > 0 && (!c || !status)) return fail(ORBX_ERR_INVALID, "NULL argument");
+    return pool_run(p, ncalls, [c, status](orbx_matcher *m, int i) {
+        orbx_bow_call &a = c[i];
+        status[i] = orbx_search_by_bow_frame(m, a.nn_kf, a.nodes_kf, a.ptr_kf, a.idx_kf, a.nn_f, a.nodes_f, a.ptr_f, a.idx_f, a.desc_kf, a.n_kf, a.desc_f,
+                                             a.n_f, a.skip_kf, a.angle_kf, a.angle_f, a.ncam_f, a.cam_off_f, a.nnratio, a.check_orientation, a.match_f,
+                                             &a.nmatches);
+    });
 }
 
 }  // extern "C"

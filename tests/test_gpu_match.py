@@ -992,3 +992,58 @@ def test_search_for_triangulation_full_kb8(M):
         assert nm > 50
         checked += 1
     assert checked >= 4
+
+
+# ---- guided matchers batched across frames (orbx_matcher_pool) --------------------------------------------------------------------
+def _random_points_case(rng, ncam):
+    frame, base = _random_frame(rng, ncam, int(rng.choice([60, 400])))
+    cam_off, kps, N = frame['cam_off'], frame['kps'], int(frame['cam_off'][-1])
+    n = int(rng.choice([200, 1100, 2500]))
+    tgt = rng.integers(0, N, n)
+    px = np.zeros((n, 4), np.float32); py = np.zeros((n, 4), np.float32)
+    for c in range(ncam):
+        kk = np.where((tgt >= cam_off[c]) & (tgt < cam_off[c + 1]), tgt, rng.integers(cam_off[c], cam_off[c + 1], n))
+        px[:, c] = kps['x'][kk] + rng.uniform(-4, 4, n); py[:, c] = kps['y'][kk] + rng.uniform(-4, 4, n)
+    pdesc = base[rng.integers(0, base.shape[0], n)] ^ np.packbits(rng.random((n, 256)) < 0.03, axis=1, bitorder='little')
+    octv = np.clip(kps['octave'][tgt] + rng.integers(-1, 2, n), 0, 7).astype(np.int32)
+    in_view = (rng.random((n, 4)) < 0.8).astype(np.uint8); in_view[:, ncam:] = 0
+    points = dict(in_view=in_view, proj_x=px, proj_y=py, level=np.repeat(octv[:, None], 4, 1).astype(np.int32),
+                  view_cos=rng.choice([0.9990, 0.99], (n, 4)).astype(np.float32), desc=pdesc, depth=rng.uniform(1, 80, n).astype(np.float32),
+                  bad=(rng.random(n) < 0.05).astype(np.uint8), has_obs=(rng.random(n) < 0.9).astype(np.uint8))
+    return dict(frame, l2r=None, r2l=None), points
+
+
+def test_matcher_pool_batches_equal_single_calls():
+    """Each call of a batch must give exactly the result of the single-frame entry point (and therefore of the oracle): 24 different
+    SearchByProjection(Frame, MapPoints) frames, 12 SearchByProjection(CurrentFrame, LastFrame) frames and 12 SearchByBoW(KF, Frame)
+    pairs on a pool of 8 lanes."""
+    if ob.device_count() == 0:
+        pytest.fail('no CUDA device')
+    pool = ob.MatcherPool(lanes=8)
+    M = ob.ORBmatcher(0.8)
+    rng = np.random.default_rng(123)
+    frames, points = [], []
+    for i in range(24):
+        f, p_ = _random_points_case(rng, ncam=[1, 2, 4][i % 3])
+        frames.append(f); points.append(p_)
+    got = pool.SearchByProjectionBatch(frames, points, 3.0, False, 50.0, 0.8)
+    for i in range(24):
+        nm, a = M.SearchByProjection(frames[i], points[i], 3.0, False, 50.0)
+        assert got[i][0] == nm and np.array_equal(got[i][1], a), i
+        rn, ra = _oracle_sbp(frames[i], points[i], 3.0, np.float32(0.8), False, 50.0)
+        assert got[i][0] == rn and np.array_equal(got[i][1], ra), i
+    M9 = ob.ORBmatcher(0.9, checkOri=True)
+    fl = [_sbp_last_case([1, 2, 4][i % 3], seed=900 + i, n=1500) for i in range(12)]
+    got = pool.SearchByProjectionLastBatch([f for f, _ in fl], [la for _, la in fl], 7.0)
+    for i, (f, la) in enumerate(fl):
+        nm, a = M9.SearchByProjectionLast(f, la, 7.0)
+        assert got[i][0] == nm and np.array_equal(got[i][1], a), i
+    cases = [_bow_case(700 + i, 900 + 50 * i, 1000, 6) for i in range(12)]      # (d1, d2, a1, a2, fv1, fv2, skip1, skip2)
+    M7 = ob.ORBmatcher(0.7, checkOri=True)
+    got = pool.SearchByBoWBatch([c[4] for c in cases], [c[5] for c in cases], [c[0] for c in cases], [c[1] for c in cases],
+                                [c[6] for c in cases], [c[2] for c in cases], [c[3] for c in cases],
+                                [np.array([0, len(c[1])], np.int32) for c in cases], 0.7, True)
+    for i, c in enumerate(cases):
+        nm, mf = M7.SearchByBoW(c[4], c[5], c[0], c[1], c[6], c[2], c[3], None)
+        assert got[i][0] == nm and np.array_equal(got[i][1], mf), i
+    pool.close()

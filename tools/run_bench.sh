@@ -12,7 +12,7 @@ print('cpu',json.dumps(d['cpu_baseline'],indent=1))
 print('secondary',json.dumps(d['secondary'],indent=1))
 print('fast',d['run']['fast_counters'])
 g=d['matching']['guided']
-for k,v in g.items(): print(k, {a:(round(b,3) if isinstance(b,float) else b) for a,b in v.items()})
+for k,v in g.items(): print(k, json.dumps(v)[:900])
 print({k:v for k,v in d['matching'].items() if k!='guided'})
 PY
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; echo "ref rc=$?"; cut -c1-700 gpurun_out/bench_ref_$TAG.log
