@@ -250,6 +250,80 @@ int refm_search_by_bow_frame(int nnKF, const int *nodesKF, const int *ptrKF, con
 }
 
 #ifndef ORBX_GLUE_BUILD
+// ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vpMatches12) (src/ORBmatcher.cc:1006-1129); same arrays as
+// orc_search_by_bow_keyframes.  match12[n1] = idx2 whose MapPoint ended up in vpMatches12[idx1], or -1.
+int refm_search_by_bow_keyframes(int nn1, const int *nodes1, const int *ptr1, const int *idx1v, int nn2, const int *nodes2, const int *ptr2,
+                                 const int *idx2v, const uint8_t *desc1, int n1, const uint8_t *desc2, int n2, const uint8_t *skip1,
+                                 const uint8_t *skip2, const float *angle1, const float *angle2, float nnratio, int checkOrientation, int *match12) {
+    KeyFrame K1, K2;
+    std::vector<MapPoint> mp1(n1), mp2(n2);
+    auto fill = [&](KeyFrame &K, int n, const uint8_t *desc, const uint8_t *skip, const float *angle, std::vector<MapPoint> &mps, int nn, const int *nodes,
+                    const int *ptr, const int *idxv) {
+        K.N = n;
+        for (int i = 0; i < n; i++) K.mvKeysUn.push_back(cv::KeyPoint(10.f, 10.f, 31.f, angle ? angle[i] : 0.f, 0.f, 0, -1));
+        K.mvKeys = K.mvKeysUn;
+        K.mDescriptors = desc_mat(desc, n);
+        K.map_points.assign(n, nullptr);
+        for (int i = 0; i < n; i++) if (!skip || !skip[i]) K.map_points[i] = &mps[i];
+        for (int a = 0; a < nn; a++)
+            for (int j = ptr[a]; j < ptr[a + 1]; j++) K.mFeatVec[(unsigned)nodes[a]].push_back((unsigned)idxv[j]);
+    };
+    fill(K1, n1, desc1, skip1, angle1, mp1, nn1, nodes1, ptr1, idx1v);
+    fill(K2, n2, desc2, skip2, angle2, mp2, nn2, nodes2, ptr2, idx2v);
+    std::vector<MapPoint *> out;
+    ORBmatcher matcher(nnratio, checkOrientation != 0);
+    const int n = matcher.SearchByBoW(&K1, &K2, out);
+    for (int i = 0; i < n1; i++) match12[i] = out[i] ? (int)(out[i] - mp2.data()) : -1;
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1985-2413), the tracking
+// matcher.  Current frame as in refm_search_by_projection.  Last frame: npts keypoints in the Nleft == -1 layout; has_mp[i] = the point
+// exists and is no outlier; its map point sits at (px[i], py[i], 1) in world = camera coordinates (Tcw = I, pixel camera), so the
+// reference projects it to exactly (px[i], py[i]) in camera 0, to (px + trl[0], py + trl[1]) in the right camera (Trl = [I | trl]) and
+// searches the side cameras around the LEFT projection (the reference's D6 behaviour, :2250-2271).  invzc = 1, so the rectified-stereo
+// test uses ur = px - mbf.  gate: 0 = neither bForward nor bBackward, 1 = bForward, 2 = bBackward (set through the z of the last pose).
+// assigned[idx] = i written to CurrentFrame.mvpMapPoints[idx] (-1 = untouched or cleared by the rotation filter).
+int refm_search_by_projection_last(int ncam, const int *cam_off, const ref_kp *kps, const uint8_t *desc, const float *bounds, const float *sf, int nsf,
+                                   const uint8_t *occupied, const float *u_right, int npts, const uint8_t *has_mp, const float *px, const float *py,
+                                   const float *trl, float mbf, const int *last_octave, const float *last_angle, const uint8_t *has_obs,
+                                   const uint8_t *pt_desc, float th, int gate, int checkOrientation, int *assigned) {
+    set_bounds(bounds);
+    Frame Cur, Last;
+    fill_frame(Cur, ncam, cam_off, kps, desc, sf, nsf);
+    const int N = Cur.N;
+    MapPoint holder;
+    holder.n_obs = 1;
+    for (int i = 0; i < N; i++) if (occupied && occupied[i]) Cur.mvpMapPoints[i] = &holder;
+    if (u_right && ncam == 1) Cur.mvuRight.assign(u_right, u_right + N);
+    PixelCamera cams[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
+    Cur.mpCamera = &cams[0]; Cur.mpCamera2 = ncam >= 2 ? &cams[1] : nullptr; Cur.mpCamera3 = ncam >= 4 ? &cams[2] : nullptr; Cur.mpCamera4 = ncam >= 4 ? &cams[3] : nullptr;
+    Cur.mb = 0.5f; Cur.mbf = mbf;
+    Cur.Trl = Sophus::SE3f(Eigen::Matrix3f::Identity(), Eigen::Vector3f(trl[0], trl[1], 0.f));
+    // tlc = Tlw * twc = the last pose's translation (twc = 0): z = +1 -> bForward, -1 -> bBackward, 0 -> neither (mb = 0.5)
+    Last.Tcw = Sophus::SE3f(Eigen::Matrix3f::Identity(), Eigen::Vector3f(0.f, 0.f, gate == 1 ? 1.f : gate == 2 ? -1.f : 0.f));
+    Last.N = npts;
+    std::vector<MapPoint> mps(npts);
+    Last.mvpMapPoints.assign(npts, nullptr);
+    Last.mvbOutlier.assign(npts, false);
+    for (int i = 0; i < npts; i++) {
+        Last.mvKeysUn.push_back(cv::KeyPoint(0.f, 0.f, 31.f, last_angle[i], 0.f, last_octave[i], -1));
+        MapPoint &P = mps[i];
+        P.world_pos = Eigen::Vector3f(px[i], py[i], 1.f);
+        P.descriptor = desc_mat(pt_desc + (size_t)i * 32, 1);
+        P.n_obs = has_obs ? has_obs[i] : 1;
+        if (has_mp[i]) Last.mvpMapPoints[i] = &P;
+    }
+    Last.mvKeys = Last.mvKeysUn;
+    ORBmatcher matcher(0.9f, checkOrientation != 0);
+    const int n = matcher.SearchByProjection(Cur, Last, th, false);
+    for (int i = 0; i < N; i++) {
+        MapPoint *p = Cur.mvpMapPoints[i];
+        assigned[i] = (p && p != &holder) ? (int)(p - mps.data()) : -1;
+    }
+    return n;
+}
+
 // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:1131-1456).
 // FeatureVectors as CSR (node ids ascending); ncam = 1 (mono / rectified stereo: NLeft == -1), 2 or 4; has_mp[idx] = GetMapPoint(idx)
 // != NULL; u_right (ncam == 1 only, may be NULL = all -1); ep = the epipole the reference computes (pKF2->mpCamera->project(T2w * Cw)):

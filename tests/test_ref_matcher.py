@@ -275,3 +275,86 @@ def test_search_by_bow_keyframe_frame(ncam):
                                             p(skip), p(aKF), p(aF), ncam, p(offF), C.c_float(0.7), chk, p(b))
             assert na == nb, (trial, chk, na, nb)
             assert np.array_equal(a, b), (trial, chk, int((a != b).sum()))
+
+
+def test_search_by_bow_keyframe_keyframe():
+    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), src/ORBmatcher.cc:1006-1129: strict < TH_LOW, ratio test, vbMatched2, rotation filter."""
+    rng = np.random.default_rng(55)
+    L = RM(); Lo = O.lib()
+    for trial in range(12):
+        n1, n2 = int(rng.integers(300, 1500)), int(rng.integers(300, 1500))
+        d2 = synth_descriptors(n2, 5900 + trial)
+        d2[5:40] = d2[5]
+        src = rng.integers(0, n2, n1)
+        flips = np.packbits(rng.random((n1, 256)) < 0.04, axis=1, bitorder='little'); flips[:, 0] &= 0xE0
+        d1 = d2[src] ^ flips
+        d1[::5] = synth_descriptors(len(d1[::5]), 99 + trial)
+        a2 = rng.uniform(0, 360, n2).astype(np.float32)
+        a1 = ((a2[src] + rng.choice([0, 0, 0, 30, 95, 190, 250], n1)) % 360).astype(np.float32)
+        fv1, fv2 = _feature_vector(d1), _feature_vector(d2)
+        s1 = (rng.random(n1) < 0.2).astype(np.uint8); s2 = (rng.random(n2) < 0.2).astype(np.uint8)
+        for chk in (0, 1):
+            a = np.zeros(n1, np.int32); b = np.zeros(n1, np.int32)
+            na = L.refm_search_by_bow_keyframes(len(fv1[0]), p(fv1[0]), p(fv1[1]), p(fv1[2]), len(fv2[0]), p(fv2[0]), p(fv2[1]), p(fv2[2]), p(d1), n1,
+                                                p(d2), n2, p(s1), p(s2), p(a1), p(a2), C.c_float(0.75), chk, p(a))
+            nb = Lo.orc_search_by_bow_keyframes(len(fv1[0]), p(fv1[0]), p(fv1[1]), p(fv1[2]), len(fv2[0]), p(fv2[0]), p(fv2[1]), p(fv2[2]), p(d1), n1,
+                                                p(d2), n2, p(s1), p(s2), p(a1), p(a2), C.c_float(0.75), chk, p(b))
+            assert na == nb and na > 10, (trial, chk, na, nb)
+            assert np.array_equal(a, b), (trial, chk, int((a != b).sum()))
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+def test_search_by_projection_current_last(ncam):
+    """SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), src/ORBmatcher.cc:1985-2413 — the tracking matcher:
+    per-camera windows (the side cameras around the LEFT projection, D6), bForward / bBackward level gates, claims in point order, the
+    empty-camera-0 `continue`, the rectified-stereo test, TH_HIGH, rotation histogram.  The reference computes the projections itself
+    from poses and a camera: identity pose, pixel camera, right camera = left + translation."""
+    rng = np.random.default_rng(400 + ncam)
+    L = RM(); Lo = O.lib()
+    w = h = 512
+    for trial in range(12):
+        per = [int(rng.integers(200, 700)) for _ in range(ncam)]
+        cam_off = np.concatenate([[0], np.cumsum(per)]).astype(np.int32)
+        N = int(cam_off[-1])
+        k = make_kps(N, rng, w, h, lattice=8 if trial % 2 else None)
+        desc = synth_descriptors(N, int(rng.integers(1 << 30)))
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        npts = int(rng.integers(200, 1500))
+        src = rng.integers(0, cam_off[1], npts)                          # planted on camera-0 keypoints
+        px = (k['x'][src] + rng.uniform(-4, 4, npts)).astype(np.float32); py = (k['y'][src] + rng.uniform(-4, 4, npts)).astype(np.float32)
+        out = rng.random(npts) < 0.08                                   # some projections fall outside the image
+        px[out] = np.float32(-50.0)
+        trl = np.array([rng.uniform(-30, 30), rng.uniform(-5, 5)], np.float32)
+        has_mp = (rng.random(npts) < 0.9).astype(np.uint8)
+        octv = np.clip(k['octave'][src] + rng.integers(-1, 2, npts), 0, 7).astype(np.int32)
+        ang = ((k['angle'][src] + np.where(rng.random(npts) < 0.8, 20 + rng.uniform(-3, 3, npts), rng.uniform(0, 360, npts))) % 360).astype(np.float32)
+        pd = synth_descriptors(npts, int(rng.integers(1 << 30)))
+        own = rng.random(npts) < 0.75
+        pd[own] = desc[src[own]] ^ np.packbits(rng.random((int(own.sum()), 256)) < 0.06, axis=1, bitorder='little')
+        if trial % 3 == 0:
+            pd[: npts // 4] = pd[0]
+        has_obs = (rng.random(npts) < 0.85).astype(np.uint8)
+        occupied = (rng.random(N) < 0.05).astype(np.uint8)
+        mbf = np.float32(17.25)
+        u_right = np.where(rng.random(N) < 0.4, k['x'] - rng.uniform(2, 40, N), -1).astype(np.float32) if ncam == 1 else None
+        th = float([7.0, 15.0][trial % 2]); gate = trial % 3; chk = (trial // 3) % 2
+        bounds = np.array([0, w, 0, h], np.float32)
+        a = np.zeros(N, np.int32)
+        na = L.refm_search_by_projection_last(ncam, p(cam_off), p(k), p(desc), p(bounds), p(sf), 8, p(occupied), p(u_right), npts, p(has_mp), p(px), p(py),
+                                              p(trl), C.c_float(mbf), p(octv), p(ang), p(has_obs), p(pd), C.c_float(th), gate, chk, p(a))
+        # the same inputs as the array-level interface sees them
+        valid = (has_mp.astype(bool) & (px >= 0) & (px <= w) & (py >= 0) & (py <= h)).astype(np.uint8)
+        PX = np.stack([px, (px + trl[0]).astype(np.float32), px, px], 1).astype(np.float32)
+        PY = np.stack([py, (py + trl[1]).astype(np.float32), py, py], 1).astype(np.float32)
+        pur = (px - mbf).astype(np.float32)
+        grids = (C.c_void_p * ncam)()
+        for c in range(ncam):
+            kc = np.ascontiguousarray(k[cam_off[c]:cam_off[c + 1]])
+            grids[c] = Lo.orc_grid_create(p(kc), len(kc), C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
+        b = np.zeros(N, np.int32)
+        nb = Lo.orc_search_by_projection_last(ncam, p(cam_off), p(k), p(desc), grids, p(sf), p(occupied), p(u_right), npts, p(valid), p(PX), p(PY), p(pur),
+                                              p(octv), p(ang), p(has_obs), p(pd), C.c_float(th), gate, chk, 100, p(b))
+        for c in range(ncam):
+            Lo.orc_grid_destroy(C.c_void_p(grids[c]))
+        assert na == nb and na > 20, (trial, na, nb)
+        assert np.array_equal(a, b), (trial, int((a != b).sum()))
