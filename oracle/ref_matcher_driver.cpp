@@ -277,6 +277,52 @@ int refm_search_by_bow_keyframes(int nn1, const int *nodes1, const int *ptr1, co
     return n;
 }
 
+// ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th, cameraID = 0) (src/ORBmatcher.cc:1458-1640) on a monocular /
+// rectified-stereo keyframe (NLeft == -1).  The keyframe sits at the origin with the pixel camera; map point q sits at (qx, qy, 1), so the
+// reference projects it to (qx, qy), uses invz = 1 (ur = qx - bf), predicts the level the driver is given, and searches
+// KeyFrame::GetFeaturesInArea (lifted from src/KeyFrame.cc).  EVERY keyframe feature already holds a map point with more observations than
+// any query point: a query with bestDist <= TH_LOW then takes the branch `pMP->Replace(pMPinKF)` (:1630-1631), which leaves the keyframe
+// untouched and records the chosen feature — best_idx[q] = that feature, or -1 when the point was not fused.  Returns nFused.
+int refm_fuse(const ref_kp *kps, const uint8_t *desc, int n, const float *bounds, const float *sf, const float *inv_sigma2, int nlev, const float *u_right,
+              float bf, int nq, const uint8_t *valid, const float *qx, const float *qy, const int *level, const uint8_t *q_desc, float th, int *best_idx) {
+    set_bounds(bounds);
+    Frame F;                                                   // builds the grid the KeyFrame constructor copies (src/KeyFrame.cc:113-131)
+    const int cam_off[2] = {0, n};
+    fill_frame(F, 1, cam_off, kps, desc, sf, nlev);
+    KeyFrame K;
+    PixelCamera cam(0);
+    K.N = n; K.mpCamera = &cam;
+    K.mvKeysUn = F.mvKeysUn; K.mvKeys = F.mvKeysUn;
+    K.mDescriptors = F.mDescriptors;
+    K.mvScaleFactors.assign(sf, sf + nlev); K.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + nlev);
+    K.mvuRight.assign(n, -1.f);
+    if (u_right) K.mvuRight.assign(u_right, u_right + n);
+    K.mbf = bf;
+    K.mnMinX = (int)bounds[0]; K.mnMaxX = (int)bounds[1]; K.mnMinY = (int)bounds[2]; K.mnMaxY = (int)bounds[3];
+    K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    K.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) K.mGrid[i][j] = F.mGrid[i][j];
+    std::vector<MapPoint> holders(n), mps(nq);
+    K.map_points.assign(n, nullptr);
+    for (int i = 0; i < n; i++) { holders[i].n_obs = 1000; K.map_points[i] = &holders[i]; }
+    std::vector<MapPoint *> vp(nq, nullptr);
+    for (int q = 0; q < nq; q++) {
+        if (!valid[q]) continue;
+        MapPoint &P = mps[q];
+        P.world_pos = Eigen::Vector3f(qx[q], qy[q], 1.f);
+        const float d = P.world_pos.norm();
+        P.normal = P.world_pos / d;                            // PO.dot(Pn) = dist3D >= 0.5 dist3D (:1557-1563)
+        P.predicted_level = level[q];
+        P.n_obs = 1;
+        P.descriptor = desc_mat(q_desc + (size_t)q * 32, 1);
+        vp[q] = &P;
+    }
+    ORBmatcher matcher(0.6f, true);
+    const int nf = matcher.Fuse(&K, vp, th, 0);
+    for (int q = 0; q < nq; q++) best_idx[q] = (valid[q] && mps[q].replaced_by) ? (int)(mps[q].replaced_by - holders.data()) : -1;
+    return nf;
+}
+
 // ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1985-2413), the tracking
 // matcher.  Current frame as in refm_search_by_projection.  Last frame: npts keypoints in the Nleft == -1 layout; has_mp[i] = the point
 // exists and is no outlier; its map point sits at (px[i], py[i], 1) in world = camera coordinates (Tcw = I, pixel camera), so the

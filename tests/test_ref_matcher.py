@@ -358,3 +358,44 @@ def test_search_by_projection_current_last(ncam):
             Lo.orc_grid_destroy(C.c_void_p(grids[c]))
         assert na == nb and na > 20, (trial, na, nb)
         assert np.array_equal(a, b), (trial, int((a != b).sum()))
+
+
+def test_fuse_keyframe_mappoints():
+    """ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th, cameraID = 0), src/ORBmatcher.cc:1458-1640: the search loop — KeyFrame::GetFeaturesInArea
+    window, level gate [l-1, l], mono (5.99) / stereo (7.8) reprojection gates, first minimum, TH_LOW — against the oracle's window search
+    (orc_window_best), which is what the device entry point orbx_window_best is tested against."""
+    rng = np.random.default_rng(66)
+    L = RM(); Lo = O.lib()
+    w, h = 640, 480
+    for trial in range(12):
+        n = int(rng.integers(300, 2000)); nq = int(rng.integers(200, 1500))
+        k = make_kps(n, rng, w, h, lattice=5 if trial % 2 else None)
+        desc = synth_descriptors(n, 6900 + trial)
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        inv_s2 = (np.float32(1.0) / (sf * sf)).astype(np.float32)
+        src = rng.integers(0, n, nq)
+        qx = (k['x'][src] + rng.uniform(-2.5, 2.5, nq)).astype(np.float32); qy = (k['y'][src] + rng.uniform(-2.5, 2.5, nq)).astype(np.float32)
+        qx[rng.random(nq) < 0.05] = np.float32(-20.0)                        # outside the image: !IsInImage
+        lvl = np.clip(k['octave'][src] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
+        qd = desc[src] ^ np.packbits(rng.random((nq, 256)) < 0.07, axis=1, bitorder='little')
+        qd[::6] = synth_descriptors(len(qd[::6]), 31 + trial)
+        bf = np.float32(19.5)
+        u_right = np.where(rng.random(n) < 0.5, k['x'] - bf + rng.uniform(-1.5, 1.5, n), -1).astype(np.float32) if trial % 2 == 0 else None
+        valid = (rng.random(nq) < 0.95).astype(np.uint8)
+        th = float([3.0, 5.0][trial % 2])
+        bounds = np.array([0, w, 0, h], np.float32)
+        a = np.zeros(nq, np.int32)
+        nf = L.refm_fuse(p(k), p(desc), n, p(bounds), p(sf), p(inv_s2), 8, p(u_right), C.c_float(bf), nq, p(valid), p(qx), p(qy), p(lvl), p(qd),
+                         C.c_float(th), p(a))
+        # the same searches as the array-level interface sees them (the continues before the search are the caller's `valid`)
+        v2 = (valid.astype(bool) & (qx >= 0) & (qx < w) & (qy >= 0) & (qy < h)).astype(np.uint8)
+        radius = (np.float32(th) * sf[lvl]).astype(np.float32)
+        q_ur = (qx - bf).astype(np.float32)
+        g = Lo.orc_grid_create(p(k), n, C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
+        bi = np.zeros(nq, np.int32); bd = np.zeros(nq, np.int32)
+        Lo.orc_window_best(C.c_void_p(g), p(k), p(desc), None, p(u_right), p(inv_s2), nq, p(v2), p(qx), p(qy), p(q_ur), p(radius),
+                           p((lvl - 1).astype(np.int32)), p(lvl), p(qd), p(bi), p(bd))
+        Lo.orc_grid_destroy(C.c_void_p(g))
+        exp = np.where(bd <= 50, bi, -1)
+        assert nf == int((exp >= 0).sum()) and nf > 20, (trial, nf, int((exp >= 0).sum()))
+        assert np.array_equal(a, exp), (trial, int((a != exp).sum()))
