@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ img,
 // phase V combines two buffered rows per output, 4 pixels per thread, one 32-bit store.  The 19-px REFLECT_101 frame is
 // written by the CTA that produced the mirrored interior pixel (extra row / byte stores on edge tiles only).
 // ------------------------------------------------------------------------------------------------------
+// (Round 2 measured a register-marching variant — 128 x 64 tiles, a lane holds 4 output columns, the horizontal pass of a source row
+//  lives in two ping-pong register sets and is reused by the next output row, no shared-memory round trip, equal-sized tiles: 104 M
+//  instead of 123 M warp-instructions on level 1 of the bench batch, but 67 % instead of 80 % issue utilisation — 145 vs 143 us.  Not kept.)
 constexpr int kRszTW = 64, kRszTH = 64;
 constexpr int kRszThreads = 256;
 // dynamic shared memory: staged source [src_rows][src_pitch] u8, horizontal sums [src_rows][kRszTW] u32, y taps [kRszTH];
@@ -407,7 +410,10 @@ __device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *scb
                            -3 * IP, -3 * IP - 1, -2 * IP - 2, -IP - 3, -3, IP - 3, 2 * IP - 2, 3 * IP - 1};
     uint32_t r[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) r[k] = __byte_perm((uint32_t)p0[o[k]], (uint32_t)p1[o[k]], 0x7470);
+    for (int k = 0; k < 16; k++) {
+        // pack on the FMA pipe (IMAD), not with PRMT / LOP3: the kernel is bound by the ALU pipe (VIMNMX3, VABSDIFF4, LOP3)
+        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r[k]) : "r"((uint32_t)p1[o[k]]), "r"((uint32_t)p0[o[k]]));
+    }
     uint32_t mx3[16], mn3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -970,12 +976,14 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o); m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o); }
+    // (Evaluating atan2 + the glibc-exact sincos once per CTA for its 8 keypoints — lane j of warp 0 takes keypoint j, two CTA barriers —
+    //  was measured slower, 0.344 vs 0.326 ms: the barriers cost more than the ~100 saved warp-instructions per keypoint.)
     const float angle = orbx_fast_atan2((float)m01, (float)m10);
-    // ---- descriptor: lane = output byte; its 16 pattern points are 32 signed bytes = two 128-bit loads (a float table — 8 float4
-    //      per lane — was measured 2x slower: 128 B per lane of strided L1 traffic)
     const float rad = __fmul_rn(angle, 0.0174532924f);   // (float)(CV_PI/180.f)
     float sn, cs;
     orbx_sincosf(rad, &sn, &cs);
+    // ---- descriptor: lane = output byte; its 16 pattern points are 32 signed bytes = two 128-bit loads (a float table — 8 float4
+    //      per lane — was measured 2x slower: 128 B per lane of strided L1 traffic)
     const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(pattern) + 2 * lane), pb = __ldg(reinterpret_cast<const uint4 *>(pattern) + 2 * lane + 1);
     const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};   // word k = (x0, y0, x1, y1) of test k
     const uint8_t *cb = tma ? dp + 18 * kDescW + 24 + ((kXO + x - 24) & 15) : plane_ptr(blur, L, b) + (long long)(kYO + y) * L.pitch + kXO + x;
