@@ -11,8 +11,8 @@
 //   ORBmatcher::SearchForInitialization(F1, F2, ...)                 src/ORBmatcher.cc:895-1004    orbx_search_for_initialization
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)                  src/ORBmatcher.cc:349-666     orbx_search_by_bow_frame
 //
-// tests/host_harness builds this file against oracle/refstub (stub Frame / KeyFrame / MapPoint with the reference's member names) and
-// tests/test_matcher_glue.py compares it, call by call, with the reference's own object code (oracle/_ref/libref_matcher.so).
+// tests/host_harness builds this file against stub Frame / KeyFrame / MapPoint headers that carry the reference's member names and
+// tests/test_matcher_glue.py compares it, call by call, with the reference's own object code (the unmodified ORBmatcher.cc compiled against the same stubs).
 #include <ORBmatcher.h>   // the REFERENCE's include/ORBmatcher.h from the include path (not the array-level header next to this file)
 
 #include <stdio.h>

@@ -108,6 +108,7 @@ struct orbx_extractor {
     float *d_st_uright = nullptr, *d_st_depth = nullptr;   // ComputeStereoMatches outputs (allocated on first use)
     int *d_st_sad = nullptr, *d_st_kept = nullptr;
     FastTile *d_fast_tiles = nullptr;
+    int fast_kb_words = 0;
     FastStats *d_fast_stats = nullptr;                     // k_fast counters, accumulated while profiling is on
     // pinned staging
     uint8_t *h_in = nullptr;
@@ -205,8 +206,13 @@ static int build_geometry(orbx_extractor *ex, int fma_mode) {
     }
     G.fast_total_tiles = ftiles;
     G.fast_ymax = max_cell_h - 6;
-    ex->fast_smem = fast_smem_bytes(G.fast_ip, G.fast_ymax);
-    if (ex->fast_smem > 200 * 1024 || G.fast_ip > 512 || (G.fast_ymax + 6 + kFastStrip) * G.fast_ip > 65535)
+    {   // keep bitmap of one cell: one bit per tested pixel, 64 bits per lane
+        int bits = 0;
+        for (int l = 0; l < nl; l++) bits = std::max(bits, G.lv[l].w_cell * G.lv[l].h_cell);
+        ex->fast_kb_words = ((bits + 63) / 64 * 2 + 3) & ~3;
+    }
+    ex->fast_smem = fast_smem_bytes(G.fast_ip, G.fast_ymax, ex->fast_kb_words);
+    if (ex->fast_smem > 200 * 1024 || G.fast_ip > 512 || (G.fast_ymax + 6) * G.fast_ip > 65535)
         return fail(ORBX_ERR_INVALID, "FAST tile does not fit in shared memory");
     ex->oct_list_cap = max_list;
     ex->oct_smem = oct_work_bytes(max_list);
@@ -385,7 +391,8 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
                     T.Y = std::max(0, std::min(T.ty0 + L.h_cell, L.h - kEdge) - T.ty0);
                     T.pc0 = (kXO + T.tx0 - 3) & ~15; T.prow0 = kYO + T.ty0 - 3; T.c0 = kXO + T.tx0 - T.pc0;
                     T.cell0 = L.cell_base + i * L.n_cols + j0;
-                    T.nstr = std::max(1, (T.Y + kFastStrip - 1) / kFastStrip); T.rs = (T.Y + T.nstr - 1) / T.nstr;
+                    T.nstr = 1; T.rs = 1;
+                    if (T.Y > 0) fast_plan_strips(T.Y, T.wc, G.fast_ip, &T.nstr, &T.rs, T.sr);
                     const long long cand0 = L.cand_off + (long long)(i * L.n_cols + j0) * L.cell_cap;
                     T.cand0_lo = (int)(unsigned)(cand0 & 0xFFFFFFFFll); T.cand0_hi = (int)(cand0 >> 32);
                     T.plane_off = L.plane_off; T.plane_bytes = L.plane_bytes; T.pitch = L.pitch;
@@ -576,7 +583,7 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
         launches++;
     }
     if (ev) ORBX_CUDA(cudaEventRecord(ev[2], sA));
-    const FastArgs fa = {G.fast_ymax, G.total_cells, i0, 0, G.cand_per_image};
+    const FastArgs fa = {G.fast_ymax, G.total_cells, i0, ex->fast_kb_words, G.cand_per_image};
     fast_kernel(G.fast_ip)<<<dim3(G.fast_total_tiles, cnt), kFastThreads, ex->fast_smem, sA>>>(ex->d_pyr, ex->d_fast_tiles, fa, ex->d_params, ex->d_cells, ex->d_cell_cnt, ex->fast_maps,
                                                                                 ex->profiling ? ex->d_fast_stats : nullptr);
     launches++;

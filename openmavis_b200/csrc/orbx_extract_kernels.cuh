@@ -370,49 +370,156 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
 // ------------------------------------------------------------------------------------------------------
 constexpr int kFastWarps = 4;                 // warps per CTA = cells per tile (one warp per cell)
 constexpr int kFastThreads = kFastWarps * 32;
-constexpr int kFastStrip = 7;                 // rows a lane marches through per work item (one 4-pixel word wide); odd, and the row pitch
-                                              // is 16 x odd bytes, so that the strips of one warp iteration fall into different banks
-constexpr int kFastQueue = 64 + 32 * 16;      // per-warp survivor queue (u16 entries): < 64 left + up to 512 new (half a strip item per lane)
+constexpr int kFastStrip = 14;                // rows a lane marches through per work item (one 4-pixel word wide): two flag registers of 7 rows
+constexpr int kFastHalf = 7;                  // rows per flag register (byte = pixel, bit = row)
+constexpr int kFastMaxStrips = 13;            // strips with host-chosen start rows (FastTile::sr); taller cells use equal strips
+constexpr int kFastQueue = 512;               // per-warp survivor queue (u16 entries): < 64 left + up to 448 new (a flag register with more
+                                              // survivors is appended in four parts)
 constexpr int kFastMaxG = kFastWarps;
 constexpr int kFastCorners = 256;             // corner list of one cell (per warp); a cell with more corners falls back to a sweep
-constexpr int kFastMaxY = 64;                 // rows / columns of a cell the fast emission path handles (two rows per lane, 64-bit row masks)
 
 // One FAST tile (CTA) of an image: up to kFastMaxG adjacent cells of one cell row; built on the host once per handle.
 struct __align__(16) FastTile {
     int lvl, ncell, wc, cell_cap;      // level, cells in this tile, nominal cell width, candidate slots per cell
     int tx0, ty0, X, Y;                // tested area in level coordinates: x in [tx0, tx0 + X), y in [ty0, ty0 + Y)
     int pc0, prow0, c0, cell0;         // staged tile: plane column (16-B aligned) and plane row of its corner; smem column of tx0; first cell index
-    int nstr, rs, cand0_lo, cand0_hi;  // strips of rs <= 8 rows; slot offset of the first cell's candidate slots in an image's arena
+    int nstr, rs, cand0_lo, cand0_hi;  // strips of rs <= kFastStrip rows; slot offset of the first cell's candidate slots in an image's arena
     long long plane_off, plane_bytes;  // (cp.async fallback) byte offset of image 0's plane, bytes per plane
-    int pitch, pad0, pad1, pad2;
+    int pitch;
+    unsigned short sr[kFastMaxStrips + 1];   // nstr <= kFastMaxStrips: first row of strip s (sr[nstr] = Y); a strip owns the rows up to the next
+                                             // strip's first row.  The host picks the start rows so that the strips of one warp iteration
+                                             // fall into different shared-memory banks (fast_plan_strips)
 };
+static_assert(sizeof(FastTile) == 112, "FastTile layout");
 
 // shared memory of one CTA (ip = row pitch in bytes, a template constant so that every row offset is an immediate):
-//   img [(ymax + 6)][ip]  level pixels, row 0 = tile row -3, column 0 = plane column pc0 (16-byte aligned)
-//   sc  [(ymax + 2)][ip]  scores, same column indexing, rows 0 and Y+1 stay zero
-//   bm  [ymax][ceil(ip / 32)]   keep bitmap (rounded up to 16 bytes)
-//   q   [kFastWarps][kFastQueue] u16 survivor queues (entries = byte offsets into img), cl [kFastWarps][kFastCorners] u16 corner lists
-__host__ __device__ inline int fast_zero_bytes(int ip, int ymax) { return ((ymax + 2) * ip + ymax * ((ip + 31) >> 5) * 4 + 15) & ~15; }
-__host__ __device__ inline size_t fast_smem_bytes(int ip, int ymax) {
-    return (size_t)(ymax + 6 + kFastStrip) * ip + fast_zero_bytes(ip, ymax) + (size_t)kFastWarps * (kFastQueue + kFastCorners) * 2;
+//   img [(ymax + 6)][ip]               level pixels, row 0 = tile row -3, column 0 = plane column pc0 (16-byte aligned)
+//   sc  [(ymax + 2)][ip]               scores, same column indexing, rows 0 and Y+1 stay zero
+//   per warp: q [kFastQueue] u16 survivor queue (entries = byte offsets into img), cl [kFastCorners] u16 corner list,
+//   kb [kb_words] u32 keep bitmap of the warp's cell (bit = row * cell width + column)
+__host__ __device__ inline int fast_zero_bytes(int ip, int ymax) { return ((ymax + 2) * ip + 15) & ~15; }
+__host__ __device__ inline int fast_warp_bytes(int kb_words) { return kb_words * 4 + (kFastQueue + kFastCorners) * 2; }
+__host__ __device__ inline size_t fast_smem_bytes(int ip, int ymax, int kb_words) {
+    return (size_t)(ymax + 6) * ip + fast_zero_bytes(ip, ymax) + (size_t)kFastWarps * fast_warp_bytes(kb_words);
 }
 
 // exact x / d for 0 <= x < 65536, 8 <= d: (x + 0.5) / d is at least 0.5 / d away from an integer, far above fp32 error
 __device__ __forceinline__ int small_div(int x, float inv_d) { return (int)(((float)x + 0.5f) * inv_d); }
 
+// Host side: strips of a tile.  A lane marches down rs rows of one word column; item f of a cell = (strip f / nw, word f % nw).  The
+// count / height of the strips is chosen for lane utilisation, their first rows for bank spread: the lanes of one warp iteration read
+// word (row * P + word) of the tile, so two strips whose first rows differ by d rows are d * P banks apart.
+inline void fast_plan_strips(int Y, int wc, int ip, int *nstr_out, int *rs_out, unsigned short *sr) {
+    const int P = ip / 4;
+    int nws[4];
+    for (int off = 0; off < 4; off++) nws[off] = (off + wc + 3) / 4;   // words a cell row spans at each alignment of its first pixel
+    const int nw = nws[1];                                             // bank spread is evaluated for a common alignment
+    // greedy start rows for n strips of rs rows: strip s starts at the row in [prev + 1, prev + rs] (coverage of the rest permitting)
+    // that collides least with the lanes already placed in the same 32-lane group; returns the number of colliding lanes
+    auto place = [&](int n, int rs, unsigned short *st) {
+        int total = 0;
+        st[0] = 0;
+        for (int s = 1; s < n; s++) {
+            // (every strip lies inside the Y rows, so the march never reads past the staged tile; a strip may own no row at all)
+            const int lo = std::max((int)st[s - 1], Y - (n - s) * rs), hi = std::min(st[s - 1] + rs, Y - rs);
+            int best_r = hi, best_c = 1 << 30;
+            for (int r = hi; r >= lo; r--) {                           // (late starts first: fewer rows tested twice)
+                int c = 0;
+                for (int w = 0; w < nw; w++)
+                    for (int s2 = 0; s2 < s; s2++)
+                        for (int w2 = 0; w2 < nw; w2++)
+                            if (((s2 * nw + w2) >> 5) == ((s * nw + w) >> 5) && ((st[s2] * P + w2 - r * P - w) & 31) == 0) c++;
+                if (c < best_c) { best_c = c; best_r = r; }
+            }
+            st[s] = (unsigned short)best_r;
+            total += best_c;
+        }
+        st[n] = (unsigned short)Y;
+        return total;
+    };
+    const int nmin = (Y + kFastStrip - 1) / kFastStrip;
+    int best_n = nmin, best_rs = (Y + nmin - 1) / nmin;
+    double best_cost = 1e30;
+    unsigned short st[kFastMaxStrips + 1];
+    for (int s = 0; s <= kFastMaxStrips; s++) sr[s] = 0;
+    for (int n = nmin; n <= std::min(std::max(nmin, Y), kFastMaxStrips); n++)
+        for (int rs = Y >= kFastStrip ? kFastStrip : (Y + n - 1) / n; rs <= std::min(Y, kFastStrip); rs++) {   // (full-height strips run the
+                                                                                                               //  branch-free variant of the quick test)
+            double cost = 0;
+            for (int off = 0; off < 4; off++) cost += 0.25 * ((n * nws[off] + 31) / 32) * (rs * 36.0 + 130.0);   // instructions per cell pass
+            cost += 0.5 * place(n, rs, st) * (3 * rs + 14);                                                        // extra LDS wavefronts
+            if (cost < best_cost) { best_cost = cost; best_n = n; best_rs = rs; memcpy(sr, st, sizeof(st)); }
+        }
+    *nstr_out = best_n; *rs_out = best_rs;   // (more than kFastMaxStrips strips: equal strips s * rs, no table)
+}
+
+// Shared memory is addressed through 32-bit shared-window addresses held in registers the compiler cannot re-derive (sa_keep): with
+// generic pointers it rebuilt the per-warp base addresses (S2R / cluster-window LEA chains) inside every inner loop.  *_ro loads are for
+// the read-only image tile (free to schedule); the others are ordered (volatile, memory clobber): scores, queue, lists, keep bits.
+__device__ __forceinline__ uint32_t sa_keep(uint32_t a) { asm volatile("" : "+r"(a)::"memory"); return a; }
+__device__ __forceinline__ uint32_t lds32_ro(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8_ro(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128_zero(uint32_t a) { asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u) : "memory"); }
+__device__ __forceinline__ void reds_or32(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_add64(uint32_t a, unsigned long long v) { asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+
+// Quick reject of one work item: rows [0, rs) of one word column (4 pixels), col = shared address of the word in the strip's first img row
+// (the centre of strip row i is img row i + 3).  A FAST-9 corner at threshold t has an arc of 9 ring pixels with |v - r| > t; an arc of 9
+// holds one pixel of every opposite pair (k, k + 8), so |v - r| > t must hold on at least one pixel of each of the four pairs of the even
+// ring positions: (0, +-3), (+-3, 0), (2, 2)/(-2, -2), (2, -2)/(-2, 2).  Byte-SIMD: 4 pixels per VABSDIFF4, the compare is the carry into
+// bit 7 of d + (127 - t) (or d >= 128); flags of strip rows 0-6 go to mA, rows 7-13 to mB (byte = pixel, bit = row).
+// (On the bench images: 12.5 % of the pixels survive, 4.2 % are corners; the former test on the pairs (0, 8) and (4, 12) alone left 23.5 %.)
+template <int IP, bool FULL>
+__device__ __forceinline__ void fast_quick8(uint32_t col, int rs, uint32_t cadd, uint32_t &mA, uint32_t &mB) {
+    uint32_t cu[kFastStrip + 6], dm[kFastStrip + 6], dp[kFastStrip + 6], hl[kFastStrip + 6], hr[kFastStrip + 6];
+    mA = 0; mB = 0;
+#pragma unroll
+    for (int j = 0; j < kFastStrip + 6; j++) {
+        if (FULL || j < 7 || j < rs + 6) {               // (warp-uniform; FULL: rs == kFastStrip)
+            const uint32_t rp = col + j * IP;
+            cu[j] = lds32_ro(rp);
+            if (j >= 1 && j <= kFastStrip + 4) {         // rows that serve as y - 2, y, y + 2 of some centre row
+                const uint32_t pv = lds32_ro(rp - 4), nx = lds32_ro(rp + 4);
+                dm[j] = __byte_perm(pv, cu[j], 0x5432);  // pixels x - 2
+                dp[j] = __byte_perm(cu[j], nx, 0x5432);  // pixels x + 2
+                if (j >= 3 && j <= kFastStrip + 2) { hl[j] = __byte_perm(pv, cu[j], 0x4321); hr[j] = __byte_perm(cu[j], nx, 0x6543); }
+            }
+            if (j >= 6) {
+                const int i = j - 6;                     // centre row of the strip, img row i + 3
+                const uint32_t v = cu[i + 3];
+                const uint32_t d0 = __vabsdiffu4(v, cu[i]), d8 = __vabsdiffu4(v, cu[i + 6]);
+                const uint32_t d4 = __vabsdiffu4(v, hr[i + 3]), d12 = __vabsdiffu4(v, hl[i + 3]);
+                const uint32_t d2 = __vabsdiffu4(v, dp[i + 5]), d10 = __vabsdiffu4(v, dm[i + 1]);
+                const uint32_t d6 = __vabsdiffu4(v, dp[i + 1]), d14 = __vabsdiffu4(v, dm[i + 5]);
+                const uint32_t acc = (d0 | d8 | (d0 + cadd) | (d8 + cadd)) & (d4 | d12 | (d4 + cadd) | (d12 + cadd)) &
+                                     (d2 | d10 | (d2 + cadd) | (d10 + cadd)) & (d6 | d14 | (d6 + cadd) | (d14 + cadd));
+                if (i < kFastHalf) mA |= (acc >> (7 - i)) & (0x01010101u << i);
+                else mB |= (acc >> (7 - (i - kFastHalf))) & (0x01010101u << (i - kFastHalf));
+            }
+        }
+    }
+}
+
 // Scores the centre pixels at img offsets a0 / a1 (queue entries) with packed u16x2 arithmetic, stores S where S >= t and
-// appends those pixels to the warp's corner list (ncl = warp-uniform fill level).  scb[a] is the score of the pixel at img offset a.
+// appends those pixels to the warp's corner list at shared address cl (ncl = warp-uniform fill level).  img / scb: shared addresses of
+// the image tile and of the score of img offset 0.
 template <int IP>
-__device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *scb, int a0, int a1, bool ok0, bool ok1, int t,
-                                                unsigned short *cl, int &ncl, unsigned lt_mask) {
-    const uint8_t *p0 = img + a0, *p1 = img + a1;
+__device__ __forceinline__ void fast_score_pair(uint32_t img, uint32_t scb, int a0, int a1, bool ok0, bool ok1, int t,
+                                                uint32_t cl, int &ncl, unsigned lt_mask) {
+    const uint32_t p0 = img + a0, p1 = img + a1;
     constexpr int o[16] = {3 * IP, 3 * IP + 1, 2 * IP + 2, IP + 3, 3, -IP + 3, -2 * IP + 2, -3 * IP + 1,
                            -3 * IP, -3 * IP - 1, -2 * IP - 2, -IP - 3, -3, IP - 3, 2 * IP - 2, 3 * IP - 1};
     uint32_t r[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         // pack on the FMA pipe (IMAD), not with PRMT / LOP3: the kernel is bound by the ALU pipe (VIMNMX3, VABSDIFF4, LOP3)
-        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r[k]) : "r"((uint32_t)p1[o[k]]), "r"((uint32_t)p0[o[k]]));
+        asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r[k]) : "r"(lds8_ro(p1 + o[k])), "r"(lds8_ro(p0 + o[k])));
     }
     uint32_t mx3[16], mn3[16];
 #pragma unroll
@@ -432,30 +539,31 @@ __device__ __forceinline__ void fast_score_pair(const uint8_t *img, uint8_t *scb
     }
     // S = max(v - A, B - v) - 1 for both halves at once: v - A and B - v never wrap when they matter (A <= v or B >= v for a corner),
     // a wrapped half is > 255 as u16 only if it was negative, in which case the other term or the threshold test discards it
-    const int v0 = p0[0], v1 = p1[0];
+    const int v0 = (int)lds8_ro(p0), v1 = (int)lds8_ro(p1);
     const int s0 = max(v0 - (int)(A & 0xFFFFu), (int)(B & 0xFFFFu) - v0) - 1;
     const int s1 = max(v1 - (int)(A >> 16), (int)(B >> 16) - v1) - 1;
     const bool c0 = ok0 && s0 >= t, c1 = ok1 && s1 >= t;
-    if (c0) scb[a0] = (uint8_t)s0;
-    if (c1) scb[a1] = (uint8_t)s1;
+    if (c0) sts8(scb + a0, (uint32_t)s0);
+    if (c1) sts8(scb + a1, (uint32_t)s1);
     const unsigned b0 = __ballot_sync(0xFFFFFFFFu, c0), b1 = __ballot_sync(0xFFFFFFFFu, c1);
     const int n0 = __popc(b0);
-    if (c0) { const int p = ncl + __popc(b0 & lt_mask); if (p < kFastCorners) cl[p] = (unsigned short)a0; }
-    if (c1) { const int p = ncl + n0 + __popc(b1 & lt_mask); if (p < kFastCorners) cl[p] = (unsigned short)a1; }
+    if (c0) { const int p = ncl + __popc(b0 & lt_mask); if (p < kFastCorners) sts16(cl + 2 * p, (uint32_t)a0); }
+    if (c1) { const int p = ncl + n0 + __popc(b1 & lt_mask); if (p < kFastCorners) sts16(cl + 2 * p, (uint32_t)a1); }
     ncl += n0 + __popc(b1);
 }
 
-// strict 3x3 maximum of the score at (tile row, img column) inside its cell (columns [cx0, cx0 + wc)) -> keep bitmap
+// strict 3x3 maximum of the score at (tile row, img column) inside its cell (columns [cx0, cx0 + wc), wdt of them tested) -> keep bitmap
+// of the cell (bit = row * wdt + column inside the cell); sc1 / kb: shared addresses of the score of tile row 0, column 0 and of the bitmap
 template <int IP>
-__device__ __forceinline__ bool fast_nms_one(const uint8_t *sc1, uint32_t *bm, int row, int col, int cx0, int wc) {
-    const uint8_t *n = sc1 + row * IP + col;
-    const int s = n[0];
+__device__ __forceinline__ bool fast_nms_one(uint32_t sc1, uint32_t kb, int row, int col, int cx0, int wc, int wdt) {
+    const uint32_t n = sc1 + row * IP + col;
     const int xl = col - cx0;
-    // all eight neighbours are loaded before the first compare (independent loads instead of a short-circuit chain)
-    const int u = n[-IP], d = n[IP], l = n[-1], ul = n[-IP - 1], dl = n[IP - 1], r = n[1], ur = n[-IP + 1], dr = n[IP + 1];
+    // all nine scores are loaded before the first compare (independent loads instead of a short-circuit chain)
+    const int s = lds8(n), u = lds8(n - IP), d = lds8(n + IP), l = lds8(n - 1), ul = lds8(n - IP - 1), dl = lds8(n + IP - 1), r = lds8(n + 1),
+              ur = lds8(n - IP + 1), dr = lds8(n + IP + 1);
     const int ml = xl > 0 ? max(l, max(ul, dl)) : -1, mr = xl < wc - 1 ? max(r, max(ur, dr)) : -1;
     const bool keep = s > max(max(u, d), max(ml, mr));
-    if (keep) atomicOr(&bm[row * ((IP + 31) >> 5) + (col >> 5)], 1u << (col & 31));
+    if (keep) { const int bit = row * wdt + xl; reds_or32(kb + 4 * (bit >> 5), 1u << (bit & 31)); }
     return keep;
 }
 
@@ -465,7 +573,7 @@ struct FastMaps { CUtensorMap m[kMaxLevels]; int use_tma; };
 // optional per-launch statistics (profiling mode only): tested pixels, quick-test survivors, corners, kept after NMS, retried cells, tiles
 struct FastStats { unsigned long long tested, survivors, corners, kept, retry_cells, tiles; };
 
-struct FastArgs { int ymax, total_cells, img0, pad; long long cand_per_image; };
+struct FastArgs { int ymax, total_cells, img0, kb_words; long long cand_per_image; };
 
 template <int IP>
 __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restrict__ pyr, const FastTile *__restrict__ tiles, const FastArgs A,
@@ -473,11 +581,11 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
                                                        uint32_t *__restrict__ cells, int *__restrict__ cell_cnt,
                                                        const __grid_constant__ FastMaps maps, FastStats *__restrict__ stats) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int bw = (IP + 31) >> 5;
     const int b = blockIdx.y + A.img0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // tile descriptor: the same for every thread (broadcast loads)
-    const int4 *tp = reinterpret_cast<const int4 *>(tiles + blockIdx.x);
+    const FastTile *tile = tiles + blockIdx.x;
+    const int4 *tp = reinterpret_cast<const int4 *>(tile);
     const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
     const int lvl = t0.x, ncell = t0.y, wc = t0.z, cell_cap = t0.w;
     const int tx0 = t1.x, ty0 = t1.y, X = t1.z, Y = t1.w;
@@ -488,13 +596,10 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
         return;
     }
     const int img_bytes = IP * (A.ymax + 6), zero_bytes = fast_zero_bytes(IP, A.ymax);
-    uint8_t *img = smem;
-    uint8_t *sc = img + img_bytes + kFastStrip * IP;      // (the quick test may read up to 8 rows past the staged ones; their flags are masked)
-    uint32_t *bm = reinterpret_cast<uint32_t *>(sc + IP * (A.ymax + 2));
-    unsigned short *q = reinterpret_cast<unsigned short *>(sc + zero_bytes) + wid * kFastQueue;
-    unsigned short *cl = reinterpret_cast<unsigned short *>(sc + zero_bytes) + kFastWarps * kFastQueue + wid * kFastCorners;
     // ---- stage the tile: plane rows prow0 .. prow0 + Y + 5, 16-byte columns from pc0
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ unsigned long long s_stats[4];           // (profiling mode) survivors, corners, kept, retried cells of this tile
+    if (tid < 4) s_stats[tid] = 0;
     if (maps.use_tma) {
         // ONE TMA tensor copy stages the tile (box = fast_ip x (fast_ymax + 6) from plane column pc0, row prow0; what lies
         // beyond the columns / rows this tile needs is harmless), in flight while the CTA clears the score map
@@ -502,7 +607,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
         __syncthreads();
         if (tid == 0) {
             mbar_arrive_expect_tx(&s_bar, (uint32_t)img_bytes);
-            tma_load_3d(img, &maps.m[lvl], pc0 >> 1, prow0, b, &s_bar);   // x in 16-bit elements
+            tma_load_3d(smem, &maps.m[lvl], pc0 >> 1, prow0, b, &s_bar);   // x in 16-bit elements
         }
     } else {
         // 16-byte cp.async (LDGSTS) copies.  (One TMA bulk copy per tile ROW was measured slower than this: ~190 small requests
@@ -513,220 +618,214 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
         const int nvec = (c0 + X + 3 + 15) >> 4;        // uint4 per row
         if (lane < nvec) {
             const uint8_t *src = pyr + plane_off + (long long)b * plane_bytes + (long long)prow0 * pitch + pc0 + 16 * lane;
-            const uint32_t dst = smem_u32(img) + 16 * lane;
+            const uint32_t dst = smem_u32(smem) + 16 * lane;
+#pragma unroll 1
             for (int r = wid; r < Y + 6; r += kFastWarps)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * IP), "l"(src + (long long)r * pitch) : "memory");
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    // shared addresses, opaque to the compiler from here on: image tile, score of img offset 0 / of tile row 0, this warp's region
+    // [q: kFastQueue u16][cl: kFastCorners u16][kb: kb_words u32]
+    const uint32_t sc = smem_u32(smem) + img_bytes;
     {
-        uint4 *z = reinterpret_cast<uint4 *>(sc);             // score map and bitmap are contiguous
-        const int nz = zero_bytes >> 4;
-        for (int i = tid; i < nz; i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
+#pragma unroll 2
+        for (int i = tid; i < (zero_bytes >> 4); i += kFastThreads) sts128_zero(sc + 16 * i);   // score map
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (maps.use_tma && tid < 32) mbar_wait(&s_bar, 0);
     __syncthreads();
+    const uint32_t img = sa_keep(smem_u32(smem));
+    const uint32_t scb = sa_keep(sc - 2 * IP);          // score of the pixel at img offset a: scb + a (img row = tile row + 3)
+    const uint32_t q = sa_keep(sc + zero_bytes + wid * fast_warp_bytes(A.kb_words));
+    const uint32_t cl = q + 2 * kFastQueue, kb = cl + 2 * kFastCorners;
+    const uint32_t sc1 = scb + 3 * IP;                  // score of tile row 0, column 0
     // ---- from here on every warp works alone on its own cells: quick test -> queue -> scores -> NMS -> (retry) -> emission.
     //      Cells only share the read-only image tile; scores and keep bits of a cell are written and read by its warp only.
     const int t_ini = min(max(__ldg(&params[b].ini_th_fast), 0), 255), t_min = min(max(__ldg(&params[b].min_th_fast), 0), 255);
-    uint8_t *sc1 = sc + IP;                             // score row of tile row 0
-    uint8_t *scb = sc - 2 * IP;                         // scb[img offset] = score of that pixel (img row = tile row + 3)
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned long long st_surv = 0, st_corn = 0, st_kept = 0, st_retry = 0;
+#pragma unroll 1
     for (int k = wid; k < ncell; k += kFastWarps) {
         int *cnt_out = cell_cnt + (long long)b * A.total_cells + cell0 + k;
         const int cx0 = c0 + k * wc, cx1 = min(cx0 + wc, c0 + X);   // smem columns of the cell's tested pixels
         if (cx1 <= cx0) { if (lane == 0) *cnt_out = 0; continue; }
+        const int wdt = cx1 - cx0;
         const int w0 = cx0 >> 2, w1 = (cx1 - 1) >> 2;   // words of a row that hold tested pixels of this cell
         const int nw = w1 - w0 + 1;
         const float inv_nw = 1.0f / (float)nw;
         const int nflat = nstr * nw;                    // work items: (strip of rs rows) x (word column)
+        const int nkb = (Y * wdt + 31) >> 5;            // words of the cell's keep bitmap
         bool any_kept = false;
+#pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
             const int t = pass == 0 ? t_ini : t_min;
             // per byte: x + cadd has bit 7 set iff x > t for x < 128 (x >= 128 > t is caught by OR-ing x itself, t <= 126).  A carry out
             // of a byte can only turn |d| == t of the next byte into a survivor: the quick test is a necessary condition, scoring is exact.
             const uint32_t cadd = (uint32_t)(0x80 - (min(t, 126) + 1)) * 0x01010101u;
-            // ---- 1 + 2: quick reject and pair scoring.  One lane marches down the rs rows of one word column (4 pixels) with the column's
-            //      words in registers; a corner needs |v - r| > t on at least one of the ring pixels {0, 8} (rows +-3) and one of {4, 12}
-            //      (columns +-3).  The survivor flags of the 32 pixels end up in one register (byte = pixel, bit = row).
+            if (pass == 0) {                            // (a repeated cell kept nothing: still clear)
+#pragma unroll 1
+                for (int i = lane; i < ((nkb + 1) & ~1); i += 32) sts32(kb + 4 * i, 0u);
+            }
+            // ---- 1 + 2: quick reject, survivor queue, pair scoring.  The last trip of the loop (f0 >= nflat) only drains the queue.
             int qn = 0, ncl = 0;                        // fill levels of this warp's queue and corner list (warp-uniform)
-            for (int f0 = 0; f0 < nflat; f0 += 32) {
+#pragma unroll 1
+            for (int f0 = 0;; f0 += 32) {
+                const bool drain = f0 >= nflat;
                 const int f = f0 + lane;
-                uint32_t m = 0;
+                uint32_t mA = 0, mB = 0;
                 int abase = 0;
-                if (f < nflat) {
-                    const int strip = small_div(f, inv_nw), wi = w0 + (f - strip * nw), r0 = strip * rs;
+                if (!drain && f < nflat) {
+                    const int strip = small_div(f, inv_nw), wi = w0 + (f - strip * nw);
+                    int own0, own1;                     // rows this strip owns; it marches rs rows from r0 <= own0 (never past row Y + 2)
+                    if (nstr <= kFastMaxStrips) { own0 = __ldg(&tile->sr[strip]); own1 = __ldg(&tile->sr[strip + 1]); }
+                    else { own0 = strip * rs; own1 = min(own0 + rs, Y); }
+                    const int r0 = min(own0, Y - rs);
                     // pixels of this word that belong to the cell
                     const int first = max(cx0 - 4 * wi, 0), last = min(cx1 - 1 - 4 * wi, 3);
                     const uint32_t cm = (0xFFFFFFFFu << (8 * first)) & (0xFFFFFFFFu >> (8 * (3 - last)));
                     abase = (r0 + 3) * IP + 4 * wi;
-                    const uint8_t *col = img + r0 * IP + 4 * wi;
-                    uint32_t cw[kFastStrip + 6];
-#pragma unroll
-                    for (int j = 0; j < kFastStrip + 6; j++) cw[j] = *reinterpret_cast<const uint32_t *>(col + j * IP);
-#pragma unroll
-                    for (int i = 0; i < kFastStrip; i++) {
-                        if (i < rs) {
-                            const uint8_t *cr = col + (i + 3) * IP;
-                            const uint32_t v = cw[i + 3];
-                            const uint32_t pv = *reinterpret_cast<const uint32_t *>(cr - 4), nx = *reinterpret_cast<const uint32_t *>(cr + 4);
-                            const uint32_t dl = __vabsdiffu4(v, __byte_perm(pv, v, 0x4321)), dr = __vabsdiffu4(v, __byte_perm(v, nx, 0x6543));
-                            const uint32_t du = __vabsdiffu4(v, cw[i]), dd = __vabsdiffu4(v, cw[i + 6]);
-                            const uint32_t ud = du | dd | (du + cadd) | (dd + cadd);
-                            const uint32_t lr = dl | dr | (dl + cadd) | (dr + cadd);
-                            m |= ((ud & lr) >> (7 - i)) & (0x01010101u << i);
-                        }
-                    }
-                    const int nr = min(rs, Y - r0);
-                    m &= cm & (0x01010101u * ((1u << nr) - 1u));
+                    if (rs == kFastStrip) fast_quick8<IP, true>(img + r0 * IP + 4 * wi, rs, cadd, mA, mB);
+                    else fast_quick8<IP, false>(img + r0 * IP + 4 * wi, rs, cadd, mA, mB);
+                    const uint32_t rows = ((1u << min(rs, own1 - r0)) - 1u) & ~((1u << (own0 - r0)) - 1u);   // bit i = strip row i is owned
+                    mA &= cm & (0x01010101u * (rows & ((1u << kFastHalf) - 1u)));
+                    mB &= cm & (0x01010101u * (rows >> kFastHalf));
                 }
-                if (stats) st_surv += __popc(m);
-                // append the survivors to the warp's queue in two halves (rows 0-3, rows 4-6) so that the queue stays small; entries are img
-                // byte offsets, the order inside the queue is irrelevant
-#pragma unroll
+                if (stats) { const int c = __reduce_add_sync(0xFFFFFFFFu, __popc(mA) + __popc(mB)); if (lane == 0) reds_add64(smem_u32(&s_stats[0]), (unsigned long long)c); }
+                // append the survivors to the warp's queue, one flag register at a time so that the queue stays small; entries are img byte
+                // offsets, the order inside the queue is irrelevant
+#pragma unroll 1
                 for (int half = 0; half < 2; half++) {
-                    uint32_t mh = m & (half ? 0xF0F0F0F0u : 0x0F0F0F0Fu);
-                    if (!__any_sync(0xFFFFFFFFu, mh != 0)) continue;
-                    const int cnt = __popc(mh);
-                    int inc = cnt;
+                    const uint32_t mhalf = half ? mB : mA;
+                    const int nsurv = __reduce_add_sync(0xFFFFFFFFu, __popc(mhalf));
+                    const int nsub = nsurv == 0 ? 0 : nsurv <= kFastQueue - 64 ? 1 : 4;   // (4: row pairs, at most 256 survivors each)
+                    const int ab = abase + half * (kFastHalf * IP);
+                    const int need = drain ? 1 : 64;
+#pragma unroll 1
+                    for (int sub = 0; sub < max(nsub, 1); sub++) {
+                        if (nsub) {
+                            uint32_t mh = nsub == 1 ? mhalf : mhalf & (0x03030303u << (2 * sub));
+                            const int cnt = __popc(mh);
+                            int inc = cnt;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
-                    unsigned short *qp = q + qn + inc - cnt;
-                    qn += __shfl_sync(0xFFFFFFFFu, inc, 31);
-                    while (mh) {                         // two survivors per trip: the highest and the lowest flag
-                        const int kh = 31 - __clz(mh), kl = __ffs(mh) - 1;
-                        qp[0] = (unsigned short)(abase + (kh & 7) * IP + (kh >> 3));
-                        if (kh != kl) qp[1] = (unsigned short)(abase + (kl & 7) * IP + (kl >> 3));
-                        qp += kh != kl ? 2 : 1;
-                        mh &= ~((1u << kh) | (1u << kl));
+                            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
+                            uint32_t qp = q + 2 * (qn + inc - cnt);
+                            qn += __shfl_sync(0xFFFFFFFFu, inc, 31);
+                            // two survivors per trip, the lowest and the highest flag: an odd count is evened first
+                            if (cnt & 1) {
+                                const int kl = __ffs(mh) - 1;
+                                sts16(qp, (uint32_t)(ab + (kl & 7) * IP + (kl >> 3)));
+                                qp += 2;
+                                mh &= mh - 1;
+                            }
+                            while (mh) {
+                                int kh;
+                                asm("bfind.u32 %0, %1;" : "=r"(kh) : "r"(mh));
+                                const int kl = __ffs(mh) - 1;
+                                sts16(qp, (uint32_t)(ab + (kl & 7) * IP + (kl >> 3)));
+                                sts16(qp + 2, (uint32_t)(ab + (kh & 7) * IP + (kh >> 3)));
+                                qp += 4;
+                                mh = (mh & (mh - 1)) ^ (1u << kh);
+                            }
+                            __syncwarp();
+                        }
+                        while (qn >= need) {
+                            const int n = min(qn, 64);
+                            qn -= n;
+                            const bool ok0 = lane < n, ok1 = lane + 32 < n;
+                            const int a0 = (int)lds16(q + 2 * (qn + (ok0 ? lane : 0))), a1 = (int)lds16(q + 2 * (qn + (ok1 ? lane + 32 : 0)));
+                            fast_score_pair<IP>(img, scb, a0, a1, ok0, ok1, t, cl, ncl, lt_mask);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    while (qn >= 64) {
-                        qn -= 64;
-                        fast_score_pair<IP>(img, scb, q[qn + lane], q[qn + 32 + lane], true, true, t, cl, ncl, lt_mask);
-                    }
-                    __syncwarp();
                 }
+                if (drain) break;
             }
-            if (qn > 0) {                               // the last, partial round
-                const bool ok0 = lane < qn, ok1 = lane + 32 < qn;
-                fast_score_pair<IP>(img, scb, q[ok0 ? lane : 0], q[ok1 ? lane + 32 : 0], ok0, ok1, t, cl, ncl, lt_mask);
-            }
-            __syncwarp();
             // ---- 3: strict 3x3 maximum inside the cell, over the corner list (or a sweep of the cell's score map if it overflowed)
             bool kept = false;
             if (ncl <= kFastCorners) {
+#pragma unroll 1
                 for (int i = lane; i < ncl; i += 32) {
-                    const int a = cl[i];
+                    const int a = (int)lds16(cl + 2 * i);
                     const int ri = a / IP;
-                    kept |= fast_nms_one<IP>(sc1, bm, ri - 3, a - ri * IP, cx0, wc);
+                    kept |= fast_nms_one<IP>(sc1, kb, ri - 3, a - ri * IP, cx0, wc, wdt);
                 }
             } else {
                 const int items = Y * nw;
+#pragma unroll 1
                 for (int it = lane; it < items; it += 32) {
                     const int row = small_div(it, inv_nw), wi = w0 + (it - row * nw);
-                    const uint32_t wv = *(reinterpret_cast<const uint32_t *>(sc1 + row * IP) + wi);
+                    const uint32_t wv = lds32(sc1 + row * IP + 4 * wi);
                     if (wv == 0) continue;
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++)
                         if (((wv >> (8 * kk)) & 0xFF) && 4 * wi + kk >= cx0 && 4 * wi + kk < cx1)
-                            kept |= fast_nms_one<IP>(sc1, bm, row, 4 * wi + kk, cx0, wc);
+                            kept |= fast_nms_one<IP>(sc1, kb, row, 4 * wi + kk, cx0, wc, wdt);
                 }
             }
             any_kept = __any_sync(0xFFFFFFFFu, kept);
             __syncwarp();
-            if (stats) st_corn += ncl;
+            if (stats && lane == 0) reds_add64(smem_u32(&s_stats[1]), (unsigned long long)ncl);
             // ---- 4: a cell that found nothing is repeated with minThFAST (src/ORBextractor.cc:760-782)
             if (any_kept || t_min >= t_ini) break;
-            if (pass == 0 && stats) st_retry++;
+            if (pass == 0 && stats && lane == 0) reds_add64(smem_u32(&s_stats[3]), 1ull);
         }
-        // ---- 5: emission in cv::FAST order (row-major inside the cell) from the keep bitmap: lane = row (two rows per lane)
-        const long long cand0 = ((long long)(unsigned)t3.z) | ((long long)t3.w << 32);
-        uint32_t *out = cells + (long long)b * A.cand_per_image + cand0 + (long long)k * cell_cap;
+        // ---- 5: emission in cv::FAST order (row-major inside the cell) = ascending bit index of the cell's keep bitmap: a lane takes
+        //      64 bits, one warp scan per 2048 bits (a 37 x 37 cell has 1369)
         int total = 0;
         if (any_kept) {
-            const int wdt = cx1 - cx0;
-            if (Y <= kFastMaxY && wdt <= 64) {
-                uint32_t vlo[2], vhi[2];
-                int n[2];
-                const int wa = cx0 >> 5, sh = cx0 & 31;
-                const uint32_t mlo = wdt >= 32 ? 0xFFFFFFFFu : (1u << wdt) - 1u, mhi = wdt >= 64 ? 0xFFFFFFFFu : wdt > 32 ? (1u << (wdt - 32)) - 1u : 0u;
+            const long long cand0 = ((long long)(unsigned)t3.z) | ((long long)t3.w << 32);
+            uint32_t *out = cells + (long long)b * A.cand_per_image + cand0 + (long long)k * cell_cap;
+            // row of bit x = x / wdt as a multiply-high (exact for x * wdt < 2^32; x < 2^16 here)
+            const uint32_t magic = 0xFFFFFFFFu / (uint32_t)wdt + 1u;
+            // border-relative coordinates (src/ORBextractor.cc:784-791): level coordinate - 16
+            const uint32_t base = (uint32_t)(tx0 + k * wc - kFastBorder) | ((uint32_t)(ty0 - kFastBorder) << 12);
+            const uint32_t scc = sc1 + cx0;
+#pragma unroll 1
+            for (int w2 = 2 * lane; w2 - 2 * lane < nkb; w2 += 64) {     // (warp-uniform trip count; one trip for cells up to 2048 pixels)
+                uint32_t v0 = w2 < nkb ? lds32(kb + 4 * w2) : 0u, v1 = w2 + 1 < nkb ? lds32(kb + 4 * w2 + 4) : 0u;
+                const int n = __popc(v0) + __popc(v1);
+                int inc = n;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int row = lane + 32 * h;
-                    vlo[h] = vhi[h] = 0;
-                    if (row < Y) {
-                        const uint32_t *br = bm + row * bw;
-                        const uint32_t a = br[wa], b2 = wa + 1 < bw ? br[wa + 1] : 0u, c2 = wa + 2 < bw ? br[wa + 2] : 0u;
-                        vlo[h] = __funnelshift_r(a, b2, sh) & mlo; vhi[h] = __funnelshift_r(b2, c2, sh) & mhi;
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
+                const int nchunk = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                // the lanes list the set bits of their 64 in order (a short serial loop; the corner list is free again), then the list is
+                // emitted one keypoint per lane; what does not fit the list (> kFastCorners kept pixels in 2048) is written directly
+                int li = inc - n;
+#pragma unroll 1
+                while (v0 | v1) {
+                    const bool lo = v0 != 0;
+                    const uint32_t vv = lo ? v0 : v1;
+                    const int bit = 32 * w2 + (lo ? 0 : 32) + __ffs(vv) - 1;
+                    if (lo) v0 &= v0 - 1; else v1 &= v1 - 1;
+                    if (li < kFastCorners) sts16(cl + 2 * li, (uint32_t)bit);
+                    else if (total + li < cell_cap) {
+                        const int row = __umulhi((uint32_t)bit, magic), xc = bit - row * wdt;
+                        out[total + li] = (base + (uint32_t)xc + ((uint32_t)row << 12)) | (lds8(scc + row * IP + xc) << 24);
                     }
-                    n[h] = __popc(vlo[h]) + __popc(vhi[h]);
+                    li++;
                 }
-                int i0 = n[0], i1 = n[1];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u0 = __shfl_up_sync(0xFFFFFFFFu, i0, o), u1 = __shfl_up_sync(0xFFFFFFFFu, i1, o);
-                    if (lane >= o) { i0 += u0; i1 += u1; }
+                __syncwarp();
+                const int nlist = min(min(nchunk, kFastCorners), cell_cap - total);
+#pragma unroll 1
+                for (int j = lane; j < nlist; j += 32) {
+                    const int bit = (int)lds16(cl + 2 * j);
+                    const int row = __umulhi((uint32_t)bit, magic), xc = bit - row * wdt;
+                    out[total + j] = (base + (uint32_t)xc + ((uint32_t)row << 12)) | (lds8(scc + row * IP + xc) << 24);
                 }
-                const int tot0 = __shfl_sync(0xFFFFFFFFu, i0, 31);
-                total = tot0 + __shfl_sync(0xFFFFFFFFu, i1, 31);
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    if (!(vlo[h] | vhi[h])) continue;
-                    const int row = lane + 32 * h;
-                    uint32_t *op = out + (h ? tot0 + i1 - n[1] : i0 - n[0]);
-                    uint32_t *const oend = out + cell_cap;
-                    const uint8_t *srow = sc1 + row * IP + cx0;
-                    // border-relative coordinates (src/ORBextractor.cc:784-791): level coordinate - 16
-                    const uint32_t base = (uint32_t)(tx0 + k * wc - kFastBorder) | ((uint32_t)(ty0 + row - kFastBorder) << 12);
-#pragma unroll
-                    for (int part = 0; part < 2; part++) {
-                        uint32_t vv = part ? vhi[h] : vlo[h];
-                        while (vv) {
-                            const int i = __ffs(vv) - 1 + 32 * part;
-                            vv &= vv - 1;
-                            if (op < oend) *op = (base + (uint32_t)i) | ((uint32_t)srow[i] << 24);
-                            op++;
-                        }
-                    }
-                }
-            } else {
-                // general geometry (very tall or wide cells): one lane per row, bit by bit
-                for (int r0 = 0; r0 < Y; r0 += 32) {
-                    const int row = r0 + lane;
-                    int n = 0;
-                    if (row < Y) for (int c = cx0; c < cx1; c++) n += (bm[row * bw + (c >> 5)] >> (c & 31)) & 1u;
-                    int inc = n;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
-                    int pos = total + inc - n;
-                    total += __shfl_sync(0xFFFFFFFFu, inc, 31);
-                    if (n) {
-                        const uint8_t *srow = sc1 + row * IP;
-                        const uint32_t ybits = (uint32_t)(ty0 + row - kFastBorder) << 12;
-                        for (int c = cx0; c < cx1; c++)
-                            if ((bm[row * bw + (c >> 5)] >> (c & 31)) & 1u) {
-                                if (pos < cell_cap) out[pos] = (uint32_t)(tx0 + (c - c0) - kFastBorder) | ybits | ((uint32_t)srow[c] << 24);
-                                pos++;
-                            }
-                    }
-                }
+                __syncwarp();
+                total += nchunk;
             }
         }
         if (lane == 0) *cnt_out = min(total, cell_cap);
-        st_kept += total;
+        if (stats && lane == 0) reds_add64(smem_u32(&s_stats[2]), (unsigned long long)total);
     }
     if (stats) {
-        st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 16); st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 8);
-        st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 4); st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 2);
-        st_surv += __shfl_xor_sync(0xFFFFFFFFu, st_surv, 1);
-        if (lane == 0) {
-            atomicAdd(&stats->survivors, st_surv); atomicAdd(&stats->corners, st_corn); atomicAdd(&stats->kept, st_kept);
-            atomicAdd(&stats->retry_cells, st_retry);
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(&stats->survivors, s_stats[0]); atomicAdd(&stats->corners, s_stats[1]); atomicAdd(&stats->kept, s_stats[2]);
+            atomicAdd(&stats->retry_cells, s_stats[3]);
+            atomicAdd(&stats->tested, (unsigned long long)X * Y); atomicAdd(&stats->tiles, 1ull);
         }
-        if (tid == 0) { atomicAdd(&stats->tested, (unsigned long long)X * Y); atomicAdd(&stats->tiles, 1ull); }
     }
 }
 
