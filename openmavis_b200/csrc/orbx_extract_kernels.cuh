@@ -475,6 +475,8 @@ __device__ __forceinline__ void reds_add64(uint32_t a, unsigned long long v) { a
 // ring positions: (0, +-3), (+-3, 0), (2, 2)/(-2, -2), (2, -2)/(-2, 2).  Byte-SIMD: 4 pixels per VABSDIFF4, the compare is the carry into
 // bit 7 of d + (127 - t) (or d >= 128); flags of strip rows 0-6 go to mA, rows 7-13 to mB (byte = pixel, bit = row).
 // (On the bench images: 12.5 % of the pixels survive, 4.2 % are corners; the former test on the pairs (0, 8) and (4, 12) alone left 23.5 %.)
+// (Moving the byte funnel shifts and the flag gather to the FMA pipe — mul.hi + mad instead of PRMT, mad.hi instead of SHF + LOP3 — was
+//  measured slower, 0.73 vs 0.705 ms: the ALU pipe drops from 65 % to 56 % but the kernel is bound by issue slots, not by that pipe.)
 template <int IP, bool FULL>
 __device__ __forceinline__ void fast_quick8(uint32_t col, int rs, uint32_t cadd, uint32_t &mA, uint32_t &mB) {
     uint32_t cu[kFastStrip + 6], dm[kFastStrip + 6], dp[kFastStrip + 6], hl[kFastStrip + 6], hr[kFastStrip + 6];
@@ -691,40 +693,37 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
                     mB &= cm & (0x01010101u * (rows >> kFastHalf));
                 }
                 if (stats) { const int c = __reduce_add_sync(0xFFFFFFFFu, __popc(mA) + __popc(mB)); if (lane == 0) reds_add64(smem_u32(&s_stats[0]), (unsigned long long)c); }
-                // append the survivors to the warp's queue, one flag register at a time so that the queue stays small; entries are img byte
-                // offsets, the order inside the queue is irrelevant
-#pragma unroll 1
-                for (int half = 0; half < 2; half++) {
-                    const uint32_t mhalf = half ? mB : mA;
-                    const int nsurv = __reduce_add_sync(0xFFFFFFFFu, __popc(mhalf));
-                    const int nsub = nsurv == 0 ? 0 : nsurv <= kFastQueue - 64 ? 1 : 4;   // (4: row pairs, at most 256 survivors each)
-                    const int ab = abase + half * (kFastHalf * IP);
+                // append the survivors of both flag registers to the warp's queue (entries are img byte offsets, the order inside the queue
+                // is irrelevant): one warp scan, then every lane lists its flags, one of each register per trip.  More survivors than the
+                // queue holds (rare: > 448 of 1792 pixels) are appended row by row.
+                {
+                    const int nsurv = __reduce_add_sync(0xFFFFFFFFu, __popc(mA) + __popc(mB));
+                    const int nsub = nsurv == 0 ? 0 : nsurv <= kFastQueue - 64 ? 1 : kFastHalf;
                     const int need = drain ? 1 : 64;
 #pragma unroll 1
                     for (int sub = 0; sub < max(nsub, 1); sub++) {
                         if (nsub) {
-                            uint32_t mh = nsub == 1 ? mhalf : mhalf & (0x03030303u << (2 * sub));
-                            const int cnt = __popc(mh);
+                            uint32_t fa = nsub == 1 ? mA : mA & (0x01010101u << sub), fb = nsub == 1 ? mB : mB & (0x01010101u << sub);
+                            const int ca = __popc(fa), cnt = ca + __popc(fb);
                             int inc = cnt;
 #pragma unroll
                             for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
-                            uint32_t qp = q + 2 * (qn + inc - cnt);
+                            uint32_t qa = q + 2 * (qn + inc - cnt), qb = qa + 2 * ca;
                             qn += __shfl_sync(0xFFFFFFFFu, inc, 31);
-                            // two survivors per trip, the lowest and the highest flag: an odd count is evened first
-                            if (cnt & 1) {
-                                const int kl = __ffs(mh) - 1;
-                                sts16(qp, (uint32_t)(ab + (kl & 7) * IP + (kl >> 3)));
-                                qp += 2;
-                                mh &= mh - 1;
-                            }
-                            while (mh) {
-                                int kh;
-                                asm("bfind.u32 %0, %1;" : "=r"(kh) : "r"(mh));
-                                const int kl = __ffs(mh) - 1;
-                                sts16(qp, (uint32_t)(ab + (kl & 7) * IP + (kl >> 3)));
-                                sts16(qp + 2, (uint32_t)(ab + (kh & 7) * IP + (kh >> 3)));
-                                qp += 4;
-                                mh = (mh & (mh - 1)) ^ (1u << kh);
+                            const int ab2 = abase + kFastHalf * IP;
+                            while (fa | fb) {
+                                if (fa) {
+                                    const int kl = __ffs(fa) - 1;
+                                    sts16(qa, (uint32_t)(abase + (kl & 7) * IP + (kl >> 3)));
+                                    qa += 2;
+                                    fa &= fa - 1;
+                                }
+                                if (fb) {
+                                    const int kl = __ffs(fb) - 1;
+                                    sts16(qb, (uint32_t)(ab2 + (kl & 7) * IP + (kl >> 3)));
+                                    qb += 2;
+                                    fb &= fb - 1;
+                                }
                             }
                             __syncwarp();
                         }
