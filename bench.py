@@ -720,14 +720,16 @@ def main():
                 d_t = shard.gather_train_rows(d_local_train, n, dist)
                 m.knnMatch2_device(d_q.data_ptr(), hi - lo, d_t.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
             elif world > 1:
-                # The one real exchange step, fused with the compute: every rank publishes its train rows in a peer-mapped
-                # buffer and each rank's 2-NN kernels read all parts in place over NVLink (no all-gather, no staging copy);
-                # one tiny all-reduce per step is the stream-ordered barrier (see openmavis_b200.SharedRows).
-                buf = step_no[0] & 1
+                # The one real exchange step, fused with the compute: every rank publishes its train rows in a peer-mapped buffer and
+                # an epoch flag; the pull kernel of each rank waits for the peers' flags on the device and fetches their rows over
+                # NVLink on an auxiliary stream while the main stream already matches the own rows (see openmavis_b200.SharedRows):
+                # no collective call, no host synchronisation.
                 step_no[0] += 1
+                buf = step_no[0] & 1
                 shared.fill(buf, d_local_train.data_ptr(), stream.cuda_stream)
-                dist.all_reduce(token)
-                m.knnMatch2_device_parts(d_q.data_ptr(), hi - lo, shared.ptrs[buf], shared.rows, d_idx.data_ptr(), d_dist.data_ptr())
+                shared.publish(step_no[0], stream.cuda_stream)
+                m.knnMatch2_device_parts_sync(d_q.data_ptr(), hi - lo, shared.ptrs[buf], shared.rows, rank, shared.flags, step_no[0],
+                                              d_idx.data_ptr(), d_dist.data_ptr(), timeout_s=20.0)
             else:
                 m.knnMatch2_device(d_q.data_ptr(), hi - lo, d_local_train.data_ptr(), n, d_idx.data_ptr(), d_dist.data_ptr())
         for _ in range(2):
@@ -748,7 +750,7 @@ def main():
                     'executed_popc_per_pair': 6, 'executed_popc_frac_of_peak': 6 * pairs / (ms_knn * 1e-3) / 1e9 / world / popc,
                     'note': 'algorithmic work = 8 popc.b32 per pair (SURVEY.md 8d); the kernel executes 6 (two carry-save adders per pair), so the '
                             'XU-pipe utilisation is the executed figure', 'n_gpus': world,
-                    'collective': None if world == 1 else ('none for the data: peer-mapped train rows pulled over NVLink (cudaIpc); one 4-byte all-reduce per step as barrier' if shared is not None else 'nccl all_gather of the train rows (peer mapping unavailable)')}
+                    'collective': None if world == 1 else ('none: peer-mapped train rows pulled over NVLink (cudaIpc) behind device-side epoch flags, overlapped with the 2-NN over the own rows' if shared is not None else 'nccl all_gather of the train rows (peer mapping unavailable)')}
         if rank == 0:
             torch.cuda.set_stream(torch.cuda.default_stream(dev))
             matching['guided'] = guided_matchers(ob, local)

@@ -185,8 +185,20 @@ int orbx_knn2_device(orbx_matcher *m, const uint8_t *d_query, int nq, const uint
  * matcher's stream; the caller orders it after the peers have written their rows (a barrier). */
 int orbx_knn2_device_parts(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *const *d_train_parts,
                            const int *part_rows, int nparts, int *d_idx, int *d_dist);
+/* The same with the barrier and the overlap built in.  d_flags[p] = device pointer (peer-mapped for p != self) to part p's 32-bit
+ * epoch word: the owner of part p calls orbx_shared_publish(flag, k) on its stream after its rows of step k are in place, and this
+ * call (with epoch = k) waits for the peers' flags ON THE DEVICE, inside the kernel that pulls their rows over NVLink on an auxiliary
+ * stream, while the main stream already matches the own part (index `self`, or -1) in place: no collective, no host synchronisation.
+ * With two shared buffers per rank (step k uses buffer k & 1) no further barrier is needed: a rank can only see epoch k of a peer
+ * after that peer has finished pulling step k - 1.  A peer that never publishes makes the pull kernel trap after timeout_s (<= 0: 10 s)
+ * — the next CUDA call reports the error; nothing spins forever. */
+int orbx_knn2_device_parts_sync(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *const *d_train_parts,
+                                const int *part_rows, int nparts, int self, const uint32_t *const *d_flags, uint32_t epoch,
+                                double timeout_s, int *d_idx, int *d_dist);
+/* Stores `epoch` into a flag word with release semantics at system scope, ordered after everything queued on cuda_stream. */
+int orbx_shared_publish(int device, void *d_flag, uint32_t epoch, void *cuda_stream);
 /* Device buffers that other processes on the same node can map (cudaIpc): alloc in the owner (handle = 64 opaque bytes to
- * send to the peers), open / close in a peer, free in the owner. */
+ * send to the peers), open / close in a peer, free in the owner.  A new buffer is zero-filled. */
 int orbx_shared_alloc(int device, size_t bytes, void **d_ptr, void *ipc_handle64);
 int orbx_shared_open(int device, const void *ipc_handle64, void **d_ptr);
 int orbx_shared_close(int device, void *d_ptr);

@@ -378,6 +378,19 @@ class ORBmatcher:
         rows = np.ascontiguousarray(part_rows, np.int32)
         _check(self.L.orbx_knn2_device_parts(self.h, C.c_void_p(d_query), int(nq), ptrs, _p(rows), n, C.c_void_p(d_idx), C.c_void_p(d_dist)))
 
+    def knnMatch2_device_parts_sync(self, d_query, nq, part_ptrs, part_rows, self_index, flag_ptrs, epoch, d_idx, d_dist, timeout_s=10.0):
+        """Sharded 2-NN with the barrier on the device: waits (inside the pull kernel, on an auxiliary stream) until every peer has
+        published `epoch` in its flag word, pulls the peers' rows over NVLink while the main stream matches the own part
+        (`self_index`) in place, then matches the pulled parts and merges.  No collective, no host synchronisation."""
+        n = len(part_ptrs)
+        ptrs = (C.c_void_p * n)(*[int(x) for x in part_ptrs])
+        flags = (C.c_void_p * n)(*[int(x) for x in flag_ptrs])
+        rows = np.ascontiguousarray(part_rows, np.int32)
+        self.L.orbx_knn2_device_parts_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                       C.c_uint32, C.c_double, C.c_void_p, C.c_void_p]
+        _check(self.L.orbx_knn2_device_parts_sync(self.h, C.c_void_p(d_query), int(nq), ptrs, _p(rows), n, int(self_index), flags,
+                                                  int(epoch) & 0xFFFFFFFF, float(timeout_s), C.c_void_p(d_idx), C.c_void_p(d_dist)))
+
     @staticmethod
     def ratio_test(dist, ratio):
         dist = np.ascontiguousarray(dist, np.int32)
@@ -844,18 +857,19 @@ class SharedRows:
         self.L.orbx_shared_close.argtypes = [C.c_int, C.c_void_p]
         self.L.orbx_shared_free.argtypes = [C.c_int, C.c_void_p]
         self.L.orbx_device_copy.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
-        self.own, self.ptrs = [], []
+        self.L.orbx_shared_publish.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
+        self.own, self.ptrs, self.flags = [], [], []
         # collectives first (allocation + handle exchange), then the purely local peer mappings: a rank whose mapping fails has
         # no collective left to skip, so the caller can agree on a fallback with one more all-reduce
         handles = []
-        for _ in range(2):
+        for i in range(3):                       # two row buffers and the epoch word (a zero-filled 256-byte buffer)
             own, handle = C.c_void_p(), C.create_string_buffer(64)
-            _check(self.L.orbx_shared_alloc(self.device, max(self.rows[self.rank], 1) * 32, C.byref(own), handle))
+            _check(self.L.orbx_shared_alloc(self.device, max(self.rows[self.rank], 1) * 32 if i < 2 else 256, C.byref(own), handle))
             self.own.append(own.value)
             got = [None] * self.world
             dist.all_gather_object(got, handle.raw)
             handles.append(got)
-        for buf in range(2):
+        for buf in range(3):
             ptrs = []
             for r in range(self.world):
                 if r == self.rank:
@@ -865,19 +879,24 @@ class SharedRows:
                     _check(self.L.orbx_shared_open(self.device, handles[buf][r], C.byref(q)))
                     ptrs.append(q.value)
             self.ptrs.append(ptrs)
+        self.flags = self.ptrs.pop()             # flags[r] = rank r's epoch word
 
     def fill(self, buf, d_local_rows_ptr, cuda_stream):
         """Copies this rank's rows (device pointer) into its shared buffer `buf` on `cuda_stream`."""
         _check(self.L.orbx_device_copy(self.device, C.c_void_p(self.own[buf]), C.c_void_p(d_local_rows_ptr), self.rows[self.rank] * 32,
                                        C.c_void_p(cuda_stream)))
 
+    def publish(self, epoch, cuda_stream):
+        """Stores `epoch` in this rank's flag word, ordered after everything queued on `cuda_stream` (the fill)."""
+        _check(self.L.orbx_shared_publish(self.device, C.c_void_p(self.own[2]), int(epoch) & 0xFFFFFFFF, C.c_void_p(cuda_stream)))
+
     def close(self, barrier=True):
-        for buf in range(len(self.ptrs)):
-            for r, q in enumerate(self.ptrs[buf]):
+        for lst in self.ptrs + ([self.flags] if self.flags else []):
+            for r, q in enumerate(lst):
                 if r != self.rank and q:
                     self.L.orbx_shared_close(self.device, C.c_void_p(q))
         if barrier:
             self.dist.barrier()                  # nobody maps the buffers any more
         for own in self.own:
             self.L.orbx_shared_free(self.device, C.c_void_p(own))
-        self.ptrs, self.own = [], []
+        self.ptrs, self.own, self.flags = [], [], []

@@ -51,8 +51,8 @@ struct orbx_vocabulary {
 struct orbx_matcher {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;   // aux: the peer pull of the sharded 2-NN
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     int last_launches = 0;
     bool timed = false;
     DBuf b[24];
@@ -68,8 +68,10 @@ static int upload(orbx_matcher *m, DBuf &buf, const void *src, size_t bytes) {
 
 // Train set = concatenation of `nparts` parts (one for the single-GPU call; one per rank, read through peer-mapped pointers over
 // NVLink, for the sharded matcher).  One k_knn2 launch per part, all writing slices of the same partial buffer, one merge.
+// `first` (or -1): the part whose kernels are launched first; `wait_after_first` (or nullptr): event the stream waits for before the
+// kernels of the other parts (the peer rows arrive on another stream while the own part is being matched).
 static int knn2_launch_parts(orbx_matcher *m, const uint8_t *d_q, int nq, const uint8_t *const *d_parts, const int *part_rows, int nparts,
-                             int *d_idx, int *d_dist) {
+                             int *d_idx, int *d_dist, int first = -1, cudaEvent_t wait_after_first = nullptr) {
     long long nt = 0;
     for (int p = 0; p < nparts; p++) nt += part_rows[p];
     if (nt >= (1 << kKeyShift)) return fail(ORBX_ERR_INVALID, "knn2: more than 8388607 train rows are not supported");
@@ -88,15 +90,18 @@ static int knn2_launch_parts(orbx_matcher *m, const uint8_t *d_q, int nq, const 
         total_slices += slices[p];
     }
     M_CUDA(m->b[0].ensure((size_t)std::max(total_slices, 1) * nq * sizeof(uint2)));
-    int slice_base = 0, row_off = 0;
-    for (int p = 0; p < nparts; p++) {
-        if (slices[p] > 0) {
-            k_knn2<<<dim3(qblocks, slices[p]), kKnnThreads, 0, m->stream>>>((const uint4 *)d_q, nq, (const uint4 *)d_parts[p], part_rows[p],
-                                                                            slice_rows[p], m->b[0].as<uint2>() + (size_t)slice_base * nq, row_off);
-            m->last_launches++;
-        }
-        slice_base += slices[p]; row_off += part_rows[p];
-    }
+    std::vector<int> slice_base(nparts), row_off(nparts);
+    for (int p = 0, sb = 0, ro = 0; p < nparts; p++) { slice_base[p] = sb; row_off[p] = ro; sb += slices[p]; ro += part_rows[p]; }
+    auto launch = [&](int p) {
+        if (slices[p] <= 0) return;
+        k_knn2<<<dim3(qblocks, slices[p]), kKnnThreads, 0, m->stream>>>((const uint4 *)d_q, nq, (const uint4 *)d_parts[p], part_rows[p],
+                                                                        slice_rows[p], m->b[0].as<uint2>() + (size_t)slice_base[p] * nq, row_off[p]);
+        m->last_launches++;
+    };
+    if (first >= 0) launch(first);
+    if (wait_after_first) M_CUDA(cudaStreamWaitEvent(m->stream, wait_after_first, 0));
+    for (int p = 0; p < nparts; p++)
+        if (p != first) launch(p);
     k_knn2_merge<<<(nq + 255) / 256, 256, 0, m->stream>>>(m->b[0].as<uint2>(), nq, total_slices, d_idx, d_dist);
     m->last_launches++;
     M_CUDA(cudaGetLastError());
@@ -109,6 +114,7 @@ static int knn2_launch(orbx_matcher *m, const uint8_t *d_q, int nq, const uint8_
 
 extern "C" {
 
+void orbx_matcher_destroy(orbx_matcher *m);
 int orbx_matcher_create(orbx_matcher **out, int device) {
     if (!out) return fail(ORBX_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -120,11 +126,20 @@ int orbx_matcher_create(orbx_matcher **out, int device) {
     m->device = device;
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess) {
-        delete m;
+        orbx_matcher_destroy(m);
         return fail(ORBX_ERR_CUDA, "stream/event creation failed");
     }
     m->stream = m->own_stream;
+    {   // load the kernels of the sharded 2-NN now: with lazy module loading the FIRST launch of a kernel may have to wait for running
+        // kernels, and the pull kernel of that path spins on a flag that another kernel publishes
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_publish_epoch); cudaFuncGetAttributes(&fa, k_pull_parts_wait); cudaFuncGetAttributes(&fa, k_pull_parts);
+        cudaFuncGetAttributes(&fa, k_knn2); cudaFuncGetAttributes(&fa, k_knn2_merge);
+    }
     *out = m;
     return ORBX_OK;
 }
@@ -135,6 +150,9 @@ void orbx_matcher_destroy(orbx_matcher *m) {
     for (auto &b : m->b) b.release();
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     delete m;
 }
@@ -226,6 +244,58 @@ int orbx_knn2_device_parts(orbx_matcher *m, const uint8_t *d_query, int nq, cons
     return ORBX_OK;
 }
 
+int orbx_knn2_device_parts_sync(orbx_matcher *m, const uint8_t *d_query, int nq, const uint8_t *const *d_train_parts, const int *part_rows,
+                                int nparts, int self, const uint32_t *const *d_flags, uint32_t epoch, double timeout_s, int *d_idx, int *d_dist) {
+    if (!m || nq < 0 || nparts < 1 || nparts > 64 || !d_train_parts || !part_rows || !d_idx || !d_dist || !d_flags || self < -1 || self >= nparts)
+        return fail(ORBX_ERR_INVALID, "bad arguments");
+    long long nt = 0;
+    for (int p = 0; p < nparts; p++) {
+        if (part_rows[p] < 0 || (part_rows[p] && (!d_train_parts[p] || (p != self && !d_flags[p])))) return fail(ORBX_ERR_INVALID, "bad part");
+        nt += part_rows[p];
+    }
+    M_CUDA(cudaSetDevice(m->device));
+    m->last_launches = 0;
+    if (nq == 0) return ORBX_OK;
+    M_CUDA(cudaEventRecord(m->ev0, m->stream));
+    if (nt == 0) {
+        M_CUDA(cudaMemsetAsync(d_idx, 0xFF, (size_t)nq * 2 * sizeof(int), m->stream));
+        M_CUDA(cudaMemsetAsync(d_dist, 0xFF, (size_t)nq * 2 * sizeof(int), m->stream));
+    } else {
+        // aux stream: wait for the peers' epoch flags and pull their rows into a local buffer laid out like the whole train set;
+        // main stream: match the own part in place meanwhile, then the pulled parts, then one merge
+        KnnParts P;
+        KnnFlags F;
+        P.nparts = nparts; P.first_vec[0] = 0;
+        std::vector<const uint8_t *> local(nparts);
+        M_CUDA(m->b[2].ensure((size_t)nt * 32));
+        for (int p = 0; p < nparts; p++) {
+            P.ptr[p] = (const uint4 *)d_train_parts[p]; P.first_vec[p + 1] = P.first_vec[p] + 2 * part_rows[p];
+            F.flag[p] = d_flags[p];
+            local[p] = p == self ? d_train_parts[p] : m->b[2].as<uint8_t>() + (size_t)P.first_vec[p] * 16;
+        }
+        F.epoch = epoch; F.self = self;
+        F.timeout_ns = (unsigned long long)(std::max(0.001, timeout_s > 0 ? timeout_s : 10.0) * 1e9);
+        M_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+        M_CUDA(cudaStreamWaitEvent(m->aux_stream, m->ev_fork, 0));
+        k_pull_parts_wait<<<std::min(m->sm_count, (P.first_vec[nparts] + 255) / 256), 256, 0, m->aux_stream>>>(P, F, m->b[2].as<uint4>());
+        m->last_launches++;
+        M_CUDA(cudaEventRecord(m->ev_join, m->aux_stream));
+        int st = knn2_launch_parts(m, d_query, nq, local.data(), part_rows, nparts, d_idx, d_dist, self, m->ev_join);
+        if (st != ORBX_OK) return st;
+    }
+    M_CUDA(cudaEventRecord(m->ev1, m->stream));
+    m->timed = true;
+    return ORBX_OK;
+}
+
+int orbx_shared_publish(int device, void *d_flag, uint32_t epoch, void *cuda_stream) {
+    if (!d_flag) return fail(ORBX_ERR_INVALID, "flag is NULL");
+    M_CUDA(cudaSetDevice(device));
+    k_publish_epoch<<<1, 1, 0, (cudaStream_t)cuda_stream>>>((uint32_t *)d_flag, epoch);
+    M_CUDA(cudaGetLastError());
+    return ORBX_OK;
+}
+
 // ---- device buffers that peer processes (one per GPU) can map: the train rows of the sharded brute-force matcher are read
 // in place over NVLink instead of being all-gathered first
 int orbx_shared_alloc(int device, size_t bytes, void **d_ptr, void *ipc_handle64) {
@@ -233,6 +303,8 @@ int orbx_shared_alloc(int device, size_t bytes, void **d_ptr, void *ipc_handle64
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
     M_CUDA(cudaSetDevice(device));
     M_CUDA(cudaMalloc(d_ptr, bytes));
+    M_CUDA(cudaMemset(*d_ptr, 0, bytes));              // (epoch flags start at 0)
+    { cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_publish_epoch); }   // (loaded before anybody can wait for it)
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
     if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return fail(ORBX_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }

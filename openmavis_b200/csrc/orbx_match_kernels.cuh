@@ -80,6 +80,47 @@ __global__ void __launch_bounds__(256) k_pull_parts(KnnParts P, uint4 *__restric
     }
 }
 
+// Epoch flags of the sharded matcher (one 32-bit word per rank, in peer-mapped device memory): a rank publishes epoch k after its
+// rows of step k are in its shared buffer; the peers' pull kernels wait for it.  Release / acquire at system scope: the flag and
+// the rows cross NVLink.
+__global__ void k_publish_epoch(uint32_t *flag, uint32_t epoch) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
+struct KnnFlags { const uint32_t *flag[64]; uint32_t epoch; int self; unsigned long long timeout_ns; };
+
+// Pull with the barrier built in: thread 0 of every CTA waits until every peer part's flag has reached `epoch` (the own part needs
+// no wait and is not copied: self = its index, or -1), then the CTA copies its share of the peer rows with L1-bypassing 128-bit loads.
+// dst is laid out like the concatenation of ALL parts, so indices stay global.  A peer that never publishes makes the kernel trap after
+// timeout_ns instead of spinning forever.
+__global__ void __launch_bounds__(256) k_pull_parts_wait(KnnParts P, KnnFlags F, uint4 *__restrict__ dst) {
+    if (threadIdx.x == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (int p = 0; p < P.nparts; p++) {
+            if (p == F.self || P.first_vec[p + 1] == P.first_vec[p]) continue;
+            for (;;) {
+                uint32_t v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(F.flag[p]) : "memory");
+                if ((int)(v - F.epoch) >= 0) break;
+                __nanosleep(200);
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > F.timeout_ns) __trap();
+            }
+        }
+    }
+    __syncthreads();
+    const int total = P.first_vec[P.nparts];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int p = 0;
+        while (i >= P.first_vec[p + 1]) p++;
+        if (p == F.self) continue;
+        dst[i] = __ldcv(P.ptr[p] + (i - P.first_vec[p]));
+    }
+}
+
 __global__ void k_knn2_merge(const uint2 *__restrict__ partial, int nq, int nslices, int *__restrict__ idx, int *__restrict__ dist) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;

@@ -2,6 +2,10 @@
 Reference: src/ORBmatcher.cc (DescriptorDistance :2577, SearchByProjection :23-340, SearchForTriangulation :1131-1456),
 cv::BFMatcher::knnMatch at src/Frame.cc:1427,1483, Frame grid src/Frame.cc:541-582, 890-967."""
 import ctypes as C
+import os
+import subprocess
+import sys
+import time
 
 import numpy as np
 import pytest
@@ -641,7 +645,41 @@ def test_knn2_parts_equals_single_call(M):
     assert np.array_equal(idx.cpu().numpy(), ridx) and np.array_equal(dd.cpu().numpy(), rdist)
 
 
-def _peer_worker(rank, world, port, n, out):
+def test_knn2_parts_sync_waits_for_the_flags(M):
+    """orbx_knn2_device_parts_sync on one GPU: parts and epoch flags in local memory; the flags are published from ANOTHER stream only
+    after the call was queued, so the pull kernel really has to wait; result == one contiguous train set.  A flag that never arrives
+    must end in a CUDA error (trap after the timeout), not in a hang — checked last, in a subprocess, because it kills the context."""
+    import torch
+    t = synth_descriptors(4000, 31); q = synth_query_from_train(t, 32)[:900]
+    dq = torch.from_numpy(q).cuda()
+    cuts = ((0, 1500), (1500, 1500), (1500, 2600), (2600, 4000))
+    parts = [torch.from_numpy(t[a:b].copy()).cuda() for a, b in cuts]
+    flags = torch.zeros((len(cuts), 64), dtype=torch.int32, device='cuda')     # one word per part, 256 bytes apart
+    idx = torch.empty((900, 2), dtype=torch.int32, device='cuda'); dd = torch.empty((900, 2), dtype=torch.int32, device='cuda')
+    torch.cuda.synchronize()
+    L = ob.lib()
+    L.orbx_shared_publish.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
+    side = torch.cuda.Stream()
+    for epoch in (1, 2):
+        M.knnMatch2_device_parts_sync(dq.data_ptr(), 900, [p.data_ptr() if p.numel() else 0 for p in parts], [p.shape[0] for p in parts], 2,
+                                      [flags[i].data_ptr() for i in range(len(cuts))], epoch, idx.data_ptr(), dd.data_ptr(), timeout_s=30.0)
+        time.sleep(0.05)                                                       # the pull kernel is spinning by now
+        for i in (0, 3):
+            assert L.orbx_shared_publish(0, C.c_void_p(flags[i].data_ptr()), epoch, C.c_void_p(side.cuda_stream)) == 0
+        M.last_ms()
+        ridx, rdist = O.knn2(q, t)
+        assert np.array_equal(idx.cpu().numpy(), ridx) and np.array_equal(dd.cpu().numpy(), rdist)
+    code = ("import numpy as np, torch, openmavis_b200 as ob\n"
+            "m = ob.ORBmatcher(0.8)\n"
+            "t = torch.zeros((64, 32), dtype=torch.uint8, device='cuda'); f = torch.zeros(64, dtype=torch.int32, device='cuda')\n"
+            "o = torch.empty((64, 2), dtype=torch.int32, device='cuda'); d = torch.empty((64, 2), dtype=torch.int32, device='cuda')\n"
+            "m.knnMatch2_device_parts_sync(t.data_ptr(), 64, [t.data_ptr(), t.data_ptr()], [64, 64], 0, [f.data_ptr(), f.data_ptr()], 1, o.data_ptr(), d.data_ptr(), timeout_s=0.5)\n"
+            "try:\n    m.last_ms(); torch.cuda.synchronize(); print('NO ERROR')\nexcept Exception as e:\n    print('ERROR', type(e).__name__)\n")
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert 'ERROR' in r.stdout and 'NO ERROR' not in r.stdout, (r.stdout, r.stderr[-500:])
+
+
+def _peer_worker(rank, world, port, n, out, sync=False):
     """One process per 'GPU' (all on device 0 when the box has a single GPU): publishes its train rows in a peer-mapped buffer,
     reads everybody's rows in place, answers its own query shard."""
     import os
@@ -660,12 +698,18 @@ def _peer_worker(rank, world, port, n, out):
         d_local = torch.from_numpy(train[lo:lo + cnt].copy()).cuda()
         d_q = torch.from_numpy(query[lo:lo + cnt].copy()).cuda()
         d_idx = torch.empty((cnt, 2), dtype=torch.int32, device='cuda'); d_dist = torch.empty((cnt, 2), dtype=torch.int32, device='cuda')
-        for step in range(3):                                    # exercises both buffers of the double buffer
+        for step in range(1, 5):                                 # exercises both buffers of the double buffer
             shared.fill(step & 1, d_local.data_ptr(), 0)
-            torch.cuda.synchronize()
-            dist.barrier()                                       # (gloo here; bench.py uses a stream-ordered NCCL all-reduce)
-            m.knnMatch2_device_parts(d_q.data_ptr(), cnt, shared.ptrs[step & 1], shared.rows, d_idx.data_ptr(), d_dist.data_ptr())
-            m.last_ms()
+            if sync:                                             # device-side epoch flags: no barrier, no host synchronisation
+                shared.publish(step, 0)
+                m.knnMatch2_device_parts_sync(d_q.data_ptr(), cnt, shared.ptrs[step & 1], shared.rows, rank, shared.flags, step,
+                                              d_idx.data_ptr(), d_dist.data_ptr(), timeout_s=60.0)
+            else:
+                torch.cuda.synchronize()
+                dist.barrier()                                   # any barrier will do (gloo here)
+                m.knnMatch2_device_parts(d_q.data_ptr(), cnt, shared.ptrs[step & 1], shared.rows, d_idx.data_ptr(), d_dist.data_ptr())
+                m.last_ms()
+        m.last_ms()
         full_idx, full_dist = shard.gather_results(d_idx.cpu().numpy(), d_dist.cpu().numpy(), n, dist)
         if rank == 0:
             np.savez(out, idx=full_idx, dist=full_dist)
@@ -675,15 +719,15 @@ def _peer_worker(rank, world, port, n, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_sharded_knn2_over_peer_mapped_rows(tmp_path, world):
+@pytest.mark.parametrize('world,sync', [(2, False), (3, False), (2, True), (3, True)])
+def test_sharded_knn2_over_peer_mapped_rows(tmp_path, world, sync):
     if ob.device_count() == 0:
         pytest.fail('no CUDA device')
     import socket
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     n, out = 3001, str(tmp_path / 'res.npz')
-    mp.spawn(_peer_worker, args=(world, port, n, out), nprocs=world, join=True)
+    mp.spawn(_peer_worker, args=(world, port, n, out, sync), nprocs=world, join=True)
     got = np.load(out)
     train = synth_descriptors(n, 5); query = synth_query_from_train(train, 6)
     ridx, rdist = O.knn2(query, train)
