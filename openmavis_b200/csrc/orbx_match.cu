@@ -54,6 +54,7 @@ struct orbx_matcher {
     cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;   // aux: the peer pull of the sharded 2-NN
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     int last_launches = 0;
+    int knn_resident = 8;                           // CTAs of k_knn2 one SM holds
     bool timed = false;
     DBuf b[24];
 };
@@ -66,10 +67,10 @@ static int upload(orbx_matcher *m, DBuf &buf, const void *src, size_t bytes) {
     return ORBX_OK;
 }
 
-// Train set = concatenation of `nparts` parts (one for the single-GPU call; one per rank, read through peer-mapped pointers over
-// NVLink, for the sharded matcher).  One k_knn2 launch per part, all writing slices of the same partial buffer, one merge.
-// `first` (or -1): the part whose kernels are launched first; `wait_after_first` (or nullptr): event the stream waits for before the
-// kernels of the other parts (the peer rows arrive on another stream while the own part is being matched).
+// Train set = concatenation of `nparts` parts (one for the single-GPU call; one per rank for the sharded matcher).  The parts are
+// matched in at most two launches — the part `first` alone (or nothing: -1), then all the others in ONE launch after the stream has
+// waited for `wait_after_first` (the peer rows arrive on another stream while the own part is being matched) — every launch cut into
+// enough train slices for two full waves of resident CTAs, all slices writing one partial buffer, one merge.
 static int knn2_launch_parts(orbx_matcher *m, const uint8_t *d_q, int nq, const uint8_t *const *d_parts, const int *part_rows, int nparts,
                              int *d_idx, int *d_dist, int first = -1, cudaEvent_t wait_after_first = nullptr) {
     long long nt = 0;
@@ -77,31 +78,41 @@ static int knn2_launch_parts(orbx_matcher *m, const uint8_t *d_q, int nq, const 
     if (nt >= (1 << kKeyShift)) return fail(ORBX_ERR_INVALID, "knn2: more than 8388607 train rows are not supported");
     const int per_block = kKnnThreads * kKnnQPT;
     const int qblocks = (nq + per_block - 1) / per_block;
-    // split the train set so that small problems still fill the machine (2 waves of 148 SMs x resident CTAs)
-    const int want = std::max(1, (2 * m->sm_count * 4 + qblocks - 1) / qblocks);
-    std::vector<int> slices(nparts), slice_rows(nparts);
+    std::vector<int> row_off(nparts);
+    for (int p = 0, ro = 0; p < nparts; p++) { row_off[p] = ro; ro += part_rows[p]; }
+    // the two groups and their slices
+    KnnGroup G[2];
     int total_slices = 0;
-    for (int p = 0; p < nparts; p++) {
-        const int rows = part_rows[p];
-        if (rows <= 0) { slices[p] = 0; slice_rows[p] = kKnnTile; continue; }
-        int s = std::max(1, std::min((int)((long long)want * rows / std::max<long long>(nt, 1)) + 1, (rows + kKnnTile - 1) / kKnnTile));
-        slice_rows[p] = ((rows + s - 1) / s + kKnnTile - 1) / kKnnTile * kKnnTile;
-        slices[p] = (rows + slice_rows[p] - 1) / slice_rows[p];
-        total_slices += slices[p];
+    for (int g = 0; g < 2; g++) {
+        KnnGroup &K = G[g];
+        K.nparts = 0; K.first_slice[0] = total_slices;
+        long long rows_g = 0;
+        for (int p = 0; p < nparts; p++) if ((p == first) == (g == 0) && part_rows[p] > 0) rows_g += part_rows[p];
+        if (rows_g == 0) continue;
+        // slices of the group: two waves of the CTAs the device holds at once, at least one tile per slice
+        const int want = std::max(1, (2 * m->sm_count * m->knn_resident + qblocks - 1) / qblocks);
+        for (int p = 0; p < nparts; p++) {
+            if ((p == first) != (g == 0) || part_rows[p] <= 0) continue;
+            const int rows = part_rows[p], tiles = (rows + kKnnTile - 1) / kKnnTile;
+            const int s = std::max(1, std::min((int)((long long)want * rows / rows_g) + 1, tiles));
+            const int srows = ((rows + s - 1) / s + kKnnTile - 1) / kKnnTile * kKnnTile;
+            const int k = K.nparts++;
+            K.t[k] = (const uint4 *)d_parts[p]; K.nt[k] = rows; K.row_off[k] = row_off[p]; K.slice_rows[k] = srows;
+            total_slices += (rows + srows - 1) / srows;
+            K.first_slice[k + 1] = total_slices;
+        }
     }
     M_CUDA(m->b[0].ensure((size_t)std::max(total_slices, 1) * nq * sizeof(uint2)));
-    std::vector<int> slice_base(nparts), row_off(nparts);
-    for (int p = 0, sb = 0, ro = 0; p < nparts; p++) { slice_base[p] = sb; row_off[p] = ro; sb += slices[p]; ro += part_rows[p]; }
-    auto launch = [&](int p) {
-        if (slices[p] <= 0) return;
-        k_knn2<<<dim3(qblocks, slices[p]), kKnnThreads, 0, m->stream>>>((const uint4 *)d_q, nq, (const uint4 *)d_parts[p], part_rows[p],
-                                                                        slice_rows[p], m->b[0].as<uint2>() + (size_t)slice_base[p] * nq, row_off[p]);
+    for (int g = 0; g < 2; g++) {
+        if (g == 1 && wait_after_first) M_CUDA(cudaStreamWaitEvent(m->stream, wait_after_first, 0));
+        const KnnGroup &K = G[g];
+        if (K.nparts == 0) continue;
+        const int ns = K.first_slice[K.nparts] - K.first_slice[0];
+        KnnGroup L = K;                              // slice numbers relative to the launch
+        for (int k = 0; k <= L.nparts; k++) L.first_slice[k] -= K.first_slice[0];
+        k_knn2<<<dim3(qblocks, ns), kKnnThreads, 0, m->stream>>>((const uint4 *)d_q, nq, L, m->b[0].as<uint2>() + (size_t)K.first_slice[0] * nq);
         m->last_launches++;
-    };
-    if (first >= 0) launch(first);
-    if (wait_after_first) M_CUDA(cudaStreamWaitEvent(m->stream, wait_after_first, 0));
-    for (int p = 0; p < nparts; p++)
-        if (p != first) launch(p);
+    }
     k_knn2_merge<<<(nq + 255) / 256, 256, 0, m->stream>>>(m->b[0].as<uint2>(), nq, total_slices, d_idx, d_dist);
     m->last_launches++;
     M_CUDA(cudaGetLastError());
@@ -139,6 +150,8 @@ int orbx_matcher_create(orbx_matcher **out, int device) {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, k_publish_epoch); cudaFuncGetAttributes(&fa, k_pull_parts_wait); cudaFuncGetAttributes(&fa, k_pull_parts);
         cudaFuncGetAttributes(&fa, k_knn2); cudaFuncGetAttributes(&fa, k_knn2_merge);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_knn2, kKnnThreads, 0) == cudaSuccess && nb > 0) m->knn_resident = nb;
     }
     *out = m;
     return ORBX_OK;

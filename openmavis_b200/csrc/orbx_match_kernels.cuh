@@ -31,9 +31,17 @@ __device__ __forceinline__ void top2_insert(uint32_t &k0, uint32_t &k1, uint32_t
     k0 = min(k0, k);
 }
 
-// t / nt: one part of the train set (possibly the mapped memory of a peer GPU); row_off = global index of its first row.
-__global__ void __launch_bounds__(kKnnThreads) k_knn2(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt,
-                                                      int slice_rows, uint2 *__restrict__ partial, int row_off) {
+// One launch covers a GROUP of train parts (the whole train set of the single-GPU call; the own rows, or all the pulled peer rows, of
+// the sharded matcher): grid.y = slices of all parts of the group, slice y belongs to the part p with first_slice[p] <= y.
+// t[p] / nt[p]: rows of part p, row_off[p] = global index of its first row, slice_rows[p] = rows per slice (a multiple of kKnnTile).
+struct KnnGroup { const uint4 *t[64]; int nt[64], row_off[64], slice_rows[64], first_slice[65]; int nparts; };
+
+__global__ void __launch_bounds__(kKnnThreads) k_knn2(const uint4 *__restrict__ q, int nq, const __grid_constant__ KnnGroup G,
+                                                      uint2 *__restrict__ partial) {
+    int part = 0;
+    while (part + 1 < G.nparts && (int)blockIdx.y >= G.first_slice[part + 1]) part++;
+    const uint4 *__restrict__ t = G.t[part];
+    const int nt = G.nt[part], slice_rows = G.slice_rows[part], row_off = G.row_off[part];
     __shared__ uint4 s_t[kKnnTile * 2];
     const int qbase = (blockIdx.x * kKnnThreads + threadIdx.x) * kKnnQPT;
     uint4 qa[kKnnQPT], qb[kKnnQPT];
@@ -44,7 +52,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn2(const uint4 *__restrict__ 
         qa[u] = q[2 * qi]; qb[u] = q[2 * qi + 1];
         k0[u] = kKeyNone; k1[u] = kKeyNone;
     }
-    const int t_begin = blockIdx.y * slice_rows;
+    const int t_begin = ((int)blockIdx.y - G.first_slice[part]) * slice_rows;
     const int t_end = min(nt, t_begin + slice_rows);
     for (int base = t_begin; base < t_end; base += kKnnTile) {
         const int rows = min(kKnnTile, t_end - base);
