@@ -119,7 +119,7 @@ MC_HD void orbx_sincosf(float y, float *sn, float *cs) {
 
 // ---- cv::resize(INTER_LINEAR, 8U) coefficient tables (OpenCV imgproc/resize.cpp) ---------
 // tap = {first source index, second source index (clamped), a0, a1} with a0/a1 in Q11.
-struct ResizeTap { unsigned short s0, s1; short a0, a1; };
+struct alignas(8) ResizeTap { unsigned short s0, s1; short a0, a1; };   // (8-byte aligned: one 64-bit load per tap)
 
 inline void orbx_resize_taps(int src, int dst, ResizeTap *taps) {
     const double inv_scale = (double)dst / src;
