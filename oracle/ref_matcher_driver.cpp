@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <memory>
+#include <set>
 #include <vector>
 
 #include "ORBmatcher.h"
@@ -428,6 +429,170 @@ int refm_search_for_triangulation(int ncam, const int *cam_off1, const ref_kp *k
 #endif
 
 // the pixel camera's epipolar predicate, for the oracle-side callback of the same test
+// KeyFrame with one camera block (NLeft == -1) over n keypoints: grid as the KeyFrame constructor copies it from the Frame
+// (src/KeyFrame.cc:113-131); the other cameras' grids exist and are empty
+static void fill_keyframe(KeyFrame &K, PixelCamera *cams, const ref_kp *kps, const uint8_t *desc, int n, const float *bounds, const float *sf, int nlev) {
+    Frame F;
+    const int cam_off[2] = {0, n};
+    fill_frame(F, 1, cam_off, kps, desc, sf, nlev);
+    K.N = n;
+    K.mpCamera = &cams[0]; K.mpCamera2 = &cams[1]; K.mpCamera3 = &cams[2]; K.mpCamera4 = &cams[3];
+    K.mvKeysUn = F.mvKeysUn; K.mvKeys = F.mvKeysUn;
+    K.mDescriptors = F.mDescriptors;
+    K.mvScaleFactors.assign(sf, sf + nlev);
+    K.mvuRight.assign(n, -1.f);
+    K.mnMinX = (int)bounds[0]; K.mnMaxX = (int)bounds[1]; K.mnMinY = (int)bounds[2]; K.mnMaxY = (int)bounds[3];
+    K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    K.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    K.mGridRight = K.mGrid; K.mGridSideLeft = K.mGrid; K.mGridSideRight = K.mGrid;
+    for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) K.mGrid[i][j] = F.mGrid[i][j];
+    K.map_points.assign(n, nullptr);
+}
+
+// a map point that projects to (x, y) with every geometric gate open: world = camera coordinates (identity poses), z = 1, normal = PO / |PO|
+static void place_point(MapPoint &P, float x, float y, int level, const uint8_t *d) {
+    P.world_pos = Eigen::Vector3f(x, y, 1.f);
+    P.normal = P.world_pos / P.world_pos.norm();
+    P.predicted_level = level;
+    P.n_obs = 1;
+    P.descriptor = desc_mat(d, 1);
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+// (src/ORBmatcher.cc:2415-2535), the relocalisation matcher.  Current frame: one camera block, `occupied` keypoints hold a map point.
+// KeyFrame: npts map points (has_mp), point i at (px, py, 1) with predicted level level[i], its keypoint angle kf_angle[i];
+// already_found[i] = the point is in sAlreadyFound.  assigned[idx] = i written to CurrentFrame.mvpMapPoints[idx] (-1: untouched / cleared).
+int refm_search_by_projection_reloc(const ref_kp *kps, const uint8_t *desc, int n, const float *bounds, const float *sf, int nsf, const uint8_t *occupied,
+                                    int npts, const uint8_t *has_mp, const uint8_t *already_found, const float *px, const float *py, const int *level,
+                                    const float *kf_angle, const uint8_t *pt_desc, float th, int ORBdist, int checkOrientation, int *assigned) {
+    set_bounds(bounds);
+    Frame Cur;
+    const int cam_off[2] = {0, n};
+    fill_frame(Cur, 1, cam_off, kps, desc, sf, nsf);
+    PixelCamera cams[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
+    Cur.mpCamera = &cams[0];
+    MapPoint holder;
+    holder.n_obs = 1;
+    for (int i = 0; i < n; i++) if (occupied && occupied[i]) Cur.mvpMapPoints[i] = &holder;
+    KeyFrame K;
+    K.N = npts;
+    std::vector<MapPoint> mps(npts);
+    K.map_points.assign(npts, nullptr);
+    std::set<MapPoint *> found;
+    for (int i = 0; i < npts; i++) {
+        K.mvKeysUn.push_back(cv::KeyPoint(0.f, 0.f, 31.f, kf_angle[i], 0.f, 0, -1));
+        if (!has_mp[i]) continue;
+        place_point(mps[i], px[i], py[i], level[i], pt_desc + (size_t)i * 32);
+        K.map_points[i] = &mps[i];
+        if (already_found && already_found[i]) found.insert(&mps[i]);
+    }
+    ORBmatcher matcher(0.9f, checkOrientation != 0);
+    const int nm = matcher.SearchByProjection(Cur, &K, found, th, ORBdist);
+    for (int i = 0; i < n; i++) {
+        MapPoint *m = Cur.mvpMapPoints[i];
+        assigned[i] = (m && m != &holder) ? (int)(m - mps.data()) : -1;
+    }
+    return nm;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame *pKF, Sim3f &Scw, vpPoints, vpMatched, th, ratioHamming, cameraID = 0) (src/ORBmatcher.cc:668-777)
+// and, with with_kfs != 0, the overload that also records the points' keyframes (:779-893).  Scw = identity.  matched_in[idx] = vpMatched
+// already holds a point there; candidate point i at (px, py, 1); skip[i] = the point is bad or already in vpMatched.
+// assigned[idx] = i for the entries the call wrote (-1 elsewhere); matched_kf_ok = every written entry of vpMatchedKF is the point's keyframe.
+int refm_search_by_projection_sim3(const ref_kp *kps, const uint8_t *desc, int n, const float *bounds, const float *sf, int nsf, const uint8_t *matched_in,
+                                   int npts, const uint8_t *skip, const float *px, const float *py, const int *level, const uint8_t *pt_desc, int th,
+                                   float ratioHamming, int with_kfs, int *assigned, int *matched_kf_ok) {
+    set_bounds(bounds);
+    PixelCamera cams[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
+    KeyFrame K;
+    fill_keyframe(K, cams, kps, desc, n, bounds, sf, nsf);
+    std::vector<MapPoint> mps(npts), holders(n);
+    std::vector<KeyFrame> kfs(npts);
+    std::vector<MapPoint *> vpPoints(npts), vpMatched(n, nullptr);
+    std::vector<KeyFrame *> vpPointsKFs(npts), vpMatchedKF(n, nullptr);
+    for (int i = 0; i < n; i++) if (matched_in && matched_in[i]) vpMatched[i] = &holders[i];
+    int nskip_found = 0;
+    for (int i = 0; i < npts; i++) {
+        place_point(mps[i], px[i], py[i], level[i], pt_desc + (size_t)i * 32);
+        vpPoints[i] = &mps[i]; vpPointsKFs[i] = &kfs[i];
+        if (skip && skip[i] == 1) mps[i].bad = true;
+        if (skip && skip[i] == 2) { // already found: the point itself sits in vpMatched (at a keypoint that is occupied anyway)
+            for (int k = nskip_found; k < n; k++) if (vpMatched[k]) { vpMatched[k] = &mps[i]; nskip_found = k + 1; break; }
+        }
+    }
+    std::vector<MapPoint *> before = vpMatched;
+    Sophus::Sim3f Scw;
+    ORBmatcher matcher(0.9f, true);
+    const int nm = with_kfs ? matcher.SearchByProjection(&K, Scw, vpPoints, vpPointsKFs, vpMatched, vpMatchedKF, th, ratioHamming, 0)
+                            : matcher.SearchByProjection(&K, Scw, vpPoints, vpMatched, th, ratioHamming, 0);
+    int ok = 1;
+    for (int i = 0; i < n; i++) {
+        assigned[i] = (vpMatched[i] && vpMatched[i] != before[i]) ? (int)(vpMatched[i] - mps.data()) : -1;
+        if (with_kfs && assigned[i] >= 0 && vpMatchedKF[i] != &kfs[assigned[i]]) ok = 0;
+    }
+    if (matched_kf_ok) *matched_kf_ok = ok;
+    return nm;
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1771-1983): T1w = T2w = I, S12 = identity, fx = fy = 1,
+// cx = cy = 0, so map point i1 of KF1 at (u1, v1, 1) projects to (u1, v1) in KF2 and vice versa.  pre12[i1] = keypoint of KF2 that
+// vpMatches12[i1] already points to on entry (-1: none; -2: a point that is not in KF2; >= n2: an index the reference ignores, :1802).  match12[i1] = keypoint of KF2 the call matched (-1: none / was pre-matched).
+int refm_search_by_sim3(const ref_kp *kps1, const uint8_t *desc1, int n1, const ref_kp *kps2, const uint8_t *desc2, int n2, const float *bounds,
+                        const float *sf, int nsf, const uint8_t *has_mp1, const float *u1, const float *v1, const int *level1, const uint8_t *mpdesc1,
+                        const uint8_t *has_mp2, const float *u2, const float *v2, const int *level2, const uint8_t *mpdesc2, const int *pre12, float th,
+                        int *match12) {
+    set_bounds(bounds);
+    PixelCamera cams[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
+    KeyFrame K1, K2;
+    fill_keyframe(K1, cams, kps1, desc1, n1, bounds, sf, nsf);
+    fill_keyframe(K2, cams, kps2, desc2, n2, bounds, sf, nsf);
+    std::vector<MapPoint> mp1(n1), mp2(n2), pre(n1);
+    for (int i = 0; i < n1; i++) if (has_mp1[i]) { place_point(mp1[i], u1[i], v1[i], level1[i], mpdesc1 + (size_t)i * 32); K1.map_points[i] = &mp1[i]; }
+    for (int i = 0; i < n2; i++) if (has_mp2[i]) { place_point(mp2[i], u2[i], v2[i], level2[i], mpdesc2 + (size_t)i * 32); K2.map_points[i] = &mp2[i]; }
+    std::vector<MapPoint *> vpMatches12(n1, nullptr);
+    for (int i = 0; i < n1; i++)
+        if (pre12 && pre12[i] != -1) { if (pre12[i] >= 0) pre[i].index_in_kf[&K2] = pre12[i]; vpMatches12[i] = &pre[i]; }
+    ORBmatcher matcher(0.75f, true);
+    const Sophus::Sim3f S12;
+    const int nf = matcher.SearchBySim3(&K1, &K2, vpMatches12, S12, th);
+    for (int i = 0; i < n1; i++) {
+        MapPoint *m = vpMatches12[i];
+        match12[i] = (m && m >= mp2.data() && m < mp2.data() + n2) ? (int)(m - mp2.data()) : -1;
+    }
+    return nf;
+}
+
+// ORBmatcher::Fuse(KeyFrame *pKF, Sim3f &Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:1648-1769), the loop-closing fuse: Scw =
+// identity, the keyframe's keypoints with has_mp hold a map point (-> vpReplacePoint), the others get the point added.  Cameras 1-3 of the
+// keyframe exist and are empty (the reference walks all four).  best_idx[q] = keypoint the search of point q ended on (-1: none).
+int refm_fuse_sim3(const ref_kp *kps, const uint8_t *desc, int n, const float *bounds, const float *sf, int nlev, const uint8_t *has_mp, int nq,
+                   const uint8_t *valid, const float *qx, const float *qy, const int *level, const uint8_t *q_desc, float th, int *best_idx) {
+    set_bounds(bounds);
+    PixelCamera cams[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
+    KeyFrame K;
+    fill_keyframe(K, cams, kps, desc, n, bounds, sf, nlev);
+    std::vector<MapPoint> holders(n), mps(nq);
+    for (int i = 0; i < n; i++) if (!has_mp || has_mp[i]) { holders[i].n_obs = 3; K.map_points[i] = &holders[i]; }
+    std::vector<MapPoint *> vp(nq), rep(nq, nullptr);
+    for (int q = 0; q < nq; q++) {
+        place_point(mps[q], qx[q], qy[q], level[q], q_desc + (size_t)q * 32);
+        mps[q].n_obs = 0;
+        if (!valid[q]) mps[q].bad = true;
+        vp[q] = &mps[q];
+    }
+    Sophus::Sim3f Scw;
+    ORBmatcher matcher(0.8f, true);
+    const int nf = matcher.Fuse(&K, Scw, vp, th, rep);
+    for (int q = 0; q < nq; q++) {
+        best_idx[q] = -1;
+        MapPoint *r = rep[q];
+        if (r && r >= holders.data() && r < holders.data() + n) best_idx[q] = (int)(r - holders.data());
+        else if (r) best_idx[q] = r->index_in_kf[&K];                   // replaced by a point an earlier search added at that keypoint
+        else if (mps[q].index_in_kf.count(&K)) best_idx[q] = mps[q].index_in_kf[&K];   // added
+    }
+    return nf;
+}
+
 int refm_pair_hash(float x1, float y1, float x2, float y2, int id1, int id2) { return PixelCamera::pair_hash(x1, y1, x2, y2, id1, id2) ? 1 : 0; }
 
 }  // extern "C"

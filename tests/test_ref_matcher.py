@@ -399,3 +399,171 @@ def test_fuse_keyframe_mappoints():
         exp = np.where(bd <= 50, bi, -1)
         assert nf == int((exp >= 0).sum()) and nf > 20, (trial, nf, int((exp >= 0).sum()))
         assert np.array_equal(a, exp), (trial, int((a != exp).sum()))
+
+
+def _oracle_last(Lo, k, desc, w, h, sf, occupied, npts, valid, px, py, octv, ang, pd, th, gate, chk, max_dist):
+    """orc_search_by_projection_last for one camera block (what orbx_search_by_projection_last is tested against on the GPU)."""
+    n = len(k)
+    cam_off = np.array([0, n], np.int32)
+    grids = (C.c_void_p * 1)()
+    grids[0] = Lo.orc_grid_create(p(k), n, C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
+    PX = np.repeat(px[:, None], 4, 1).astype(np.float32); PY = np.repeat(py[:, None], 4, 1).astype(np.float32)
+    b = np.zeros(n, np.int32)
+    nb = Lo.orc_search_by_projection_last(1, p(cam_off), p(k), p(desc), grids, p(sf), p(occupied), None, npts, p(valid), p(PX), p(PY), None, p(octv),
+                                          p(ang), None, p(pd), C.c_float(th), gate, chk, max_dist, p(b))
+    Lo.orc_grid_destroy(C.c_void_p(grids[0]))
+    return nb, b
+
+
+def _planted_points(rng, k, desc, npts, w, h, spread=4.0):
+    src = rng.integers(0, len(k), npts)
+    px = (k['x'][src] + rng.uniform(-spread, spread, npts)).astype(np.float32); py = (k['y'][src] + rng.uniform(-spread, spread, npts)).astype(np.float32)
+    px[rng.random(npts) < 0.06] = np.float32(-30.0)                           # outside the image
+    lvl = np.clip(k['octave'][src] + rng.integers(-1, 2, npts), 0, 7).astype(np.int32)
+    pd = synth_descriptors(npts, int(rng.integers(1 << 30)))
+    own = rng.random(npts) < 0.75
+    pd[own] = desc[src[own]] ^ np.packbits(rng.random((int(own.sum()), 256)) < 0.06, axis=1, bitorder='little')
+    return src, px, py, lvl, pd
+
+
+def test_search_by_projection_relocalisation():
+    """SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2415-2535: inclusive image
+    bounds, level gate [l-1, l+1] inside GetFeaturesInArea, claims in point order, ORBdist, rotation histogram — against
+    orc_search_by_projection_last (gate 0), the function the device entry point is tested against."""
+    rng = np.random.default_rng(77)
+    L = RM(); Lo = O.lib()
+    w = h = 512
+    for trial in range(12):
+        n = int(rng.integers(300, 1500)); npts = int(rng.integers(200, 1500))
+        k = make_kps(n, rng, w, h, lattice=8 if trial % 2 else None)
+        desc = synth_descriptors(n, 7700 + trial)
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        src, px, py, lvl, pd = _planted_points(rng, k, desc, npts, w, h)
+        if trial % 3 == 0:
+            pd[: npts // 4] = pd[0]                                           # many points compete for the same keypoints
+        ang = ((k['angle'][src] + np.where(rng.random(npts) < 0.8, 20 + rng.uniform(-3, 3, npts), rng.uniform(0, 360, npts))) % 360).astype(np.float32)
+        has_mp = (rng.random(npts) < 0.9).astype(np.uint8); found = (rng.random(npts) < 0.1).astype(np.uint8)
+        occupied = (rng.random(n) < 0.05).astype(np.uint8)
+        th = float([10.0, 15.0][trial % 2]); orb_dist = [100, 64][trial % 2]; chk = (trial // 2) % 2
+        bounds = np.array([0, w, 0, h], np.float32)
+        a = np.zeros(n, np.int32)
+        na = L.refm_search_by_projection_reloc(p(k), p(desc), n, p(bounds), p(sf), 8, p(occupied), npts, p(has_mp), p(found), p(px), p(py), p(lvl), p(ang),
+                                               p(pd), C.c_float(th), orb_dist, chk, p(a))
+        valid = (has_mp.astype(bool) & ~found.astype(bool) & (px >= 0) & (px <= w) & (py >= 0) & (py <= h)).astype(np.uint8)
+        nb, b = _oracle_last(Lo, k, desc, w, h, sf, occupied, npts, valid, px, py, lvl, ang, pd, th, 0, chk, orb_dist)
+        assert na == nb and na > 20, (trial, na, nb)
+        assert np.array_equal(a, b), (trial, int((a != b).sum()))
+
+
+@pytest.mark.parametrize('with_kfs', [0, 1])
+def test_search_by_projection_keyframe_sim3(with_kfs):
+    """Both SearchByProjection(KeyFrame*, Sim3f&, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th, ratioHamming, cameraID) overloads,
+    src/ORBmatcher.cc:668-893: IsInImage (half-open), KeyFrame::GetFeaturesInArea without level gate, the [l-1, l] gate in the loop,
+    vpMatched as occupancy, TH_LOW * ratioHamming — against orc_search_by_projection_last (gate 3)."""
+    rng = np.random.default_rng(88 + with_kfs)
+    L = RM(); Lo = O.lib()
+    w, h = 640, 480
+    for trial in range(10):
+        n = int(rng.integers(300, 1500)); npts = int(rng.integers(200, 1500))
+        k = make_kps(n, rng, w, h, lattice=8 if trial % 2 else None)
+        desc = synth_descriptors(n, 8800 + trial)
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        src, px, py, lvl, pd = _planted_points(rng, k, desc, npts, w, h)
+        if trial % 3 == 0:
+            pd[: npts // 4] = pd[0]
+        matched_in = (rng.random(n) < 0.08).astype(np.uint8)
+        skip = rng.choice([0, 1, 2], npts, p=[0.9, 0.06, 0.04]).astype(np.uint8)
+        skip[np.cumsum(skip == 2) > int(matched_in.sum())] = 0                # every 'already found' point needs an occupied keypoint to sit in
+        th = [4, 8][trial % 2]; ratio = [1.0, 0.8, 0.9][trial % 3]
+        bounds = np.array([0, w, 0, h], np.float32)
+        a = np.zeros(n, np.int32); ok = C.c_int(0)
+        na = L.refm_search_by_projection_sim3(p(k), p(desc), n, p(bounds), p(sf), 8, p(matched_in), npts, p(skip), p(px), p(py), p(lvl), p(pd), th,
+                                              C.c_float(ratio), with_kfs, p(a), C.byref(ok))
+        valid = ((skip == 0) & (px >= 0) & (px < w) & (py >= 0) & (py < h)).astype(np.uint8)
+        max_dist = int(np.floor(np.float32(50) * np.float32(ratio)))
+        ang = np.zeros(npts, np.float32)
+        nb, b = _oracle_last(Lo, k, desc, w, h, sf, matched_in, npts, valid, px, py, lvl, ang, pd, float(th), 3, 0, max_dist)
+        assert na == nb and na > 20, (trial, na, nb)
+        assert np.array_equal(a, b), (trial, int((a != b).sum()))
+        assert not with_kfs or ok.value == 1
+
+
+def test_search_by_sim3():
+    """ORBmatcher::SearchBySim3, src/ORBmatcher.cc:1771-1983: the already-matched bookkeeping through GetIndexInKeyFrame, the two window
+    searches (TH_HIGH, [l-1, l] gate, first minimum) and the agreement check — against orc_search_by_sim3."""
+    rng = np.random.default_rng(99)
+    L = RM(); Lo = O.lib()
+    w, h = 640, 480
+    for trial in range(10):
+        n1 = int(rng.integers(300, 1200)); n2 = int(rng.integers(300, 1200))
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        k2 = make_kps(n2, rng, w, h, lattice=6 if trial % 2 else None); d2 = synth_descriptors(n2, 9900 + trial)
+        # KF1's keypoints: most of them are KF2 keypoints seen again (so that the two searches can agree)
+        src = rng.integers(0, n2, n1)
+        k1 = make_kps(n1, rng, w, h)
+        again = rng.random(n1) < 0.7
+        k1['x'][again] = (k2['x'][src[again]] + rng.uniform(-2, 2, int(again.sum()))).astype(np.float32)
+        k1['y'][again] = (k2['y'][src[again]] + rng.uniform(-2, 2, int(again.sum()))).astype(np.float32)
+        k1['octave'][again] = k2['octave'][src[again]]
+        d1 = synth_descriptors(n1, 9950 + trial)
+        d1[again] = d2[src[again]] ^ np.packbits(rng.random((int(again.sum()), 256)) < 0.05, axis=1, bitorder='little')
+        has1 = (rng.random(n1) < 0.85).astype(np.uint8); has2 = (rng.random(n2) < 0.85).astype(np.uint8)
+        # a map point of KF1 projects near its own keypoint in KF2's image (identity Sim3), with its keypoint's descriptor
+        u1 = (k1['x'] + rng.uniform(-2, 2, n1)).astype(np.float32); v1 = (k1['y'] + rng.uniform(-2, 2, n1)).astype(np.float32)
+        u2 = (k2['x'] + rng.uniform(-2, 2, n2)).astype(np.float32); v2 = (k2['y'] + rng.uniform(-2, 2, n2)).astype(np.float32)
+        u1[rng.random(n1) < 0.05] = np.float32(-20.0); v2[rng.random(n2) < 0.05] = np.float32(h + 5.0)
+        l1 = np.clip(k1['octave'] + rng.integers(0, 2, n1), 0, 7).astype(np.int32); l2 = np.clip(k2['octave'] + rng.integers(0, 2, n2), 0, 7).astype(np.int32)
+        m1 = d1.copy(); m2 = d2.copy()
+        pre12 = np.where(rng.random(n1) < 0.06, rng.integers(-2, n2 + 3, n1), -1).astype(np.int32)   # -2: not in KF2; >= n2: ignored (:1802)
+        pre12[pre12 == -1] = -1
+        th = float([7.5, 10.0][trial % 2])
+        bounds = np.array([0, w, 0, h], np.float32)
+        a = np.zeros(n1, np.int32)
+        na = L.refm_search_by_sim3(p(k1), p(d1), n1, p(k2), p(d2), n2, p(bounds), p(sf), 8, p(has1), p(u1), p(v1), p(l1), p(m1), p(has2), p(u2), p(v2),
+                                   p(l2), p(m2), p(pre12), C.c_float(th), p(a))
+        already1 = pre12 != -1                                                 # vpMatches12[i] != NULL
+        already2 = np.zeros(n2, bool)
+        idx2 = pre12[(pre12 >= 0) & (pre12 < n2)]
+        already2[idx2] = True
+        val1 = (has1.astype(bool) & ~already1 & (u1 >= 0) & (u1 < w) & (v1 >= 0) & (v1 < h)).astype(np.uint8)
+        val2 = (has2.astype(bool) & ~already2 & (u2 >= 0) & (u2 < w) & (v2 >= 0) & (v2 < h)).astype(np.uint8)
+        r1 = (np.float32(th) * sf[l1]).astype(np.float32); r2 = (np.float32(th) * sf[l2]).astype(np.float32)
+        g1 = Lo.orc_grid_create(p(k1), n1, C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
+        g2 = Lo.orc_grid_create(p(k2), n2, C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
+        b = np.zeros(n1, np.int32)
+        nb = Lo.orc_search_by_sim3(C.c_void_p(g1), p(k1), p(d1), n1, C.c_void_p(g2), p(k2), p(d2), n2, p(val1), p(u1), p(v1), p(r1), p(l1), p(m1),
+                                   p(val2), p(u2), p(v2), p(r2), p(l2), p(m2), p(b))
+        Lo.orc_grid_destroy(C.c_void_p(g1)); Lo.orc_grid_destroy(C.c_void_p(g2))
+        assert na == nb and na > 20, (trial, na, nb)
+        assert np.array_equal(a, b), (trial, int((a != b).sum()))
+
+
+def test_fuse_keyframe_sim3():
+    """ORBmatcher::Fuse(KeyFrame*, Sim3f &Scw, vpPoints, th, vpReplacePoint), src/ORBmatcher.cc:1648-1769, the loop-closing fuse: the search
+    loop without reprojection gates ([l-1, l] level gate, first minimum, TH_LOW) — against orc_window_best."""
+    rng = np.random.default_rng(111)
+    L = RM(); Lo = O.lib()
+    w, h = 640, 480
+    for trial in range(10):
+        n = int(rng.integers(300, 2000)); nq = int(rng.integers(200, 1500))
+        k = make_kps(n, rng, w, h, lattice=5 if trial % 2 else None)
+        desc = synth_descriptors(n, 11100 + trial)
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        src, qx, qy, lvl, qd = _planted_points(rng, k, desc, nq, w, h, spread=2.5)
+        lvl = np.clip(k['octave'][src] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
+        has_mp = (rng.random(n) < 0.7).astype(np.uint8)
+        valid = (rng.random(nq) < 0.95).astype(np.uint8)
+        th = float([3.0, 5.0][trial % 2])
+        bounds = np.array([0, w, 0, h], np.float32)
+        a = np.zeros(nq, np.int32)
+        nf = L.refm_fuse_sim3(p(k), p(desc), n, p(bounds), p(sf), 8, p(has_mp), nq, p(valid), p(qx), p(qy), p(lvl), p(qd), C.c_float(th), p(a))
+        v2 = (valid.astype(bool) & (qx >= 0) & (qx < w) & (qy >= 0) & (qy < h)).astype(np.uint8)
+        radius = (np.float32(th) * sf[lvl]).astype(np.float32)
+        g = Lo.orc_grid_create(p(k), n, C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
+        bi = np.zeros(nq, np.int32); bd = np.zeros(nq, np.int32)
+        Lo.orc_window_best(C.c_void_p(g), p(k), p(desc), None, None, None, nq, p(v2), p(qx), p(qy), None, p(radius), p((lvl - 1).astype(np.int32)),
+                           p(lvl), p(qd), p(bi), p(bd))
+        Lo.orc_grid_destroy(C.c_void_p(g))
+        exp = np.where(bd <= 50, bi, -1)
+        assert nf == int((exp >= 0).sum()) and nf > 20, (trial, nf, int((exp >= 0).sum()))
+        assert np.array_equal(a, exp), (trial, int((a != exp).sum()))
