@@ -15,7 +15,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 typedef unsigned char uchar;
@@ -135,6 +138,7 @@ class Mat {
     static Mat zeros(int r, int c, int type) { Mat m(r, c, type); if (m.rows > 0) memset(m.data, 0, (size_t)m.rows * m.step); return m; }
 
     bool empty() const { return data == 0 || rows == 0 || cols == 0; }
+    void release() { own_.reset(); data = 0; rows = cols = 0; step = 0; }
     int type() const { return type_; }
     size_t elemSize() const { return esz(type_); }
     size_t step1() const { return step / esz(type_); }   // single-channel: elements per row
@@ -202,5 +206,30 @@ inline void Mat::copyTo(const _OutputArray &dst) const {
 }
 
 static inline float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }
+
+// cv::FileStorage / cv::FileNode: inert stand-ins.  DBoW2's TemplatedVocabulary has VIRTUAL save / load members on them, which are
+// instantiated with the class; nothing in the tests calls them (the vocabulary is read with the reference's loadFromTextFile).
+class FileNode {
+  public:
+    size_t size() const { return 0; }
+    FileNode operator[](const std::string &) const { return FileNode(); }
+    FileNode operator[](const char *) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    operator int() const { return 0; }
+    operator float() const { return 0.f; }
+    operator double() const { return 0.0; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+  public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const std::string &, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const std::string &) const { return FileNode(); }
+    FileNode operator[](const char *) const { return FileNode(); }
+};
+template <class T> static inline FileStorage &operator<<(FileStorage &fs, const T &) { return fs; }
 
 }  // namespace cv
