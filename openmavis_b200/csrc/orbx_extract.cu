@@ -102,6 +102,10 @@ struct orbx_extractor {
     int *d_cell_cnt = nullptr, *d_cell_off = nullptr, *d_lin_n = nullptr, *d_lvl_n = nullptr, *d_slot = nullptr;
     int *d_n_kp = nullptr, *d_n_mono = nullptr, *d_nfeat = nullptr, *d_desc_blocks = nullptr, *d_blur_tiles = nullptr;
     int desc_blocks = 0;
+    int *d_desc_blocks2 = nullptr;   // k_orient_desc_batch: CTA -> level | first slot << 4 (kOdSlotsPerCta slots per CTA)
+    int desc_blocks2 = 0;
+    bool desc_batch = false;         // k_orient_desc_batch instead of k_orient_desc (measured equal to slower: see the kernel's comment)
+    int desc_ring = 4;
     float *d_lvl_angle = nullptr;
     orbx_kp *d_out_kp = nullptr;
     orbx_image_params *d_params = nullptr;
@@ -255,7 +259,7 @@ void orbx_extractor_destroy(orbx_extractor *ex) {
     cudaFree(ex->d_pattern); cudaFree(ex->d_cells); cudaFree(ex->d_lin); cudaFree(ex->d_lvl_kp); cudaFree(ex->d_node);
     cudaFree(ex->d_cell_cnt); cudaFree(ex->d_cell_off); cudaFree(ex->d_lin_n); cudaFree(ex->d_lvl_n); cudaFree(ex->d_slot);
     cudaFree(ex->d_n_kp); cudaFree(ex->d_n_mono); cudaFree(ex->d_nfeat); cudaFree(ex->d_lvl_angle); cudaFree(ex->d_out_kp);
-    cudaFree(ex->d_params); cudaFree(ex->d_fast_stats); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps); cudaFree(ex->d_desc_blocks); cudaFree(ex->d_blur_tiles);
+    cudaFree(ex->d_params); cudaFree(ex->d_fast_stats); cudaFree(ex->d_fast_tiles); cudaFree(ex->d_patch_maps); cudaFree(ex->d_desc_blocks); cudaFree(ex->d_desc_blocks2); cudaFree(ex->d_blur_tiles);
     cudaFree(ex->d_st_uright); cudaFree(ex->d_st_depth); cudaFree(ex->d_st_sad); cudaFree(ex->d_st_kept);
     if (ex->h_in) cudaFreeHost(ex->h_in);
     if (ex->h_params) cudaFreeHost(ex->h_params);
@@ -417,6 +421,14 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
         ex->desc_blocks = (int)binfo.size();
         EX_CUDA(dalloc(&ex->d_desc_blocks, binfo.size()));
         EX_CUDA(cudaMemcpy(ex->d_desc_blocks, binfo.data(), binfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<int> binfo2;
+        for (int l = 0; l < nlevels; l++)
+            for (int i0 = 0; i0 < G.lv[l].kp_cap; i0 += kOdSlotsPerCta) binfo2.push_back(l | (i0 << 4));
+        ex->desc_blocks2 = (int)binfo2.size();
+        EX_CUDA(dalloc(&ex->d_desc_blocks2, binfo2.size()));
+        EX_CUDA(cudaMemcpy(ex->d_desc_blocks2, binfo2.data(), binfo2.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (const char *t = getenv("ORBX_DESC_BATCH")) ex->desc_batch = atoi(t) != 0;   // tuning knob: 1 = one warp per group of 16 keypoints
+        if (const char *t = getenv("ORBX_DESC_RING")) ex->desc_ring = std::max(3, std::min(5, atoi(t)));
         static const signed char pat[1024] = {ORBX_PATTERN_VALUES};
         EX_CUDA(dalloc(&ex->d_pattern, (size_t)1024));
         EX_CUDA(cudaMemcpy(ex->d_pattern, pat, 1024, cudaMemcpyHostToDevice));
@@ -436,6 +448,12 @@ int orbx_extractor_create(orbx_extractor **out, int device, int width, int heigh
         EX_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
         EX_CUDA(cudaFuncSetAttribute(k_octree_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
         EX_CUDA(cudaFuncSetAttribute(k_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+        EX_CUDA(cudaFuncSetAttribute(k_orient_desc_batch<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, od_smem_bytes(3)));
+        EX_CUDA(cudaFuncSetAttribute(k_orient_desc_batch<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, od_smem_bytes(3)));
+        EX_CUDA(cudaFuncSetAttribute(k_orient_desc_batch<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, od_smem_bytes(4)));
+        EX_CUDA(cudaFuncSetAttribute(k_orient_desc_batch<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, od_smem_bytes(4)));
+        EX_CUDA(cudaFuncSetAttribute(k_orient_desc_batch<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, od_smem_bytes(5)));
+        EX_CUDA(cudaFuncSetAttribute(k_orient_desc_batch<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, od_smem_bytes(5)));
     }
     {   // TMA tensor maps of the pyramid levels for the blur tiles (driver entry point through the runtime: no -lcuda)
         memset(&ex->blur_maps, 0, sizeof(ex->blur_maps));
@@ -609,7 +627,17 @@ static int enqueue_chunk(orbx_extractor *ex, int i0, int cnt, const uint8_t *d_i
     launches++;
     if (ev) ORBX_CUDA(cudaEventRecord(ev[5], sA));
     if (sB != sA) ORBX_CUDA(cudaStreamWaitEvent(sA, ex->ev_blur[lane], 0));
-    {
+    if (ex->patch_maps.use_tma && ex->desc_batch) {   // one warp per group of kOdG keypoints
+        const dim3 grid(ex->desc_blocks2, cnt);
+#define ORBX_LAUNCH_DESC_BATCH(FMA, RING)                                                                                                    \
+    k_orient_desc_batch<FMA, RING><<<grid, kOdWarps * 32, od_smem_bytes(RING), sA>>>(G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot,     \
+                                                                                      ex->d_lvl_angle, ex->d_out_kp, ex->d_out_desc, ex->d_patch_maps, \
+                                                                                      ex->d_desc_blocks2, i0)
+        if (ex->desc_ring == 3) { if (G.fma_mode) ORBX_LAUNCH_DESC_BATCH(true, 3); else ORBX_LAUNCH_DESC_BATCH(false, 3); }
+        else if (ex->desc_ring == 4) { if (G.fma_mode) ORBX_LAUNCH_DESC_BATCH(true, 4); else ORBX_LAUNCH_DESC_BATCH(false, 4); }
+        else { if (G.fma_mode) ORBX_LAUNCH_DESC_BATCH(true, 5); else ORBX_LAUNCH_DESC_BATCH(false, 5); }
+#undef ORBX_LAUNCH_DESC_BATCH
+    } else {
         const dim3 grid(ex->desc_blocks, cnt);
 #define ORBX_LAUNCH_DESC(FMA, TMA)                                                                                             \
     k_orient_desc<FMA, TMA><<<grid, 256, 0, sA>>>(ex->d_pyr, ex->d_blur, G, ex->d_pattern, ex->d_lvl_kp, ex->d_lvl_n, ex->d_slot, \

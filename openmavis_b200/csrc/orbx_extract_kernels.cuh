@@ -991,6 +991,38 @@ constexpr int kOriW = 48, kOriH = 31, kDescW = 64, kDescH = 37;   // widths incl
 constexpr int kOriBytes = kOriW * kOriH, kDescBytes = kDescW * kDescH;
 constexpr int kPatchStride = ((kOriBytes + 127) & ~127) + ((kDescBytes + 127) & ~127);      // per warp, 128-byte aligned parts
 
+// IC_Angle, one patch row per lane: the lane holds its whole staged 48-byte row as twelve words (three 128-bit loads: with a row pitch
+// of 48 bytes the eight lanes of a quarter warp hit eight different 16-byte bank groups, so the loads are conflict-free, while the nine
+// 32-bit loads per lane this replaces ran into 4-way conflicts — 36 instead of 12 shared-memory wavefronts per keypoint, in a kernel that
+// is bound by the L1 / shared-memory pipe).  The 31 pixels u = -15..15 start at byte c0 of the row (1 <= c0 <= 16): words kS = c0 >> 2
+// onwards, funnel-shifted by sh = 8 * (c0 & 3); msk = the disc as byte masks; m10 += sum u I (IDP.4A, signed weights), rowsum += sum I.
+template <int kS>
+__device__ __forceinline__ void ic_row_sums(const uint32_t (&w)[12], int sh, const uint32_t (&msk)[8], int &m10, int &rowsum) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t a = __funnelshift_r(w[kS + q], w[kS + q + 1 < 12 ? kS + q + 1 : 11], sh) & msk[q];   // (kS == 4: sh == 0, the high word is unused)
+        const int u0 = 4 * q - kHalfPatch;                       // weights u0 .. u0 + 3 as signed bytes
+        const uint32_t wu = (uint32_t)(u0 & 0xFF) | ((uint32_t)((u0 + 1) & 0xFF) << 8) | ((uint32_t)((u0 + 2) & 0xFF) << 16) |
+                            ((uint32_t)((u0 + 3) & 0xFF) << 24);
+        asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(a), "r"(wu));
+        rowsum = (int)__dp4a(a, 0x01010101u, (uint32_t)rowsum);
+    }
+}
+__device__ __forceinline__ void ic_row(uint32_t row_addr, int c0, const uint32_t (&msk)[8], int &m10, int &rowsum) {
+    uint32_t w[12];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * k]), "=r"(w[4 * k + 1]), "=r"(w[4 * k + 2]), "=r"(w[4 * k + 3]) : "r"(row_addr + 16 * k) : "memory");
+    const int sh = 8 * (c0 & 3);
+    switch (c0 >> 2) {                                           // warp-uniform
+    case 0: ic_row_sums<0>(w, sh, msk, m10, rowsum); break;
+    case 1: ic_row_sums<1>(w, sh, msk, m10, rowsum); break;
+    case 2: ic_row_sums<2>(w, sh, msk, m10, rowsum); break;
+    case 3: ic_row_sums<3>(w, sh, msk, m10, rowsum); break;
+    default: ic_row_sums<4>(w, sh, msk, m10, rowsum); break;
+    }
+}
+
 // grid.x enumerates CTAs of 8 keypoint slots; a CTA belongs to one level: block_info[blockIdx.x] = level | first slot << 4
 template <bool kFma, bool kTma>
 __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, Geom G,
@@ -1035,6 +1067,9 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
             const int m = (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15);                      // umax[|v|], src/ORBextractor.cc:399-413
             const uint32_t bits = ((2u << (2 * m)) - 1u) << (kHalfPatch - m);                    // bytes 15 - m .. 15 + m of the row
             const int c0 = ((kXO + x - 16) & 15) + 1;                                            // byte of column x - 15 in the staged row
+            // (nine 32-bit loads per lane: with the 48-byte row pitch they run into 4-way bank conflicts; three conflict-free 128-bit
+            //  loads of the whole row + a warp-uniform switch over the first word — ic_row below, used by the batched kernel — cost 8
+            //  more registers here (6 instead of 7 CTAs per SM) and were measured slower in this kernel: 0.343 vs 0.327 ms)
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(op + lane * kOriW + (c0 & ~3));
             const int sh = 8 * (c0 & 3);
             uint32_t w[9];
@@ -1111,6 +1146,188 @@ __global__ void __launch_bounds__(256) k_orient_desc(const uint8_t *__restrict__
         if (lvl != 0) { o.x = __fmul_rn(o.x, L.scale); o.y = __fmul_rn(o.y, L.scale); }
         o.size = L.patch; o.angle = angle; o.response = (float)cand_score(kp); o.octave = lvl; o.class_id = -1;
         out_kp[(long long)b * G.out_cap + s] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4 + K6 + K7b, batched (round 2): one warp per GROUP of kOdG keypoint slots of one (image, level) instead of one warp per keypoint.
+// What a keypoint-per-warp kernel pays once per keypoint, the group pays once per lane or once per warp:
+//   * atan2 + the glibc-exact sincos (about 105 warp-instructions, 18 % of the kernel) run with lane l = keypoint l after the
+//     moments of the whole group are known, i.e. once per 16 keypoints instead of once per keypoint with 32 identical lanes;
+//   * the lane's 32 pattern coordinates are converted int8 -> float ONCE and stay in registers (no I2F in the sample loop), and
+//     cvRound is the add of 1.5 * 2^23 (round-to-nearest-even, exact for |v| < 2^22) whose bias is folded into the patch base
+//     address (no F2I either): the sample loop has no instruction left on the quarter-rate conversion pipe;
+//   * the disc masks of IC_Angle depend on the lane (= patch row) only and are built once.
+// Patches: a ring of kOdRing shared-memory slots per warp, filled by TMA tensor copies on the warp's own mbarriers; request k of a
+// group of n keypoints is the orientation patch of keypoint k (k < n) or the descriptor patch of keypoint k - n, so the first
+// descriptor patches are in flight while the last orientations are computed and while the lanes evaluate atan2 / sincos.
+// Results are bit-identical to k_orient_desc (same integer moments, same separately rounded float operations).
+// MEASURED (B200, 320 images, 482 k keypoints): 219 M warp-instructions instead of 285 M, but 0.340 ms (ring of 4 slots, 16 warps per SM;
+// 0.43 ms with 3 slots / 20 warps, 0.38 ms with 5 / 12) against 0.327 ms for k_orient_desc: neither kernel is bound by instruction
+// issue.  Per keypoint 3.9 KB of patches cross the L2 -> SM path (2.4 GB per launch = 7.1 TB/s, L2 65 % busy, the L1 / shared-memory
+// pipe 85 %: TMA fills + the byte gathers of the descriptor, 4.7 wavefronts per load), and a patch ring deep enough to hide the TMA
+// latency leaves this kernel shared memory for 16 warps per SM only.  It is therefore OPT-IN (ORBX_DESC_BATCH=1, ORBX_DESC_RING=3..5;
+// tests/test_gpu_extract.py::test_batched_orientation_descriptor_kernel checks its bits); the default stays one warp per keypoint.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kOdG = 16, kOdWarps = 4;
+constexpr int kOdSlotBytes = (kDescBytes + 127) & ~127;          // a slot holds either patch (orientation 48 x 31, descriptor 64 x 37)
+constexpr int kOdSlotsPerCta = kOdG * kOdWarps;                  // block_info2[blockIdx.x] = level | first slot << 4
+
+constexpr int kOdRedBytes = kOdG * 33 * 4;                       // per warp: partial moments [keypoint][33] (one word per patch row)
+__host__ __device__ constexpr int od_smem_bytes(int ring) { return kOdWarps * (ring * kOdSlotBytes + kOdRedBytes); }
+
+template <bool kFma, int kOdRing>
+__global__ void __launch_bounds__(kOdWarps * 32, kOdRing <= 3 ? 6 : 5) k_orient_desc_batch(Geom G, const signed char *__restrict__ pattern,
+                                                                        const uint32_t *__restrict__ lvl_kp, const int *__restrict__ lvl_n,
+                                                                        const int *__restrict__ slot, float *__restrict__ lvl_angle,
+                                                                        orbx_kp *__restrict__ out_kp, uint8_t *__restrict__ out_desc,
+                                                                        const PatchMaps *__restrict__ maps, const int *__restrict__ block_info,
+                                                                        int img0) {
+    extern __shared__ __align__(128) uint8_t s_ring[];           // [warp][ring slot][kOdSlotBytes], then [warp][kOdG][33] u32
+    __shared__ __align__(8) uint64_t s_bar[kOdWarps * kOdRing];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.y + img0;
+    const int info = __ldg(block_info + blockIdx.x);
+    const int lvl = info & 15;
+    const LevelGeom &L = G.lv[lvl];
+    const int i0 = (info >> 4) + wid * kOdG;
+    const int n = min(kOdG, lvl_n[b * G.nlevels + lvl] - i0);   // keypoints of this warp's group
+    if (n <= 0) return;
+    const long long first = (long long)b * G.kp_per_image + L.kp_off + i0;
+    // lane l < n owns keypoint l of the group: coordinates, output slot, later its moments / angle / rotation
+    const uint32_t kp_m = lane < n ? lvl_kp[first + lane] : 0u;
+    const int slot_m = lane < n ? slot[first + lane] : 0;
+    const int x_m = cand_x(kp_m), y_m = cand_y(kp_m);
+    const uint32_t ring = smem_u32(s_ring) + wid * (kOdRing * kOdSlotBytes);
+    const uint32_t red = smem_u32(s_ring) + kOdWarps * (kOdRing * kOdSlotBytes) + wid * kOdRedBytes;
+    uint64_t *bar = s_bar + wid * kOdRing;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < kOdRing; r++) mbar_init(&bar[r], 1);
+    }
+    __syncwarp();
+    const CUtensorMap *map_o = &maps->pyr[lvl], *map_d = &maps->blur[lvl];
+    const int nreq = 2 * n;
+    int k_issue = 0, s_issue = 0;                                // next request and its ring slot
+    // (all lanes call: the coordinates come from the owning lane; lane 0 issues the copy)
+    auto issue = [&]() {
+        const int j = k_issue < n ? k_issue : k_issue - n;
+        const int xj = __shfl_sync(0xFFFFFFFFu, x_m, j), yj = __shfl_sync(0xFFFFFFFFu, y_m, j);
+        if (lane == 0) {
+            uint64_t *br = &bar[s_issue];
+            const uint32_t dst = ring + s_issue * kOdSlotBytes;
+            const bool ori = k_issue < n;
+            mbar_arrive_expect_tx(br, ori ? (uint32_t)kOriBytes : (uint32_t)kDescBytes);
+            const int c0 = ori ? ((kXO + xj - 16) & ~15) : ((kXO + xj - 24) & ~15), c1 = ori ? kYO + yj - kHalfPatch : kYO + yj - 18;
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                         "l"(reinterpret_cast<uint64_t>(ori ? map_o : map_d)), "r"(smem_u32(br)), "r"(c0), "r"(c1), "r"(b)
+                         : "memory");
+        }
+        k_issue++;
+        s_issue = s_issue == kOdRing - 1 ? 0 : s_issue + 1;
+    };
+#pragma unroll
+    for (int r = 0; r < kOdRing; r++)
+        if (k_issue < nreq) issue();
+    // ---- per-lane constants
+    // IC_Angle: lane = row v of the 31 x 31 patch; bytes 15 - m .. 15 + m of the row lie inside the disc (m = umax[|v|])
+    const int v = lane - kHalfPatch, av = v < 0 ? -v : v;
+    uint32_t msk[8];
+    {
+        const int m = lane < 31 ? (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15) : -1;   // src/ORBextractor.cc:399-413
+        const uint32_t bits = m < 0 ? 0u : ((2u << (2 * m)) - 1u) << (kHalfPatch - m);
+#pragma unroll
+        for (int j = 0; j < 8; j++) msk[j] = ((((bits >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+    }
+    // descriptor: lane = output byte; its 8 tests x 2 points as floats (x, y)
+    float fpx[16], fpy[16];
+    {
+        const uint4 pa = __ldg(reinterpret_cast<const uint4 *>(pattern) + 2 * lane), pb = __ldg(reinterpret_cast<const uint4 *>(pattern) + 2 * lane + 1);
+        const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};   // word k = (x0, y0, x1, y1) of test k
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                fpx[2 * k + e] = (float)(signed char)(pw[k] >> (16 * e));
+                fpy[2 * k + e] = (float)(signed char)(pw[k] >> (16 * e + 8));
+            }
+    }
+    int s_use = 0;                                               // ring slot of the request being consumed
+    uint32_t par = 0;                                            // bit s = parity the next wait on slot s expects
+    // ---- phase 1: moments of every keypoint of the group (src/ORBextractor.cc:19-43)
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+        const int xj = __shfl_sync(0xFFFFFFFFu, x_m, j);
+        mbar_wait(&bar[s_use], (par >> s_use) & 1u);
+        par ^= 1u << s_use;
+        const uint32_t op = ring + s_use * kOdSlotBytes;
+        const int c0 = ((kXO + xj - 16) & 15) + 1;               // byte of column x - 15 in the staged row
+        int m10 = 0, rowsum = 0;
+        ic_row(op + min(lane, 30) * kOriW, c0, msk, m10, rowsum);
+        // the row's two sums as one word (|m10| < 2^17, rowsum < 2^13); they are added up after the loop, a keypoint per lane:
+        // no shuffle chain inside the loop
+        sts32(red + 4 * (j * 33 + lane), ((uint32_t)m10 << 13) | (uint32_t)rowsum);
+        __syncwarp();                                            // every lane has read the slot
+        if (k_issue < nreq) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue();
+        }
+        s_use = s_use == kOdRing - 1 ? 0 : s_use + 1;
+    }
+    // ---- lane l: angle and rotation of keypoint l, its KeyPoint record
+    float sn_m = 0.f, cs_m = 1.f;
+    __syncwarp();
+    if (lane < n) {
+        int mm10 = 0, mm01 = 0;
+#pragma unroll
+        for (int r = 0; r < 31; r++) {                           // (column reads of a [.][33] array: conflict-free)
+            const uint32_t pk = lds32(red + 4 * (lane * 33 + r));
+            mm10 += (int)pk >> 13;
+            mm01 += (r - kHalfPatch) * (int)(pk & 0x1FFFu);
+        }
+        const float angle = orbx_fast_atan2((float)mm01, (float)mm10);
+        const float rad = __fmul_rn(angle, 0.0174532924f);       // (float)(CV_PI/180.f)
+        orbx_sincosf(rad, &sn_m, &cs_m);
+        lvl_angle[first + lane] = angle;
+        orbx_kp o;
+        o.x = (float)x_m; o.y = (float)y_m;
+        if (lvl != 0) { o.x = __fmul_rn(o.x, L.scale); o.y = __fmul_rn(o.y, L.scale); }
+        o.size = L.patch; o.angle = angle; o.response = (float)cand_score(kp_m); o.octave = lvl; o.class_id = -1;
+        out_kp[(long long)b * G.out_cap + slot_m] = o;
+    }
+    // ---- phase 2: 256-bit rBRIEF of every keypoint (src/ORBextractor.cc:46-90)
+    constexpr float kRound = 12582912.f;                         // 1.5 * 2^23: (v + kRound) has cvRound(v) in its low mantissa bits
+    constexpr uint32_t kRoundBits = 0x4B400000u;
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+        const int xj = __shfl_sync(0xFFFFFFFFu, x_m, j), sj = __shfl_sync(0xFFFFFFFFu, slot_m, j);
+        const float sn = __shfl_sync(0xFFFFFFFFu, sn_m, j), cs = __shfl_sync(0xFFFFFFFFu, cs_m, j);
+        mbar_wait(&bar[s_use], (par >> s_use) & 1u);
+        par ^= 1u << s_use;
+        // shared address of the patch centre, minus the bias of the two rounded coordinates: address = cb + iy * kDescW + ix
+        const uint32_t cb = ring + s_use * kOdSlotBytes + 18 * kDescW + 24 + ((kXO + xj - 24) & 15) - kRoundBits * (uint32_t)(kDescW + 1);
+        uint32_t val = 0;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            int tv[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const float px = fpx[2 * k + e], py = fpy[2 * k + e];
+                float fy, fx;
+                if (kFma) { fy = __fmaf_rn(px, sn, __fmul_rn(py, cs)); fx = __fmaf_rn(px, cs, -__fmul_rn(py, sn)); }
+                else { fy = __fadd_rn(__fmul_rn(px, sn), __fmul_rn(py, cs)); fx = __fsub_rn(__fmul_rn(px, cs), __fmul_rn(py, sn)); }
+                const uint32_t iy = __float_as_uint(__fadd_rn(fy, kRound)), ix = __float_as_uint(__fadd_rn(fx, kRound));
+                tv[e] = (int)lds8(cb + iy * (uint32_t)kDescW + ix);
+            }
+            val = __funnelshift_l((uint32_t)(tv[0] - tv[1]), val, 1);   // (val << 1) | (tv[0] < tv[1]): test k ends up in bit k
+        }
+        out_desc[((long long)b * G.out_cap + sj) * 32 + lane] = (uint8_t)val;
+        __syncwarp();
+        if (k_issue < nreq) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue();
+        }
+        s_use = s_use == kOdRing - 1 ? 0 : s_use + 1;
     }
 }
 

@@ -426,7 +426,6 @@ int refm_search_for_triangulation(int ncam, const int *cam_off1, const ref_kp *k
     for (auto &p : pairs) match12[p.first] = (int)p.second;
     return n;
 }
-#endif
 
 // the pixel camera's epipolar predicate, for the oracle-side callback of the same test
 // KeyFrame with one camera block (NLeft == -1) over n keypoints: grid as the KeyFrame constructor copies it from the Frame
@@ -593,6 +592,7 @@ int refm_fuse_sim3(const ref_kp *kps, const uint8_t *desc, int n, const float *b
     return nf;
 }
 
+#endif   // !ORBX_GLUE_BUILD (the glue implements the methods the tracking / mapping front end calls: tests/test_matcher_glue.py)
 int refm_pair_hash(float x1, float y1, float x2, float y2, int id1, int id2) { return PixelCamera::pair_hash(x1, y1, x2, y2, id1, id2) ? 1 : 0; }
 
 }  // extern "C"

@@ -63,3 +63,15 @@ def test_product_does_not_reference_oracle():
                 if re.search(r'oracle/|orb_oracle|oracle_lib|orc_', open(os.path.join(dp, f), errors='ignore').read().replace('orc_search_by_projection', '')):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_harness_libraries_load_without_a_gpu(ob):
+    """The C++ drop-in classes (libshim_harness.so) and the reference-signature matcher glue (libglue_matcher.so) resolve every symbol
+    at load time — the GPU tests dlopen them on the box, where nothing can be rebuilt (the glue needs the reference checkout)."""
+    import ctypes
+    ob.lib()
+    hh = os.path.join(ROOT, 'tests', 'host_harness')
+    if not os.path.exists(os.path.join(hh, 'libglue_matcher.so')) or not os.path.exists(os.path.join(hh, 'libshim_harness.so')):
+        subprocess.check_call(['make', '-C', hh])
+    for name in ('libshim_harness.so', 'libglue_matcher.so'):
+        ctypes.CDLL(os.path.join(hh, name), mode=os.RTLD_NOW)

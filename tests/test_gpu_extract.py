@@ -319,6 +319,21 @@ def test_staging_fallback_paths_without_tma(monkeypatch):
     compare_image(rig, 0, img, 1500, 20, 7, (0, 720), b)
 
 
+@pytest.mark.parametrize('ring,fma', [(3, 0), (4, 0), (4, 1), (5, 0)])
+def test_batched_orientation_descriptor_kernel(monkeypatch, ring, fma):
+    """k_orient_desc_batch (one warp per group of 16 keypoints, TMA patch ring, per-lane atan2 / sincos, conversion-free sample loop;
+    opt-in through ORBX_DESC_BATCH because it was measured no faster than one warp per keypoint) gives the same bits: angles, keypoint
+    records, descriptors — against the oracle and the compiled reference, in both float-contraction modes."""
+    _need_gpu()
+    monkeypatch.setenv('ORBX_DESC_BATCH', '1')
+    monkeypatch.setenv('ORBX_DESC_RING', str(ring))
+    imgs = [synth_image(720, 540, 8200 + c) for c in range(2)]
+    rig = ob.RigExtractor(720, 540, 2, 1500, fma_mode=fma)      # the knobs are read when the handle is created
+    res = rig.extract(imgs, ob.make_params(2, 1500, 20, 7, (0, 720)))
+    for b in range(2):
+        compare_image(rig, b, imgs[b], 1500, 20, 7, (0, 720), res[b], fma_mode=fma, stages=(b == 0))
+
+
 def test_concurrent_extractor_threads_reference_usage():
     """The reference calls operator() from 2-4 std::threads, one per extractor instance (src/Frame.cc:1841-1862): four handles,
     four host threads, repeated small calls (the cached CUDA-graph path with thread-local capture) - every result must equal the
