@@ -84,6 +84,30 @@ def test_knn2_100k_property(M):
     assert np.array_equal(idx[rows], ridx) and np.array_equal(dist[rows], rdist)
 
 
+def test_knn2_100k_config5_generator(M):
+    """The 100k x 100k workload exactly as SURVEY.md §8(d) config 5 defines it and bench.py times it (train = uniform random rows of
+    seed 5; query i = a train row with Binomial(256, 0.08) bit flips for 80 % of the rows, fresh random rows for 20 %: real nearest
+    neighbours AND distance ties): size-independent properties + a sampled full scan by the oracle."""
+    from openmavis_b200.synth import synth_query_from_train
+    n = 100000
+    train = synth_descriptors(n, 5)
+    q = synth_query_from_train(train, 6)
+    idx, dist = M.knnMatch2(q, train)
+    assert idx.shape == (n, 2) and (idx >= 0).all() and (idx < n).all()
+    got_d0 = np.unpackbits(q ^ train[idx[:, 0]], axis=1).sum(axis=1)
+    got_d1 = np.unpackbits(q ^ train[idx[:, 1]], axis=1).sum(axis=1)
+    assert np.array_equal(got_d0, dist[:, 0]) and np.array_equal(got_d1, dist[:, 1])          # reported distances are the true ones
+    assert (dist[:, 0] <= dist[:, 1]).all() and (idx[:, 0] != idx[:, 1]).all()
+    tie = dist[:, 0] == dist[:, 1]
+    assert (idx[tie, 0] < idx[tie, 1]).all()                                                  # (distance asc, index asc)
+    near = dist[:, 0] < 60                                                                     # the planted 80 %: Binomial(256, 0.08) stays below 60
+    assert 0.78 < near.mean() < 0.82
+    assert (dist[~near, 0] >= 60).all() and dist[~near, 0].min() >= 70                         # fresh rows: nearest of 100k random rows
+    rows = np.concatenate([np.random.default_rng(7).integers(0, n, size=40), np.flatnonzero(tie)[:8]])
+    ridx, rdist = O.knn2(q[rows], train)
+    assert np.array_equal(idx[rows], ridx) and np.array_equal(dist[rows], rdist)
+
+
 def _oracle_csr(q, t, row_ptr, cand):
     nq = q.shape[0]
     out = dict(best_idx=np.full(nq, -1, np.int32), best_dist=np.full(nq, 256, np.int32), second_dist=np.full(nq, 256, np.int32),
