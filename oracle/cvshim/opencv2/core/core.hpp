@@ -207,6 +207,19 @@ inline void Mat::copyTo(const _OutputArray &dst) const {
 
 static inline float fastAtan2(float y, float x) { return orc_fast_atan2(y, x); }
 
+// cv::norm(a, b, NORM_L1) of two 8-bit single-channel matrices of equal size: the sum of absolute differences as a double (OpenCV
+// accumulates 8-bit L1 norms in integers and returns the exact sum; tests/test_oracle_vs_cv2.py pins this against cv2.norm).
+// Called by Frame::ComputeStereoMatches (src/Frame.cc:1167).
+static inline double norm(const Mat &a, const Mat &b, int normType) {
+    long long s = 0;
+    if (normType != NORM_L1 || a.type() != CV_8U || b.type() != CV_8U || a.rows != b.rows || a.cols != b.cols) return -1.0;
+    for (int y = 0; y < a.rows; y++) {
+        const uchar *pa = a.data + (size_t)y * a.step, *pb = b.data + (size_t)y * b.step;
+        for (int x = 0; x < a.cols; x++) s += pa[x] > pb[x] ? pa[x] - pb[x] : pb[x] - pa[x];
+    }
+    return (double)s;
+}
+
 // cv::FileStorage / cv::FileNode: inert stand-ins.  DBoW2's TemplatedVocabulary has VIRTUAL save / load members on them, which are
 // instantiated with the class; nothing in the tests calls them (the vocabulary is read with the reference's loadFromTextFile).
 class FileNode {
