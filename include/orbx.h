@@ -304,6 +304,10 @@ int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off
                                    const float *proj_ur, const int *last_octave, const float *last_angle, const uint8_t *has_obs,
                                    const uint8_t *pt_desc, float th, int level_gate, int check_orientation, int max_dist,
                                    int *assigned, int *nmatches);
+/* After orbx_search_by_projection_last: cleared[idx] = 1 for the keypoints that were claimed and then cleared by the rotation filter —
+ * the reference writes NULL into CurrentFrame.mvpMapPoints there (src/ORBmatcher.cc:2404), while a keypoint no point claimed keeps what
+ * it held; assigned[] reports -1 for both.  n = the keypoint count of that call.  HOST pointer. */
+int orbx_search_by_projection_last_cleared(const orbx_matcher *m, uint8_t *cleared, int n);
 
 /* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:895-1004), whole
  * function: kps / desc = mvKeysUn / mDescriptors of the two frames, grid_bounds2 = F2's {mnMinX, mnMaxX, mnMinY, mnMaxY};

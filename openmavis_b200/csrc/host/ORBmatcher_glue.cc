@@ -10,6 +10,12 @@
 //   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, ...)  src/ORBmatcher.cc:23-340      orbx_search_by_projection
 //   ORBmatcher::SearchForInitialization(F1, F2, ...)                 src/ORBmatcher.cc:895-1004    orbx_search_for_initialization
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)                  src/ORBmatcher.cc:349-666     orbx_search_by_bow_frame
+//   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)               src/ORBmatcher.cc:1006-1129   orbx_search_by_bow_keyframes
+//   ORBmatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono)          :1985-2413   orbx_search_by_projection_last
+//   ORBmatcher::SearchByProjection(Frame &Cur, KeyFrame*, sAlreadyFound, th, ORBdist) :2415-2535   orbx_search_by_projection_last
+// The two projection matchers compute their projections here, on the host, with the integrator's own Eigen / Sophus types and the
+// reference's expressions (a few thousand 3-D points per call); window search, Hamming distances, ordered claims and the rotation
+// filter run on the device.
 //
 // tests/host_harness builds this file against stub Frame / KeyFrame / MapPoint headers that carry the reference's member names and
 // tests/test_matcher_glue.py compares it, call by call, with the reference's own object code (the unmodified ORBmatcher.cc compiled against the same stubs).
@@ -19,6 +25,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <set>
 #include <vector>
 
 #include "orbx.h"
@@ -208,6 +215,166 @@ int ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint *> &vp
         die("SearchByBoW(KeyFrame, Frame)");
     for (int i = 0; i < nF; i++)
         if (matchF[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[matchF[i]];
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:1006-1129
+int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12) {
+    const std::vector<MapPoint *> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int n1 = (int)vpMapPoints1.size(), n2 = (int)vpMapPoints2.size();
+    vpMatches12 = std::vector<MapPoint *>(n1, static_cast<MapPoint *>(NULL));          // :1017
+    if (n1 == 0 || n2 == 0) return 0;
+    std::vector<int> nk1, pk1, ik1, nk2, pk2, ik2;
+    feature_vector_csr(pKF1->mFeatVec, nk1, pk1, ik1);
+    feature_vector_csr(pKF2->mFeatVec, nk2, pk2, ik2);
+    std::vector<unsigned char> skip1(n1), skip2(n2), t1, t2;
+    for (int i = 0; i < n1; i++) skip1[i] = (pKF1->NLeft != -1 && i >= pKF1->N) || !vpMapPoints1[i] || vpMapPoints1[i]->isBad();   // :1036-1044
+    for (int i = 0; i < n2; i++) skip2[i] = (pKF2->NLeft != -1 && i >= pKF2->N) || !vpMapPoints2[i] || vpMapPoints2[i]->isBad();   // :1052-1061
+    std::vector<float> a1(n1, 0.f), a2(n2, 0.f);
+    if (mbCheckOrientation) {                                                           // vKeysUn1[idx1].angle - vKeysUn2[bestIdx2].angle, :1087
+        for (int i = 0; i < n1 && i < (int)pKF1->mvKeysUn.size(); i++) a1[i] = pKF1->mvKeysUn[i].angle;
+        for (int i = 0; i < n2 && i < (int)pKF2->mvKeysUn.size(); i++) a2[i] = pKF2->mvKeysUn[i].angle;
+    }
+    if (pKF1->mDescriptors.rows < n1 || pKF2->mDescriptors.rows < n2) { fprintf(stderr, "ORBmatcher::SearchByBoW: fewer descriptor rows than map point slots\n"); abort(); }
+    std::vector<int> match12(n1, -1);
+    int nmatches = 0;
+    if (orbx_search_by_bow_keyframes(handle(), (int)nk1.size(), nk1.data(), pk1.data(), ik1.data(), (int)nk2.size(), nk2.data(), pk2.data(), ik2.data(),
+                                     desc_rows(pKF1->mDescriptors, t1), n1, desc_rows(pKF2->mDescriptors, t2), n2, skip1.data(), skip2.data(), a1.data(),
+                                     a2.data(), mfNNratio, mbCheckOrientation ? 1 : 0, match12.data(), &nmatches) != ORBX_OK)
+        die("SearchByBoW(KeyFrame, KeyFrame)");
+    for (int i = 0; i < n1; i++)
+        if (match12[i] >= 0) vpMatches12[i] = vpMapPoints2[match12[i]];                 // :1084
+    return nmatches;
+}
+
+namespace {
+// keypoint i of a Frame in global feature order (the reference's kpLF / nLastOctave selection, :2027-2038, 2107-2117)
+const cv::KeyPoint &frame_key(const Frame &F, int i, bool undistorted_if_single) {
+    if (F.Nleft == -1) return undistorted_if_single ? F.mvKeysUn[i] : F.mvKeys[i];
+    if (i < F.Nleft) return F.mvKeys[i];
+    if (i < F.Nleft + F.Nright) return F.mvKeysRight[i - F.Nleft];
+    if (i < F.Nleft + F.Nright + F.Nsideleft) return F.mvKeysSideLeft[i - F.Nleft - F.Nright];
+    return F.mvKeysSideRight[i - F.Nleft - F.Nright - F.Nsideleft];
+}
+}  // namespace
+
+// src/ORBmatcher.cc:1985-2413 — the tracking matcher (Tracking::TrackWithMotionModel)
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono) {
+    std::vector<orbx_kp> kps;
+    int cam_off[5];
+    const int ncam = frame_layout(CurrentFrame, kps, cam_off);
+    const int N = CurrentFrame.N, npts = LastFrame.N;
+    if (N == 0 || npts == 0) return 0;
+    // :1998-2004
+    const Sophus::SE3f Tcw = CurrentFrame.GetPose();
+    const Eigen::Vector3f twc = Tcw.inverse().translation();
+    const Sophus::SE3f Tlw = LastFrame.GetPose();
+    const Eigen::Vector3f tlc = Tlw * twc;
+    const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;
+    const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono;
+    std::vector<unsigned char> valid(npts, 0), has_obs(npts, 0), pt_desc((size_t)npts * 32, 0);
+    std::vector<float> px((size_t)npts * 4, 0.f), py((size_t)npts * 4, 0.f), pur(npts, 0.f), last_angle(npts, 0.f);
+    std::vector<int> last_octave(npts, 0);
+    for (int i = 0; i < npts; i++) {
+        MapPoint *pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;                                  // :2007-2009
+        Eigen::Vector3f x3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f x3Dc = Tcw * x3Dw;
+        const float invzc = 1.0 / x3Dc(2);                                              // :2016
+        if (invzc < 0) continue;
+        Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+        if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+        if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+        valid[i] = 1;
+        px[4 * i] = uv(0); py[4 * i] = uv(1);
+        pur[i] = uv(0) - CurrentFrame.mbf * invzc;                                      // :2080
+        if (CurrentFrame.Nleft != -1) {                                                 // :2132-2134 (projected with mpCamera, as the reference does)
+            Eigen::Vector3f x3Dr = CurrentFrame.GetRelativePoseTrl() * x3Dc;
+            Eigen::Vector2f uvr = CurrentFrame.mpCamera->project(x3Dr);
+            px[4 * i + 1] = uvr(0); py[4 * i + 1] = uvr(1);
+        }
+        px[4 * i + 2] = px[4 * i + 3] = uv(0); py[4 * i + 2] = py[4 * i + 3] = uv(1);   // the side cameras are searched around the LEFT projection (:2250-2271)
+        last_octave[i] = frame_key(LastFrame, i, false).octave;                         // :2027-2038 (mvKeys for a single-camera frame)
+        last_angle[i] = frame_key(LastFrame, i, true).angle;                            // :2107-2117 (mvKeysUn for a single-camera frame)
+        has_obs[i] = pMP->Observations() > 0;
+        const cv::Mat d = pMP->GetDescriptor();
+        memcpy(&pt_desc[(size_t)i * 32], d.ptr<unsigned char>(0), 32);
+    }
+    std::vector<unsigned char> occupied(N, 0), dtmp;
+    for (int i = 0; i < N; i++) occupied[i] = CurrentFrame.mvpMapPoints[i] && CurrentFrame.mvpMapPoints[i]->Observations() > 0;   // :2072-2074
+    float bounds[16];
+    for (int c = 0; c < 4; c++) { bounds[4 * c] = CurrentFrame.mnMinX; bounds[4 * c + 1] = CurrentFrame.mnMaxX; bounds[4 * c + 2] = CurrentFrame.mnMinY; bounds[4 * c + 3] = CurrentFrame.mnMaxY; }
+    const bool stereo = ncam == 1 && (int)CurrentFrame.mvuRight.size() == N;            // :2076
+    std::vector<int> assigned(N, -1);
+    int nmatches = 0;
+    orbx_matcher *h = handle();
+    if (orbx_search_by_projection_last(h, ncam, cam_off, kps.data(), desc_rows(CurrentFrame.mDescriptors, dtmp), bounds, CurrentFrame.mvScaleFactors.data(),
+                                       (int)CurrentFrame.mvScaleFactors.size(), occupied.data(), stereo ? CurrentFrame.mvuRight.data() : nullptr, npts,
+                                       valid.data(), px.data(), py.data(), pur.data(), last_octave.data(), last_angle.data(), has_obs.data(), pt_desc.data(),
+                                       th, bForward ? ORBX_GATE_FORWARD : bBackward ? ORBX_GATE_BACKWARD : ORBX_GATE_AROUND, mbCheckOrientation ? 1 : 0,
+                                       TH_HIGH, assigned.data(), &nmatches) != ORBX_OK)
+        die("SearchByProjection(CurrentFrame, LastFrame)");
+    std::vector<unsigned char> cleared(N, 0);
+    if (mbCheckOrientation && orbx_search_by_projection_last_cleared(h, cleared.data(), N) != ORBX_OK) die("SearchByProjection(CurrentFrame, LastFrame)");
+    for (int i = 0; i < N; i++) {
+        if (assigned[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[assigned[i]];   // :2104
+        else if (cleared[i]) CurrentFrame.mvpMapPoints[i] = static_cast<MapPoint *>(NULL);           // :2404
+    }
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:2415-2535 — the relocalisation matcher (searches camera 0 only)
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint *> &sAlreadyFound, const float th, const int ORBdist) {
+    const Sophus::SE3f Tcw = CurrentFrame.GetPose();
+    Eigen::Vector3f Ow = Tcw.inverse().translation();
+    const std::vector<MapPoint *> vpMPs = pKF->GetMapPointMatches();
+    const int npts = (int)vpMPs.size();
+    // camera 0 of the current frame: Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) searches mvKeysUn (Nleft == -1) or mvKeys[0, Nleft)
+    const int n0 = CurrentFrame.Nleft == -1 ? CurrentFrame.N : CurrentFrame.Nleft;
+    if (npts == 0 || n0 == 0) return 0;
+    std::vector<orbx_kp> kps(n0);
+    for (int i = 0; i < n0; i++) {
+        const cv::KeyPoint &k = CurrentFrame.Nleft == -1 ? CurrentFrame.mvKeysUn[i] : CurrentFrame.mvKeys[i];
+        memcpy(&kps[i], &k, sizeof(orbx_kp));
+        if (i < (int)CurrentFrame.mvKeysUn.size()) kps[i].angle = CurrentFrame.mvKeysUn[i].angle;   // :2503
+    }
+    const int cam_off[2] = {0, n0};
+    std::vector<unsigned char> valid(npts, 0), pt_desc((size_t)npts * 32, 0);
+    std::vector<float> px((size_t)npts * 4, 0.f), py((size_t)npts * 4, 0.f), last_angle(npts, 0.f);   // [point][camera], camera 0 used
+    std::vector<int> level(npts, 0);
+    const int nlevels = (int)CurrentFrame.mvScaleFactors.size();
+    for (int i = 0; i < npts; i++) {
+        MapPoint *pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;                 // :2436-2437
+        Eigen::Vector3f x3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f x3Dc = Tcw * x3Dw;
+        const Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+        if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+        if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+        Eigen::Vector3f PO = x3Dw - Ow;
+        float dist3D = PO.norm();
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        if (dist3D < minDistance || dist3D > maxDistance) continue;                     // :2458
+        const int nPredictedLevel = pMP->PredictScale(dist3D, &CurrentFrame);
+        if (nPredictedLevel < 0 || nPredictedLevel >= nlevels) continue;                // (the reference would index mvScaleFactors out of range)
+        valid[i] = 1; px[4 * i] = uv(0); py[4 * i] = uv(1); level[i] = nPredictedLevel;
+        last_angle[i] = i < (int)pKF->mvKeysUn.size() ? pKF->mvKeysUn[i].angle : 0.f;   // :2503
+        const cv::Mat d = pMP->GetDescriptor();
+        memcpy(&pt_desc[(size_t)i * 32], d.ptr<unsigned char>(0), 32);
+    }
+    std::vector<unsigned char> occupied(n0, 0), dtmp;
+    for (int i = 0; i < n0; i++) occupied[i] = CurrentFrame.mvpMapPoints[i] != NULL;    // :2484
+    const float bounds[4] = {CurrentFrame.mnMinX, CurrentFrame.mnMaxX, CurrentFrame.mnMinY, CurrentFrame.mnMaxY};
+    std::vector<int> assigned(n0, -1);
+    int nmatches = 0;
+    if (orbx_search_by_projection_last(handle(), 1, cam_off, kps.data(), desc_rows(CurrentFrame.mDescriptors, dtmp), bounds, CurrentFrame.mvScaleFactors.data(),
+                                       nlevels, occupied.data(), nullptr, npts, valid.data(), px.data(), py.data(), nullptr, level.data(), last_angle.data(),
+                                       nullptr, pt_desc.data(), th, ORBX_GATE_AROUND, mbCheckOrientation ? 1 : 0, ORBdist, assigned.data(), &nmatches) != ORBX_OK)
+        die("SearchByProjection(CurrentFrame, KeyFrame)");
+    // (only keypoints that held NULL can be claimed, so a claim cleared by the rotation filter, :2527, leaves what was there: NULL)
+    for (int i = 0; i < n0; i++)
+        if (assigned[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[assigned[i]];       // :2499
     return nmatches;
 }
 

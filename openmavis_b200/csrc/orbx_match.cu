@@ -57,6 +57,7 @@ struct orbx_matcher {
     int knn_resident = 8;                           // CTAs of k_knn2 one SM holds
     bool timed = false;
     DBuf b[24];
+    std::vector<uint8_t> last_cleared;              // orbx_search_by_projection_last: keypoints whose claim the rotation filter cleared
 };
 
 #define M_CUDA ORBX_CUDA
@@ -1024,6 +1025,7 @@ int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off
     const int N = cam_off[ncam];
     for (int i = 0; i < N; i++) assigned[i] = -1;
     *nmatches = 0;
+    m->last_cleared.assign((size_t)std::max(N, 0), 0);
     if (npts == 0 || N == 0) return ORBX_OK;
     if (N >= 65535) return fail(ORBX_ERR_INVALID, "more than 65534 keypoints per frame are not supported");
     for (int i = 0; i < npts; i++)
@@ -1083,6 +1085,16 @@ int orbx_search_by_projection_last(orbx_matcher *m, int ncam, const int *cam_off
     M_CUDA(cudaStreamSynchronize(m->stream));
     *nmatches = nm_st[0];
     if (nm_st[1] != 0) return fail(ORBX_ERR_CUDA, "ordered resolver did not converge (internal error)");
+    m->last_cleared.assign((size_t)N, 0);
+    for (int i = 0; i < N; i++)
+        if (assigned[i] == -2) { assigned[i] = -1; m->last_cleared[i] = 1; }
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection_last_cleared(const orbx_matcher *m, uint8_t *cleared, int n) {
+    if (!m || !cleared || n < 0) return fail(ORBX_ERR_INVALID, "orbx_search_by_projection_last_cleared: bad argument");
+    if ((size_t)n != m->last_cleared.size()) return fail(ORBX_ERR_INVALID, "orbx_search_by_projection_last_cleared: n differs from the last call's keypoint count");
+    if (n) memcpy(cleared, m->last_cleared.data(), (size_t)n);
     return ORBX_OK;
 }
 

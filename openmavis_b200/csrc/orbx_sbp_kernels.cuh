@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(1024) k_sbp_resolve(SbpFrame F, SbpPoints P, S
         if (bin == s_ind[0] || bin == s_ind[1] || bin == s_ind[2]) continue;
         if (P.mode == 2) {   // :982-985: only matches that were not evicted meanwhile
             if (W.match12[ev & 0xFFFF] >= 0) { W.match12[ev & 0xFFFF] = -1; atomicSub(&W.nmatches[0], 1); }
-        } else { W.assigned[ev & 0xFFFF] = -1; atomicSub(&W.nmatches[0], 1); }
+        } else { W.assigned[ev & 0xFFFF] = -2; atomicSub(&W.nmatches[0], 1); }   // -2 = claimed, then cleared (the reference writes NULL, :2404); the host reports -1
     }
 }
 

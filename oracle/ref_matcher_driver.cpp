@@ -250,7 +250,6 @@ int refm_search_by_bow_frame(int nnKF, const int *nodesKF, const int *ptrKF, con
     return n;
 }
 
-#ifndef ORBX_GLUE_BUILD
 // ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vpMatches12) (src/ORBmatcher.cc:1006-1129); same arrays as
 // orc_search_by_bow_keyframes.  match12[n1] = idx2 whose MapPoint ended up in vpMatches12[idx1], or -1.
 int refm_search_by_bow_keyframes(int nn1, const int *nodes1, const int *ptr1, const int *idx1v, int nn2, const int *nodes2, const int *ptr2,
@@ -278,6 +277,7 @@ int refm_search_by_bow_keyframes(int nn1, const int *nodes1, const int *ptr1, co
     return n;
 }
 
+#ifndef ORBX_GLUE_BUILD   // (not implemented by the glue: the reference body stays)
 // ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th, cameraID = 0) (src/ORBmatcher.cc:1458-1640) on a monocular /
 // rectified-stereo keyframe (NLeft == -1).  The keyframe sits at the origin with the pixel camera; map point q sits at (qx, qy, 1), so the
 // reference projects it to (qx, qy), uses invz = 1 (ur = qx - bf), predicts the level the driver is given, and searches
@@ -324,13 +324,15 @@ int refm_fuse(const ref_kp *kps, const uint8_t *desc, int n, const float *bounds
     return nf;
 }
 
+#endif
 // ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1985-2413), the tracking
 // matcher.  Current frame as in refm_search_by_projection.  Last frame: npts keypoints in the Nleft == -1 layout; has_mp[i] = the point
 // exists and is no outlier; its map point sits at (px[i], py[i], 1) in world = camera coordinates (Tcw = I, pixel camera), so the
 // reference projects it to exactly (px[i], py[i]) in camera 0, to (px + trl[0], py + trl[1]) in the right camera (Trl = [I | trl]) and
 // searches the side cameras around the LEFT projection (the reference's D6 behaviour, :2250-2271).  invzc = 1, so the rectified-stereo
 // test uses ur = px - mbf.  gate: 0 = neither bForward nor bBackward, 1 = bForward, 2 = bBackward (set through the z of the last pose).
-// assigned[idx] = i written to CurrentFrame.mvpMapPoints[idx] (-1 = untouched or cleared by the rotation filter).
+// assigned[idx] = i written to CurrentFrame.mvpMapPoints[idx] (-1 = untouched or cleared by the rotation filter; -3 = the keypoint still
+// holds the unobserved point it held before the call, occupied[idx] == 2).
 int refm_search_by_projection_last(int ncam, const int *cam_off, const ref_kp *kps, const uint8_t *desc, const float *bounds, const float *sf, int nsf,
                                    const uint8_t *occupied, const float *u_right, int npts, const uint8_t *has_mp, const float *px, const float *py,
                                    const float *trl, float mbf, const int *last_octave, const float *last_angle, const uint8_t *has_obs,
@@ -339,9 +341,9 @@ int refm_search_by_projection_last(int ncam, const int *cam_off, const ref_kp *k
     Frame Cur, Last;
     fill_frame(Cur, ncam, cam_off, kps, desc, sf, nsf);
     const int N = Cur.N;
-    MapPoint holder;
-    holder.n_obs = 1;
-    for (int i = 0; i < N; i++) if (occupied && occupied[i]) Cur.mvpMapPoints[i] = &holder;
+    MapPoint holder, holder0;                                  // occupied[i] == 1: a point with observations; == 2: a point WITHOUT (claimable, :2072-2074)
+    holder.n_obs = 1; holder0.n_obs = 0;
+    for (int i = 0; i < N; i++) if (occupied && occupied[i]) Cur.mvpMapPoints[i] = occupied[i] == 2 ? &holder0 : &holder;
     if (u_right && ncam == 1) Cur.mvuRight.assign(u_right, u_right + N);
     PixelCamera cams[4] = {PixelCamera(0), PixelCamera(1), PixelCamera(2), PixelCamera(3)};
     Cur.mpCamera = &cams[0]; Cur.mpCamera2 = ncam >= 2 ? &cams[1] : nullptr; Cur.mpCamera3 = ncam >= 4 ? &cams[2] : nullptr; Cur.mpCamera4 = ncam >= 4 ? &cams[3] : nullptr;
@@ -366,10 +368,11 @@ int refm_search_by_projection_last(int ncam, const int *cam_off, const ref_kp *k
     const int n = matcher.SearchByProjection(Cur, Last, th, false);
     for (int i = 0; i < N; i++) {
         MapPoint *p = Cur.mvpMapPoints[i];
-        assigned[i] = (p && p != &holder) ? (int)(p - mps.data()) : -1;
+        assigned[i] = p == &holder0 ? -3 : (p && p != &holder) ? (int)(p - mps.data()) : -1;   // -3: still the unobserved point it held (not claimed, not cleared)
     }
     return n;
 }
+#ifndef ORBX_GLUE_BUILD
 
 // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:1131-1456).
 // FeatureVectors as CSR (node ids ascending); ncam = 1 (mono / rectified stereo: NLeft == -1), 2 or 4; has_mp[idx] = GetMapPoint(idx)
@@ -426,6 +429,7 @@ int refm_search_for_triangulation(int ncam, const int *cam_off1, const ref_kp *k
     for (auto &p : pairs) match12[p.first] = (int)p.second;
     return n;
 }
+#endif
 
 // the pixel camera's epipolar predicate, for the oracle-side callback of the same test
 // KeyFrame with one camera block (NLeft == -1) over n keypoints: grid as the KeyFrame constructor copies it from the Frame
@@ -493,6 +497,7 @@ int refm_search_by_projection_reloc(const ref_kp *kps, const uint8_t *desc, int 
     }
     return nm;
 }
+#ifndef ORBX_GLUE_BUILD
 
 // ORBmatcher::SearchByProjection(KeyFrame *pKF, Sim3f &Scw, vpPoints, vpMatched, th, ratioHamming, cameraID = 0) (src/ORBmatcher.cc:668-777)
 // and, with with_kfs != 0, the overload that also records the points' keyframes (:779-893).  Scw = identity.  matched_in[idx] = vpMatched

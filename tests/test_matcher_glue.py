@@ -109,3 +109,38 @@ def test_search_by_bow_keyframe_frame(ncam):
                 outs.append((n, m))
             assert outs[0][0] == outs[1][0], (trial, chk, outs[0][0], outs[1][0])
             assert np.array_equal(outs[0][1], outs[1][1]), (trial, chk, int((outs[0][1] != outs[1][1]).sum()))
+
+
+def test_search_by_bow_keyframe_keyframe():
+    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), src/ORBmatcher.cc:1006-1129, through the glue."""
+    for S in R.bow_keyframes_scenarios():
+        for chk in (0, 1):
+            na, a = R.call_bow_keyframes(R.RM(), S, chk)
+            nb, b = R.call_bow_keyframes(G(), S, chk)
+            assert na == nb and na > 10, (S[0], chk, na, nb)
+            assert np.array_equal(a, b), (S[0], chk, int((a != b).sum()))
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+def test_search_by_projection_current_last(ncam):
+    """The tracking matcher SearchByProjection(CurrentFrame, LastFrame, th, bMono), src/ORBmatcher.cc:1985-2413: the glue computes the
+    projections on the host with the reference's expressions (poses, camera->project, Trl) and runs the search on the device."""
+    seen = [0, 0]
+    for S in R.sbp_last_scenarios(ncam):
+        na, a = R.call_sbp_last(R.RM(), S)
+        nb, b = R.call_sbp_last(G(), S)
+        assert na == nb and na > 20, (S['trial'], na, nb)
+        # (-3 = a keypoint that still holds the unobserved point it held: untouched, as opposed to claimed and cleared by the rotation filter,
+        #  which the reference sets to NULL — the glue tells them apart through orbx_search_by_projection_last_cleared)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
+        seen[0] += int((a == -3).sum()); seen[1] += int(((a == -1) & (S['occupied'] == 2)).sum())
+    assert seen[0] > 20 and seen[1] > 0
+
+
+def test_search_by_projection_relocalisation():
+    """SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2415-2535, through the glue."""
+    for S in R.reloc_scenarios():
+        na, a = R.call_reloc(R.RM(), S)
+        nb, b = R.call_reloc(G(), S)
+        assert na == nb and na > 20, (S['trial'], na, nb)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))

@@ -277,10 +277,9 @@ def test_search_by_bow_keyframe_frame(ncam):
             assert np.array_equal(a, b), (trial, chk, int((a != b).sum()))
 
 
-def test_search_by_bow_keyframe_keyframe():
-    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), src/ORBmatcher.cc:1006-1129: strict < TH_LOW, ratio test, vbMatched2, rotation filter."""
+def bow_keyframes_scenarios():
+    """(n1, n2, d1, d2, a1, a2, fv1, fv2, s1, s2) per trial: planted neighbours, duplicate rows, skipped features, rotated angles."""
     rng = np.random.default_rng(55)
-    L = RM(); Lo = O.lib()
     for trial in range(12):
         n1, n2 = int(rng.integers(300, 1500)), int(rng.integers(300, 1500))
         d2 = synth_descriptors(n2, 5900 + trial)
@@ -293,24 +292,35 @@ def test_search_by_bow_keyframe_keyframe():
         a1 = ((a2[src] + rng.choice([0, 0, 0, 30, 95, 190, 250], n1)) % 360).astype(np.float32)
         fv1, fv2 = _feature_vector(d1), _feature_vector(d2)
         s1 = (rng.random(n1) < 0.2).astype(np.uint8); s2 = (rng.random(n2) < 0.2).astype(np.uint8)
+        yield trial, n1, n2, d1, d2, a1, a2, fv1, fv2, s1, s2
+
+
+def call_bow_keyframes(L, S, chk):
+    trial, n1, n2, d1, d2, a1, a2, fv1, fv2, s1, s2 = S
+    a = np.zeros(n1, np.int32)
+    na = L.refm_search_by_bow_keyframes(len(fv1[0]), p(fv1[0]), p(fv1[1]), p(fv1[2]), len(fv2[0]), p(fv2[0]), p(fv2[1]), p(fv2[2]), p(d1), n1,
+                                        p(d2), n2, p(s1), p(s2), p(a1), p(a2), C.c_float(0.75), chk, p(a))
+    return na, a
+
+
+def test_search_by_bow_keyframe_keyframe():
+    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12), src/ORBmatcher.cc:1006-1129: strict < TH_LOW, ratio test, vbMatched2, rotation filter."""
+    L = RM(); Lo = O.lib()
+    for S in bow_keyframes_scenarios():
+        trial, n1, n2, d1, d2, a1, a2, fv1, fv2, s1, s2 = S
         for chk in (0, 1):
-            a = np.zeros(n1, np.int32); b = np.zeros(n1, np.int32)
-            na = L.refm_search_by_bow_keyframes(len(fv1[0]), p(fv1[0]), p(fv1[1]), p(fv1[2]), len(fv2[0]), p(fv2[0]), p(fv2[1]), p(fv2[2]), p(d1), n1,
-                                                p(d2), n2, p(s1), p(s2), p(a1), p(a2), C.c_float(0.75), chk, p(a))
+            b = np.zeros(n1, np.int32)
+            na, a = call_bow_keyframes(L, S, chk)
             nb = Lo.orc_search_by_bow_keyframes(len(fv1[0]), p(fv1[0]), p(fv1[1]), p(fv1[2]), len(fv2[0]), p(fv2[0]), p(fv2[1]), p(fv2[2]), p(d1), n1,
                                                 p(d2), n2, p(s1), p(s2), p(a1), p(a2), C.c_float(0.75), chk, p(b))
             assert na == nb and na > 10, (trial, chk, na, nb)
             assert np.array_equal(a, b), (trial, chk, int((a != b).sum()))
 
 
-@pytest.mark.parametrize('ncam', [1, 2, 4])
-def test_search_by_projection_current_last(ncam):
-    """SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), src/ORBmatcher.cc:1985-2413 — the tracking matcher:
-    per-camera windows (the side cameras around the LEFT projection, D6), bForward / bBackward level gates, claims in point order, the
-    empty-camera-0 `continue`, the rectified-stereo test, TH_HIGH, rotation histogram.  The reference computes the projections itself
-    from poses and a camera: identity pose, pixel camera, right camera = left + translation."""
+def sbp_last_scenarios(ncam):
+    """One dict per trial for SearchByProjection(CurrentFrame, LastFrame): planted projections, some outside the image, competing points,
+    occupied keypoints, rectified-stereo coordinates (one camera), the three direction gates, rotation filter on / off."""
     rng = np.random.default_rng(400 + ncam)
-    L = RM(); Lo = O.lib()
     w = h = 512
     for trial in range(12):
         per = [int(rng.integers(200, 700)) for _ in range(ncam)]
@@ -335,13 +345,35 @@ def test_search_by_projection_current_last(ncam):
             pd[: npts // 4] = pd[0]
         has_obs = (rng.random(npts) < 0.85).astype(np.uint8)
         occupied = (rng.random(N) < 0.05).astype(np.uint8)
+        occupied[rng.random(N) < 0.04] = 2                              # holds a point WITHOUT observations: claimable; NULL only if a claim is cleared
         mbf = np.float32(17.25)
         u_right = np.where(rng.random(N) < 0.4, k['x'] - rng.uniform(2, 40, N), -1).astype(np.float32) if ncam == 1 else None
         th = float([7.0, 15.0][trial % 2]); gate = trial % 3; chk = (trial // 3) % 2
         bounds = np.array([0, w, 0, h], np.float32)
-        a = np.zeros(N, np.int32)
-        na = L.refm_search_by_projection_last(ncam, p(cam_off), p(k), p(desc), p(bounds), p(sf), 8, p(occupied), p(u_right), npts, p(has_mp), p(px), p(py),
-                                              p(trl), C.c_float(mbf), p(octv), p(ang), p(has_obs), p(pd), C.c_float(th), gate, chk, p(a))
+        yield dict(trial=trial, ncam=ncam, cam_off=cam_off, N=N, k=k, desc=desc, sf=sf, npts=npts, px=px, py=py, trl=trl, has_mp=has_mp, octv=octv, ang=ang,
+                   pd=pd, has_obs=has_obs, occupied=occupied, mbf=mbf, u_right=u_right, th=th, gate=gate, chk=chk, bounds=bounds, w=w, h=h)
+
+
+def call_sbp_last(L, S):
+    a = np.zeros(S['N'], np.int32)
+    na = L.refm_search_by_projection_last(S['ncam'], p(S['cam_off']), p(S['k']), p(S['desc']), p(S['bounds']), p(S['sf']), 8, p(S['occupied']), p(S['u_right']),
+                                          S['npts'], p(S['has_mp']), p(S['px']), p(S['py']), p(S['trl']), C.c_float(S['mbf']), p(S['octv']), p(S['ang']),
+                                          p(S['has_obs']), p(S['pd']), C.c_float(S['th']), S['gate'], S['chk'], p(a))
+    return na, a
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+def test_search_by_projection_current_last(ncam):
+    """SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), src/ORBmatcher.cc:1985-2413 — the tracking matcher:
+    per-camera windows (the side cameras around the LEFT projection, D6), bForward / bBackward level gates, claims in point order, the
+    empty-camera-0 `continue`, the rectified-stereo test, TH_HIGH, rotation histogram.  The reference computes the projections itself
+    from poses and a camera: identity pose, pixel camera, right camera = left + translation."""
+    L = RM(); Lo = O.lib()
+    for S in sbp_last_scenarios(ncam):
+        trial, cam_off, N, k, desc, sf, npts, px, py, trl = (S[x] for x in ('trial', 'cam_off', 'N', 'k', 'desc', 'sf', 'npts', 'px', 'py', 'trl'))
+        has_mp, octv, ang, pd, has_obs, occupied, mbf, u_right, th, gate, chk, w, h = (S[x] for x in ('has_mp', 'octv', 'ang', 'pd', 'has_obs', 'occupied', 'mbf',
+                                                                                                  'u_right', 'th', 'gate', 'chk', 'w', 'h'))
+        na, a = call_sbp_last(L, S)
         # the same inputs as the array-level interface sees them
         valid = (has_mp.astype(bool) & (px >= 0) & (px <= w) & (py >= 0) & (py <= h)).astype(np.uint8)
         PX = np.stack([px, (px + trl[0]).astype(np.float32), px, px], 1).astype(np.float32)
@@ -352,12 +384,14 @@ def test_search_by_projection_current_last(ncam):
             kc = np.ascontiguousarray(k[cam_off[c]:cam_off[c + 1]])
             grids[c] = Lo.orc_grid_create(p(kc), len(kc), C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
         b = np.zeros(N, np.int32)
-        nb = Lo.orc_search_by_projection_last(ncam, p(cam_off), p(k), p(desc), grids, p(sf), p(occupied), p(u_right), npts, p(valid), p(PX), p(PY), p(pur),
+        occ1 = (occupied == 1).astype(np.uint8)                          # what the array-level interface calls occupied
+        nb = Lo.orc_search_by_projection_last(ncam, p(cam_off), p(k), p(desc), grids, p(sf), p(occ1), p(u_right), npts, p(valid), p(PX), p(PY), p(pur),
                                               p(octv), p(ang), p(has_obs), p(pd), C.c_float(th), gate, chk, 100, p(b))
         for c in range(ncam):
             Lo.orc_grid_destroy(C.c_void_p(grids[c]))
         assert na == nb and na > 20, (trial, na, nb)
-        assert np.array_equal(a, b), (trial, int((a != b).sum()))
+        assert (occupied[a == -3] == 2).all()
+        assert np.array_equal(np.where(a == -3, -1, a), b), (trial, int((a != b).sum()))
 
 
 def test_fuse_keyframe_mappoints():
@@ -426,12 +460,8 @@ def _planted_points(rng, k, desc, npts, w, h, spread=4.0):
     return src, px, py, lvl, pd
 
 
-def test_search_by_projection_relocalisation():
-    """SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2415-2535: inclusive image
-    bounds, level gate [l-1, l+1] inside GetFeaturesInArea, claims in point order, ORBdist, rotation histogram — against
-    orc_search_by_projection_last (gate 0), the function the device entry point is tested against."""
+def reloc_scenarios():
     rng = np.random.default_rng(77)
-    L = RM(); Lo = O.lib()
     w = h = 512
     for trial in range(12):
         n = int(rng.integers(300, 1500)); npts = int(rng.integers(200, 1500))
@@ -446,13 +476,31 @@ def test_search_by_projection_relocalisation():
         occupied = (rng.random(n) < 0.05).astype(np.uint8)
         th = float([10.0, 15.0][trial % 2]); orb_dist = [100, 64][trial % 2]; chk = (trial // 2) % 2
         bounds = np.array([0, w, 0, h], np.float32)
-        a = np.zeros(n, np.int32)
-        na = L.refm_search_by_projection_reloc(p(k), p(desc), n, p(bounds), p(sf), 8, p(occupied), npts, p(has_mp), p(found), p(px), p(py), p(lvl), p(ang),
-                                               p(pd), C.c_float(th), orb_dist, chk, p(a))
-        valid = (has_mp.astype(bool) & ~found.astype(bool) & (px >= 0) & (px <= w) & (py >= 0) & (py <= h)).astype(np.uint8)
-        nb, b = _oracle_last(Lo, k, desc, w, h, sf, occupied, npts, valid, px, py, lvl, ang, pd, th, 0, chk, orb_dist)
-        assert na == nb and na > 20, (trial, na, nb)
-        assert np.array_equal(a, b), (trial, int((a != b).sum()))
+        yield dict(trial=trial, n=n, npts=npts, k=k, desc=desc, sf=sf, px=px, py=py, lvl=lvl, pd=pd, ang=ang, has_mp=has_mp, found=found, occupied=occupied,
+                   th=th, orb_dist=orb_dist, chk=chk, bounds=bounds, w=w, h=h)
+
+
+def call_reloc(L, S):
+    a = np.zeros(S['n'], np.int32)
+    na = L.refm_search_by_projection_reloc(p(S['k']), p(S['desc']), S['n'], p(S['bounds']), p(S['sf']), 8, p(S['occupied']), S['npts'], p(S['has_mp']),
+                                           p(S['found']), p(S['px']), p(S['py']), p(S['lvl']), p(S['ang']), p(S['pd']), C.c_float(S['th']), S['orb_dist'],
+                                           S['chk'], p(a))
+    return na, a
+
+
+def test_search_by_projection_relocalisation():
+    """SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2415-2535: inclusive image
+    bounds, level gate [l-1, l+1] inside GetFeaturesInArea, claims in point order, ORBdist, rotation histogram — against
+    orc_search_by_projection_last (gate 0), the function the device entry point is tested against."""
+    L = RM(); Lo = O.lib()
+    for S in reloc_scenarios():
+        na, a = call_reloc(L, S)
+        px, py, w, h = S['px'], S['py'], S['w'], S['h']
+        valid = (S['has_mp'].astype(bool) & ~S['found'].astype(bool) & (px >= 0) & (px <= w) & (py >= 0) & (py <= h)).astype(np.uint8)
+        nb, b = _oracle_last(Lo, S['k'], S['desc'], w, h, S['sf'], S['occupied'], S['npts'], valid, px, py, S['lvl'], S['ang'], S['pd'], S['th'], 0, S['chk'],
+                             S['orb_dist'])
+        assert na == nb and na > 20, (S['trial'], na, nb)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
 
 
 @pytest.mark.parametrize('with_kfs', [0, 1])
