@@ -13,6 +13,9 @@
 //   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)               src/ORBmatcher.cc:1006-1129   orbx_search_by_bow_keyframes
 //   ORBmatcher::SearchByProjection(Frame &Cur, const Frame &Last, th, bMono)          :1985-2413   orbx_search_by_projection_last
 //   ORBmatcher::SearchByProjection(Frame &Cur, KeyFrame*, sAlreadyFound, th, ORBdist) :2415-2535   orbx_search_by_projection_last
+//   ORBmatcher::SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpMatched, th, ratioHamming, cameraID)              :668-777   "
+//   ORBmatcher::SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpPointsKFs, vpMatched, vpMatchedKF, th, ratio, cameraID) :779-893   "
+//   ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th, cameraID)           src/ORBmatcher.cc:1458-1647   orbx_window_best + the graph updates, in point order
 // The two projection matchers compute their projections here, on the host, with the integrator's own Eigen / Sophus types and the
 // reference's expressions (a few thousand 3-D points per call); window search, Hamming distances, ordered claims and the rotation
 // filter run on the device.
@@ -21,6 +24,7 @@
 // tests/test_matcher_glue.py compares it, call by call, with the reference's own object code (the unmodified ORBmatcher.cc compiled against the same stubs).
 #include <ORBmatcher.h>   // the REFERENCE's include/ORBmatcher.h from the include path (not the array-level header next to this file)
 
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -376,6 +380,163 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std
     for (int i = 0; i < n0; i++)
         if (assigned[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[assigned[i]];       // :2499
     return nmatches;
+}
+
+namespace {
+// The loop-closing matchers (:668-777 and :779-893 differ only in vpMatchedKF): candidate map points projected into ONE camera of a
+// KeyFrame under a Sim3, each matched to the most similar still-unmatched keypoint of that camera's block within [level - 1, level].
+int search_keyframe_sim3(KeyFrame *pKF, Sophus::Sim3f &Siw, const std::vector<MapPoint *> &vpPoints, const std::vector<KeyFrame *> *vpPointsKFs,
+                         std::vector<MapPoint *> &vpMatched, std::vector<KeyFrame *> *vpMatchedKF, int th, float ratioHamming, int cameraID) {
+    Sophus::SE3f Tiw = Sophus::SE3f(Siw.rotationMatrix(), Siw.translation() / Siw.scale());   // :682
+    Eigen::Vector3f Ow = Tiw.inverse().translation();
+    std::set<MapPoint *> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint *>(NULL));
+    // the camera's block of the KeyFrame (KeyFrame::GetFeaturesInArea, src/KeyFrame.cc:771-834: global index = block offset + grid index)
+    const std::vector<cv::KeyPoint> &keys = pKF->NLeft == -1 ? pKF->mvKeysUn : cameraID == 0 ? pKF->mvKeys : cameraID == 1 ? pKF->mvKeysRight
+                                            : cameraID == 2 ? pKF->mvKeysSideLeft : pKF->mvKeysSideRight;
+    const int off = pKF->NLeft == -1 || cameraID == 0 ? 0 : cameraID == 1 ? pKF->NLeft : cameraID == 2 ? pKF->NLeft + pKF->NRight
+                                                                                     : pKF->NLeft + pKF->NRight + pKF->NSideLeft;
+    const int n = pKF->NLeft == -1 ? pKF->N : (int)keys.size();
+    const int npts = (int)vpPoints.size();
+    if (n == 0 || npts == 0) return 0;
+    const int nlevels = (int)pKF->mvScaleFactors.size();
+    std::vector<unsigned char> valid(npts, 0), pt_desc((size_t)npts * 32, 0);
+    std::vector<float> px((size_t)npts * 4, 0.f), py((size_t)npts * 4, 0.f), angle(npts, 0.f);
+    std::vector<int> level(npts, 0);
+    for (int iMP = 0; iMP < npts; iMP++) {
+        MapPoint *pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;                        // :696
+        Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f p3Dc = Tiw * p3Dw;
+        if (p3Dc(2) < 0.0) continue;                                                    // :706
+        const Eigen::Vector2f uv = pKF->GetCamera(cameraID)->project(p3Dc);
+        if (!pKF->IsInImage(uv(0), uv(1))) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        Eigen::Vector3f PO = p3Dw - Ow;
+        const float dist = PO.norm();
+        if (dist < minDistance || dist > maxDistance) continue;
+        Eigen::Vector3f Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist) continue;                                          // :728
+        const int nPredictedLevel = pMP->PredictScale(dist, pKF);
+        if (nPredictedLevel < 0 || nPredictedLevel >= nlevels) continue;                // (the reference would index mvScaleFactors out of range)
+        valid[iMP] = 1; px[4 * iMP] = uv(0); py[4 * iMP] = uv(1); level[iMP] = nPredictedLevel;
+        const cv::Mat d = pMP->GetDescriptor();
+        memcpy(&pt_desc[(size_t)iMP * 32], d.ptr<unsigned char>(0), 32);
+    }
+    std::vector<unsigned char> occupied(n, 0), dtmp;
+    for (int i = 0; i < n; i++) occupied[i] = vpMatched[off + i] != NULL;               // :749
+    const unsigned char *desc = desc_rows(pKF->mDescriptors, dtmp) + (size_t)off * 32;
+    const int cam_off[2] = {0, n};
+    const float bounds[4] = {(float)pKF->mnMinX, (float)pKF->mnMaxX, (float)pKF->mnMinY, (float)pKF->mnMaxY};
+    const int max_dist = (int)floorf(ORBmatcher::TH_LOW * ratioHamming);                // bestDist <= TH_LOW * ratioHamming, :767
+    std::vector<int> assigned(n, -1);
+    int nmatches = 0;
+    if (orbx_search_by_projection_last(handle(), 1, cam_off, (const orbx_kp *)keys.data(), desc, bounds, pKF->mvScaleFactors.data(), nlevels, occupied.data(),
+                                       nullptr, npts, valid.data(), px.data(), py.data(), nullptr, level.data(), angle.data(), nullptr, pt_desc.data(),
+                                       (float)th, ORBX_GATE_BELOW, 0, max_dist < 0 ? 0 : max_dist > 255 ? 255 : max_dist, assigned.data(), &nmatches) != ORBX_OK)
+        die("SearchByProjection(KeyFrame, Sim3)");
+    for (int i = 0; i < n; i++)
+        if (assigned[i] >= 0) {
+            vpMatched[off + i] = vpPoints[assigned[i]];                                 // :768
+            if (vpMatchedKF) (*vpMatchedKF)[off + i] = (*vpPointsKFs)[assigned[i]];     // :888
+        }
+    return nmatches;
+}
+}  // namespace
+
+// src/ORBmatcher.cc:668-777
+int ORBmatcher::SearchByProjection(KeyFrame *pKF, Sophus::Sim3f &Siw, const std::vector<MapPoint *> &vpPoints, std::vector<MapPoint *> &vpMatched, int th,
+                                   float ratioHamming, int cameraID) {
+    return search_keyframe_sim3(pKF, Siw, vpPoints, nullptr, vpMatched, nullptr, th, ratioHamming, cameraID);
+}
+
+// src/ORBmatcher.cc:779-893
+int ORBmatcher::SearchByProjection(KeyFrame *pKF, Sophus::Sim3<float> &Siw, const std::vector<MapPoint *> &vpPoints, const std::vector<KeyFrame *> &vpPointsKFs,
+                                   std::vector<MapPoint *> &vpMatched, std::vector<KeyFrame *> &vpMatchedKF, int th, float ratioHamming, int cameraID) {
+    return search_keyframe_sim3(pKF, Siw, vpPoints, &vpPointsKFs, vpMatched, &vpMatchedKF, th, ratioHamming, cameraID);
+}
+
+// src/ORBmatcher.cc:1458-1647 — LocalMapping::SearchInNeighbors.  The searches of all points run in one device call (a search reads
+// keypoints and descriptors only, nothing the graph updates change); the updates follow in point order with the reference's
+// dynamic tests (isBad / IsInKeyFrame / GetMapPoint) evaluated at that moment.
+int ORBmatcher::Fuse(KeyFrame *pKF, const std::vector<MapPoint *> &vpMapPoints, const float th, const int cameraID) {
+    GeometricCamera *pCamera = nullptr;
+    Sophus::SE3f Tcw;
+    Eigen::Vector3f Ow;
+    switch (cameraID) {                                                                  // :1467-1495
+    case 0: Tcw = pKF->GetPose(); Ow = pKF->GetCameraCenter(); pCamera = pKF->mpCamera; break;
+    case 1: Tcw = pKF->GetRightPose(); Ow = pKF->GetRightCameraCenter(); pCamera = pKF->mpCamera2; break;
+    case 2: Tcw = pKF->GetSideLeftPose(); Ow = pKF->GetSideLeftCameraCenter(); pCamera = pKF->mpCamera3; break;
+    case 3: Tcw = pKF->GetSideRightPose(); Ow = pKF->GetSideRightCameraCenter(); pCamera = pKF->mpCamera4; break;
+    default: break;
+    }
+    const float &bf = pKF->mbf;
+    const std::vector<cv::KeyPoint> &keys = pKF->NLeft == -1 ? pKF->mvKeysUn : cameraID == 0 ? pKF->mvKeys : cameraID == 1 ? pKF->mvKeysRight
+                                            : cameraID == 2 ? pKF->mvKeysSideLeft : pKF->mvKeysSideRight;
+    const int off = pKF->NLeft == -1 || cameraID == 0 ? 0 : cameraID == 1 ? pKF->NLeft : cameraID == 2 ? pKF->NLeft + pKF->NRight
+                                                                                     : pKF->NLeft + pKF->NRight + pKF->NSideLeft;
+    const int n = pKF->NLeft == -1 ? pKF->N : (int)keys.size();
+    const int nMPs = (int)vpMapPoints.size();
+    if (!pCamera || n == 0 || nMPs == 0) return 0;
+    const int nlevels = (int)pKF->mvScaleFactors.size();
+    std::vector<unsigned char> valid(nMPs, 0), q_desc((size_t)nMPs * 32, 0);
+    std::vector<float> qx(nMPs, 0.f), qy(nMPs, 0.f), qur(nMPs, 0.f), radius(nMPs, 0.f);
+    std::vector<int> min_level(nMPs, 0), max_level(nMPs, 0);
+    for (int i = 0; i < nMPs; i++) {
+        MapPoint *pMP = vpMapPoints[i];
+        if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                    // (tested again, at its turn, below)
+        Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f p3Dc = Tcw * p3Dw;
+        if (p3Dc(2) < 0.0f) continue;                                                    // :1528
+        const float invz = 1 / p3Dc(2);
+        const Eigen::Vector2f uv = pCamera->project(p3Dc);
+        if (!pKF->IsInImage(uv(0), uv(1))) continue;
+        const float ur = uv(0) - bf * invz;                                              // :1543
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        Eigen::Vector3f PO = p3Dw - Ow;
+        const float dist3D = PO.norm();
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        Eigen::Vector3f Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist3D) continue;                                         // :1560
+        const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+        if (nPredictedLevel < 0 || nPredictedLevel >= nlevels) continue;                 // (the reference would index mvScaleFactors out of range)
+        valid[i] = 1; qx[i] = uv(0); qy[i] = uv(1); qur[i] = ur;
+        radius[i] = th * pKF->mvScaleFactors[nPredictedLevel];                           // :1568
+        min_level[i] = nPredictedLevel - 1; max_level[i] = nPredictedLevel;              // :1592
+        const cv::Mat d = pMP->GetDescriptor();
+        memcpy(&q_desc[(size_t)i * 32], d.ptr<unsigned char>(0), 32);
+    }
+    // the stereo reprojection test applies to camera 0 only (:1595): other cameras pass no right coordinates
+    const bool stereo = cameraID == 0 && (int)pKF->mvuRight.size() >= off + n;
+    std::vector<unsigned char> dtmp;
+    const float bounds[4] = {(float)pKF->mnMinX, (float)pKF->mnMaxX, (float)pKF->mnMinY, (float)pKF->mnMaxY};
+    std::vector<int> best_idx(nMPs, -1), best_dist(nMPs, 256);
+    if (orbx_window_best(handle(), (const orbx_kp *)keys.data(), desc_rows(pKF->mDescriptors, dtmp) + (size_t)off * 32, n, bounds, nullptr,
+                         stereo ? pKF->mvuRight.data() + off : nullptr, pKF->mvInvLevelSigma2.data(), nlevels, nMPs, valid.data(), qx.data(), qy.data(),
+                         qur.data(), radius.data(), min_level.data(), max_level.data(), q_desc.data(), best_idx.data(), best_dist.data()) != ORBX_OK)
+        die("Fuse(KeyFrame, MapPoints)");
+    int nFused = 0;
+    for (int i = 0; i < nMPs; i++) {
+        if (!valid[i]) continue;
+        MapPoint *pMP = vpMapPoints[i];
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                            // :1511-1517, now that the earlier points have been fused
+        if (best_idx[i] < 0 || best_dist[i] > TH_LOW) continue;                          // :1628
+        const int bestIdx = off + best_idx[i];
+        MapPoint *pMPinKF = pKF->GetMapPoint(bestIdx);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, bestIdx);
+            pKF->AddMapPoint(pMP, bestIdx);
+        }
+        nFused++;
+    }
+    return nFused;
 }
 
 }  // namespace ORB_SLAM3

@@ -277,7 +277,6 @@ int refm_search_by_bow_keyframes(int nn1, const int *nodes1, const int *ptr1, co
     return n;
 }
 
-#ifndef ORBX_GLUE_BUILD   // (not implemented by the glue: the reference body stays)
 // ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th, cameraID = 0) (src/ORBmatcher.cc:1458-1640) on a monocular /
 // rectified-stereo keyframe (NLeft == -1).  The keyframe sits at the origin with the pixel camera; map point q sits at (qx, qy, 1), so the
 // reference projects it to (qx, qy), uses invz = 1 (ur = qx - bf), predicts the level the driver is given, and searches
@@ -324,7 +323,67 @@ int refm_fuse(const ref_kp *kps, const uint8_t *desc, int n, const float *bounds
     return nf;
 }
 
-#endif
+// ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th, 0) with every branch of its graph update (:1628-1645): keyframe as in refm_fuse, but
+// kf_state[idx] chooses what the keyframe feature holds: 0 = a point with 1000 observations (the query is Replace()d by it), 1 = no point
+// (AddObservation / AddMapPoint), 2 = a point with no observations (it is Replace()d by the query), 3 = a bad point (nothing happens, still
+// counted).  dup_of[q] >= 0: query q is the SAME MapPoint object as query dup_of[q] (a point observed by two cameras appears twice in
+// GetMapPointMatches()) — once fused it is in the keyframe (or bad) and the reference skips it at its second turn.
+// Outputs: q_repl[q] = feature whose point replaced query q (-1 none; -2 - j: replaced by query j, which an earlier turn had added), kf_mp[idx] = query stored in the keyframe by AddMapPoint (-1),
+// holder_repl[idx] = query that replaced the point the feature held (-1).  Returns nFused.
+int refm_fuse_graph(const ref_kp *kps, const uint8_t *desc, int n, const float *bounds, const float *sf, const float *inv_sigma2, int nlev,
+                    const float *u_right, float bf, const uint8_t *kf_state, int nq, const uint8_t *valid, const int *dup_of, const float *qx, const float *qy,
+                    const int *level, const uint8_t *q_desc, float th, int *q_repl, int *kf_mp, int *holder_repl) {
+    set_bounds(bounds);
+    Frame F;
+    const int cam_off[2] = {0, n};
+    fill_frame(F, 1, cam_off, kps, desc, sf, nlev);
+    KeyFrame K;
+    PixelCamera cam(0);
+    K.N = n; K.mpCamera = &cam;
+    K.mvKeysUn = F.mvKeysUn; K.mvKeys = F.mvKeysUn;
+    K.mDescriptors = F.mDescriptors;
+    K.mvScaleFactors.assign(sf, sf + nlev); K.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + nlev);
+    K.mvuRight.assign(n, -1.f);
+    if (u_right) K.mvuRight.assign(u_right, u_right + n);
+    K.mbf = bf;
+    K.mnMinX = (int)bounds[0]; K.mnMaxX = (int)bounds[1]; K.mnMinY = (int)bounds[2]; K.mnMaxY = (int)bounds[3];
+    K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    K.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) K.mGrid[i][j] = F.mGrid[i][j];
+    std::vector<MapPoint> holders(n), mps(nq);
+    K.map_points.assign(n, nullptr);
+    for (int i = 0; i < n; i++) {
+        const int st = kf_state ? kf_state[i] : 0;
+        holders[i].n_obs = st == 2 ? 0 : 1000; holders[i].bad = st == 3;
+        if (st != 1) K.map_points[i] = &holders[i];
+    }
+    std::vector<MapPoint *> vp(nq, nullptr);
+    for (int q = 0; q < nq; q++) {
+        if (!valid[q]) continue;
+        if (dup_of && dup_of[q] >= 0 && dup_of[q] < q && valid[dup_of[q]]) { vp[q] = vp[dup_of[q]]; continue; }
+        MapPoint &P = mps[q];
+        P.world_pos = Eigen::Vector3f(qx[q], qy[q], 1.f);
+        P.normal = P.world_pos / P.world_pos.norm();
+        P.predicted_level = level[q];
+        P.n_obs = 1;
+        P.descriptor = desc_mat(q_desc + (size_t)q * 32, 1);
+        vp[q] = &P;
+    }
+    ORBmatcher matcher(0.6f, true);
+    const int nf = matcher.Fuse(&K, vp, th, 0);
+    for (int q = 0; q < nq; q++) {
+        MapPoint *r = vp[q] == &mps[q] ? mps[q].replaced_by : nullptr;
+        q_repl[q] = !r ? -1 : (r >= holders.data() && r < holders.data() + n) ? (int)(r - holders.data()) : -2 - (int)(r - mps.data());   // (-2 - j: by query j, added earlier)
+    }
+    for (int i = 0; i < n; i++) {
+        MapPoint *m = K.map_points[i];
+        kf_mp[i] = (m && m >= mps.data() && m < mps.data() + nq) ? (int)(m - mps.data()) : -1;
+        MapPoint *r = holders[i].replaced_by;
+        holder_repl[i] = (r && r >= mps.data() && r < mps.data() + nq) ? (int)(r - mps.data()) : -1;
+    }
+    return nf;
+}
+
 // ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) (src/ORBmatcher.cc:1985-2413), the tracking
 // matcher.  Current frame as in refm_search_by_projection.  Last frame: npts keypoints in the Nleft == -1 layout; has_mp[i] = the point
 // exists and is no outlier; its map point sits at (px[i], py[i], 1) in world = camera coordinates (Tcw = I, pixel camera), so the
@@ -497,7 +556,6 @@ int refm_search_by_projection_reloc(const ref_kp *kps, const uint8_t *desc, int 
     }
     return nm;
 }
-#ifndef ORBX_GLUE_BUILD
 
 // ORBmatcher::SearchByProjection(KeyFrame *pKF, Sim3f &Scw, vpPoints, vpMatched, th, ratioHamming, cameraID = 0) (src/ORBmatcher.cc:668-777)
 // and, with with_kfs != 0, the overload that also records the points' keyframes (:779-893).  Scw = identity.  matched_in[idx] = vpMatched
@@ -537,6 +595,7 @@ int refm_search_by_projection_sim3(const ref_kp *kps, const uint8_t *desc, int n
     if (matched_kf_ok) *matched_kf_ok = ok;
     return nm;
 }
+#ifndef ORBX_GLUE_BUILD
 
 // ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1771-1983): T1w = T2w = I, S12 = identity, fx = fy = 1,
 // cx = cy = 0, so map point i1 of KF1 at (u1, v1, 1) projects to (u1, v1) in KF2 and vice versa.  pre12[i1] = keypoint of KF2 that

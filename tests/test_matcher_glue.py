@@ -144,3 +144,26 @@ def test_search_by_projection_relocalisation():
         nb, b = R.call_reloc(G(), S)
         assert na == nb and na > 20, (S['trial'], na, nb)
         assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
+
+
+@pytest.mark.parametrize('with_kfs', [0, 1])
+def test_search_by_projection_keyframe_sim3(with_kfs):
+    """Both loop-closing overloads SearchByProjection(KeyFrame*, Sim3f&, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th, ratioHamming,
+    cameraID), src/ORBmatcher.cc:668-893, through the glue (incl. the vpMatchedKF bookkeeping of the second one)."""
+    for S in R.kf_sim3_scenarios(with_kfs):
+        na, a, oka = R.call_kf_sim3(R.RM(), S)
+        nb, b, okb = R.call_kf_sim3(G(), S)
+        assert na == nb and na > 20, (S['trial'], na, nb)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
+        assert oka == okb and (not with_kfs or okb == 1)
+
+
+def test_fuse_keyframe_mappoints():
+    """Fuse(KeyFrame*, vpMapPoints, th, cameraID), src/ORBmatcher.cc:1458-1647, through the glue: one device call for all searches, then the
+    graph updates in point order — Replace in both directions, AddObservation / AddMapPoint, bad points, a map point that is listed twice."""
+    for S in R.fuse_graph_scenarios():
+        ra = R.call_fuse_graph(R.RM(), S)
+        rb = R.call_fuse_graph(G(), S)
+        assert ra[0] == rb[0] and ra[0] > 20, (S['trial'], ra[0], rb[0])
+        for x, y, name in zip(ra[1:], rb[1:], ('q_repl', 'kf_mp', 'holder_repl')):
+            assert np.array_equal(x, y), (S['trial'], name, int((x != y).sum()))

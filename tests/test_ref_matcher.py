@@ -435,6 +435,57 @@ def test_fuse_keyframe_mappoints():
         assert np.array_equal(a, exp), (trial, int((a != exp).sum()))
 
 
+def fuse_graph_scenarios():
+    """Fuse with every branch of the graph update: keyframe features holding a well-observed point / nothing / an unobserved point / a bad
+    point, and map points that appear twice in the candidate list."""
+    rng = np.random.default_rng(67)
+    w, h = 640, 480
+    for trial in range(10):
+        n = int(rng.integers(300, 2000)); nq = int(rng.integers(200, 1500))
+        k = make_kps(n, rng, w, h, lattice=5 if trial % 2 else None)
+        desc = synth_descriptors(n, 6700 + trial)
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        inv_s2 = (np.float32(1.0) / (sf * sf)).astype(np.float32)
+        src = rng.integers(0, n, nq)
+        qx = (k['x'][src] + rng.uniform(-2.5, 2.5, nq)).astype(np.float32); qy = (k['y'][src] + rng.uniform(-2.5, 2.5, nq)).astype(np.float32)
+        qx[rng.random(nq) < 0.05] = np.float32(-20.0)
+        lvl = np.clip(k['octave'][src] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
+        qd = desc[src] ^ np.packbits(rng.random((nq, 256)) < 0.07, axis=1, bitorder='little')
+        qd[::6] = synth_descriptors(len(qd[::6]), 31 + trial)
+        bf = np.float32(19.5)
+        u_right = np.where(rng.random(n) < 0.5, k['x'] - bf + rng.uniform(-1.5, 1.5, n), -1).astype(np.float32) if trial % 2 == 0 else None
+        valid = (rng.random(nq) < 0.95).astype(np.uint8)
+        kf_state = rng.choice([0, 1, 2, 3], n, p=[0.4, 0.3, 0.2, 0.1]).astype(np.uint8)
+        dup_of = np.full(nq, -1, np.int32)
+        for q in rng.choice(np.arange(1, nq), nq // 10, replace=False):
+            dup_of[q] = int(rng.integers(0, q))
+        th = float([3.0, 5.0][trial % 2])
+        bounds = np.array([0, w, 0, h], np.float32)
+        yield dict(trial=trial, n=n, nq=nq, k=k, desc=desc, sf=sf, inv_s2=inv_s2, qx=qx, qy=qy, lvl=lvl, qd=qd, bf=bf, u_right=u_right, valid=valid,
+                   kf_state=kf_state, dup_of=dup_of, th=th, bounds=bounds)
+
+
+def call_fuse_graph(L, S):
+    q_repl = np.zeros(S['nq'], np.int32); kf_mp = np.zeros(S['n'], np.int32); holder_repl = np.zeros(S['n'], np.int32)
+    nf = L.refm_fuse_graph(p(S['k']), p(S['desc']), S['n'], p(S['bounds']), p(S['sf']), p(S['inv_s2']), 8, p(S['u_right']), C.c_float(S['bf']), p(S['kf_state']),
+                           S['nq'], p(S['valid']), p(S['dup_of']), p(S['qx']), p(S['qy']), p(S['lvl']), p(S['qd']), C.c_float(S['th']), p(q_repl), p(kf_mp),
+                           p(holder_repl))
+    return nf, q_repl, kf_mp, holder_repl
+
+
+def test_fuse_graph_updates_reference_runs_every_branch():
+    """(sanity of the scenario generator on the reference itself: each of the four outcomes occurs)"""
+    L = RM()
+    seen = np.zeros(3, np.int64)
+    for S in fuse_graph_scenarios():
+        nf, q_repl, kf_mp, holder_repl = call_fuse_graph(L, S)
+        assert nf > 20
+        assert ((kf_mp >= 0) <= (S['kf_state'] == 1)).all() and ((holder_repl >= 0) <= (S['kf_state'] == 2)).all()
+        assert (S['kf_state'][q_repl[q_repl >= 0]] == 0).all() and (q_repl <= -2).any()
+        seen += [(q_repl >= 0).sum(), (kf_mp >= 0).sum(), (holder_repl >= 0).sum()]
+    assert (seen > 50).all(), seen
+
+
 def _oracle_last(Lo, k, desc, w, h, sf, occupied, npts, valid, px, py, octv, ang, pd, th, gate, chk, max_dist):
     """orc_search_by_projection_last for one camera block (what orbx_search_by_projection_last is tested against on the GPU)."""
     n = len(k)
@@ -503,13 +554,8 @@ def test_search_by_projection_relocalisation():
         assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
 
 
-@pytest.mark.parametrize('with_kfs', [0, 1])
-def test_search_by_projection_keyframe_sim3(with_kfs):
-    """Both SearchByProjection(KeyFrame*, Sim3f&, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th, ratioHamming, cameraID) overloads,
-    src/ORBmatcher.cc:668-893: IsInImage (half-open), KeyFrame::GetFeaturesInArea without level gate, the [l-1, l] gate in the loop,
-    vpMatched as occupancy, TH_LOW * ratioHamming — against orc_search_by_projection_last (gate 3)."""
+def kf_sim3_scenarios(with_kfs):
     rng = np.random.default_rng(88 + with_kfs)
-    L = RM(); Lo = O.lib()
     w, h = 640, 480
     for trial in range(10):
         n = int(rng.integers(300, 1500)); npts = int(rng.integers(200, 1500))
@@ -524,16 +570,33 @@ def test_search_by_projection_keyframe_sim3(with_kfs):
         skip[np.cumsum(skip == 2) > int(matched_in.sum())] = 0                # every 'already found' point needs an occupied keypoint to sit in
         th = [4, 8][trial % 2]; ratio = [1.0, 0.8, 0.9][trial % 3]
         bounds = np.array([0, w, 0, h], np.float32)
-        a = np.zeros(n, np.int32); ok = C.c_int(0)
-        na = L.refm_search_by_projection_sim3(p(k), p(desc), n, p(bounds), p(sf), 8, p(matched_in), npts, p(skip), p(px), p(py), p(lvl), p(pd), th,
-                                              C.c_float(ratio), with_kfs, p(a), C.byref(ok))
-        valid = ((skip == 0) & (px >= 0) & (px < w) & (py >= 0) & (py < h)).astype(np.uint8)
-        max_dist = int(np.floor(np.float32(50) * np.float32(ratio)))
-        ang = np.zeros(npts, np.float32)
-        nb, b = _oracle_last(Lo, k, desc, w, h, sf, matched_in, npts, valid, px, py, lvl, ang, pd, float(th), 3, 0, max_dist)
-        assert na == nb and na > 20, (trial, na, nb)
-        assert np.array_equal(a, b), (trial, int((a != b).sum()))
-        assert not with_kfs or ok.value == 1
+        yield dict(trial=trial, n=n, npts=npts, k=k, desc=desc, sf=sf, px=px, py=py, lvl=lvl, pd=pd, matched_in=matched_in, skip=skip, th=th, ratio=ratio,
+                   bounds=bounds, w=w, h=h, with_kfs=with_kfs)
+
+
+def call_kf_sim3(L, S):
+    a = np.zeros(S['n'], np.int32); ok = C.c_int(0)
+    na = L.refm_search_by_projection_sim3(p(S['k']), p(S['desc']), S['n'], p(S['bounds']), p(S['sf']), 8, p(S['matched_in']), S['npts'], p(S['skip']), p(S['px']),
+                                          p(S['py']), p(S['lvl']), p(S['pd']), S['th'], C.c_float(S['ratio']), S['with_kfs'], p(a), C.byref(ok))
+    return na, a, ok.value
+
+
+@pytest.mark.parametrize('with_kfs', [0, 1])
+def test_search_by_projection_keyframe_sim3(with_kfs):
+    """Both SearchByProjection(KeyFrame*, Sim3f&, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th, ratioHamming, cameraID) overloads,
+    src/ORBmatcher.cc:668-893: IsInImage (half-open), KeyFrame::GetFeaturesInArea without level gate, the [l-1, l] gate in the loop,
+    vpMatched as occupancy, TH_LOW * ratioHamming — against orc_search_by_projection_last (gate 3)."""
+    L = RM(); Lo = O.lib()
+    for S in kf_sim3_scenarios(with_kfs):
+        na, a, ok = call_kf_sim3(L, S)
+        px, py, w, h = S['px'], S['py'], S['w'], S['h']
+        valid = ((S['skip'] == 0) & (px >= 0) & (px < w) & (py >= 0) & (py < h)).astype(np.uint8)
+        max_dist = int(np.floor(np.float32(50) * np.float32(S['ratio'])))
+        ang = np.zeros(S['npts'], np.float32)
+        nb, b = _oracle_last(Lo, S['k'], S['desc'], w, h, S['sf'], S['matched_in'], S['npts'], valid, px, py, S['lvl'], ang, S['pd'], float(S['th']), 3, 0, max_dist)
+        assert na == nb and na > 20, (S['trial'], na, nb)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
+        assert not with_kfs or ok == 1
 
 
 def test_search_by_sim3():
