@@ -16,6 +16,8 @@
 //   ORBmatcher::SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpMatched, th, ratioHamming, cameraID)              :668-777   "
 //   ORBmatcher::SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpPointsKFs, vpMatched, vpMatchedKF, th, ratio, cameraID) :779-893   "
 //   ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th, cameraID)           src/ORBmatcher.cc:1458-1647   orbx_window_best + the graph updates, in point order
+//   ORBmatcher::Fuse(KeyFrame*, Sim3f&, vpPoints, th, vpReplacePoint) src/ORBmatcher.cc:1648-1769  orbx_window_best per camera + the updates
+//   ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th)       src/ORBmatcher.cc:1771-1983   orbx_search_by_sim3
 // The two projection matchers compute their projections here, on the host, with the integrator's own Eigen / Sophus types and the
 // reference's expressions (a few thousand 3-D points per call); window search, Hamming distances, ordered claims and the rotation
 // filter run on the device.
@@ -30,6 +32,7 @@
 #include <string.h>
 
 #include <set>
+#include <tuple>
 #include <vector>
 
 #include "orbx.h"
@@ -537,6 +540,162 @@ int ORBmatcher::Fuse(KeyFrame *pKF, const std::vector<MapPoint *> &vpMapPoints, 
         nFused++;
     }
     return nFused;
+}
+
+namespace {
+// one camera's block of a KeyFrame: its keypoints, the offset of its first feature in the global order, its size
+const std::vector<cv::KeyPoint> &keyframe_block(KeyFrame *pKF, int cameraID, int &off, int &n) {
+    const std::vector<cv::KeyPoint> &keys = pKF->NLeft == -1 ? pKF->mvKeysUn : cameraID == 0 ? pKF->mvKeys : cameraID == 1 ? pKF->mvKeysRight
+                                            : cameraID == 2 ? pKF->mvKeysSideLeft : pKF->mvKeysSideRight;
+    off = pKF->NLeft == -1 || cameraID == 0 ? 0 : cameraID == 1 ? pKF->NLeft : cameraID == 2 ? pKF->NLeft + pKF->NRight : pKF->NLeft + pKF->NRight + pKF->NSideLeft;
+    n = pKF->NLeft == -1 ? (cameraID == 0 ? pKF->N : 0) : (int)keys.size();     // (a single-camera keyframe has empty grids for cameras 1-3)
+    return keys;
+}
+}  // namespace
+
+// src/ORBmatcher.cc:1648-1769 — the loop-closing fuse: every candidate point is searched in all four cameras of the keyframe
+int ORBmatcher::Fuse(KeyFrame *pKF, Sophus::Sim3f &Scw, const std::vector<MapPoint *> &vpPoints, float th, std::vector<MapPoint *> &vpReplacePoint) {
+    const std::set<MapPoint *> spAlreadyFound = pKF->GetMapPoints();
+    const int nPoints = (int)vpPoints.size();
+    if (nPoints == 0) return 0;
+    const int nlevels = (int)pKF->mvScaleFactors.size();
+    std::vector<unsigned char> usable(nPoints, 0), q_desc((size_t)nPoints * 32, 0), dtmp;
+    for (int i = 0; i < nPoints; i++) {
+        MapPoint *pMP = vpPoints[i];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;                         // :1675
+        usable[i] = 1;
+        const cv::Mat d = pMP->GetDescriptor();
+        memcpy(&q_desc[(size_t)i * 32], d.ptr<unsigned char>(0), 32);
+    }
+    const unsigned char *desc = desc_rows(pKF->mDescriptors, dtmp);
+    const float bounds[4] = {(float)pKF->mnMinX, (float)pKF->mnMaxX, (float)pKF->mnMinY, (float)pKF->mnMaxY};
+    std::vector<unsigned char> valid[4];
+    std::vector<int> best_idx[4], best_dist[4];
+    int off[4] = {0, 0, 0, 0};
+    Sophus::SE3f Tlw = Sophus::SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale());   // :1693
+    for (int camId = 0; camId < 4; camId++) {
+        int n;
+        const std::vector<cv::KeyPoint> &keys = keyframe_block(pKF, camId, off[camId], n);
+        valid[camId].assign(nPoints, 0); best_idx[camId].assign(nPoints, -1); best_dist[camId].assign(nPoints, 256);
+        if (n == 0) continue;
+        Sophus::SE3f Tiw = (camId == 0) ? Tlw : (camId == 1) ? pKF->GetRelativePoseTrl() * Tlw : (camId == 2) ? pKF->GetRelativePoseTsll() * Tlw
+                                                                                               : pKF->GetRelativePoseTsrl() * Tlw;
+        Eigen::Vector3f Ow = Tiw.inverse().translation();
+        std::vector<float> qx(nPoints, 0.f), qy(nPoints, 0.f), radius(nPoints, 0.f);
+        std::vector<int> min_level(nPoints, 0), max_level(nPoints, 0);
+        for (int i = 0; i < nPoints; i++) {
+            if (!usable[i]) continue;
+            MapPoint *pMP = vpPoints[i];
+            Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+            Eigen::Vector3f p3Dc = Tiw * p3Dw;
+            if (p3Dc(2) < 0.0f) continue;                                                // :1707
+            const Eigen::Vector2f uv = pKF->GetCamera(camId)->project(p3Dc);
+            if (!pKF->IsInImage(uv(0), uv(1))) continue;
+            Eigen::Vector3f PO = p3Dw - Ow;
+            const float dist3D = PO.norm();
+            const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);                  // (no distance / viewing-angle gate in this overload)
+            if (nPredictedLevel < 0 || nPredictedLevel >= nlevels) continue;
+            valid[camId][i] = 1; qx[i] = uv(0); qy[i] = uv(1);
+            radius[i] = th * pKF->mvScaleFactors[nPredictedLevel];
+            min_level[i] = nPredictedLevel - 1; max_level[i] = nPredictedLevel;
+        }
+        if (orbx_window_best(handle(), (const orbx_kp *)keys.data(), desc + (size_t)off[camId] * 32, n, bounds, nullptr, nullptr, nullptr, nlevels, nPoints,
+                             valid[camId].data(), qx.data(), qy.data(), nullptr, radius.data(), min_level.data(), max_level.data(), q_desc.data(),
+                             best_idx[camId].data(), best_dist[camId].data()) != ORBX_OK)
+            die("Fuse(KeyFrame, Sim3)");
+    }
+    int nFused = 0;
+    for (int iMP = 0; iMP < nPoints; iMP++) {
+        if (!usable[iMP]) continue;
+        MapPoint *pMP = vpPoints[iMP];
+        for (int camId = 0; camId < 4; camId++) {
+            if (!valid[camId][iMP] || best_idx[camId][iMP] < 0 || best_dist[camId][iMP] > TH_LOW) continue;   // :1750
+            const int bestIdx = off[camId] + best_idx[camId][iMP];
+            MapPoint *pMPinKF = pKF->GetMapPoint(bestIdx);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF;
+            } else {
+                pMP->AddObservation(pKF, bestIdx);
+                pKF->AddMapPoint(pMP, bestIdx);
+            }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+
+// src/ORBmatcher.cc:1771-1983
+int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12, const Sophus::Sim3f &S12, const float th) {
+    const float &fx = pKF1->fx;
+    const float &fy = pKF1->fy;
+    const float &cx = pKF1->cx;
+    const float &cy = pKF1->cy;
+    Sophus::SE3f T1w = pKF1->GetPose();
+    Sophus::SE3f T2w = pKF2->GetPose();
+    Sophus::Sim3f S21 = S12.inverse();
+    const std::vector<MapPoint *> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size();
+    const std::vector<MapPoint *> vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N2 = (int)vpMapPoints2.size();
+    if (N1 == 0 || N2 == 0) return 0;
+    std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+    for (int i = 0; i < N1; i++) {                                                       // :1798-1806
+        MapPoint *pMP = vpMatches12[i];
+        if (pMP) {
+            vbAlreadyMatched1[i] = true;
+            int idx2 = std::get<0>(pMP->GetIndexInKeyFrame(pKF2));
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+        }
+    }
+    // one direction: the points of `from` (pose Tfw) mapped by S into the camera of `to`
+    auto side = [&](const std::vector<MapPoint *> &pts, const std::vector<bool> &already, const Sophus::SE3f &Tfw, const Sophus::Sim3f &S, KeyFrame *to,
+                    std::vector<unsigned char> &valid, std::vector<float> &u, std::vector<float> &v, std::vector<float> &radius, std::vector<int> &level,
+                    std::vector<unsigned char> &mp_desc) {
+        const int n = (int)pts.size(), nlevels = (int)to->mvScaleFactors.size();
+        valid.assign(n, 0); u.assign(n, 0.f); v.assign(n, 0.f); radius.assign(n, 0.f); level.assign(n, 0); mp_desc.assign((size_t)n * 32, 0);
+        for (int i = 0; i < n; i++) {
+            MapPoint *pMP = pts[i];
+            if (!pMP || already[i]) continue;
+            if (pMP->isBad()) continue;
+            Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+            Eigen::Vector3f p3Dcf = Tfw * p3Dw;
+            Eigen::Vector3f p3Dct = S * p3Dcf;
+            if (p3Dct(2) < 0.0) continue;                                                // :1827
+            const float invz = 1.0 / p3Dct(2);
+            const float x = p3Dct(0) * invz;
+            const float y = p3Dct(1) * invz;
+            const float uu = fx * x + cx;
+            const float vv = fy * y + cy;
+            if (!to->IsInImage(uu, vv)) continue;
+            const float maxDistance = pMP->GetMaxDistanceInvariance();
+            const float minDistance = pMP->GetMinDistanceInvariance();
+            const float dist3D = p3Dct.norm();
+            if (dist3D < minDistance || dist3D > maxDistance) continue;
+            const int nPredictedLevel = pMP->PredictScale(dist3D, to);
+            if (nPredictedLevel < 0 || nPredictedLevel >= nlevels) continue;
+            valid[i] = 1; u[i] = uu; v[i] = vv; level[i] = nPredictedLevel;
+            radius[i] = th * to->mvScaleFactors[nPredictedLevel];
+            const cv::Mat d = pMP->GetDescriptor();
+            memcpy(&mp_desc[(size_t)i * 32], d.ptr<unsigned char>(0), 32);
+        }
+    };
+    std::vector<unsigned char> valid1, valid2, md1, md2, t1, t2;
+    std::vector<float> u1, v1, r1, u2, v2, r2;
+    std::vector<int> l1, l2;
+    side(vpMapPoints1, vbAlreadyMatched1, T1w, S21, pKF2, valid1, u1, v1, r1, l1, md1);  // KF1's points searched in KF2 (:1812-1887)
+    side(vpMapPoints2, vbAlreadyMatched2, T2w, S12, pKF1, valid2, u2, v2, r2, l2, md2);  // KF2's points searched in KF1 (:1890-1965)
+    const float b1[4] = {(float)pKF1->mnMinX, (float)pKF1->mnMaxX, (float)pKF1->mnMinY, (float)pKF1->mnMaxY};
+    const float b2[4] = {(float)pKF2->mnMinX, (float)pKF2->mnMaxX, (float)pKF2->mnMinY, (float)pKF2->mnMaxY};
+    if ((int)pKF1->mvKeysUn.size() < N1 || (int)pKF2->mvKeysUn.size() < N2) { fprintf(stderr, "ORBmatcher::SearchBySim3: fewer undistorted keypoints than map point slots\n"); abort(); }
+    std::vector<int> match12(N1, -1);
+    int nFound = 0;
+    if (orbx_search_by_sim3(handle(), (const orbx_kp *)pKF1->mvKeysUn.data(), desc_rows(pKF1->mDescriptors, t1), N1, b1, (const orbx_kp *)pKF2->mvKeysUn.data(),
+                            desc_rows(pKF2->mDescriptors, t2), N2, b2, valid1.data(), u1.data(), v1.data(), r1.data(), l1.data(), md1.data(), valid2.data(),
+                            u2.data(), v2.data(), r2.data(), l2.data(), md2.data(), match12.data(), &nFound) != ORBX_OK)
+        die("SearchBySim3");
+    for (int i1 = 0; i1 < N1; i1++)
+        if (match12[i1] >= 0) vpMatches12[i1] = vpMapPoints2[match12[i1]];              // :1975
+    return nFound;
 }
 
 }  // namespace ORB_SLAM3

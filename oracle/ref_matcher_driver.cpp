@@ -595,7 +595,6 @@ int refm_search_by_projection_sim3(const ref_kp *kps, const uint8_t *desc, int n
     if (matched_kf_ok) *matched_kf_ok = ok;
     return nm;
 }
-#ifndef ORBX_GLUE_BUILD
 
 // ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th) (src/ORBmatcher.cc:1771-1983): T1w = T2w = I, S12 = identity, fx = fy = 1,
 // cx = cy = 0, so map point i1 of KF1 at (u1, v1, 1) projects to (u1, v1) in KF2 and vice versa.  pre12[i1] = keypoint of KF2 that
@@ -656,7 +655,6 @@ int refm_fuse_sim3(const ref_kp *kps, const uint8_t *desc, int n, const float *b
     return nf;
 }
 
-#endif   // !ORBX_GLUE_BUILD (the glue implements the methods the tracking / mapping front end calls: tests/test_matcher_glue.py)
 int refm_pair_hash(float x1, float y1, float x2, float y2, int id1, int id2) { return PixelCamera::pair_hash(x1, y1, x2, y2, id1, id2) ? 1 : 0; }
 
 }  // extern "C"

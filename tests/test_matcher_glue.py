@@ -167,3 +167,23 @@ def test_fuse_keyframe_mappoints():
         assert ra[0] == rb[0] and ra[0] > 20, (S['trial'], ra[0], rb[0])
         for x, y, name in zip(ra[1:], rb[1:], ('q_repl', 'kf_mp', 'holder_repl')):
             assert np.array_equal(x, y), (S['trial'], name, int((x != y).sum()))
+
+
+def test_search_by_sim3():
+    """SearchBySim3(pKF1, pKF2, vpMatches12, S12, th), src/ORBmatcher.cc:1771-1983, through the glue: both projection loops on the host,
+    both window searches and the agreement check on the device."""
+    for S in R.sim3_scenarios():
+        na, a = R.call_sim3(R.RM(), S)
+        nb, b = R.call_sim3(G(), S)
+        assert na == nb and na > 20, (S['trial'], na, nb)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
+
+
+def test_fuse_keyframe_sim3():
+    """Fuse(KeyFrame*, Sim3f&, vpPoints, th, vpReplacePoint), src/ORBmatcher.cc:1648-1769, through the glue: one device search per camera of
+    the keyframe, then vpReplacePoint / AddObservation / AddMapPoint in point order."""
+    for S in R.fuse_sim3_scenarios():
+        na, a = R.call_fuse_sim3(R.RM(), S)
+        nb, b = R.call_fuse_sim3(G(), S)
+        assert na == nb and na > 20, (S['trial'], na, nb)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))

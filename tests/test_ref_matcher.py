@@ -599,11 +599,8 @@ def test_search_by_projection_keyframe_sim3(with_kfs):
         assert not with_kfs or ok == 1
 
 
-def test_search_by_sim3():
-    """ORBmatcher::SearchBySim3, src/ORBmatcher.cc:1771-1983: the already-matched bookkeeping through GetIndexInKeyFrame, the two window
-    searches (TH_HIGH, [l-1, l] gate, first minimum) and the agreement check — against orc_search_by_sim3."""
+def sim3_scenarios():
     rng = np.random.default_rng(99)
-    L = RM(); Lo = O.lib()
     w, h = 640, 480
     for trial in range(10):
         n1 = int(rng.integers(300, 1200)); n2 = int(rng.integers(300, 1200))
@@ -629,15 +626,32 @@ def test_search_by_sim3():
         pre12[pre12 == -1] = -1
         th = float([7.5, 10.0][trial % 2])
         bounds = np.array([0, w, 0, h], np.float32)
-        a = np.zeros(n1, np.int32)
-        na = L.refm_search_by_sim3(p(k1), p(d1), n1, p(k2), p(d2), n2, p(bounds), p(sf), 8, p(has1), p(u1), p(v1), p(l1), p(m1), p(has2), p(u2), p(v2),
-                                   p(l2), p(m2), p(pre12), C.c_float(th), p(a))
+        yield dict(trial=trial, n1=n1, n2=n2, sf=sf, k1=k1, k2=k2, d1=d1, d2=d2, has1=has1, has2=has2, u1=u1, v1=v1, u2=u2, v2=v2, l1=l1, l2=l2, m1=m1, m2=m2,
+                   pre12=pre12, th=th, bounds=bounds, w=w, h=h)
+
+
+def call_sim3(L, S):
+    a = np.zeros(S['n1'], np.int32)
+    na = L.refm_search_by_sim3(p(S['k1']), p(S['d1']), S['n1'], p(S['k2']), p(S['d2']), S['n2'], p(S['bounds']), p(S['sf']), 8, p(S['has1']), p(S['u1']),
+                               p(S['v1']), p(S['l1']), p(S['m1']), p(S['has2']), p(S['u2']), p(S['v2']), p(S['l2']), p(S['m2']), p(S['pre12']),
+                               C.c_float(S['th']), p(a))
+    return na, a
+
+
+def test_search_by_sim3():
+    """ORBmatcher::SearchBySim3, src/ORBmatcher.cc:1771-1983: the already-matched bookkeeping through GetIndexInKeyFrame, the two window
+    searches (TH_HIGH, [l-1, l] gate, first minimum) and the agreement check — against orc_search_by_sim3."""
+    L = RM(); Lo = O.lib()
+    for S in sim3_scenarios():
+        na, a = call_sim3(L, S)
+        n1, n2, w, h, sf, th = S['n1'], S['n2'], S['w'], S['h'], S['sf'], S['th']
+        k1, k2, d1, d2, u1, v1, u2, v2, l1, l2, m1, m2, pre12 = (S[x] for x in ('k1', 'k2', 'd1', 'd2', 'u1', 'v1', 'u2', 'v2', 'l1', 'l2', 'm1', 'm2', 'pre12'))
         already1 = pre12 != -1                                                 # vpMatches12[i] != NULL
         already2 = np.zeros(n2, bool)
         idx2 = pre12[(pre12 >= 0) & (pre12 < n2)]
         already2[idx2] = True
-        val1 = (has1.astype(bool) & ~already1 & (u1 >= 0) & (u1 < w) & (v1 >= 0) & (v1 < h)).astype(np.uint8)
-        val2 = (has2.astype(bool) & ~already2 & (u2 >= 0) & (u2 < w) & (v2 >= 0) & (v2 < h)).astype(np.uint8)
+        val1 = (S['has1'].astype(bool) & ~already1 & (u1 >= 0) & (u1 < w) & (v1 >= 0) & (v1 < h)).astype(np.uint8)
+        val2 = (S['has2'].astype(bool) & ~already2 & (u2 >= 0) & (u2 < w) & (v2 >= 0) & (v2 < h)).astype(np.uint8)
         r1 = (np.float32(th) * sf[l1]).astype(np.float32); r2 = (np.float32(th) * sf[l2]).astype(np.float32)
         g1 = Lo.orc_grid_create(p(k1), n1, C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
         g2 = Lo.orc_grid_create(p(k2), n2, C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
@@ -645,15 +659,12 @@ def test_search_by_sim3():
         nb = Lo.orc_search_by_sim3(C.c_void_p(g1), p(k1), p(d1), n1, C.c_void_p(g2), p(k2), p(d2), n2, p(val1), p(u1), p(v1), p(r1), p(l1), p(m1),
                                    p(val2), p(u2), p(v2), p(r2), p(l2), p(m2), p(b))
         Lo.orc_grid_destroy(C.c_void_p(g1)); Lo.orc_grid_destroy(C.c_void_p(g2))
-        assert na == nb and na > 20, (trial, na, nb)
-        assert np.array_equal(a, b), (trial, int((a != b).sum()))
+        assert na == nb and na > 20, (S['trial'], na, nb)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
 
 
-def test_fuse_keyframe_sim3():
-    """ORBmatcher::Fuse(KeyFrame*, Sim3f &Scw, vpPoints, th, vpReplacePoint), src/ORBmatcher.cc:1648-1769, the loop-closing fuse: the search
-    loop without reprojection gates ([l-1, l] level gate, first minimum, TH_LOW) — against orc_window_best."""
+def fuse_sim3_scenarios():
     rng = np.random.default_rng(111)
-    L = RM(); Lo = O.lib()
     w, h = 640, 480
     for trial in range(10):
         n = int(rng.integers(300, 2000)); nq = int(rng.integers(200, 1500))
@@ -666,15 +677,30 @@ def test_fuse_keyframe_sim3():
         valid = (rng.random(nq) < 0.95).astype(np.uint8)
         th = float([3.0, 5.0][trial % 2])
         bounds = np.array([0, w, 0, h], np.float32)
-        a = np.zeros(nq, np.int32)
-        nf = L.refm_fuse_sim3(p(k), p(desc), n, p(bounds), p(sf), 8, p(has_mp), nq, p(valid), p(qx), p(qy), p(lvl), p(qd), C.c_float(th), p(a))
-        v2 = (valid.astype(bool) & (qx >= 0) & (qx < w) & (qy >= 0) & (qy < h)).astype(np.uint8)
-        radius = (np.float32(th) * sf[lvl]).astype(np.float32)
+        yield dict(trial=trial, n=n, nq=nq, k=k, desc=desc, sf=sf, qx=qx, qy=qy, lvl=lvl, qd=qd, has_mp=has_mp, valid=valid, th=th, bounds=bounds, w=w, h=h)
+
+
+def call_fuse_sim3(L, S):
+    a = np.zeros(S['nq'], np.int32)
+    nf = L.refm_fuse_sim3(p(S['k']), p(S['desc']), S['n'], p(S['bounds']), p(S['sf']), 8, p(S['has_mp']), S['nq'], p(S['valid']), p(S['qx']), p(S['qy']),
+                          p(S['lvl']), p(S['qd']), C.c_float(S['th']), p(a))
+    return nf, a
+
+
+def test_fuse_keyframe_sim3():
+    """ORBmatcher::Fuse(KeyFrame*, Sim3f &Scw, vpPoints, th, vpReplacePoint), src/ORBmatcher.cc:1648-1769, the loop-closing fuse: the search
+    loop without reprojection gates ([l-1, l] level gate, first minimum, TH_LOW) — against orc_window_best."""
+    L = RM(); Lo = O.lib()
+    for S in fuse_sim3_scenarios():
+        nf, a = call_fuse_sim3(L, S)
+        n, nq, k, desc, sf, qx, qy, lvl, qd, w, h = (S[x] for x in ('n', 'nq', 'k', 'desc', 'sf', 'qx', 'qy', 'lvl', 'qd', 'w', 'h'))
+        v2 = (S['valid'].astype(bool) & (qx >= 0) & (qx < w) & (qy >= 0) & (qy < h)).astype(np.uint8)
+        radius = (np.float32(S['th']) * sf[lvl]).astype(np.float32)
         g = Lo.orc_grid_create(p(k), n, C.c_float(0), C.c_float(w), C.c_float(0), C.c_float(h))
         bi = np.zeros(nq, np.int32); bd = np.zeros(nq, np.int32)
         Lo.orc_window_best(C.c_void_p(g), p(k), p(desc), None, None, None, nq, p(v2), p(qx), p(qy), None, p(radius), p((lvl - 1).astype(np.int32)),
                            p(lvl), p(qd), p(bi), p(bd))
         Lo.orc_grid_destroy(C.c_void_p(g))
         exp = np.where(bd <= 50, bi, -1)
-        assert nf == int((exp >= 0).sum()) and nf > 20, (trial, nf, int((exp >= 0).sum()))
-        assert np.array_equal(a, exp), (trial, int((a != exp).sum()))
+        assert nf == int((exp >= 0).sum()) and nf > 20, (S['trial'], nf, int((exp >= 0).sum()))
+        assert np.array_equal(a, exp), (S['trial'], int((a != exp).sum()))
