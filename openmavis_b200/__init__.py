@@ -649,7 +649,16 @@ class ORBmatcher:
         _check(self.L.orbx_search_by_projection_last(self.h, ncam, _p(cam_off), _p(kps), _p(desc), _p(bounds), _p(sf), sf.size, _p(occ),
                                                      _p(ur), n, _p(valid), _p(px), _p(py), _p(pur), _p(octv), _p(ang), _p(ho), _p(pd),
                                                      C.c_float(th), int(gate), int(self.mbCheckOrientation), int(max_dist), _p(assigned), C.byref(nm)))
+        self._last_n = N
         return nm.value, assigned[:N]
+
+    def SearchByProjectionLastCleared(self):
+        """After SearchByProjectionLast: cleared[N] = 1 where a claim was made and then cleared by the rotation filter (the reference writes
+        NULL into CurrentFrame.mvpMapPoints there, src/ORBmatcher.cc:2404; `assigned` is -1 both there and at keypoints nobody claimed)."""
+        n = int(getattr(self, '_last_n', 0))
+        cleared = np.zeros(max(n, 1), np.uint8)
+        _check(self.L.orbx_search_by_projection_last_cleared(self.h, _p(cleared), n))
+        return cleared[:n]
 
 class _SbpCall(C.Structure):
     _fields_ = [('ncam', C.c_int), ('cam_off', C.c_void_p), ('kps', C.c_void_p), ('desc', C.c_void_p), ('grid_bounds', C.c_void_p),

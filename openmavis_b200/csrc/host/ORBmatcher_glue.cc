@@ -4,7 +4,7 @@
 // Compiled against the integrator's own headers (ORBmatcher.h, Frame.h, KeyFrame.h, MapPoint.h): it only touches the members the
 // reference bodies touch.  Every search runs on the device; what stays here is what the reference does around it on the host —
 // reading Frame / KeyFrame / MapPoint members into flat arrays and writing the matches back into F.mvpMapPoints / the output vectors.
-// Methods not listed here keep their reference bodies (their device entry points are documented in INTEGRATION.md).
+// Every public method of the class is here.
 //
 //   ORBmatcher::DescriptorDistance                                   src/ORBmatcher.cc:2577-2591   host popcount (8 words)
 //   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, ...)  src/ORBmatcher.cc:23-340      orbx_search_by_projection
@@ -18,6 +18,7 @@
 //   ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th, cameraID)           src/ORBmatcher.cc:1458-1647   orbx_window_best + the graph updates, in point order
 //   ORBmatcher::Fuse(KeyFrame*, Sim3f&, vpPoints, th, vpReplacePoint) src/ORBmatcher.cc:1648-1769  orbx_window_best per camera + the updates
 //   ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th)       src/ORBmatcher.cc:1771-1983   orbx_search_by_sim3
+//   ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse)  :1131-1456   orbx_search_for_triangulation_full
 // The two projection matchers compute their projections here, on the host, with the integrator's own Eigen / Sophus types and the
 // reference's expressions (a few thousand 3-D points per call); window search, Hamming distances, ordered claims and the rotation
 // filter run on the device.
@@ -25,6 +26,9 @@
 // tests/host_harness builds this file against stub Frame / KeyFrame / MapPoint headers that carry the reference's member names and
 // tests/test_matcher_glue.py compares it, call by call, with the reference's own object code (the unmodified ORBmatcher.cc compiled against the same stubs).
 #include <ORBmatcher.h>   // the REFERENCE's include/ORBmatcher.h from the include path (not the array-level header next to this file)
+#ifndef ORBX_GLUE_BUILD
+#include <CameraModels/KannalaBrandt8.h>   // GetPrecision() of the fisheye model (SearchForTriangulation)
+#endif
 
 #include <math.h>
 #include <stdio.h>
@@ -33,6 +37,7 @@
 
 #include <set>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "orbx.h"
@@ -696,6 +701,135 @@ int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoin
     for (int i1 = 0; i1 < N1; i1++)
         if (match12[i1] >= 0) vpMatches12[i1] = vpMapPoints2[match12[i1]];              // :1975
     return nFound;
+}
+
+namespace {
+// keypoints of a KeyFrame in global feature order and its camera blocks (as frame_layout does for a Frame)
+int keyframe_layout(KeyFrame *K, std::vector<orbx_kp> &kps, int cam_off[5]) {
+    auto add = [&](const std::vector<cv::KeyPoint> &v, int n) { kps.insert(kps.end(), (const orbx_kp *)v.data(), (const orbx_kp *)v.data() + n); };
+    kps.clear();
+    cam_off[0] = 0;
+    if (K->NLeft == -1) {
+        add(K->mvKeysUn, K->N);
+        for (int c = 1; c <= 4; c++) cam_off[c] = K->N;
+        return 1;
+    }
+    add(K->mvKeys, K->NLeft); cam_off[1] = K->NLeft;
+    add(K->mvKeysRight, K->NRight); cam_off[2] = K->NLeft + K->NRight;
+    if (K->NSideLeft == -1 && K->NSideRight == -1) { cam_off[3] = cam_off[4] = cam_off[2]; return 2; }
+    add(K->mvKeysSideLeft, K->NSideLeft); cam_off[3] = cam_off[2] + K->NSideLeft;
+    add(K->mvKeysSideRight, K->NSideRight); cam_off[4] = cam_off[3] + K->NSideRight;
+    return 4;
+}
+
+// one camera pair of SearchForTriangulation as the device predicate takes it: Pinhole::epipolarConstrain's fundamental matrix
+// (src/CameraModels/Pinhole.cpp:112-115, the reference's own expression, evaluated once per pair instead of once per candidate) or the
+// Kannala-Brandt parameters of KannalaBrandt8::epipolarConstrain (src/CameraModels/KannalaBrandt8.cpp:219-230)
+void epipolar_pair(orbx_epipolar_pair &P, GeometricCamera *c1, GeometricCamera *c2, const Eigen::Matrix3f &R12, const Eigen::Vector3f &t12) {
+    memset(&P, 0, sizeof(P));
+    if (!c1 || !c2) return;
+    if (c1->GetType() == GeometricCamera::CAM_PINHOLE) {
+        P.model = ORBX_CAM_PINHOLE;
+        Eigen::Matrix3f t12x = Sophus::SO3f::hat(t12);
+        Eigen::Matrix3f K1 = c1->toK_();
+        Eigen::Matrix3f K2 = c2->toK_();
+        Eigen::Matrix3f F12 = K1.transpose().inverse() * t12x * R12 * K2.inverse();
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) P.F12[3 * i + j] = F12(i, j);
+    } else {
+        P.model = ORBX_CAM_KB8;
+        for (int i = 0; i < 8; i++) { P.kb8.cam1[i] = c1->getParameter(i); P.kb8.cam2[i] = c2->getParameter(i); }
+        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) P.kb8.R12[3 * i + j] = R12(i, j); P.kb8.t12[i] = t12(i); }
+#ifdef ORBX_GLUE_BUILD
+        P.kb8.precision1 = P.kb8.precision2 = 1e-6f;           // (the test harness has no KannalaBrandt8 class; KannalaBrandt8.h:21)
+#else
+        P.kb8.precision1 = static_cast<KannalaBrandt8 *>(c1)->GetPrecision(); P.kb8.precision2 = static_cast<KannalaBrandt8 *>(c2)->GetPrecision();
+#endif
+    }
+}
+}  // namespace
+
+// src/ORBmatcher.cc:1131-1456 — LocalMapping::CreateNewMapPoints
+int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<std::pair<size_t, size_t>> &vMatchedPairs, const bool bOnlyStereo,
+                                       const bool bCoarse) {
+    // :1141-1198, the reference's expressions
+    Sophus::SE3f T1w = pKF1->GetPose();
+    Sophus::SE3f T2w = pKF2->GetPose();
+    Sophus::SE3f Tw2 = pKF2->GetPoseInverse();
+    Eigen::Vector3f Cw = pKF1->GetCameraCenter();
+    Eigen::Vector3f C2 = T2w * Cw;
+    Eigen::Vector2f ep = pKF2->mpCamera->project(C2);
+    Sophus::SE3f T12, Tll, Tlr, Trl, Trr, Tlsl, Tsll, Tslsl, Trsr, Tsrr, Tsrsr;
+    const bool rig2 = pKF1->mpCamera2 || pKF2->mpCamera2;                                // (:1156: the single-camera branch needs both to be NULL)
+    const bool both2 = pKF1->mpCamera2 && pKF2->mpCamera2;
+    const bool rig4 = pKF1->mpCamera3 && pKF2->mpCamera3 && pKF1->mpCamera4 && pKF2->mpCamera4;
+    if (!rig2) {
+        T12 = T1w * Tw2;
+    } else {
+        Sophus::SE3f Tr1w = pKF1->GetRightPose();
+        Sophus::SE3f Twr2 = pKF2->GetRightPoseInverse();
+        Tll = T1w * Tw2; Tlr = T1w * Twr2; Trl = Tr1w * Tw2; Trr = Tr1w * Twr2;
+    }
+    if (rig4) {
+        Sophus::SE3f Tr1w = pKF1->GetRightPose();
+        Sophus::SE3f Twr2 = pKF2->GetRightPoseInverse();
+        Sophus::SE3f Tsl1w = pKF1->GetSideLeftPose();
+        Sophus::SE3f Twsl2 = pKF2->GetSideLeftPoseInverse();
+        Sophus::SE3f Tsr1w = pKF1->GetSideRightPose();
+        Sophus::SE3f Twsr2 = pKF2->GetSideRightPoseInverse();
+        Tlsl = T1w * Twsl2; Tsll = Tsl1w * Tw2; Tslsl = Tsl1w * Twsl2;
+        Trsr = Tr1w * Twsr2; Tsrr = Tsr1w * Twr2; Tsrsr = Tsr1w * Twsr2;
+    }
+    std::vector<orbx_kp> kps1, kps2;
+    int off1[5], off2[5];
+    const int ncam1 = keyframe_layout(pKF1, kps1, off1), ncam2 = keyframe_layout(pKF2, kps2, off2);
+    const int ncam = !both2 ? 1 : rig4 ? 4 : 2;                                          // the branches the reference's loop can take (:1301, 1331)
+    if (ncam1 != ncam2 || ncam1 != ncam) { fprintf(stderr, "ORBmatcher::SearchForTriangulation: keyframes of different rigs are not supported\n"); abort(); }
+    const int n1 = pKF1->N, n2 = pKF2->N;
+    vMatchedPairs.clear();
+    if (n1 == 0 || n2 == 0) return 0;
+    // [0] the single-camera pair, [1] ll, [2] lr, [3] rl, [4] rr, [5] l-sl, [6] sl-l, [7] sl-sl, [8] r-sr, [9] sr-r, [10] sr-sr (:1301-1378)
+    orbx_epipolar_pair pairs[11];
+    memset(pairs, 0, sizeof(pairs));
+    if (!bCoarse) {
+        GeometricCamera *a0 = pKF1->mpCamera, *a1 = pKF1->mpCamera2, *a2 = pKF1->mpCamera3, *a3 = pKF1->mpCamera4;
+        GeometricCamera *b0 = pKF2->mpCamera, *b1 = pKF2->mpCamera2, *b2 = pKF2->mpCamera3, *b3 = pKF2->mpCamera4;
+        if (ncam == 1) epipolar_pair(pairs[0], a0, b0, T12.rotationMatrix(), T12.translation());
+        if (ncam >= 2) {
+            epipolar_pair(pairs[1], a0, b0, Tll.rotationMatrix(), Tll.translation());
+            epipolar_pair(pairs[2], a0, b1, Tlr.rotationMatrix(), Tlr.translation());
+            epipolar_pair(pairs[3], a1, b0, Trl.rotationMatrix(), Trl.translation());
+            epipolar_pair(pairs[4], a1, b1, Trr.rotationMatrix(), Trr.translation());
+        }
+        if (ncam == 4) {
+            epipolar_pair(pairs[5], a0, b2, Tlsl.rotationMatrix(), Tlsl.translation());
+            epipolar_pair(pairs[6], a2, b0, Tsll.rotationMatrix(), Tsll.translation());
+            epipolar_pair(pairs[7], a2, b2, Tslsl.rotationMatrix(), Tslsl.translation());
+            epipolar_pair(pairs[8], a1, b3, Trsr.rotationMatrix(), Trsr.translation());
+            epipolar_pair(pairs[9], a3, b1, Tsrr.rotationMatrix(), Tsrr.translation());
+            epipolar_pair(pairs[10], a3, b3, Tsrsr.rotationMatrix(), Tsrsr.translation());
+        }
+    }
+    std::vector<int> nk1, pk1, ik1, nk2, pk2, ik2;
+    feature_vector_csr(pKF1->mFeatVec, nk1, pk1, ik1);
+    feature_vector_csr(pKF2->mFeatVec, nk2, pk2, ik2);
+    std::vector<unsigned char> mp1(n1), mp2(n2), t1, t2;
+    for (int i = 0; i < n1; i++) mp1[i] = pKF1->GetMapPoint(i) != NULL;                  // :1224-1229
+    for (int i = 0; i < n2; i++) mp2[i] = pKF2->GetMapPoint(i) != NULL;                  // :1260-1264
+    const int nlevels = (int)pKF2->mvScaleFactors.size();
+    std::vector<int> match12(n1, -1);
+    int nmatches = 0;
+    const float epf[2] = {ep(0), ep(1)};
+    if (orbx_search_for_triangulation_full(handle(), ncam, off1, kps1.data(), desc_rows(pKF1->mDescriptors, t1), mp1.data(),
+                                           ncam == 1 ? pKF1->mvuRight.data() : nullptr, (int)nk1.size(), nk1.data(), pk1.data(), ik1.data(), off2, kps2.data(),
+                                           desc_rows(pKF2->mDescriptors, t2), mp2.data(), ncam == 1 ? pKF2->mvuRight.data() : nullptr, (int)nk2.size(),
+                                           nk2.data(), pk2.data(), ik2.data(), epf, pKF2->mvScaleFactors.data(), pKF1->mvLevelSigma2.data(),
+                                           pKF2->mvLevelSigma2.data(), nlevels, bOnlyStereo ? 1 : 0, bCoarse ? 1 : 0, mbCheckOrientation ? 1 : 0,
+                                           bCoarse ? nullptr : pairs, match12.data(), &nmatches) != ORBX_OK)
+        die("SearchForTriangulation");
+    vMatchedPairs.reserve(nmatches);                                                     // :1446-1453
+    for (int i = 0; i < n1; i++)
+        if (match12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)match12[i]));
+    return nmatches;
 }
 
 }  // namespace ORB_SLAM3

@@ -22,6 +22,24 @@ float Frame::mfGridElementWidthInv = 0, Frame::mfGridElementHeightInv = 0;
 // reference bodies, lifted at build time (oracle/Makefile: sed -n '<range>p' of the mounted sources)
 #include "_ref/gen/frame_grid.inc"      // src/Frame.cc:541-582 AssignFeaturesToGrid, :890-967 GetFeaturesInArea, :969-978 PosInGrid
 #include "_ref/gen/keyframe_grid.inc"   // src/KeyFrame.cc:769-834 GetFeaturesInArea
+
+// A pinhole camera whose epipolarConstrain is the REFERENCE's (src/CameraModels/Pinhole.cpp:103-132, lifted at build time): project() and
+// toK_() are the two obvious lines of include/CameraModels/Pinhole.h / Pinhole.cpp:28-35, 95-100 on the parameters {fx, fy, cx, cy}.
+class Pinhole : public GeometricCamera {
+  public:
+    Pinhole(float fx, float fy, float cx, float cy) { mvParameters = {fx, fy, cx, cy}; mnType = CAM_PINHOLE; }
+    Eigen::Vector2f project(const Eigen::Vector3f &v3D) override {
+        return Eigen::Vector2f(mvParameters[0] * v3D[0] / v3D[2] + mvParameters[2], mvParameters[1] * v3D[1] / v3D[2] + mvParameters[3]);
+    }
+    Eigen::Matrix3f toK_() override {
+        Eigen::Matrix3f K;
+        K(0, 0) = mvParameters[0]; K(0, 2) = mvParameters[2]; K(1, 1) = mvParameters[1]; K(1, 2) = mvParameters[3]; K(2, 2) = 1.f;
+        return K;
+    }
+    bool epipolarConstrain(GeometricCamera *pCamera2, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const Eigen::Matrix3f &R12,
+                           const Eigen::Vector3f &t12, const float sigmaLevel, const float unc) override;
+};
+#include "_ref/gen/pinhole_epipolar.inc"   // src/CameraModels/Pinhole.cpp:103-132 Pinhole::epipolarConstrain
 }  // namespace ORB_SLAM3
 
 using namespace ORB_SLAM3;
@@ -431,7 +449,6 @@ int refm_search_by_projection_last(int ncam, const int *cam_off, const ref_kp *k
     }
     return n;
 }
-#ifndef ORBX_GLUE_BUILD
 
 // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:1131-1456).
 // FeatureVectors as CSR (node ids ascending); ncam = 1 (mono / rectified stereo: NLeft == -1), 2 or 4; has_mp[idx] = GetMapPoint(idx)
@@ -488,7 +505,63 @@ int refm_search_for_triangulation(int ncam, const int *cam_off1, const ref_kp *k
     for (auto &p : pairs) match12[p.first] = (int)p.second;
     return n;
 }
-#endif
+
+// ORBmatcher::SearchForTriangulation with REAL pinhole geometry: cameras cam[c] = {fx, fy, cx, cy} (the same rig in both keyframes),
+// identity rotations, KF2 at the origin, KF1's pose translation t1w, right / side-left / side-right cameras at the translations rel[0..2]
+// from the left one.  The reference computes the epipole, the eleven (R12, t12) pairs and — through Pinhole::epipolarConstrain, its own
+// code — the fundamental matrices itself.  sigma2[nsf] = mvLevelSigma2 of both keyframes.  Everything else as refm_search_for_triangulation.
+int refm_search_for_triangulation_pinhole(int ncam, const int *cam_off1, const ref_kp *kps1, const uint8_t *desc1, const uint8_t *has_mp1,
+                                          const float *u_right1, int nn1, const int *nodes1, const int *ptr1, const int *idx1v, const int *cam_off2,
+                                          const ref_kp *kps2, const uint8_t *desc2, const uint8_t *has_mp2, const float *u_right2, int nn2,
+                                          const int *nodes2, const int *ptr2, const int *idx2v, const float *cam, const float *t1w, const float *rel,
+                                          const float *sf2, const float *sigma2, int nsf, int bOnlyStereo, int bCoarse, int checkOrientation,
+                                          int *match12) {
+    KeyFrame K1, K2;
+    std::vector<Pinhole> c1, c2;
+    for (int c = 0; c < 4; c++) { c1.push_back(Pinhole(cam[4 * c], cam[4 * c + 1], cam[4 * c + 2], cam[4 * c + 3])); c2.push_back(c1.back()); }
+    MapPoint holder;
+    auto fill = [&](KeyFrame &K, const int *cam_off, const ref_kp *kps, const uint8_t *desc, const uint8_t *has_mp, const float *u_right, int nn,
+                    const int *nodes, const int *ptr, const int *idxv, std::vector<Pinhole> &cams) {
+        K.N = cam_off[ncam];
+        if (ncam == 1) {
+            for (int i = 0; i < K.N; i++) K.mvKeysUn.push_back(to_cv(kps[i]));
+            K.mvKeys = K.mvKeysUn;
+        } else {
+            K.NLeft = cam_off[1] - cam_off[0]; K.NRight = cam_off[2] - cam_off[1];
+            K.NSideLeft = ncam >= 4 ? cam_off[3] - cam_off[2] : -1; K.NSideRight = ncam >= 4 ? cam_off[4] - cam_off[3] : -1;
+            for (int i = cam_off[0]; i < cam_off[1]; i++) K.mvKeys.push_back(to_cv(kps[i]));
+            for (int i = cam_off[1]; i < cam_off[2]; i++) K.mvKeysRight.push_back(to_cv(kps[i]));
+            if (ncam >= 4) {
+                for (int i = cam_off[2]; i < cam_off[3]; i++) K.mvKeysSideLeft.push_back(to_cv(kps[i]));
+                for (int i = cam_off[3]; i < cam_off[4]; i++) K.mvKeysSideRight.push_back(to_cv(kps[i]));
+            }
+        }
+        K.mDescriptors = desc_mat(desc, K.N);
+        K.map_points.assign(K.N, nullptr);
+        for (int i = 0; i < K.N; i++) if (has_mp[i]) K.map_points[i] = &holder;
+        K.mvuRight.assign(K.N, -1.f);
+        if (u_right && ncam == 1) K.mvuRight.assign(u_right, u_right + K.N);
+        K.mvScaleFactors.assign(sf2, sf2 + nsf);
+        K.mvLevelSigma2.assign(sigma2, sigma2 + nsf);
+        K.mpCamera = &cams[0];
+        if (ncam >= 2) K.mpCamera2 = &cams[1];
+        if (ncam >= 4) { K.mpCamera3 = &cams[2]; K.mpCamera4 = &cams[3]; }
+        K.Trl = Sophus::SE3f(Eigen::Matrix3f::Identity(), Eigen::Vector3f(rel[0], rel[1], rel[2]));
+        K.Tsll = Sophus::SE3f(Eigen::Matrix3f::Identity(), Eigen::Vector3f(rel[3], rel[4], rel[5]));
+        K.Tsrl = Sophus::SE3f(Eigen::Matrix3f::Identity(), Eigen::Vector3f(rel[6], rel[7], rel[8]));
+        for (int a = 0; a < nn; a++)
+            for (int j = ptr[a]; j < ptr[a + 1]; j++) K.mFeatVec[(unsigned)nodes[a]].push_back((unsigned)idxv[j]);
+    };
+    fill(K1, cam_off1, kps1, desc1, has_mp1, u_right1, nn1, nodes1, ptr1, idx1v, c1);
+    fill(K2, cam_off2, kps2, desc2, has_mp2, u_right2, nn2, nodes2, ptr2, idx2v, c2);
+    K1.Tcw = Sophus::SE3f(Eigen::Matrix3f::Identity(), Eigen::Vector3f(t1w[0], t1w[1], t1w[2]));
+    std::vector<std::pair<size_t, size_t>> pairs;
+    ORBmatcher matcher(0.6f, checkOrientation != 0);
+    const int n = matcher.SearchForTriangulation(&K1, &K2, pairs, bOnlyStereo != 0, bCoarse != 0);
+    for (int i = 0; i < K1.N; i++) match12[i] = -1;
+    for (auto &pr : pairs) match12[pr.first] = (int)pr.second;
+    return n;
+}
 
 // the pixel camera's epipolar predicate, for the oracle-side callback of the same test
 // KeyFrame with one camera block (NLeft == -1) over n keypoints: grid as the KeyFrame constructor copies it from the Frame

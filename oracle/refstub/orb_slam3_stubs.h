@@ -63,6 +63,15 @@ struct Matrix3f {
     float &operator()(int i, int j) { return m[i][j]; }
     const float &operator()(int i, int j) const { return m[i][j]; }
     Matrix3f transpose() const { Matrix3f r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[i][j] = m[j][i]; return r; }
+    Matrix3f inverse() const {   // adjugate / determinant (what the harness cameras' fundamental matrices are built with, on both sides of a comparison)
+        Matrix3f r;
+        const float c00 = m[1][1] * m[2][2] - m[1][2] * m[2][1], c01 = m[1][2] * m[2][0] - m[1][0] * m[2][2], c02 = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+        const float det = m[0][0] * c00 + m[0][1] * c01 + m[0][2] * c02, id = 1.f / det;
+        r.m[0][0] = c00 * id; r.m[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) * id; r.m[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) * id;
+        r.m[1][0] = c01 * id; r.m[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) * id; r.m[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id;
+        r.m[2][0] = c02 * id; r.m[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) * id; r.m[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
+        return r;
+    }
 };
 static inline Vector3f operator*(const Matrix3f &A, const Vector3f &x) {
     Vector3f r;
@@ -93,6 +102,15 @@ template <class T> class SE3 {
     Eigen::Vector3f t_;
 };
 typedef SE3<float> SE3f;
+template <class T> class SO3 {
+  public:
+    static Eigen::Matrix3f hat(const Eigen::Vector3f &w) {   // the cross-product matrix
+        Eigen::Matrix3f r;
+        r(0, 1) = -w(2); r(0, 2) = w(1); r(1, 0) = w(2); r(1, 2) = -w(0); r(2, 0) = -w(1); r(2, 1) = w(0);
+        return r;
+    }
+};
+typedef SO3<float> SO3f;
 template <class T> class Sim3 {
   public:
     Sim3() : R_(Eigen::Matrix3f::Identity()), s_(1.f) {}
@@ -127,6 +145,14 @@ class GeometricCamera {
     virtual Eigen::Vector2f project(const Eigen::Vector3f &v3D) = 0;
     virtual bool epipolarConstrain(GeometricCamera *pCamera2, const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const Eigen::Matrix3f &R12,
                                    const Eigen::Vector3f &t12, const float sigmaLevel, const float unc) = 0;
+    virtual Eigen::Matrix3f toK_() { return Eigen::Matrix3f::Identity(); }   // (pure virtual in the reference)
+    float getParameter(const int i) { return mvParameters[i]; }
+    unsigned int GetType() { return mnType; }
+    const static unsigned int CAM_PINHOLE = 0;
+    const static unsigned int CAM_FISHEYE = 1;
+  protected:
+    std::vector<float> mvParameters;
+    unsigned int mnType = CAM_PINHOLE;
 };
 
 // include/MapPoint.h — tracking fields (public data members in the reference too) and the accessors ORBmatcher.cc calls

@@ -420,9 +420,15 @@ def test_search_by_projection_last_frame(ncam, th, fwd, bwd, check):
     assert rn == nm, (rn, nm)
     assert np.array_equal(assigned, rassigned), int((assigned != rassigned).sum())
     assert nm > 300
+    cleared = M.SearchByProjectionLastCleared()
     if check:   # the filter did remove something: without it there are more matches
-        n_all, _ = _oracle_sbp_last(frame, last, th, fwd, bwd, False)
+        n_all, a_all = _oracle_sbp_last(frame, last, th, fwd, bwd, False)
         assert n_all > rn
+        # orbx_search_by_projection_last_cleared: exactly the keypoints whose claim the rotation filter cleared (NULL in the reference, :2404)
+        assert cleared.sum() > 0 and (assigned[cleared == 1] == -1).all()
+        assert np.array_equal(cleared == 1, (a_all >= 0) & (rassigned < 0))
+    else:
+        assert cleared.sum() == 0
 
 
 @pytest.mark.parametrize('th', [1.0, 3.0])

@@ -187,3 +187,20 @@ def test_fuse_keyframe_sim3():
         nb, b = R.call_fuse_sim3(G(), S)
         assert na == nb and na > 20, (S['trial'], na, nb)
         assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+@pytest.mark.parametrize('coarse', [0, 1])
+def test_search_for_triangulation_pinhole(ncam, coarse):
+    """SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), src/ORBmatcher.cc:1131-1456, through the glue, with real
+    pinhole rigs (1 / 2 / 4 cameras): the glue derives the epipole and the eleven camera pairs from the poses with the reference's
+    expressions and hands the device one fundamental matrix per pair; the reference side runs its own Pinhole::epipolarConstrain
+    (src/CameraModels/Pinhole.cpp:103-132) per candidate.  Descriptor gate, epipole reject, carried pair state, last minimum, rotation filter."""
+    tot = 0
+    for S in R.sft_pinhole_scenarios(ncam, coarse):
+        na, a = R.call_sft_pinhole(R.RM(), S)
+        nb, b = R.call_sft_pinhole(G(), S)
+        assert na == nb, (S['trial'], na, nb)
+        assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
+        tot += na
+    assert tot > 100

@@ -244,6 +244,72 @@ def test_search_for_triangulation(ncam, coarse):
             assert len(set(states)) >= 8                      # the scenario exercises the carried camera-pair states
 
 
+def sft_pinhole_scenarios(ncam, coarse):
+    """SearchForTriangulation with real pinhole geometry: every KF2 keypoint is the image of a 3-D point in its camera; a KF1 keypoint
+    planted on it is the image of the same point in ITS camera (+ up to 1.5 px of noise, 12 px for 40 % of them), so that the reference's own
+    Pinhole::epipolarConstrain accepts most planted pairs under the right camera pair and few under a wrong (carried) one."""
+    rng = np.random.default_rng(140 + 10 * ncam + coarse)
+    cam = np.array([[400, 400, 320, 240], [410, 405, 318, 243], [395, 398, 322, 238], [402, 401, 321, 241]], np.float32)
+    rel = np.array([[-0.12, 0.0, 0.0], [0.05, -0.03, 0.0], [-0.2, 0.03, 0.01]], np.float32)        # right, side-left, side-right from the left camera
+    relc = np.concatenate([np.zeros((1, 3), np.float32), rel])
+    for trial in range(8):
+        per1 = [int(rng.integers(150, 500)) for _ in range(ncam)]; per2 = [int(rng.integers(150, 500)) for _ in range(ncam)]
+        off1 = np.concatenate([[0], np.cumsum(per1)]).astype(np.int32); off2 = np.concatenate([[0], np.cumsum(per2)]).astype(np.int32)
+        n1, n2 = int(off1[-1]), int(off2[-1])
+        k2 = make_kps(n2, rng); d2 = synth_descriptors(n2, 14000 + trial)
+        d2[10:40] = d2[10]
+        src = rng.integers(0, n2, n1)
+        flips = np.packbits(rng.random((n1, 256)) < 0.05, axis=1, bitorder='little'); flips[:, 0] &= 0xE0
+        d1 = d2[src] ^ flips
+        d1[::6] = synth_descriptors(len(d1[::6]), 143 + trial)
+        k1 = make_kps(n1, rng)
+        t1w = np.array([[-0.05, 0.02, -0.5], [-0.3, 0.02, 0.05]][trial % 2], np.float32)           # forward motion (epipole inside the image) / sideways
+        c2 = np.searchsorted(off2, np.arange(n2), side='right') - 1; c1 = np.searchsorted(off1, np.arange(n1), side='right') - 1
+        z = rng.uniform(2.0, 8.0, n2)
+        X = np.stack([(k2['x'] - cam[c2, 2]) / cam[c2, 0] * z, (k2['y'] - cam[c2, 3]) / cam[c2, 1] * z, z], 1) - relc[c2]   # world = KF2's left camera
+        Xc1 = X[src] + t1w + relc[c1]
+        planted = (np.arange(n1) % 6 != 0) & (Xc1[:, 2] > 0.2)
+        noise = np.where(rng.random(n1) < 0.6, 1.5, 12.0)                                          # 40 % are off the epipolar line by up to 12 px
+        u1 = cam[c1, 0] * Xc1[:, 0] / Xc1[:, 2] + cam[c1, 2] + rng.uniform(-1, 1, n1) * noise
+        v1 = cam[c1, 1] * Xc1[:, 1] / Xc1[:, 2] + cam[c1, 3] + rng.uniform(-1, 1, n1) * noise
+        k1['x'][planted] = u1[planted].astype(np.float32); k1['y'][planted] = v1[planted].astype(np.float32)
+        fv1, fv2 = _feature_vector(d1), _feature_vector(d2)
+        mp1 = (rng.random(n1) < 0.2).astype(np.uint8); mp2 = (rng.random(n2) < 0.2).astype(np.uint8)
+        ur1 = ur2 = None; only_stereo = 0
+        if ncam == 1 and trial % 2 == 1:
+            ur1 = np.where(rng.random(n1) < 0.5, 10.0, -1.0).astype(np.float32); ur2 = np.where(rng.random(n2) < 0.5, 10.0, -1.0).astype(np.float32)
+            only_stereo = int(trial % 4 == 3)
+        sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+        yield dict(trial=trial, ncam=ncam, coarse=coarse, off1=off1, off2=off2, n1=n1, n2=n2, k1=k1, k2=k2, d1=d1, d2=d2, fv1=fv1, fv2=fv2, mp1=mp1, mp2=mp2,
+                   ur1=ur1, ur2=ur2, only_stereo=only_stereo, cam=np.ascontiguousarray(cam), t1w=t1w, rel=np.ascontiguousarray(rel), sf=sf,
+                   sigma2=(sf * sf).astype(np.float32), chk=trial % 2)
+
+
+def call_sft_pinhole(L, S):
+    a = np.zeros(S['n1'], np.int32)
+    fv1, fv2 = S['fv1'], S['fv2']
+    n = L.refm_search_for_triangulation_pinhole(S['ncam'], p(S['off1']), p(S['k1']), p(S['d1']), p(S['mp1']), p(S['ur1']), len(fv1[0]), p(fv1[0]), p(fv1[1]),
+                                                p(fv1[2]), p(S['off2']), p(S['k2']), p(S['d2']), p(S['mp2']), p(S['ur2']), len(fv2[0]), p(fv2[0]), p(fv2[1]),
+                                                p(fv2[2]), p(S['cam']), p(S['t1w']), p(S['rel']), p(S['sf']), p(S['sigma2']), 8, S['only_stereo'], S['coarse'],
+                                                S['chk'], p(a))
+    return n, a
+
+
+@pytest.mark.parametrize('ncam', [1, 2, 4])
+def test_search_for_triangulation_pinhole_scenario(ncam):
+    """(sanity of the pinhole scenario on the reference itself: the epipolar predicate — the reference's own Pinhole::epipolarConstrain —
+    rejects a good part of what the coarse mode accepts, and still leaves matches)"""
+    L = RM()
+    tot = [0, 0]
+    for Sf, Sc in zip(sft_pinhole_scenarios(ncam, 0), sft_pinhole_scenarios(ncam, 1)):
+        nf, af = call_sft_pinhole(L, Sf)
+        Sc2 = dict(Sf); Sc2['coarse'] = 1
+        nc, ac = call_sft_pinhole(L, Sc2)
+        assert nf == int((af >= 0).sum()) and nc == int((ac >= 0).sum())
+        tot[0] += nf; tot[1] += nc
+    assert tot[0] > 300 and tot[0] < 0.9 * tot[1], tot
+
+
 @pytest.mark.parametrize('ncam', [1, 2, 4])
 def test_search_by_bow_keyframe_frame(ncam):
     """SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), src/ORBmatcher.cc:349-666: per-camera best / second, the `|| true` ratio tests of
