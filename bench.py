@@ -626,11 +626,14 @@ def main():
                     hbuf.copy_(dbuf, non_blocking=True)
         s_in.synchronize(); s_out.synchronize()
     copy_run(2)
-    barrier()
-    t0 = time.perf_counter()
-    copy_run(e2e_steps)
-    barrier()
-    ms_copy = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    ms_copy = None
+    for _ in range(3):                                     # a roofline is what the link CAN do: the best of three trials (max over ranks each)
+        barrier()
+        t0 = time.perf_counter()
+        copy_run(e2e_steps)
+        barrier()
+        t = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        ms_copy = t if ms_copy is None else min(ms_copy, t)
     copy_value = world * frames * e2e_steps / (ms_copy * 1e-3)
     del cr_in, cr_out_d
     # latency-oriented variant: one synchronous orbx_extract_batch call per step
@@ -806,7 +809,7 @@ def main():
                     'one_rig_frame_latency_ms': ms_one_frame,
                     'copy_roofline': {'value': copy_value, 'unit': 'rig-frames/s', 'ms_per_step': ms_copy / e2e_steps,
                                       'h2d_gb_per_s_per_gpu': h2d / (ms_copy / e2e_steps * 1e-3) / 1e9, 'd2h_gb_per_s_per_gpu': d2h / (ms_copy / e2e_steps * 1e-3) / 1e9,
-                                      'what': 'the same pinned buffers moved by plain cudaMemcpyAsync on two streams, all ranks at once, no kernels'},
+                                      'what': 'the same pinned buffers moved by plain cudaMemcpyAsync on two streams, all ranks at once, no kernels; best of 3 trials'},
                     'frac_of_copy_roofline': e2e_value / copy_value},
             'gpu_launches': launches_per_step * args.steps,
             'clocks': clocks, 'roofline': roofline, 'sustained': sustained, 'cpu_baseline': cpu, 'secondary': secondary, 'matching': matching,
