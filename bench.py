@@ -326,6 +326,47 @@ def guided_matchers(ob, device):
                        'oracle restatement / the batch time; the Python-side marshalling of the F argument sets is inside the timed call')
     out['batched_across_frames'] = batched
     pool.close()
+    # ---- SearchForTriangulation (src/ORBmatcher.cc:1131-1456), BASELINE config 2 style: the two keyframes of a 752x480 stereo setup with 1200
+    #      features each, FeatureVector groups = 32 vocabulary nodes; bCoarse = true (no geometry) and the run LocalMapping makes
+    #      (bCoarse = false: epipole reject + Pinhole::epipolarConstrain per candidate), both with the rotation filter
+    n1 = n2 = 1200
+    k2 = np.zeros(n2, ob.KP_DTYPE)
+    k2['x'] = rng.uniform(20, 732, n2); k2['y'] = rng.uniform(20, 460, n2); k2['octave'] = rng.integers(0, 8, n2); k2['angle'] = rng.uniform(0, 360, n2)
+    d2s = synth_descriptors(n2, 4242)
+    ssrc = rng.permutation(n2)[:n1]
+    sfl = np.packbits(rng.random((n1, 256)) < 0.05, axis=1, bitorder='little'); sfl[:, 0] &= 0xE0
+    d1s = d2s[ssrc] ^ sfl
+    d1s[::6] = synth_descriptors(len(d1s[::6]), 4343)
+    k1 = k2[ssrc].copy()
+    k1['x'] += rng.uniform(-30, 30, n1).astype(np.float32); k1['y'] += rng.uniform(-2.5, 2.5, n1).astype(np.float32)   # near the epipolar line y2 = y1
+    k1['angle'] = (k1['angle'] + rng.choice([0, 0, 0, 45, 200], n1)) % 360
+
+    def fvec5(d):
+        node = d[:, 0].astype(np.int32) & 31
+        order = np.argsort(node, kind='stable')
+        nodes, counts = np.unique(node, return_counts=True)
+        return nodes.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), order.astype(np.int32)
+    one = np.array([0, n1], np.int32)
+    kf1 = dict(cam_off=one, kps=k1, desc=d1s, has_mp=(rng.random(n1) < 0.3).astype(np.uint8), u_right=None, fv=fvec5(d1s))
+    kf2 = dict(cam_off=one.copy(), kps=k2, desc=d2s, has_mp=(rng.random(n2) < 0.3).astype(np.uint8), u_right=None, fv=fvec5(d2s))
+    ep = np.array([k2['x'][7] + 2.0, k2['y'][7] - 1.0], np.float32)
+    sfs = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
+    sg = (sfs * sfs).astype(np.float32)
+    prs = ob.epipolar_pairs()
+    for s_ in range(11):
+        prs['model'][s_] = ob.CAM_PINHOLE
+        prs['F12'][s_] = np.array([0, 0, 0, 0, 0, -1, 0, 1, 0], np.float32)        # epipolar line y2 = y1 (a rectified pair)
+    sft = {}
+    for name, coarse in (('coarse', True), ('epipolar', False)):
+        def run_sft():
+            nm[0] = m.SearchForTriangulationFull(kf1, kf2, ep, sfs, sg, sg, prs, False, coarse, True)[0]
+        ms = timed(run_sft)
+        dms = m.last_ms()
+        cpu_ms = timed(lambda: T._oracle_sft(kf1, kf2, ep, sfs, sg, sg, prs, False, coarse, True), reps=3)
+        sft[name] = {'matches': int(nm[0]), 'ms_per_call': ms, 'device_ms': dms, 'cpu_ms_per_call': cpu_ms}
+    out['search_for_triangulation'] = dict(sft, features=[n1, n2], nodes=32,
+                                           what='BASELINE config 2 style (2 x 1200 features, 32 shared vocabulary nodes): bCoarse = true and the bCoarse = false '
+                                                'run with the pinhole epipolar predicate on the device; CPU = the oracle restatement, one host thread')
     # ---- ComputeStereoMatches (src/Frame.cc:1057-1219)
     left = synth_image(752, 480, 2001)
     xs = np.arange(752)
