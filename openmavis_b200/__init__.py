@@ -453,7 +453,8 @@ class ORBmatcher:
                                                          _p(o2), _p(k2), _p(d2), _p(mp2), _p(ur2), n2n.size, _p(n2n), _p(p2), _p(i2), _p(ep), _p(sf2),
                                                          _p(s1), _p(s2), sf2.size, int(only_stereo), int(coarse), int(check_orientation), _p(pr),
                                                          _p(m12), C.byref(nm)))
-        return nm.value, [(int(i), int(m12[i])) for i in np.nonzero(m12 >= 0)[0]], m12
+        i1 = np.flatnonzero(m12 >= 0)
+        return nm.value, list(zip(i1.tolist(), m12[i1].tolist())), m12
 
     def window_best(self, kps, desc, bounds, qx, qy, radius, min_level, max_level, q_desc, valid=None, skip=None, u_right=None,
                     q_ur=None, inv_level_sigma2=None):

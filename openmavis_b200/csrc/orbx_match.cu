@@ -58,6 +58,9 @@ struct orbx_matcher {
     bool timed = false;
     DBuf b[24];
     std::vector<uint8_t> last_cleared;              // orbx_search_by_projection_last: keypoints whose claim the rotation filter cleared
+    uint8_t *stage_h = nullptr;                     // pinned staging of the small matchers' inputs: ONE host-to-device copy per call (Packer)
+    size_t stage_hcap = 0;
+    DBuf stage_d;
 };
 
 #define M_CUDA ORBX_CUDA
@@ -67,6 +70,38 @@ static int upload(orbx_matcher *m, DBuf &buf, const void *src, size_t bytes) {
     if (bytes) M_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, m->stream));
     return ORBX_OK;
 }
+
+// The guided matchers of one frame are a dozen small arrays in, a few kernels, one array out: a dozen cudaMemcpyAsync from pageable
+// memory cost more than the kernels (each is staged by the driver on its own).  A Packer gathers the arrays of a call in the handle's
+// pinned staging buffer (256-byte aligned offsets) and moves them with ONE asynchronous copy into one device arena; the call's final
+// stream synchronisation (every entry point ends with one) makes the staging buffer free again.
+struct Packer {
+    struct Item { size_t off; const void *src; size_t bytes; };
+    std::vector<Item> items;
+    size_t total = 0;
+    size_t add(const void *src, size_t bytes) {
+        const size_t o = total;
+        items.push_back({o, src, bytes});
+        total += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+    int commit(orbx_matcher *m, uint8_t **base) {
+        const size_t need = std::max<size_t>(total, 256);
+        if (need > m->stage_hcap) {
+            if (m->stage_h) cudaFreeHost(m->stage_h);
+            m->stage_h = nullptr; m->stage_hcap = 0;
+            const size_t want = need + need / 4;
+            M_CUDA(cudaHostAlloc((void **)&m->stage_h, want, cudaHostAllocDefault));
+            m->stage_hcap = want;
+        }
+        M_CUDA(m->stage_d.ensure(need));
+        for (const Item &it : items)
+            if (it.bytes) memcpy(m->stage_h + it.off, it.src, it.bytes);
+        if (total) M_CUDA(cudaMemcpyAsync(m->stage_d.p, m->stage_h, total, cudaMemcpyHostToDevice, m->stream));
+        *base = m->stage_d.as<uint8_t>();
+        return ORBX_OK;
+    }
+};
 
 // Train set = concatenation of `nparts` parts (one for the single-GPU call; one per rank for the sharded matcher).  The parts are
 // matched in at most two launches — the part `first` alone (or nothing: -1), then all the others in ONE launch after the stream has
@@ -162,6 +197,8 @@ void orbx_matcher_destroy(orbx_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (auto &b : m->b) b.release();
+    m->stage_d.release();
+    if (m->stage_h) cudaFreeHost(m->stage_h);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
@@ -541,21 +578,19 @@ int orbx_search_for_triangulation_full(orbx_matcher *m, int ncam, const int *cam
     const int tot2 = ptr2[nn2];
     for (int k = 0; k < tot2; k++)
         if (idx2[k] < 0 || idx2[k] >= n2) return fail(ORBX_ERR_INVALID, "idx2 out of range");
-    int st;
-    if ((st = upload(m, m->b[1], desc1, (size_t)n1 * 32)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[2], desc2, (size_t)n2 * 32)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[3], kps1, (size_t)n1 * sizeof(orbx_kp))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[4], kps2, (size_t)n2 * sizeof(orbx_kp))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[5], st1.data(), (size_t)std::max(n1, 1))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[6], st2.data(), (size_t)std::max(n2, 1))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[9], row_q.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[10], row_begin.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[11], row_len.data(), (size_t)nrows * sizeof(int))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[12], idx2, (size_t)tot2 * sizeof(int))) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[13], skip2.data(), (size_t)std::max(n2, 1))) != ORBX_OK) return st;
     std::vector<orbx_epipolar_pair> pz(kSftStates);
     memset(pz.data(), 0, pz.size() * sizeof(orbx_epipolar_pair));
-    if ((st = upload(m, m->b[7], pairs ? pairs : pz.data(), kSftStates * sizeof(orbx_epipolar_pair))) != ORBX_OK) return st;
+    Packer pk;
+    const size_t o_d1 = pk.add(desc1, (size_t)n1 * 32), o_d2 = pk.add(desc2, (size_t)n2 * 32);
+    const size_t o_k1 = pk.add(kps1, (size_t)n1 * sizeof(orbx_kp)), o_k2 = pk.add(kps2, (size_t)n2 * sizeof(orbx_kp));
+    const size_t o_st1 = pk.add(st1.data(), (size_t)std::max(n1, 1)), o_st2 = pk.add(st2.data(), (size_t)std::max(n2, 1));
+    const size_t o_rq = pk.add(row_q.data(), (size_t)nrows * sizeof(int)), o_rb = pk.add(row_begin.data(), (size_t)nrows * sizeof(int));
+    const size_t o_rl = pk.add(row_len.data(), (size_t)nrows * sizeof(int)), o_i2 = pk.add(idx2, (size_t)tot2 * sizeof(int));
+    const size_t o_sk2 = pk.add(skip2.data(), (size_t)std::max(n2, 1));
+    const size_t o_pr = pk.add(pairs ? pairs : pz.data(), kSftStates * sizeof(orbx_epipolar_pair));
+    uint8_t *base = nullptr;
+    int st;
+    if ((st = pk.commit(m, &base)) != ORBX_OK) return st;
     M_CUDA(m->b[14].ensure((size_t)n1 * sizeof(int)));
     M_CUDA(m->b[15].ensure((size_t)nrows * sizeof(int)));
     M_CUDA(m->b[16].ensure((size_t)(nrows + 1) * sizeof(int)));
@@ -563,13 +598,14 @@ int orbx_search_for_triangulation_full(orbx_matcher *m, int ncam, const int *cam
     M_CUDA(cudaMemsetAsync(m->b[16].p, 0, (size_t)(nrows + 1) * sizeof(int), m->stream));
     SftArgs A;
     memset(&A, 0, sizeof(A));
-    A.d1 = (const uint4 *)m->b[1].p; A.d2 = (const uint4 *)m->b[2].p; A.k1 = m->b[3].as<orbx_kp>(); A.k2 = m->b[4].as<orbx_kp>();
-    A.nrows = nrows; A.row_q = m->b[9].as<int>(); A.row_begin = m->b[10].as<int>(); A.row_len = m->b[11].as<int>(); A.idx2 = m->b[12].as<int>();
-    A.skip2 = m->b[13].as<uint8_t>(); A.st1 = m->b[5].as<uint8_t>(); A.st2 = m->b[6].as<uint8_t>(); A.ncam = ncam;
+    A.d1 = (const uint4 *)(base + o_d1); A.d2 = (const uint4 *)(base + o_d2); A.k1 = (const orbx_kp *)(base + o_k1); A.k2 = (const orbx_kp *)(base + o_k2);
+    A.nrows = nrows; A.row_q = (const int *)(base + o_rq); A.row_begin = (const int *)(base + o_rb); A.row_len = (const int *)(base + o_rl);
+    A.idx2 = (const int *)(base + o_i2);
+    A.skip2 = base + o_sk2; A.st1 = base + o_st1; A.st2 = base + o_st2; A.ncam = ncam;
     for (int c = 0; c <= 4; c++) { A.off1[c] = cam_off1[std::min(c, ncam)]; A.off2[c] = cam_off2[std::min(c, ncam)]; }
     A.ep[0] = ep[0]; A.ep[1] = ep[1];
     for (int l = 0; l < 16; l++) { const int k = std::min(l, nlevels - 1); A.sf2[l] = sf2[k]; A.sigma1[l] = sigma2_1[k]; A.sigma2[l] = sigma2_2[k]; }
-    A.coarse = coarse != 0; A.pairs = m->b[7].as<orbx_epipolar_pair>();
+    A.coarse = coarse != 0; A.pairs = (const orbx_epipolar_pair *)(base + o_pr);
     A.match12 = m->b[14].as<int>(); A.exit_state = m->b[15].as<int>(); A.unresolved = m->b[16].as<int>();
     M_CUDA(cudaEventRecord(m->ev0, m->stream));
     k_sft_rows<<<(nrows + 127) / 128, 128, 0, m->stream>>>(A);
@@ -636,19 +672,16 @@ static int search_by_bow_impl(orbx_matcher *m, int variant, int nn1, const int *
     if (skip2) memcpy(s2.data(), skip2, n2);
     std::vector<float> zero;
     if (!check_orientation) { zero.assign(std::max(n1, n2), 0.0f); angle1 = angle2 = zero.data(); }
+    Packer pk;
+    const size_t o_d1 = pk.add(desc1, (size_t)n1 * 32), o_d2 = pk.add(desc2, (size_t)n2 * 32);
+    const size_t o_pa = pk.add(pa.data(), (size_t)npairs * 4), o_pb = pk.add(pb.data(), (size_t)npairs * 4);
+    const size_t o_p1 = pk.add(ptr1, (size_t)(nn1 + 1) * 4), o_i1 = pk.add(idx1, (size_t)tot1 * 4);
+    const size_t o_p2 = pk.add(ptr2, (size_t)(nn2 + 1) * 4), o_i2 = pk.add(idx2, (size_t)tot2 * 4);
+    const size_t o_s1 = pk.add(s1.data(), (size_t)n1), o_s2 = pk.add(s2.data(), (size_t)n2);
+    const size_t o_a1 = pk.add(angle1, (size_t)n1 * 4), o_a2 = pk.add(angle2, (size_t)n2 * 4);
+    uint8_t *base = nullptr;
     int st;
-    if ((st = upload(m, m->b[1], desc1, (size_t)n1 * 32)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[2], desc2, (size_t)n2 * 32)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[3], pa.data(), (size_t)npairs * 4)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[4], pb.data(), (size_t)npairs * 4)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[5], ptr1, (size_t)(nn1 + 1) * 4)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[6], idx1, (size_t)tot1 * 4)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[7], ptr2, (size_t)(nn2 + 1) * 4)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[8], idx2, (size_t)tot2 * 4)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[9], s1.data(), (size_t)n1)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[10], s2.data(), (size_t)n2)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[11], angle1, (size_t)n1 * 4)) != ORBX_OK) return st;
-    if ((st = upload(m, m->b[12], angle2, (size_t)n2 * 4)) != ORBX_OK) return st;
+    if ((st = pk.commit(m, &base)) != ORBX_OK) return st;
     // work: match [nout] | events [4 n1] (both -1) | claimed2 [n2] | nmatches [1] (both 0)
     const size_t o_ev = (size_t)nout, o_cl = o_ev + 4 * (size_t)n1, o_nm = o_cl + n2;
     M_CUDA(m->b[13].ensure((o_nm + 1) * 4));
@@ -657,11 +690,11 @@ static int search_by_bow_impl(orbx_matcher *m, int variant, int nn1, const int *
     M_CUDA(cudaMemsetAsync(w + o_cl, 0, ((size_t)n2 + 1) * 4, m->stream));
     BowArgs A;
     A.variant = variant; A.npairs = npairs;
-    A.pair_a = m->b[3].as<int>(); A.pair_b = m->b[4].as<int>();
-    A.ptr1 = m->b[5].as<int>(); A.idx1 = m->b[6].as<int>(); A.ptr2 = m->b[7].as<int>(); A.idx2 = m->b[8].as<int>();
-    A.desc1 = (const uint4 *)m->b[1].p; A.desc2 = (const uint4 *)m->b[2].p;
-    A.skip1 = m->b[9].as<uint8_t>(); A.skip2 = m->b[10].as<uint8_t>();
-    A.angle1 = m->b[11].as<float>(); A.angle2 = m->b[12].as<float>();
+    A.pair_a = (const int *)(base + o_pa); A.pair_b = (const int *)(base + o_pb);
+    A.ptr1 = (const int *)(base + o_p1); A.idx1 = (const int *)(base + o_i1); A.ptr2 = (const int *)(base + o_p2); A.idx2 = (const int *)(base + o_i2);
+    A.desc1 = (const uint4 *)(base + o_d1); A.desc2 = (const uint4 *)(base + o_d2);
+    A.skip1 = base + o_s1; A.skip2 = base + o_s2;
+    A.angle1 = (const float *)(base + o_a1); A.angle2 = (const float *)(base + o_a2);
     A.ncam2 = variant == 0 ? ncam2 : 1;
     for (int c = 0; c < 5; c++) A.cam_off2[c] = (variant == 0 && ncam2 > 1 && c <= ncam2) ? cam_off2[c] : n2;
     A.nnratio = nnratio; A.check_ori = check_orientation ? 1 : 0;
