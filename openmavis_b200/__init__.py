@@ -426,8 +426,8 @@ class ORBmatcher:
         _check(self.L.orbx_search_for_triangulation(self.h, n1n.size, _p(n1n), _p(p1), _p(i1), n2n.size, _p(n2n), _p(p2), _p(i2),
                                                     _p(d1), d1.shape[0], _p(d2), d2.shape[0], _p(s1), _p(s2), _p(m12),
                                                     C.byref(nm)))
-        pairs = [(int(i), int(m12[i])) for i in np.nonzero(m12 >= 0)[0]]
-        return nm.value, pairs, m12
+        ii = np.flatnonzero(m12 >= 0)
+        return nm.value, list(zip(ii.tolist(), m12[ii].tolist())), m12
 
     def SearchForTriangulationFull(self, kf1, kf2, ep, scale_factors2, sigma2_1, sigma2_2, pairs=None, only_stereo=False, coarse=False,
                                    check_orientation=False):
