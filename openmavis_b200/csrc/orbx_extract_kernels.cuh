@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ img,
 //  instead of 123 M warp-instructions on level 1 of the bench batch, but 67 % instead of 80 % issue utilisation — 145 vs 143 us.  Not kept.)
 constexpr int kRszTW = 64, kRszTH = 64;
 constexpr int kRszThreads = 256;
-// dynamic shared memory: staged source [src_rows][src_pitch] u8, horizontal sums [src_rows][kRszTW] u32, y taps [kRszTH];
+// dynamic shared memory: staged source [src_rows][src_pitch] u8, horizontal sums [src_rows][kRszTW] u32, y taps [kRszTH], row mirrors [kRszTH];
 // src_rows / src_pitch are the maxima over all tiles of all levels, computed by the host from the tap tables
 __host__ __device__ inline size_t resize_smem_bytes(int src_rows, int src_pitch) {
-    return (size_t)src_rows * src_pitch + (size_t)src_rows * kRszTW * 4 + kRszTH * sizeof(int4);
+    return (size_t)src_rows * src_pitch + (size_t)src_rows * kRszTW * 4 + kRszTH * sizeof(int4) + kRszTH * sizeof(int);
 }
 
 // REFLECT_101 image of interior row y in the top / bottom frame, or INT_MIN (levels are at least 68 rows high: at most one)
@@ -107,6 +107,14 @@ __device__ __forceinline__ int resize_row_mirror(int y, int h) {
     if (y >= 1 && y <= kEdge) return -y;
     if (y <= h - 2 && y >= h - 1 - kEdge) return 2 * (h - 1) - y;
     return INT_MIN;
+}
+
+// ((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2 with b already shifted left by 16
+__device__ __forceinline__ uint32_t resize_vtap(uint32_t b0, uint32_t h0, uint32_t b1, uint32_t h1) {
+    uint32_t a, r;
+    asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(a) : "r"(b0), "r"(h0));
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(b1), "r"(h1), "r"(a));
+    return r >> 2;
 }
 
 // source level of one resize launch as a TMA tensor: dims (pitch bytes, plane rows, images), box = (src_pitch, src_rows, 1)
@@ -129,9 +137,11 @@ __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ py
     const int sx_lo = tapx[0].s0, sx_hi = tapx[ow - 1].s1;
     const int sx_al = sx_lo & ~15;                              // staged columns start 16-byte aligned
     const int nrow = sy_hi - sy_lo + 1, nvec = (sx_hi - sx_al + 16) >> 4;
+    int *s_ym = reinterpret_cast<int *>(s_ty + kRszTH);        // row of the tile row's image in the top / bottom frame, or INT_MIN
     if (tid < oh) {
         const ResizeTap t = tapy[tid];
         s_ty[tid] = make_int4((t.s0 - sy_lo) * kRszTW, (t.s1 - sy_lo) * kRszTW, (int)t.a0 << 16, (int)t.a1 << 16);
+        s_ym[tid] = resize_row_mirror(oy0 + tid, D.h);
     }
     __shared__ __align__(8) uint64_t s_bar;
     if (map.use_tma) {
@@ -202,16 +212,17 @@ __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ py
             const int4 t = s_ty[r];
             const uint4 h0 = *reinterpret_cast<const uint4 *>(s_h + t.x + c4);
             const uint4 h1 = *reinterpret_cast<const uint4 *>(s_h + t.y + c4);
-            const uint32_t p0 = (__umulhi((uint32_t)t.z, h0.x) + __umulhi((uint32_t)t.w, h1.x) + 2u) >> 2;
-            const uint32_t p1 = (__umulhi((uint32_t)t.z, h0.y) + __umulhi((uint32_t)t.w, h1.y) + 2u) >> 2;
-            const uint32_t p2 = (__umulhi((uint32_t)t.z, h0.z) + __umulhi((uint32_t)t.w, h1.z) + 2u) >> 2;
-            const uint32_t p3 = (__umulhi((uint32_t)t.z, h0.w) + __umulhi((uint32_t)t.w, h1.w) + 2u) >> 2;
+            // (the rounding constant rides on the first multiply-high's addend: two IMAD.HI + one shift per pixel)
+            const uint32_t p0 = resize_vtap((uint32_t)t.z, h0.x, (uint32_t)t.w, h1.x);
+            const uint32_t p1 = resize_vtap((uint32_t)t.z, h0.y, (uint32_t)t.w, h1.y);
+            const uint32_t p2 = resize_vtap((uint32_t)t.z, h0.z, (uint32_t)t.w, h1.z);
+            const uint32_t p3 = resize_vtap((uint32_t)t.z, h0.w, (uint32_t)t.w, h1.w);
             const uint32_t out = __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
             if (nvalid == 4) *reinterpret_cast<uint32_t *>(drow) = out;
             else for (int k = 0; k < nvalid; k++) drow[k] = (uint8_t)(out >> (8 * k));
             if (x_band) s_out[r * (kRszTW / 4) + (c4 >> 2)] = out;
             if (y_band) {   // this row's image in the top / bottom frame
-                const int y = oy0 + r, ym = resize_row_mirror(y, D.h);
+                const int ym = s_ym[r];
                 if (ym != INT_MIN) {
                     uint8_t *mrow = dplane + (long long)(kYO + ym) * D.pitch + x;
                     if (nvalid == 4) *reinterpret_cast<uint32_t *>(mrow) = out;
@@ -224,18 +235,37 @@ __global__ void __launch_bounds__(kRszThreads) k_resize(uint8_t *__restrict__ py
     // frame pass (tiles at the left / right edge only): interior columns 1..19 -> -1..-19, w-2..w-20 -> w..w+18, for every row
     // of the tile and its own image in the top / bottom frame
     __syncthreads();
-    const uint8_t *ob = reinterpret_cast<const uint8_t *>(s_out);
-    for (int i = tid; i < oh * 2 * kEdge; i += kRszThreads) {
-        const int r = i / (2 * kEdge), j = i - r * (2 * kEdge);
-        const int side = j >= kEdge, k = j - side * kEdge + 1;          // k = 1..19
-        const int xx = side ? D.w - 1 - k : k;                          // mirrored interior column
-        if (xx < ox0 || xx >= ox0 + ow) continue;
-        const uint8_t pv = ob[r * kRszTW + (xx - ox0)];
-        const int dx = side ? D.w - 1 + k : -k;
-        const int y = oy0 + r;
-        dplane[(long long)(kYO + y) * D.pitch + dx] = pv;
-        const int ym = resize_row_mirror(y, D.h);
-        if (ym != INT_MIN) dplane[(long long)(kYO + ym) * D.pitch + dx] = pv;
+    if (ox0 == 0) {
+        // left frame, one aligned word per item: columns -4j-4 .. -4j-1 are the interior columns 4j+4 .. 4j+1 — the bytes of two
+        // adjacent words of the output tile in reverse order (ONE PRMT).  Column -20 lies outside the frame: word 4 is written as
+        // one byte + one half-word.  (Round 2: was one byte store per frame pixel, 13 % of the kernel's instructions.)
+        for (int i = tid; i < oh * 5; i += kRszThreads) {
+            const int r = i / 5, j = i - r * 5;
+            const uint32_t wv = __byte_perm(s_out[r * (kRszTW / 4) + j], s_out[r * (kRszTW / 4) + j + 1], 0x1234);
+            const int ym = s_ym[r];
+            uint8_t *d0 = dplane + (long long)(kYO + oy0 + r) * D.pitch - 4 * j - 4;
+            uint8_t *d1 = dplane + (long long)(kYO + (ym != INT_MIN ? ym : oy0 + r)) * D.pitch - 4 * j - 4;   // (no mirror: the same word again)
+            if (j < 4) {
+                *reinterpret_cast<uint32_t *>(d0) = wv;
+                *reinterpret_cast<uint32_t *>(d1) = wv;
+            } else {
+                d0[1] = (uint8_t)(wv >> 8); *reinterpret_cast<unsigned short *>(d0 + 2) = (unsigned short)(wv >> 16);
+                d1[1] = (uint8_t)(wv >> 8); *reinterpret_cast<unsigned short *>(d1 + 2) = (unsigned short)(wv >> 16);
+            }
+        }
+    }
+    if (ox0 + ow - 1 >= D.w - 1 - kEdge) {
+        // right frame: byte stores (the mirrored columns may straddle the last two tiles; each tile writes the pixels it holds)
+        const uint8_t *ob = reinterpret_cast<const uint8_t *>(s_out);
+        for (int i = tid; i < oh * kEdge; i += kRszThreads) {
+            const int r = i / kEdge, k = i - r * kEdge + 1;                 // k = 1..19
+            const int xx = D.w - 1 - k - ox0;                               // mirrored interior column inside the tile
+            if (xx < 0 || xx >= ow) continue;
+            const uint8_t pv = ob[r * kRszTW + xx];
+            const int ym = s_ym[r];
+            dplane[(long long)(kYO + oy0 + r) * D.pitch + D.w - 1 + k] = pv;
+            if (ym != INT_MIN) dplane[(long long)(kYO + ym) * D.pitch + D.w - 1 + k] = pv;
+        }
     }
 }
 
