@@ -867,11 +867,16 @@ struct DevCtx {
     __device__ __forceinline__ int atomic_add(int *p, int v) { return atomicAdd(p, v); }
     __device__ __forceinline__ void atomic_max(unsigned *p, unsigned v) { atomicMax(p, v); }
     __device__ __forceinline__ void hist_add(int *cnt, int key, bool valid, int nkeys) {
-        if (nkeys <= 32) {   // one ballot per key, one atomic per (warp, key): thousands of candidates share these few counters
-            for (int k = 0; k < nkeys; k++) {
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, valid && key == k);
-                if (m && (tid & 31) == 0) atomicAdd(&cnt[k], __popc(m));
+        if (nkeys <= 32) {
+            // thousands of candidates share these few counters: one atomic per (warp, key).  Lane k counts key k from bit-sliced
+            // ballots (one per key BIT plus the valid mask: at most 6 ballots instead of one ballot per key)
+            unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
+            const int lane = tid & 31;
+            for (int j = 0; (1 << j) < nkeys; j++) {
+                const unsigned bj = __ballot_sync(0xFFFFFFFFu, (key >> j) & 1);
+                m &= ((lane >> j) & 1) ? bj : ~bj;
             }
+            if (lane < nkeys && m) atomicAdd(&cnt[lane], __popc(m));
         } else if (valid) {
             atomicAdd(&cnt[key], 1);
         }
