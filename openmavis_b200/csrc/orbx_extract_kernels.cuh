@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
     const uint8_t *sp = s_src + (wid * kBlurStrip) * kBlurSP + 12 + 4 * lane;
     uint8_t *dst = plane_ptr(blur, L, b) + (long long)(kYO + ys) * L.pitch + kXO + xb;
     const int nrows = min(kBlurStrip, L.h - ys);       // output rows of the strip
+    uint8_t *drow = dst;
+    const long long pitch = L.pitch;
     // register window: the horizontal sums (<= 65280, 16 bits) of the last rows, packed in pairs  pr[j] = h[row - 1] | h[row] << 16,
     // so that the vertical pass is 3 IDP.2A (two taps each) + 1 multiply-add per pixel
     uint32_t pr[6][4], hprev[4];
@@ -360,13 +362,17 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
             for (int k = 0; k < 4; k++)   // rows r-6 .. r with weights 18 34 48 56 48 34 18: pairs (r-6, r-5), (r-4, r-3), (r-2, r-1), and row r
                 v[k] = __dp2a_lo(pr[1][k], 0x2212u, __dp2a_lo(pr[3][k], 0x3830u, __dp2a_lo(pr[5][k], 0x2230u, 18u * h[k] + 32768u)));
             const uint32_t lo = __byte_perm(v[0], v[1], 0x0062), hi = __byte_perm(v[2], v[3], 0x0062);
-            if (r - 6 < nrows) *reinterpret_cast<uint32_t *>(dst + (long long)(r - 6) * L.pitch) = __byte_perm(lo, hi, 0x5410);
+            // (a running row pointer the compiler cannot re-derive: it rebuilt dst + (r - 6) * pitch from the kernel parameters
+            //  for every row otherwise, ten instructions per store)
+            if (r - 6 < nrows) *reinterpret_cast<uint32_t *>(drow) = __byte_perm(lo, hi, 0x5410);
+            drow += pitch;
+            asm volatile("" : "+l"(drow));
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {   // pr[j] holds the pair that ends at row r - 5 + j
 #pragma unroll
             for (int j = 0; j < 5; j++) pr[j][k] = pr[j + 1][k];
-            pr[5][k] = hprev[k] | (h[k] << 16);
+            pr[5][k] = __byte_perm(hprev[k], h[k], 0x5410);   // hprev | h << 16 (both < 2^16) as ONE PRMT
             hprev[k] = h[k];
         }
     }
