@@ -290,6 +290,9 @@ struct BlurTiles { int base[kMaxLevels + 1]; };
 // one tensor map per level over the pyramid arena: dims (pitch bytes, plane rows, images), box = the staged blur tile
 struct BlurMaps { CUtensorMap m[kMaxLevels]; int use_tma; };
 
+__constant__ uint32_t kBlurW[13] = {0x30221200u, 0x12223038u, 0x22120000u, 0x22303830u, 0x00000012u, 0x12000000u, 0x30383022u,
+                                    0x00001222u, 0x38302212u, 0x00122230u, 0x2212u, 0x3830u, 0x2230u};
+
 __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, Geom G,
                                                           const int *__restrict__ tile_info, const __grid_constant__ BlurMaps maps, int img0) {
     extern __shared__ __align__(128) uint8_t s_src[];   // [kBlurSR][kBlurSP]
@@ -331,7 +334,9 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
     const uint8_t *sp = s_src + (wid * kBlurStrip) * kBlurSP + 12 + 4 * lane;
     uint8_t *dst = plane_ptr(blur, L, b) + (long long)(kYO + ys) * L.pitch + kXO + xb;
     const int nrows = min(kBlurStrip, L.h - ys);       // output rows of the strip
-    uint8_t *drow = dst;
+    unsigned long long drow = (unsigned long long)__cvta_generic_to_global(dst);
+    int nrows_k = nrows;
+    asm("" : "+r"(nrows_k));
     const long long pitch = L.pitch;
     // register window: the horizontal sums (<= 65280, 16 bits) of the last rows, packed in pairs  pr[j] = h[row - 1] | h[row] << 16,
     // so that the vertical pass is 3 IDP.2A (two taps each) + 1 multiply-add per pixel
@@ -352,21 +357,23 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
         uint32_t h[4];
         // pixel k needs bytes k+1 .. k+7 of the 12-byte window (wl, wc, wr): instead of shifting the pixels into place, the
         // kernel {18,34,48,56,48,34,18} is shifted inside the weight words (10 IDP.4A, no funnel shifts)
-        h[0] = __dp4a(wl, 0x30221200u, __dp4a(wc, 0x12223038u, 0u));
-        h[1] = __dp4a(wl, 0x22120000u, __dp4a(wc, 0x22303830u, __dp4a(wr, 0x00000012u, 0u)));
-        h[2] = __dp4a(wl, 0x12000000u, __dp4a(wc, 0x30383022u, __dp4a(wr, 0x00001222u, 0u)));
-        h[3] = __dp4a(wc, 0x38302212u, __dp4a(wr, 0x00122230u, 0u));
+        // (the weight words are constant-bank operands: as immediates ptxas re-materialised them into a handful of uniform registers
+        //  nine times per row)
+        h[0] = __dp4a(wl, kBlurW[0], __dp4a(wc, kBlurW[1], 0u));
+        h[1] = __dp4a(wl, kBlurW[2], __dp4a(wc, kBlurW[3], __dp4a(wr, kBlurW[4], 0u)));
+        h[2] = __dp4a(wl, kBlurW[5], __dp4a(wc, kBlurW[6], __dp4a(wr, kBlurW[7], 0u)));
+        h[3] = __dp4a(wc, kBlurW[8], __dp4a(wr, kBlurW[9], 0u));
         if (r >= 6) {
             uint32_t v[4];
 #pragma unroll
             for (int k = 0; k < 4; k++)   // rows r-6 .. r with weights 18 34 48 56 48 34 18: pairs (r-6, r-5), (r-4, r-3), (r-2, r-1), and row r
-                v[k] = __dp2a_lo(pr[1][k], 0x2212u, __dp2a_lo(pr[3][k], 0x3830u, __dp2a_lo(pr[5][k], 0x2230u, 18u * h[k] + 32768u)));
+                v[k] = __dp2a_lo(pr[1][k], kBlurW[10], __dp2a_lo(pr[3][k], kBlurW[11], __dp2a_lo(pr[5][k], kBlurW[12], 18u * h[k] + 32768u)));
             const uint32_t lo = __byte_perm(v[0], v[1], 0x0062), hi = __byte_perm(v[2], v[3], 0x0062);
             // (a running row pointer the compiler cannot re-derive: it rebuilt dst + (r - 6) * pitch from the kernel parameters
             //  for every row otherwise, ten instructions per store)
-            if (r - 6 < nrows) *reinterpret_cast<uint32_t *>(drow) = __byte_perm(lo, hi, 0x5410);
+            if (r - 6 < nrows_k) asm volatile("st.global.u32 [%0], %1;" ::"l"(drow), "r"(__byte_perm(lo, hi, 0x5410)) : "memory");
             drow += pitch;
-            asm volatile("" : "+l"(drow));
+            asm("" : "+l"(drow));
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {   // pr[j] holds the pair that ends at row r - 5 + j
