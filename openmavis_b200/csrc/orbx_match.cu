@@ -1471,7 +1471,10 @@ static void pool_worker(orbx_matcher_pool *p, int lane) {
             if (p->stop) return;
             seen = p->generation;
         }
-        for (int i = p->next.fetch_add(1); i < p->n_calls; i = p->next.fetch_add(1)) p->job(p->lanes[lane], i);
+        // a batch smaller than the pool uses the first lanes only: their buffers have their size from earlier calls (a lane's first
+        // call allocates), so a one-frame batch costs what a plain call costs
+        if (lane < p->n_calls)
+            for (int i = p->next.fetch_add(1); i < p->n_calls; i = p->next.fetch_add(1)) p->job(p->lanes[lane], i);
         {
             std::lock_guard<std::mutex> lk(p->mu);
             if (--p->running == 0) p->cv_done.notify_all();
