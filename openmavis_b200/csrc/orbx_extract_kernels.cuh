@@ -413,7 +413,9 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
 // ------------------------------------------------------------------------------------------------------
 constexpr int kFastWarps = 4;                 // warps per CTA = cells per tile (one warp per cell)
 constexpr int kFastThreads = kFastWarps * 32;
-constexpr int kFastStrip = 14;                // rows a lane marches through per work item (one 4-pixel word wide): two flag registers of 7 rows
+constexpr int kFastStrip = 13;                // rows a lane marches through per work item (one 4-pixel word wide): flag registers of 7 + 6 rows.
+                                              // (Cells are 35-42 rows high: three 13-row strips march 39 rows where three 14-row strips marched 42 —
+                                              //  0.660 -> 0.649 ms per 320 images; 12-row strips need a fourth strip: 0.778 ms)
 constexpr int kFastHalf = 7;                  // rows per flag register (byte = pixel, bit = row)
 constexpr int kFastMaxStrips = 13;            // strips with host-chosen start rows (FastTile::sr); taller cells use equal strips
 constexpr int kFastQueue = 512;               // per-warp survivor queue (u16 entries): < 64 left + up to 448 new (a flag register with more
@@ -516,7 +518,7 @@ __device__ __forceinline__ void reds_add64(uint32_t a, unsigned long long v) { a
 // (the centre of strip row i is img row i + 3).  A FAST-9 corner at threshold t has an arc of 9 ring pixels with |v - r| > t; an arc of 9
 // holds one pixel of every opposite pair (k, k + 8), so |v - r| > t must hold on at least one pixel of each of the four pairs of the even
 // ring positions: (0, +-3), (+-3, 0), (2, 2)/(-2, -2), (2, -2)/(-2, 2).  Byte-SIMD: 4 pixels per VABSDIFF4, the compare is the carry into
-// bit 7 of d + (127 - t) (or d >= 128); flags of strip rows 0-6 go to mA, rows 7-13 to mB (byte = pixel, bit = row).
+// bit 7 of d + (127 - t) (or d >= 128); flags of strip rows 0-6 go to mA, rows 7-12 to mB (byte = pixel, bit = row).
 // (On the bench images: 12.5 % of the pixels survive, 4.2 % are corners; the former test on the pairs (0, 8) and (4, 12) alone left 23.5 %.)
 // (Moving the byte funnel shifts and the flag gather to the FMA pipe — mul.hi + mad instead of PRMT, mad.hi instead of SHF + LOP3 — was
 //  measured slower, 0.73 vs 0.705 ms: the ALU pipe drops from 65 % to 56 % but the kernel is bound by issue slots, not by that pipe.)
@@ -754,8 +756,8 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
                             uint32_t qa = q + 2 * (qn + inc - cnt), qb = qa + 2 * ca;
                             qn += __shfl_sync(0xFFFFFFFFu, inc, 31);
                             const int ab2 = abase + kFastHalf * IP;
-                            // branch-free listing: every lane walks its 2 x 28 flag positions once (flag test, predicated store, predicated
-                            // pointer bump, entry value: 4 instructions per position, 224 per append).  The former next-set-bit loop ran as
+                            // branch-free listing: every lane walks its 28 + 24 flag positions once (flag test, predicated store, predicated
+                            // pointer bump, entry value: 4 instructions per position, 208 per append).  The former next-set-bit loop ran as
                             // many trips as the fullest lane had flags — 12 on average with 7 of 32 lanes active, 450 instructions per
                             // append (round 2: k_fast 0.729 -> 0.661 ms per 320 images).
 #pragma unroll
@@ -763,7 +765,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
 #pragma unroll
                                 for (int i = 0; i < kFastHalf; i++) {
                                     if (fa & (1u << (8 * px + i))) { sts16(qa, (uint32_t)(abase + i * IP + px)); qa += 2; }
-                                    if (fb & (1u << (8 * px + i))) { sts16(qb, (uint32_t)(ab2 + i * IP + px)); qb += 2; }
+                                    if (kFastHalf + i < kFastStrip && (fb & (1u << (8 * px + i)))) { sts16(qb, (uint32_t)(ab2 + i * IP + px)); qb += 2; }
                                 }
                             }
                             __syncwarp();
