@@ -622,6 +622,13 @@ struct FastStats { unsigned long long tested, survivors, corners, kept, retry_ce
 
 struct FastArgs { int ymax, total_cells, img0, kb_words; long long cand_per_image; };
 
+// ceil(2^32 / d) for 2 <= d < 128: x / d == umulhi(x, magic) for x * d < 2^32 (d == 1 is handled by the caller)
+struct DivMagicTable {
+    uint32_t v[128];
+    constexpr DivMagicTable() : v() { for (int d = 1; d < 128; d++) v[d] = 0xFFFFFFFFu / (uint32_t)d + 1u; }
+};
+__constant__ DivMagicTable kDivMagic = DivMagicTable();
+
 template <int IP>
 __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restrict__ pyr, const FastTile *__restrict__ tiles, const FastArgs A,
                                                        const orbx_image_params *__restrict__ params,
@@ -699,7 +706,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
         const int wdt = cx1 - cx0;
         const int w0 = cx0 >> 2, w1 = (cx1 - 1) >> 2;   // words of a row that hold tested pixels of this cell
         const int nw = w1 - w0 + 1;
-        const float inv_nw = 1.0f / (float)nw;
+        const float inv_nw = __fdividef(1.0f, (float)nw);   // (2 ulp are far inside small_div's margin; the IEEE division is 20 instructions)
         const int nflat = nstr * nw;                    // work items: (strip of rs rows) x (word column)
         const int nkb = (Y * wdt + 31) >> 5;            // words of the cell's keep bitmap
         bool any_kept = false;
@@ -818,7 +825,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
             const long long cand0 = ((long long)(unsigned)t3.z) | ((long long)t3.w << 32);
             uint32_t *out = cells + (long long)b * A.cand_per_image + cand0 + (long long)k * cell_cap;
             // row of bit x = x / wdt as a multiply-high (exact for x * wdt < 2^32; x < 2^16 here)
-            const uint32_t magic = 0xFFFFFFFFu / (uint32_t)wdt + 1u;
+            const uint32_t magic = wdt < 128 ? kDivMagic.v[wdt] : 0xFFFFFFFFu / (uint32_t)wdt + 1u;   // (table: the division is 25 instructions)
             // border-relative coordinates (src/ORBextractor.cc:784-791): level coordinate - 16
             const uint32_t base = (uint32_t)(tx0 + k * wc - kFastBorder) | ((uint32_t)(ty0 - kFastBorder) << 12);
             const uint32_t scc = sc1 + cx0;
@@ -841,7 +848,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
                     if (lo) v0 &= v0 - 1; else v1 &= v1 - 1;
                     if (li < kFastCorners) sts16(cl + 2 * li, (uint32_t)bit);
                     else if (total + li < cell_cap) {
-                        const int row = __umulhi((uint32_t)bit, magic), xc = bit - row * wdt;
+                        const int row = wdt == 1 ? bit : (int)__umulhi((uint32_t)bit, magic), xc = bit - row * wdt;   // (2^32 / 1 has no 32-bit magic)
                         out[total + li] = (base + (uint32_t)xc + ((uint32_t)row << 12)) | (lds8(scc + row * IP + xc) << 24);
                     }
                     li++;
@@ -851,7 +858,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_fast(const uint8_t *__restr
 #pragma unroll 1
                 for (int j = lane; j < nlist; j += 32) {
                     const int bit = (int)lds16(cl + 2 * j);
-                    const int row = __umulhi((uint32_t)bit, magic), xc = bit - row * wdt;
+                    const int row = wdt == 1 ? bit : (int)__umulhi((uint32_t)bit, magic), xc = bit - row * wdt;   // (2^32 / 1 has no 32-bit magic)
                     out[total + j] = (base + (uint32_t)xc + ((uint32_t)row << 12)) | (lds8(scc + row * IP + xc) << 24);
                 }
                 __syncwarp();

@@ -285,12 +285,21 @@ def test_compute_stereo_matches(bf):
     assert n2 == n and np.array_equal(u2[:N].view(np.uint32), u[:N].view(np.uint32)) and np.array_equal(d2[:N].view(np.uint32), d[:N].view(np.uint32))
 
 
-@pytest.mark.parametrize('w,h,nl,sf,nf', [(751, 479, 8, 1.2, 800), (333, 247, 5, 1.2, 500), (1000, 341, 6, 1.3, 900), (640, 480, 3, 2.0, 600)])
+@pytest.mark.parametrize('w,h,nl,sf,nf', [(751, 479, 8, 1.2, 800), (333, 247, 5, 1.2, 500), (1000, 341, 6, 1.3, 900), (640, 480, 3, 2.0, 600),
+                                            (1083, 203, 3, 1.2, 900), (1119, 150, 2, 1.2, 600)])
 def test_odd_geometries_and_pyramid_shapes(w, h, nl, sf, nf):
     """Widths / strides that are not multiples of 4 or 16, wide aspect ratios (2-3 quadtree roots), other level counts and
-    scale factors: planes, tiles and taps are derived per handle, nothing may assume the benchmark geometry."""
+    scale factors, level widths whose last FAST cell is ONE pixel wide (1083, 1119): planes, tiles and taps are derived per handle, nothing
+    may assume the benchmark geometry."""
     _need_gpu()
     img = synth_image(w, h, 9000 + w)
+    if w in (1083, 1119):   # isolated bright pixels (FAST corners) in the one tested column of the last cell of level 0, and its mirror
+        n = (w - 32) // 35      # (src/ORBextractor.cc:729-751: borders 16, nCols, wCell)
+        xt = 16 + (n - 1) * -(-(w - 32) // n) + 3
+        for y in range(30, h - 30, 23):
+            for x in (xt, w - 1 - xt):
+                img[y - 4:y + 5, x - 4:x + 5] = 20
+                img[y, x] = 255
     rig = ob.RigExtractor(w, h, 2, nf, sf, nl)
     res = rig.extract([img, img[:, ::-1].copy()], ob.make_params(2, nf, 20, 7, [(0, 0), (w // 3, w // 2)]))
     E = O.OracleExtractor(nf, sf, nl, 20, 7)
