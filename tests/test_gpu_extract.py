@@ -286,7 +286,7 @@ def test_compute_stereo_matches(bf):
 
 
 @pytest.mark.parametrize('w,h,nl,sf,nf', [(751, 479, 8, 1.2, 800), (333, 247, 5, 1.2, 500), (1000, 341, 6, 1.3, 900), (640, 480, 3, 2.0, 600),
-                                            (1083, 203, 3, 1.2, 900), (1119, 150, 2, 1.2, 600)])
+                                            (1083, 203, 3, 1.2, 900), (1119, 150, 2, 1.2, 600), (700, 1083, 2, 1.2, 900)])
 def test_odd_geometries_and_pyramid_shapes(w, h, nl, sf, nf):
     """Widths / strides that are not multiples of 4 or 16, wide aspect ratios (2-3 quadtree roots), other level counts and
     scale factors, level widths whose last FAST cell is ONE pixel wide (1083, 1119): planes, tiles and taps are derived per handle, nothing
@@ -300,6 +300,12 @@ def test_odd_geometries_and_pyramid_shapes(w, h, nl, sf, nf):
             for x in (xt, w - 1 - xt):
                 img[y - 4:y + 5, x - 4:x + 5] = 20
                 img[y, x] = 255
+    if h == 1083:           # the same for the ONE tested row of the last cell row
+        n = (h - 32) // 35
+        yt = 16 + (n - 1) * -(-(h - 32) // n) + 3
+        for x in range(30, w - 30, 23):
+            img[yt - 4:yt + 5, x - 4:x + 5] = 20
+            img[yt, x] = 255
     rig = ob.RigExtractor(w, h, 2, nf, sf, nl)
     res = rig.extract([img, img[:, ::-1].copy()], ob.make_params(2, nf, 20, 7, [(0, 0), (w // 3, w // 2)]))
     E = O.OracleExtractor(nf, sf, nl, 20, 7)
