@@ -425,3 +425,65 @@ def test_first_handle_of_a_process_at_any_geometry(w, h, nf):
     assert out.returncode == 0, out.stderr[-800:]
     a, b = (int(x) for x in out.stdout.split())
     assert a >= nf * 0.9 and b >= nf * 0.9
+
+
+def _fuzz_case(seed):
+    """A random but supported extractor configuration (src/ORBextractor.cc:351-420 accepts any of them) and a random image."""
+    rng = np.random.default_rng(77000 + seed)
+    nl = int(rng.integers(1, 9))
+    sf = float(rng.choice([1.1, 1.2, 1.25, 1.5, 2.0]))
+    smallest = 110                                     # the smallest level keeps a few cells in both directions
+    while smallest * sf ** (nl - 1) > 800: nl -= 1     # (bounded image sizes: the CPU oracle runs every case)
+    lo = int(np.ceil(smallest * sf ** (nl - 1)))
+    w = int(rng.integers(max(lo, 160), max(lo, 160) + 700))
+    h = int(rng.integers(max(lo, 120), max(lo, 120) + 500))
+    w = max(w, int(0.65 * h) + 45)                      # (nIni = round(width / height) is 0 on no level: the reference divides by it)
+    nf = int(rng.integers(30, 2500))
+    f = 1.0 / sf
+    n0 = nf * (1 - f) / (1 - f ** nl) if nl > 1 else nf   # features asked of level 0 (src/ORBextractor.cc:373-384)
+    if n0 > 1900: nf = int(nf * 1900 / n0)              # (the product's quadtree workspace holds about 2000 nodes per level)
+    ini = int(rng.integers(3, 70)); mn = int(rng.integers(1, ini + 1))
+    kind = rng.choice(['synth', 'synth', 'synth', 'noise', 'checker', 'halfflat', 'lowcontrast'])
+    if kind == 'noise':
+        img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    elif kind == 'checker':
+        p = int(rng.integers(3, 12)); yy, xx = np.mgrid[0:h, 0:w]
+        img = ((((yy // p) + (xx // p)) % 2) * int(rng.integers(10, 200)) + 20).astype(np.uint8)
+    else:
+        img = synth_image(w, h, 5000 + seed)
+        if kind == 'halfflat': img[:, : w // 2] = 90
+        if kind == 'lowcontrast': img = (img // 6 + 100).astype(np.uint8)
+    a = int(rng.integers(0, w)); b = int(rng.integers(0, w))
+    lap = (0, 0) if rng.random() < 0.4 else (min(a, b), max(a, b))
+    return w, h, nl, sf, nf, ini, mn, img, lap, kind
+
+
+@pytest.mark.parametrize('seed', range(int(os.environ.get('ORBX_FUZZ_N', '48'))))
+def test_random_configurations_against_the_oracle(seed):
+    """Differential test over random geometries (level counts, scale factors, image sizes that are multiples of nothing), feature
+    budgets, FAST thresholds, lapping areas and image kinds: pyramid planes incl. frame, FAST candidates per level (position,
+    order, response) and the final keypoints / descriptors / return value, bit-exact against the CPU oracle and against the compiled reference
+    (ORBX_FUZZ_N widens the sweep: 800 configurations were run green on the B200 in round 2)."""
+    _need_gpu()
+    w, h, nl, sf, nf, ini, mn, img, lap, kind = _fuzz_case(seed)
+    rig = ob.RigExtractor(w, h, 1, nf, sf, nl)
+    res = rig.extract([img], ob.make_params(1, nf, ini, mn, lap))
+    E = O.OracleExtractor(nf, sf, nl, ini, mn)
+    mono, kps, desc = E(img, lap)
+    ctx = (seed, w, h, nl, sf, nf, ini, mn, lap, kind)
+    for l in range(nl):
+        assert np.array_equal(E.level(l), rig.pyramid_level(0, l, with_border=True)), ('pyramid', l) + ctx
+        xs, ys, sc = E.level_candidates(l)
+        gx, gy, gs = rig.debug_candidates(0, l)
+        assert np.array_equal(xs, gx) and np.array_equal(ys, gy) and np.array_equal(sc, gs), ('candidates', l) + ctx
+    gmono, gk, gd = res[0]
+    assert gmono == mono and len(gk) == len(kps), ('counts', gmono, mono, len(gk), len(kps)) + ctx
+    for f in KPF:
+        assert np.array_equal(kps[f].view(np.uint32), gk[f].view(np.uint32)), ('field', f) + ctx
+    assert np.array_equal(desc, gd), ('descriptors',) + ctx
+    # and against the reference's own object code (src/ORBextractor.cc compiled unmodified, oracle/_ref)
+    rmono, rk, rd = O.RefExtractor(nf, sf, nl, ini, mn, fma=False)(img, lap)
+    assert gmono == rmono and len(gk) == len(rk), ('reference counts',) + ctx
+    for f in KPF:
+        assert np.array_equal(rk[f].view(np.uint32), gk[f].view(np.uint32)), ('reference field', f) + ctx
+    assert np.array_equal(rd, gd), ('reference descriptors',) + ctx
