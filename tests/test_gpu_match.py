@@ -860,7 +860,7 @@ def _random_frame(rng, ncam, n_per_cam, size=200.0, pool=6):
     return frame, base
 
 
-@pytest.mark.parametrize('seed', range(12))
+@pytest.mark.parametrize('seed', range(int(os.environ.get('ORBX_STRESS_N', '12'))))
 def test_ordered_resolver_stress(seed):
     """Many small, dense, adversarial cases of the three ordered matchers (claims in point order, eviction, mirrors): every one must
     equal the sequential oracle.  Sizes straddle the resolver's 1024-point window and its 12-entry touch cache."""

@@ -17,6 +17,7 @@ from openmavis_b200.synth import synth_descriptors
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 p = R.p
+TRIALS_X = int(os.environ.get('ORBX_GLUE_TRIALS_X', '1'))   # multiplies the random scenarios per test (a wide sweep before a release)
 _glue = None
 
 
@@ -42,7 +43,7 @@ def test_descriptor_distance_host_side():
 @pytest.mark.parametrize('ncam', [1, 2, 4])
 def test_search_by_projection_frame_mappoints(ncam):
     rng = np.random.default_rng(200 + ncam)
-    for trial in range(6):
+    for trial in range(6 * TRIALS_X):
         S = R.sbp_scenario(rng, ncam, int(rng.integers(200, 1500)), crowded=trial % 2 == 1)
         th = float([1.0, 3.0, 6.0][trial % 3]); far = trial % 4 == 3
         N = int(S['cam_off'][-1])
@@ -60,7 +61,7 @@ def test_search_by_projection_frame_mappoints(ncam):
 
 def test_search_for_initialization():
     rng = np.random.default_rng(18)
-    for trial in range(8):
+    for trial in range(8 * TRIALS_X):
         n1, n2 = int(rng.integers(100, 1500)), int(rng.integers(100, 1500))
         k2 = R.make_kps(n2, rng, lattice=6 if trial % 2 else None); k2['octave'][rng.random(n2) < 0.6] = 0
         d2 = synth_descriptors(n2, 1900 + trial)
@@ -83,7 +84,7 @@ def test_search_for_initialization():
 @pytest.mark.parametrize('ncam', [1, 2, 4])
 def test_search_by_bow_keyframe_frame(ncam):
     rng = np.random.default_rng(300 + ncam)
-    for trial in range(6):
+    for trial in range(6 * TRIALS_X):
         nF = int(rng.integers(300, 1500)); nKF = int(rng.integers(300, 1500))
         dF = synth_descriptors(nF, 2900 + trial)
         dF[5:40] = dF[5]                                     # equal distances
@@ -200,6 +201,11 @@ def test_search_for_triangulation_pinhole(ncam, coarse):
     for S in R.sft_pinhole_scenarios(ncam, coarse):
         na, a = R.call_sft_pinhole(R.RM(), S)
         nb, b = R.call_sft_pinhole(G(), S)
+        ub = -1 if coarse else R.sft_row_on_uninitialised_pair(S)
+        if ub >= 0 and S['chk']:
+            continue                     # (with the rotation filter a different match in that row can shift the histogram for every row)
+        if ub >= 0 and a[ub] != b[ub]:   # the one row the reference decides on uninitialised R12 / t12
+            na -= int(a[ub] >= 0); nb -= int(b[ub] >= 0); a[ub] = b[ub] = -1
         assert na == nb, (S['trial'], na, nb)
         assert np.array_equal(a, b), (S['trial'], int((a != b).sum()))
         tot += na

@@ -11,6 +11,8 @@ import pytest
 import oracle_lib as O
 from openmavis_b200.synth import synth_descriptors
 
+TRIALS_X = int(os.environ.get('ORBX_GLUE_TRIALS_X', '1'))   # multiplies the random scenarios per test (a wide sweep before a release)
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KP = O.KP_DTYPE
 _lib = None
@@ -56,7 +58,7 @@ def test_three_maxima():
     rng = np.random.default_rng(5)
     L = RM()
     O.lib().orc_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-    for trial in range(400):
+    for trial in range(400 * TRIALS_X):
         sizes = rng.integers(0, [3, 10, 60][trial % 3], 30).astype(np.int32)
         if trial % 7 == 0:
             sizes[rng.integers(0, 30, 3)] = sizes.max()       # ties between the maxima
@@ -69,7 +71,7 @@ def test_three_maxima():
 def test_frame_grid_get_features_in_area():
     rng = np.random.default_rng(6)
     L = RM()
-    for trial in range(60):
+    for trial in range(60 * TRIALS_X):
         n = int(rng.integers(1, 1500))
         k = make_kps(n, rng, lattice=4 if trial % 3 == 0 else None)
         bounds = np.array([0, 640, 0, 480], np.float32) if trial % 2 else np.array([-13.5, 655.25, -9.0, 489.75], np.float32)
@@ -129,7 +131,7 @@ def test_search_by_projection_frame_mappoints(ncam):
     and the left/right mirror writes."""
     rng = np.random.default_rng(100 + ncam)
     L = RM(); Lo = O.lib()
-    for trial in range(12):
+    for trial in range(12 * TRIALS_X):
         S = sbp_scenario(rng, ncam, int(rng.integers(200, 1500)), crowded=trial % 2 == 1)
         th = float([1.0, 3.0, 6.0][trial % 3]); far = trial % 4 == 3; nnr = 0.8
         N = int(S['cam_off'][-1])
@@ -155,7 +157,7 @@ def test_search_by_projection_frame_mappoints(ncam):
 def test_search_for_initialization():
     rng = np.random.default_rng(8)
     L = RM(); Lo = O.lib()
-    for trial in range(20):
+    for trial in range(20 * TRIALS_X):
         n1, n2 = int(rng.integers(100, 1500)), int(rng.integers(100, 1500))
         k2 = make_kps(n2, rng, lattice=6 if trial % 2 else None); k2['octave'][rng.random(n2) < 0.6] = 0
         d2 = synth_descriptors(n2, 900 + trial)
@@ -200,7 +202,7 @@ def test_search_for_triangulation(ncam, coarse):
     rng = np.random.default_rng(40 + 10 * ncam + coarse)
     L = RM(); Lo = O.lib()
     L.refm_pair_hash.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
-    for trial in range(10):
+    for trial in range(10 * TRIALS_X):
         per1 = [int(rng.integers(150, 500)) for _ in range(ncam)]; per2 = [int(rng.integers(150, 500)) for _ in range(ncam)]
         off1 = np.concatenate([[0], np.cumsum(per1)]).astype(np.int32); off2 = np.concatenate([[0], np.cumsum(per2)]).astype(np.int32)
         n1, n2 = int(off1[-1]), int(off2[-1])
@@ -252,7 +254,7 @@ def sft_pinhole_scenarios(ncam, coarse):
     cam = np.array([[400, 400, 320, 240], [410, 405, 318, 243], [395, 398, 322, 238], [402, 401, 321, 241]], np.float32)
     rel = np.array([[-0.12, 0.0, 0.0], [0.05, -0.03, 0.0], [-0.2, 0.03, 0.01]], np.float32)        # right, side-left, side-right from the left camera
     relc = np.concatenate([np.zeros((1, 3), np.float32), rel])
-    for trial in range(8):
+    for trial in range(8 * TRIALS_X):
         per1 = [int(rng.integers(150, 500)) for _ in range(ncam)]; per2 = [int(rng.integers(150, 500)) for _ in range(ncam)]
         off1 = np.concatenate([[0], np.cumsum(per1)]).astype(np.int32); off2 = np.concatenate([[0], np.cumsum(per2)]).astype(np.int32)
         n1, n2 = int(off1[-1]), int(off2[-1])
@@ -283,6 +285,31 @@ def sft_pinhole_scenarios(ncam, coarse):
         yield dict(trial=trial, ncam=ncam, coarse=coarse, off1=off1, off2=off2, n1=n1, n2=n2, k1=k1, k2=k2, d1=d1, d2=d2, fv1=fv1, fv2=fv2, mp1=mp1, mp2=mp2,
                    ur1=ur1, ur2=ur2, only_stereo=only_stereo, cam=np.ascontiguousarray(cam), t1w=t1w, rel=np.ascontiguousarray(rel), sf=sf,
                    sigma2=(sf * sf).astype(np.float32), chk=trial % 2)
+
+
+def sft_row_on_uninitialised_pair(S):
+    """KF1 index of the row that is tested on uninitialised geometry, or -1: if the FIRST candidate of the call that passes the descriptor
+    gate is a camera combination without a branch in the pair selection (left / side-right, right / side-left, ...), the reference
+    evaluates epipolarConstrain on R12 / t12 it never initialised (src/ORBmatcher.cc:1152-1154, 1301-1387) — undefined behaviour; that one
+    row has nothing to be compared against (the product tests the candidate with the left-left pair)."""
+    if S['ncam'] < 4:
+        return -1
+    branch = {(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0), (2, 2), (1, 3), (3, 1), (3, 3)}
+    (nodes1, ptr1, ord1), (nodes2, ptr2, ord2) = S['fv1'], S['fv2']
+    pos2 = {int(n): k for k, n in enumerate(nodes2)}
+    for a, node in enumerate(nodes1):
+        b = pos2.get(int(node))
+        if b is None:
+            continue
+        for i1 in ord1[ptr1[a]:ptr1[a + 1]]:
+            if S['mp1'][i1]:
+                continue
+            for i2 in ord2[ptr2[b]:ptr2[b + 1]]:
+                if S['mp2'][i2] or int(np.unpackbits(S['d1'][i1] ^ S['d2'][i2]).sum()) > 50:
+                    continue
+                c1 = int(np.searchsorted(S['off1'], i1, side='right') - 1); c2 = int(np.searchsorted(S['off2'], i2, side='right') - 1)
+                return -1 if (c1, c2) in branch else int(i1)
+    return -1
 
 
 def call_sft_pinhole(L, S):
@@ -316,7 +343,7 @@ def test_search_by_bow_keyframe_frame(ncam):
     cameras 1-3 nested in camera 0's TH_LOW test, already-matched rule, rotation histogram."""
     rng = np.random.default_rng(300 + ncam)
     L = RM(); Lo = O.lib()
-    for trial in range(10):
+    for trial in range(10 * TRIALS_X):
         nF = int(rng.integers(300, 1500)); nKF = int(rng.integers(300, 1500))
         dF = synth_descriptors(nF, 2900 + trial)
         dF[5:40] = dF[5]
@@ -346,7 +373,7 @@ def test_search_by_bow_keyframe_frame(ncam):
 def bow_keyframes_scenarios():
     """(n1, n2, d1, d2, a1, a2, fv1, fv2, s1, s2) per trial: planted neighbours, duplicate rows, skipped features, rotated angles."""
     rng = np.random.default_rng(55)
-    for trial in range(12):
+    for trial in range(12 * TRIALS_X):
         n1, n2 = int(rng.integers(300, 1500)), int(rng.integers(300, 1500))
         d2 = synth_descriptors(n2, 5900 + trial)
         d2[5:40] = d2[5]
@@ -388,7 +415,7 @@ def sbp_last_scenarios(ncam):
     occupied keypoints, rectified-stereo coordinates (one camera), the three direction gates, rotation filter on / off."""
     rng = np.random.default_rng(400 + ncam)
     w = h = 512
-    for trial in range(12):
+    for trial in range(12 * TRIALS_X):
         per = [int(rng.integers(200, 700)) for _ in range(ncam)]
         cam_off = np.concatenate([[0], np.cumsum(per)]).astype(np.int32)
         N = int(cam_off[-1])
@@ -467,7 +494,7 @@ def test_fuse_keyframe_mappoints():
     rng = np.random.default_rng(66)
     L = RM(); Lo = O.lib()
     w, h = 640, 480
-    for trial in range(12):
+    for trial in range(12 * TRIALS_X):
         n = int(rng.integers(300, 2000)); nq = int(rng.integers(200, 1500))
         k = make_kps(n, rng, w, h, lattice=5 if trial % 2 else None)
         desc = synth_descriptors(n, 6900 + trial)
@@ -506,7 +533,7 @@ def fuse_graph_scenarios():
     point, and map points that appear twice in the candidate list."""
     rng = np.random.default_rng(67)
     w, h = 640, 480
-    for trial in range(10):
+    for trial in range(10 * TRIALS_X):
         n = int(rng.integers(300, 2000)); nq = int(rng.integers(200, 1500))
         k = make_kps(n, rng, w, h, lattice=5 if trial % 2 else None)
         desc = synth_descriptors(n, 6700 + trial)
@@ -580,7 +607,7 @@ def _planted_points(rng, k, desc, npts, w, h, spread=4.0):
 def reloc_scenarios():
     rng = np.random.default_rng(77)
     w = h = 512
-    for trial in range(12):
+    for trial in range(12 * TRIALS_X):
         n = int(rng.integers(300, 1500)); npts = int(rng.integers(200, 1500))
         k = make_kps(n, rng, w, h, lattice=8 if trial % 2 else None)
         desc = synth_descriptors(n, 7700 + trial)
@@ -623,7 +650,7 @@ def test_search_by_projection_relocalisation():
 def kf_sim3_scenarios(with_kfs):
     rng = np.random.default_rng(88 + with_kfs)
     w, h = 640, 480
-    for trial in range(10):
+    for trial in range(10 * TRIALS_X):
         n = int(rng.integers(300, 1500)); npts = int(rng.integers(200, 1500))
         k = make_kps(n, rng, w, h, lattice=8 if trial % 2 else None)
         desc = synth_descriptors(n, 8800 + trial)
@@ -668,7 +695,7 @@ def test_search_by_projection_keyframe_sim3(with_kfs):
 def sim3_scenarios():
     rng = np.random.default_rng(99)
     w, h = 640, 480
-    for trial in range(10):
+    for trial in range(10 * TRIALS_X):
         n1 = int(rng.integers(300, 1200)); n2 = int(rng.integers(300, 1200))
         sf = np.array([np.float32(1.2) ** i for i in range(8)], np.float32)
         k2 = make_kps(n2, rng, w, h, lattice=6 if trial % 2 else None); d2 = synth_descriptors(n2, 9900 + trial)
@@ -732,7 +759,7 @@ def test_search_by_sim3():
 def fuse_sim3_scenarios():
     rng = np.random.default_rng(111)
     w, h = 640, 480
-    for trial in range(10):
+    for trial in range(10 * TRIALS_X):
         n = int(rng.integers(300, 2000)); nq = int(rng.integers(200, 1500))
         k = make_kps(n, rng, w, h, lattice=5 if trial % 2 else None)
         desc = synth_descriptors(n, 11100 + trial)
