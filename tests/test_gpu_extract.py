@@ -285,6 +285,36 @@ def test_compute_stereo_matches(bf):
     assert n2 == n and np.array_equal(u2[:N].view(np.uint32), u[:N].view(np.uint32)) and np.array_equal(d2[:N].view(np.uint32), d[:N].view(np.uint32))
 
 
+@pytest.mark.parametrize('seed', range(int(os.environ.get('ORBX_STEREO_N', '6'))))
+def test_compute_stereo_matches_random_pairs(seed):
+    """ComputeStereoMatches (src/Frame.cc:1057-1219) over random image sizes, feature budgets, disparity fields (incl. small and negative
+    disparities, which the reference rejects), noise levels and baselines: match count, mvuRight and mvDepth bits == the oracle."""
+    _need_gpu()
+    rng = np.random.default_rng(31000 + seed)
+    w = int(rng.integers(400, 900)); h = int(rng.integers(300, 600)); nf = int(rng.integers(300, 1800))
+    left = synth_image(w, h, 7000 + seed)
+    xs = np.arange(w)
+    disp = (rng.uniform(-2, 25) + rng.uniform(2, 20) * np.sin(xs / rng.uniform(40, 200) + rng.uniform(0, 6))).astype(np.int64)
+    right = left[:, np.clip(xs + disp, 0, w - 1)]
+    amp = int(rng.integers(0, 6))
+    right = np.clip(right.astype(np.int32) + rng.integers(-amp, amp + 1, right.shape), 0, 255).astype(np.uint8)
+    if rng.random() < 0.3:
+        right = np.roll(right, int(rng.integers(-2, 3)), axis=0)       # imperfect rectification: rows off by up to 2
+    mb = float(rng.uniform(0.05, 0.6)); mbf = float(mb * rng.uniform(200, 500))
+    rig = ob.RigExtractor(w, h, 2, nf)
+    res = rig.extract([left, right], ob.make_params(2, nf, 20, 7, (0, 0)))
+    n, u, d = rig.compute_stereo_matches(0, 1, mb, mbf)
+    EL = O.OracleExtractor(nf, 1.2, 8, 20, 7); ER = O.OracleExtractor(nf, 1.2, 8, 20, 7)
+    EL(left, (0, 0)); ER(right, (0, 0))
+    N = len(res[0][1])
+    ru = np.zeros(N, np.float32); rd = np.zeros(N, np.float32)
+    O.lib().orc_compute_stereo_matches.argtypes = [O.C.c_void_p, O.C.c_void_p, O.C.c_float, O.C.c_float, O.C.c_void_p, O.C.c_void_p]
+    rn = O.lib().orc_compute_stereo_matches(EL.h, ER.h, mb, mbf, O.p(ru), O.p(rd))
+    assert rn == n, (seed, rn, n)
+    assert np.array_equal(ru.view(np.uint32), u[:N].view(np.uint32)), (seed, int((ru != u[:N]).sum()))
+    assert np.array_equal(rd.view(np.uint32), d[:N].view(np.uint32)), seed
+
+
 @pytest.mark.parametrize('w,h,nl,sf,nf', [(751, 479, 8, 1.2, 800), (333, 247, 5, 1.2, 500), (1000, 341, 6, 1.3, 900), (640, 480, 3, 2.0, 600),
                                             (1083, 203, 3, 1.2, 900), (1119, 150, 2, 1.2, 600), (700, 1083, 2, 1.2, 900)])
 def test_odd_geometries_and_pyramid_shapes(w, h, nl, sf, nf):
