@@ -594,8 +594,11 @@ __device__ __forceinline__ void fast_score_pair(uint32_t img, uint32_t scb, int 
     if (c1) sts8(scb + a1, (uint32_t)s1);
     const unsigned b0 = __ballot_sync(0xFFFFFFFFu, c0), b1 = __ballot_sync(0xFFFFFFFFu, c1);
     const int n0 = __popc(b0);
-    if (c0) { const int p = ncl + __popc(b0 & lt_mask); if (p < kFastCorners) sts16(cl + 2 * p, (uint32_t)a0); }
-    if (c1) { const int p = ncl + n0 + __popc(b1 & lt_mask); if (p < kFastCorners) sts16(cl + 2 * p, (uint32_t)a1); }
+    {   // (positions for every lane, predicated stores: as two divergent blocks this tail cost 10 more instructions per call)
+        const int p0 = ncl + __popc(b0 & lt_mask), p1 = ncl + n0 + __popc(b1 & lt_mask);
+        if (c0 && p0 < kFastCorners) sts16(cl + 2 * p0, (uint32_t)a0);
+        if (c1 && p1 < kFastCorners) sts16(cl + 2 * p1, (uint32_t)a1);
+    }
     ncl += n0 + __popc(b1);
 }
 
@@ -610,7 +613,9 @@ __device__ __forceinline__ bool fast_nms_one(uint32_t sc1, uint32_t kb, int row,
               ur = lds8(n - IP + 1), dr = lds8(n + IP + 1);
     const int ml = xl > 0 ? max(l, max(ul, dl)) : -1, mr = xl < wc - 1 ? max(r, max(ur, dr)) : -1;
     const bool keep = s > max(max(u, d), max(ml, mr));
-    if (keep) { const int bit = row * wdt + xl; reds_or32(kb + 4 * (bit >> 5), 1u << (bit & 31)); }
+    const int bit = row * wdt + xl;
+    const uint32_t ka = kb + 4 * (bit >> 5), kv = 1u << (bit & 31);
+    if (keep) reds_or32(ka, kv);
     return keep;
 }
 
