@@ -402,14 +402,15 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur(const uint8_t *__restr
 // one CTA = one tile of up to G adjacent cells of a cell row, staged once in shared memory, one warp per cell.
 //   0. the tile (4 cells) is staged once (one TMA tensor copy); from then on every WARP works alone on its own cell — no CTA barriers, no
 //      shared counters, no atomics except the keep bitmap words two neighbouring cells share;
-//   1. quick reject with byte-SIMD (VABSDIFF4): a corner needs |v - r| > t on at least one of the ring pixels {0, 8} and one of
-//      {4, 12}.  One lane marches down up to 8 rows of one 4-pixel word column with the column in registers (no index arithmetic
-//      in the loop); the 32 survivor flags of a lane end up in one register;
-//   2. survivors are compacted into the warp's queue (one warp scan per 512 pixels) and scored two at a time with packed
-//      u16x2 3-input min/max (VIMNMX3.U16x2): no divergence, no per-threshold corner test;
+//   1. quick reject with byte-SIMD (VABSDIFF4): a corner needs |v - r| > t on one pixel of each of the four opposite pairs of the
+//      even ring positions (fast_quick8).  One lane marches down a strip of 13 rows of one 4-pixel word column with the column in
+//      registers (no index arithmetic in the loop); the survivor flags of a lane end up in two registers (7 + 6 rows);
+//   2. survivors are compacted into the warp's queue (one warp scan per work item, then a branch-free walk over the flag positions
+//      with predicated stores) and scored two at a time with packed u16x2 3-input min/max (VIMNMX3.U16x2): no divergence, no
+//      per-threshold corner test;
 //   3. strict 3x3 maximum inside the cell over the warp's corner list -> keep bitmap;
 //   4. a cell without a keypoint repeats 1-3 with minThFAST (only its own warp, rare);
-//   5. emission in row-major order (the order of cv::FAST): lane = row, 64-bit row masks, one warp scan.
+//   5. emission in row-major order (the order of cv::FAST): a lane takes 64 bits of the keep bitmap, one warp scan.
 // ------------------------------------------------------------------------------------------------------
 constexpr int kFastWarps = 4;                 // warps per CTA = cells per tile (one warp per cell)
 constexpr int kFastThreads = kFastWarps * 32;
